@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Headline benchmark: fused approxNDCG forward+backward, slates/s (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (loss + d loss/d y_pred) over one batch of 4096 synthetic
+MSLR-shaped slates of 128 docs (labels U{0..4}, valid length U{64..128}, -1 padding, scores
+N(0,1), alpha = 10), per GPU.  Slates are independent, so N GPUs each take their own batch
+(weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
+
+  value        slates/s, inputs resident in HBM, CUDA events around K back-to-back launches of the
+               C-ABI entry `ltr_approx_ndcg_fwdbwd`, max over ranks.
+  e2e          same metric through the host-buffer C-ABI call (`ltr_approx_ndcg_fwdbwd_host`):
+               pinned host y_pred/y_true -> H2D -> kernel -> D2H of loss and gradient, all inside
+               the timed region.
+  roofline     SFU (MUFU) roofline of the pairwise kernel: algorithmic 2 SFU ops per ordered valid
+               pair / measured kernel time, against the SFU peak measured on this GPU by
+               a pure ex2.approx loop in the same run; `roofline_hbm` gives the HBM view.
+  cpu_baseline the oracle port of the reference's CPU algorithm (oracle/ltr_oracle.py, torch CPU,
+               all host threads) on a bounded sample of the same workload.
+
+`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to
+the GPU box; the port is pinned to it by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.join(ROOT, "nn-with-pytorch-personalized-losses_b200")
+for _p in (ROOT, PKG_ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "approxNDCG fwd+bwd slates/sec (n=128)"
+UNIT = "slates/s"
+B_PER_GPU = 4096
+N_DOCS = 128
+ALPHA = 10.0
+SEED = 2020
+RING = 48          # distinct batches cycled through: 48 x (2+2+2 MB) = 288 MB > 126 MB L2
+
+
+def make_batch(seed: int, B: int = B_PER_GPU, n: int = N_DOCS):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    lens = torch.randint(n // 2, n + 1, (B,), generator=g)
+    y[torch.arange(n)[None, :] >= lens[:, None]] = -1.0
+    s = torch.randn(B, n, generator=g)
+    return s, y, lens
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks: NVML polling thread (the timed region is milliseconds long; nvidia-smi -lms is too slow)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+        0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting",
+        0x10: "sync_boost",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            self._nv = pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-safe: match by PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self._h = h
+                        break
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self._h is not None:
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._h is not None and self._t.is_alive():
+            self._t.join()
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        reasons = [name for bit, name in self.REASONS.items() if self.reason_bits & bit]
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_step(s, y):
+    from oracle import ltr_oracle as O
+    sc = s.clone().requires_grad_(True)
+    loss = O.approx_ndcg_loss(sc, y, alpha=ALPHA)
+    loss.backward()
+    return float(loss)
+
+
+def cpu_throughput(sample_slates: int, reps: int, seed: int = SEED):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    s, y, _ = make_batch(seed, B=sample_slates)
+    cpu_step(s[:8], y[:8])
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(s, y)
+        best = min(best, time.perf_counter() - t0)
+    return sample_slates / best, cores
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # size the per-step sample so that (steps + warmup) steps end within ~2 minutes
+    probe_rate, _ = cpu_throughput(256, 1)
+    budget_s = 120.0
+    sample = int(max(16, min(B_PER_GPU, budget_s * probe_rate / max(1, args.steps + args.warmup))))
+    s, y, _ = make_batch(SEED, B=sample)
+    for _ in range(args.warmup):
+        cpu_step(s, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(s, y)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"approxNDCG alpha=10 fwd+bwd, {sample} slates x {N_DOCS} docs per step "
+                               f"(bounded sample of the 4096 x 128 batch), labels U{{0..4}}, len U{{64..128}}, scores N(0,1)",
+                   "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} slates x {N_DOCS} docs per step, {args.steps} steps, torch CPU fp32, "
+                                   f"{cores} threads (oracle/ltr_oracle.py port of losses/approxNDCG.py)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, local_rank, world):
+    import ctypes
+
+    import torch.distributed as dist
+    from ltr_b200 import _lib, _runtime as rt
+    from ltr_b200.host import ApproxNDCGHost
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, n = B_PER_GPU, N_DOCS
+
+    # ---- synthetic inputs: RING distinct batches per rank, generated on the host, resident in HBM ----
+    host_batches = [make_batch(SEED + 1000 * rank + i) for i in range(RING)]
+    pairs_per_batch = [int((l * (l - 1)).sum()) for _, _, l in host_batches]
+    d_s = [s.to(dev) for s, _, _ in host_batches]
+    d_y = [y.to(dev) for _, y, _ in host_batches]
+    d_grad = [torch.empty(B, n, device=dev) for _ in range(RING)]
+    d_slate = torch.empty(B, device=dev)
+    d_loss = torch.empty(1, device=dev)
+    tab = rt.disc_prefix(dev)
+    ws = rt.workspace(dev)
+    stream = rt.stream_ptr()
+
+    def launch(i):
+        k = i % RING
+        rc = lib.ltr_approx_ndcg_fwdbwd(d_s[k].data_ptr(), d_y[k].data_ptr(), B, n, ALPHA, 1e-10, -1.0,
+                                        tab.data_ptr(), tab.numel(), d_slate.data_ptr(), d_loss.data_ptr(),
+                                        d_grad[k].data_ptr(), ws.data_ptr(), stream)
+        if rc:
+            _lib.check(rc, "ltr_approx_ndcg_fwdbwd")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    # ---- device-resident throughput (`value`) --------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    for i in range(args.warmup):
+        launch(i)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        launch(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    loss_value = float(d_loss.cpu())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the host C-ABI, copies inside the timed region ---------------------
+    plan = ApproxNDCGHost(B, n, alpha=ALPHA, device=dev, depth=3)
+    h_s = [s.pin_memory() for s, _, _ in host_batches[:8]]
+    h_y = [y.pin_memory() for _, y, _ in host_batches[:8]]
+    e2e_steps = max(1, min(args.steps, 2000))
+    for i in range(min(args.warmup, 20) + 3):
+        plan.submit(h_s[i % 8], h_y[i % 8])
+    plan.wait_all()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        plan.submit(h_s[i % 8], h_y[i % 8])
+    plan.wait_all()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop()
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    h2d = 2 * B * n * 4
+    d2h = B * n * 4 + 4
+
+    if rank != 0:
+        return
+
+    # ---- roofline denominators measured here: SFU (ex2 loop), FP32 (FFMA loop) ------------------------
+    probe_out = torch.zeros(1, device=dev)
+    ops = ctypes.c_longlong(0)
+
+    def probe(fn, iters):
+        fn(probe_out.data_ptr(), iters, ctypes.byref(ops), stream)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(probe_out.data_ptr(), iters, ctypes.byref(ops), stream)
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return ops.value / (best * 1e-3)
+
+    sfu_peak = probe(lib.ltr_probe_sfu, 4096)
+    fma_peak = probe(lib.ltr_probe_fma, 4096)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    # kernel time per launch = ms / steps (one launch per step, nothing else on the stream)
+    t_launch = ms * 1e-3 / args.steps
+    used = [(args.warmup + i) % RING for i in range(args.steps)]
+    mean_pairs = sum(pairs_per_batch[k] for k in used) / len(used)
+    sfu_ops = 2.0 * mean_pairs                       # 2 SFU ops per ordered valid pair
+    achieved = sfu_ops / t_launch
+    alg_bytes = 12.0 * n * B                          # read s, y; write grad
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("approx_ndcg_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu_rate, cores = cpu_throughput(1024, 3) if world == 1 else (None, None)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"approxNDCG alpha=10 fused fwd+bwd, {B} slates x {n} docs per GPU per step "
+                        "(BASELINE configs[1]), labels U{0..4}, valid len U{64..128} (-1 padding), scores N(0,1)",
+            "global_batch": world * B, "slate_len": n, "parallelism": f"query-sharded x{world}, no data-path collective",
+            "l2_policy": f"inputs larger than L2: ring of {RING} distinct batches ({RING * 3 * B * n * 4 // 2**20} MB of s/y/grad) cycled",
+            "loss_check": loss_value,
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "path": "ltr_approx_ndcg_fwdbwd_host (pinned host buffers, 3 streams in flight)"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "sfu", "achieved": achieved / 1e12, "peak": sfu_peak / 1e12, "unit": "TSFU-op/s",
+            "frac": achieved / sfu_peak, "traffic": traffic,
+            "kernel": "approx_ndcg_kernel<128>", "kernel_us": t_launch * 1e6,
+            "algorithmic": f"2 SFU ops per ordered valid pair, {mean_pairs:.0f} pairs per launch (SURVEY 8d)",
+            "peak_source": "measured in this run: pure ex2.approx loop (ltr_probe_sfu)",
+            "peak_nominal": 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
+            "fp32_peak_measured_tflane_ops": fma_peak / 1e12,
+        },
+        "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / t_launch / 1e9 / hbm_peak, "peak_source": hbm_src,
+                         "note": "pairwise kernel is SFU/issue bound; HBM view shown for completeness"},
+    }
+    if cpu_rate is not None:
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "1024 slates x 128 docs fwd+bwd, best of 3, torch CPU fp32 "
+                                          "(oracle/ltr_oracle.py port of losses/approxNDCG.py)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29541"),
+               os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup)]
+        raise SystemExit(subprocess.call(cmd))
+
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200_arm(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,392 @@
+// K1: fused forward+backward approxNDCG (replaces losses/approxNDCG.py:7-53 of the reference).
+//
+// One CTA works on one slate at a time (persistent CTAs pull slates from an atomic counter).
+// Valid (non-padded) docs are compacted to the front of shared memory -- the loss is
+// permutation invariant, so no score sort is needed.  The O(m^2) pairwise
+// sigmoid sigma_ij = 1 / (1 + 2^(t_i - t_j)), t = alpha*log2(e)*s, is evaluated in registers:
+//   * factorised form  sigma_ij = rcp(1 + u_i * v_j),  u_i = 2^(t_i - c), v_j = 2^-(t_j - c)
+//     -> one FFMA + one MUFU.RCP per ordered pair (used when the slate's score range keeps
+//        u, v inside fp32 range; otherwise the direct ex2 form is used);
+//   * pass 1 accumulates soft ranks pos_i, pass 2 the analytic gradient
+//        d loss/d s_k = alpha * sum_j w_kj (c_j - c_k),  w = sigma(1-sigma),
+//        c_i = G_i / (B ln2 (1+pos_i) log2(1+pos_i)^2)          (SURVEY A.1).
+// The B x n x n tensors of the reference never exist.
+#include "ltr_common.cuh"
+#include "ltr_host.h"
+
+namespace ltr {
+
+struct ApproxParams {
+    const float* s;
+    const float* y;
+    int B, n, npad;
+    float alpha, eps, pad, inv_B;
+    const double* disc_prefix;
+    int disc_len;
+    float* slate_out;
+    float* loss_out;
+    float* grad;
+    unsigned* ws;   // [0] next-slate counter, [1] finished-CTA counter (both left at 0)
+    int clamp;      // 1: apply the eps clamp per pair exactly (large eps), 0: it is below fp32 resolution
+};
+
+// sigma for one (row, column) in either formulation
+template <bool FACT>
+__device__ __forceinline__ float pair_sigma(float row, float col) {
+    if (FACT) return rcp_approx(fmaf(row, col, 1.0f));   // row = u_i, col = v_j
+    return rcp_approx(1.0f + ex2_approx(row - col));      // row = t_i, col = t_j
+}
+
+template <int THREADS, bool FACT, bool CLAMP>
+__device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m, const float* sh_row,
+                                            const float* sh_col, float* sh_c, const float* sh_g,
+                                            const int* sh_idx, float* red) {
+    const int tid = threadIdx.x;
+    const int m4 = (m + 3) & ~3;
+    const float eps = p.eps;
+    // ---------------- pass 1: soft ranks, per-doc dloss/dpos, slate value -----------------
+    float ndcg_part = 0.f;
+    for (int i = tid; i < m; i += THREADS) {
+        const float r = sh_row[i];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < m4; j += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(sh_col + j);
+            float s0 = pair_sigma<FACT>(r, c4.x), s1 = pair_sigma<FACT>(r, c4.y);
+            float s2 = pair_sigma<FACT>(r, c4.z), s3 = pair_sigma<FACT>(r, c4.w);
+            if (CLAMP) {
+                s0 = fmaxf(s0, eps); s1 = fmaxf(s1, eps); s2 = fmaxf(s2, eps); s3 = fmaxf(s3, eps);
+            }
+            a0 += s0; a1 += s1; a2 += s2; a3 += s3;
+        }
+        float self = pair_sigma<FACT>(r, sh_col[i]);
+        if (CLAMP) self = fmaxf(self, eps);
+        float acc = (a0 + a1) + (a2 + a3) - self;
+        if (CLAMP) acc -= (float)(m4 - m) * eps;            // padded columns were clamped up to eps
+        const float pos = 1.0f + acc;
+        const float l2 = log2f(1.0f + pos);
+        const float g = sh_g[i];
+        ndcg_part += g / l2;
+        sh_c[i] = p.inv_B * g / (kLn2 * (1.0f + pos) * l2 * l2);
+    }
+    const float ndcg = block_sum<THREADS>(ndcg_part, red);   // also orders sh_c writes before pass 2
+    if (tid == 0) p.slate_out[b] = ndcg;
+    if (p.grad == nullptr) return;
+    __syncthreads();
+    // ---------------- pass 2: analytic gradient ---------------------------------------------
+    for (int i = tid; i < m; i += THREADS) {
+        const float r = sh_row[i];
+        float A0 = 0.f, A1 = 0.f, W0 = 0.f, W1 = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < m4; j += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(sh_col + j);
+            const float4 k4 = *reinterpret_cast<const float4*>(sh_c + j);
+            const float s0 = pair_sigma<FACT>(r, c4.x), s1 = pair_sigma<FACT>(r, c4.y);
+            const float s2 = pair_sigma<FACT>(r, c4.z), s3 = pair_sigma<FACT>(r, c4.w);
+            float w0 = fmaf(-s0, s0, s0), w1 = fmaf(-s1, s1, s1), w2 = fmaf(-s2, s2, s2), w3 = fmaf(-s3, s3, s3);
+            if (CLAMP) {
+                // row term: d pos_i / d s_i passes only where sigma_ij >= eps;
+                // column term: d pos_j / d s_i passes only where sigma_ji = 1 - sigma_ij >= eps
+                A0 = fmaf((1.0f - s0 >= eps) ? w0 : 0.f, k4.x, A0);
+                A1 = fmaf((1.0f - s1 >= eps) ? w1 : 0.f, k4.y, A1);
+                A0 = fmaf((1.0f - s2 >= eps) ? w2 : 0.f, k4.z, A0);
+                A1 = fmaf((1.0f - s3 >= eps) ? w3 : 0.f, k4.w, A1);
+                W0 += (s0 >= eps) ? w0 : 0.f;
+                W1 += (s1 >= eps) ? w1 : 0.f;
+                W0 += (s2 >= eps) ? w2 : 0.f;
+                W1 += (s3 >= eps) ? w3 : 0.f;
+            } else {
+                A0 = fmaf(w0, k4.x, A0); A1 = fmaf(w1, k4.y, A1);
+                A0 = fmaf(w2, k4.z, A0); A1 = fmaf(w3, k4.w, A1);
+                W0 += w0; W1 += w1; W0 += w2; W1 += w3;
+            }
+        }
+        // the j == i term is w_ii (c_i - c_i) = 0 and needs no special case (without the clamp asymmetry)
+        const float ci = sh_c[i];
+        float gsum = (A0 + A1) - ci * (W0 + W1);
+        // (with the clamp, the self pair sigma_ii = 0.5 passes both masks and still cancels)
+        p.grad[(size_t)b * p.n + sh_idx[i]] = p.alpha * gsum;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int W = THREADS / 32;
+    const int npad = p.npad;
+    float* sh_a = smem;              // scaled scores t (direct form) or u (factorised form)
+    float* sh_v = sh_a + npad;       // v (factorised form) / sort scratch
+    float* sh_c = sh_v + npad;       // dloss/dpos per doc       / sort scratch (cont.)
+    float* sh_g = sh_c + npad;       // labels, then normalised gains G
+    int* sh_idx = reinterpret_cast<int*>(sh_g + npad);   // original position of compacted doc
+    __shared__ float red[4 * 32];
+    __shared__ int sh_wcnt[32];
+    __shared__ int sh_lvl[16];
+    __shared__ int sh_next;
+    __shared__ float sh_maxdcg;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n;
+    const float scale = p.alpha * kLog2e;
+    const float inf = __int_as_float(0x7f800000);
+
+    for (;;) {
+        if (tid == 0) sh_next = (int)atomicAdd(&p.ws[0], 1u);
+        if (tid < 16) sh_lvl[tid] = 0;
+        __syncthreads();
+        const int b = sh_next;
+        if (b >= p.B) break;
+        const float* srow = p.s + (size_t)b * n;
+        const float* yrow = p.y + (size_t)b * n;
+
+        // ---- load, compact valid docs to the front, gather per-slate statistics --------------
+        int m = 0;
+        float tmin = inf, tmax = -inf, lmax = 0.f;
+        int all_int = 1;
+        for (int base = 0; base < n; base += THREADS) {
+            const int i = base + tid;
+            float sv = 0.f, yv = p.pad;
+            if (i < n) {
+                sv = ld_stream(srow + i);
+                yv = ld_stream(yrow + i);
+            }
+            const bool valid = (i < n) && (yv != p.pad);
+            const unsigned bal = __ballot_sync(LTR_FULL_MASK, valid);
+            if (lane == 0) sh_wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = m, tot = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int c = sh_wcnt[w];
+                off += (w < warp) ? c : 0;
+                tot += c;
+            }
+            if (valid) {
+                const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                const float t = sv * scale;
+                const float yc = fmaxf(yv, 0.f);            // approxNDCG.py:37-38 clamp
+                sh_a[pos] = t;
+                sh_g[pos] = yc;
+                sh_idx[pos] = i;
+                tmin = fminf(tmin, t);
+                tmax = fmaxf(tmax, t);
+                lmax = fmaxf(lmax, yc);
+                all_int &= (yc == floorf(yc)) ? 1 : 0;
+            } else if (i < n && p.grad != nullptr) {
+                p.grad[(size_t)b * n + i] = 0.f;            // padded docs get exactly 0
+            }
+            m += tot;
+            __syncthreads();
+        }
+        if (m == 0) {                                        // fully padded slate: value 0, no gradient
+            if (tid == 0) p.slate_out[b] = 0.f;
+            continue;
+        }
+        // block reduce (min, max, label max, all-int flag)
+        tmin = warp_min(tmin);
+        tmax = warp_max(tmax);
+        lmax = warp_max(lmax);
+        all_int = __all_sync(LTR_FULL_MASK, all_int);
+        if (lane == 0) {
+            red[warp] = tmin;
+            red[32 + warp] = tmax;
+            red[64 + warp] = lmax;
+            red[96 + warp] = (float)all_int;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            tmin = fminf(tmin, red[w]);
+            tmax = fmaxf(tmax, red[32 + w]);
+            lmax = fmaxf(lmax, red[64 + w]);
+            all_int &= (int)red[96 + w];
+        }
+        const int m4 = (m + 3) & ~3;
+
+        // ---- ideal DCG over ALL positions (approxNDCG.py:41-43) --------------------------------
+        const bool hist_ok = all_int && lmax <= 15.f && p.disc_prefix != nullptr && m < p.disc_len;
+        if (hist_ok) {
+            // integer labels: count docs per level, each level occupies a contiguous rank range
+            const int lmaxi = (int)lmax;
+            for (int base = 0; base < m; base += THREADS) {
+                const int i = base + tid;
+                const int yi = (i < m) ? (int)sh_g[i] : -1;
+                for (int L = 1; L <= lmaxi; ++L) {
+                    const int c = __popc(__ballot_sync(LTR_FULL_MASK, yi == L));
+                    if (lane == 0 && c) atomicAdd(&sh_lvl[L], c);
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double contrib = 0.0;
+                if (lane >= 1 && lane <= lmaxi) {
+                    int start = 0;
+                    for (int L = lane + 1; L <= lmaxi; ++L) start += sh_lvl[L];
+                    const int cnt = sh_lvl[lane];
+                    contrib = (double)((float)(1u << lane) - 1.0f) * (p.disc_prefix[start + cnt] - p.disc_prefix[start]);
+                }
+                contrib = warp_sum(contrib);
+                if (lane == 0) sh_maxdcg = fmaxf((float)contrib, p.eps);
+            }
+        } else {
+            // general labels: bitonic sort (descending) in scratch aliased over sh_v/sh_c
+            float* sortbuf = sh_v;
+            const int len = next_pow2(m);
+            for (int i = tid; i < len; i += THREADS) sortbuf[i] = (i < m) ? sh_g[i] : 0.f;
+            block_bitonic_desc(sortbuf, len);
+            float part = 0.f;
+            for (int i = tid; i < m; i += THREADS) part += gain_exp2(sortbuf[i]) / log2f(2.0f + (float)i);
+            const float tot = block_sum<THREADS>(part, red);
+            if (tid == 0) sh_maxdcg = fmaxf(tot, p.eps);
+        }
+        __syncthreads();
+        const float maxdcg = sh_maxdcg;
+
+        // ---- per-doc quantities -----------------------------------------------------------------
+        const float range = tmax - tmin;
+        const bool fact = (range < 250.0f);                  // false for inf/NaN ranges too
+        const float center = 0.5f * (tmax + tmin);
+        for (int i = tid; i < m4 + 4 && i < npad; i += THREADS) {
+            if (i < m) {
+                sh_g[i] = gain_exp2(sh_g[i]) / maxdcg;       // G_i (approxNDCG.py:44)
+                if (fact) {
+                    const float tc = sh_a[i] - center;
+                    sh_a[i] = ex2_approx(tc);
+                    sh_v[i] = ex2_approx(-tc);
+                }
+            } else {
+                // padding columns: sigma = 0 exactly (u*inf = inf, or 2^(t - -inf) = inf)
+                sh_a[i] = fact ? 1.0f : -inf;
+                sh_v[i] = inf;
+                sh_c[i] = 0.f;
+                sh_g[i] = 0.f;
+            }
+        }
+        __syncthreads();
+
+        if (fact) {
+            if (p.clamp) pair_passes<THREADS, true, true>(p, b, m, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
+            else         pair_passes<THREADS, true, false>(p, b, m, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
+        } else {
+            if (p.clamp) pair_passes<THREADS, false, true>(p, b, m, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
+            else         pair_passes<THREADS, false, false>(p, b, m, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
+        }
+        __syncthreads();
+    }
+
+    // ---- last CTA to finish reduces the per-slate values in a fixed order ------------------------
+    __shared__ double dred[32];
+    __syncthreads();   // every thread has read its last sh_next before it is reused as the "last CTA" flag
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&p.ws[1], 1u);
+        sh_next = (done == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_next) {
+        __threadfence();
+        double acc = 0.0;
+        for (int i = tid; i < p.B; i += THREADS) acc += (double)__ldcg(p.slate_out + i);
+        acc = warp_sum(acc);
+        if (lane == 0) dred[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < W; ++w) t += dred[w];
+            p.loss_out[0] = (float)(-t / (double)p.B);       // approxNDCG.py:53
+            p.ws[0] = 0u;
+            p.ws[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+template <int THREADS>
+static int launch_approx(const ApproxParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)p.npad * 5 * sizeof(float);
+    static size_t attr_smem = 0;
+    static int occ_cached = 0;
+    static size_t occ_smem = (size_t)-1;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_smem = smem;
+    }
+    if (occ_smem != smem) {
+        LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_kernel<THREADS>, THREADS,
+                                                               smem));
+        occ_smem = smem;
+    }
+    int grid = device_sm_count() * (occ_cached > 0 ? occ_cached : 1);
+    if (grid > p.B) grid = p.B;
+    approx_ndcg_kernel<THREADS><<<grid, THREADS, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ltr
+
+LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float alpha, float eps,
+                                   float pad_value, const double* disc_prefix, int disc_len, float* slate_ndcg,
+                                   float* loss, float* grad, void* workspace, void* stream) {
+    using namespace ltr;
+    if (!y_pred || !y_true || !slate_ndcg || !loss || !workspace || B <= 0 || n <= 0)
+        return set_error(LTR_EINVAL, "ltr_approx_ndcg_fwdbwd: null pointer or non-positive B/n");
+    if (n > ltr_max_slate_len()) return set_error(LTR_ETOOBIG, "ltr_approx_ndcg_fwdbwd: slate too long");
+    ApproxParams p;
+    p.s = y_pred;
+    p.y = y_true;
+    p.B = B;
+    p.n = n;
+    p.npad = ((n + 3) & ~3) + 4;
+    p.alpha = alpha;
+    p.eps = eps;
+    p.pad = pad_value;
+    p.inv_B = 1.0f / (float)B;
+    p.disc_prefix = disc_prefix;
+    p.disc_len = disc_prefix ? disc_len : 0;
+    p.slate_out = slate_ndcg;
+    p.loss_out = loss;
+    p.grad = grad;
+    p.ws = reinterpret_cast<unsigned*>(workspace);
+    // the per-pair eps clamp moves pos_i (>= 1) by at most n*eps: below fp32 resolution for the default 1e-10
+    p.clamp = ((double)n * (double)eps > 2e-7) ? 1 : 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = (n <= 512) ? launch_approx<128>(p, st) : launch_approx<256>(p, st);
+    return rc ? set_cuda_error(rc, "ltr_approx_ndcg_fwdbwd") : 0;
+}
+
+// ---- host-buffer entry: H2D copies, the fused kernel, D2H copies, all on `stream` ---------------
+LTR_API size_t ltr_approx_ndcg_host_scratch_bytes(int B, int n) {
+    const size_t bn = (((size_t)B * n + 3) & ~(size_t)3);
+    const size_t b4 = (((size_t)B + 3) & ~(size_t)3);
+    return (3 * bn + b4 + 4) * sizeof(float);
+}
+
+LTR_API int ltr_approx_ndcg_fwdbwd_host(const float* h_y_pred, const float* h_y_true, int B, int n, float alpha,
+                                        float eps, float pad_value, const double* disc_prefix, int disc_len,
+                                        float* h_loss, float* h_grad, float* h_slate_ndcg, void* d_scratch,
+                                        size_t scratch_bytes, void* workspace, void* stream) {
+    using namespace ltr;
+    if (!h_y_pred || !h_y_true || !h_loss || !d_scratch || B <= 0 || n <= 0)
+        return set_error(LTR_EINVAL, "ltr_approx_ndcg_fwdbwd_host: null pointer or non-positive B/n");
+    if (scratch_bytes < ltr_approx_ndcg_host_scratch_bytes(B, n))
+        return set_error(LTR_EINVAL, "ltr_approx_ndcg_fwdbwd_host: scratch too small");
+    const size_t bn = (((size_t)B * n + 3) & ~(size_t)3);
+    const size_t b4 = (((size_t)B + 3) & ~(size_t)3);
+    float* d_pred = reinterpret_cast<float*>(d_scratch);
+    float* d_true = d_pred + bn;
+    float* d_grad = d_true + bn;
+    float* d_slate = d_grad + bn;
+    float* d_loss = d_slate + b4;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)B * n * sizeof(float);
+    LTR_CUDA(cudaMemcpyAsync(d_pred, h_y_pred, bytes, cudaMemcpyHostToDevice, st));
+    LTR_CUDA(cudaMemcpyAsync(d_true, h_y_true, bytes, cudaMemcpyHostToDevice, st));
+    int rc = ltr_approx_ndcg_fwdbwd(d_pred, d_true, B, n, alpha, eps, pad_value, disc_prefix, disc_len, d_slate, d_loss,
+                                    h_grad ? d_grad : nullptr, workspace, stream);
+    if (rc) return rc;
+    LTR_CUDA(cudaMemcpyAsync(h_loss, d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_grad) LTR_CUDA(cudaMemcpyAsync(h_grad, d_grad, bytes, cudaMemcpyDeviceToHost, st));
+    if (h_slate_ndcg) LTR_CUDA(cudaMemcpyAsync(h_slate_ndcg, d_slate, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+}

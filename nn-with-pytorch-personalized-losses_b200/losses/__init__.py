@@ -1,0 +1,4 @@
+"""Top-level drop-in: put this directory on sys.path in place of the reference checkout and the
+reference drivers' imports (`from losses import *`, `from losses.lambdaL import lambdaLoss`, ...)
+resolve to the B200 implementations."""
+from ltr_b200.losses import approxNDCG  # noqa: F401

@@ -1,0 +1,63 @@
+"""ctypes binding of the C-ABI in include/ltr_b200.h.
+
+There is NO fallback: if the CUDA library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libltr_b200.so")
+
+WORKSPACE_BYTES = 4096
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: (restype, [argtypes])
+    "ltr_version": (c_char_p, []),
+    "ltr_last_error": (c_char_p, []),
+    "ltr_max_slate_len": (c_int, []),
+    "ltr_fill_disc_prefix": (c_int, [_P, c_int, _P]),
+    "ltr_approx_ndcg_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P]),
+    "ltr_approx_ndcg_host_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "ltr_approx_ndcg_fwdbwd_host": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P,
+                                            c_size_t, _P, _P]),
+    "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
+    "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
+}
+
+_lib = None
+
+
+class LtrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libltr_b200.so (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LtrError(
+            f"{LIB_PATH} not found: build it with `python -m ltr_b200.build` "
+            "(or __graft_entry__.build()). The B200 path has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES.keys())
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().ltr_last_error().decode(errors="replace")
+        raise LtrError(f"{what} failed with status {status}: {msg}")

@@ -1,0 +1,56 @@
+"""Device-side plumbing: per-(device, stream) workspaces, discount tables, tensor checks.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libltr_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DISC_LEN = 16384 + 1
+_workspaces = {}
+_disc_tables = {}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.LtrError("ltr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch (counters) owned by one (device, stream); kernels leave it zeroed."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.WORKSPACE_BYTES // 4, dtype=torch.int32, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def disc_prefix(device: torch.device) -> torch.Tensor:
+    """fp64 table P[r] = sum_{q<=r} 1/log2(1+q), built on the device by the library."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    tab = _disc_tables.get(key)
+    if tab is None:
+        tab = torch.empty(_DISC_LEN, dtype=torch.float64, device=device)
+        _lib.check(_lib.load().ltr_fill_disc_prefix(tab.data_ptr(), _DISC_LEN, stream_ptr()), "ltr_fill_disc_prefix")
+        _disc_tables[key] = tab
+    return tab
+
+
+def as_device_f32(t: torch.Tensor, device=None) -> torch.Tensor:
+    """fp32, contiguous, on the GPU.  CPU tensors (the reference's calling convention) are copied over."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if t.device.type != "cuda":
+        require_cuda()
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        t = t.to(dev, dtype=torch.float32, non_blocking=True)
+    elif t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

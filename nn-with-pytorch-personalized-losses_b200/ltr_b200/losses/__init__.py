@@ -1,0 +1,3 @@
+"""Drop-in mirror of the reference's `losses` package (losses/__init__.py:1-5 exposes exactly
+these five modules; listnet and ordinal are imported by path, as the reference drivers do)."""
+from . import approxNDCG  # noqa: F401

@@ -1,0 +1,47 @@
+"""Shared test helpers: seeded synthetic slates and the parity tolerances."""
+import numpy as np
+import torch
+
+LOSS_RTOL = 1e-5     # north_star: losses within 1e-5 relative
+GRAD_RTOL = 1e-4     # north_star: gradients within 1e-4 relative (fp32)
+GRAD_ATOL_FRAC = 1e-6  # + this fraction of max|g_ref| (elements that are ~0 by cancellation)
+
+
+def make_slates(B, n, seed=2020, min_len=None, ties=False, pad_anywhere=False, score_scale=1.0):
+    """labels U{0..4} fp32, scores N(0,1) (tie set: U{0..5}/3), valid length U{min_len..n}, -1 padding.
+    Generated on the CPU with a seeded generator so the oracle and the GPU see identical bits."""
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    s = (torch.randint(0, 6, (B, n), generator=g).float() / 3.0) if ties else torch.randn(B, n, generator=g)
+    s = s * score_scale
+    if min_len is not None:
+        lens = torch.randint(min_len, n + 1, (B,), generator=g)
+        if pad_anywhere:
+            for b in range(B):
+                drop = torch.randperm(n, generator=g)[: n - int(lens[b])]
+                y[b, drop] = -1.0
+        else:
+            y[torch.arange(n)[None, :] >= lens[:, None]] = -1.0
+    return s, y
+
+
+def assert_loss_close(got, ref, rtol=LOSS_RTOL, atol=1e-7):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = np.abs(got - ref)
+    tol = rtol * np.abs(ref) + atol
+    assert np.all(err <= tol), f"loss mismatch: got {got}, ref {ref}, rel {err / (np.abs(ref) + 1e-30)}"
+
+
+def assert_grad_close(got, ref, rtol=GRAD_RTOL, atol_frac=GRAD_ATOL_FRAC):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert np.all(np.isfinite(got)), "non-finite gradient"
+    scale = float(np.abs(ref).max())
+    err = np.abs(got - ref)
+    tol = rtol * np.abs(ref) + atol_frac * scale + 1e-30
+    bad = err > tol
+    assert not bad.any(), (f"{int(bad.sum())} of {bad.size} gradient elements out of tolerance; "
+                           f"worst err/scale {float((err / (scale + 1e-30)).max()):.3e}")

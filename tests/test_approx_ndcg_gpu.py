@@ -1,0 +1,128 @@
+"""approxNDCG: CUDA path (through the C-ABI) vs golden vectors from the reference and vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from ltr_testing import assert_grad_close, assert_loss_close, make_slates
+
+pytestmark = pytest.mark.gpu
+G = golden()
+
+
+def _run_gpu(s, y, **kw):
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    sd = s.cuda().requires_grad_(True)
+    loss = approxNDCGLoss(sd, y.cuda(), **kw)
+    loss.backward()
+    return loss.detach().cpu().numpy(), sd.grad.cpu().numpy()
+
+
+def _run_oracle(s, y, **kw):
+    from oracle import ltr_oracle as O
+    sc = s.clone().requires_grad_(True)
+    loss = O.approx_ndcg_loss(sc, y, **kw)
+    loss.backward()
+    return loss.detach().numpy(), sc.grad.numpy()
+
+
+@pytest.mark.parametrize("name", G.names("approx/"))
+def test_golden(name):
+    ins = G.inputs(name)
+    loss, grad = _run_gpu(torch.from_numpy(ins["y_pred"]), torch.from_numpy(ins["y_true"]), **G.kwargs(name))
+    assert loss.shape == G.out(name).shape == ()
+    assert_loss_close(loss, G.out(name))
+    assert_grad_close(grad, G.grad(name, "y_pred"))
+
+
+@pytest.mark.parametrize("B,n,min_len,alpha,kw", [
+    (64, 128, 64, 10.0, {}),
+    (64, 128, 64, 1.0, {}),
+    (33, 100, 1, 10.0, dict(pad_anywhere=True)),
+    (16, 300, 150, 10.0, {}),
+    (6, 1024, 512, 10.0, {}),
+    (4, 1500, 700, 1.0, {}),
+    (32, 128, 64, 10.0, dict(ties=True)),
+    (32, 128, 64, 10.0, dict(score_scale=25.0)),     # range too wide for the factorised form
+    (8, 7, 1, 10.0, {}),
+])
+def test_vs_oracle(B, n, min_len, alpha, kw):
+    s, y = make_slates(B, n, seed=7 + n, min_len=min_len, **kw)
+    loss, grad = _run_gpu(s, y, alpha=alpha)
+    rloss, rgrad = _run_oracle(s, y, alpha=alpha)
+    assert_loss_close(loss, rloss)
+    assert_grad_close(grad, rgrad)
+    assert np.all(grad[(y == -1).numpy()] == 0.0), "padded docs must get exactly zero gradient"
+
+
+def test_fractional_labels_take_the_sort_path():
+    s, y = make_slates(16, 96, seed=3, min_len=40)
+    y = torch.where(y >= 0, y * 0.37, y)
+    loss, grad = _run_gpu(s, y, alpha=5.0)
+    rloss, rgrad = _run_oracle(s, y, alpha=5.0)
+    assert_loss_close(loss, rloss)
+    assert_grad_close(grad, rgrad)
+
+
+def test_large_eps_clamp_is_exact():
+    s, y = make_slates(16, 64, seed=5, min_len=30)
+    for eps in (1e-3, 1e-6):
+        loss, grad = _run_gpu(s, y, alpha=10.0, eps=eps)
+        rloss, rgrad = _run_oracle(s, y, alpha=10.0, eps=eps)
+        assert_loss_close(loss, rloss)
+        assert_grad_close(grad, rgrad)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (4096 x 128): permutation invariance, padding invariance, oracle on a sample."""
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    from ltr_b200 import ops
+    B, n = 4096, 128
+    s, y = make_slates(B, n, seed=2020, min_len=64)
+    sd, yd = s.cuda(), y.cuda()
+    base = approxNDCGLoss(sd, yd, alpha=10.0)
+    # determinism: bitwise-equal on repeat
+    assert torch.equal(base, approxNDCGLoss(sd, yd, alpha=10.0))
+    # permutation of docs inside every slate leaves the loss unchanged
+    perm = torch.argsort(torch.rand(B, n, device="cuda"), dim=1)
+    shuffled = approxNDCGLoss(sd.gather(1, perm), yd.gather(1, perm), alpha=10.0)
+    assert abs(float(shuffled) - float(base)) <= 2e-6 * abs(float(base))
+    # appending padded docs changes nothing
+    sp = torch.cat([sd, torch.randn(B, 32, device="cuda")], dim=1)
+    yp = torch.cat([yd, torch.full((B, 32), -1.0, device="cuda")], dim=1)
+    padded = approxNDCGLoss(sp, yp, alpha=10.0)
+    assert abs(float(padded) - float(base)) <= 1e-6 * abs(float(base))
+    # mean of slates == loss; a 256-slate sample agrees with the oracle
+    sub = slice(1000, 1256)
+    loss_sub, grad_sub = _run_gpu(s[sub], y[sub], alpha=10.0)
+    rloss, rgrad = _run_oracle(s[sub], y[sub], alpha=10.0)
+    assert_loss_close(loss_sub, rloss)
+    assert_grad_close(grad_sub, rgrad)
+
+
+def test_cpu_tensors_in_cpu_loss_out():
+    """Reference calling convention: CPU tensors in, CPU scalar out, .grad on the CPU leaf."""
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    s, y = make_slates(8, 40, seed=11, min_len=20)
+    y0 = y.clone()
+    sc = s.clone().requires_grad_(True)
+    loss = approxNDCGLoss(sc, y, alpha=10.0)
+    assert loss.device.type == "cpu" and loss.dim() == 0
+    loss.backward(retain_graph=True)
+    loss.backward()          # stash survives a retained graph (main_batch_execution.py:170)
+    rloss, rgrad = _run_oracle(s, y, alpha=10.0)
+    assert_loss_close(loss.detach().numpy(), rloss)
+    assert_grad_close(sc.grad.numpy() / 2.0, rgrad)
+    assert torch.equal(y, y0), "inputs must not be mutated"
+
+
+def test_forward_only_and_errors():
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    from ltr_b200._lib import LtrError
+    s, y = make_slates(4, 30, seed=13, min_len=10)
+    loss = approxNDCGLoss(s.cuda(), y.cuda(), alpha=10.0)
+    assert not loss.requires_grad
+    rloss, _ = _run_oracle(s, y, alpha=10.0)
+    assert_loss_close(loss.cpu().numpy(), rloss)
+    with pytest.raises(LtrError):
+        approxNDCGLoss(torch.zeros(1, 100000, device="cuda"), torch.zeros(1, 100000, device="cuda"))

@@ -1,0 +1,43 @@
+"""CPU-side checks of the boundary: the library builds, loads, and exports every symbol the
+header declares; the product path refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ltr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ltr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from ltr_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert declared, "header declares nothing?"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/ltr_b200.h but not exported"
+    assert sorted(_lib.exported_symbols()) == declared, "ctypes signatures out of sync with the header"
+    assert b"sm_100a" in lib.ltr_version()
+
+
+def test_library_contains_sm100a_sass_only():
+    import subprocess
+    from ltr_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from ltr_b200._lib import LtrError
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    with pytest.raises(LtrError):
+        approxNDCGLoss(torch.randn(2, 5, requires_grad=True), torch.ones(2, 5))
