@@ -98,6 +98,49 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     return t;
 }
 
+// ---- single-instruction warp reductions (REDUX) on order-preserving integer keys ---------------
+__device__ __forceinline__ int float_order_key(float f) {
+    const int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);          // monotone: a < b  <=>  key(a) < key(b)
+}
+__device__ __forceinline__ float float_from_key(int k) {
+    return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
+}
+__device__ __forceinline__ float warp_max_redux(float v) {
+    return float_from_key(__reduce_max_sync(LTR_FULL_MASK, float_order_key(v)));
+}
+__device__ __forceinline__ float warp_min_redux(float v) {
+    return float_from_key(__reduce_min_sync(LTR_FULL_MASK, float_order_key(v)));
+}
+
+// ---- mbarrier (shared::cta) producer/consumer primitives ----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// named barrier among `count` threads (count a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---- streaming global access -------------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
     float4 r;
