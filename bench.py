@@ -223,14 +223,36 @@ def run_b200_arm(args, rank, local_rank, world):
         return ms
 
     # ---- device-resident throughput (`value`) --------------------------------------------------------
+    # The kernel (~10 us) is shorter than a Python->ctypes->cudaLaunchKernel round trip, so the timed
+    # launches are replayed from a CUDA graph holding one pass over the ring (RING launches of the
+    # same C-ABI entry, captured on the launching stream); the remainder is launched directly.
     sampler = ClockSampler(local_rank)
     for i in range(args.warmup):
         launch(i)
     barrier()
+    graph, n_replays = None, 0
+    if args.steps >= RING and not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            stream = rt.stream_ptr()
+            ws = rt.workspace(dev)
+            launch(0)                                   # warm this stream's workspace outside the capture
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(RING):
+                    launch(args.warmup + i)
+        stream = rt.stream_ptr()
+        ws = rt.workspace(dev)
+        n_replays = args.steps // RING
+        graph.replay()                                  # one untimed replay (graph upload)
+    barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
+    for _ in range(n_replays):
+        graph.replay()
+    for i in range(n_replays * RING, args.steps):
         launch(args.warmup + i)
     ev1.record()
     barrier()
@@ -315,6 +337,8 @@ def run_b200_arm(args, rank, local_rank, world):
             "global_batch": world * B, "slate_len": n, "parallelism": f"query-sharded x{world}, no data-path collective",
             "l2_policy": f"inputs larger than L2: ring of {RING} distinct batches ({RING * 3 * B * n * 4 // 2**20} MB of s/y/grad) cycled",
             "loss_check": loss_value,
+            "launch_mode": (f"CUDA graph of {RING} launches replayed {n_replays}x + {args.steps - n_replays * RING} direct"
+                            if graph is not None else "direct launches"),
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "ltr_approx_ndcg_fwdbwd_host (pinned host buffers, 3 streams in flight)"},
@@ -346,6 +370,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

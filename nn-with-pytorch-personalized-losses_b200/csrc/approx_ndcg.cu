@@ -11,34 +11,21 @@
 //        d loss/d s_k = alpha * sum_j w_kj (c_j - c_k),  w = sigma(1-sigma),
 //        c_i = G_i / (B ln2 (1+pos_i) log2(1+pos_i)^2)          (SURVEY A.1).
 // The B x n x n tensors of the reference never exist.
+#include "approx_ndcg_sym.cuh"
 #include "ltr_common.cuh"
 #include "ltr_host.h"
 
 namespace ltr {
 
-struct ApproxParams {
-    const float* s;
-    const float* y;
-    int B, n, npad;
-    float alpha, eps, pad, inv_B;
-    const double* disc_prefix;
-    int disc_len;
-    float* slate_out;
-    float* loss_out;
-    float* grad;
-    unsigned* ws;   // [0] next-slate counter, [1] finished-CTA counter (both left at 0)
-    int clamp;      // 1: apply the eps clamp per pair exactly (large eps), 0: it is below fp32 resolution
-};
-
-// sigma for one (row, column) in either formulation
+// p = 2^(t_i - t_j) for one (row, column) in either formulation; sigma_ij = 1/(1+p), sigma_ji = p/(1+p)
 template <bool FACT>
-__device__ __forceinline__ float pair_sigma(float row, float col) {
-    if (FACT) return rcp_approx(fmaf(row, col, 1.0f));   // row = u_i, col = v_j
-    return rcp_approx(1.0f + ex2_approx(row - col));      // row = t_i, col = t_j
+__device__ __forceinline__ float pair_p(float row, float col, float scale) {
+    if (FACT) return row * col;                                       // row = u_i, col = v_j
+    return ex2_approx(fminf((row - col) * scale, 126.0f));            // row = s_i, col = s_j (raw scores)
 }
 
 template <int THREADS, bool FACT, bool CLAMP>
-__device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m, const float* sh_row,
+__device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m, float scale, const float* sh_row,
                                             const float* sh_col, float* sh_c, const float* sh_g,
                                             const int* sh_idx, float* red) {
     const int tid = threadIdx.x;
@@ -52,17 +39,19 @@ __device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m,
 #pragma unroll 4
         for (int j = 0; j < m4; j += 4) {
             const float4 c4 = *reinterpret_cast<const float4*>(sh_col + j);
-            float s0 = pair_sigma<FACT>(r, c4.x), s1 = pair_sigma<FACT>(r, c4.y);
-            float s2 = pair_sigma<FACT>(r, c4.z), s3 = pair_sigma<FACT>(r, c4.w);
+            float s0 = rcp_approx(1.0f + pair_p<FACT>(r, c4.x, scale)), s1 = rcp_approx(1.0f + pair_p<FACT>(r, c4.y, scale));
+            float s2 = rcp_approx(1.0f + pair_p<FACT>(r, c4.z, scale)), s3 = rcp_approx(1.0f + pair_p<FACT>(r, c4.w, scale));
             if (CLAMP) {
                 s0 = fmaxf(s0, eps); s1 = fmaxf(s1, eps); s2 = fmaxf(s2, eps); s3 = fmaxf(s3, eps);
             }
             a0 += s0; a1 += s1; a2 += s2; a3 += s3;
         }
-        float self = pair_sigma<FACT>(r, sh_col[i]);
+        float self = rcp_approx(1.0f + pair_p<FACT>(r, sh_col[i], scale));
         if (CLAMP) self = fmaxf(self, eps);
         float acc = (a0 + a1) + (a2 + a3) - self;
-        if (CLAMP) acc -= (float)(m4 - m) * eps;            // padded columns were clamped up to eps
+        // padding columns: the factorised form reads sigma = 1 there (v = 0), the direct form 0 (clamped up to eps)
+        if (FACT) acc -= (float)(m4 - m);
+        else if (CLAMP) acc -= (float)(m4 - m) * eps;
         const float pos = 1.0f + acc;
         const float l2 = log2f(1.0f + pos);
         const float g = sh_g[i];
@@ -81,16 +70,20 @@ __device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m,
         for (int j = 0; j < m4; j += 4) {
             const float4 c4 = *reinterpret_cast<const float4*>(sh_col + j);
             const float4 k4 = *reinterpret_cast<const float4*>(sh_c + j);
-            const float s0 = pair_sigma<FACT>(r, c4.x), s1 = pair_sigma<FACT>(r, c4.y);
-            const float s2 = pair_sigma<FACT>(r, c4.z), s3 = pair_sigma<FACT>(r, c4.w);
-            float w0 = fmaf(-s0, s0, s0), w1 = fmaf(-s1, s1, s1), w2 = fmaf(-s2, s2, s2), w3 = fmaf(-s3, s3, s3);
+            const float p0 = pair_p<FACT>(r, c4.x, scale), p1 = pair_p<FACT>(r, c4.y, scale);
+            const float p2 = pair_p<FACT>(r, c4.z, scale), p3 = pair_p<FACT>(r, c4.w, scale);
+            const float s0 = rcp_approx(1.0f + p0), s1 = rcp_approx(1.0f + p1);
+            const float s2 = rcp_approx(1.0f + p2), s3 = rcp_approx(1.0f + p3);
+            const float q0 = p0 * s0, q1 = p1 * s1, q2 = p2 * s2, q3 = p3 * s3;      // sigma_ji
+            // w = sigma_ij * sigma_ji: the sigmoid derivative without the 1 - sigma cancellation
+            const float w0 = s0 * q0, w1 = s1 * q1, w2 = s2 * q2, w3 = s3 * q3;
             if (CLAMP) {
                 // row term: d pos_i / d s_i passes only where sigma_ij >= eps;
-                // column term: d pos_j / d s_i passes only where sigma_ji = 1 - sigma_ij >= eps
-                A0 = fmaf((1.0f - s0 >= eps) ? w0 : 0.f, k4.x, A0);
-                A1 = fmaf((1.0f - s1 >= eps) ? w1 : 0.f, k4.y, A1);
-                A0 = fmaf((1.0f - s2 >= eps) ? w2 : 0.f, k4.z, A0);
-                A1 = fmaf((1.0f - s3 >= eps) ? w3 : 0.f, k4.w, A1);
+                // column term: d pos_j / d s_i passes only where sigma_ji >= eps
+                A0 = fmaf((q0 >= eps) ? w0 : 0.f, k4.x, A0);
+                A1 = fmaf((q1 >= eps) ? w1 : 0.f, k4.y, A1);
+                A0 = fmaf((q2 >= eps) ? w2 : 0.f, k4.z, A0);
+                A1 = fmaf((q3 >= eps) ? w3 : 0.f, k4.w, A1);
                 W0 += (s0 >= eps) ? w0 : 0.f;
                 W1 += (s1 >= eps) ? w1 : 0.f;
                 W0 += (s2 >= eps) ? w2 : 0.f;
@@ -163,7 +156,7 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
             }
             if (valid) {
                 const int pos = off + __popc(bal & ((1u << lane) - 1u));
-                const float t = sv * scale;
+                const float t = sv;                         // raw score; scaled per pair / per doc below
                 const float yc = fmaxf(yv, 0.f);            // approxNDCG.py:37-38 clamp
                 sh_a[pos] = t;
                 sh_g[pos] = yc;
@@ -243,21 +236,23 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
         const float maxdcg = sh_maxdcg;
 
         // ---- per-doc quantities -----------------------------------------------------------------
-        const float range = tmax - tmin;
-        const bool fact = (range < 250.0f);                  // false for inf/NaN ranges too
-        const float center = 0.5f * (tmax + tmin);
+        const float range = (tmax - tmin) * scale;
+        const bool fact = (fabsf(range) < 126.0f);           // false for inf/NaN ranges too; keeps u*v finite
+        const float center = 0.5f * tmax + 0.5f * tmin;
+        const float sentinel = (scale >= 0.f) ? -inf : inf;  // direct form: 2^(scale*(x - pad)) saturates at 2^126
         for (int i = tid; i < m4 + 4 && i < npad; i += THREADS) {
             if (i < m) {
                 sh_g[i] = gain_exp2(sh_g[i]) / maxdcg;       // G_i (approxNDCG.py:44)
                 if (fact) {
-                    const float tc = sh_a[i] - center;
+                    const float tc = (sh_a[i] - center) * scale;
                     sh_a[i] = ex2_approx(tc);
                     sh_v[i] = ex2_approx(-tc);
                 }
             } else {
-                // padding columns: sigma = 0 exactly (u*inf = inf, or 2^(t - -inf) = inf)
-                sh_a[i] = fact ? 1.0f : -inf;
-                sh_v[i] = inf;
+                // padding columns: factorised p = 0 (sigma = 1, w = 0; counted out in pair_passes),
+                // direct p = 2^126 (sigma ~ 0, w ~ 0)
+                sh_a[i] = fact ? 0.0f : sentinel;
+                sh_v[i] = 0.0f;
                 sh_c[i] = 0.f;
                 sh_g[i] = 0.f;
             }
@@ -265,11 +260,11 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
         __syncthreads();
 
         if (fact) {
-            if (p.clamp) pair_passes<THREADS, true, true>(p, b, m, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
-            else         pair_passes<THREADS, true, false>(p, b, m, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
+            if (p.clamp) pair_passes<THREADS, true, true>(p, b, m, scale, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
+            else         pair_passes<THREADS, true, false>(p, b, m, scale, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
         } else {
-            if (p.clamp) pair_passes<THREADS, false, true>(p, b, m, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
-            else         pair_passes<THREADS, false, false>(p, b, m, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
+            if (p.clamp) pair_passes<THREADS, false, true>(p, b, m, scale, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
+            else         pair_passes<THREADS, false, false>(p, b, m, scale, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
         }
         __syncthreads();
     }
@@ -323,6 +318,18 @@ static int launch_approx(const ApproxParams& p, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
+    static int occ_cached = 0;
+    if (occ_cached == 0) {
+        LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_sym_kernel, SYM_THREADS, 0));
+        if (occ_cached <= 0) occ_cached = 1;
+    }
+    int grid = device_sm_count() * occ_cached;
+    if (grid > p.B) grid = p.B;
+    approx_ndcg_sym_kernel<<<grid, SYM_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace ltr
 
 LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float alpha, float eps,
@@ -351,7 +358,10 @@ LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int
     // the per-pair eps clamp moves pos_i (>= 1) by at most n*eps: below fp32 resolution for the default 1e-10
     p.clamp = ((double)n * (double)eps > 2e-7) ? 1 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int rc = (n <= 512) ? launch_approx<128>(p, st) : launch_approx<256>(p, st);
+    int rc;
+    if (n <= SYM_N && !p.clamp && p.disc_prefix != nullptr && p.disc_len > SYM_N)
+        rc = launch_approx_sym(p, st);                                 // symmetric pair schedule, 4 warps per slate
+    else rc = (n <= 512) ? launch_approx<128>(p, st) : launch_approx<256>(p, st);
     return rc ? set_cuda_error(rc, "ltr_approx_ndcg_fwdbwd") : 0;
 }
 

@@ -1,0 +1,529 @@
+// K1 fast path: fused forward+backward approxNDCG for slates of at most 128 docs
+// (replaces losses/approxNDCG.py:7-53 of the reference; BASELINE configs[1]).
+//
+// One CTA of 4 warps (one per SM sub-partition) works on one slate at a time; persistent CTAs pull
+// slates from an atomic counter and prefetch the next slate's scores/labels into registers.
+// The pairwise work exploits  sigma_ji = 1 - sigma_ij  and evaluates every UNORDERED pair once per pass:
+//
+//   u_i = 2^(t_i - c), v_j = 2^-(t_j - c), t = alpha*log2(e)*s      (2 MUFU per doc)
+//   p = u_i * v_j = 2^(t_i - t_j);  r = rcp(1 + p) = sigma_ij;  p*r = sigma_ji      (1 MUFU per pair)
+//   w = sigma_ij * sigma_ji   (the sigmoid derivative, exact at both tails)
+//
+// Pair ownership is a block-circulant: lane a of every warp owns the R = max(2, ceil(m/32)) consecutive
+// docs of row block a; at step D it meets column block (a + D) mod T, T = ceil(m/R).  Steps
+// D = 1 .. T/2 cover every unordered block pair once, except that for even T the antipodal step
+// (D = T/2) meets every pair twice and is weighted 1/2; the R(R-1)/2 pairs inside a lane's own block
+// are an extra triangular step.  The T/2 steps are split between the 4 warps (the split rotates
+// with the slate index so that no sub-partition always gets the long share).  The column block's
+// values and accumulators travel from lane to lane with warp shuffles; row accumulators never
+// leave their lane.  Registers stay low (no per-pair state is kept), so 8+ CTAs are resident per
+// SM and the MUFU pipe -- one rcp per unordered pair per pass -- is the only saturated resource.
+//
+//   forward :  pos_i = 1 + sum_{j != i} sigma_ij,  slate value = sum_i G_i / log2(1 + pos_i)
+//   backward:  d loss / d s_k = alpha * sum_j w_kj (c_j - c_k),
+//              c_i = G_i / (B ln2 (1 + pos_i) log2(1 + pos_i)^2)            
+//
+// Slates whose scaled score range exceeds the fp32 exponent budget of the factorised form take
+// `direct_slate` (one doc per thread, p = ex2(min(alpha*log2e*(s_i - s_j), 126)) per ordered pair).
+#pragma once
+#include "ltr_common.cuh"
+
+namespace ltr {
+
+struct ApproxParams {
+    const float* s;
+    const float* y;
+    int B, n, npad;
+    float alpha, eps, pad, inv_B;
+    const double* disc_prefix;
+    int disc_len;
+    float* slate_out;
+    float* loss_out;
+    float* grad;
+    unsigned* ws;   // [0] next-slate counter, [1] finished-CTA counter, [2..3] 64-bit fixed-point loss sum,
+                    // [4] non-finite flag (all left at 0)
+    int clamp;      // 1: apply the eps clamp per pair exactly (large eps), 0: it is below fp32 resolution
+};
+
+constexpr int SYM_N = 128;        // longest slate of the fast path
+constexpr int SYM_THREADS = 128;  // 4 warps: one per SM sub-partition
+constexpr int SYM_MAX_LABEL = 4;  // integer labels 0..4 take the histogram ideal-DCG (others: sort)
+
+struct SymShared {
+    double P[SYM_N + 4];          // discount prefix sums P[r] = sum_{q<=r} 1/log2(1+q)
+    float u[SYM_N];               // 2^(t - c)   (direct form: raw score)
+    float v[SYM_N];               // 2^-(t - c)
+    float c[SYM_N];               // d loss / d pos_i
+    float part[4][2][SYM_N];      // per-warp row / column partial sums (ranks, then gradients)
+    float sortbuf[SYM_N];
+    int4 wstat[4];                // per warp: {valid count | bad-label flag << 16, min key, max key, packed label counts}
+    float red[4];
+    int next_b;
+};
+
+// Everything a thread keeps about its own doc across the phases of a slate.
+struct SymDoc {
+    bool valid;
+    int dst;        // compacted position of this thread's doc
+    float gain;     // normalised gain G_i
+};
+
+// Shared middle of a slate: soft rank -> slate value and d loss / d pos_i (sh.c), then fetch the next
+// slate index and prefetch its scores/labels.  `sum` = sum_{j != i} sigma_ij of this thread's doc.
+// Per-CTA running state that survives from slate to slate (meaningful in thread 0 only).
+struct SymCarry {
+    int claimed;          // slate index already claimed from the global counter for the NEXT iteration
+    long long fx;         // sum of this CTA's slate values in 2^-40 fixed point (order-independent, so the
+                          // batch loss is bitwise reproducible although slates are handed out dynamically)
+    int nonfinite;
+};
+constexpr float kFixScale = 1099511627776.0f;   // 2^40
+
+__device__ __forceinline__ void carry_add(SymCarry& cy, float v) {
+    if (fabsf(v) < 4.0e6f) cy.fx += __float2ll_rn(v * kFixScale);
+    else cy.nonfinite = 1;                       // NaN / inf / absurd: the batch loss becomes NaN
+}
+
+__device__ __forceinline__ void slate_middle(const ApproxParams& p, SymShared& sh, int b, const SymDoc& doc, float sum,
+                                             SymCarry& cy, float& next_s, float& next_y, int& next_b) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float ndcg_part = 0.f;
+    if (doc.valid) {
+        const float pos1 = 2.0f + sum;                       // 1 + pos_i
+        const float l2 = lg2_approx(pos1);
+        const float il2 = rcp_approx(l2);
+        ndcg_part = doc.gain * il2;
+        sh.c[doc.dst] = (p.inv_B * (1.0f / kLn2)) * doc.gain * il2 * il2 * rcp_approx(pos1);
+    }
+    ndcg_part = warp_sum(ndcg_part);
+    if (lane == 0) sh.red[warp] = ndcg_part;
+    if (tid == 0) {
+        sh.next_b = cy.claimed;                                   // claimed one slate ago: latency long hidden
+        cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));  // result is first read a whole slate later
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float val = (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
+        p.slate_out[b] = val;
+        carry_add(cy, val);
+    }
+    next_b = sh.next_b;
+    if (next_b < p.B && tid < p.n) {
+        next_s = ld_stream(p.s + (size_t)next_b * p.n + tid);
+        next_y = ld_stream(p.y + (size_t)next_b * p.n + tid);
+    }
+}
+
+// Slates whose scaled score range does not fit the factorised form (rare): one doc per thread,
+// p = ex2(min(alpha*log2e*(s_i - s_j), 126)) per ordered pair, recomputed in the gradient pass.
+// sh.u holds the raw scores of the m compacted docs.
+__device__ __noinline__ void direct_slate(const ApproxParams& p, SymShared& sh, int b, int m, float scale,
+                                          const SymDoc& doc, SymCarry& cy, float& next_s, float& next_y, int& next_b) {
+    const int tid = threadIdx.x;
+    const float si = doc.valid ? sh.u[doc.dst] : 0.f;
+    float sum = -0.5f;                                           // the j == i term below is exactly 1/2
+    if (doc.valid) {
+        for (int j = 0; j < m; ++j) {
+            const float pp = ex2_approx(fminf((si - sh.u[j]) * scale, 126.0f));
+            sum += rcp_approx(pp + 1.0f);
+        }
+    }
+    slate_middle(p, sh, b, doc, sum, cy, next_s, next_y, next_b);
+    if (p.grad != nullptr && tid < p.n) {
+        float acc = 0.f;
+        if (doc.valid) {
+            const float ci = sh.c[doc.dst];
+            for (int j = 0; j < m; ++j) {
+                const float pp = ex2_approx(fminf((si - sh.u[j]) * scale, 126.0f));
+                const float rr = rcp_approx(pp + 1.0f);
+                acc = fmaf(rr * (pp * rr), sh.c[j] - ci, acc);
+            }
+        }
+        p.grad[(size_t)b * p.n + tid] = p.alpha * acc;
+    }
+    __syncthreads();
+}
+
+// ---- pair tiles: R rows of this lane against the R docs of the visiting column block ---------------
+// Columns are processed two at a time with packed fp32x2 arithmetic (FFMA2/FADD2/FMUL2 halve the issue
+// slots of the FP32 work; the MUFU.RCP per pair stays scalar).  An odd last column is done in scalar.
+//
+// Rank pass: q = 1 + u_i v_j, r = rcp(q) = sigma_ij is added to BOTH the row and the column
+// accumulator; the column side is turned into sum sigma_ji = (#rows met) - sum sigma_ij afterwards,
+// so a pair costs 1 FFMA + 1 MUFU + 2 FADD.
+template <int R>
+__device__ __forceinline__ void rank_tile(const float (&urow)[R], const float (&vcol)[R], float h, float (&acc_r)[R],
+                                          float (&acc_r_hi)[R], float (&acc_c)[R]) {
+    const f32x2 one2 = pack2(1.0f, 1.0f);
+    const f32x2 h2 = pack2(h, h);                // step weight (1/2 on the antipodal step) rides on the FMA
+#pragma unroll
+    for (int c = 0; c + 1 < R; c += 2) {
+        const f32x2 v2 = pack2(vcol[c], vcol[c + 1]);
+        f32x2 ac2 = pack2(acc_c[c], acc_c[c + 1]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const f32x2 q2 = fma2(pack2(urow[r], urow[r]), v2, one2);
+            float q0, q1;
+            unpack2(q2, q0, q1);
+            const f32x2 r2 = pack2(rcp_approx(q0), rcp_approx(q1));
+            ac2 = fma2(r2, h2, ac2);
+            const f32x2 ar2 = fma2(r2, h2, pack2(acc_r[r], acc_r_hi[r]));
+            unpack2(ar2, acc_r[r], acc_r_hi[r]);
+        }
+        unpack2(ac2, acc_c[c], acc_c[c + 1]);
+    }
+    if (R & 1) {
+        constexpr int c = R - 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float rr = rcp_approx(fmaf(urow[r], vcol[c], 1.0f));
+            acc_r[r] = fmaf(rr, h, acc_r[r]);
+            acc_c[c] = fmaf(rr, h, acc_c[c]);
+        }
+    }
+}
+
+// Gradient pass: w = sigma_ij * sigma_ji = r * (p r) (exact at both tails), e = w (c_j - c_i) goes to
+// the row accumulator with + and to the column accumulator with -.
+template <int R>
+__device__ __forceinline__ void grad_tile(const float (&urow)[R], const float (&vcol)[R], const float (&crow)[R],
+                                          const float (&ccol)[R], float (&acc_r)[R], float (&acc_r_hi)[R],
+                                          float (&acc_c)[R]) {
+    const f32x2 one2 = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int c = 0; c + 1 < R; c += 2) {
+        const f32x2 v2 = pack2(vcol[c], vcol[c + 1]);
+        const f32x2 cc2 = pack2(ccol[c], ccol[c + 1]);
+        f32x2 ac2 = pack2(acc_c[c], acc_c[c + 1]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float cr = crow[r];
+            const f32x2 p2 = mul2(pack2(urow[r], urow[r]), v2);
+            const f32x2 q2 = add2(p2, one2);
+            float q0, q1;
+            unpack2(q2, q0, q1);
+            const f32x2 r2 = pack2(rcp_approx(q0), rcp_approx(q1));
+            const f32x2 w2 = mul2(r2, mul2(p2, r2));
+            const f32x2 e2 = mul2(w2, sub2(cc2, pack2(cr, cr)));
+            ac2 = sub2(ac2, e2);
+            const f32x2 ar2 = add2(pack2(acc_r[r], acc_r_hi[r]), e2);
+            unpack2(ar2, acc_r[r], acc_r_hi[r]);
+        }
+        unpack2(ac2, acc_c[c], acc_c[c + 1]);
+    }
+    if (R & 1) {
+        constexpr int c = R - 1;
+        const float cc = ccol[c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float cr = crow[r];
+            const float pp = urow[r] * vcol[c];
+            const float rr = rcp_approx(pp + 1.0f);
+            const float e = (rr * (pp * rr)) * (cc - cr);
+            acc_r[r] += e;
+            acc_c[c] -= e;
+        }
+    }
+}
+
+// One slate in the factorised form, R docs per lane.  Called by all 128 threads with CTA-uniform arguments.
+template <int R>
+__device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, int b, int m, const SymDoc& doc,
+                                          SymCarry& cy, float& next_s, float& next_y, int& next_b) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = (m + R - 1) / R;            // active lanes = row blocks
+    const int S = T >> 1;                     // circulant steps D = 1 .. T/2 (D = 0 is the in-block triangle)
+    const int role = (warp + b) & 3;
+    const int d_lo = 1 + ((role * S) >> 2);
+    const int d_hi = 1 + (((role + 1) * S) >> 2);
+    const bool active = lane < T;
+    const int src = active ? ((lane + 1 == T) ? 0 : lane + 1) : lane;
+    int cb = lane + d_lo;
+    if (cb >= T) cb -= T;
+    if (!active) cb = 0;
+    int cb_last = lane + d_hi - 1;
+    if (cb_last >= T) cb_last -= T;
+    if (d_hi == d_lo || !active) cb_last = lane;   // nothing accumulated: the column sums are zero
+
+    float urow[R], vcol[R], acc_r[R], acc_r_hi[R], acc_c[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        urow[r] = sh.u[lane * R + r];
+        vcol[r] = sh.v[cb * R + r];
+        acc_r[r] = 0.f;
+        acc_r_hi[r] = 0.f;
+        acc_c[r] = 0.f;
+    }
+
+    // ---------------- rank pass: one MUFU.RCP per unordered pair -----------------------------
+    if (R > 1 && role == 0) {                 // pairs inside the lane's own block
+        float vrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int c = r + 1; c < R; ++c) {
+                const float pp = urow[r] * vrow[c];
+                const float rr = rcp_approx(pp + 1.0f);
+                acc_r[r] += rr;
+                acc_r[c] = fmaf(pp, rr, acc_r[c]);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int D = d_lo; D < d_hi; ++D) {
+        rank_tile<R>(urow, vcol, (2 * D == T) ? 0.5f : 1.0f, acc_r, acc_r_hi, acc_c);   // antipodal: pairs met twice
+        if (D + 1 < d_hi) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            sh.part[warp][0][lane * R + r] = acc_r[r] + acc_r_hi[r];
+            sh.part[warp][1][cb_last * R + r] = acc_c[r];
+        }
+    }
+    __syncthreads();
+
+    // ---------------- per doc: soft rank, slate value, d loss / d pos --------------------------
+    float sum = 0.f;
+    if (doc.valid) {
+        float rows = 0.f, cols = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rows += sh.part[k][0][doc.dst], cols += sh.part[k][1][doc.dst];
+        // column side: sum sigma_ji = (#rows met, antipodal ones at 1/2) - sum sigma_ij = R (T-1)/2 - cols.
+        // padded tail of the last block (u = v = 0): as a column it reads sigma_ij = 1 on the row side.
+        const int npadc = T * R - m;
+        const int e = T - 1 - doc.dst / R;               // circulant distance to the last block
+        const float f = (2 * e == T) ? 0.5f : ((2 * e < T) ? 1.0f : 0.0f);
+        sum = (rows - f * (float)npadc) + (0.5f * (float)(R * (T - 1)) - cols);
+    }
+    slate_middle(p, sh, b, doc, sum, cy, next_s, next_y, next_b);
+    if (p.grad == nullptr) {
+        __syncthreads();
+        return;
+    }
+
+    // ---------------- gradient pass: sigma recomputed, one MUFU.RCP per unordered pair ---------
+    float crow[R], ccol[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        crow[r] = sh.c[lane * R + r];
+        ccol[r] = sh.c[cb * R + r];
+        vcol[r] = sh.v[cb * R + r];
+        acc_r[r] = 0.f;
+        acc_r_hi[r] = 0.f;
+        acc_c[r] = 0.f;
+    }
+    if (R > 1 && role == 0) {
+        float vrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int c = r + 1; c < R; ++c) {
+                const float pp = urow[r] * vrow[c];
+                const float rr = rcp_approx(pp + 1.0f);
+                const float e = (rr * (pp * rr)) * (crow[c] - crow[r]);
+                acc_r[r] += e;
+                acc_r[c] -= e;
+            }
+        }
+    }
+#pragma unroll 1
+    for (int D = d_lo; D < d_hi; ++D) {
+        if (2 * D == T) {                       // antipodal step: weight 1/2 goes onto the c differences
+            float ch[R], cch[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) ch[r] = 0.5f * crow[r], cch[r] = 0.5f * ccol[r];
+            grad_tile<R>(urow, vcol, ch, cch, acc_r, acc_r_hi, acc_c);
+        } else {
+            grad_tile<R>(urow, vcol, crow, ccol, acc_r, acc_r_hi, acc_c);
+        }
+        if (D + 1 < d_hi) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                ccol[r] = __shfl_sync(LTR_FULL_MASK, ccol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            sh.part[warp][0][lane * R + r] = acc_r[r] + acc_r_hi[r];
+            sh.part[warp][1][cb_last * R + r] = acc_c[r];
+        }
+    }
+    __syncthreads();
+    if (tid < p.n) {
+        float sum2 = 0.f;
+        if (doc.valid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sum2 += sh.part[k][0][doc.dst] + sh.part[k][1][doc.dst];
+        }
+        p.grad[(size_t)b * p.n + tid] = p.alpha * sum2;          // padded docs: exactly 0
+    }
+}
+
+__global__ void __launch_bounds__(SYM_THREADS, 8) approx_ndcg_sym_kernel(const ApproxParams p) {
+    __shared__ __align__(16) SymShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n;
+    const float scale = p.alpha * kLog2e;
+
+    int b = (int)blockIdx.x;                      // first slate is static, the rest come from the counter
+    float cur_s = 0.f, cur_y = p.pad;
+    if (b < p.B && tid < n) {
+        cur_s = ld_stream(p.s + (size_t)b * n + tid);
+        cur_y = ld_stream(p.y + (size_t)b * n + tid);
+    }
+    SymCarry cy;
+    cy.fx = 0;
+    cy.nonfinite = 0;
+    cy.claimed = 0;
+    if (tid == 0) cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
+    for (int i = tid; i <= SYM_N; i += SYM_THREADS) sh.P[i] = p.disc_prefix[i];
+    // (made visible by the first slate's barrier)
+
+    while (b < p.B) {
+        // ---- compaction offsets + per-slate statistics: 5 warp collectives, one barrier ---------
+        const float sv = cur_s, yv = cur_y;
+        SymDoc doc;
+        doc.valid = (tid < n) && (yv != p.pad);
+        const float yc = fmaxf(yv, 0.f);                         // approxNDCG.py:37-38 clamp
+        const int lvl = (int)fminf(yc, 100.f);
+        const bool small_int = (yc == (float)lvl) && (lvl <= SYM_MAX_LABEL);
+        const unsigned bal = __ballot_sync(LTR_FULL_MASK, doc.valid);
+        const unsigned bad = __ballot_sync(LTR_FULL_MASK, doc.valid && !small_int);
+        const int key = float_order_key(sv);
+        const int kmin = __reduce_min_sync(LTR_FULL_MASK, doc.valid ? key : 0x7fffffff);
+        const int kmax = __reduce_max_sync(LTR_FULL_MASK, doc.valid ? key : (int)0x80000000);
+        // label histogram: one 8-bit field per level 1..4 (<= 32 per warp, <= 128 per slate)
+        const unsigned field = (doc.valid && small_int && lvl >= 1) ? (1u << (8 * (lvl - 1))) : 0u;
+        const unsigned cnts = __reduce_add_sync(LTR_FULL_MASK, field);
+        if (lane == 0) sh.wstat[warp] = make_int4(__popc(bal) | (bad ? 0x10000 : 0), kmin, kmax, (int)cnts);
+        __syncthreads();
+        int m = 0, off = 0, any_bad = 0;
+        int gmin = 0x7fffffff, gmax = (int)0x80000000;
+        unsigned packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int4 st = sh.wstat[k];
+            const int cnt = st.x & 0xffff;
+            off += (k < warp) ? cnt : 0;
+            m += cnt;
+            any_bad |= st.x >> 16;
+            gmin = min(gmin, st.y);
+            gmax = max(gmax, st.z);
+            packed += (unsigned)st.w;
+        }
+        doc.dst = off + __popc(bal & ((1u << lane) - 1u));
+        doc.gain = 0.f;
+
+        int next_b = 0;
+        float next_s = 0.f, next_y = p.pad;
+        if (m == 0) {                                            // fully padded slate: value 0, no gradient
+            if (tid == 0) {
+                p.slate_out[b] = 0.f;
+                sh.next_b = cy.claimed;
+                cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
+            }
+            if (tid < n && p.grad != nullptr) p.grad[(size_t)b * n + tid] = 0.f;
+            __syncthreads();
+            next_b = sh.next_b;
+            if (next_b < p.B && tid < n) {
+                next_s = ld_stream(p.s + (size_t)next_b * n + tid);
+                next_y = ld_stream(p.y + (size_t)next_b * n + tid);
+            }
+            __syncthreads();
+        } else {
+            // ---- ideal DCG over ALL positions (approxNDCG.py:41-43) -----------------------------
+            float maxdcg, gain;
+            if (!any_bad) {
+                // labels 0..4: level L fills ideal ranks (e_{L+1}, e_L], e_L = #docs with label >= L, so
+                // maxDCG = sum_L (2^L - 1)(P[e_L] - P[e_{L+1}]) = 8 P[e4] + 4 P[e3] + 2 P[e2] + P[e1]
+                const int e4 = packed >> 24;
+                const int e3 = e4 + ((packed >> 16) & 255);
+                const int e2 = e3 + ((packed >> 8) & 255);
+                const int e1 = e2 + (packed & 255);
+                const double dcg = 8.0 * sh.P[e4] + 4.0 * sh.P[e3] + 2.0 * sh.P[e2] + sh.P[e1];
+                maxdcg = fmaxf((float)dcg, p.eps);
+                gain = (float)((1 << lvl) - 1);
+            } else {
+                // general labels: bitonic sort (descending) of the clamped labels
+                sh.sortbuf[tid] = doc.valid ? yc : -1.0f;        // -1 sorts after every clamped label
+                block_bitonic_desc(sh.sortbuf, SYM_N);
+                const float lab = sh.sortbuf[tid];
+                float part = (lab >= 0.f) ? gain_exp2(lab) / log2f(2.0f + (float)tid) : 0.f;
+                part = warp_sum(part);
+                if (lane == 0) sh.red[warp] = part;
+                __syncthreads();
+                maxdcg = fmaxf((sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]), p.eps);
+                gain = gain_exp2(yc);
+                __syncthreads();
+            }
+            doc.gain = gain / maxdcg;                            // G_i (approxNDCG.py:44)
+
+            // ---- compacted per-doc quantities -----------------------------------------------------
+            const float smin = float_from_key(gmin), smax = float_from_key(gmax);
+            const float range = (smax - smin) * scale;
+            const bool fact = fabsf(range) < 126.0f;             // false for inf / NaN ranges too
+            const float smid = 0.5f * smin + 0.5f * smax;
+            if (doc.valid) {
+                if (fact) {
+                    const float tc = (sv - smid) * scale;
+                    sh.u[doc.dst] = ex2_approx(tc);
+                    sh.v[doc.dst] = ex2_approx(-tc);
+                } else {
+                    sh.u[doc.dst] = sv;
+                }
+            }
+            if (tid >= m) {                                      // zero tail: p = 0, w = 0 for padding
+                sh.u[tid] = 0.f;
+                sh.v[tid] = 0.f;
+                sh.c[tid] = 0.f;
+            }
+            __syncthreads();
+
+            if (!fact) direct_slate(p, sh, b, m, scale, doc, cy, next_s, next_y, next_b);
+            else if (m > 96) sym_slate<4>(p, sh, b, m, doc, cy, next_s, next_y, next_b);
+            else if (m > 64) sym_slate<3>(p, sh, b, m, doc, cy, next_s, next_y, next_b);
+            else sym_slate<2>(p, sh, b, m, doc, cy, next_s, next_y, next_b);   // (short slates leave lanes idle)
+        }
+        b = next_b;
+        cur_s = next_s;
+        cur_y = next_y;
+    }
+
+    // ---- batch loss: per-CTA fixed-point sums meet in the workspace; the last CTA to arrive converts ----
+    if (tid == 0) {
+        unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(p.ws + 2);
+        atomicAdd(acc64, (unsigned long long)cy.fx);
+        if (cy.nonfinite) atomicOr(&p.ws[4], 1u);
+        __threadfence();
+        const unsigned done = atomicAdd(&p.ws[1], 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence();
+            const long long total = (long long)atomicAdd(acc64, 0ull);
+            const unsigned bad = atomicOr(&p.ws[4], 0u);
+            const double mean = (double)total / ((double)kFixScale * (double)p.B);
+            p.loss_out[0] = bad ? __int_as_float(0x7fc00000) : (float)(-mean);       // approxNDCG.py:53
+            p.ws[0] = 0u;
+            p.ws[1] = 0u;
+            p.ws[4] = 0u;
+            *acc64 = 0ull;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace ltr

@@ -54,6 +54,11 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
     return r;
 }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+    return r;
+}
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     f32x2 r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
@@ -176,7 +181,9 @@ __device__ __forceinline__ int next_pow2(int v) {
 // `len` must be a power of two. Keys only (used for ideal-DCG label order, where ties are
 // value-identical and so order-free).
 __device__ __forceinline__ void block_bitonic_desc(float* keys, int len) {
+#pragma unroll 1
     for (int k = 2; k <= len; k <<= 1) {
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
             __syncthreads();
             for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {

@@ -4,7 +4,10 @@ import torch
 
 LOSS_RTOL = 1e-5     # north_star: losses within 1e-5 relative
 GRAD_RTOL = 1e-4     # north_star: gradients within 1e-4 relative (fp32)
-GRAD_ATOL_FRAC = 1e-6  # + this fraction of max|g_ref| (elements that are ~0 by cancellation)
+# + this fraction of max|g_ref| for elements that are ~0 by cancellation.  The floor is set by the
+# reference itself: on the saturated `approx/big_scores` golden its own fp32 gradient is 2.0e-6 * max|g|
+# away from the same graph evaluated in fp64 (sigmoid'(x) formed as y * (1 - y) next to y = 1).
+GRAD_ATOL_FRAC = 5e-6
 
 
 def make_slates(B, n, seed=2020, min_len=None, ties=False, pad_anywhere=False, score_scale=1.0):
@@ -34,7 +37,10 @@ def assert_loss_close(got, ref, rtol=LOSS_RTOL, atol=1e-7):
     assert np.all(err <= tol), f"loss mismatch: got {got}, ref {ref}, rel {err / (np.abs(ref) + 1e-30)}"
 
 
-def assert_grad_close(got, ref, rtol=GRAD_RTOL, atol_frac=GRAD_ATOL_FRAC):
+def assert_grad_close(got, ref, rtol=GRAD_RTOL, atol_frac=GRAD_ATOL_FRAC, ref64=None):
+    """|got - ref| <= rtol |ref| + atol_frac max|ref| (+ 2 |ref - ref64| when the same oracle graph evaluated
+    in fp64 is supplied: where the fp32 reference is itself off by more than the tolerance -- saturated
+    slates, sigmoid'(x) = y (1 - y) next to y = 1 -- the CUDA result may sit on the exact side of it)."""
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape, (got.shape, ref.shape)
@@ -42,6 +48,8 @@ def assert_grad_close(got, ref, rtol=GRAD_RTOL, atol_frac=GRAD_ATOL_FRAC):
     scale = float(np.abs(ref).max())
     err = np.abs(got - ref)
     tol = rtol * np.abs(ref) + atol_frac * scale + 1e-30
+    if ref64 is not None:
+        tol = tol + 2.0 * np.abs(ref - np.asarray(ref64, dtype=np.float64))
     bad = err > tol
     assert not bad.any(), (f"{int(bad.sum())} of {bad.size} gradient elements out of tolerance; "
                            f"worst err/scale {float((err / (scale + 1e-30)).max()):.3e}")

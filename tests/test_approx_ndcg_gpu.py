@@ -18,12 +18,22 @@ def _run_gpu(s, y, **kw):
     return loss.detach().cpu().numpy(), sd.grad.cpu().numpy()
 
 
-def _run_oracle(s, y, **kw):
+def _run_oracle(s, y, dtype=torch.float32, **kw):
     from oracle import ltr_oracle as O
-    sc = s.clone().requires_grad_(True)
-    loss = O.approx_ndcg_loss(sc, y, **kw)
+    sc = s.to(dtype).clone().requires_grad_(True)
+    loss = O.approx_ndcg_loss(sc, y.to(dtype), **kw)
     loss.backward()
     return loss.detach().numpy(), sc.grad.numpy()
+
+
+def _check(s, y, **kw):
+    """GPU vs the fp32 oracle, with the oracle's own fp32-vs-fp64 distance as extra slack (see ltr_testing)."""
+    loss, grad = _run_gpu(s, y, **kw)
+    rloss, rgrad = _run_oracle(s, y, **kw)
+    _, rgrad64 = _run_oracle(s, y, dtype=torch.float64, **kw)
+    assert_loss_close(loss, rloss)
+    assert_grad_close(grad, rgrad, ref64=rgrad64)
+    return loss, grad
 
 
 @pytest.mark.parametrize("name", G.names("approx/"))
@@ -32,7 +42,9 @@ def test_golden(name):
     loss, grad = _run_gpu(torch.from_numpy(ins["y_pred"]), torch.from_numpy(ins["y_true"]), **G.kwargs(name))
     assert loss.shape == G.out(name).shape == ()
     assert_loss_close(loss, G.out(name))
-    assert_grad_close(grad, G.grad(name, "y_pred"))
+    _, g64 = _run_oracle(torch.from_numpy(ins["y_pred"]), torch.from_numpy(ins["y_true"]), dtype=torch.float64,
+                         **G.kwargs(name))
+    assert_grad_close(grad, G.grad(name, "y_pred"), ref64=g64)
 
 
 @pytest.mark.parametrize("B,n,min_len,alpha,kw", [
@@ -53,6 +65,29 @@ def test_vs_oracle(B, n, min_len, alpha, kw):
     assert_loss_close(loss, rloss)
     assert_grad_close(grad, rgrad)
     assert np.all(grad[(y == -1).numpy()] == 0.0), "padded docs must get exactly zero gradient"
+
+
+def test_every_valid_length_1_to_128():
+    """One slate per valid length 0..128: every (R, T) shape of the block-circulant pair schedule,
+    odd and even T, ragged last blocks."""
+    n = 128
+    s, y = make_slates(n + 1, n, seed=99)
+    for b in range(n + 1):
+        y[b, b:] = -1.0                      # slate b has b valid docs
+    for alpha in (1.0, 10.0):
+        _check(s, y, alpha=alpha)
+    # per-slate values, not only their mean
+    for b in list(range(1, 12)) + [31, 32, 33, 63, 64, 65, 66, 95, 96, 97, 127, 128]:
+        _check(s[b:b + 1], y[b:b + 1], alpha=10.0)
+        _check(s[b:b + 1], y[b:b + 1], alpha=1.0)
+
+
+def test_wide_score_range_mixed_batch():
+    """Slates beyond the factorised form's exponent budget (direct form) mixed with ordinary ones."""
+    s, y = make_slates(40, 128, seed=17, min_len=20, pad_anywhere=True)
+    s[::3] *= 40.0
+    s[1::3] += 1000.0                        # large common offset, ordinary spread
+    _check(s, y, alpha=10.0)
 
 
 def test_fractional_labels_take_the_sort_path():
