@@ -13,8 +13,8 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - every call is asynchronous on `stream` and returns 0 on success, a cudaError_t value
  *     or a negative LTR_E* code otherwise; nothing throws across the boundary;
- *   - `workspace` is LTR_WORKSPACE_BYTES of device memory, zero-filled ONCE by the caller
- *     and then reused by every call issued on the same stream (the kernels leave it zeroed);
+ *   - `workspace` is LTR_WORKSPACE_BYTES of 16-byte aligned device memory, zero-filled ONCE by the
+ *     caller and then reused by every call issued on the same stream (the kernels leave it zeroed);
  *   - `disc_prefix` is the fp64 table P[r] = sum_{q=1..r} 1/log2(1+q), r = 0..disc_len-1
  *     (P[0] = 0), on the device; ltr_fill_disc_prefix() builds it.  It may be NULL, in which
  *     case ideal DCGs always take the sorting path.
@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LTR_WORKSPACE_BYTES 4096
+#define LTR_WORKSPACE_BYTES 131072
 
 #define LTR_EINVAL (-1)  /* bad argument (null pointer, n out of range, unknown enum) */
 #define LTR_ETOOBIG (-2) /* slate longer than the shared-memory capacity supports   */
@@ -67,6 +67,119 @@ int ltr_approx_ndcg_fwdbwd_host(const float* h_y_pred, const float* h_y_true, in
                                 float pad_value, const double* disc_prefix, int disc_len, float* h_loss,
                                 float* h_grad, float* h_slate_ndcg, void* d_scratch, size_t scratch_bytes,
                                 void* workspace, void* stream);
+
+/*
+ * ListNet, fused forward + backward.          replaces losses/listnet.py:5-16   (NB: y_true FIRST, as there)
+ *   y_true, y_pred : [B, n], n <= 1024, no padding mask (the reference has none)
+ *   slate_loss     : [B] out or NULL, -sum_i softmax(y_true)_i log softmax(y_pred)_i   (apply_sigmoid: -sum sigmoid(.))
+ *   loss           : [1] out, sum over the batch                                         (listnet.py:16)
+ *   grad           : [B, n] out or NULL, d loss / d y_pred
+ * One warp streams one slate; 12 n bytes of HBM traffic per slate.
+ */
+int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, int n, int apply_sigmoid, float* slate_loss,
+                       float* loss, float* grad, void* workspace, void* stream);
+
+/*
+ * Ordinal loss, fused forward + backward.     replaces losses/ordinal.py:9-53
+ *   y_pred : [B, n, levels] probabilities, y_true : [B, n]; loss [1]; grad [B, n, levels] or NULL.
+ *   A label of -1 makes all targets of the doc -1 (with_ordinals' default); entries whose TARGET equals
+ *   pad_indicator are masked (ordinal.py:41).  The caller raises, as torch's BCELoss does, when a -1 target survives.
+ */
+int ltr_ordinal_fwdbwd(const float* y_pred, const float* y_true, int B, int n, int levels, float pad_indicator,
+                       float* loss, float* grad, void* workspace, void* stream);
+
+/* tie rules of the sorting entry points */
+#define LTR_TIES_STABLE 0   /* equal keys in ascending index order: python sorted(reverse=True), metrics.py:51 */
+#define LTR_TIES_STDSORT 1  /* torch.sort / argsort on the CPU (libstdc++ std::sort over (key, index)), SURVEY A.3 */
+#define LTR_TIES_REVERSED 2 /* equal keys in descending index order: np.argsort(kind="stable")[::-1]              */
+
+/*
+ * Descending sort of every row.               replaces Tensor.sort(descending=True) / torch.argsort on [B, n]
+ *   perm        : [B, n] int32 out or NULL, perm[b, r] = index of the doc at rank r (NaN first, -inf last)
+ *   sorted_keys : [B, n] out or NULL
+ */
+int ltr_sort_desc(const float* keys, int B, int n, int tie_rule, int* perm, float* sorted_keys, void* stream);
+
+/*
+ * NDCG@k, fp32.                               replaces utils/metrics.py:83-104 (torchNdcg)
+ *   y_true, y_pred : [Q, n]; ks : nk <= 32 HOST ints (k <= 0 or k > n: no truncation); out : [Q, nk]
+ *   disc32 : n device floats, disc32[r] = (float)log2(2 + r) (the reference divides by np.log2(1 + i) rounded to fp32)
+ *   gains 2^l - 1, sequential fp32 accumulation, 0/0 = NaN (the 'tensor' return type maps NaN to 0 in the caller).
+ *   All k of a sweep are served by one read and one sort of the query.
+ */
+int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
+                  const float* disc32, float* out, void* stream);
+
+/*
+ * NDCG@k, fp64.                               replaces utils/metrics.py:48-80 (dcg / ndcg / mNdcg)
+ *   gains linear (exponential_gains = 0) or 2^l - 1; disc64[r] = log2(2 + r); k clipped to n; a query whose
+ *   ideal DCG is 0 gets empty_value (1.0 for no_relevant=True, 0.0 otherwise); out : [Q, nk] doubles.
+ */
+int ltr_ndcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
+                      int exponential_gains, double empty_value, const double* disc64, double* out, void* stream);
+
+/*
+ * exactNDCG "loss", forward only.             replaces losses/exactNDCG.py:5-29 (ndcgLoss; y_true FIRST)
+ *   slate_value [B] = -dcg/idcg on softmaxed labels ordered by softmax(y_pred), discount ln(r) + 1; loss [1] = mean.
+ */
+int ltr_exact_ndcg(const float* y_true, const float* y_pred, int B, int n, float* slate_value, float* loss, void* stream);
+
+/*
+ * orderScore loss, fused forward + backward.  replaces losses/orderScore.py:5-24 (y_true FIRST)
+ *   slate_value [B] = -sum_r (-n + 2r) log softmax(y_pred)[order_r], order = argsort(softmax(y_true), descending);
+ *   loss [1] = mean; grad [B, n] or NULL.
+ */
+int ltr_order_score_fwdbwd(const float* y_true, const float* y_pred, int B, int n, float* slate_value, float* loss,
+                           float* grad, void* stream);
+
+/* weighing schemes of ltr_lambda_fwdbwd (losses/lambdaL.py:96-127) */
+#define LTR_SCHEME_NONE 0        /* weighing_scheme=None, rankNet_scheme                     */
+#define LTR_SCHEME_NDCG1 1       /* ndcgLoss1_scheme                                         */
+#define LTR_SCHEME_NDCG2 2       /* ndcgLoss2_scheme                                         */
+#define LTR_SCHEME_LAMBDARANK 3  /* lamdbaRank_scheme [sic]                                  */
+#define LTR_SCHEME_NDCG2PP 4     /* ndcgLoss2PP_scheme                                       */
+#define LTR_SCHEME_GTDIFF 5      /* rankNetWeightedByGTDiff_scheme                           */
+#define LTR_SCHEME_GTDIFF_POW 6  /* rankNetWeightedByGTDiffPowed_scheme                      */
+
+/*
+ * LambdaLoss framework, fused forward + backward.   replaces losses/lambdaL.py:7-93 (lambdaMask + lambdaLoss)
+ *   y_pred, y_true : [B, n], n <= 2048; k <= 0: no NDCG@k truncation
+ *   slate_sum, slate_count : [B] out, sum / number of the masked pair log-probabilities of each slate
+ *   loss       : [1] out, -sum (reduction_mean = 0) or -sum/count over the whole batch (lambdaL.py:86-89)
+ *   pair_count : [1] out or NULL, number of masked pairs in the batch
+ *   grad       : [B, n] out or NULL, d loss / d y_pred (0 for padded docs)
+ */
+int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value, int scheme,
+                      int k, float sigma, float mu, int reduction_mean, int natural_log, float* slate_sum,
+                      float* slate_count, float* loss, float* pair_count, float* grad, void* stream);
+
+/*
+ * Risk-sensitive losses, ListNet family.      replaces losses/riskLosses/riskLosses.py:8-60, 128-180, 247-291
+ *
+ * ltr_risk_listnet_rows: mat[b, :] = effectiveness of {model, S baseline systems, (ideal)} for query b
+ *   transformation 1: sum_d (p_t p_s - p_t^2)^2   2: cosine(p_t, p_s)   3: (sum p_t p_s - sum p_t^2)^2,
+ *   p = softmax over the docs; t_variant selects tRiskListnetLoss' cosine(p_t^2, p_t p_s) (riskLosses.py:262).
+ *   y_baselines : [B, n, S] or NULL (S = 0); mat : [B, 1 + S + add_ideal]
+ * ltr_risk_listnet_rows_bwd: grad[b, :] = gq[b] * d mat[b, 0] / d y_pred[b, :]
+ */
+int ltr_risk_listnet_rows(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
+                          int transformation, int add_ideal, int t_variant, float* mat, void* stream);
+int ltr_risk_listnet_rows_bwd(const float* y_pred, const float* y_true, int B, int n, int transformation, int t_variant,
+                              const float* gq, float* grad, void* stream);
+
+/*
+ * zRisk / geoRisk / tRisk over a query x system matrix.   replaces losses/riskLosses/riskFunctions.py:4-33 and the
+ * epilogues riskLosses.py:49-58, 274-291.  Three phases so that query-sharded callers can all-reduce in between:
+ *   phase 1 (local)  state1 = {max(mat), sum mat[:,0], sum mat[:,C-1], sum(mat), Q}     -> MAX on [0], SUM on [1..4]
+ *   phase 2          state2 = per used column {sum z c, sum A T, sum A e, sum c/sqrt(e), sum A}, #maxima, t-risk sums -> SUM
+ *   phase 3          loss[0], gq[q] = d loss / d mat[q, 0] and gmat[q, i] = d loss / d mat[q, i]   (either may be NULL)
+ *   kind 0 zRisk, 1 geoRisk, 2 tRisk (columns 0 = model, 1 = baseline); invert: mat <- max(mat) - mat;
+ *   return_strategy 1: f r(0), 2: f (r(-1) - r(0)), 3: f (r(-1) - r(0))^2; precedence_quirk: strategy 2 is
+ *   f r(-1) - r(0) (zRiskListnetLoss, riskLosses.py:176); negative = f.  state1/state2: 16 device doubles each.
+ */
+int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int invert, int return_strategy,
+                   int precedence_quirk, float alpha, float negative, double* state1, double* state2, float* loss,
+                   float* gq, float* gmat, void* stream);
 
 /*
  * Roofline probes (measurement only): a pure ex2.approx loop and a pure FFMA loop, 8 CTAs of

@@ -1,0 +1,271 @@
+// K2: fused forward+backward LambdaLoss framework (replaces losses/lambdaL.py:7-127 of the reference):
+// lambdaMask + lambdaLoss with the seven weighing schemes, NDCG@k truncation, sum / mean reduction and
+// binary / natural logarithm.  One CTA per slate:
+//   1. scores (padding -> -inf) are sorted in shared memory with torch.sort's tie order (sort_common.cuh),
+//      labels follow the permutation; a second, values-only sort of the labels gives the ideal DCG@k;
+//   2. each thread owns rows i = tid, tid + 128, ... of the k x k block of rank positions and walks the
+//      columns j; a visited pair (i, j) with label_i != label_j belongs to the mask exactly once, as
+//      (hi, lo) = the doc with the larger label first, so ONE evaluation per visit serves both the
+//      loss (counted by the thread that owns `hi`) and d loss / d s_i;
+//   3. per pair: e = 2^(-sigma log2e (s_hi - s_lo)), sig = 1/(1+e), l = w * max(log2 eps, -log2(1+e)),
+//      clamped again at log2 eps (lambdaL.py:51), d l / d delta = w sigma (1 - sig) where unclamped:
+//      3 MUFU (ex2, rcp, lg2) + ~15 FP32; the B x n x n tensors of the reference never exist.
+// `ndcgLoss1_scheme` has no label condition (lambdaL.py:26): every ordered pair of real docs, the diagonal
+// included, is in the mask with weight G_i / D_i.
+#include "ltr_host.h"
+#include "sort_common.cuh"
+
+namespace ltr {
+
+constexpr int LAMBDA_THREADS = 128;
+constexpr int LAMBDA_MAX_N = 2048;
+
+enum LambdaScheme {
+    SCHEME_NONE = 0,            // weighing_scheme=None and rankNet_scheme: w = 1
+    SCHEME_NDCG1 = 1,           // G_i / D_i
+    SCHEME_NDCG2 = 2,           // delta_|i-j| |G_i - G_j|
+    SCHEME_LAMBDARANK = 3,      // |1/D_i - 1/D_j| |G_i - G_j|
+    SCHEME_NDCG2PP = 4,         // mu * ndcgLoss2 + lambdaRank
+    SCHEME_GTDIFF = 5,          // |y_i - y_j|
+    SCHEME_GTDIFF_POW = 6,      // |y_i^2 - y_j^2|
+};
+
+struct LambdaParams {
+    const float* y_pred;
+    const float* y_true;
+    int B, n, len, k;           // k <= 0: no truncation
+    float eps, pad, sigma, mu;
+    int natural_log;            // 0: log2, 1: ln
+    float* slate_sum;           // [B] sum of the masked pair log-probabilities of the slate
+    float* slate_cnt;           // [B] number of masked pairs
+    float* grad;                // [B, n] d(-sum)/d y_pred, unscaled; null = forward only
+};
+
+template <int SCHEME>
+__device__ __forceinline__ float pair_weight(int i, int j, const float* G, const float* invD, const float* dtab,
+                                             const float* Y, float mu) {
+    if (SCHEME == SCHEME_NONE) return 1.0f;
+    if (SCHEME == SCHEME_NDCG1) return G[i] * invD[i];
+    if (SCHEME == SCHEME_GTDIFF) return fabsf(fmaxf(Y[i], 0.f) - fmaxf(Y[j], 0.f));          // clamped labels (:37)
+    if (SCHEME == SCHEME_GTDIFF_POW) {
+        const float a = fmaxf(Y[i], 0.f), c = fmaxf(Y[j], 0.f);
+        return fabsf(a * a - c * c);
+    }
+    const float dg = fabsf(G[i] - G[j]);
+    const int gap = i > j ? i - j : j - i;
+    if (SCHEME == SCHEME_NDCG2) return dtab[gap] * dg;
+    const float lr = fabsf(invD[i] - invD[j]) * dg;
+    if (SCHEME == SCHEME_LAMBDARANK) return lr;
+    return mu * (dtab[gap] * dg) + lr;                           // SCHEME_NDCG2PP (lambdaL.py:115)
+}
+
+// log-probability of one pair and its derivative w.r.t. delta = s_hi - s_lo
+__device__ __forceinline__ void pair_logprob(float delta, float w, float sig_scale, float log_eps2, float out_scale,
+                                             float& l, float& dl) {
+    // lambdaL.py:49-50: clamp to +-1e8, NaN (-inf - -inf) -> 0
+    delta = (delta != delta) ? 0.f : fminf(fmaxf(delta, -1e8f), 1e8f);
+    const float e = ex2_approx(fminf(-sig_scale * delta, 126.0f));      // exp(-sigma delta)
+    const float q = 1.0f + e;
+    const float sig = rcp_approx(q);
+    float l2 = -lg2_approx(q);                                    // log2 sigmoid
+    bool open = l2 >= log_eps2;                                   // inner clamp(min=eps) inactive
+    l2 = fmaxf(l2, log_eps2);
+    float lw = w * l2;                                            // log2 of (.)^w
+    open = open && (lw >= log_eps2);                              // outer clamp inactive
+    lw = fmaxf(lw, log_eps2);
+    l = lw * out_scale;                                           // out_scale = 1 (binary) or ln 2 (natural)
+    // d log_b(sig^w) / d delta = w sigma (1 - sig) / ln b;  1 - sig = e * sig
+    dl = open ? w * (e * sig) : 0.f;
+}
+
+template <int SCHEME>
+__global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[32];
+    __shared__ int sh_m;
+    const int n = p.n, len = p.len;
+    float* K = reinterpret_cast<float*>(smem_raw);          // scores in rank order
+    int* I = reinterpret_cast<int*>(K + len);               // permutation
+    float* Y = reinterpret_cast<float*>(I + len);           // sort scratch, then labels in rank order (-inf = padding)
+    float* G = Y + len;                                     // ideal labels, then gains in rank order
+    float* invD = G + len;                                  // 1 / log2(1 + r), r = 1..n
+    float* dtab = invD + len;                               // |1/D_t - 1/D_{t+1}| by rank gap t (0 on the diagonal)
+    const float ninf = __int_as_float(0xff800000);
+    const int tid = threadIdx.x;
+
+    for (int r = tid; r < n; r += LAMBDA_THREADS) invD[r] = 1.0f / log2f(2.0f + (float)r);
+    __syncthreads();
+    for (int t = tid; t < n; t += LAMBDA_THREADS) dtab[t] = (t == 0) ? 0.f : fabsf(invD[t - 1] - invD[t]);   // lambdaL.py:101-104
+    const float sig_scale = p.sigma * kLog2e;
+    const float log_eps2 = log2f(p.eps);
+    const float out_scale = p.natural_log ? kLn2 : 1.0f;
+    // d/d delta of log_b: w sigma (1-sig) / ln b -> binary: / ln 2, natural: 1
+    const float grad_scale = p.natural_log ? p.sigma : p.sigma / kLn2;
+
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const float* sp = p.y_pred + (size_t)b * n;
+        const float* yp = p.y_true + (size_t)b * n;
+        int cnt_valid = 0;
+        for (int i = tid; i < n; i += LAMBDA_THREADS) {
+            const float y = yp[i];
+            const bool pad = (y == p.pad);
+            K[i] = pad ? ninf : sp[i];
+            cnt_valid += pad ? 0 : 1;
+        }
+        if (tid == 0) sh_m = 0;
+        __syncthreads();
+        cnt_valid = (int)warp_sum((float)cnt_valid);
+        if ((tid & 31) == 0) atomicAdd(&sh_m, cnt_valid);
+        __syncthreads();
+        const int m = sh_m;
+        block_sort_desc(K, I, Y, n, len, TIES_STDSORT, m);
+        // labels: ideal order (values only) -> ideal DCG@k; rank order -> gains
+        for (int i = tid; i < len; i += LAMBDA_THREADS) {
+            float y = (i < n) ? yp[i] : ninf;
+            if (y == p.pad) y = ninf;
+            G[i] = y;
+        }
+        block_bitonic_desc(G, len);
+        const int kk = (p.k > 0 && p.k < n) ? p.k : n;
+        float part = 0.f;
+        for (int r = tid; r < kk; r += LAMBDA_THREADS) part += (exp2f(fmaxf(G[r], 0.f)) - 1.0f) * invD[r];
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = 0.f;
+        part = warp_sum(part);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = part;
+        __syncthreads();
+        const float maxdcg = fmaxf((red[0] + red[1]) + (red[2] + red[3]), p.eps);
+        __syncthreads();
+        for (int r = tid; r < n; r += LAMBDA_THREADS) {
+            float y = yp[I[r]];
+            if (y == p.pad) y = ninf;
+            Y[r] = y;                                             // raw label: the mask compares these (:24-27)
+            G[r] = (exp2f(fmaxf(y, 0.f)) - 1.0f) / maxdcg;
+        }
+        __syncthreads();
+
+        // ---- pair loop over the top-k block of real docs -------------------------------------------
+        const int lim = kk < m ? kk : m;
+        float loss_part = 0.f, cnt_part = 0.f;
+        for (int i = tid; i < n; i += LAMBDA_THREADS) {
+            float g = 0.f;
+            if (i < lim) {
+                const float yi = Y[i], si = K[i];
+                for (int j = 0; j < lim; ++j) {
+                    const float yj = Y[j], sj = K[j];
+                    float l, dl;
+                    if (SCHEME == SCHEME_NDCG1) {
+                        // (i, j) as row and (j, i) as column; both always in the mask (labels finite)
+                        pair_logprob(si - sj, pair_weight<SCHEME>(i, j, G, invD, dtab, Y, p.mu), sig_scale, log_eps2,
+                                     out_scale, l, dl);
+                        loss_part += l;
+                        cnt_part += 1.0f;
+                        g -= dl;
+                        pair_logprob(sj - si, pair_weight<SCHEME>(j, i, G, invD, dtab, Y, p.mu), sig_scale, log_eps2,
+                                     out_scale, l, dl);
+                        g += dl;
+                    } else if (yi != yj) {
+                        const bool row = yi > yj;                 // this thread's doc is the better-labelled one
+                        const float w = pair_weight<SCHEME>(i, j, G, invD, dtab, Y, p.mu);   // symmetric in (i, j)
+                        pair_logprob(row ? si - sj : sj - si, w, sig_scale, log_eps2, out_scale, l, dl);
+                        if (row) {
+                            loss_part += l;
+                            cnt_part += 1.0f;
+                            g -= dl;
+                        } else {
+                            g += dl;
+                        }
+                    }
+                }
+            }
+            if (p.grad) p.grad[(size_t)b * n + I[i]] = (i < m) ? g * grad_scale : 0.f;
+        }
+        loss_part = warp_sum(loss_part);
+        cnt_part = warp_sum(cnt_part);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = loss_part, red[8 + (tid >> 5)] = cnt_part;
+        __syncthreads();
+        if (tid == 0) {
+            p.slate_sum[b] = (red[0] + red[1]) + (red[2] + red[3]);
+            p.slate_cnt[b] = (red[8] + red[9]) + (red[10] + red[11]);
+        }
+        __syncthreads();
+    }
+}
+
+// loss = -sum (reduction "sum") or -sum / count ("mean"); for "mean" the gradient is scaled by 1/count too.
+__global__ void __launch_bounds__(256) lambda_finish_kernel(const float* slate_sum, const float* slate_cnt, int B, int mean,
+                                                            float* loss, float* count_out, float* grad, long long total) {
+    __shared__ double red[2][8];
+    __shared__ float sh_inv;
+    double s = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < B; i += 256) s += (double)slate_sum[i], c += (double)slate_cnt[i];
+    s = warp_sum(s);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s, red[1][threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tc = 0.0;
+        for (int w = 0; w < 8; ++w) ts += red[0][w], tc += red[1][w];
+        if (blockIdx.x == 0) {
+            loss[0] = mean ? (float)(-ts / tc) : (float)(-ts);
+            if (count_out) count_out[0] = (float)tc;
+        }
+        sh_inv = (float)(1.0 / tc);
+    }
+    __syncthreads();
+    if (!mean || !grad) return;
+    const float inv = sh_inv;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) grad[i] *= inv;
+}
+
+template <int SCHEME>
+static int launch_lambda(const LambdaParams& p, size_t smem, int grid, cudaStream_t st) {
+    if (smem > 48 * 1024)
+        LTR_CUDA(cudaFuncSetAttribute(lambda_kernel<SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lambda_kernel<SCHEME><<<grid, LAMBDA_THREADS, smem, st>>>(p);
+    return 0;
+}
+
+}  // namespace ltr
+
+LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value,
+                              int scheme, int k, float sigma, float mu, int reduction_mean, int natural_log,
+                              float* slate_sum, float* slate_count, float* loss, float* pair_count, float* grad,
+                              void* stream) {
+    using namespace ltr;
+    if (!y_pred || !y_true || !slate_sum || !slate_count || !loss || B <= 0 || n <= 0)
+        return set_error(LTR_EINVAL, "ltr_lambda_fwdbwd: null pointer or non-positive B/n");
+    if (scheme < 0 || scheme > 6) return set_error(LTR_EINVAL, "ltr_lambda_fwdbwd: unknown weighing scheme");
+    if (n > LAMBDA_MAX_N) return set_error(LTR_ETOOBIG, "ltr_lambda_fwdbwd: slate too long");
+    LambdaParams p;
+    p.y_pred = y_pred; p.y_true = y_true; p.B = B; p.n = n; p.k = k;
+    p.len = 32;
+    while (p.len < n) p.len <<= 1;
+    p.eps = eps; p.pad = pad_value; p.sigma = sigma; p.mu = mu; p.natural_log = natural_log;
+    p.slate_sum = slate_sum; p.slate_cnt = slate_count; p.grad = grad;
+    const size_t smem = (size_t)p.len * 6 * sizeof(float);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int cap = device_sm_count() * 8;
+    const int grid = B < cap ? B : cap;
+    int rc = 0;
+    switch (scheme) {
+        case SCHEME_NONE: rc = launch_lambda<SCHEME_NONE>(p, smem, grid, st); break;
+        case SCHEME_NDCG1: rc = launch_lambda<SCHEME_NDCG1>(p, smem, grid, st); break;
+        case SCHEME_NDCG2: rc = launch_lambda<SCHEME_NDCG2>(p, smem, grid, st); break;
+        case SCHEME_LAMBDARANK: rc = launch_lambda<SCHEME_LAMBDARANK>(p, smem, grid, st); break;
+        case SCHEME_NDCG2PP: rc = launch_lambda<SCHEME_NDCG2PP>(p, smem, grid, st); break;
+        case SCHEME_GTDIFF: rc = launch_lambda<SCHEME_GTDIFF>(p, smem, grid, st); break;
+        default: rc = launch_lambda<SCHEME_GTDIFF_POW>(p, smem, grid, st); break;
+    }
+    if (rc) return rc;
+    const long long total = (long long)B * n;
+    int fgrid = reduction_mean && grad ? (int)((total + 256 * 8 - 1) / (256 * 8)) : 1;
+    if (fgrid > cap) fgrid = cap;
+    if (fgrid < 1) fgrid = 1;
+    lambda_finish_kernel<<<fgrid, 256, 0, st>>>(slate_sum, slate_count, B, reduction_mean, loss, pair_count, grad, total);
+    rc = (int)cudaGetLastError();
+    return rc ? set_cuda_error(rc, "ltr_lambda_fwdbwd") : 0;
+}

@@ -11,6 +11,17 @@ int set_cuda_error(int cuda_code, const char* where);  // records "<where>: <cud
 int device_sm_count();                               // SM count of the current device (cached per device)
 int device_max_optin_smem();                         // bytes of opt-in shared memory per CTA
 
+// ---- layout of the caller-provided workspace (LTR_WORKSPACE_BYTES, zero-filled once) -------------------------
+//   u32 [0..4]    approxNDCG: next-slate counter, finished-CTA counter, 64-bit fixed-point loss sum, non-finite flag
+//   u32 [16]      streaming kernels: finished-CTA counter
+//   f32 [32..33]  ordinal: BCE sum, number of valid docs
+//   byte 1024 ..  streaming kernels: per-CTA fp64 partial sums, [grid <= 2048][4]
+constexpr int LTR_WS_STREAM_COUNTER = 16;
+constexpr int LTR_WS_ORDINAL_SUMS = 32;
+inline unsigned* ws_counter(void* ws, int idx) { return reinterpret_cast<unsigned*>(ws) + idx; }
+inline float* ws_floats(void* ws, int idx) { return reinterpret_cast<float*>(ws) + idx; }
+inline double* ws_partials(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 1024); }
+
 }  // namespace ltr
 
 #define LTR_CUDA(expr)                                                  \

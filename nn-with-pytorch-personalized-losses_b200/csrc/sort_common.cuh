@@ -1,0 +1,220 @@
+// K5: CTA-level descending sort of one slate with the tie order of the reference's sorts.
+//
+// The reference sorts with `torch.sort(descending=True)` / `torch.argsort` on the CPU with the default
+// stable=False, which is libstdc++ `std::sort` (introsort: median-of-3 quicksort down to 16 elements, heap
+// sort when the depth limit 2*floor(log2 n) is hit, then one insertion sort) over (key, index) pairs with
+// the key-only comparator "NaN first, else greater" (SURVEY A.3).  For distinct keys any correct sort
+// gives the same permutation; for tied keys the result is whatever that exact sequence of swaps
+// leaves behind.  So:
+//   1. a bitonic network sorts (key desc, NaN first, index asc) -- the STABLE order -- in shared memory;
+//   2. if the slate has tied keys and more than 16 docs (std::sort is an insertion sort, hence
+//      stable, up to 16), one thread replays std::sort's exact sequence of moves on a copy in the original order.
+// Tie rules: LTR_TIES_STABLE (python sorted(reverse=True), metrics.py:51), LTR_TIES_STDSORT
+// (torch CPU), LTR_TIES_REVERSED (np.argsort(kind="stable")[::-1]: tied docs in descending index order).
+#pragma once
+#include "ltr_common.cuh"
+
+namespace ltr {
+
+constexpr int TIES_STABLE = 0;
+constexpr int TIES_STDSORT = 1;
+constexpr int TIES_REVERSED = 2;
+
+// key-only comparator of at::native KeyValueCompDesc: a goes before b
+__device__ __forceinline__ bool key_before(float a, float b) {
+    return (a != a && b == b) || (a > b);
+}
+__device__ __forceinline__ bool key_equiv(float a, float b) { return !key_before(a, b) && !key_before(b, a); }
+
+// composite order: key (NaN first, then descending), ties by index (ascending, or descending for REVERSED)
+template <bool IDX_DESC>
+__device__ __forceinline__ bool pair_before(float ka, int ia, float kb, int ib) {
+    if (key_before(ka, kb)) return true;
+    if (key_before(kb, ka)) return false;
+    return IDX_DESC ? (ia > ib) : (ia < ib);
+}
+
+// Bitonic sort of len (power of two) (key, index) pairs in shared memory by all threads of the CTA.
+template <bool IDX_DESC>
+__device__ __forceinline__ void block_bitonic_pairs(float* K, int* I, int len) {
+#pragma unroll 1
+    for (int k = 2; k <= len; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const bool up = ((lo & k) == 0);                 // this run ends up in "before" order
+                const float ka = K[lo], kb = K[hi];
+                const int ia = I[lo], ib = I[hi];
+                const bool b_first = pair_before<IDX_DESC>(kb, ib, ka, ia);
+                if (up ? b_first : !b_first) {
+                    K[lo] = kb; K[hi] = ka;
+                    I[lo] = ib; I[hi] = ia;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- libstdc++ std::sort, replayed by ONE thread on (K, I) in their original order ---------------------
+struct StdSortEmu {
+    float* K;
+    int* I;
+    __device__ __forceinline__ bool lt(int a, int b) const { return key_before(K[a], K[b]); }
+    __device__ __forceinline__ void swp(int a, int b) {
+        const float k = K[a]; K[a] = K[b]; K[b] = k;
+        const int i = I[a]; I[a] = I[b]; I[b] = i;
+    }
+    __device__ void unguarded_linear_insert(int last) {
+        const float vk = K[last];
+        const int vi = I[last];
+        int next = last - 1;
+        while (key_before(vk, K[next])) {
+            K[last] = K[next]; I[last] = I[next];
+            last = next;
+            --next;
+        }
+        K[last] = vk; I[last] = vi;
+    }
+    __device__ void insertion_sort(int first, int last) {
+        if (first == last) return;
+        for (int i = first + 1; i != last; ++i) {
+            if (lt(i, first)) {
+                const float vk = K[i];
+                const int vi = I[i];
+                for (int j = i; j > first; --j) { K[j] = K[j - 1]; I[j] = I[j - 1]; }
+                K[first] = vk; I[first] = vi;
+            } else {
+                unguarded_linear_insert(i);
+            }
+        }
+    }
+    __device__ void adjust_heap(int first, int hole, int len, float vk, int vi) {
+        const int top = hole;
+        int child = hole;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (lt(first + child, first + child - 1)) --child;
+            K[first + hole] = K[first + child]; I[first + hole] = I[first + child];
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            K[first + hole] = K[first + child - 1]; I[first + hole] = I[first + child - 1];
+            hole = child - 1;
+        }
+        int parent = (hole - 1) / 2;                              // __push_heap
+        while (hole > top && key_before(K[first + parent], vk)) {
+            K[first + hole] = K[first + parent]; I[first + hole] = I[first + parent];
+            hole = parent;
+            parent = (hole - 1) / 2;
+        }
+        K[first + hole] = vk; I[first + hole] = vi;
+    }
+    __device__ void heap_sort(int first, int last) {              // __partial_sort(first, last, last)
+        const int len = last - first;
+        if (len >= 2) {
+            for (int parent = (len - 2) / 2;; --parent) {         // __make_heap
+                adjust_heap(first, parent, len, K[first + parent], I[first + parent]);
+                if (parent == 0) break;
+            }
+        }
+        for (int end = last; end - first > 1;) {                  // __sort_heap
+            --end;
+            const float vk = K[end];
+            const int vi = I[end];
+            K[end] = K[first]; I[end] = I[first];
+            adjust_heap(first, 0, end - first, vk, vi);
+        }
+    }
+    __device__ int partition_pivot(int first, int last) {         // __unguarded_partition_pivot
+        const int mid = first + (last - first) / 2;
+        const int a = first + 1, b = mid, c = last - 1;           // __move_median_to_first(first, a, b, c)
+        if (lt(a, b)) {
+            if (lt(b, c)) swp(first, b);
+            else if (lt(a, c)) swp(first, c);
+            else swp(first, a);
+        } else if (lt(a, c)) swp(first, a);
+        else if (lt(b, c)) swp(first, c);
+        else swp(first, b);
+        int lo = first + 1, hi = last;                            // __unguarded_partition(first + 1, last, first)
+        for (;;) {
+            while (lt(lo, first)) ++lo;
+            --hi;
+            while (lt(first, hi)) --hi;
+            if (!(lo < hi)) return lo;
+            swp(lo, hi);
+            ++lo;
+        }
+    }
+    __device__ void sort(int n) {
+        if (n <= 1) return;
+        int depth0 = 0;
+        for (int t = n; t > 1; t >>= 1) ++depth0;                 // __lg(n)
+        depth0 *= 2;
+        // __introsort_loop with an explicit stack (sub-ranges are disjoint, so their order is immaterial)
+        int stk_first[48], stk_last[48], stk_depth[48];
+        int sp = 0;
+        stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = depth0; sp = 1;
+        while (sp > 0) {
+            --sp;
+            const int first = stk_first[sp];
+            int last = stk_last[sp], depth = stk_depth[sp];
+            while (last - first > 16) {
+                if (depth == 0) {
+                    heap_sort(first, last);
+                    break;
+                }
+                --depth;
+                const int cut = partition_pivot(first, last);
+                stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
+                last = cut;
+            }
+        }
+        if (n > 16) {                                             // __final_insertion_sort
+            insertion_sort(0, 16);
+            for (int i = 16; i < n; ++i) unguarded_linear_insert(i);
+        } else {
+            insertion_sort(0, n);
+        }
+    }
+};
+
+// Sort one slate.  On entry K[0..n) holds the keys in original order.  On exit K/I[0..n) hold the sorted
+// keys and the permutation (I[r] = original index of the doc at rank r).  K, I: `len` = next_pow2(n)
+// shared-memory entries each; K0 (n floats) is scratch that keeps the original keys for the replay.
+// Only ties among the first `tie_limit` sorted entries trigger the replay (callers whose trailing entries
+// are -inf padding that no output depends on pass the number of real docs).
+__device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int n, int len, int tie_rule,
+                                                int tie_limit = 1 << 30) {
+    const float ninf = __int_as_float(0xff800000);
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        if (i < n) K0[i] = K[i];
+        else K[i] = ninf;
+        I[i] = i;                                                 // sentinels: -inf with index >= n, i.e. last
+    }
+    __syncthreads();
+    if (tie_rule == TIES_REVERSED) {
+        // sentinels must stay last among -inf keys although indices now sort descending
+        for (int i = n + threadIdx.x; i < len; i += blockDim.x) I[i] = -1 - i;
+        block_bitonic_pairs<true>(K, I, len);
+    } else {
+        block_bitonic_pairs<false>(K, I, len);
+    }
+    if (tie_rule != TIES_STDSORT || n <= 16) return;
+    int tie = 0;
+    const int lim = tie_limit < n ? tie_limit : n;
+    for (int i = threadIdx.x; i + 1 < lim; i += blockDim.x) tie |= key_equiv(K[i], K[i + 1]) ? 1 : 0;
+    if (!__syncthreads_or(tie)) return;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n; ++i) { K[i] = K0[i]; I[i] = i; }
+        StdSortEmu emu{K, I};
+        emu.sort(n);
+    }
+    __syncthreads();
+}
+
+}  // namespace ltr

@@ -1,1 +1,1 @@
-from ltr_b200.losses.approxNDCG import approxNDCGLoss  # noqa: F401
+from ltr_b200.losses.approxNDCG import *  # noqa: F401,F403

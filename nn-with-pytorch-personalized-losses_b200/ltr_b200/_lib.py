@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libltr_b200.so")
 
-WORKSPACE_BYTES = 4096
+WORKSPACE_BYTES = 131072
 
 _P = c_void_p
 _SIGNATURES = {
@@ -24,6 +24,19 @@ _SIGNATURES = {
     "ltr_approx_ndcg_host_scratch_bytes": (c_size_t, [c_int, c_int]),
     "ltr_approx_ndcg_fwdbwd_host": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P,
                                             c_size_t, _P, _P]),
+    "ltr_listnet_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "ltr_ordinal_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "ltr_sort_desc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    "ltr_ndcg_at_k": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P]),
+    "ltr_ndcg_at_k_f64": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, c_int, c_double, _P, _P, _P]),
+    "ltr_exact_ndcg": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "ltr_order_score_fwdbwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "ltr_lambda_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, c_int,
+                                  _P, _P, _P, _P, _P, _P]),
+    "ltr_risk_listnet_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "ltr_risk_listnet_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
+                               _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
     "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
 }

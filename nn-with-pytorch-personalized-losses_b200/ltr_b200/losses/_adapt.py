@@ -20,3 +20,13 @@ def to_device(t: torch.Tensor) -> torch.Tensor:
 
 def back_to(loss: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
     return loss if like.device.type == "cuda" else loss.to(like.device)
+
+
+def to_device_2d(t: torch.Tensor) -> torch.Tensor:
+    """[B, n] view for the row kernels; a trailing singleton dim (the rankers emit [B, n, 1]) is dropped."""
+    t = to_device(t)
+    if t.dim() == 3 and t.shape[2] == 1:
+        t = t.squeeze(2)
+    if t.dim() != 2:
+        raise ValueError(f"expected a [batch, slate] tensor, got shape {tuple(t.shape)}")
+    return t.contiguous()

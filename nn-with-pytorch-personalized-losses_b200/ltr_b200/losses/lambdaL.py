@@ -1,0 +1,55 @@
+"""LambdaLoss framework -- drop-in for reference losses/lambdaL.py:67-93 (lambdaLoss; same name, argument
+order, defaults and exceptions), computed by the fused sm_100a kernel `ltr_lambda_fwdbwd`."""
+from __future__ import annotations
+
+from .. import ops
+from ._adapt import back_to, to_device
+
+PADDED_Y_VALUE = -1
+DEFAULT_EPS = 1e-10
+
+
+def _scheme_id(weighing_scheme):
+    if weighing_scheme is None:
+        return 0
+    name = weighing_scheme if isinstance(weighing_scheme, str) else getattr(weighing_scheme, "__name__", weighing_scheme)
+    if name not in ops.LAMBDA_SCHEMES:
+        raise KeyError(name)             # the reference resolves the name with globals()[...] (lambdaL.py:46)
+    return ops.LAMBDA_SCHEMES[name]
+
+
+def lambdaLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, weighing_scheme=None, k=None,
+               sigma=1., mu=10., reduction="sum", reduction_log="binary"):
+    """
+    LambdaLoss framework for LTR losses implementations, introduced in "The LambdaLoss Framework for Ranking
+    Metric Optimization".  Contains implementations of different weighing schemes corresponding to e.g.
+    LambdaRank or RankNet.
+    :param y_pred: predictions from the model, shape [batch_size, slate_length]
+    :param y_true: ground truth labels, shape [batch_size, slate_length]
+    :param eps: epsilon value, used for numerical stability
+    :param padded_value_indicator: an indicator of the y_true index containing a padded item, e.g. -1
+    :param weighing_scheme: a string corresponding to a name of one of the weighing schemes
+    :param k: rank at which the loss is truncated
+    :param sigma: score difference weight used in the sigmoid function
+    :param mu: optional weight used in NDCGLoss2++ weighing scheme
+    :param reduction: losses reduction method, could be either a sum or a mean
+    :param reduction_log: logarithm variant used prior to masking and loss reduction, either binary or natural
+    :return: loss value, a torch.Tensor
+    """
+    scheme = _scheme_id(weighing_scheme)
+    if reduction_log not in ("natural", "binary"):
+        raise ValueError("Reduction logarithm base can be either natural or binary")      # lambdaL.py:57
+    if reduction not in ("sum", "mean"):
+        raise ValueError("Reduction method can be either sum or mean")                    # lambdaL.py:91
+    loss = ops.lambda_loss(to_device(y_pred), to_device(y_true.detach()), eps, float(padded_value_indicator), scheme,
+                           0 if k is None else int(k), sigma, mu, reduction == "mean", reduction_log == "natural")
+    return back_to(loss, y_pred)
+
+
+# names of the weighing schemes, importable like the reference's functions (they are selected by name)
+def ndcgLoss1_scheme(*_a, **_k):
+    raise NotImplementedError("weighing schemes are evaluated inside the fused kernel; pass the name to lambdaLoss")
+
+
+ndcgLoss2_scheme = lamdbaRank_scheme = ndcgLoss2PP_scheme = rankNet_scheme = ndcgLoss1_scheme
+rankNetWeightedByGTDiff_scheme = rankNetWeightedByGTDiffPowed_scheme = ndcgLoss1_scheme

@@ -1,13 +1,41 @@
-"""autograd Functions over the C-ABI: forward computes the loss AND stashes d loss / d y_pred
-(the kernels are fused fwd+bwd); backward only scales the stash by grad_output, so it survives
-`backward(retain_graph=True)` as the reference drivers call it (main_batch_execution.py:170)."""
+"""autograd Functions over the C-ABI (include/ltr_b200.h).
+
+Every kernel is fused forward+backward: `forward` computes the loss AND stashes d loss / d y_pred;
+`backward` only scales the stash by grad_output, so it survives `backward(retain_graph=True)` as
+the reference drivers call it (main_batch_execution.py:170).  PyTorch provides device memory, the
+current stream and (for query-sharded GeoRisk) the NCCL collectives; all arithmetic of the path
+happens in libltr_b200.so.  There is no CPU fallback anywhere in this module.
+"""
 from __future__ import annotations
 
+import ctypes
+
+import numpy as np
 import torch
 
 from . import _lib, _runtime as rt
 
+TIES_STABLE, TIES_STDSORT, TIES_REVERSED = 0, 1, 2
 
+LAMBDA_SCHEMES = {
+    None: 0,
+    "rankNet_scheme": 0,
+    "ndcgLoss1_scheme": 1,
+    "ndcgLoss2_scheme": 2,
+    "lamdbaRank_scheme": 3,      # [sic] the reference's spelling (losses/lambdaL.py:109)
+    "ndcgLoss2PP_scheme": 4,
+    "rankNetWeightedByGTDiff_scheme": 5,
+    "rankNetWeightedByGTDiffPowed_scheme": 6,
+}
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# approxNDCG                                                           losses/approxNDCG.py:7-53
+# ------------------------------------------------------------------------------------------------
 class _ApproxNDCG(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y_pred, y_true, eps, pad, alpha):
@@ -22,7 +50,7 @@ class _ApproxNDCG(torch.autograd.Function):
         _lib.check(lib.ltr_approx_ndcg_fwdbwd(
             y_pred.data_ptr(), y_true.data_ptr(), B, n, float(alpha), float(eps), float(pad),
             tab.data_ptr(), tab.numel(), slate.data_ptr(), loss.data_ptr(),
-            grad.data_ptr() if need_grad else None, rt.workspace(dev).data_ptr(), rt.stream_ptr()),
+            _ptr(grad), rt.workspace(dev).data_ptr(), rt.stream_ptr()),
             "ltr_approx_ndcg_fwdbwd")
         ctx.grad = grad
         ctx.slate_ndcg = slate
@@ -37,3 +65,271 @@ class _ApproxNDCG(torch.autograd.Function):
 def approx_ndcg(y_pred, y_true, eps=1e-10, pad=-1.0, alpha=1.0):
     """Device entry: y_pred/y_true are CUDA fp32 contiguous [B, n]."""
     return _ApproxNDCG.apply(y_pred, y_true, eps, pad, alpha)
+
+
+# ------------------------------------------------------------------------------------------------
+# ListNet                                                                 losses/listnet.py:5-16
+# ------------------------------------------------------------------------------------------------
+class _ListNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, apply_sigmoid):
+        lib = _lib.load()
+        B, n = y_pred.shape
+        dev = y_pred.device
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(y_pred) if need_grad else None
+        _lib.check(lib.ltr_listnet_fwdbwd(y_true.data_ptr(), y_pred.data_ptr(), B, n, int(bool(apply_sigmoid)), None,
+                                          loss.data_ptr(), _ptr(grad), rt.workspace(dev).data_ptr(), rt.stream_ptr()),
+                   "ltr_listnet_fwdbwd")
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (ctx.grad * grad_out if ctx.grad is not None else None), None, None
+
+
+def listnet(y_true, y_pred, apply_sigmoid=False):
+    return _ListNet.apply(y_pred, y_true, apply_sigmoid)
+
+
+# ------------------------------------------------------------------------------------------------
+# ordinal                                                                 losses/ordinal.py:27-53
+# ------------------------------------------------------------------------------------------------
+class _Ordinal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, levels, pad):
+        lib = _lib.load()
+        B, n, L = y_pred.shape
+        dev = y_pred.device
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(y_pred) if need_grad else None
+        _lib.check(lib.ltr_ordinal_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, L, float(pad), loss.data_ptr(),
+                                          _ptr(grad), rt.workspace(dev).data_ptr(), rt.stream_ptr()),
+                   "ltr_ordinal_fwdbwd")
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (ctx.grad * grad_out if ctx.grad is not None else None), None, None, None
+
+
+def ordinal(y_pred, y_true, levels, pad=-1.0):
+    return _Ordinal.apply(y_pred, y_true, levels, pad)
+
+
+# ------------------------------------------------------------------------------------------------
+# LambdaLoss                                                            losses/lambdaL.py:67-93
+# ------------------------------------------------------------------------------------------------
+class _Lambda(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural):
+        lib = _lib.load()
+        B, n = y_pred.shape
+        dev = y_pred.device
+        need_grad = ctx.needs_input_grad[0]
+        sums = torch.empty(2, B, dtype=torch.float32, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(y_pred) if need_grad else None
+        _lib.check(lib.ltr_lambda_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, float(eps), float(pad), int(scheme),
+                                         int(k), float(sigma), float(mu), int(mean), int(natural), sums[0].data_ptr(),
+                                         sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), _ptr(grad),
+                                         rt.stream_ptr()), "ltr_lambda_fwdbwd")
+        ctx.grad = grad
+        ctx.slate_sums = sums
+        return out[0].reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 9
+
+
+def lambda_loss(y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural):
+    return _Lambda.apply(y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural)
+
+
+# ------------------------------------------------------------------------------------------------
+# orderScore / exactNDCG                              losses/orderScore.py:5-24, exactNDCG.py:5-29
+# ------------------------------------------------------------------------------------------------
+class _OrderScore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true):
+        lib = _lib.load()
+        B, n = y_pred.shape
+        dev = y_pred.device
+        need_grad = ctx.needs_input_grad[0]
+        slate = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(y_pred) if need_grad else None
+        _lib.check(lib.ltr_order_score_fwdbwd(y_true.data_ptr(), y_pred.data_ptr(), B, n, slate.data_ptr(),
+                                              loss.data_ptr(), _ptr(grad), rt.stream_ptr()), "ltr_order_score_fwdbwd")
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (ctx.grad * grad_out if ctx.grad is not None else None), None
+
+
+def order_score(y_true, y_pred):
+    return _OrderScore.apply(y_pred, y_true)
+
+
+def exact_ndcg(y_true, y_pred):
+    """Forward only: the reference's ndcgLoss gives y_pred no gradient (exactNDCG.py:7 'not differentiable')."""
+    lib = _lib.load()
+    B, n = y_pred.shape
+    dev = y_pred.device
+    slate = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    _lib.check(lib.ltr_exact_ndcg(y_true.data_ptr(), y_pred.data_ptr(), B, n, slate.data_ptr(), loss.data_ptr(),
+                                  rt.stream_ptr()), "ltr_exact_ndcg")
+    return loss.reshape(())
+
+
+# ------------------------------------------------------------------------------------------------
+# sorting and NDCG@k                                                     utils/metrics.py:48-104
+# ------------------------------------------------------------------------------------------------
+def sort_desc(keys, tie_rule=TIES_STDSORT, want_values=True):
+    """[B, n] CUDA fp32 -> (sorted values or None, int32 permutation) with the reference's tie order."""
+    lib = _lib.load()
+    B, n = keys.shape
+    perm = torch.empty(B, n, dtype=torch.int32, device=keys.device)
+    vals = torch.empty_like(keys) if want_values else None
+    _lib.check(lib.ltr_sort_desc(keys.data_ptr(), B, n, int(tie_rule), perm.data_ptr(), _ptr(vals), rt.stream_ptr()),
+               "ltr_sort_desc")
+    return vals, perm
+
+
+_disc_cache = {}
+
+
+def _disc_tables(n, device):
+    """disc32[r] = float32(np.log2(2 + r)) and disc64[r] = np.log2(2 + r): bit-for-bit the reference's divisors
+    (metrics.py:65 and :91, where the fp32 tensor is divided by the numpy scalar rounded to fp32)."""
+    key = (n, device.index)
+    if key not in _disc_cache:
+        d64 = np.log2(np.arange(n, dtype=np.float64) + 2.0)
+        _disc_cache[key] = (torch.from_numpy(d64.astype(np.float32)).to(device), torch.from_numpy(d64).to(device))
+    return _disc_cache[key]
+
+
+def _ks_array(ks):
+    arr = (ctypes.c_int * len(ks))(*[int(k) if k is not None else 0 for k in ks])
+    return arr
+
+
+def ndcg_at_k(y_true, y_pred, ks, tie_rule=TIES_STDSORT):
+    """torchNdcg arithmetic (fp32, gains 2^l - 1).  Returns [Q, len(ks)] fp32 on the device (NaN for 0/0)."""
+    lib = _lib.load()
+    Q, n = y_pred.shape
+    d32, _ = _disc_tables(n, y_pred.device)
+    out = torch.empty(Q, len(ks), dtype=torch.float32, device=y_pred.device)
+    _lib.check(lib.ltr_ndcg_at_k(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
+                                 d32.data_ptr(), out.data_ptr(), rt.stream_ptr()), "ltr_ndcg_at_k")
+    return out
+
+
+def ndcg_at_k_f64(y_true, y_pred, ks, tie_rule=TIES_STABLE, exponential=False, empty_value=1.0):
+    """metrics.dcg/ndcg arithmetic (fp64).  Returns [Q, len(ks)] fp64 on the device."""
+    lib = _lib.load()
+    Q, n = y_pred.shape
+    _, d64 = _disc_tables(n, y_pred.device)
+    out = torch.empty(Q, len(ks), dtype=torch.float64, device=y_pred.device)
+    _lib.check(lib.ltr_ndcg_at_k_f64(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
+                                     int(bool(exponential)), float(empty_value), d64.data_ptr(), out.data_ptr(),
+                                     rt.stream_ptr()), "ltr_ndcg_at_k_f64")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# risk functions and the ListNet-style risk losses       losses/riskLosses/riskFunctions.py, riskLosses.py
+# ------------------------------------------------------------------------------------------------
+KIND_Z, KIND_GEO, KIND_T = 0, 1, 2
+
+
+def _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, want_gq, want_gmat, group=None):
+    """Runs the three phases of ltr_risk_phase on the local rows `mat` [Q, C]; with a process group the
+    16-double state blocks are all-reduced between the phases (NCCL on the current stream): MAX for the
+    matrix-wide max, SUM for everything else.  Returns (loss[1], gq[Q] or None, gmat[Q, C] or None)."""
+    lib = _lib.load()
+    Q, C = mat.shape
+    dev = mat.device
+    state = torch.zeros(2, 16, dtype=torch.float64, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    gq = torch.empty(Q, dtype=torch.float32, device=dev) if want_gq else None
+    gmat = torch.empty(Q, C, dtype=torch.float32, device=dev) if want_gmat else None
+    sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+
+    def phase(i):
+        _lib.check(lib.ltr_risk_phase(i, mat.data_ptr(), Q, C, int(kind), int(invert), int(strategy), int(quirk),
+                                      float(alpha), float(negative), state[0].data_ptr(), state[1].data_ptr(),
+                                      loss.data_ptr(), _ptr(gq), _ptr(gmat), rt.stream_ptr()), "ltr_risk_phase")
+
+    phase(1)
+    if sharded:
+        torch.distributed.all_reduce(state[0, 0:1], op=torch.distributed.ReduceOp.MAX, group=group)
+        torch.distributed.all_reduce(state[0, 1:5], op=torch.distributed.ReduceOp.SUM, group=group)
+    phase(2)
+    if sharded:
+        torch.distributed.all_reduce(state[1], op=torch.distributed.ReduceOp.SUM, group=group)
+    phase(3)
+    return loss, gq, gmat
+
+
+class _RiskFn(torch.autograd.Function):
+    """zRisk / geoRisk of column 0 of `mat` (callers permute the requested column to the front)."""
+
+    @staticmethod
+    def forward(ctx, mat, kind, alpha):
+        need = ctx.needs_input_grad[0]
+        loss, _, gmat = _risk_phases(mat, kind, 0, 1, 0, alpha, 1.0, False, need)
+        ctx.gmat = gmat
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (ctx.gmat * grad_out if ctx.gmat is not None else None), None, None
+
+
+def risk_fn(mat, kind, alpha):
+    return _RiskFn.apply(mat, kind, alpha)
+
+
+class _RiskListnet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk, group):
+        lib = _lib.load()
+        B, n = y_pred.shape
+        dev = y_pred.device
+        S = 0 if y_base is None else y_base.shape[2]
+        tvar = 1 if kind == KIND_T else 0
+        C = 1 + S + (1 if add_ideal else 0)
+        mat = torch.empty(B, C, dtype=torch.float32, device=dev)
+        _lib.check(lib.ltr_risk_listnet_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
+                                             int(bool(add_ideal)), tvar, mat.data_ptr(), rt.stream_ptr()),
+                   "ltr_risk_listnet_rows")
+        # mat <- max(mat) - mat: riskLosses.py:49-50 (lt 1, 3) and :274-275 (t-risk: lt 1 only)
+        invert = (lt == 1) if kind == KIND_T else (lt in (1, 3))
+        need = ctx.needs_input_grad[0]
+        loss, gq, _ = _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, need, False, group)
+        grad = None
+        if need:
+            grad = torch.empty_like(y_pred)
+            _lib.check(lib.ltr_risk_listnet_rows_bwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, int(lt), tvar,
+                                                     gq.data_ptr(), grad.data_ptr(), rt.stream_ptr()),
+                       "ltr_risk_listnet_rows_bwd")
+        ctx.grad = grad
+        ctx.mat = mat
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 10
+
+
+def risk_listnet(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk=False, group=None):
+    return _RiskListnet.apply(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk, group)

@@ -1,0 +1,326 @@
+"""Every remaining hot-path callable: CUDA path (through the C-ABI and the drop-in callables) vs the golden
+vectors generated from the unmodified reference, and vs the oracle on larger seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from ltr_testing import assert_grad_close, assert_loss_close, make_slates
+
+pytestmark = pytest.mark.gpu
+G = golden()
+
+
+def _fns():
+    from ltr_b200.losses.exactNDCG import ndcgLoss
+    from ltr_b200.losses.lambdaL import lambdaLoss
+    from ltr_b200.losses.listnet import listnetLoss
+    from ltr_b200.losses.orderScore import orderScoreLoss
+    from ltr_b200.losses.ordinal import ordinalLoss
+    from ltr_b200.losses.riskLosses import riskLosses as RL
+    return {
+        "lambdaLoss": (lambdaLoss, ("y_pred", "y_true")),
+        "listnetLoss": (listnetLoss, ("y_true", "y_pred")),
+        "orderScoreLoss": (orderScoreLoss, ("y_true", "y_pred")),
+        "ndcgLoss": (ndcgLoss, ("y_true", "y_pred")),
+        "ordinalLoss": (ordinalLoss, ("y_pred", "y_true")),
+        "geoRiskListnetLoss": (RL.geoRiskListnetLoss, ("y_pred", "y_true", "y_baselines")),
+        "zRiskListnetLoss": (RL.zRiskListnetLoss, ("y_pred", "y_true", "y_baselines")),
+        "tRiskListnetLoss": (RL.tRiskListnetLoss, ("y_pred", "y_true", "y_baselines")),
+    }
+
+
+def _oracle_fns():
+    from oracle import ltr_oracle as O
+    return {
+        "lambdaLoss": O.lambda_loss, "listnetLoss": O.listnet_loss, "orderScoreLoss": O.order_score_loss,
+        "ndcgLoss": O.ndcg_loss, "ordinalLoss": O.ordinal_loss, "geoRiskListnetLoss": O.geo_risk_listnet_loss,
+        "zRiskListnetLoss": O.z_risk_listnet_loss, "tRiskListnetLoss": O.t_risk_listnet_loss,
+    }
+
+
+LOSS_FNS = ("lambdaLoss", "listnetLoss", "orderScoreLoss", "ndcgLoss", "ordinalLoss", "geoRiskListnetLoss",
+            "zRiskListnetLoss", "tRiskListnetLoss")
+CASES = [n for n, c in G.cases.items() if c["fn"] in LOSS_FNS]
+
+
+def _run(fn_name, tensors, kwargs, device="cuda"):
+    fn, order = _fns()[fn_name]
+    leaf = {k: torch.as_tensor(v).clone().to(device).requires_grad_(k == "y_pred") for k, v in tensors.items()}
+    out = fn(*[leaf[k] for k in order if k in leaf], **kwargs)
+    grad = None
+    if out is not None and out.requires_grad:
+        out.sum().backward()
+        grad = leaf["y_pred"].grad.cpu().numpy()
+    return (None if out is None else out.detach().cpu().numpy()), grad
+
+
+def _run_oracle(fn_name, tensors, kwargs, dtype=torch.float32):
+    fn = _oracle_fns()[fn_name]
+    _, order = _fns()[fn_name]
+    leaf = {k: torch.as_tensor(v).clone().to(dtype).requires_grad_(k == "y_pred") for k, v in tensors.items()}
+    out = fn(*[leaf[k] for k in order if k in leaf], **kwargs)
+    grad = None
+    if out.requires_grad:
+        out.sum().backward()
+        grad = leaf["y_pred"].grad.numpy()
+    return out.detach().numpy(), grad
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden(name):
+    case = G.cases[name]
+    ins = G.inputs(name)
+    out, grad = _run(case["fn"], ins, G.kwargs(name))
+    ref = G.out(name)
+    assert tuple(out.shape) == tuple(ref.shape), "return shape (0-dim vs [1]) must match the reference"
+    assert_loss_close(out, ref, atol=2e-6)
+    if G.has_grad(name, "y_pred"):
+        gref = G.grad(name, "y_pred")
+        g64 = None
+        if case["fn"] == "lambdaLoss":
+            _, g64 = _run_oracle(case["fn"], ins, G.kwargs(name), dtype=torch.float64)
+        assert_grad_close(grad, gref, ref64=g64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# larger seeded inputs against the oracle
+# ---------------------------------------------------------------------------------------------------
+def _check(fn_name, tensors, kwargs, f64_slack=False, **tol):
+    out, grad = _run(fn_name, tensors, kwargs)
+    rout, rgrad = _run_oracle(fn_name, tensors, kwargs)
+    assert tuple(out.shape) == tuple(rout.shape)
+    o64, g64 = _run_oracle(fn_name, tensors, kwargs, dtype=torch.float64) if f64_slack else (None, None)
+    assert_loss_close(out, rout, ref64=o64, **tol)
+    if rgrad is not None:
+        assert_grad_close(grad, rgrad, ref64=g64)
+
+
+@pytest.mark.parametrize("B,n", [(64, 128), (7, 100), (3, 1000), (1, 37), (300, 5)])
+@pytest.mark.parametrize("sig", [False, True])
+def test_listnet_vs_oracle(B, n, sig):
+    s, y = make_slates(B, n, seed=B + n)
+    _check("listnetLoss", {"y_true": y, "y_pred": s}, {"apply_sigmoid": sig})
+
+
+def test_listnet_full_size_properties():
+    """BASELINE config 1 shape at 65,536 slates: the batch loss is the sum of the slate losses, gradient rows sum to 0,
+    a 512-slate sample agrees with the oracle."""
+    from ltr_b200.losses.listnet import listnetLoss
+    B, n = 65536, 128
+    s, y = make_slates(B, n, seed=5)
+    sd = s.cuda().requires_grad_(True)
+    yd = y.cuda()
+    loss = listnetLoss(yd, sd)
+    loss.backward()
+    assert torch.equal(loss, listnetLoss(yd, sd.detach())), "batch sum must be bitwise reproducible"
+    assert float(sd.grad.sum(dim=1).abs().max()) < 1e-5          # softmax(s) - softmax(y) sums to 0 per slate
+    parts = sum(float(listnetLoss(yd[i:i + 8192], sd.detach()[i:i + 8192])) for i in range(0, B, 8192))
+    assert abs(parts - float(loss)) <= 1e-5 * abs(float(loss))
+    _check("listnetLoss", {"y_true": y[1000:1512], "y_pred": s[1000:1512]}, {})
+
+
+SCHEMES = [None, "ndcgLoss1_scheme", "ndcgLoss2_scheme", "lamdbaRank_scheme", "ndcgLoss2PP_scheme", "rankNet_scheme",
+           "rankNetWeightedByGTDiff_scheme", "rankNetWeightedByGTDiffPowed_scheme"]
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_lambda_schemes_vs_oracle(scheme):
+    s, y = make_slates(12, 64, seed=21, min_len=20, pad_anywhere=True)
+    _check("lambdaLoss", {"y_pred": s, "y_true": y}, {"weighing_scheme": scheme}, f64_slack=True)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(weighing_scheme="ndcgLoss2PP_scheme", k=10),
+    dict(weighing_scheme="ndcgLoss2PP_scheme", reduction="mean", reduction_log="natural"),
+    dict(weighing_scheme="ndcgLoss1_scheme", k=5, sigma=2.0),
+    dict(weighing_scheme="lamdbaRank_scheme", mu=3.0, sigma=0.5, reduction="mean"),
+    dict(weighing_scheme=None, eps=1e-4),
+])
+def test_lambda_options_vs_oracle(kw):
+    s, y = make_slates(9, 50, seed=33, min_len=10)
+    _check("lambdaLoss", {"y_pred": s, "y_true": y}, kw, f64_slack=True)
+
+
+def test_lambda_config3_shape_and_ties():
+    """BASELINE config 3 shape (256-doc slates, ndcgLoss2PP) on a sample, plus a tie-heavy set where the rank
+    positions depend on torch.sort's tie order (up to 1.3e-2 relative if the order were different)."""
+    s, y = make_slates(16, 256, seed=2020, min_len=128)
+    _check("lambdaLoss", {"y_pred": s, "y_true": y}, {"weighing_scheme": "ndcgLoss2PP_scheme"}, f64_slack=True)
+    s, y = make_slates(16, 100, seed=8, min_len=40, ties=True)
+    for scheme in ("ndcgLoss2PP_scheme", "lamdbaRank_scheme", "ndcgLoss1_scheme"):
+        _check("lambdaLoss", {"y_pred": s, "y_true": y}, {"weighing_scheme": scheme}, f64_slack=True)
+
+
+def test_lambda_errors():
+    from ltr_b200.losses.lambdaL import lambdaLoss
+    s, y = make_slates(2, 8, seed=1)
+    with pytest.raises(KeyError):
+        lambdaLoss(s.cuda(), y.cuda(), weighing_scheme="noSuch_scheme")
+    with pytest.raises(ValueError):
+        lambdaLoss(s.cuda(), y.cuda(), reduction_log="decimal")
+    with pytest.raises(ValueError):
+        lambdaLoss(s.cuda(), y.cuda(), reduction="median")
+
+
+@pytest.mark.parametrize("B,n", [(16, 12), (8, 40), (5, 128), (3, 300)])
+def test_order_score_and_exact_ndcg_vs_oracle(B, n):
+    s, y = make_slates(B, n, seed=n)
+    _check("orderScoreLoss", {"y_true": y, "y_pred": s}, {})
+    _check("ndcgLoss", {"y_true": y, "y_pred": s}, {})
+    st, _ = make_slates(B, n, seed=n + 1, ties=True)               # tied predictions: argsort tie order matters
+    _check("ndcgLoss", {"y_true": y, "y_pred": st}, {})
+
+
+def test_ordinal_vs_oracle_and_padding_error():
+    from ltr_b200.losses.ordinal import ordinalLoss
+    g = torch.Generator().manual_seed(4)
+    y = torch.randint(0, 5, (6, 30), generator=g).float()
+    p = torch.rand(6, 30, 4, generator=g) * 0.98 + 0.01
+    _check("ordinalLoss", {"y_pred": p, "y_true": y}, {"n": 4})
+    y[0, 3] = -1.0
+    with pytest.raises(ValueError):
+        ordinalLoss(p.cuda(), y.cuda(), 4)
+
+
+@pytest.mark.parametrize("fn", ["geoRiskListnetLoss", "zRiskListnetLoss"])
+@pytest.mark.parametrize("lt", [1, 2, 3])
+@pytest.mark.parametrize("rs", [1, 2, 3])
+def test_risk_listnet_vs_oracle(fn, lt, rs):
+    g = torch.Generator().manual_seed(10 * lt + rs)
+    B, n, S = 96, 128, 2
+    s = torch.randn(B, n, generator=g)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    base = torch.randn(B, n, S, generator=g)
+    for ideal in (1, 2):
+        _check(fn, {"y_pred": s, "y_true": y, "y_baselines": base},
+               dict(listnet_transformation=lt, return_strategy=rs, add_ideal_ranking_to_mat=ideal), atol=1e-6,
+               f64_slack=True)
+
+
+@pytest.mark.parametrize("lt", [1, 2, 3])
+def test_trisk_listnet_vs_oracle(lt):
+    g = torch.Generator().manual_seed(lt)
+    B, n = 64, 100
+    s = torch.randn(B, n, generator=g)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    base = torch.randn(B, n, generator=g)
+    _check("tRiskListnetLoss", {"y_pred": s, "y_true": y, "y_baselines": base}, dict(listnet_transformation=lt), atol=1e-6)
+
+
+def test_risk_misc_semantics():
+    from ltr_b200.losses.riskLosses import riskLosses as RL
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(8, 16, generator=g).cuda()
+    y = torch.randint(0, 5, (8, 16), generator=g).float().cuda()
+    assert RL.geoRiskListnetLoss(s, y, None, return_strategy=7, add_ideal_ranking_to_mat=2) is None   # riskLosses.py:60
+    with pytest.raises(UnboundLocalError):
+        RL.geoRiskListnetLoss(s, y, None, listnet_transformation=4)
+    out = RL.geoRiskListnetLoss(s, y, None, add_ideal_ranking_to_mat=2, negative=-1)
+    assert out.shape == (1,)
+
+
+# ---------------------------------------------------------------------------------------------------
+# risk functions, sorting, NDCG evaluation
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.names("georisk_fn/") + G.names("zrisk_fn/"))
+def test_risk_functions_golden(name):
+    from ltr_b200.losses.riskLosses.riskFunctions import geoRisk, zRisk
+    fn = geoRisk if G.cases[name]["fn"] == "geoRisk" else zRisk
+    mat = torch.from_numpy(G.inputs(name)["mat"]).cuda()
+    out = fn(mat, **G.kwargs(name))
+    assert tuple(out.shape) == tuple(G.out(name).shape)
+    assert_loss_close(out.cpu().numpy(), G.out(name), rtol=2e-6)
+
+
+def test_georisk_known_answer_and_gradient():
+    """reference tests/georiskTorchTest.py:5-12 -> 0.31438308416523303; gradient w.r.t. the whole matrix vs the oracle."""
+    from ltr_b200.losses.riskLosses.riskFunctions import geoRisk
+    from ltr_b200.utils.metrics import getGeoRiskDefault
+    from oracle import ltr_oracle as O
+    known = torch.from_numpy(G.inputs("georisk_fn/known5x8/i0")["mat"])
+    assert abs(float(geoRisk(known.cuda(), 3)) - 0.31438308416523303) < 1e-6
+    np.testing.assert_allclose(getGeoRiskDefault(known.numpy(), 3), G.out("georisk_default/known5x8"), rtol=1e-6)
+    for i in (0, 3, -1):
+        m = known.clone().cuda().requires_grad_(True)
+        geoRisk(m, 3, i=i).sum().backward()
+        mc = known.clone().requires_grad_(True)
+        O.geo_risk(mc, 3, i=i).sum().backward()
+        assert_grad_close(m.grad.cpu().numpy(), mc.grad.numpy())
+
+
+@pytest.mark.parametrize("name", G.names("sort/"))
+def test_sort_golden(name):
+    """torch.sort(descending=True) tie order (std::sort over (key, index)): permutations bit-exact."""
+    from ltr_b200 import ops
+    keys = torch.from_numpy(G.inputs(name)["keys"])
+    vals, perm = ops.sort_desc(keys.cuda(), ops.TIES_STDSORT)
+    ref_idx = G.out(name)
+    assert np.array_equal(perm.cpu().numpy().astype(np.int64), ref_idx.astype(np.int64))
+    assert np.array_equal(vals.cpu().numpy(), np.take_along_axis(keys.numpy(), ref_idx.astype(np.int64), axis=1))
+
+
+@pytest.mark.parametrize("n", [17, 31, 64, 100, 128, 200, 256, 500, 1024, 2000])
+def test_sort_vs_torch_cpu(n):
+    """Against torch's CPU sort on this box: heavy ties, -inf runs, NaNs, distinct keys; plus the other tie rules."""
+    from ltr_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    keys = torch.randint(0, 3, (24, n), generator=g).float()
+    keys[1] = torch.randn(n, generator=g)
+    keys[2, n // 3:] = float("-inf")
+    keys[3, ::7] = float("nan")
+    keys[4] = 1.0
+    keys[5] = torch.randint(0, n // 2, (n,), generator=g).float()
+    ref_vals, ref_idx = keys.sort(descending=True, dim=-1)
+    vals, perm = ops.sort_desc(keys.cuda(), ops.TIES_STDSORT)
+    assert np.array_equal(perm.cpu().numpy(), ref_idx.numpy().astype(np.int32))
+    assert np.array_equal(vals.cpu().numpy(), ref_vals.numpy(), equal_nan=True)
+    _, stable = ops.sort_desc(keys.cuda(), ops.TIES_STABLE)
+    ref_stable = keys.sort(descending=True, dim=-1, stable=True).indices
+    assert np.array_equal(stable.cpu().numpy(), ref_stable.numpy().astype(np.int32))
+    clean = torch.nan_to_num(keys, nan=5.0, neginf=-9.0)
+    _, rev = ops.sort_desc(clean.cuda(), ops.TIES_REVERSED)
+    ref_rev = np.argsort(clean.numpy(), axis=1, kind="stable")[:, ::-1]
+    assert np.array_equal(rev.cpu().numpy(), ref_rev.astype(np.int32))
+
+
+@pytest.mark.parametrize("name", G.names("torchndcg/"))
+def test_torch_ndcg_golden(name):
+    from ltr_b200.utils.metrics import torchNdcg
+    ins = G.inputs(name)
+    kw = G.kwargs(name)
+    out = torchNdcg(torch.from_numpy(ins["ys_true"]).cuda(), torch.from_numpy(ins["ys_pred"]).cuda(), **kw)
+    if kw.get("return_type") == "list":
+        assert isinstance(out, list)
+        out = torch.stack([o.reshape(()) for o in out])
+    np.testing.assert_allclose(out.cpu().numpy(), G.out(name), rtol=2e-6, atol=1e-7, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", G.names("mndcg/"))
+def test_mndcg_golden(name):
+    from ltr_b200.utils.metrics import mNdcg
+    ins = G.inputs(name)
+    out = mNdcg(ins["true"], ins["pred"], **G.kwargs(name))
+    assert isinstance(out, list) and isinstance(out[0], float)
+    np.testing.assert_allclose(np.asarray(out), G.out(name), rtol=1e-12, atol=1e-15)
+
+
+def test_ndcg_sweep_full_size():
+    """BASELINE config 5 evaluation shape (8192 queries x 1024 docs would take the oracle minutes; the sweep is
+    checked on a 64-query sample at n = 1024 and by properties at full size)."""
+    from ltr_b200.utils.metrics import ndcg_sweep
+    from oracle import ltr_oracle as O
+    s, y = make_slates(64, 1024, seed=77)
+    got = ndcg_sweep(y.cuda(), s.cuda(), ks=(1, 5, 10)).cpu().numpy()
+    for j, k in enumerate((1, 5, 10)):
+        ref = O.torch_ndcg(y, s, k=k, return_type="tensor").numpy()
+        np.testing.assert_allclose(np.nan_to_num(got[:, j]), ref, rtol=2e-6, atol=1e-7)
+    Q, n = 8192, 128
+    s, y = make_slates(Q, n, seed=78)
+    sd, yd = s.cuda(), y.cuda()
+    sweep = ndcg_sweep(yd, sd, ks=(1, 5, 10, None))
+    assert float(ndcg_sweep(yd, yd + 1e-3 * sd, ks=(10,)).min()) > 0.999999     # ranking by the labels is ideal
+    assert float(sweep.max()) <= 1.0 + 1e-6 and float(sweep.min()) >= 0.0
+    perm = torch.argsort(torch.rand(Q, n, device="cuda"), dim=1)                 # distinct scores: order-free
+    again = ndcg_sweep(yd.gather(1, perm), sd.gather(1, perm), ks=(1, 5, 10, None))
+    assert torch.allclose(sweep, again, rtol=1e-6, atol=1e-7)
