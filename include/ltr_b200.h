@@ -168,6 +168,32 @@ int ltr_risk_listnet_rows_bwd(const float* y_pred, const float* y_true, int B, i
                               const float* gq, float* grad, void* stream);
 
 /*
+ * Risk-sensitive losses, LambdaLoss family.   replaces losses/riskLosses/riskLosses.py:63-125, 183-244, 294-345
+ *
+ * ltr_risk_lambda_rows: per system, the column sums (over dim 1) of lambdaMask(softmax(scores), softmax(y_true),
+ *   weighing_scheme, return_losses=True) -- the UNMASKED pair log-probabilities, lambdaMask's default eps / sigma /
+ *   mu -- are compared with those of the labels ranked by themselves:
+ *   transformation 1: sum_j (c_j - base_j)^2   2: cosine(base, c)   3 (t-risk only): (sum c - sum base)^2
+ *   mat : [B, 1 + S + add_ideal]; ideal_ones: the ideal column of transformation 2 is 1 (geoRisk, :107) instead of
+ *   cosine(base, base) (zRisk, :227); dvec : [B, n] out or NULL, d mat[b, 0] / d (model column sum j), rank order.
+ * ltr_risk_lambda_rows_bwd: grad[b, :] = gq[b] * d mat[b, 0] / d y_pred[b, :] (pair pass + softmax Jacobian).
+ */
+int ltr_risk_lambda_rows(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
+                         int transformation, int add_ideal, int ideal_ones, int scheme, float* mat, float* dvec,
+                         void* stream);
+int ltr_risk_lambda_rows_bwd(const float* y_pred, const float* y_true, int B, int n, int scheme, const float* gq,
+                             const float* dvec, float* grad, void* stream);
+
+/*
+ * lambdaMask.                                 replaces losses/lambdaL.py:7-64
+ *   logp : [B, n, n] out, log-probability of every pair of rank positions (the return_losses=True result);
+ *   mask : [B, n, n] bytes out or NULL, 1 where the pair enters lambdaLoss (label_i > label_j, both real, both < k).
+ */
+int ltr_lambda_pair_matrix(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value, int scheme,
+                           int k, float sigma, float mu, int natural_log, float* logp, unsigned char* mask,
+                           void* stream);
+
+/*
  * zRisk / geoRisk / tRisk over a query x system matrix.   replaces losses/riskLosses/riskFunctions.py:4-33 and the
  * epilogues riskLosses.py:49-58, 274-291.  Three phases so that query-sharded callers can all-reduce in between:
  *   phase 1 (local)  state1 = {max(mat), sum mat[:,0], sum mat[:,C-1], sum(mat), Q}     -> MAX on [0], SUM on [1..4]

@@ -12,6 +12,7 @@
 //      3 MUFU (ex2, rcp, lg2) + ~15 FP32; the B x n x n tensors of the reference never exist.
 // `ndcgLoss1_scheme` has no label condition (lambdaL.py:26): every ordered pair of real docs, the diagonal
 // included, is in the mask with weight G_i / D_i.
+#include "lambda_common.cuh"
 #include "ltr_host.h"
 #include "sort_common.cuh"
 
@@ -19,16 +20,6 @@ namespace ltr {
 
 constexpr int LAMBDA_THREADS = 128;
 constexpr int LAMBDA_MAX_N = 2048;
-
-enum LambdaScheme {
-    SCHEME_NONE = 0,            // weighing_scheme=None and rankNet_scheme: w = 1
-    SCHEME_NDCG1 = 1,           // G_i / D_i
-    SCHEME_NDCG2 = 2,           // delta_|i-j| |G_i - G_j|
-    SCHEME_LAMBDARANK = 3,      // |1/D_i - 1/D_j| |G_i - G_j|
-    SCHEME_NDCG2PP = 4,         // mu * ndcgLoss2 + lambdaRank
-    SCHEME_GTDIFF = 5,          // |y_i - y_j|
-    SCHEME_GTDIFF_POW = 6,      // |y_i^2 - y_j^2|
-};
 
 struct LambdaParams {
     const float* y_pred;
@@ -40,43 +31,6 @@ struct LambdaParams {
     float* slate_cnt;           // [B] number of masked pairs
     float* grad;                // [B, n] d(-sum)/d y_pred, unscaled; null = forward only
 };
-
-template <int SCHEME>
-__device__ __forceinline__ float pair_weight(int i, int j, const float* G, const float* invD, const float* dtab,
-                                             const float* Y, float mu) {
-    if (SCHEME == SCHEME_NONE) return 1.0f;
-    if (SCHEME == SCHEME_NDCG1) return G[i] * invD[i];
-    if (SCHEME == SCHEME_GTDIFF) return fabsf(fmaxf(Y[i], 0.f) - fmaxf(Y[j], 0.f));          // clamped labels (:37)
-    if (SCHEME == SCHEME_GTDIFF_POW) {
-        const float a = fmaxf(Y[i], 0.f), c = fmaxf(Y[j], 0.f);
-        return fabsf(a * a - c * c);
-    }
-    const float dg = fabsf(G[i] - G[j]);
-    const int gap = i > j ? i - j : j - i;
-    if (SCHEME == SCHEME_NDCG2) return dtab[gap] * dg;
-    const float lr = fabsf(invD[i] - invD[j]) * dg;
-    if (SCHEME == SCHEME_LAMBDARANK) return lr;
-    return mu * (dtab[gap] * dg) + lr;                           // SCHEME_NDCG2PP (lambdaL.py:115)
-}
-
-// log-probability of one pair and its derivative w.r.t. delta = s_hi - s_lo
-__device__ __forceinline__ void pair_logprob(float delta, float w, float sig_scale, float log_eps2, float out_scale,
-                                             float& l, float& dl) {
-    // lambdaL.py:49-50: clamp to +-1e8, NaN (-inf - -inf) -> 0
-    delta = (delta != delta) ? 0.f : fminf(fmaxf(delta, -1e8f), 1e8f);
-    const float e = ex2_approx(fminf(-sig_scale * delta, 126.0f));      // exp(-sigma delta)
-    const float q = 1.0f + e;
-    const float sig = rcp_approx(q);
-    float l2 = -lg2_approx(q);                                    // log2 sigmoid
-    bool open = l2 >= log_eps2;                                   // inner clamp(min=eps) inactive
-    l2 = fmaxf(l2, log_eps2);
-    float lw = w * l2;                                            // log2 of (.)^w
-    open = open && (lw >= log_eps2);                              // outer clamp inactive
-    lw = fmaxf(lw, log_eps2);
-    l = lw * out_scale;                                           // out_scale = 1 (binary) or ln 2 (natural)
-    // d log_b(sig^w) / d delta = w sigma (1 - sig) / ln b;  1 - sig = e * sig
-    dl = open ? w * (e * sig) : 0.f;
-}
 
 template <int SCHEME>
 __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaParams p) {

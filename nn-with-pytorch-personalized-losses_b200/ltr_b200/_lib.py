@@ -35,6 +35,10 @@ _SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P]),
     "ltr_risk_listnet_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ltr_risk_listnet_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ltr_risk_lambda_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ltr_risk_lambda_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "ltr_lambda_pair_matrix": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, _P,
+                                       _P, _P]),
     "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
                                _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),

@@ -18,6 +18,24 @@ def _scheme_id(weighing_scheme):
     return ops.LAMBDA_SCHEMES[name]
 
 
+def lambdaMask(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, weighing_scheme=None, k=None,
+               sigma=1., mu=10., reduction="sum", reduction_log="binary", return_losses=False):
+    """
+    The pair log-probabilities lambdaLoss reduces (lambdaL.py:7-64): the 1-D tensor of the masked pairs, in
+    (slate, rank_i, rank_j) order, or -- return_losses=True -- the unmasked [batch, slate, slate] tensor.
+    Forward only (the fused training path is lambdaLoss); the boolean gather is index plumbing on the device.
+    """
+    scheme = _scheme_id(weighing_scheme)
+    if reduction_log not in ("natural", "binary"):
+        raise ValueError("Reduction logarithm base can be either natural or binary")
+    logp, mask = ops.lambda_pair_matrix(to_device(y_pred.detach()), to_device(y_true.detach()), eps,
+                                        float(padded_value_indicator), scheme, 0 if k is None else int(k), sigma, mu,
+                                        reduction_log == "natural", not return_losses)
+    if return_losses:
+        return back_to(logp, y_pred)
+    return back_to(logp[mask.bool()], y_pred)
+
+
 def lambdaLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, weighing_scheme=None, k=None,
                sigma=1., mu=10., reduction="sum", reduction_log="binary"):
     """

@@ -333,3 +333,51 @@ class _RiskListnet(torch.autograd.Function):
 
 def risk_listnet(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk=False, group=None):
     return _RiskListnet.apply(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk, group)
+
+
+class _RiskLambda(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, scheme, group):
+        lib = _lib.load()
+        B, n = y_pred.shape
+        dev = y_pred.device
+        S = 0 if y_base is None else y_base.shape[2]
+        C = 1 + S + (1 if add_ideal else 0)
+        need = ctx.needs_input_grad[0]
+        mat = torch.empty(B, C, dtype=torch.float32, device=dev)
+        dvec = torch.empty(B, n, dtype=torch.float32, device=dev) if need else None
+        _lib.check(lib.ltr_risk_lambda_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
+                                            int(bool(add_ideal)), int(kind == KIND_GEO), int(scheme), mat.data_ptr(),
+                                            _ptr(dvec), rt.stream_ptr()), "ltr_risk_lambda_rows")
+        invert = (lt == 1)                                   # riskLosses.py:114-115, :335
+        loss, gq, _ = _risk_phases(mat, kind, invert, strategy, 0, alpha, negative, need, False, group)
+        grad = None
+        if need:
+            grad = torch.empty_like(y_pred)
+            _lib.check(lib.ltr_risk_lambda_rows_bwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, int(scheme),
+                                                    gq.data_ptr(), dvec.data_ptr(), grad.data_ptr(), rt.stream_ptr()),
+                       "ltr_risk_lambda_rows_bwd")
+        ctx.grad = grad
+        ctx.mat = mat
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 10
+
+
+def risk_lambda(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, scheme, group=None):
+    return _RiskLambda.apply(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, scheme, group)
+
+
+def lambda_pair_matrix(y_pred, y_true, eps, pad, scheme, k, sigma, mu, natural, want_mask):
+    """[B, n, n] pair log-probabilities in rank order (+ the lambdaLoss pair mask as uint8)."""
+    lib = _lib.load()
+    B, n = y_pred.shape
+    dev = y_pred.device
+    logp = torch.empty(B, n, n, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, n, n, dtype=torch.uint8, device=dev) if want_mask else None
+    _lib.check(lib.ltr_lambda_pair_matrix(y_pred.data_ptr(), y_true.data_ptr(), B, n, float(eps), float(pad), int(scheme),
+                                          int(k), float(sigma), float(mu), int(natural), logp.data_ptr(), _ptr(mask),
+                                          rt.stream_ptr()), "ltr_lambda_pair_matrix")
+    return logp, mask

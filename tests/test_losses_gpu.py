@@ -27,6 +27,9 @@ def _fns():
         "geoRiskListnetLoss": (RL.geoRiskListnetLoss, ("y_pred", "y_true", "y_baselines")),
         "zRiskListnetLoss": (RL.zRiskListnetLoss, ("y_pred", "y_true", "y_baselines")),
         "tRiskListnetLoss": (RL.tRiskListnetLoss, ("y_pred", "y_true", "y_baselines")),
+        "geoRiskLambdaLoss": (RL.geoRiskLambdaLoss, ("y_pred", "y_true", "y_baselines")),
+        "zRiskLambdaLoss": (RL.zRiskLambdaLoss, ("y_pred", "y_true", "y_baselines")),
+        "tRiskLambdaLoss": (RL.tRiskLambdaLoss, ("y_pred", "y_true", "y_baselines")),
     }
 
 
@@ -36,11 +39,13 @@ def _oracle_fns():
         "lambdaLoss": O.lambda_loss, "listnetLoss": O.listnet_loss, "orderScoreLoss": O.order_score_loss,
         "ndcgLoss": O.ndcg_loss, "ordinalLoss": O.ordinal_loss, "geoRiskListnetLoss": O.geo_risk_listnet_loss,
         "zRiskListnetLoss": O.z_risk_listnet_loss, "tRiskListnetLoss": O.t_risk_listnet_loss,
+        "geoRiskLambdaLoss": O.geo_risk_lambda_loss, "zRiskLambdaLoss": O.z_risk_lambda_loss,
+        "tRiskLambdaLoss": O.t_risk_lambda_loss,
     }
 
 
 LOSS_FNS = ("lambdaLoss", "listnetLoss", "orderScoreLoss", "ndcgLoss", "ordinalLoss", "geoRiskListnetLoss",
-            "zRiskListnetLoss", "tRiskListnetLoss")
+            "zRiskListnetLoss", "tRiskListnetLoss", "geoRiskLambdaLoss", "zRiskLambdaLoss", "tRiskLambdaLoss")
 CASES = [n for n, c in G.cases.items() if c["fn"] in LOSS_FNS]
 
 
@@ -74,13 +79,13 @@ def test_golden(name):
     out, grad = _run(case["fn"], ins, G.kwargs(name))
     ref = G.out(name)
     assert tuple(out.shape) == tuple(ref.shape), "return shape (0-dim vs [1]) must match the reference"
-    assert_loss_close(out, ref, atol=2e-6)
+    o64 = g64 = None
+    if "ambda" in case["fn"] or "Risk" in case["fn"]:
+        # pairwise / risk values are differences of nearly equal fp32 sums: allow the reference's own fp32 rounding
+        o64, g64 = _run_oracle(case["fn"], ins, G.kwargs(name), dtype=torch.float64)
+    assert_loss_close(out, ref, atol=2e-6, ref64=o64)
     if G.has_grad(name, "y_pred"):
-        gref = G.grad(name, "y_pred")
-        g64 = None
-        if case["fn"] == "lambdaLoss":
-            _, g64 = _run_oracle(case["fn"], ins, G.kwargs(name), dtype=torch.float64)
-        assert_grad_close(grad, gref, ref64=g64)
+        assert_grad_close(grad, G.grad(name, "y_pred"), ref64=g64)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -206,6 +211,47 @@ def test_trisk_listnet_vs_oracle(lt):
     y = torch.randint(0, 5, (B, n), generator=g).float()
     base = torch.randn(B, n, generator=g)
     _check("tRiskListnetLoss", {"y_pred": s, "y_true": y, "y_baselines": base}, dict(listnet_transformation=lt), atol=1e-6)
+
+
+@pytest.mark.parametrize("fn,lt", [("geoRiskLambdaLoss", 1), ("geoRiskLambdaLoss", 2), ("zRiskLambdaLoss", 1),
+                                   ("zRiskLambdaLoss", 2), ("tRiskLambdaLoss", 1), ("tRiskLambdaLoss", 2),
+                                   ("tRiskLambdaLoss", 3)])
+def test_risk_lambda_vs_oracle(fn, lt):
+    g = torch.Generator().manual_seed(100 + lt)
+    B, n, S = 12, 40, 2
+    s = torch.randn(B, n, generator=g)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    if fn.startswith("tRisk"):
+        base = torch.randn(B, n, generator=g)
+        _check(fn, {"y_pred": s, "y_true": y, "y_baselines": base}, dict(listnet_transformation=lt), atol=1e-6,
+               f64_slack=True)
+        return
+    base = torch.randn(B, n, S, generator=g)
+    for rs, ideal, scheme in ((1, 1, "ndcgLoss2PP_scheme"), (2, 2, "ndcgLoss2PP_scheme"), (3, 2, "lamdbaRank_scheme"),
+                              (1, 2, None), (1, 1, "ndcgLoss1_scheme")):
+        _check(fn, {"y_pred": s, "y_true": y, "y_baselines": base},
+               dict(listnet_transformation=lt, return_strategy=rs, add_ideal_ranking_to_mat=ideal, weighing_scheme=scheme),
+               atol=1e-6, f64_slack=True)
+
+
+@pytest.mark.parametrize("name", G.names("lambda_mask_full/"))
+def test_lambda_mask_full_golden(name):
+    from ltr_b200.losses.lambdaL import lambdaMask
+    ins = G.inputs(name)
+    out = lambdaMask(torch.from_numpy(ins["y_pred"]).cuda(), torch.from_numpy(ins["y_true"]).cuda(), **G.kwargs(name))
+    np.testing.assert_allclose(out.cpu().numpy(), G.out(name), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("scheme", [None, "ndcgLoss1_scheme", "ndcgLoss2PP_scheme"])
+def test_lambda_mask_masked_vs_oracle(scheme):
+    from ltr_b200.losses.lambdaL import lambdaMask
+    from oracle import ltr_oracle as O
+    s, y = make_slates(5, 30, seed=44, min_len=12, pad_anywhere=True)
+    for kw in (dict(), dict(k=7), dict(reduction_log="natural", sigma=2.0)):
+        got = lambdaMask(s.cuda(), y.cuda(), weighing_scheme=scheme, **kw).cpu().numpy()
+        ref = O.lambda_mask(s, y, weighing_scheme=scheme, **kw).numpy()
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
 
 
 def test_risk_misc_semantics():
