@@ -105,10 +105,12 @@ int ltr_sort_desc(const float* keys, int B, int n, int tie_rule, int* perm, floa
  *   y_true, y_pred : [Q, n]; ks : nk <= 32 HOST ints (k <= 0 or k > n: no truncation); out : [Q, nk]
  *   disc32 : n device floats, disc32[r] = (float)log2(2 + r) (the reference divides by np.log2(1 + i) rounded to fp32)
  *   gains 2^l - 1, sequential fp32 accumulation, 0/0 = NaN (the 'tensor' return type maps NaN to 0 in the caller).
- *   All k of a sweep are served by one read and one sort of the query.
+ *   All k of a sweep are served by one read of the query.  flags: Q + 1 device ints of scratch or NULL; with it, sweeps
+ *   whose largest k is <= 31 take the top-k path (one warp per query, no sort) and only queries with tied keys
+ *   among their first k + 1 ranks are sorted in full.
  */
 int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
-                  const float* disc32, float* out, void* stream);
+                  const float* disc32, float* out, int* flags, void* stream);
 
 /*
  * NDCG@k, fp64.                               replaces utils/metrics.py:48-80 (dcg / ndcg / mNdcg)
@@ -116,7 +118,8 @@ int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const 
  *   ideal DCG is 0 gets empty_value (1.0 for no_relevant=True, 0.0 otherwise); out : [Q, nk] doubles.
  */
 int ltr_ndcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
-                      int exponential_gains, double empty_value, const double* disc64, double* out, void* stream);
+                      int exponential_gains, double empty_value, const double* disc64, double* out, int* flags,
+                      void* stream);
 
 /*
  * exactNDCG "loss", forward only.             replaces losses/exactNDCG.py:5-29 (ndcgLoss; y_true FIRST)

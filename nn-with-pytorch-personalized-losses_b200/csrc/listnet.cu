@@ -76,6 +76,91 @@ __global__ void __launch_bounds__(STREAM_THREADS) listnet_kernel(const ListnetPa
     stream_finish(vals, 1, p.partials, p.counter, p.loss, scale, nullptr);
 }
 
+// Vectorised variant (n % 4 == 0, 16-byte aligned rows): lane l owns the float4s l, l + 32, ... of the row, so a
+// 128-doc slate is ONE 128-bit load per lane per array and one 128-bit store for the gradient.  The two row
+// maxima are single REDUX instructions on order-preserving integer keys; the three sums the slate needs
+//   sy = sum e^(y - my),  ss = sum e^(s - ms),  dot = sum e^(y - my) s
+// are reduced together (independent shuffle chains), and  loss_b = lse(s) - dot / sy  (sum p = 1).
+template <int V>
+__global__ void __launch_bounds__(STREAM_THREADS) listnet_vec_kernel(const ListnetParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * STREAM_WARPS;
+    const float ninf = __int_as_float(0xff800000);
+    const int n4 = p.n >> 2;
+    double acc = 0.0;
+    // software pipeline: the next slate's two rows are in flight while this one is reduced
+    float4 yn[V], sn[V];
+    auto issue_loads = [&](int b) {
+        const float4* yrow = reinterpret_cast<const float4*>(p.y_true + (size_t)b * p.n);
+        const float4* srow = reinterpret_cast<const float4*>(p.y_pred + (size_t)b * p.n);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int i = lane + 32 * j;
+            yn[j] = (i < n4) ? ld_stream4(reinterpret_cast<const float*>(yrow + i)) : make_float4(ninf, ninf, ninf, ninf);
+            sn[j] = (i < n4) ? ld_stream4(reinterpret_cast<const float*>(srow + i)) : make_float4(ninf, ninf, ninf, ninf);
+        }
+    };
+    if (gwarp < p.B) issue_loads(gwarp);
+    for (int b = gwarp; b < p.B; b += nwarps) {
+        float4 y[V], s[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) y[j] = yn[j], s[j] = sn[j];
+        if (b + nwarps < p.B) issue_loads(b + nwarps);
+        float my = ninf, ms = ninf;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            my = fmaxf(my, fmaxf(fmaxf(y[j].x, y[j].y), fmaxf(y[j].z, y[j].w)));
+            ms = fmaxf(ms, fmaxf(fmaxf(s[j].x, s[j].y), fmaxf(s[j].z, s[j].w)));
+        }
+        my = warp_max_redux(my);
+        ms = warp_max_redux(ms);
+        float sy = 0.f, ss = 0.f, dot = 0.f;
+        const float kmy = -my * kLog2e, kms = -ms * kLog2e;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const bool in = (lane + 32 * j) < n4;
+            const float4 sv = s[j];
+            // e^(x - m) = 2^(x log2e - m log2e); padding lanes give 2^-inf = 0
+            y[j].x = ex2_approx(fmaf(y[j].x, kLog2e, kmy)); y[j].y = ex2_approx(fmaf(y[j].y, kLog2e, kmy));
+            y[j].z = ex2_approx(fmaf(y[j].z, kLog2e, kmy)); y[j].w = ex2_approx(fmaf(y[j].w, kLog2e, kmy));
+            s[j].x = ex2_approx(fmaf(sv.x, kLog2e, kms)); s[j].y = ex2_approx(fmaf(sv.y, kLog2e, kms));
+            s[j].z = ex2_approx(fmaf(sv.z, kLog2e, kms)); s[j].w = ex2_approx(fmaf(sv.w, kLog2e, kms));
+            sy += (y[j].x + y[j].y) + (y[j].z + y[j].w);
+            ss += (s[j].x + s[j].y) + (s[j].z + s[j].w);
+            if (in) dot += (y[j].x * sv.x + y[j].y * sv.y) + (y[j].z * sv.z + y[j].w * sv.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sy += __shfl_xor_sync(LTR_FULL_MASK, sy, o);
+            ss += __shfl_xor_sync(LTR_FULL_MASK, ss, o);
+            dot += __shfl_xor_sync(LTR_FULL_MASK, dot, o);
+        }
+        const float isy = __fdividef(1.0f, sy), iss = __fdividef(1.0f, ss);
+        const float part = (ms + __logf(ss)) - dot * isy;           // -sum p_i log q_i
+        if (p.grad) {
+            float4* grow = reinterpret_cast<float4*>(p.grad + (size_t)b * p.n);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int i = lane + 32 * j;
+                if (i < n4) {
+                    float4 g;
+                    g.x = fmaf(s[j].x, iss, -y[j].x * isy); g.y = fmaf(s[j].y, iss, -y[j].y * isy);
+                    g.z = fmaf(s[j].z, iss, -y[j].z * isy); g.w = fmaf(s[j].w, iss, -y[j].w * isy);
+                    st_stream4(reinterpret_cast<float*>(grow + i), g);
+                }
+            }
+        }
+        if (lane == 0) {
+            if (p.slate_loss) p.slate_loss[b] = part;
+            acc += (double)part;
+        }
+    }
+    double vals[STREAM_MAX_OUT] = {acc, 0.0, 0.0, 0.0};
+    const double scale[STREAM_MAX_OUT] = {1.0, 1.0, 1.0, 1.0};
+    stream_finish(vals, 1, p.partials, p.counter, p.loss, scale, nullptr);
+}
+
 // ---------------------------------------------------------------------------------------------
 // ordinal loss: y_pred [B, n, L] probabilities, y_true [B, n]; target_l = [y >= l + 1], label == -1
 // marks a padded doc for with_ordinals (its default, ordinal.py:39 does not forward the caller's
@@ -157,7 +242,13 @@ LTR_API int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, 
                     ws_counter(workspace, LTR_WS_STREAM_COUNTER)};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = stream_grid(B);
-    if (n <= 128) listnet_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);
+    const bool vec = !apply_sigmoid && (n % 4 == 0) && n <= 512 &&
+                     ((reinterpret_cast<uintptr_t>(y_true) | reinterpret_cast<uintptr_t>(y_pred) |
+                       reinterpret_cast<uintptr_t>(grad)) % 16 == 0);
+    if (vec && n <= 128) listnet_vec_kernel<1><<<grid, STREAM_THREADS, 0, st>>>(p);
+    else if (vec && n <= 256) listnet_vec_kernel<2><<<grid, STREAM_THREADS, 0, st>>>(p);
+    else if (vec) listnet_vec_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);
+    else if (n <= 128) listnet_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);
     else if (n <= 256) listnet_kernel<8><<<grid, STREAM_THREADS, 0, st>>>(p);
     else if (n <= 512) listnet_kernel<16><<<grid, STREAM_THREADS, 0, st>>>(p);
     else listnet_kernel<32><<<grid, STREAM_THREADS, 0, st>>>(p);

@@ -80,6 +80,9 @@ struct NdcgParams {
     double empty_value;
     float* out32;
     double* out64;
+    int kmax;                // largest k of the sweep (top-k fast path)
+    int* flags;              // [1 + B] scratch: flags[0] = number of queries the top-k path left to the full sort
+                             // (a tie among their first kmax + 1 ranks), flags[1..] = their indices
 };
 
 template <bool F64>
@@ -87,7 +90,10 @@ __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RankSmem sm(smem_raw, p.len);
     const float ninf = __int_as_float(0xff800000);
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    // with the top-k fast path in front, only the queries it appended to the flagged list are sorted here
+    const int work = p.flags ? p.flags[0] : p.B;
+    for (int w = blockIdx.x; w < work; w += gridDim.x) {
+        const int b = p.flags ? p.flags[1 + w] : w;
         const float* yt = p.y_true + (size_t)b * p.n;
         for (int i = threadIdx.x; i < p.n; i += blockDim.x) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
         __syncthreads();
@@ -121,6 +127,170 @@ __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) 
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Top-k fast path of the NDCG sweep (all k <= 31): one WARP per query, the row in registers, no sort.
+//   predicted order: kmax rounds of "lane-local max (a max tree, no index), REDUX.MAX over the warp, retire
+//     the element(s) equal to it".  If a round retires more than one element, or two consecutive rounds give
+//     equal keys, a tie group reaches into the first kmax ranks: with LTR_TIES_STDSORT (and n > 16) the query is appended
+//     to the flagged list and left to the full-sort kernel; with the index-ordered tie rules the round falls
+//     back to an exact arg-max on (key, index).  A tie group entirely below rank kmax cannot change the top-k ranks.
+//   ideal order: labels that are integers 0..7 (MSLR / Istella: 0..4) are counted per level with ballots and rank r
+//     reads its label off the cumulative counts; other labels take top-k rounds of their own (values only).
+//   DCG sums: lane r holds the term of rank r; the running sums are formed in rank order (the reference
+//     accumulates sequentially in fp32 / fp64) and written where r + 1 equals a k of the sweep.
+// 8 n bytes of HBM traffic per query.
+__device__ __forceinline__ int topk_key(float f) {
+    if (f != f) return 0x7fffffff;                                // NaN first (at::native KeyValueCompDesc)
+    return float_order_key(f + 0.0f);                             // -0 -> +0 so that key equality == float equality
+}
+
+template <int ITEMS>
+__device__ __forceinline__ int tree_max(const int (&v)[ITEMS]) {
+    int m[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) m[k] = v[k];
+#pragma unroll
+    for (int w = ITEMS / 2; w > 0; w >>= 1) {
+#pragma unroll
+        for (int k = 0; k < w; ++k) m[k] = max(m[k], m[k + w]);
+    }
+    return m[0];
+}
+
+template <int ITEMS, bool F64>
+__global__ void __launch_bounds__(256) ndcg_topk_kernel(const NdcgParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * 8;
+    const int TAKEN = (int)0x80000000;
+    const bool idx_desc = (p.tie_rule == TIES_REVERSED);
+    const bool want_std = (p.tie_rule == TIES_STDSORT) && p.n > 16;
+    int myk = -1;                                                 // lane j writes the j-th k of the sweep
+    for (int j = 0; j < p.nk; ++j) myk = (lane == j) ? p.ks[j] : myk;
+    for (int b = gwarp; b < p.B; b += nwarps) {
+        const float* sp = p.y_pred + (size_t)b * p.n;
+        const float* yp = p.y_true + (size_t)b * p.n;
+        int ks_[ITEMS];
+        float yv[ITEMS];
+        bool small_int = true;
+        int lmax = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int i = lane + 32 * k;
+            const bool in = i < p.n;
+            const float s = in ? ld_stream(sp + i) : 0.f;
+            yv[k] = in ? ld_stream(yp + i) : 0.f;
+            ks_[k] = in ? topk_key(s) : TAKEN;
+            const int lv = (int)fminf(fmaxf(yv[k], -1.f), 8.f);
+            small_int = small_int && (!in || ((float)lv == yv[k] && lv >= 0 && lv <= 7));
+            lmax = max(lmax, lv);
+        }
+        small_int = __all_sync(LTR_FULL_MASK, small_int);
+        lmax = __reduce_max_sync(LTR_FULL_MASK, lmax);
+
+        // ---- predicted order: label at rank r ends up in lane r --------------------------------------
+        float lab_pred = 0.f;
+        int prev_key = 0x7ffffffe, tie = 0;
+        for (int r = 0; r < p.kmax; ++r) {
+            const int wk = __reduce_max_sync(LTR_FULL_MASK, tree_max(ks_));
+            int hits = 0;
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const bool hit = (ks_[k] == wk) && (wk != TAKEN);
+                hits += hit ? 1 : 0;
+                mine = hit ? yv[k] : mine;
+            }
+            const unsigned owners = __ballot_sync(LTR_FULL_MASK, hits > 0);
+            const bool multi = (__popc(owners) > 1) || __any_sync(LTR_FULL_MASK, hits > 1);
+            int widx = -1;                                        // exact winner index, only needed on a tie
+            if (multi || wk == prev_key) {
+                if (want_std) { tie = 1; break; }
+                int cand = idx_desc ? -1 : 0x7fffffff;
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k)
+                    if (ks_[k] == wk) cand = idx_desc ? max(cand, lane + 32 * k) : min(cand, lane + 32 * k);
+                widx = idx_desc ? __reduce_max_sync(LTR_FULL_MASK, cand) : __reduce_min_sync(LTR_FULL_MASK, cand);
+            }
+            int owner = __ffs(owners) - 1;
+            if (widx >= 0) {
+                owner = widx & 31;
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) {
+                    if (lane + 32 * k == widx) { mine = yv[k]; ks_[k] = TAKEN; }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) ks_[k] = (ks_[k] == wk) ? TAKEN : ks_[k];
+            }
+            const float labw = __shfl_sync(LTR_FULL_MASK, mine, owner < 0 ? 0 : owner);
+            if (lane == r) lab_pred = (wk == TAKEN) ? 0.f : labw;
+            prev_key = (wk == TAKEN) ? 0x7ffffffe - r : wk;
+        }
+        if (tie) {                                                // left to the full sort (std::sort tie order)
+            if (lane == 0) p.flags[1 + atomicAdd(p.flags, 1)] = b;
+            continue;
+        }
+
+        // ---- ideal order -----------------------------------------------------------------------------
+        float lab_ideal = 0.f;
+        if (small_int) {
+            int ge = 0;                                           // lane r: number of levels L >= 1 with #(label >= L) > r
+            int cum = 0;
+            for (int L = lmax; L >= 1; --L) {
+                int c = 0;
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k)
+                    c += __popc(__ballot_sync(LTR_FULL_MASK, (lane + 32 * k < p.n) && yv[k] == (float)L));
+                cum += c;                                         // docs with label >= L
+                ge += (cum > lane) ? 1 : 0;
+            }
+            lab_ideal = (float)ge;                                // labels fill the ranks from the top level down
+        } else {
+            int kl_[ITEMS];
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) kl_[k] = (lane + 32 * k < p.n) ? topk_key(yv[k]) : TAKEN;
+            for (int r = 0; r < p.kmax; ++r) {
+                const int wl = __reduce_max_sync(LTR_FULL_MASK, tree_max(kl_));
+                bool have = false;
+                float mine = 0.f;
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k)
+                    if (!have && kl_[k] == wl && wl != TAKEN) { have = true; mine = yv[k]; }
+                const int owner = __ffs(__ballot_sync(LTR_FULL_MASK, have)) - 1;
+                bool done = false;
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k)
+                    if (lane == owner && !done && kl_[k] == wl) { kl_[k] = TAKEN; done = true; }
+                const float labi = __shfl_sync(LTR_FULL_MASK, mine, owner < 0 ? 0 : owner);
+                if (lane == r) lab_ideal = (owner < 0) ? 0.f : labi;
+            }
+        }
+
+        // ---- DCG sums in rank order ------------------------------------------------------------------
+        if (!F64) {
+            const float d = (lane < p.kmax) ? p.disc32[lane] : 1.0f;
+            const float tp = (exp2f(lab_pred) - 1.0f) / d, ti = (exp2f(lab_ideal) - 1.0f) / d;
+            float got = 0.f, ideal = 0.f;
+            for (int r = 0; r < p.kmax; ++r) {
+                got += __shfl_sync(LTR_FULL_MASK, tp, r);
+                ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
+                if (myk == r + 1) p.out32[(size_t)b * p.nk + lane] = got / ideal;
+            }
+        } else {
+            const double d = (lane < p.kmax) ? p.disc64[lane] : 1.0;
+            const double lp = (double)lab_pred, li = (double)lab_ideal;
+            const double tp = (p.exp_gains ? exp2(lp) - 1.0 : lp) / d, ti = (p.exp_gains ? exp2(li) - 1.0 : li) / d;
+            double got = 0.0, ideal = 0.0;
+            for (int r = 0; r < p.kmax; ++r) {
+                got += __shfl_sync(LTR_FULL_MASK, tp, r);
+                ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
+                if (myk == r + 1) p.out64[(size_t)b * p.nk + lane] = (ideal == 0.0) ? p.empty_value : got / ideal;
+            }
+        }
     }
 }
 
@@ -245,9 +415,36 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     if (p.n > RANK_MAX_N) return set_error(LTR_ETOOBIG, "ltr_ndcg_at_k: slate too long");
     p.len = rank_len(p.n);
     p.nk = nk;
-    for (int j = 0; j < nk; ++j) p.ks[j] = ks[j];
+    // effective k of every entry (k <= 0 or k > n: the whole slate, metrics.py:54-55,87-88)
+    int kmax = 0;
+    for (int j = 0; j < nk; ++j) {
+        p.ks[j] = (ks[j] <= 0 || ks[j] > p.n) ? p.n : ks[j];
+        kmax = p.ks[j] > kmax ? p.ks[j] : kmax;
+    }
+    p.kmax = kmax;
     const size_t smem = rank_smem(p.len);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (kmax <= 31 && p.n <= 1024 && p.flags) {
+        // top-k fast path (one warp per query), then the full sort for the queries it flagged
+        LTR_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(int), st));
+        int g = (p.B + 7) / 8;
+        const int cap = device_sm_count() * 8;
+        g = g < cap ? g : cap;
+#define LTR_TOPK(ITEMS)                                                      \
+        if (f64) ndcg_topk_kernel<ITEMS, true><<<g, 256, 0, st>>>(p);            \
+        else ndcg_topk_kernel<ITEMS, false><<<g, 256, 0, st>>>(p)
+        if (p.n <= 128) { LTR_TOPK(4); }
+        else if (p.n <= 256) { LTR_TOPK(8); }
+        else if (p.n <= 512) { LTR_TOPK(16); }
+        else { LTR_TOPK(32); }
+#undef LTR_TOPK
+        if (p.tie_rule != TIES_STDSORT || p.n <= 16) {
+            const int rc0 = (int)cudaGetLastError();
+            return rc0 ? set_cuda_error(rc0, "ltr_ndcg_at_k") : 0;
+        }
+    } else {
+        p.flags = nullptr;
+    }
     if (f64) {
         if (int rc = rank_prepare(ndcg_kernel<true>, smem)) return rc;
         ndcg_kernel<true><<<rank_grid(p.B), RANK_THREADS, smem, st>>>(p);
@@ -260,18 +457,20 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
 }
 
 LTR_API int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
-                          const float* disc32, float* out, void* stream) {
+                          const float* disc32, float* out, int* flags, void* stream) {
     ltr::NdcgParams p{};
     p.y_true = y_true; p.y_pred = y_pred; p.B = Q; p.n = n; p.tie_rule = tie_rule; p.disc32 = disc32; p.out32 = out;
+    p.flags = flags;
     if (!disc32 || !out) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k: null table / output");
     return ndcg_common(p, ks, nk, false, stream);
 }
 
 LTR_API int ltr_ndcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
                               int exponential_gains, double empty_value, const double* disc64, double* out,
-                              void* stream) {
+                              int* flags, void* stream) {
     ltr::NdcgParams p{};
     p.y_true = y_true; p.y_pred = y_pred; p.B = Q; p.n = n; p.tie_rule = tie_rule; p.disc64 = disc64; p.out64 = out;
+    p.flags = flags;
     p.exp_gains = exponential_gains; p.empty_value = empty_value;
     if (!disc64 || !out) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k_f64: null table / output");
     return ndcg_common(p, ks, nk, true, stream);

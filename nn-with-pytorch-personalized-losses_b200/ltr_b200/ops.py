@@ -228,8 +228,9 @@ def ndcg_at_k(y_true, y_pred, ks, tie_rule=TIES_STDSORT):
     Q, n = y_pred.shape
     d32, _ = _disc_tables(n, y_pred.device)
     out = torch.empty(Q, len(ks), dtype=torch.float32, device=y_pred.device)
+    flags = torch.empty(Q + 1, dtype=torch.int32, device=y_pred.device)
     _lib.check(lib.ltr_ndcg_at_k(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
-                                 d32.data_ptr(), out.data_ptr(), rt.stream_ptr()), "ltr_ndcg_at_k")
+                                 d32.data_ptr(), out.data_ptr(), flags.data_ptr(), rt.stream_ptr()), "ltr_ndcg_at_k")
     return out
 
 
@@ -239,9 +240,10 @@ def ndcg_at_k_f64(y_true, y_pred, ks, tie_rule=TIES_STABLE, exponential=False, e
     Q, n = y_pred.shape
     _, d64 = _disc_tables(n, y_pred.device)
     out = torch.empty(Q, len(ks), dtype=torch.float64, device=y_pred.device)
+    flags = torch.empty(Q + 1, dtype=torch.int32, device=y_pred.device)
     _lib.check(lib.ltr_ndcg_at_k_f64(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
                                      int(bool(exponential)), float(empty_value), d64.data_ptr(), out.data_ptr(),
-                                     rt.stream_ptr()), "ltr_ndcg_at_k_f64")
+                                     flags.data_ptr(), rt.stream_ptr()), "ltr_ndcg_at_k_f64")
     return out
 
 

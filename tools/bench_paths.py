@@ -1,0 +1,205 @@
+"""Secondary measurements of the hot path (every kernel family besides the headline approxNDCG line):
+ListNet fwd+bwd, NDCG@k evaluation sweep, LambdaLoss, GeoRisk-ListNet, approxNDCG at n = 1024.
+
+    python tools/bench_paths.py [--only listnet,ndcg,...] [--iters N] [--profile]
+
+Each entry is timed with CUDA events on the launching stream after warm-up, over a ring of distinct
+batches larger than the 126 MB L2 where the kernel is HBM-bound, and reports algorithmic bytes / time
+against the measured HBM peak (MEASURED_PEAKS.json).  `--profile` runs 3 iterations per kernel only (for ncu).
+bench.py imports `run_all` for the `secondary` block of its JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "nn-with-pytorch-personalized-losses_b200")]
+
+import torch  # noqa: E402
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+def _time(fn, iters, warm=5):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(warm + i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3          # seconds per call
+
+
+def _slates(B, n, seed, pad=True, dev="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    if pad:
+        lens = torch.randint(n // 2, n + 1, (B,), generator=g)
+        y[torch.arange(n)[None, :] >= lens[:, None]] = -1.0
+    s = torch.randn(B, n, generator=g)
+    return s.to(dev), y.to(dev)
+
+
+def _roof(alg_bytes, sec):
+    peak, src = _hbm_peak()
+    gbs = alg_bytes / sec / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src}
+
+
+def bench_listnet(iters=200, B=65536, n=128):
+    """BASELINE configs[0] loss: ListNet fwd+bwd, no padding.  12 n bytes per slate."""
+    from ltr_b200 import _lib, _runtime as rt
+    lib = _lib.load()
+    ring = 3                                             # 3 x 96 MB of y/s/grad > L2
+    data = [_slates(B, n, 100 + i, pad=False) for i in range(ring)]
+    grads = [torch.empty(B, n, device="cuda") for _ in range(ring)]
+    loss = torch.empty(1, device="cuda")
+    ws = rt.workspace(torch.device("cuda", torch.cuda.current_device()))
+
+    def step(i):
+        s, y = data[i % ring]
+        lib.ltr_listnet_fwdbwd(y.data_ptr(), s.data_ptr(), B, n, 0, None, loss.data_ptr(), grads[i % ring].data_ptr(),
+                               ws.data_ptr(), rt.stream_ptr())
+
+    sec = _time(step, iters)
+    return {"metric": "ListNet fwd+bwd slates/s", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
+            "config": {"workload": f"{B} slates x {n} docs, no padding, ring of {ring} batches"},
+            "roofline": dict(_roof(12.0 * n * B, sec), kernel="listnet_kernel<4>", algorithmic="12 n bytes per slate")}
+
+
+def bench_ndcg(iters=100, Q=65536, n=128, ks=(1, 5, 10)):
+    """NDCG@{1,5,10} evaluation sweep: one read + one sort per query.  8 n + 4 |ks| bytes per query."""
+    from ltr_b200 import ops
+    ring = 3
+    data = [_slates(Q, n, 200 + i, pad=False) for i in range(ring)]
+
+    def step(i):
+        s, y = data[i % ring]
+        ops.ndcg_at_k(y, s, list(ks), ops.TIES_STDSORT)
+
+    sec = _time(step, iters)
+    return {"metric": f"NDCG@{{{','.join(map(str, ks))}}} eval queries/s (n={n})", "value": Q / sec, "unit": "queries/s",
+            "us_per_call": sec * 1e6, "config": {"workload": f"{Q} queries x {n} docs, k sweep {list(ks)}, torchNdcg arithmetic"},
+            "roofline": dict(_roof((8.0 * n + 4.0 * len(ks)) * Q, sec), kernel="ndcg_kernel<false>",
+                             algorithmic="8 n + 4 |ks| bytes per query")}
+
+
+def bench_lambda(iters=50, B=1024, n=256):
+    """BASELINE configs[2]: LambdaLoss ndcgLoss2PP, 256-doc slates, 1024 slates per GPU."""
+    from ltr_b200 import _lib, _runtime as rt
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(300)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    lens = torch.randint(n // 2, n + 1, (B,), generator=g)
+    y[torch.arange(n)[None, :] >= lens[:, None]] = -1.0
+    s = torch.randn(B, n, generator=g)
+    yv = y.clone()
+    pairs = 0
+    for lv in range(5):                                  # ordered pairs with label_i > label_j, both valid
+        cnt_hi = (yv > lv).sum(1)
+        cnt_eq = (yv == lv).sum(1)
+        pairs += int((cnt_hi * cnt_eq).sum())
+    s, y = s.cuda(), y.cuda()
+    sums = torch.empty(2, B, device="cuda")
+    out = torch.empty(2, device="cuda")
+    grad = torch.empty(B, n, device="cuda")
+
+    def step(i):
+        lib.ltr_lambda_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 1e-10, -1.0, 4, 0, 1.0, 10.0, 0, 0, sums[0].data_ptr(),
+                              sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), grad.data_ptr(), rt.stream_ptr())
+
+    sec = _time(step, iters)
+    return {"metric": "LambdaLoss ndcgLoss2PP fwd+bwd slates/s (n=256)", "value": B / sec, "unit": "slates/s",
+            "us_per_call": sec * 1e6,
+            "config": {"workload": f"{B} slates x {n} docs, valid len U{{128..256}}, sigma=1, mu=10, sum, binary"},
+            "roofline": {"bound": "sfu", "achieved": 3.0 * pairs / sec / 1e12, "unit": "TSFU-op/s",
+                         "algorithmic": f"3 SFU ops per masked ordered pair, {pairs} pairs per launch (SURVEY 8d)",
+                         "kernel": "lambda_kernel<4>"}}
+
+
+def bench_georisk(iters=100, B=8192, n=128, S=2):
+    """BASELINE configs[3] on one GPU: geoRiskListnetLoss lt=1, rs=1, alpha=5, fwd+bwd (rows + 3 phases + bwd)."""
+    from ltr_b200 import ops
+    g = torch.Generator().manual_seed(400)
+    s = torch.randn(B, n, generator=g).cuda().requires_grad_(True)
+    y = torch.randint(0, 5, (B, n), generator=g).float().cuda()
+    base = torch.randn(B, n, S, generator=g).cuda()
+
+    def step(i):
+        ops.risk_listnet(s, y, base, ops.KIND_GEO, 5.0, 1, 1, 1.0, False)
+
+    sec = _time(step, iters)
+    alg = (4.0 * n * (2 + S) + 4.0 * n) * B + 8.0 * n * B      # rows read + grad write + backward re-read of s, y
+    return {"metric": "geoRiskListnetLoss fwd+bwd queries/s (n=128, S=2)", "value": B / sec, "unit": "queries/s",
+            "us_per_call": sec * 1e6, "config": {"workload": f"{B} queries x {n} docs x {S} baseline systems, lt=1, rs=1"},
+            "roofline": dict(_roof(alg, sec), kernel="risk_rows_kernel<4> + risk phases + risk_rows_bwd_kernel<4>",
+                             algorithmic="4 n (2+S) read + 4 n written + 8 n re-read per query")}
+
+
+def bench_approx_1024(iters=50, B=64, n=1024):
+    """BASELINE configs[4] loss: approxNDCG on 1024-doc slates (general kernel, one CTA per slate)."""
+    from ltr_b200 import _lib, _runtime as rt
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator().manual_seed(500)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    lens = torch.randint(n // 2, n + 1, (B,), generator=g)
+    y[torch.arange(n)[None, :] >= lens[:, None]] = -1.0
+    s = torch.randn(B, n, generator=g)
+    pairs = int((lens * (lens - 1)).sum())
+    s, y = s.cuda(), y.cuda()
+    grad, slate, loss = torch.empty_like(s), torch.empty(B, device="cuda"), torch.empty(1, device="cuda")
+    tab, ws = rt.disc_prefix(dev), rt.workspace(dev)
+
+    def step(i):
+        lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
+                                   slate.data_ptr(), loss.data_ptr(), grad.data_ptr(), ws.data_ptr(), rt.stream_ptr())
+
+    sec = _time(step, iters)
+    return {"metric": "approxNDCG fwd+bwd slates/s (n=1024)", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
+            "config": {"workload": f"{B} slates x {n} docs, valid len U{{512..1024}}, alpha=10"},
+            "roofline": {"bound": "sfu", "achieved": 2.0 * pairs / sec / 1e12, "unit": "TSFU-op/s",
+                         "algorithmic": f"2 SFU ops per ordered valid pair, {pairs} pairs per launch",
+                         "kernel": "approx_ndcg_kernel<256>"}}
+
+
+def bench_ndcg_1024(iters=30):
+    """BASELINE configs[4] evaluation sweep: 8192 queries x 1024 docs."""
+    return bench_ndcg(iters, Q=8192, n=1024)
+
+
+ALL = {"listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg1024": bench_ndcg_1024, "lambda": bench_lambda,
+       "georisk": bench_georisk, "approx1024": bench_approx_1024}
+
+
+def run_all(only=None, iters=None):
+    out = {}
+    for name, fn in ALL.items():
+        if only and name not in only:
+            continue
+        out[name] = fn(iters) if iters else fn()
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=0)
+    ap.add_argument("--profile", action="store_true")
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    res = run_all([x for x in a.only.split(",") if x] or None, 3 if a.profile else (a.iters or None))
+    for k, v in res.items():
+        print(json.dumps({k: v}))
