@@ -345,10 +345,14 @@ def run_b200_arm(args, rank, local_rank, world):
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": {
-            "bound": "sfu", "achieved": achieved / 1e12, "peak": sfu_peak / 1e12, "unit": "TSFU-op/s",
+            "bound": "sfu", "bound_note": "pairwise kernel: MUFU (SFU) pipe roofline as BASELINE.json north_star asks; "
+                                           "the HBM view of the same kernel is in roofline_hbm",
+            "achieved": achieved / 1e12, "peak": sfu_peak / 1e12, "unit": "TSFU-op/s",
             "frac": achieved / sfu_peak, "traffic": traffic,
-            "kernel": "approx_ndcg_kernel<128>", "kernel_us": t_launch * 1e6,
-            "algorithmic": f"2 SFU ops per ordered valid pair, {mean_pairs:.0f} pairs per launch (SURVEY 8d)",
+            "kernel": "approx_ndcg_sym_kernel", "kernel_us": t_launch * 1e6,
+            "algorithmic": f"2 SFU ops per ordered valid pair, {mean_pairs:.0f} pairs per launch (SURVEY 8d); the kernel "
+                           "itself issues 1 MUFU.RCP per ordered pair (sigma_ji = 1 - sigma_ij), so frac may exceed 0.5 "
+                           "of the pipe's busy time and is capped at 2.0",
             "peak_source": "measured in this run: pure ex2.approx loop (ltr_probe_sfu)",
             "peak_nominal": 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
             "fp32_peak_measured_tflane_ops": fma_peak / 1e12,
@@ -357,6 +361,15 @@ def run_b200_arm(args, rank, local_rank, world):
                          "frac": alg_bytes / t_launch / 1e9 / hbm_peak, "peak_source": hbm_src,
                          "note": "pairwise kernel is SFU/issue bound; HBM view shown for completeness"},
     }
+    if world == 1 and not args.no_secondary:
+        # the other kernel families of the path (ListNet, NDCG@k sweep, LambdaLoss, GeoRisk, approxNDCG n=1024):
+        # measured by tools/bench_paths.py with CUDA events; reported beside the headline, never mixed into it
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_paths
+            line["secondary"] = bench_paths.run_all()
+        except Exception as exc:                      # the headline line must still be printed
+            line["secondary"] = {"error": repr(exc)}
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "1024 slates x 128 docs fwd+bwd, best of 3, torch CPU fp32 "
@@ -371,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python (no CUDA graph)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary kernel-family measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

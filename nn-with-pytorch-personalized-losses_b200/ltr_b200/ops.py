@@ -13,7 +13,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib, _runtime as rt
+from . import _lib, _runtime as rt, sharding
 
 TIES_STABLE, TIES_STDSORT, TIES_REVERSED = 0, 1, 2
 
@@ -264,7 +264,7 @@ def _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, want_gq, w
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     gq = torch.empty(Q, dtype=torch.float32, device=dev) if want_gq else None
     gmat = torch.empty(Q, C, dtype=torch.float32, device=dev) if want_gmat else None
-    sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+    sharded = sharding.is_sharded(group)
 
     def phase(i):
         _lib.check(lib.ltr_risk_phase(i, mat.data_ptr(), Q, C, int(kind), int(invert), int(strategy), int(quirk),
@@ -273,11 +273,10 @@ def _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, want_gq, w
 
     phase(1)
     if sharded:
-        torch.distributed.all_reduce(state[0, 0:1], op=torch.distributed.ReduceOp.MAX, group=group)
-        torch.distributed.all_reduce(state[0, 1:5], op=torch.distributed.ReduceOp.SUM, group=group)
+        sharding.allreduce_risk_state1(state[0], group)
     phase(2)
     if sharded:
-        torch.distributed.all_reduce(state[1], op=torch.distributed.ReduceOp.SUM, group=group)
+        sharding.allreduce_risk_state2(state[1], group)
     phase(3)
     return loss, gq, gmat
 

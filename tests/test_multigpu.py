@@ -1,0 +1,105 @@
+"""Query sharding on real GPUs (needs >= 2 devices: `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`).
+Every rank runs the kernels on its own contiguous query range; the risk losses all-reduce their phase states over NCCL.
+The sharded result must equal the single-GPU result on the whole batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_ROOT, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_q):
+    import sys
+    for p in (ROOT, PKG_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from ltr_b200 import sharding
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    from ltr_b200.losses.lambdaL import lambdaLoss
+    from ltr_b200.losses.riskLosses import riskLosses as RL
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = torch.Generator().manual_seed(11)
+        B, n, S = 301, 128, 2
+        s = torch.randn(B, n, generator=g)
+        y = torch.randint(0, 5, (B, n), generator=g).float()
+        base = torch.randn(B, n, S, generator=g)
+        lo, hi = sharding.shard_bounds(B, rank, world)
+        res = {}
+        for name, fn, kw in (("geoListnet", RL.geoRiskListnetLoss, dict(listnet_transformation=1, return_strategy=1)),
+                             ("zListnet_rs3", RL.zRiskListnetLoss, dict(listnet_transformation=3, return_strategy=3,
+                                                                        add_ideal_ranking_to_mat=2)),
+                             ("geoLambda", RL.geoRiskLambdaLoss, dict(listnet_transformation=1, return_strategy=2,
+                                                                      add_ideal_ranking_to_mat=2))):
+            sl = s[lo:hi].cuda().requires_grad_(True)
+            loss = fn(sl, y[lo:hi].cuda(), base[lo:hi].cuda(), process_group=dist.group.WORLD, **kw)
+            loss.sum().backward()
+            res[name] = (loss.detach().cpu().numpy(), sl.grad.cpu().numpy())
+        # per-slate losses: no collective on the data path, only scalar bookkeeping
+        sl = s[lo:hi].cuda().requires_grad_(True)
+        yl = y[lo:hi].cuda()
+        la = approxNDCGLoss(sl, yl, alpha=10.0)
+        res["approx_mean"] = float(sharding.global_mean(la, hi - lo, dist.group.WORLD))
+        ll = lambdaLoss(sl, yl, weighing_scheme="ndcgLoss2PP_scheme")
+        res["lambda_sum"] = float(sharding.global_sum(ll, dist.group.WORLD))
+        out_q.put((rank, (lo, hi), res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_query_sharded_losses_match_single_gpu():
+    import torch.multiprocessing as mp
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    from ltr_b200.losses.lambdaL import lambdaLoss
+    from ltr_b200.losses.riskLosses import riskLosses as RL
+    from ltr_testing import assert_grad_close, assert_loss_close
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(11)
+    B, n, S = 301, 128, 2
+    s = torch.randn(B, n, generator=g)
+    y = torch.randint(0, 5, (B, n), generator=g).float()
+    base = torch.randn(B, n, S, generator=g)
+    single = {}
+    for name, fn, kw in (("geoListnet", RL.geoRiskListnetLoss, dict(listnet_transformation=1, return_strategy=1)),
+                         ("zListnet_rs3", RL.zRiskListnetLoss, dict(listnet_transformation=3, return_strategy=3,
+                                                                    add_ideal_ranking_to_mat=2)),
+                         ("geoLambda", RL.geoRiskLambdaLoss, dict(listnet_transformation=1, return_strategy=2,
+                                                                  add_ideal_ranking_to_mat=2))):
+        sd = s.cuda().requires_grad_(True)
+        loss = fn(sd, y.cuda(), base.cuda(), **kw)
+        loss.sum().backward()
+        single[name] = (loss.detach().cpu().numpy(), sd.grad.cpu().numpy())
+    for rank, (lo, hi), res in outs:
+        for name, (loss1, grad1) in single.items():
+            assert_loss_close(res[name][0], loss1, rtol=2e-6)
+            assert_grad_close(res[name][1], grad1[lo:hi], rtol=1e-5)
+        a = approxNDCGLoss(s.cuda(), y.cuda(), alpha=10.0)
+        assert abs(res["approx_mean"] - float(a)) <= 1e-6 * abs(float(a))
+        ls = lambdaLoss(s.cuda(), y.cuda(), weighing_scheme="ndcgLoss2PP_scheme")
+        assert abs(res["lambda_sum"] - float(ls)) <= 1e-5 * abs(float(ls))
