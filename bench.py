@@ -206,7 +206,7 @@ def run_b200_arm(args, rank, local_rank, world):
         k = i % RING
         rc = lib.ltr_approx_ndcg_fwdbwd(d_s[k].data_ptr(), d_y[k].data_ptr(), B, n, ALPHA, 1e-10, -1.0,
                                         tab.data_ptr(), tab.numel(), d_slate.data_ptr(), d_loss.data_ptr(),
-                                        d_grad[k].data_ptr(), ws.data_ptr(), stream)
+                                        d_grad[k].data_ptr(), None, 0, ws.data_ptr(), stream)
         if rc:
             _lib.check(rc, "ltr_approx_ndcg_fwdbwd")
 

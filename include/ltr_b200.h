@@ -51,11 +51,15 @@ int ltr_fill_disc_prefix(double* disc_prefix, int len, void* stream);
  *   slate_ndcg     : [B]    out, per-slate approximate NDCG (sum_i G_i / log2(1+pos_i))
  *   loss           : [1]    out, -mean_b slate_ndcg[b]               (approxNDCG.py:53)
  *   grad           : [B, n] out, d loss / d y_pred (0 for padded docs); NULL = forward only
- * One CTA per slate, pairs evaluated in registers; no [B,n,n] tensor exists anywhere.
+ *   scratch        : ltr_approx_ndcg_scratch_bytes(B, n) bytes of device memory, or NULL.  With it, batches of few
+ *                    long slates (n > 256) spread every slate over ceil(n/128) CTAs (rank launch, gradient launch).
+ * Pairs are evaluated in registers; no [B,n,n] tensor exists anywhere.
  */
+size_t ltr_approx_ndcg_scratch_bytes(int B, int n);
 int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float alpha, float eps,
                            float pad_value, const double* disc_prefix, int disc_len, float* slate_ndcg,
-                           float* loss, float* grad, void* workspace, void* stream);
+                           float* loss, float* grad, void* scratch, size_t scratch_bytes, void* workspace,
+                           void* stream);
 
 /*
  * Same computation from HOST buffers (pinned for asynchrony): H2D of y_pred / y_true, the fused

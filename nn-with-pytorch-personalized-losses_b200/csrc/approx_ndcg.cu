@@ -24,16 +24,21 @@ __device__ __forceinline__ float pair_p(float row, float col, float scale) {
     return ex2_approx(fminf((row - col) * scale, 126.0f));            // row = s_i, col = s_j (raw scores)
 }
 
-template <int THREADS, bool FACT, bool CLAMP>
+// PHASE 0: both passes over all rows of the slate (one CTA per slate).  PHASE 1 / 2: the rank pass / the gradient
+// pass over the rows [row_lo, row_hi) only -- long slates are split over several CTAs (and two launches: the
+// gradient pass needs every doc's d loss / d pos, exchanged through p.cbuf).
+template <int THREADS, bool FACT, bool CLAMP, int PHASE>
 __device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m, float scale, const float* sh_row,
                                             const float* sh_col, float* sh_c, const float* sh_g,
-                                            const int* sh_idx, float* red) {
+                                            const int* sh_idx, float* red, int row_lo, int row_hi) {
     const int tid = threadIdx.x;
     const int m4 = (m + 3) & ~3;
     const float eps = p.eps;
+    if (row_hi > m) row_hi = m;
     // ---------------- pass 1: soft ranks, per-doc dloss/dpos, slate value -----------------
     float ndcg_part = 0.f;
-    for (int i = tid; i < m; i += THREADS) {
+    if (PHASE != 2)
+    for (int i = row_lo + tid; i < row_hi; i += THREADS) {
         const float r = sh_row[i];
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
@@ -56,14 +61,21 @@ __device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m,
         const float l2 = log2f(1.0f + pos);
         const float g = sh_g[i];
         ndcg_part += g / l2;
-        sh_c[i] = p.inv_B * g / (kLn2 * (1.0f + pos) * l2 * l2);
+        const float ci = p.inv_B * g / (kLn2 * (1.0f + pos) * l2 * l2);
+        if (PHASE == 1) p.cbuf[(size_t)b * p.n + i] = ci;
+        else sh_c[i] = ci;
     }
-    const float ndcg = block_sum<THREADS>(ndcg_part, red);   // also orders sh_c writes before pass 2
-    if (tid == 0) p.slate_out[b] = ndcg;
-    if (p.grad == nullptr) return;
+    if (PHASE != 2) {
+        const float ndcg = block_sum<THREADS>(ndcg_part, red);   // also orders sh_c writes before pass 2
+        if (tid == 0) {
+            if (PHASE == 1) p.part[(size_t)b * gridDim.x + blockIdx.x] = ndcg;
+            else p.slate_out[b] = ndcg;
+        }
+    }
+    if (PHASE == 1 || p.grad == nullptr) return;
     __syncthreads();
     // ---------------- pass 2: analytic gradient ---------------------------------------------
-    for (int i = tid; i < m; i += THREADS) {
+    for (int i = row_lo + tid; i < row_hi; i += THREADS) {
         const float r = sh_row[i];
         float A0 = 0.f, A1 = 0.f, W0 = 0.f, W1 = 0.f;
 #pragma unroll 4
@@ -102,7 +114,7 @@ __device__ __forceinline__ void pair_passes(const ApproxParams& p, int b, int m,
     }
 }
 
-template <int THREADS>
+template <int THREADS, int PHASE>
 __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int W = THREADS / 32;
@@ -124,10 +136,10 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
     const float inf = __int_as_float(0x7f800000);
 
     for (;;) {
-        if (tid == 0) sh_next = (int)atomicAdd(&p.ws[0], 1u);
+        if (PHASE == 0 && tid == 0) sh_next = (int)atomicAdd(&p.ws[0], 1u);
         if (tid < 16) sh_lvl[tid] = 0;
         __syncthreads();
-        const int b = sh_next;
+        const int b = (PHASE == 0) ? sh_next : (int)blockIdx.y;
         if (b >= p.B) break;
         const float* srow = p.s + (size_t)b * n;
         const float* yrow = p.y + (size_t)b * n;
@@ -165,15 +177,19 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
                 tmax = fmaxf(tmax, t);
                 lmax = fmaxf(lmax, yc);
                 all_int &= (yc == floorf(yc)) ? 1 : 0;
-            } else if (i < n && p.grad != nullptr) {
+            } else if (i < n && p.grad != nullptr && PHASE != 1 && (PHASE == 0 || blockIdx.x == 0)) {
                 p.grad[(size_t)b * n + i] = 0.f;            // padded docs get exactly 0
             }
             m += tot;
             __syncthreads();
         }
         if (m == 0) {                                        // fully padded slate: value 0, no gradient
-            if (tid == 0) p.slate_out[b] = 0.f;
-            continue;
+            if (tid == 0) {
+                if (PHASE == 0) p.slate_out[b] = 0.f;
+                if (PHASE == 1) p.part[(size_t)b * gridDim.x + blockIdx.x] = 0.f;
+            }
+            if (PHASE == 0) continue;
+            return;
         }
         // block reduce (min, max, label max, all-int flag)
         tmin = warp_min(tmin);
@@ -259,15 +275,26 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
         }
         __syncthreads();
 
-        if (fact) {
-            if (p.clamp) pair_passes<THREADS, true, true>(p, b, m, scale, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
-            else         pair_passes<THREADS, true, false>(p, b, m, scale, sh_a, sh_v, sh_c, sh_g, sh_idx, red);
-        } else {
-            if (p.clamp) pair_passes<THREADS, false, true>(p, b, m, scale, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
-            else         pair_passes<THREADS, false, false>(p, b, m, scale, sh_a, sh_a, sh_c, sh_g, sh_idx, red);
+        int row_lo = 0, row_hi = m;
+        if (PHASE != 0) {
+            row_lo = (int)blockIdx.x * p.rows_per_cta;
+            row_hi = row_lo + p.rows_per_cta;
+            if (PHASE == 2) {                                // every doc's d loss / d pos from the rank launch
+                for (int i = tid; i < m; i += THREADS) sh_c[i] = p.cbuf[(size_t)b * n + i];
+                __syncthreads();
+            }
         }
+        if (fact) {
+            if (p.clamp) pair_passes<THREADS, true, true, PHASE>(p, b, m, scale, sh_a, sh_v, sh_c, sh_g, sh_idx, red, row_lo, row_hi);
+            else         pair_passes<THREADS, true, false, PHASE>(p, b, m, scale, sh_a, sh_v, sh_c, sh_g, sh_idx, red, row_lo, row_hi);
+        } else {
+            if (p.clamp) pair_passes<THREADS, false, true, PHASE>(p, b, m, scale, sh_a, sh_a, sh_c, sh_g, sh_idx, red, row_lo, row_hi);
+            else         pair_passes<THREADS, false, false, PHASE>(p, b, m, scale, sh_a, sh_a, sh_c, sh_g, sh_idx, red, row_lo, row_hi);
+        }
+        if (PHASE != 0) return;
         __syncthreads();
     }
+    if (PHASE != 0) return;
 
     // ---- last CTA to finish reduces the per-slate values in a fixed order ------------------------
     __shared__ double dred[32];
@@ -303,18 +330,58 @@ static int launch_approx(const ApproxParams& p, cudaStream_t st) {
     static int occ_cached = 0;
     static size_t occ_smem = (size_t)-1;
     if (smem > 48 * 1024 && smem > attr_smem) {
-        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_kernel<THREADS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         attr_smem = smem;
     }
     if (occ_smem != smem) {
-        LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_kernel<THREADS>, THREADS,
+        LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_kernel<THREADS, 0>, THREADS,
                                                                smem));
         occ_smem = smem;
     }
     int grid = device_sm_count() * (occ_cached > 0 ? occ_cached : 1);
     if (grid > p.B) grid = p.B;
-    approx_ndcg_kernel<THREADS><<<grid, THREADS, smem, st>>>(p);
+    approx_ndcg_kernel<THREADS, 0><<<grid, THREADS, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// slate value = sum of its chunks' partial values; loss = -mean (fixed reduction shape, one CTA)
+__global__ void __launch_bounds__(256) approx_finish_kernel(const float* part, int nchunks, int B, float* slate_out,
+                                                            float* loss_out) {
+    __shared__ double red[8];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        float v = 0.f;
+        for (int c = 0; c < nchunks; ++c) v += part[(size_t)b * nchunks + c];
+        slate_out[b] = v;
+        acc += (double)v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        loss_out[0] = (float)(-t / (double)B);               // approxNDCG.py:53
+    }
+}
+
+// Long slates, few of them: rows of a slate are split over ceil(n / 128) CTAs, rank launch then gradient launch.
+static int launch_approx_split(ApproxParams p, cudaStream_t st) {
+    constexpr int THREADS = 128;
+    const size_t smem = (size_t)p.npad * 5 * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_kernel<THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_kernel<THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    p.rows_per_cta = THREADS;
+    const int nchunks = (p.n + THREADS - 1) / THREADS;
+    const dim3 grid(nchunks, p.B);
+    approx_ndcg_kernel<THREADS, 1><<<grid, THREADS, smem, st>>>(p);
+    if (p.grad) approx_ndcg_kernel<THREADS, 2><<<grid, THREADS, smem, st>>>(p);
+    approx_finish_kernel<<<1, 256, 0, st>>>(p.part, nchunks, p.B, p.slate_out, p.loss_out);
     return (int)cudaGetLastError();
 }
 
@@ -332,9 +399,16 @@ static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
 
 }  // namespace ltr
 
+LTR_API size_t ltr_approx_ndcg_scratch_bytes(int B, int n) {
+    if (B <= 0 || n <= ltr::SYM_N) return 0;
+    const size_t chunks = ((size_t)n + 127) / 128;
+    return ((size_t)B * n + (size_t)B * chunks) * sizeof(float);
+}
+
 LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float alpha, float eps,
                                    float pad_value, const double* disc_prefix, int disc_len, float* slate_ndcg,
-                                   float* loss, float* grad, void* workspace, void* stream) {
+                                   float* loss, float* grad, void* scratch, size_t scratch_bytes, void* workspace,
+                                   void* stream) {
     using namespace ltr;
     if (!y_pred || !y_true || !slate_ndcg || !loss || !workspace || B <= 0 || n <= 0)
         return set_error(LTR_EINVAL, "ltr_approx_ndcg_fwdbwd: null pointer or non-positive B/n");
@@ -358,9 +432,15 @@ LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int
     // the per-pair eps clamp moves pos_i (>= 1) by at most n*eps: below fp32 resolution for the default 1e-10
     p.clamp = ((double)n * (double)eps > 2e-7) ? 1 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    p.cbuf = reinterpret_cast<float*>(scratch);
+    p.part = p.cbuf ? p.cbuf + (size_t)B * n : nullptr;
+    p.rows_per_cta = 0;
     int rc;
     if (n <= SYM_N && !p.clamp && p.disc_prefix != nullptr && p.disc_len > SYM_N)
         rc = launch_approx_sym(p, st);                                 // symmetric pair schedule, 4 warps per slate
+    else if (n > 256 && scratch != nullptr && scratch_bytes >= ltr_approx_ndcg_scratch_bytes(B, n) &&
+             B < 8 * device_sm_count())
+        rc = launch_approx_split(p, st);                               // few long slates: several CTAs per slate
     else rc = (n <= 512) ? launch_approx<128>(p, st) : launch_approx<256>(p, st);
     return rc ? set_cuda_error(rc, "ltr_approx_ndcg_fwdbwd") : 0;
 }
@@ -393,7 +473,7 @@ LTR_API int ltr_approx_ndcg_fwdbwd_host(const float* h_y_pred, const float* h_y_
     LTR_CUDA(cudaMemcpyAsync(d_pred, h_y_pred, bytes, cudaMemcpyHostToDevice, st));
     LTR_CUDA(cudaMemcpyAsync(d_true, h_y_true, bytes, cudaMemcpyHostToDevice, st));
     int rc = ltr_approx_ndcg_fwdbwd(d_pred, d_true, B, n, alpha, eps, pad_value, disc_prefix, disc_len, d_slate, d_loss,
-                                    h_grad ? d_grad : nullptr, workspace, stream);
+                                    h_grad ? d_grad : nullptr, nullptr, 0, workspace, stream);
     if (rc) return rc;
     LTR_CUDA(cudaMemcpyAsync(h_loss, d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
     if (h_grad) LTR_CUDA(cudaMemcpyAsync(h_grad, d_grad, bytes, cudaMemcpyDeviceToHost, st));

@@ -43,6 +43,9 @@ struct ApproxParams {
     unsigned* ws;   // [0] next-slate counter, [1] finished-CTA counter, [2..3] 64-bit fixed-point loss sum,
                     // [4] non-finite flag (all left at 0)
     int clamp;      // 1: apply the eps clamp per pair exactly (large eps), 0: it is below fp32 resolution
+    float* cbuf;    // split path: [B, n] d loss / d pos of every compacted doc (rank launch -> gradient launch)
+    float* part;    // split path: [B, chunks] partial slate values
+    int rows_per_cta;
 };
 
 constexpr int SYM_N = 128;        // longest slate of the fast path
@@ -374,7 +377,10 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
     }
 }
 
-__global__ void __launch_bounds__(SYM_THREADS, 8) approx_ndcg_sym_kernel(const ApproxParams p) {
+#ifndef SYM_MIN_CTAS
+#define SYM_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_kernel(const ApproxParams p) {
     __shared__ __align__(16) SymShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n;
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(SYM_THREADS, 8) approx_ndcg_sym_kernel(const A
                 gain = gain_exp2(yc);
                 __syncthreads();
             }
-            doc.gain = gain / maxdcg;                            // G_i (approxNDCG.py:44)
+            doc.gain = __fdividef(gain, maxdcg);                 // G_i (approxNDCG.py:44)
 
             // ---- compacted per-doc quantities -----------------------------------------------------
             const float smin = float_from_key(gmin), smax = float_from_key(gmax);

@@ -39,8 +39,9 @@ __device__ __forceinline__ float pair_weight(int i, int j, const float* G, const
 template <bool PRECISE = false>
 __device__ __forceinline__ void pair_logprob(float delta, float w, float sig_scale, float log_eps2, float out_scale,
                                              float& l, float& dl) {
-    // lambdaL.py:49-50: clamp to +-1e8, NaN (-inf - -inf) -> 0
-    delta = (delta != delta) ? 0.f : fminf(fmaxf(delta, -1e8f), 1e8f);
+    // lambdaL.py:49-50: clamp to +-1e8, NaN (-inf - -inf) -> 0.  The clamp itself is subsumed by the exponent cap
+    // below (2^126 and 2^-inf = 0 are reached long before |delta| = 1e8 for any sigma that is not denormal).
+    delta = (delta != delta) ? 0.f : delta;
     const float x = fminf(-sig_scale * delta, 126.0f);
     const float e = PRECISE ? exp2f(x) : ex2_approx(x);           // exp(-sigma delta)
     const float q = 1.0f + e;

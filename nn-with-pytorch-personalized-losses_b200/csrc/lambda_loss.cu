@@ -32,6 +32,140 @@ struct LambdaParams {
     float* grad;                // [B, n] d(-sum)/d y_pred, unscaled; null = forward only
 };
 
+// ---- symmetric pair schedule for top-k blocks of up to 256 docs --------------------------------------
+// Same block-circulant ownership as the approxNDCG fast path: lane a of every warp owns R consecutive
+// rank positions (score, label, gain, 1/D in registers); at step D it meets the R docs of block (a + D) mod T,
+// which travel from lane to lane by warp shuffle together with their gradient accumulators.  Every
+// UNORDERED pair is visited once (twice at weight 1/2 on the antipodal step of an even T): the doc with
+// the larger label is the "hi" side, one evaluation gives the loss term and both gradient contributions.
+// Steps are split over the 4 warps; partial gradients meet in shared memory.
+struct LDoc {
+    float s, y, g, d;      // score, label (NaN: not a doc of the block), gain, 1 / log2(1 + rank)
+};
+
+template <int SCHEME>
+__device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b, int ib, float h, const float* dtab,
+                                            float mu, float sig_scale, float log_eps2, float out_scale, float& loss,
+                                            float& cnt, float& ga, float& gb) {
+    // docs outside the block carry y = NaN: every ordered comparison with them is false
+    if (SCHEME == SCHEME_NDCG1) {
+        if (!(a.y == a.y) || !(b.y == b.y)) return;
+        // no label condition: both ordered pairs are in the mask, weight G_i / D_i of the FIRST doc (lambdaL.py:96-97)
+        float l1, d1, l2, d2;
+        pair_logprob(a.s - b.s, a.g * a.d, sig_scale, log_eps2, out_scale, l1, d1);
+        pair_logprob(b.s - a.s, b.g * b.d, sig_scale, log_eps2, out_scale, l2, d2);
+        loss = fmaf(h, l1 + l2, loss);
+        cnt = fmaf(h, 2.0f, cnt);
+        const float dd = h * (d2 - d1);
+        ga += dd;
+        gb -= dd;
+        return;
+    }
+    const bool a_hi = a.y > b.y;
+    if (!a_hi && !(a.y < b.y)) return;        // equal labels, or one of the two is not a doc of the block
+    float w;
+    if (SCHEME == SCHEME_NONE) w = 1.0f;
+    else if (SCHEME == SCHEME_GTDIFF) w = fabsf(fmaxf(a.y, 0.f) - fmaxf(b.y, 0.f));
+    else if (SCHEME == SCHEME_GTDIFF_POW) {
+        const float u = fmaxf(a.y, 0.f), v = fmaxf(b.y, 0.f);
+        w = fabsf(u * u - v * v);
+    } else {
+        const float dg = fabsf(a.g - b.g);
+        const int gap = ia > ib ? ia - ib : ib - ia;
+        if (SCHEME == SCHEME_NDCG2) w = dtab[gap] * dg;
+        else if (SCHEME == SCHEME_LAMBDARANK) w = fabsf(a.d - b.d) * dg;
+        else w = mu * (dtab[gap] * dg) + fabsf(a.d - b.d) * dg;
+    }
+    float l, dl;
+    pair_logprob(a_hi ? a.s - b.s : b.s - a.s, w, sig_scale, log_eps2, out_scale, l, dl);
+    loss = fmaf(h, l, loss);
+    cnt += h;
+    dl *= a_hi ? -h : h;                      // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
+    ga += dl;
+    gb -= dl;
+}
+
+// K, Y, G, invD: the slate in rank order (Y = -inf beyond the block); gpart: [4][2][256] floats of shared memory.
+// On exit gpart holds the per-warp row / column partial gradients of positions 0 .. lim-1 (after a barrier).
+template <int SCHEME, int R>
+__device__ __forceinline__ void lambda_sym_slate(const float* K, const float* Y, const float* G, const float* invD,
+                                                 const float* dtab, int lim, int b, float mu, float sig_scale,
+                                                 float log_eps2, float out_scale, float* gpart, float& loss, float& cnt) {
+    const float ninf = __int_as_float(0x7fc00000);           // (a quiet NaN marks "not a doc of the block")
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = (lim + R - 1) / R;
+    const int S = T >> 1;
+    const int role = (warp + b) & 3;
+    const int d_lo = 1 + ((role * S) >> 2);
+    const int d_hi = 1 + (((role + 1) * S) >> 2);
+    const bool active = lane < T;
+    const int src = active ? ((lane + 1 == T) ? 0 : lane + 1) : lane;
+    int cb = lane + d_lo;
+    if (cb >= T) cb -= T;
+    if (!active) cb = 0;
+    LDoc row[R], col[R];
+    float g_r[R], g_c[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = lane * R + r, j = cb * R + r;
+        const bool vi = active && i < lim, vj = active && j < lim;
+        row[r].s = vi ? K[i] : 0.f; row[r].y = vi ? Y[i] : ninf; row[r].g = vi ? G[i] : 0.f; row[r].d = vi ? invD[i] : 0.f;
+        col[r].s = vj ? K[j] : 0.f; col[r].y = vj ? Y[j] : ninf; col[r].g = vj ? G[j] : 0.f; col[r].d = vj ? invD[j] : 0.f;
+        g_r[r] = 0.f;
+        g_c[r] = 0.f;
+    }
+    if (role == 0) {                          // pairs inside the lane's own block (+ the diagonal of ndcgLoss1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (SCHEME == SCHEME_NDCG1 && row[r].y == row[r].y) {
+                float l, dl;
+                pair_logprob(0.f, row[r].g * row[r].d, sig_scale, log_eps2, out_scale, l, dl);
+                loss += l;
+                cnt += 1.0f;
+            }
+#pragma unroll
+            for (int c = r + 1; c < R; ++c)
+                lambda_pair<SCHEME>(row[r], lane * R + r, row[c], lane * R + c, 1.0f, dtab, mu, sig_scale, log_eps2,
+                                    out_scale, loss, cnt, g_r[r], g_r[c]);
+        }
+    }
+#pragma unroll 1
+    for (int D = d_lo; D < d_hi; ++D) {
+        const float h = (2 * D == T) ? 0.5f : 1.0f;
+        int cblk = lane + D;                   // block visiting this lane at step D
+        if (cblk >= T) cblk -= T;
+        const int j0 = cblk * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int c = 0; c < R; ++c)
+                lambda_pair<SCHEME>(row[r], lane * R + r, col[c], j0 + c, h, dtab, mu, sig_scale, log_eps2, out_scale, loss,
+                                    cnt, g_r[r], g_c[c]);
+        }
+        if (D + 1 < d_hi) {
+#pragma unroll
+            for (int c = 0; c < R; ++c) {
+                col[c].s = __shfl_sync(LTR_FULL_MASK, col[c].s, src);
+                col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
+                col[c].g = __shfl_sync(LTR_FULL_MASK, col[c].g, src);
+                col[c].d = __shfl_sync(LTR_FULL_MASK, col[c].d, src);
+                g_c[c] = __shfl_sync(LTR_FULL_MASK, g_c[c], src);
+            }
+        }
+    }
+    if (active) {
+        int cblk = lane + d_hi - 1;           // the block whose accumulators ended up here
+        if (cblk >= T) cblk -= T;
+        if (d_hi == d_lo) cblk = lane;        // nothing accumulated: zeros to the own slots
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            gpart[(warp * 2 + 0) * 256 + lane * R + r] = g_r[r];
+            gpart[(warp * 2 + 1) * 256 + cblk * R + r] = g_c[r];
+        }
+    }
+    __syncthreads();
+}
+
 template <int SCHEME>
 __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -44,6 +178,7 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
     float* G = Y + len;                                     // ideal labels, then gains in rank order
     float* invD = G + len;                                  // 1 / log2(1 + r), r = 1..n
     float* dtab = invD + len;                               // |1/D_t - 1/D_{t+1}| by rank gap t (0 on the diagonal)
+    float* gpart = dtab + len;                              // [4 warps][row / column][256] partial gradients (symmetric path)
     const float ninf = __int_as_float(0xff800000);
     const int tid = threadIdx.x;
 
@@ -102,6 +237,21 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
         // ---- pair loop over the top-k block of real docs -------------------------------------------
         const int lim = kk < m ? kk : m;
         float loss_part = 0.f, cnt_part = 0.f;
+        if (lim <= 256) {
+            if (lim > 128) lambda_sym_slate<SCHEME, 8>(K, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, out_scale, gpart, loss_part, cnt_part);
+            else if (lim > 64) lambda_sym_slate<SCHEME, 4>(K, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, out_scale, gpart, loss_part, cnt_part);
+            else lambda_sym_slate<SCHEME, 2>(K, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, out_scale, gpart, loss_part, cnt_part);
+            if (p.grad) {
+                for (int i = tid; i < n; i += LAMBDA_THREADS) {
+                    float g = 0.f;
+                    if (i < lim) {
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8) g += gpart[k8 * 256 + i];
+                    }
+                    p.grad[(size_t)b * n + I[i]] = g * grad_scale;     // docs outside the block / padding: 0
+                }
+            }
+        } else
         for (int i = tid; i < n; i += LAMBDA_THREADS) {
             float g = 0.f;
             if (i < lim) {
@@ -200,7 +350,7 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
     while (p.len < n) p.len <<= 1;
     p.eps = eps; p.pad = pad_value; p.sigma = sigma; p.mu = mu; p.natural_log = natural_log;
     p.slate_sum = slate_sum; p.slate_cnt = slate_count; p.grad = grad;
-    const size_t smem = (size_t)p.len * 6 * sizeof(float);
+    const size_t smem = ((size_t)p.len * 6 + 8 * 256) * sizeof(float);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int cap = device_sm_count() * 8;
     const int grid = B < cap ? B : cap;

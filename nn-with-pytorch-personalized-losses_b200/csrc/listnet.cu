@@ -241,10 +241,23 @@ LTR_API int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, 
     ListnetParams p{y_true, y_pred, B, n, apply_sigmoid, slate_loss, loss, grad, ws_partials(workspace),
                     ws_counter(workspace, LTR_WS_STREAM_COUNTER)};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int grid = stream_grid(B);
+    int grid = stream_grid(B);
     const bool vec = !apply_sigmoid && (n % 4 == 0) && n <= 512 &&
                      ((reinterpret_cast<uintptr_t>(y_true) | reinterpret_cast<uintptr_t>(y_pred) |
                        reinterpret_cast<uintptr_t>(grad)) % 16 == 0);
+    if (vec) {
+        // one resident wave: the slate assignment is static, a partial second wave would only add a tail
+        static int occ[3] = {0, 0, 0};
+        const int which = n <= 128 ? 0 : (n <= 256 ? 1 : 2);
+        if (occ[which] == 0) {
+            if (which == 0) LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], listnet_vec_kernel<1>, STREAM_THREADS, 0));
+            else if (which == 1) LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], listnet_vec_kernel<2>, STREAM_THREADS, 0));
+            else LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], listnet_vec_kernel<4>, STREAM_THREADS, 0));
+            if (occ[which] <= 0) occ[which] = 1;
+        }
+        const int cap = device_sm_count() * occ[which];
+        if (grid > cap) grid = cap;
+    }
     if (vec && n <= 128) listnet_vec_kernel<1><<<grid, STREAM_THREADS, 0, st>>>(p);
     else if (vec && n <= 256) listnet_vec_kernel<2><<<grid, STREAM_THREADS, 0, st>>>(p);
     else if (vec) listnet_vec_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);

@@ -295,6 +295,133 @@ __global__ void __launch_bounds__(256) ndcg_topk_kernel(const NdcgParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Long rows (256 < n <= 1024): one CTA of 4 warps per query.  Every warp extracts the top-kmax (key, label)
+// candidates of its 256-doc quarter with the rounds above (8 docs per lane, so registers stay low and many
+// queries are resident per SM), the per-warp label histograms and candidates meet in shared memory, and warp 0
+// runs the same rounds over the <= 4 kmax candidates.  Any tie met on the way, and labels that are not integers
+// 0..7, send the query to the full-sort kernel.
+template <bool F64>
+__global__ void __launch_bounds__(128) ndcg_topk_wide_kernel(const NdcgParams p) {
+    constexpr int ITEMS = 8;
+    __shared__ int cand_key[4][32];
+    __shared__ float cand_lab[4][32];
+    __shared__ int hist[4][8];
+    __shared__ int sh_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TAKEN = (int)0x80000000;
+    int myk = -1;
+    for (int j = 0; j < p.nk; ++j) myk = (lane == j) ? p.ks[j] : myk;
+    if (tid == 0) sh_flag = 0;
+    __syncthreads();
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const float* sp = p.y_pred + (size_t)b * p.n;
+        const float* yp = p.y_true + (size_t)b * p.n;
+        int ks_[ITEMS];
+        float yv[ITEMS];
+        bool small_int = true;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int i = warp * 256 + lane + 32 * k;
+            const bool in = i < p.n;
+            const float s = in ? ld_stream(sp + i) : 0.f;
+            yv[k] = in ? ld_stream(yp + i) : 0.f;
+            ks_[k] = in ? topk_key(s) : TAKEN;
+            const int lv = (int)fminf(fmaxf(yv[k], -1.f), 8.f);
+            small_int = small_int && (!in || ((float)lv == yv[k] && lv >= 0 && lv <= 7));
+        }
+        int bad = __all_sync(LTR_FULL_MASK, small_int) ? 0 : 1;
+        // per-warp label histogram (levels 1..7)
+        for (int L = 1; L <= 7; ++L) {
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k)
+                c += __popc(__ballot_sync(LTR_FULL_MASK, (warp * 256 + lane + 32 * k < p.n) && yv[k] == (float)L));
+            if (lane == 0) hist[warp][L] = c;
+        }
+        // per-warp candidates
+        int ckey = TAKEN;
+        float clab = 0.f;
+        for (int r = 0; r < p.kmax; ++r) {
+            const int wk = __reduce_max_sync(LTR_FULL_MASK, tree_max(ks_));
+            int hits = 0;
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const bool hit = (ks_[k] == wk) && (wk != TAKEN);
+                hits += hit ? 1 : 0;
+                mine = hit ? yv[k] : mine;
+                ks_[k] = hit ? TAKEN : ks_[k];
+            }
+            const unsigned owners = __ballot_sync(LTR_FULL_MASK, hits > 0);
+            if (__popc(owners) > 1 || __any_sync(LTR_FULL_MASK, hits > 1)) bad = 1;
+            const float labw = __shfl_sync(LTR_FULL_MASK, mine, owners ? __ffs(owners) - 1 : 0);
+            if (lane == r) { ckey = wk; clab = labw; }
+        }
+        cand_key[warp][lane] = (lane < p.kmax) ? ckey : TAKEN;
+        cand_lab[warp][lane] = clab;
+        if (bad && lane == 0) sh_flag = 1;       // (benign race: every writer stores 1)
+        __syncthreads();
+        if (warp == 0) {
+            int tie = sh_flag;
+            __syncwarp();
+            if (lane == 0) sh_flag = 0;          // re-armed for the next query (ordered by the barrier below)
+            int mk[4];
+            float ml[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mk[k] = cand_key[k][lane], ml[k] = cand_lab[k][lane];
+            float lab_pred = 0.f;
+            for (int r = 0; r < p.kmax && !tie; ++r) {
+                const int wk = __reduce_max_sync(LTR_FULL_MASK, tree_max(mk));
+                int hits = 0;
+                float mine = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool hit = (mk[k] == wk) && (wk != TAKEN);
+                    hits += hit ? 1 : 0;
+                    mine = hit ? ml[k] : mine;
+                    mk[k] = hit ? TAKEN : mk[k];
+                }
+                const unsigned owners = __ballot_sync(LTR_FULL_MASK, hits > 0);
+                if (__popc(owners) > 1 || __any_sync(LTR_FULL_MASK, hits > 1)) tie = 1;
+                const float labw = __shfl_sync(LTR_FULL_MASK, mine, owners ? __ffs(owners) - 1 : 0);
+                if (lane == r) lab_pred = (wk == TAKEN) ? 0.f : labw;
+            }
+            if (tie) {
+                if (lane == 0) p.flags[1 + atomicAdd(p.flags, 1)] = b;
+            } else {
+                int ge = 0, cum = 0;
+                for (int L = 7; L >= 1; --L) {
+                    cum += (hist[0][L] + hist[1][L]) + (hist[2][L] + hist[3][L]);
+                    ge += (cum > lane) ? 1 : 0;
+                }
+                const float lab_ideal = (float)ge;
+                if (!F64) {
+                    const float d = (lane < p.kmax) ? p.disc32[lane] : 1.0f;
+                    const float tp = (exp2f(lab_pred) - 1.0f) / d, ti = (exp2f(lab_ideal) - 1.0f) / d;
+                    float got = 0.f, ideal = 0.f;
+                    for (int r = 0; r < p.kmax; ++r) {
+                        got += __shfl_sync(LTR_FULL_MASK, tp, r);
+                        ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
+                        if (myk == r + 1) p.out32[(size_t)b * p.nk + lane] = got / ideal;
+                    }
+                } else {
+                    const double d = (lane < p.kmax) ? p.disc64[lane] : 1.0;
+                    const double lp = (double)lab_pred, li = (double)lab_ideal;
+                    const double tp = (p.exp_gains ? exp2(lp) - 1.0 : lp) / d, ti = (p.exp_gains ? exp2(li) - 1.0 : li) / d;
+                    double got = 0.0, ideal = 0.0;
+                    for (int r = 0; r < p.kmax; ++r) {
+                        got += __shfl_sync(LTR_FULL_MASK, tp, r);
+                        ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
+                        if (myk == r + 1) p.out64[(size_t)b * p.nk + lane] = (ideal == 0.0) ? p.empty_value : got / ideal;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // exactNDCG (MODE 0) and orderScore (MODE 1).  Both work on softmax(y_true) / softmax(y_pred).
 struct RankLossParams {
     const float* y_true;
@@ -433,12 +560,17 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
 #define LTR_TOPK(ITEMS)                                                      \
         if (f64) ndcg_topk_kernel<ITEMS, true><<<g, 256, 0, st>>>(p);            \
         else ndcg_topk_kernel<ITEMS, false><<<g, 256, 0, st>>>(p)
+        bool wide = false;
         if (p.n <= 128) { LTR_TOPK(4); }
         else if (p.n <= 256) { LTR_TOPK(8); }
-        else if (p.n <= 512) { LTR_TOPK(16); }
-        else { LTR_TOPK(32); }
+        else {
+            wide = true;                           // ties of any rule go to the full sort there
+            const int gw = p.B < cap ? p.B : cap;
+            if (f64) ndcg_topk_wide_kernel<true><<<gw, 128, 0, st>>>(p);
+            else ndcg_topk_wide_kernel<false><<<gw, 128, 0, st>>>(p);
+        }
 #undef LTR_TOPK
-        if (p.tie_rule != TIES_STDSORT || p.n <= 16) {
+        if (!wide && (p.tie_rule != TIES_STDSORT || p.n <= 16)) {
             const int rc0 = (int)cudaGetLastError();
             return rc0 ? set_cuda_error(rc0, "ltr_ndcg_at_k") : 0;
         }

@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libltr_b200.so")
+LIB_PATH = os.environ.get("LTR_B200_LIB") or os.path.join(_HERE, "lib", "libltr_b200.so")   # (override: A/B builds)
 
 WORKSPACE_BYTES = 131072
 
@@ -20,7 +20,9 @@ _SIGNATURES = {
     "ltr_last_error": (c_char_p, []),
     "ltr_max_slate_len": (c_int, []),
     "ltr_fill_disc_prefix": (c_int, [_P, c_int, _P]),
-    "ltr_approx_ndcg_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P]),
+    "ltr_approx_ndcg_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "ltr_approx_ndcg_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P,
+                                       c_size_t, _P, _P]),
     "ltr_approx_ndcg_host_scratch_bytes": (c_size_t, [c_int, c_int]),
     "ltr_approx_ndcg_fwdbwd_host": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P,
                                             c_size_t, _P, _P]),

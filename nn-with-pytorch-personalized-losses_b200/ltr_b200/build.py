@@ -66,6 +66,31 @@ def _compile_one(nvcc, src, verbose):
     return obj, r.stderr
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B experiments: compile every source with extra -D flags into lib/variants/<name>/libltr_b200.so."""
+    nvcc = _nvcc()
+    out_dir = os.path.join(LIB_DIR, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+    for src in _sources():
+        obj = os.path.join(out_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr, file=sys.stderr)
+        objs.append(obj)
+    lib = os.path.join(out_dir, "libltr_b200.so")
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH

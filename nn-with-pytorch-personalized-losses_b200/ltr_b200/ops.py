@@ -47,10 +47,12 @@ class _ApproxNDCG(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         grad = torch.empty_like(y_pred) if need_grad else None
         tab = rt.disc_prefix(dev)
+        nscratch = lib.ltr_approx_ndcg_scratch_bytes(B, n)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev) if nscratch else None
         _lib.check(lib.ltr_approx_ndcg_fwdbwd(
             y_pred.data_ptr(), y_true.data_ptr(), B, n, float(alpha), float(eps), float(pad),
             tab.data_ptr(), tab.numel(), slate.data_ptr(), loss.data_ptr(),
-            _ptr(grad), rt.workspace(dev).data_ptr(), rt.stream_ptr()),
+            _ptr(grad), _ptr(scratch), nscratch, rt.workspace(dev).data_ptr(), rt.stream_ptr()),
             "ltr_approx_ndcg_fwdbwd")
         ctx.grad = grad
         ctx.slate_ndcg = slate

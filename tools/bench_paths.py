@@ -162,17 +162,20 @@ def bench_approx_1024(iters=50, B=64, n=1024):
     s, y = s.cuda(), y.cuda()
     grad, slate, loss = torch.empty_like(s), torch.empty(B, device="cuda"), torch.empty(1, device="cuda")
     tab, ws = rt.disc_prefix(dev), rt.workspace(dev)
+    nscratch = lib.ltr_approx_ndcg_scratch_bytes(B, n)
+    scratch = torch.empty(max(nscratch, 1), dtype=torch.uint8, device="cuda")
 
     def step(i):
         lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
-                                   slate.data_ptr(), loss.data_ptr(), grad.data_ptr(), ws.data_ptr(), rt.stream_ptr())
+                                   slate.data_ptr(), loss.data_ptr(), grad.data_ptr(), scratch.data_ptr(), nscratch,
+                                   ws.data_ptr(), rt.stream_ptr())
 
     sec = _time(step, iters)
     return {"metric": "approxNDCG fwd+bwd slates/s (n=1024)", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
             "config": {"workload": f"{B} slates x {n} docs, valid len U{{512..1024}}, alpha=10"},
             "roofline": {"bound": "sfu", "achieved": 2.0 * pairs / sec / 1e12, "unit": "TSFU-op/s",
                          "algorithmic": f"2 SFU ops per ordered valid pair, {pairs} pairs per launch",
-                         "kernel": "approx_ndcg_kernel<256>"}}
+                         "kernel": "approx_ndcg_kernel<128, 1> + <128, 2> (rows of a slate split over 8 CTAs)"}}
 
 
 def bench_ndcg_1024(iters=30):

@@ -22,7 +22,7 @@ loss = torch.empty(1, device=dev)
 tab, ws = rt.disc_prefix(dev), rt.workspace(dev)
 for _ in range(reps):
     _lib.check(lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
-                                          slate.data_ptr(), loss.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                                          slate.data_ptr(), loss.data_ptr(), grad.data_ptr(), None, 0, ws.data_ptr(),
                                           rt.stream_ptr()), "approx")
 torch.cuda.synchronize()
 print("loss", float(loss), "grad_abs_sum", float(grad.abs().sum()))
