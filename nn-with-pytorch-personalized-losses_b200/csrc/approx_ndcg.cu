@@ -391,7 +391,7 @@ static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
         LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_sym_kernel, SYM_THREADS, 0));
         if (occ_cached <= 0) occ_cached = 1;
     }
-    int grid = device_sm_count() * occ_cached;
+    int grid = device_sm_count() * ((SYM_GRID_PER_SM > 0 && SYM_GRID_PER_SM < occ_cached) ? SYM_GRID_PER_SM : occ_cached);
     if (grid > p.B) grid = p.B;
     approx_ndcg_sym_kernel<<<grid, SYM_THREADS, 0, st>>>(p);
     return (int)cudaGetLastError();

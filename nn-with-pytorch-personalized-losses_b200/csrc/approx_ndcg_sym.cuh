@@ -28,6 +28,17 @@
 #pragma once
 #include "ltr_common.cuh"
 
+// build-time knobs (A/B experiments: `ltr_b200.build.build_variant`)
+#ifndef SYM_MIN_CTAS
+#define SYM_MIN_CTAS 8       // resident CTAs per SM the register allocation is tuned for
+#endif
+#ifndef SYM_CLAIM_AHEAD
+#define SYM_CLAIM_AHEAD 0    // 1: claim the next slate index one slate ahead (hides the atomic latency; measured neutral)
+#endif
+#ifndef SYM_GRID_PER_SM
+#define SYM_GRID_PER_SM 0    // CTAs launched per SM (0: as many as are resident)
+#endif
+
 namespace ltr {
 
 struct ApproxParams {
@@ -101,8 +112,12 @@ __device__ __forceinline__ void slate_middle(const ApproxParams& p, SymShared& s
     ndcg_part = warp_sum(ndcg_part);
     if (lane == 0) sh.red[warp] = ndcg_part;
     if (tid == 0) {
+#if SYM_CLAIM_AHEAD
         sh.next_b = cy.claimed;                                   // claimed one slate ago: latency long hidden
         cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));  // result is first read a whole slate later
+#else
+        sh.next_b = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
+#endif
     }
     __syncthreads();
     if (tid == 0) {
@@ -377,9 +392,6 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
     }
 }
 
-#ifndef SYM_MIN_CTAS
-#define SYM_MIN_CTAS 8
-#endif
 __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_kernel(const ApproxParams p) {
     __shared__ __align__(16) SymShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -396,7 +408,9 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
     cy.fx = 0;
     cy.nonfinite = 0;
     cy.claimed = 0;
+#if SYM_CLAIM_AHEAD
     if (tid == 0) cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
+#endif
     for (int i = tid; i <= SYM_N; i += SYM_THREADS) sh.P[i] = p.disc_prefix[i];
     // (made visible by the first slate's barrier)
 
@@ -440,8 +454,12 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
         if (m == 0) {                                            // fully padded slate: value 0, no gradient
             if (tid == 0) {
                 p.slate_out[b] = 0.f;
+#if SYM_CLAIM_AHEAD
                 sh.next_b = cy.claimed;
                 cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
+#else
+                sh.next_b = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
+#endif
             }
             if (tid < n && p.grad != nullptr) p.grad[(size_t)b * n + tid] = 0.f;
             __syncthreads();
