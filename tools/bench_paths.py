@@ -178,13 +178,46 @@ def bench_approx_1024(iters=50, B=64, n=1024):
                          "kernel": "approx_ndcg_kernel<128, 1> + <128, 2> (rows of a slate split over 8 CTAs)"}}
 
 
+def bench_approx_large(iters=30, B=65536, n=128):
+    """The headline kernel on a 16x larger batch (launch ramp and tail amortised): same slate distribution."""
+    from ltr_b200 import _lib, _runtime as rt
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ring = 2
+    data = []
+    pairs = []
+    for i in range(ring):
+        g = torch.Generator().manual_seed(600 + i)
+        y = torch.randint(0, 5, (B, n), generator=g).float()
+        lens = torch.randint(n // 2, n + 1, (B,), generator=g)
+        y[torch.arange(n)[None, :] >= lens[:, None]] = -1.0
+        s = torch.randn(B, n, generator=g)
+        pairs.append(int((lens * (lens - 1)).sum()))
+        data.append((s.cuda(), y.cuda()))
+    grad = [torch.empty(B, n, device="cuda") for _ in range(ring)]
+    slate, loss = torch.empty(B, device="cuda"), torch.empty(1, device="cuda")
+    tab, ws = rt.disc_prefix(dev), rt.workspace(dev)
+
+    def step(i):
+        s, y = data[i % ring]
+        lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
+                                   slate.data_ptr(), loss.data_ptr(), grad[i % ring].data_ptr(), None, 0, ws.data_ptr(),
+                                   rt.stream_ptr())
+
+    sec = _time(step, iters)
+    return {"metric": "approxNDCG fwd+bwd slates/s (n=128, 65536 slates per launch)", "value": B / sec, "unit": "slates/s",
+            "us_per_call": sec * 1e6, "config": {"workload": f"{B} slates x {n} docs, valid len U{{64..128}}, alpha=10"},
+            "roofline": {"bound": "sfu", "achieved": 2.0 * (sum(pairs) / ring) / sec / 1e12, "unit": "TSFU-op/s",
+                         "algorithmic": "2 SFU ops per ordered valid pair", "kernel": "approx_ndcg_sym_kernel"}}
+
+
 def bench_ndcg_1024(iters=30):
     """BASELINE configs[4] evaluation sweep: 8192 queries x 1024 docs."""
     return bench_ndcg(iters, Q=8192, n=1024)
 
 
 ALL = {"listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg1024": bench_ndcg_1024, "lambda": bench_lambda,
-       "georisk": bench_georisk, "approx1024": bench_approx_1024}
+       "georisk": bench_georisk, "approx1024": bench_approx_1024, "approx_large_batch": bench_approx_large}
 
 
 def run_all(only=None, iters=None):
