@@ -61,8 +61,10 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b
         gb -= dd;
         return;
     }
+    // branch-free: every slot is evaluated and masked (equal labels and non-docs get weight 0), which costs ~20 %
+    // more MUFU work than skipping them but removes a divergent branch + reconvergence per pair
     const bool a_hi = a.y > b.y;
-    if (!a_hi && !(a.y < b.y)) return;        // equal labels, or one of the two is not a doc of the block
+    const float hv = (a_hi || (a.y < b.y)) ? h : 0.f;
     float w;
     if (SCHEME == SCHEME_NONE) w = 1.0f;
     else if (SCHEME == SCHEME_GTDIFF) w = fabsf(fmaxf(a.y, 0.f) - fmaxf(b.y, 0.f));
@@ -74,13 +76,14 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b
         const int gap = ia > ib ? ia - ib : ib - ia;
         if (SCHEME == SCHEME_NDCG2) w = dtab[gap] * dg;
         else if (SCHEME == SCHEME_LAMBDARANK) w = fabsf(a.d - b.d) * dg;
-        else w = mu * (dtab[gap] * dg) + fabsf(a.d - b.d) * dg;
+        else w = dg * fmaf(mu, dtab[gap], fabsf(a.d - b.d));
     }
+    const float d0 = a.s - b.s;
     float l, dl;
-    pair_logprob(a_hi ? a.s - b.s : b.s - a.s, w, sig_scale, log_eps2, out_scale, l, dl);
-    loss = fmaf(h, l, loss);
-    cnt += h;
-    dl *= a_hi ? -h : h;                      // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
+    pair_logprob(a_hi ? d0 : -d0, (hv != 0.f) ? w : 0.f, sig_scale, log_eps2, out_scale, l, dl);
+    loss = fmaf(hv, l, loss);
+    cnt += hv;
+    dl *= a_hi ? -hv : hv;                    // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
     ga += dl;
     gb -= dl;
 }

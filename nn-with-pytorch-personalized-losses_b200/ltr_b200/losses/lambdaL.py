@@ -38,21 +38,12 @@ def lambdaMask(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_
 
 def lambdaLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, weighing_scheme=None, k=None,
                sigma=1., mu=10., reduction="sum", reduction_log="binary"):
-    """
-    LambdaLoss framework for LTR losses implementations, introduced in "The LambdaLoss Framework for Ranking
-    Metric Optimization".  Contains implementations of different weighing schemes corresponding to e.g.
-    LambdaRank or RankNet.
-    :param y_pred: predictions from the model, shape [batch_size, slate_length]
-    :param y_true: ground truth labels, shape [batch_size, slate_length]
-    :param eps: epsilon value, used for numerical stability
-    :param padded_value_indicator: an indicator of the y_true index containing a padded item, e.g. -1
-    :param weighing_scheme: a string corresponding to a name of one of the weighing schemes
-    :param k: rank at which the loss is truncated
-    :param sigma: score difference weight used in the sigmoid function
-    :param mu: optional weight used in NDCGLoss2++ weighing scheme
-    :param reduction: losses reduction method, could be either a sum or a mean
-    :param reduction_log: logarithm variant used prior to masking and loss reduction, either binary or natural
-    :return: loss value, a torch.Tensor
+    """LambdaLoss (Wang et al., "The LambdaLoss Framework for Ranking Metric Optimization"): -sum / -mean over the
+    pairs (i, j) of real docs with label_i > label_j and both rank positions < k of log_b(sigmoid(sigma (s_i - s_j))^w_ij),
+    w_ij given by `weighing_scheme` (None, ndcgLoss1_scheme, ndcgLoss2_scheme, lamdbaRank_scheme, ndcgLoss2PP_scheme
+    with weight `mu`, rankNet_scheme, rankNetWeightedByGTDiff_scheme, rankNetWeightedByGTDiffPowed_scheme).
+    y_pred, y_true: [batch, slate]; labels equal to `padded_value_indicator` mark padding; `reduction` is "sum" or
+    "mean", `reduction_log` "binary" or "natural".  Returns a 0-dim tensor attached to autograd.
     """
     scheme = _scheme_id(weighing_scheme)
     if reduction_log not in ("natural", "binary"):

@@ -10,25 +10,18 @@ PADDED_Y_VALUE = -1
 
 
 def with_ordinals(y, n, padded_value_indicator=PADDED_Y_VALUE):
-    """
-    Helper of the reference (ordinal.py:9-24): labels [batch, slate] -> ordinals [batch, slate, n].
-    Index plumbing only (comparisons against 1..n); the loss kernel forms the same targets on the fly.
-    """
-    one_to_n = torch.arange(start=1, end=n + 1, dtype=torch.float, device=y.device)
-    unsqueezed = y.unsqueeze(2).repeat(1, 1, n)
-    mask = unsqueezed == padded_value_indicator
-    ordinals = (unsqueezed >= one_to_n).type(torch.float)
-    ordinals[mask] = padded_value_indicator
-    return ordinals
+    """Labels [batch, slate] -> ordinal targets [batch, slate, n]: target l is 1 when label >= l + 1, and every
+    target of a doc whose label equals the padding value is the padding value (reference ordinal.py:9-24).
+    Comparison / broadcast plumbing only; the loss kernel forms the same targets on the fly."""
+    thresholds = torch.arange(1, n + 1, dtype=torch.float, device=y.device).view(1, 1, n)
+    labels = y.unsqueeze(-1).expand(-1, -1, n)
+    targets = (labels >= thresholds).to(torch.float)
+    return torch.where(labels == padded_value_indicator, torch.full_like(targets, padded_value_indicator), targets)
 
 
 def ordinalLoss(y_pred, y_true, n, padded_value_indicator=PADDED_Y_VALUE):
-    """
-    :param y_pred: predictions from the model, shape [batch_size, slate_length, n]
-    :param y_true: ground truth labels, shape [batch_size, slate_length]
-    :param n: number of ordinal values, int
-    :param padded_value_indicator: an indicator of the y_true index containing a padded item, e.g. -1
-    :return: loss value, a torch.Tensor
+    """y_pred [batch, slate, n] probabilities of "label > level", y_true [batch, slate] labels, n ordinal levels;
+    returns the masked BCE sum divided by the number of docs with an unmasked target (0-dim tensor).
     Like the reference this raises ValueError when a label equals -1: `with_ordinals` is called
     with its default padding value and torch's BCELoss rejects the resulting -1 targets (ordinal.py:39-44).
     """
