@@ -255,18 +255,7 @@ LTR_API int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, 
             else LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], listnet_vec_kernel<4>, STREAM_THREADS, 0));
             if (occ[which] <= 0) occ[which] = 1;
         }
-        // among occ, occ-1, occ-2 CTAs per SM take the one whose last warp-round is fullest: with B / #warps = 11.07
-        // slates per warp a round of 12 wastes 8 % of the launch, 13.84 -> 14 only 1 %
-        const int sms = device_sm_count();
-        int best_c = occ[which];
-        double best_waste = 1e9;
-        for (int c = occ[which]; c >= 1 && c >= occ[which] - 2; --c) {
-            const double per_warp = (double)B / ((double)sms * c * STREAM_WARPS);
-            const double rounds = per_warp <= 1.0 ? 1.0 : (double)(long long)(per_warp + 0.999999);
-            const double waste = rounds / (per_warp < 1.0 ? 1.0 : per_warp);
-            if (waste < best_waste - 0.02) best_waste = waste, best_c = c;
-        }
-        const int cap = sms * best_c;
+        const int cap = device_sm_count() * occ[which];
         if (grid > cap) grid = cap;
     }
     if (vec && n <= 128) listnet_vec_kernel<1><<<grid, STREAM_THREADS, 0, st>>>(p);

@@ -370,3 +370,24 @@ def test_ndcg_sweep_full_size():
     perm = torch.argsort(torch.rand(Q, n, device="cuda"), dim=1)                 # distinct scores: order-free
     again = ndcg_sweep(yd.gather(1, perm), sd.gather(1, perm), ks=(1, 5, 10, None))
     assert torch.allclose(sweep, again, rtol=1e-6, atol=1e-7)
+
+
+def test_validation_epilogue_matches_driver_block():
+    """main_batch_execution.py:173-200: mNdcg for the model and every baseline system, then geoRisk of the matrix."""
+    from ltr_b200.utils.validation import ndcg_matrix, validation_scores
+    from oracle import ltr_oracle as O
+    g = torch.Generator().manual_seed(55)
+    Q, n, S = 200, 60, 3
+    y = torch.randint(0, 5, (Q, n), generator=g).float()
+    pred = torch.randn(Q, n, 1, generator=g)
+    base = torch.randn(Q, n, S, generator=g)
+    for k in (5, 10):
+        cols = [O.m_ndcg(y.numpy(), pred[:, :, 0].numpy(), k=k)]
+        cols += [O.m_ndcg(y.numpy(), base[:, :, i].numpy(), k=k) for i in range(S)]
+        ref_mat = torch.stack([torch.tensor(c) for c in cols]).t()
+        ref_geo = float(O.geo_risk(ref_mat, 5))
+        got_mat = ndcg_matrix(y.cuda(), pred.cuda(), base.cuda(), k=k).cpu().numpy()
+        np.testing.assert_allclose(got_mat, np.asarray(cols, dtype=np.float64).T, rtol=1e-12, atol=1e-15)
+        mean, geo = validation_scores(y.cuda(), pred.cuda(), base.cuda(), k=k, alpha=5)
+        assert abs(mean - float(np.mean(cols[0]))) < 1e-12
+        assert abs(geo - ref_geo) <= 2e-6 * abs(ref_geo)
