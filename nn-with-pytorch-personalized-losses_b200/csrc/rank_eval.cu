@@ -131,33 +131,159 @@ __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Top-k fast path of the NDCG sweep (all k <= 31): one WARP per query, the row in registers, no sort.
-//   predicted order: kmax rounds of "lane-local max (a max tree, no index), REDUX.MAX over the warp, retire
-//     the element(s) equal to it".  If a round retires more than one element, or two consecutive rounds give
-//     equal keys, a tie group reaches into the first kmax ranks: with LTR_TIES_STDSORT (and n > 16) the query is appended
-//     to the flagged list and left to the full-sort kernel; with the index-ordered tie rules the round falls
-//     back to an exact arg-max on (key, index).  A tie group entirely below rank kmax cannot change the top-k ranks.
-//   ideal order: labels that are integers 0..7 (MSLR / Istella: 0..4) are counted per level with ballots and rank r
-//     reads its label off the cumulative counts; other labels take top-k rounds of their own (values only).
+// Top-k fast path of the NDCG sweep (all k <= 31): no full sort.
+//   Every lane sorts its ITEMS (key, label) pairs once with a sorting network in registers; after that the
+//   warp's largest remaining key is always at the head of some lane's queue, so one of the kmax rounds is:
+//   REDUX.MAX over the heads, ballot of the lanes whose head equals it, shuffle the winner's label to everybody,
+//   the winner pops its queue (ITEMS - 1 predicated register moves).  ~10 + 2 ITEMS issue slots per round.
+//   Two lanes with the same head, or a popped lane whose next key equals the one it just gave, mean a tie group
+//   reaches into the top kmax ranks: the query is appended to the flagged list and sorted in full by
+//   ndcg_kernel with the caller's tie rule (std::sort replay included).  A tie group entirely below rank kmax
+//   cannot change the top-k ranks.
+//   Ideal order: labels that are integers 0..7 (MSLR / Istella: 0..4) are counted per level with ballots and rank r
+//   reads its label off the cumulative counts; other labels send the query to the full sort as well.
 //   DCG sums: lane r holds the term of rank r; the running sums are formed in rank order (the reference
-//     accumulates sequentially in fp32 / fp64) and written where r + 1 equals a k of the sweep.
+//   accumulates sequentially in fp32 / fp64) and written where r + 1 equals a k of the sweep.
+// Rows of up to 256 docs: one warp per query (ITEMS = 4 or 8).  Longer rows (<= 1024): one CTA of 4 warps per
+// query, every warp reduces its 256-doc quarter to kmax candidates, warp 0 merges the 4 kmax candidates.
 // 8 n bytes of HBM traffic per query.
 __device__ __forceinline__ int topk_key(float f) {
     if (f != f) return 0x7fffffff;                                // NaN first (at::native KeyValueCompDesc)
     return float_order_key(f + 0.0f);                             // -0 -> +0 so that key equality == float equality
 }
 
+constexpr int TOPK_TAKEN = (int)0x80000000;
+
+__device__ __forceinline__ void ce_desc(int& ka, float& la, int& kb, float& lb) {
+    const bool sw = kb > ka;
+    const int k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+    const float l0 = sw ? lb : la, l1 = sw ? la : lb;
+    ka = k0; kb = k1; la = l0; lb = l1;
+}
+
+// descending sorting networks for 4 and 8 register-resident pairs (Batcher odd-even merge sort)
 template <int ITEMS>
-__device__ __forceinline__ int tree_max(const int (&v)[ITEMS]) {
-    int m[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) m[k] = v[k];
-#pragma unroll
-    for (int w = ITEMS / 2; w > 0; w >>= 1) {
-#pragma unroll
-        for (int k = 0; k < w; ++k) m[k] = max(m[k], m[k + w]);
+__device__ __forceinline__ void lane_sort_desc(int (&k)[ITEMS], float (&l)[ITEMS]) {
+#define LTR_CE(a, b) ce_desc(k[a], l[a], k[b], l[b])
+    if (ITEMS == 4) {
+        LTR_CE(0, 1); LTR_CE(2, 3); LTR_CE(0, 2); LTR_CE(1, 3); LTR_CE(1, 2);
+    } else {
+        LTR_CE(0, 1); LTR_CE(2, 3); LTR_CE(4 % ITEMS, 5 % ITEMS); LTR_CE(6 % ITEMS, 7 % ITEMS);
+        LTR_CE(0, 2); LTR_CE(1, 3); LTR_CE(4 % ITEMS, 6 % ITEMS); LTR_CE(5 % ITEMS, 7 % ITEMS);
+        LTR_CE(1, 2); LTR_CE(5 % ITEMS, 6 % ITEMS);
+        LTR_CE(0, 4 % ITEMS); LTR_CE(1, 5 % ITEMS); LTR_CE(2, 6 % ITEMS); LTR_CE(3, 7 % ITEMS);
+        LTR_CE(2, 4 % ITEMS); LTR_CE(3, 5 % ITEMS);
+        LTR_CE(1, 2); LTR_CE(3, 4 % ITEMS); LTR_CE(5 % ITEMS, 6 % ITEMS);
     }
-    return m[0];
+#undef LTR_CE
+}
+
+// kmax tournament rounds over the lane queues.  Lane r (< kmax) returns the key / label of rank r;
+// `tie` is set (warp-uniform) if a tie group reaches into the first kmax ranks.
+template <int ITEMS>
+__device__ __forceinline__ void topk_rounds(int (&k)[ITEMS], float (&l)[ITEMS], int kmax, int& key_r, float& lab_r,
+                                            int& tie) {
+    const int lane = threadIdx.x & 31;
+    int local_tie = 0;
+    unsigned multi = 0;
+    key_r = TOPK_TAKEN;
+    lab_r = 0.f;
+    for (int r = 0; r < kmax; ++r) {
+        const int wk = __reduce_max_sync(LTR_FULL_MASK, k[0]);
+        const unsigned own = __ballot_sync(LTR_FULL_MASK, k[0] == wk && wk != TOPK_TAKEN);
+        multi |= own & (own - 1);                               // more than one lane holds the maximum
+        const int owner = own ? __ffs(own) - 1 : 0;
+        const float lab = __shfl_sync(LTR_FULL_MASK, l[0], owner);
+        if (lane == r) { key_r = wk; lab_r = (wk == TOPK_TAKEN) ? 0.f : lab; }
+        const bool me = (lane == owner) && (own != 0);          // the winner pops its queue (predicated, no branch)
+#pragma unroll
+        for (int i = 0; i + 1 < ITEMS; ++i) k[i] = me ? k[i + 1] : k[i], l[i] = me ? l[i + 1] : l[i];
+        k[ITEMS - 1] = me ? TOPK_TAKEN : k[ITEMS - 1];
+        local_tie |= (me && k[0] == wk) ? 1 : 0;                // the same key again inside this lane
+    }
+    tie = (multi != 0) || __any_sync(LTR_FULL_MASK, local_tie);
+}
+
+// label at ideal rank `lane` from the per-level counts of integer labels 1..7 (cnt[L] = #docs with label L)
+__device__ __forceinline__ float ideal_label_from_counts(const int (&cnt)[8]) {
+    const int lane = threadIdx.x & 31;
+    int ge = 0, cum = 0;
+#pragma unroll
+    for (int L = 7; L >= 1; --L) {
+        cum += cnt[L];                                          // docs with label >= L
+        ge += (cum > lane) ? 1 : 0;
+    }
+    return (float)ge;                                           // labels fill the ranks from the top level down
+}
+
+template <bool F64>
+__device__ __forceinline__ void write_ndcg_sums(const NdcgParams& p, int b, int myk, float lab_pred, float lab_ideal) {
+    const int lane = threadIdx.x & 31;
+    // labels on this path are integers 0..7: 2^l - 1 is exact integer arithmetic
+    const int gp = (1 << (int)lab_pred) - 1, gi = (1 << (int)lab_ideal) - 1;
+    if (!F64) {
+        const float d = (lane < p.kmax) ? p.disc32[lane] : 1.0f;
+        const float tp = (float)gp / d, ti = (float)gi / d;
+        float got = 0.f, ideal = 0.f, got_k = 0.f, ideal_k = 0.f;
+        for (int r = 0; r < p.kmax; ++r) {
+            got += __shfl_sync(LTR_FULL_MASK, tp, r);
+            ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
+            const bool mine = (myk == r + 1);
+            got_k = mine ? got : got_k;
+            ideal_k = mine ? ideal : ideal_k;
+        }
+        if (myk > 0) p.out32[(size_t)b * p.nk + lane] = got_k / ideal_k;
+    } else {
+        const double d = (lane < p.kmax) ? p.disc64[lane] : 1.0;
+        const double tp = (p.exp_gains ? (double)gp : (double)lab_pred) / d;
+        const double ti = (p.exp_gains ? (double)gi : (double)lab_ideal) / d;
+        double got = 0.0, ideal = 0.0, got_k = 0.0, ideal_k = 0.0;
+        for (int r = 0; r < p.kmax; ++r) {
+            got += __shfl_sync(LTR_FULL_MASK, tp, r);
+            ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
+            const bool mine = (myk == r + 1);
+            got_k = mine ? got : got_k;
+            ideal_k = mine ? ideal : ideal_k;
+        }
+        if (myk > 0) p.out64[(size_t)b * p.nk + lane] = (ideal_k == 0.0) ? p.empty_value : got_k / ideal_k;
+    }
+}
+
+// loads ITEMS docs per lane starting at `base`, returns false (warp-uniform) if a label is not an integer 0..7;
+// cnt[L] = warp-wide number of docs with label L (L = 1..7)
+template <int ITEMS>
+__device__ __forceinline__ bool topk_load(const NdcgParams& p, int b, int base, int limit, int (&k)[ITEMS], float (&l)[ITEMS],
+                                          int (&cnt)[8]) {
+    const int lane = threadIdx.x & 31;
+    const float* sp = p.y_pred + (size_t)b * p.n;
+    const float* yp = p.y_true + (size_t)b * p.n;
+    bool small_int = true;
+    int lmax = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int i = base + lane + 32 * j;
+        const bool in = i < limit;
+        const float s = in ? ld_stream(sp + i) : 0.f;
+        l[j] = in ? ld_stream(yp + i) : 0.f;
+        k[j] = in ? topk_key(s) : TOPK_TAKEN;
+        const int lv = (int)fminf(fmaxf(l[j], -1.f), 8.f);
+        small_int = small_int && (!in || ((float)lv == l[j] && lv >= 0 && lv <= 7));
+        lmax = max(lmax, in ? lv : 0);
+    }
+    small_int = __all_sync(LTR_FULL_MASK, small_int);
+    lmax = min(__reduce_max_sync(LTR_FULL_MASK, lmax), 7);
+#pragma unroll
+    for (int L = 1; L <= 7; ++L) {
+        int c = 0;
+        if (L <= lmax) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                c += __popc(__ballot_sync(LTR_FULL_MASK, (base + lane + 32 * j < limit) && l[j] == (float)L));
+        }
+        cnt[L] = c;
+    }
+    cnt[0] = 0;
+    return small_int;
 }
 
 template <int ITEMS, bool F64>
@@ -165,256 +291,64 @@ __global__ void __launch_bounds__(256) ndcg_topk_kernel(const NdcgParams p) {
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * 8;
-    const int TAKEN = (int)0x80000000;
-    const bool idx_desc = (p.tie_rule == TIES_REVERSED);
-    const bool want_std = (p.tie_rule == TIES_STDSORT) && p.n > 16;
     int myk = -1;                                                 // lane j writes the j-th k of the sweep
     for (int j = 0; j < p.nk; ++j) myk = (lane == j) ? p.ks[j] : myk;
     for (int b = gwarp; b < p.B; b += nwarps) {
-        const float* sp = p.y_pred + (size_t)b * p.n;
-        const float* yp = p.y_true + (size_t)b * p.n;
-        int ks_[ITEMS];
-        float yv[ITEMS];
-        bool small_int = true;
-        int lmax = 0;
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const int i = lane + 32 * k;
-            const bool in = i < p.n;
-            const float s = in ? ld_stream(sp + i) : 0.f;
-            yv[k] = in ? ld_stream(yp + i) : 0.f;
-            ks_[k] = in ? topk_key(s) : TAKEN;
-            const int lv = (int)fminf(fmaxf(yv[k], -1.f), 8.f);
-            small_int = small_int && (!in || ((float)lv == yv[k] && lv >= 0 && lv <= 7));
-            lmax = max(lmax, lv);
-        }
-        small_int = __all_sync(LTR_FULL_MASK, small_int);
-        lmax = __reduce_max_sync(LTR_FULL_MASK, lmax);
-
-        // ---- predicted order: label at rank r ends up in lane r --------------------------------------
-        float lab_pred = 0.f;
-        int prev_key = 0x7ffffffe, tie = 0;
-        for (int r = 0; r < p.kmax; ++r) {
-            const int wk = __reduce_max_sync(LTR_FULL_MASK, tree_max(ks_));
-            int hits = 0;
-            float mine = 0.f;
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                const bool hit = (ks_[k] == wk) && (wk != TAKEN);
-                hits += hit ? 1 : 0;
-                mine = hit ? yv[k] : mine;
-            }
-            const unsigned owners = __ballot_sync(LTR_FULL_MASK, hits > 0);
-            const bool multi = (__popc(owners) > 1) || __any_sync(LTR_FULL_MASK, hits > 1);
-            int widx = -1;                                        // exact winner index, only needed on a tie
-            if (multi || wk == prev_key) {
-                if (want_std) { tie = 1; break; }
-                int cand = idx_desc ? -1 : 0x7fffffff;
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k)
-                    if (ks_[k] == wk) cand = idx_desc ? max(cand, lane + 32 * k) : min(cand, lane + 32 * k);
-                widx = idx_desc ? __reduce_max_sync(LTR_FULL_MASK, cand) : __reduce_min_sync(LTR_FULL_MASK, cand);
-            }
-            int owner = __ffs(owners) - 1;
-            if (widx >= 0) {
-                owner = widx & 31;
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k) {
-                    if (lane + 32 * k == widx) { mine = yv[k]; ks_[k] = TAKEN; }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k) ks_[k] = (ks_[k] == wk) ? TAKEN : ks_[k];
-            }
-            const float labw = __shfl_sync(LTR_FULL_MASK, mine, owner < 0 ? 0 : owner);
-            if (lane == r) lab_pred = (wk == TAKEN) ? 0.f : labw;
-            prev_key = (wk == TAKEN) ? 0x7ffffffe - r : wk;
-        }
-        if (tie) {                                                // left to the full sort (std::sort tie order)
+        int k[ITEMS], cnt[8];
+        float l[ITEMS];
+        const bool ok = topk_load<ITEMS>(p, b, 0, p.n, k, l, cnt);
+        lane_sort_desc<ITEMS>(k, l);
+        int key_r, tie;
+        float lab_pred;
+        topk_rounds<ITEMS>(k, l, p.kmax, key_r, lab_pred, tie);
+        if (tie || !ok) {                                         // left to the full sort
             if (lane == 0) p.flags[1 + atomicAdd(p.flags, 1)] = b;
             continue;
         }
-
-        // ---- ideal order -----------------------------------------------------------------------------
-        float lab_ideal = 0.f;
-        if (small_int) {
-            int ge = 0;                                           // lane r: number of levels L >= 1 with #(label >= L) > r
-            int cum = 0;
-            for (int L = lmax; L >= 1; --L) {
-                int c = 0;
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k)
-                    c += __popc(__ballot_sync(LTR_FULL_MASK, (lane + 32 * k < p.n) && yv[k] == (float)L));
-                cum += c;                                         // docs with label >= L
-                ge += (cum > lane) ? 1 : 0;
-            }
-            lab_ideal = (float)ge;                                // labels fill the ranks from the top level down
-        } else {
-            int kl_[ITEMS];
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) kl_[k] = (lane + 32 * k < p.n) ? topk_key(yv[k]) : TAKEN;
-            for (int r = 0; r < p.kmax; ++r) {
-                const int wl = __reduce_max_sync(LTR_FULL_MASK, tree_max(kl_));
-                bool have = false;
-                float mine = 0.f;
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k)
-                    if (!have && kl_[k] == wl && wl != TAKEN) { have = true; mine = yv[k]; }
-                const int owner = __ffs(__ballot_sync(LTR_FULL_MASK, have)) - 1;
-                bool done = false;
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k)
-                    if (lane == owner && !done && kl_[k] == wl) { kl_[k] = TAKEN; done = true; }
-                const float labi = __shfl_sync(LTR_FULL_MASK, mine, owner < 0 ? 0 : owner);
-                if (lane == r) lab_ideal = (owner < 0) ? 0.f : labi;
-            }
-        }
-
-        // ---- DCG sums in rank order ------------------------------------------------------------------
-        if (!F64) {
-            const float d = (lane < p.kmax) ? p.disc32[lane] : 1.0f;
-            const float tp = (exp2f(lab_pred) - 1.0f) / d, ti = (exp2f(lab_ideal) - 1.0f) / d;
-            float got = 0.f, ideal = 0.f;
-            for (int r = 0; r < p.kmax; ++r) {
-                got += __shfl_sync(LTR_FULL_MASK, tp, r);
-                ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
-                if (myk == r + 1) p.out32[(size_t)b * p.nk + lane] = got / ideal;
-            }
-        } else {
-            const double d = (lane < p.kmax) ? p.disc64[lane] : 1.0;
-            const double lp = (double)lab_pred, li = (double)lab_ideal;
-            const double tp = (p.exp_gains ? exp2(lp) - 1.0 : lp) / d, ti = (p.exp_gains ? exp2(li) - 1.0 : li) / d;
-            double got = 0.0, ideal = 0.0;
-            for (int r = 0; r < p.kmax; ++r) {
-                got += __shfl_sync(LTR_FULL_MASK, tp, r);
-                ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
-                if (myk == r + 1) p.out64[(size_t)b * p.nk + lane] = (ideal == 0.0) ? p.empty_value : got / ideal;
-            }
-        }
+        write_ndcg_sums<F64>(p, b, myk, lab_pred, ideal_label_from_counts(cnt));
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Long rows (256 < n <= 1024): one CTA of 4 warps per query.  Every warp extracts the top-kmax (key, label)
-// candidates of its 256-doc quarter with the rounds above (8 docs per lane, so registers stay low and many
-// queries are resident per SM), the per-warp label histograms and candidates meet in shared memory, and warp 0
-// runs the same rounds over the <= 4 kmax candidates.  Any tie met on the way, and labels that are not integers
-// 0..7, send the query to the full-sort kernel.
 template <bool F64>
 __global__ void __launch_bounds__(128) ndcg_topk_wide_kernel(const NdcgParams p) {
-    constexpr int ITEMS = 8;
     __shared__ int cand_key[4][32];
     __shared__ float cand_lab[4][32];
     __shared__ int hist[4][8];
-    __shared__ int sh_flag;
+    __shared__ int sh_bad[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int TAKEN = (int)0x80000000;
     int myk = -1;
     for (int j = 0; j < p.nk; ++j) myk = (lane == j) ? p.ks[j] : myk;
-    if (tid == 0) sh_flag = 0;
-    __syncthreads();
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        const float* sp = p.y_pred + (size_t)b * p.n;
-        const float* yp = p.y_true + (size_t)b * p.n;
-        int ks_[ITEMS];
-        float yv[ITEMS];
-        bool small_int = true;
+        int k[8], cnt[8];
+        float l[8];
+        const bool ok = topk_load<8>(p, b, warp * 256, p.n, k, l, cnt);
+        lane_sort_desc<8>(k, l);
+        int key_r, tie;
+        float lab_r;
+        topk_rounds<8>(k, l, p.kmax, key_r, lab_r, tie);
+        cand_key[warp][lane] = key_r;                             // TAKEN beyond the quarter's docs / beyond kmax
+        cand_lab[warp][lane] = lab_r;
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const int i = warp * 256 + lane + 32 * k;
-            const bool in = i < p.n;
-            const float s = in ? ld_stream(sp + i) : 0.f;
-            yv[k] = in ? ld_stream(yp + i) : 0.f;
-            ks_[k] = in ? topk_key(s) : TAKEN;
-            const int lv = (int)fminf(fmaxf(yv[k], -1.f), 8.f);
-            small_int = small_int && (!in || ((float)lv == yv[k] && lv >= 0 && lv <= 7));
-        }
-        int bad = __all_sync(LTR_FULL_MASK, small_int) ? 0 : 1;
-        // per-warp label histogram (levels 1..7)
-        for (int L = 1; L <= 7; ++L) {
-            int c = 0;
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k)
-                c += __popc(__ballot_sync(LTR_FULL_MASK, (warp * 256 + lane + 32 * k < p.n) && yv[k] == (float)L));
-            if (lane == 0) hist[warp][L] = c;
-        }
-        // per-warp candidates
-        int ckey = TAKEN;
-        float clab = 0.f;
-        for (int r = 0; r < p.kmax; ++r) {
-            const int wk = __reduce_max_sync(LTR_FULL_MASK, tree_max(ks_));
-            int hits = 0;
-            float mine = 0.f;
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                const bool hit = (ks_[k] == wk) && (wk != TAKEN);
-                hits += hit ? 1 : 0;
-                mine = hit ? yv[k] : mine;
-                ks_[k] = hit ? TAKEN : ks_[k];
-            }
-            const unsigned owners = __ballot_sync(LTR_FULL_MASK, hits > 0);
-            if (__popc(owners) > 1 || __any_sync(LTR_FULL_MASK, hits > 1)) bad = 1;
-            const float labw = __shfl_sync(LTR_FULL_MASK, mine, owners ? __ffs(owners) - 1 : 0);
-            if (lane == r) { ckey = wk; clab = labw; }
-        }
-        cand_key[warp][lane] = (lane < p.kmax) ? ckey : TAKEN;
-        cand_lab[warp][lane] = clab;
-        if (bad && lane == 0) sh_flag = 1;       // (benign race: every writer stores 1)
+        for (int L = 0; L < 8; ++L)
+            if (lane == L) hist[warp][L] = cnt[L];
+        if (lane == 0) sh_bad[warp] = (tie || !ok) ? 1 : 0;
         __syncthreads();
         if (warp == 0) {
-            int tie = sh_flag;
-            __syncwarp();
-            if (lane == 0) sh_flag = 0;          // re-armed for the next query (ordered by the barrier below)
-            int mk[4];
+            int mk[4], tot[8];
             float ml[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mk[k] = cand_key[k][lane], ml[k] = cand_lab[k][lane];
-            float lab_pred = 0.f;
-            for (int r = 0; r < p.kmax && !tie; ++r) {
-                const int wk = __reduce_max_sync(LTR_FULL_MASK, tree_max(mk));
-                int hits = 0;
-                float mine = 0.f;
+            for (int q = 0; q < 4; ++q) mk[q] = cand_key[q][lane], ml[q] = cand_lab[q][lane];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool hit = (mk[k] == wk) && (wk != TAKEN);
-                    hits += hit ? 1 : 0;
-                    mine = hit ? ml[k] : mine;
-                    mk[k] = hit ? TAKEN : mk[k];
-                }
-                const unsigned owners = __ballot_sync(LTR_FULL_MASK, hits > 0);
-                if (__popc(owners) > 1 || __any_sync(LTR_FULL_MASK, hits > 1)) tie = 1;
-                const float labw = __shfl_sync(LTR_FULL_MASK, mine, owners ? __ffs(owners) - 1 : 0);
-                if (lane == r) lab_pred = (wk == TAKEN) ? 0.f : labw;
-            }
-            if (tie) {
+            for (int L = 0; L < 8; ++L) tot[L] = (hist[0][L] + hist[1][L]) + (hist[2][L] + hist[3][L]);
+            const int bad = (sh_bad[0] | sh_bad[1]) | (sh_bad[2] | sh_bad[3]);
+            lane_sort_desc<4>(mk, ml);
+            int key_m, tie_m;
+            float lab_pred;
+            topk_rounds<4>(mk, ml, p.kmax, key_m, lab_pred, tie_m);
+            if (bad || tie_m) {
                 if (lane == 0) p.flags[1 + atomicAdd(p.flags, 1)] = b;
             } else {
-                int ge = 0, cum = 0;
-                for (int L = 7; L >= 1; --L) {
-                    cum += (hist[0][L] + hist[1][L]) + (hist[2][L] + hist[3][L]);
-                    ge += (cum > lane) ? 1 : 0;
-                }
-                const float lab_ideal = (float)ge;
-                if (!F64) {
-                    const float d = (lane < p.kmax) ? p.disc32[lane] : 1.0f;
-                    const float tp = (exp2f(lab_pred) - 1.0f) / d, ti = (exp2f(lab_ideal) - 1.0f) / d;
-                    float got = 0.f, ideal = 0.f;
-                    for (int r = 0; r < p.kmax; ++r) {
-                        got += __shfl_sync(LTR_FULL_MASK, tp, r);
-                        ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
-                        if (myk == r + 1) p.out32[(size_t)b * p.nk + lane] = got / ideal;
-                    }
-                } else {
-                    const double d = (lane < p.kmax) ? p.disc64[lane] : 1.0;
-                    const double lp = (double)lab_pred, li = (double)lab_ideal;
-                    const double tp = (p.exp_gains ? exp2(lp) - 1.0 : lp) / d, ti = (p.exp_gains ? exp2(li) - 1.0 : li) / d;
-                    double got = 0.0, ideal = 0.0;
-                    for (int r = 0; r < p.kmax; ++r) {
-                        got += __shfl_sync(LTR_FULL_MASK, tp, r);
-                        ideal += __shfl_sync(LTR_FULL_MASK, ti, r);
-                        if (myk == r + 1) p.out64[(size_t)b * p.nk + lane] = (ideal == 0.0) ? p.empty_value : got / ideal;
-                    }
-                }
+                write_ndcg_sums<F64>(p, b, myk, lab_pred, ideal_label_from_counts(tot));
             }
         }
         __syncthreads();
@@ -570,10 +504,7 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
             else ndcg_topk_wide_kernel<false><<<gw, 128, 0, st>>>(p);
         }
 #undef LTR_TOPK
-        if (!wide && (p.tie_rule != TIES_STDSORT || p.n <= 16)) {
-            const int rc0 = (int)cudaGetLastError();
-            return rc0 ? set_cuda_error(rc0, "ltr_ndcg_at_k") : 0;
-        }
+        (void)wide;
     } else {
         p.flags = nullptr;
     }
