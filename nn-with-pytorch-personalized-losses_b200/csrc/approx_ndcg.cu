@@ -21,7 +21,7 @@ namespace ltr {
 template <bool FACT>
 __device__ __forceinline__ float pair_p(float row, float col, float scale) {
     if (FACT) return row * col;                                       // row = u_i, col = v_j
-    return ex2_approx(fminf((row - col) * scale, 126.0f));            // row = s_i, col = s_j (raw scores)
+    return ex2_capped((row - col) * scale);                           // row = s_i, col = s_j (raw scores)
 }
 
 // PHASE 0: both passes over all rows of the slate (one CTA per slate).  PHASE 1 / 2: the rank pass / the gradient
@@ -393,10 +393,34 @@ static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
     }
     int grid = device_sm_count() * ((SYM_GRID_PER_SM > 0 && SYM_GRID_PER_SM < occ_cached) ? SYM_GRID_PER_SM : occ_cached);
     if (grid > p.B) grid = p.B;
+    if (grid > 2047) grid = 2047;                                      // the finished-CTA count has 11 bits
+#if SYM_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(SYM_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, approx_ndcg_sym_kernel, p);
+#else
     approx_ndcg_sym_kernel<<<grid, SYM_THREADS, 0, st>>>(p);
     return (int)cudaGetLastError();
+#endif
 }
 
+}  // namespace ltr
+
+namespace ltr {
+int upload_disc_prefix_constant() {
+    double host[129];
+    host[0] = 0.0;
+    for (int r = 1; r <= 128; ++r) host[r] = host[r - 1] + 1.0 / log2(1.0 + (double)r);
+    return (int)cudaMemcpyToSymbol(c_disc_prefix, host, sizeof(host));
+}
 }  // namespace ltr
 
 LTR_API size_t ltr_approx_ndcg_scratch_bytes(int B, int n) {
@@ -436,7 +460,7 @@ LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int
     p.part = p.cbuf ? p.cbuf + (size_t)B * n : nullptr;
     p.rows_per_cta = 0;
     int rc;
-    if (n <= SYM_N && !p.clamp && p.disc_prefix != nullptr && p.disc_len > SYM_N)
+    if (n <= SYM_N && !p.clamp && p.disc_prefix != nullptr && p.disc_len > SYM_N && B <= (1 << 22))
         rc = launch_approx_sym(p, st);                                 // symmetric pair schedule, 4 warps per slate
     else if (n > 256 && scratch != nullptr && scratch_bytes >= ltr_approx_ndcg_scratch_bytes(B, n) &&
              B < 8 * device_sm_count())

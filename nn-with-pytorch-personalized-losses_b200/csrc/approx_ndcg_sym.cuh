@@ -38,8 +38,15 @@
 #ifndef SYM_GRID_PER_SM
 #define SYM_GRID_PER_SM 0    // CTAs launched per SM (0: as many as are resident)
 #endif
+#ifndef SYM_PDL
+#define SYM_PDL 1            // programmatic dependent launch: overlap this launch's ramp-up with the previous kernel's tail
+#endif
 
 namespace ltr {
+
+// discount prefix sums P[r] = sum_{q<=r} 1/log2(1+q), r = 0..128, for the histogram ideal DCG of the fast path
+// (filled by ltr_fill_disc_prefix; a uniform-index constant-bank read, no per-CTA table load)
+__constant__ double c_disc_prefix[129];
 
 struct ApproxParams {
     const float* s;
@@ -51,8 +58,8 @@ struct ApproxParams {
     float* slate_out;
     float* loss_out;
     float* grad;
-    unsigned* ws;   // [0] next-slate counter, [1] finished-CTA counter, [2..3] 64-bit fixed-point loss sum,
-                    // [4] non-finite flag (all left at 0)
+    unsigned* ws;   // [0] next-slate counter, [2..3] 64-bit word: non-finite flag << 63 | finished-CTA count << 52 |
+                    // fixed-point loss sum (all left at 0)
     int clamp;      // 1: apply the eps clamp per pair exactly (large eps), 0: it is below fp32 resolution
     float* cbuf;    // split path: [B, n] d loss / d pos of every compacted doc (rank launch -> gradient launch)
     float* part;    // split path: [B, chunks] partial slate values
@@ -64,7 +71,6 @@ constexpr int SYM_THREADS = 128;  // 4 warps: one per SM sub-partition
 constexpr int SYM_MAX_LABEL = 4;  // integer labels 0..4 take the histogram ideal-DCG (others: sort)
 
 struct SymShared {
-    double P[SYM_N + 4];          // discount prefix sums P[r] = sum_{q<=r} 1/log2(1+q)
     float u[SYM_N];               // 2^(t - c)   (direct form: raw score)
     float v[SYM_N];               // 2^-(t - c)
     float c[SYM_N];               // d loss / d pos_i
@@ -91,7 +97,8 @@ struct SymCarry {
                           // batch loss is bitwise reproducible although slates are handed out dynamically)
     int nonfinite;
 };
-constexpr float kFixScale = 1099511627776.0f;   // 2^40
+constexpr float kFixScale = 67108864.0f;        // 2^26: slate values (a few units at most) of up to 2^22 slates fit 52 bits
+constexpr int kFixCountShift = 52;               // the finished-CTA count rides in bits 52..62 of the same word
 
 __device__ __forceinline__ void carry_add(SymCarry& cy, float v) {
     if (fabsf(v) < 4.0e6f) cy.fx += __float2ll_rn(v * kFixScale);
@@ -142,7 +149,7 @@ __device__ __noinline__ void direct_slate(const ApproxParams& p, SymShared& sh, 
     float sum = -0.5f;                                           // the j == i term below is exactly 1/2
     if (doc.valid) {
         for (int j = 0; j < m; ++j) {
-            const float pp = ex2_approx(fminf((si - sh.u[j]) * scale, 126.0f));
+            const float pp = ex2_capped((si - sh.u[j]) * scale);
             sum += rcp_approx(pp + 1.0f);
         }
     }
@@ -152,7 +159,7 @@ __device__ __noinline__ void direct_slate(const ApproxParams& p, SymShared& sh, 
         if (doc.valid) {
             const float ci = sh.c[doc.dst];
             for (int j = 0; j < m; ++j) {
-                const float pp = ex2_approx(fminf((si - sh.u[j]) * scale, 126.0f));
+                const float pp = ex2_capped((si - sh.u[j]) * scale);
                 const float rr = rcp_approx(pp + 1.0f);
                 acc = fmaf(rr * (pp * rr), sh.c[j] - ci, acc);
             }
@@ -398,6 +405,12 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
     const int n = p.n;
     const float scale = p.alpha * kLog2e;
 
+#if SYM_PDL
+    // let the next launch on the stream start its ramp-up now; wait for everything before us to be complete and
+    // visible before touching global memory (inputs may come from the previous kernel, ws from the previous call)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     int b = (int)blockIdx.x;                      // first slate is static, the rest come from the counter
     float cur_s = 0.f, cur_y = p.pad;
     if (b < p.B && tid < n) {
@@ -411,8 +424,6 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
 #if SYM_CLAIM_AHEAD
     if (tid == 0) cy.claimed = (int)(gridDim.x + atomicAdd(&p.ws[0], 1u));
 #endif
-    for (int i = tid; i <= SYM_N; i += SYM_THREADS) sh.P[i] = p.disc_prefix[i];
-    // (made visible by the first slate's barrier)
 
     while (b < p.B) {
         // ---- compaction offsets + per-slate statistics: 5 warp collectives, one barrier ---------
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
                 const int e3 = e4 + ((packed >> 16) & 255);
                 const int e2 = e3 + ((packed >> 8) & 255);
                 const int e1 = e2 + (packed & 255);
-                const double dcg = 8.0 * sh.P[e4] + 4.0 * sh.P[e3] + 2.0 * sh.P[e2] + sh.P[e1];
+                const double dcg = 8.0 * c_disc_prefix[e4] + 4.0 * c_disc_prefix[e3] + 2.0 * c_disc_prefix[e2] + c_disc_prefix[e1];
                 maxdcg = fmaxf((float)dcg, p.eps);
                 gain = (float)((1 << lvl) - 1);
             } else {
@@ -528,24 +539,20 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
         cur_y = next_y;
     }
 
-    // ---- batch loss: per-CTA fixed-point sums meet in the workspace; the last CTA to arrive converts ----
+    // ---- batch loss: ONE 64-bit atomic per CTA carries its fixed-point sum (low 52 bits) and counts it as finished
+    //      (bits 52..62); bit 63 is a sticky "a slate value was not finite" flag.  The CTA that completes the count
+    //      already holds the total and the flag in the value its own atomic returned: no fence, no second round trip ----
     if (tid == 0) {
         unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(p.ws + 2);
-        atomicAdd(acc64, (unsigned long long)cy.fx);
-        if (cy.nonfinite) atomicOr(&p.ws[4], 1u);
-        __threadfence();
-        const unsigned done = atomicAdd(&p.ws[1], 1u);
-        if (done == gridDim.x - 1) {
-            __threadfence();
-            const long long total = (long long)atomicAdd(acc64, 0ull);
-            const unsigned bad = atomicOr(&p.ws[4], 0u);
-            const double mean = (double)total / ((double)kFixScale * (double)p.B);
-            p.loss_out[0] = bad ? __int_as_float(0x7fc00000) : (float)(-mean);       // approxNDCG.py:53
+        if (cy.nonfinite) atomicOr(acc64, 1ull << 63);               // same address, same thread: ordered before the add
+        const unsigned long long mine = (unsigned long long)cy.fx + (1ull << kFixCountShift);
+        const unsigned long long after = atomicAdd(acc64, mine) + mine;
+        if (((after >> kFixCountShift) & 0x7ffull) == (unsigned long long)gridDim.x) {
+            const double total = (double)(after & ((1ull << kFixCountShift) - 1ull));
+            const double mean = total / ((double)kFixScale * (double)p.B);
+            p.loss_out[0] = (after >> 63) ? __int_as_float(0x7fc00000) : (float)(-mean);       // approxNDCG.py:53
             p.ws[0] = 0u;
-            p.ws[1] = 0u;
-            p.ws[4] = 0u;
             *acc64 = 0ull;
-            __threadfence();
         }
     }
 }

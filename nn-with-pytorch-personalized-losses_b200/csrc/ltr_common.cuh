@@ -21,6 +21,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// 2^min(x, 126); a NaN exponent stays NaN (fminf alone would swallow it and hide a NaN score)
+__device__ __forceinline__ float ex2_capped(float x) {
+    return ex2_approx((x != x) ? x : fminf(x, 126.0f));
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

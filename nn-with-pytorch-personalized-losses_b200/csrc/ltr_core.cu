@@ -69,5 +69,6 @@ LTR_API int ltr_fill_disc_prefix(double* disc_prefix, int len, void* stream) {
     if (!disc_prefix || len <= 0) return ltr::set_error(LTR_EINVAL, "ltr_fill_disc_prefix: bad arguments");
     ltr::disc_prefix_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(disc_prefix, len);
     int rc = (int)cudaGetLastError();
+    if (!rc) rc = ltr::upload_disc_prefix_constant();       // the approxNDCG fast path reads P[0..128] from the constant bank
     return rc ? ltr::set_cuda_error(rc, "ltr_fill_disc_prefix") : 0;
 }

@@ -10,6 +10,7 @@ int set_error(int code, const char* msg);            // records msg for ltr_last
 int set_cuda_error(int cuda_code, const char* where);  // records "<where>: <cudaGetErrorString>"
 int device_sm_count();                               // SM count of the current device (cached per device)
 int device_max_optin_smem();                         // bytes of opt-in shared memory per CTA
+int upload_disc_prefix_constant();                   // P[0..128] -> the constant bank of the current device
 
 // ---- layout of the caller-provided workspace (LTR_WORKSPACE_BYTES, zero-filled once) -------------------------
 //   u32 [0..4]    approxNDCG: next-slate counter, finished-CTA counter, 64-bit fixed-point loss sum, non-finite flag

@@ -37,8 +37,9 @@ def disc_prefix(device: torch.device) -> torch.Tensor:
     key = device.index if device.index is not None else torch.cuda.current_device()
     tab = _disc_tables.get(key)
     if tab is None:
-        tab = torch.empty(_DISC_LEN, dtype=torch.float64, device=device)
-        _lib.check(_lib.load().ltr_fill_disc_prefix(tab.data_ptr(), _DISC_LEN, stream_ptr()), "ltr_fill_disc_prefix")
+        with torch.cuda.device(device):          # the library also fills a per-device __constant__ copy
+            tab = torch.empty(_DISC_LEN, dtype=torch.float64, device=device)
+            _lib.check(_lib.load().ltr_fill_disc_prefix(tab.data_ptr(), _DISC_LEN, stream_ptr()), "ltr_fill_disc_prefix")
         _disc_tables[key] = tab
     return tab
 
