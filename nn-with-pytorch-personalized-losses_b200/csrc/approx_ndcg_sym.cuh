@@ -141,29 +141,36 @@ __device__ __forceinline__ void slate_middle(const ApproxParams& p, SymShared& s
 
 // Slates whose scaled score range does not fit the factorised form (rare): one doc per thread,
 // p = ex2(min(alpha*log2e*(s_i - s_j), 126)) per ordered pair, recomputed in the gradient pass.
-// sh.u holds the raw scores of the m compacted docs.
-__device__ __noinline__ void direct_slate(const ApproxParams& p, SymShared& sh, int b, int m, float scale,
-                                          const SymDoc& doc, SymCarry& cy, float& next_s, float& next_y, int& next_b) {
+// `raw` holds the raw scores of the m compacted docs.  The two loops are out-of-line helpers with by-value
+// arguments only (a by-reference argument of a __noinline__ function would pin the caller's slate state in
+// local memory on the fast path as well).
+__device__ __noinline__ float direct_rank_sum(const float* raw, int m, float scale, float si) {
+    float sum = -0.5f;                                           // the j == i term below is exactly 1/2
+    for (int j = 0; j < m; ++j) {
+        const float pp = ex2_capped((si - raw[j]) * scale);
+        sum += rcp_approx(pp + 1.0f);
+    }
+    return sum;
+}
+__device__ __noinline__ float direct_grad_sum(const float* raw, const float* c, int m, float scale, float si, float ci) {
+    float acc = 0.f;
+    for (int j = 0; j < m; ++j) {
+        const float pp = ex2_capped((si - raw[j]) * scale);
+        const float rr = rcp_approx(pp + 1.0f);
+        acc = fmaf(rr * (pp * rr), c[j] - ci, acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ void direct_slate(const ApproxParams& p, SymShared& sh, int b, int m, float scale,
+                                             const SymDoc& doc, SymCarry& cy, float& next_s, float& next_y, int& next_b) {
     const int tid = threadIdx.x;
     const float si = doc.valid ? sh.u[doc.dst] : 0.f;
-    float sum = -0.5f;                                           // the j == i term below is exactly 1/2
-    if (doc.valid) {
-        for (int j = 0; j < m; ++j) {
-            const float pp = ex2_capped((si - sh.u[j]) * scale);
-            sum += rcp_approx(pp + 1.0f);
-        }
-    }
+    float sum = 0.f;
+    if (doc.valid) sum = direct_rank_sum(sh.u, m, scale, si);
     slate_middle(p, sh, b, doc, sum, cy, next_s, next_y, next_b);
     if (p.grad != nullptr && tid < p.n) {
         float acc = 0.f;
-        if (doc.valid) {
-            const float ci = sh.c[doc.dst];
-            for (int j = 0; j < m; ++j) {
-                const float pp = ex2_capped((si - sh.u[j]) * scale);
-                const float rr = rcp_approx(pp + 1.0f);
-                acc = fmaf(rr * (pp * rr), sh.c[j] - ci, acc);
-            }
-        }
+        if (doc.valid) acc = direct_grad_sum(sh.u, sh.c, m, scale, si, sh.c[doc.dst]);
         p.grad[(size_t)b * p.n + tid] = p.alpha * acc;
     }
     __syncthreads();
