@@ -12,6 +12,7 @@
 //        c_i = G_i / (B ln2 (1+pos_i) log2(1+pos_i)^2)          (SURVEY A.1).
 // The B x n x n tensors of the reference never exist.
 #include "approx_ndcg_sym.cuh"
+#include "approx_ndcg_warp.cuh"
 #include "ltr_common.cuh"
 #include "ltr_host.h"
 
@@ -385,19 +386,28 @@ static int launch_approx_split(ApproxParams p, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
-    static int occ_cached = 0;
+#ifndef WPS_MIN_BATCH
+#define WPS_MIN_BATCH 16384    // batches of at least this many slates take the one-warp-per-slate kernel (coarser work
+                               // items, fewer instructions per slate); smaller ones the four-warps-per-slate kernel
+#endif
+
+// persistent launch of a fast-path kernel: as many CTAs as are resident (or fewer for small batches), with
+// programmatic stream serialization so that consecutive launches overlap ramp-up and tail
+template <typename Kernel>
+static int launch_persistent(Kernel kernel, int threads, int slates_per_cta, int per_sm_cap, const ApproxParams& p,
+                             cudaStream_t st, int& occ_cached) {
     if (occ_cached == 0) {
-        LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_sym_kernel, SYM_THREADS, 0));
+        LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, kernel, threads, 0));
         if (occ_cached <= 0) occ_cached = 1;
     }
-    int grid = device_sm_count() * ((SYM_GRID_PER_SM > 0 && SYM_GRID_PER_SM < occ_cached) ? SYM_GRID_PER_SM : occ_cached);
-    if (grid > p.B) grid = p.B;
+    int grid = device_sm_count() * ((per_sm_cap > 0 && per_sm_cap < occ_cached) ? per_sm_cap : occ_cached);
+    const int need = (p.B + slates_per_cta - 1) / slates_per_cta;
+    if (grid > need) grid = need;
     if (grid > 2047) grid = 2047;                                      // the finished-CTA count has 11 bits
 #if SYM_PDL
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(SYM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -405,11 +415,18 @@ static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, approx_ndcg_sym_kernel, p);
+    return (int)cudaLaunchKernelEx(&cfg, kernel, p);
 #else
-    approx_ndcg_sym_kernel<<<grid, SYM_THREADS, 0, st>>>(p);
+    kernel<<<grid, threads, 0, st>>>(p);
     return (int)cudaGetLastError();
 #endif
+}
+
+static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
+    static int occ_warp = 0, occ_sym = 0;
+    if (p.B >= WPS_MIN_BATCH)
+        return launch_persistent(approx_ndcg_warp_kernel, WPS_THREADS, WPS_WARPS, WPS_MIN_CTAS, p, st, occ_warp);
+    return launch_persistent(approx_ndcg_sym_kernel, SYM_THREADS, 1, SYM_GRID_PER_SM, p, st, occ_sym);
 }
 
 }  // namespace ltr

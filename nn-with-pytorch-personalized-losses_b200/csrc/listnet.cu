@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) listnet_vec_kernel(const Listn
     const float ninf = __int_as_float(0xff800000);
     const int n4 = p.n >> 2;
     double acc = 0.0;
+    pdl_prologue();
     // software pipeline: the next slate's two rows are in flight while this one is reduced
     float4 yn[V], sn[V];
     auto issue_loads = [&](int b) {
@@ -258,10 +259,13 @@ LTR_API int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, 
         const int cap = device_sm_count() * occ[which];
         if (grid > cap) grid = cap;
     }
-    if (vec && n <= 128) listnet_vec_kernel<1><<<grid, STREAM_THREADS, 0, st>>>(p);
-    else if (vec && n <= 256) listnet_vec_kernel<2><<<grid, STREAM_THREADS, 0, st>>>(p);
-    else if (vec) listnet_vec_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);
-    else if (n <= 128) listnet_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);
+    if (vec) {
+        const int rc = n <= 128 ? launch_pdl(listnet_vec_kernel<1>, grid, STREAM_THREADS, 0, st, p)
+                     : n <= 256 ? launch_pdl(listnet_vec_kernel<2>, grid, STREAM_THREADS, 0, st, p)
+                                : launch_pdl(listnet_vec_kernel<4>, grid, STREAM_THREADS, 0, st, p);
+        return rc ? set_cuda_error(rc, "ltr_listnet_fwdbwd") : 0;
+    }
+    if (n <= 128) listnet_kernel<4><<<grid, STREAM_THREADS, 0, st>>>(p);
     else if (n <= 256) listnet_kernel<8><<<grid, STREAM_THREADS, 0, st>>>(p);
     else if (n <= 512) listnet_kernel<16><<<grid, STREAM_THREADS, 0, st>>>(p);
     else listnet_kernel<32><<<grid, STREAM_THREADS, 0, st>>>(p);

@@ -150,6 +150,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// ---- programmatic dependent launch (kernels started with ltr::launch_pdl) --------------------------------------
+// Let the next launch on the stream become resident now; then wait until everything before this kernel on the
+// stream is complete and visible (inputs may come from the previous kernel, the workspace from the previous call).
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- streaming global access -------------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
     float4 r;

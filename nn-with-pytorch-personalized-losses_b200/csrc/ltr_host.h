@@ -23,6 +23,23 @@ inline unsigned* ws_counter(void* ws, int idx) { return reinterpret_cast<unsigne
 inline float* ws_floats(void* ws, int idx) { return reinterpret_cast<float*>(ws) + idx; }
 inline double* ws_partials(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 1024); }
 
+// Launch with programmatic stream serialization: the grid may become resident while the previous kernel on the
+// stream drains.  The kernel must execute `pdl_prologue()` before its first global-memory access.
+template <typename Params>
+inline int launch_pdl(void (*kernel)(Params), int grid, int threads, size_t smem, cudaStream_t st, const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 }  // namespace ltr
 
 #define LTR_CUDA(expr)                                                  \

@@ -14,7 +14,9 @@ torch.cuda.set_device(dev)
 lib = _lib.load()
 n = 128
 tab = rt.disc_prefix(dev)
-for B in (1, 148, 592, 1184, 2368, 4096, 8192, 16384, 65536):
+SIZES = [int(a) for a in sys.argv[1:]] or [1, 148, 592, 1184, 2368, 4096, 8192, 16384, 65536]
+print(os.environ.get("LTR_B200_LIB", "default"))
+for B in SIZES:
     RING = 8 if B <= 16384 else 2
     data = [bench.make_batch(2020 + i, B=B) for i in range(RING)]
     ds = [s.to(dev) for s, _, _ in data]
