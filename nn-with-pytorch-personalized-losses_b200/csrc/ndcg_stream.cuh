@@ -1,0 +1,267 @@
+// K4 fast path, second generation: NDCG@k sweep with ONE THREAD PER QUERY (replaces utils/metrics.py:48-104 for
+// sweeps whose largest k is <= 10 on rows of at most 128 docs, n % 4 == 0).
+//
+// The warp-per-query top-k kernel spends ~1,000 issue slots per query on cross-lane tournaments.  Here a warp
+// owns a tile of 32 queries and works in two phases:
+//
+//   phase 1 (lane = 4 consecutive docs of one row, coalesced 128-bit loads, next batch always in flight): the
+//     row's scores go to shared memory in a layout the second phase reads without bank conflicts, the labels
+//     packed to 4 bits; the label histogram of the row (levels 1..4, one REDUX) and its "not on the fast
+//     path" flag (NaN score, label not an integer 0..4) stay in the lane of that row;
+//   phase 2 (lane = one query, no cross-lane traffic at all): the 11th largest of the 32 quad maxima is a lower
+//     bound L of the 11th largest score (a pruned Batcher network in registers); the docs with score >= L
+//     (13.5 on average) are the only candidates: they are inserted, with their labels, into a sorted top-11 list
+//     held in registers; DCG and ideal DCG (from the histogram) are accumulated in rank order exactly as the
+//     reference does (sequential fp32 / fp64 sums).
+//
+// Exact-tie handling is unchanged: a query with equal scores among its first kmax + 1 ranks (whose order depends
+// on the reference's sort) is flagged, and ndcg_kernel sorts it in full with the caller's tie rule.
+// HBM traffic: 8 n bytes per query + the outputs, read once.
+#pragma once
+#include "ltr_common.cuh"
+
+namespace ltr {
+
+constexpr int TPQ_K = 11;              // ranks kept per query: kmax <= 10 plus one for the boundary tie check
+constexpr int TPQ_WARPS = 4;           // independent warps per CTA
+constexpr int TPQ_THREADS = 32 * TPQ_WARPS;
+constexpr int TPQ_CTAS = 3;            // CTAs per SM (shared memory: 3 x 4 x 19,072 B)
+constexpr int TPQ_N = 128;             // docs per row (one chunk)
+constexpr int TPQ_BATCH = 8;           // label rows per load batch (one 128-bit load per row and lane in flight)
+constexpr int TPQ_S_STRIDE = TPQ_N + 4;    // floats; 132 q + 4 j: conflict-free 128-bit reads per quarter warp
+constexpr int TPQ_L_STRIDE = 34;           // 16-bit units; labels of a quad packed to 4 x 4 bits
+
+struct TpqTile {
+    float s[32 * TPQ_S_STRIDE];
+    unsigned short lab[32 * TPQ_L_STRIDE];
+};
+constexpr size_t TPQ_SMEM = sizeof(TpqTile) * TPQ_WARPS;
+
+__device__ __forceinline__ float max_nan(float a, float b) {       // NaN if either operand is NaN
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned shr_clamp(unsigned v, unsigned s) {   // v >> s, 0 for s >= 32
+    unsigned r;
+    asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
+
+// insertion with a payload; an equal key goes BELOW the entries already there (ties are flagged anyway).
+// Parallel form: up[j] = x > t[j] is monotone in j (t is sorted), so every slot picks its new value from
+// {t[j-1], x, t[j]} independently -- the same 5 K instructions as a bubble chain, but dependency depth 3.
+template <int K>
+__device__ __forceinline__ void tpq_insert(float (&t)[K], int (&l)[K], float x, int lab) {
+    bool up[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) up[j] = x > t[j];
+#pragma unroll
+    for (int j = K - 1; j >= 1; --j) {
+        t[j] = up[j - 1] ? t[j - 1] : (up[j] ? x : t[j]);
+        l[j] = up[j - 1] ? l[j - 1] : (up[j] ? lab : l[j]);
+    }
+    t[0] = up[0] ? x : t[0];
+    l[0] = up[0] ? lab : l[0];
+}
+
+// the 11th largest of 32 values: Batcher's odd-even merge sort pruned to the comparators that output depends on
+__device__ __forceinline__ float tpq_select11(float (&v)[32]) {
+#define TPQ_CE(a, b)                          \
+    {                                         \
+        const float hi_ = fmaxf(v[a], v[b]);  \
+        v[b] = fminf(v[a], v[b]);             \
+        v[a] = hi_;                           \
+    }
+#include "ndcg_select32.inc"
+#undef TPQ_CE
+    return v[TPQ_K - 1];
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(TPQ_THREADS, TPQ_CTAS) ndcg_tpq_kernel(const NdcgParams p) {
+    extern __shared__ __align__(16) unsigned char tpq_smem[];
+    // term[r][l] = gain(l) / discount(r) for ranks r < 10 and labels l <= 4, divided exactly as the reference divides
+    __shared__ double term64[F64 ? (TPQ_K - 1) * 5 : 1];
+    __shared__ float term32[F64 ? 1 : (TPQ_K - 1) * 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TpqTile& tile = reinterpret_cast<TpqTile*>(tpq_smem)[warp];
+    const int gwarp = (int)blockIdx.x * TPQ_WARPS + warp;
+    const int nwarps = (int)gridDim.x * TPQ_WARPS;
+    const int ntiles = (p.B + 31) >> 5;
+    const int n = p.n;
+    const float ninf = __int_as_float(0xff800000);
+    const bool lane_in = 4 * lane < n;                     // this lane's quad exists (n % 4 == 0)
+    unsigned long long nmask[2];                           // docs < n, per 64-doc word
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int left = n - 64 * w;
+        nmask[w] = left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
+    }
+    unsigned kends = 0;                                    // bit r: some k of the sweep equals r + 1
+    for (int j = 0; j < p.nk; ++j) kends |= 1u << (p.ks[j] - 1);
+    pdl_prologue();
+    if ((int)threadIdx.x < (TPQ_K - 1) * 5) {
+        const int r = (int)threadIdx.x / 5, l = (int)threadIdx.x % 5;
+        if (r < p.kmax) {
+            if (F64) term64[threadIdx.x] = (p.exp_gains ? (double)((1 << l) - 1) : (double)l) / p.disc64[r];
+            else term32[threadIdx.x] = (float)((1 << l) - 1) / p.disc32[r];
+        }
+    }
+    __syncthreads();
+
+    // labels go through registers in batches of TPQ_BATCH rows, the next batch (of the next tile during phase 2)
+    // always in flight; scores go straight to shared memory with 16-byte asynchronous copies, a whole tile at once
+    float4 y4[TPQ_BATCH];
+    auto issue_labels = [&](int qbase) {
+        const float* yp = p.y_true + (size_t)qbase * n + 4 * lane;
+#pragma unroll
+        for (int i = 0; i < TPQ_BATCH; ++i) {
+            y4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qbase + i < p.B && lane_in) y4[i] = ld_stream4(yp + i * n);
+        }
+    };
+    if (gwarp < ntiles) issue_labels(gwarp << 5);
+
+    for (int t = gwarp; t < ntiles; t += nwarps) {
+        const int q0 = t << 5;
+        // ---------------- phase 1: rows -> shared memory, per-row histogram and flag ----------------
+        {
+            const float* sp = p.y_pred + (size_t)q0 * n + 4 * lane;
+            const unsigned dst = smem_u32(&tile.s[4 * lane]);
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                if (q0 + r < p.B && lane_in)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * TPQ_S_STRIDE * 4), "l"(sp + r * n)
+                                 : "memory");
+                else
+                    *reinterpret_cast<float4*>(&tile.s[r * TPQ_S_STRIDE + 4 * lane]) = make_float4(ninf, ninf, ninf, ninf);
+            }
+        }
+        unsigned myhist = 0;
+        int mybad = 0;
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += TPQ_BATCH) {
+            float4 yc[TPQ_BATCH];
+#pragma unroll
+            for (int i = 0; i < TPQ_BATCH; ++i) yc[i] = y4[i];
+            // next batch of this tile, or the first batch of this warp's next tile (B bounds it)
+            issue_labels(rb < 32 - TPQ_BATCH ? q0 + rb + TPQ_BATCH : ((t + nwarps < ntiles) ? ((t + nwarps) << 5) : p.B));
+            unsigned badbits = 0;
+#pragma unroll
+            for (int i = 0; i < TPQ_BATCH; ++i) {
+                const int r = rb + i;
+                const float ys[4] = {yc[i].x, yc[i].y, yc[i].z, yc[i].w};
+                unsigned hist = 0, word = 0;
+                bool ok = true;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const unsigned v = __float2uint_rz(ys[c]);                  // negative / NaN -> 0, huge -> 2^32 - 1
+                    ok = ok && ((float)v == ys[c]) && (v <= 4u);
+                    hist += shr_clamp(0x01000000u, 32u - 8u * v);              // level L counts in byte L - 1; level 0: nothing
+                    word |= (v & 0xfu) << (4 * c);
+                }
+                tile.lab[r * TPQ_L_STRIDE + lane] = (unsigned short)word;
+                badbits |= ok ? 0u : (1u << i);
+                const unsigned rowhist = __reduce_add_sync(LTR_FULL_MASK, hist);
+                myhist = (lane == r) ? rowhist : myhist;
+            }
+            badbits = __reduce_or_sync(LTR_FULL_MASK, badbits);      // one vote per batch
+            if (lane / TPQ_BATCH == rb / TPQ_BATCH) mybad = (int)((badbits >> (lane % TPQ_BATCH)) & 1u);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+
+        // ---------------- phase 2: one query per lane --------------------------------------------------
+        const int q = q0 + lane;
+        const float* srow = &tile.s[lane * TPQ_S_STRIDE];
+        // lower bound of the TPQ_K-th largest score: the TPQ_K-th largest of the 32 quad maxima
+        float qm[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(srow + 4 * j);
+            qm[j] = max_nan(max_nan(x.x, x.y), max_nan(x.z, x.w));       // a NaN score sends the query to the full sort
+        }
+        bool anynan = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) anynan = anynan || (qm[j] != qm[j]);
+        const float L = tpq_select11(qm);
+        asm volatile("" ::: "memory");          // read the row again below rather than keeping 128 scores in registers
+        // candidate docs: score >= L
+        unsigned cand[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(srow + 4 * j);
+            unsigned& w = cand[j >> 3];
+            const int b0 = 4 * (j & 7);
+            w |= (x.x >= L) ? (1u << b0) : 0u;
+            w |= (x.y >= L) ? (2u << b0) : 0u;
+            w |= (x.z >= L) ? (4u << b0) : 0u;
+            w |= (x.w >= L) ? (8u << b0) : 0u;
+        }
+        float top[TPQ_K];
+        int lab[TPQ_K];
+#pragma unroll
+        for (int j = 0; j < TPQ_K; ++j) top[j] = ninf, lab[j] = 0;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            unsigned long long m = (((unsigned long long)cand[2 * w + 1] << 32) | cand[2 * w]) & nmask[w];
+            while (m) {
+                const int d = 64 * w + (__ffsll((long long)m) - 1);
+                m &= m - 1;
+                const float x = srow[d] + 0.0f;                                  // -0 -> +0
+                const unsigned word = tile.lab[lane * TPQ_L_STRIDE + (d >> 2)];
+                tpq_insert<TPQ_K>(top, lab, x, (int)((word >> (4 * (d & 3))) & 0xfu));
+            }
+        }
+        // a tie group that reaches into the first kmax ranks needs the reference's sort order
+        int bad = mybad | (anynan ? 1 : 0);
+#pragma unroll
+        for (int j = 0; j + 1 < TPQ_K; ++j)
+            bad |= (j < p.kmax && j + 1 < n && top[j] == top[j + 1]) ? 1 : 0;
+        if (q < p.B) {
+            p.flags[1 + q] = bad;
+            if (!bad) {
+                // ideal order from the histogram: level L fills the ranks below #docs with label >= L
+                const int c4 = myhist >> 24, c3 = c4 + ((myhist >> 16) & 255), c2 = c3 + ((myhist >> 8) & 255),
+                          c1 = c2 + (myhist & 255);
+                if (!F64) {
+                    float got = 0.f, ideal = 0.f;
+                    float* out = p.out32 + (size_t)q * p.nk;
+#pragma unroll
+                    for (int r = 0; r < TPQ_K - 1; ++r) {
+                        if (r < p.kmax) {
+                            const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
+                            got += term32[5 * r + lab[r]];
+                            ideal += term32[5 * r + li];
+                            if ((kends >> r) & 1u) {
+                                const float val = got / ideal;
+                                for (int j = 0; j < p.nk; ++j)
+                                    if (p.ks[j] == r + 1) out[j] = val;
+                            }
+                        }
+                    }
+                } else {
+                    double got = 0.0, ideal = 0.0;
+                    double* out = p.out64 + (size_t)q * p.nk;
+#pragma unroll
+                    for (int r = 0; r < TPQ_K - 1; ++r) {
+                        if (r < p.kmax) {
+                            const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
+                            got += term64[5 * r + lab[r]];
+                            ideal += term64[5 * r + li];
+                            if ((kends >> r) & 1u) {
+                                const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
+                                for (int j = 0; j < p.nk; ++j)
+                                    if (p.ks[j] == r + 1) out[j] = val;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();                                            // the tile is free for the next phase 1
+    }
+}
+
+}  // namespace ltr

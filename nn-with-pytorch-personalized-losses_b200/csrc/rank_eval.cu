@@ -81,52 +81,75 @@ struct NdcgParams {
     float* out32;
     double* out64;
     int kmax;                // largest k of the sweep (top-k fast path)
-    int* flags;              // [1 + B] scratch: flags[0] = number of queries the top-k path left to the full sort
-                             // (a tie among their first kmax + 1 ranks), flags[1..] = their indices
+    int* flags;              // [1 + B] scratch: flags[1 + q] != 0 marks a query the top-k path left to the full sort
+                             // (a tie among its first kmax + 1 ranks, a NaN score, an unusual label)
 };
 
+// one query: full sort with the caller's tie rule, labels in predicted and in ideal order, all k of the sweep
+template <bool F64>
+__device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b) {
+    const float ninf = __int_as_float(0xff800000);
+    const float* yt = p.y_true + (size_t)b * p.n;
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
+    __syncthreads();
+    block_sort_desc(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule);
+    // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
+    for (int i = threadIdx.x; i < p.len; i += blockDim.x) {
+        sm.L[i] = (i < p.n) ? yt[i] : ninf;
+        if (i < p.n) sm.K0[i] = yt[sm.I[i]];
+    }
+    block_bitonic_desc(sm.L, p.len);
+    if ((int)threadIdx.x < p.nk) {
+        int k = p.ks[threadIdx.x];
+        if (k <= 0 || k > p.n) k = p.n;
+        if (!F64) {
+            float got = 0.f, ideal = 0.f;
+            for (int r = 0; r < k; ++r) {
+                const float d = p.disc32[r];
+                got += (exp2f(sm.K0[r]) - 1.0f) / d;
+                ideal += (exp2f(sm.L[r]) - 1.0f) / d;
+            }
+            p.out32[(size_t)b * p.nk + threadIdx.x] = got / ideal;
+        } else {
+            double got = 0.0, ideal = 0.0;
+            for (int r = 0; r < k; ++r) {
+                const double d = p.disc64[r];
+                const double lg = (double)sm.K0[r], li = (double)sm.L[r];
+                got += (p.exp_gains ? exp2(lg) - 1.0 : lg) / d;
+                ideal += (p.exp_gains ? exp2(li) - 1.0 : li) / d;
+            }
+            p.out64[(size_t)b * p.nk + threadIdx.x] = (ideal == 0.0) ? p.empty_value : got / ideal;
+        }
+    }
+    __syncthreads();
+}
+
+// Without flags: every query.  With flags (a top-k fast path ran in front): only the queries q it marked with
+// flags[1 + q] != 0; a CTA looks at 32 flags at a time, so a batch without marked queries costs one read per CTA.
 template <bool F64>
 __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned marked;
     RankSmem sm(smem_raw, p.len);
-    const float ninf = __int_as_float(0xff800000);
-    // with the top-k fast path in front, only the queries it appended to the flagged list are sorted here
-    const int work = p.flags ? p.flags[0] : p.B;
-    for (int w = blockIdx.x; w < work; w += gridDim.x) {
-        const int b = p.flags ? p.flags[1 + w] : w;
-        const float* yt = p.y_true + (size_t)b * p.n;
-        for (int i = threadIdx.x; i < p.n; i += blockDim.x) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
-        __syncthreads();
-        block_sort_desc(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule);
-        // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
-        for (int i = threadIdx.x; i < p.len; i += blockDim.x) {
-            sm.L[i] = (i < p.n) ? yt[i] : ninf;
-            if (i < p.n) sm.K0[i] = yt[sm.I[i]];
-        }
-        block_bitonic_desc(sm.L, p.len);
-        if ((int)threadIdx.x < p.nk) {
-            int k = p.ks[threadIdx.x];
-            if (k <= 0 || k > p.n) k = p.n;
-            if (!F64) {
-                float got = 0.f, ideal = 0.f;
-                for (int r = 0; r < k; ++r) {
-                    const float d = p.disc32[r];
-                    got += (exp2f(sm.K0[r]) - 1.0f) / d;
-                    ideal += (exp2f(sm.L[r]) - 1.0f) / d;
-                }
-                p.out32[(size_t)b * p.nk + threadIdx.x] = got / ideal;
-            } else {
-                double got = 0.0, ideal = 0.0;
-                for (int r = 0; r < k; ++r) {
-                    const double d = p.disc64[r];
-                    const double lg = (double)sm.K0[r], li = (double)sm.L[r];
-                    got += (p.exp_gains ? exp2(lg) - 1.0 : lg) / d;
-                    ideal += (p.exp_gains ? exp2(li) - 1.0 : li) / d;
-                }
-                p.out64[(size_t)b * p.nk + threadIdx.x] = (ideal == 0.0) ? p.empty_value : got / ideal;
-            }
+    pdl_prologue();
+    if (!p.flags) {
+        for (int b = blockIdx.x; b < p.B; b += gridDim.x) ndcg_sorted_query<F64>(p, sm, b);
+        return;
+    }
+    for (int base = (int)blockIdx.x * 32; base < p.B; base += (int)gridDim.x * 32) {
+        if (threadIdx.x < 32) {
+            const int q = base + (int)threadIdx.x;
+            const unsigned m = __ballot_sync(LTR_FULL_MASK, q < p.B && p.flags[1 + q] != 0);
+            if (threadIdx.x == 0) marked = m;
         }
         __syncthreads();
+        unsigned m = marked;
+        __syncthreads();
+        while (m) {
+            const int b = base + __ffs((int)m) - 1;
+            m &= m - 1;
+            ndcg_sorted_query<F64>(p, sm, b);
+        }
     }
 }
 
@@ -216,6 +239,10 @@ __device__ __forceinline__ float ideal_label_from_counts(const int (&cnt)[8]) {
     return (float)ge;                                           // labels fill the ranks from the top level down
 }
 
+}  // namespace ltr
+#include "ndcg_stream.cuh"
+namespace ltr {
+
 template <bool F64>
 __device__ __forceinline__ void write_ndcg_sums(const NdcgParams& p, int b, int myk, float lab_pred, float lab_ideal) {
     const int lane = threadIdx.x & 31;
@@ -301,10 +328,8 @@ __global__ void __launch_bounds__(256) ndcg_topk_kernel(const NdcgParams p) {
         int key_r, tie;
         float lab_pred;
         topk_rounds<ITEMS>(k, l, p.kmax, key_r, lab_pred, tie);
-        if (tie || !ok) {                                         // left to the full sort
-            if (lane == 0) p.flags[1 + atomicAdd(p.flags, 1)] = b;
-            continue;
-        }
+        if (lane == 0) p.flags[1 + b] = (tie || !ok) ? 1 : 0;     // marked queries are left to the full sort
+        if (tie || !ok) continue;
         write_ndcg_sums<F64>(p, b, myk, lab_pred, ideal_label_from_counts(cnt));
     }
 }
@@ -345,11 +370,8 @@ __global__ void __launch_bounds__(128) ndcg_topk_wide_kernel(const NdcgParams p)
             int key_m, tie_m;
             float lab_pred;
             topk_rounds<4>(mk, ml, p.kmax, key_m, lab_pred, tie_m);
-            if (bad || tie_m) {
-                if (lane == 0) p.flags[1 + atomicAdd(p.flags, 1)] = b;
-            } else {
-                write_ndcg_sums<F64>(p, b, myk, lab_pred, ideal_label_from_counts(tot));
-            }
+            if (lane == 0) p.flags[1 + b] = (bad || tie_m) ? 1 : 0;
+            if (!(bad || tie_m)) write_ndcg_sums<F64>(p, b, myk, lab_pred, ideal_label_from_counts(tot));
         }
         __syncthreads();
     }
@@ -485,35 +507,57 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     p.kmax = kmax;
     const size_t smem = rank_smem(p.len);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (kmax <= 31 && p.n <= 1024 && p.flags) {
-        // top-k fast path (one warp per query), then the full sort for the queries it flagged
-        LTR_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(int), st));
+    const int cap = device_sm_count() * 8;
+    bool marked_only = false;
+    if (kmax <= TPQ_K - 1 && p.n <= TPQ_N && p.n % 4 == 0 && p.flags &&
+        (reinterpret_cast<uintptr_t>(p.y_true) | reinterpret_cast<uintptr_t>(p.y_pred)) % 16 == 0) {
+        // one thread per query (ndcg_stream.cuh), then the full sort for the queries it marked
+        static bool attr_done = false;
+        if (!attr_done) {
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_tpq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_tpq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
+            attr_done = true;
+        }
+        const int tiles = (p.B + 31) / 32;
+        int g = (tiles + TPQ_WARPS - 1) / TPQ_WARPS;
+        const int gcap = device_sm_count() * TPQ_CTAS;
+        g = g < gcap ? g : gcap;
+        const int rc = f64 ? launch_pdl(ndcg_tpq_kernel<true>, g, TPQ_THREADS, TPQ_SMEM, st, p)
+                           : launch_pdl(ndcg_tpq_kernel<false>, g, TPQ_THREADS, TPQ_SMEM, st, p);
+        if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (one thread per query)");
+        marked_only = true;
+    } else if (kmax <= 31 && p.n <= 1024 && p.flags) {
+        // top-k fast path (one warp per query), then the full sort for the queries it marked
         int g = (p.B + 7) / 8;
-        const int cap = device_sm_count() * 8;
         g = g < cap ? g : cap;
 #define LTR_TOPK(ITEMS)                                                      \
         if (f64) ndcg_topk_kernel<ITEMS, true><<<g, 256, 0, st>>>(p);            \
         else ndcg_topk_kernel<ITEMS, false><<<g, 256, 0, st>>>(p)
-        bool wide = false;
         if (p.n <= 128) { LTR_TOPK(4); }
         else if (p.n <= 256) { LTR_TOPK(8); }
         else {
-            wide = true;                           // ties of any rule go to the full sort there
-            const int gw = p.B < cap ? p.B : cap;
+            const int gw = p.B < cap ? p.B : cap;          // ties of any rule go to the full sort there
             if (f64) ndcg_topk_wide_kernel<true><<<gw, 128, 0, st>>>(p);
             else ndcg_topk_wide_kernel<false><<<gw, 128, 0, st>>>(p);
         }
 #undef LTR_TOPK
-        (void)wide;
+        marked_only = true;
     } else {
         p.flags = nullptr;
     }
+    int gs = rank_grid(p.B);
+    if (marked_only) {
+        const int chunks = (p.B + 31) / 32;
+        gs = chunks < cap ? chunks : cap;
+    }
     if (f64) {
         if (int rc = rank_prepare(ndcg_kernel<true>, smem)) return rc;
-        ndcg_kernel<true><<<rank_grid(p.B), RANK_THREADS, smem, st>>>(p);
+        const int rc = launch_pdl(ndcg_kernel<true>, gs, RANK_THREADS, smem, st, p);
+        return rc ? set_cuda_error(rc, "ltr_ndcg_at_k") : 0;
     } else {
         if (int rc = rank_prepare(ndcg_kernel<false>, smem)) return rc;
-        ndcg_kernel<false><<<rank_grid(p.B), RANK_THREADS, smem, st>>>(p);
+        const int rc = launch_pdl(ndcg_kernel<false>, gs, RANK_THREADS, smem, st, p);
+        return rc ? set_cuda_error(rc, "ltr_ndcg_at_k") : 0;
     }
     const int rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_ndcg_at_k") : 0;
