@@ -92,7 +92,7 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
     const float* yt = p.y_true + (size_t)b * p.n;
     for (int i = threadIdx.x; i < p.n; i += blockDim.x) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
     __syncthreads();
-    block_sort_desc(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule);
+    block_sort_desc(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1);   // ranks >= kmax are never read
     // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
     for (int i = threadIdx.x; i < p.len; i += blockDim.x) {
         sm.L[i] = (i < p.n) ? yt[i] : ninf;

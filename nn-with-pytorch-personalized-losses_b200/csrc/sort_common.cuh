@@ -150,11 +150,17 @@ struct StdSortEmu {
             ++lo;
         }
     }
-    __device__ void sort(int n) {
-        if (n <= 1) return;
+    // Replays std::sort on n elements; only the first `limit` positions of the result are needed.
+    // A partition's right part [cut, last) with cut >= limit is never looked at again: introsort's sub-ranges are
+    // disjoint, and in the final insertion sort an element can only move left past keys that sort strictly after
+    // it, so nothing from such a part can enter a position below cut.  Positions >= the returned bound are left
+    // unsorted (bound >= min(limit, n); bound == n when limit >= n: the complete sort).
+    __device__ int sort(int n, int limit) {
+        if (n <= 1) return n;
         int depth0 = 0;
         for (int t = n; t > 1; t >>= 1) ++depth0;                 // __lg(n)
         depth0 *= 2;
+        int bound = n;
         // __introsort_loop with an explicit stack (sub-ranges are disjoint, so their order is immaterial)
         int stk_first[48], stk_last[48], stk_depth[48];
         int sp = 0;
@@ -170,24 +176,30 @@ struct StdSortEmu {
                 }
                 --depth;
                 const int cut = partition_pivot(first, last);
-                stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
+                if (cut < limit) {
+                    stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
+                } else if (cut < bound) {
+                    bound = cut;
+                }
                 last = cut;
             }
         }
-        if (n > 16) {                                             // __final_insertion_sort
+        if (bound > 16) {                                         // __final_insertion_sort
             insertion_sort(0, 16);
-            for (int i = 16; i < n; ++i) unguarded_linear_insert(i);
+            for (int i = 16; i < bound; ++i) unguarded_linear_insert(i);
         } else {
-            insertion_sort(0, n);
+            insertion_sort(0, bound);
         }
+        return bound;
     }
 };
 
 // Sort one slate.  On entry K[0..n) holds the keys in original order.  On exit K/I[0..n) hold the sorted
 // keys and the permutation (I[r] = original index of the doc at rank r).  K, I: `len` = next_pow2(n)
 // shared-memory entries each; K0 (n floats) is scratch that keeps the original keys for the replay.
-// Only ties among the first `tie_limit` sorted entries trigger the replay (callers whose trailing entries
-// are -inf padding that no output depends on pass the number of real docs).
+// `tie_limit`: the caller only reads the first tie_limit entries of the result (callers whose trailing entries
+// are -inf padding that no output depends on pass the number of real docs; NDCG@k passes kmax + 1).  Only ties
+// among those entries trigger the replay, and after a replay entries at and beyond tie_limit may be in any order.
 __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int n, int len, int tie_rule,
                                                 int tie_limit = 1 << 30) {
     const float ninf = __int_as_float(0xff800000);
@@ -212,7 +224,7 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
     if (threadIdx.x == 0) {
         for (int i = 0; i < n; ++i) { K[i] = K0[i]; I[i] = i; }
         StdSortEmu emu{K, I};
-        emu.sort(n);
+        emu.sort(n, lim);                                         // entries at and beyond `lim` may stay unsorted
     }
     __syncthreads();
 }
