@@ -433,9 +433,13 @@ static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
 
 namespace ltr {
 int upload_disc_prefix_constant() {
-    double host[129];
-    host[0] = 0.0;
-    for (int r = 1; r <= 128; ++r) host[r] = host[r - 1] + 1.0 / log2(1.0 + (double)r);
+    double acc = 0.0;
+    float host[129];
+    host[0] = 0.0f;
+    for (int r = 1; r <= 128; ++r) {
+        acc += 1.0 / log2(1.0 + (double)r);
+        host[r] = (float)acc;
+    }
     return (int)cudaMemcpyToSymbol(c_disc_prefix, host, sizeof(host));
 }
 }  // namespace ltr

@@ -45,8 +45,9 @@
 namespace ltr {
 
 // discount prefix sums P[r] = sum_{q<=r} 1/log2(1+q), r = 0..128, for the histogram ideal DCG of the fast path
-// (filled by ltr_fill_disc_prefix; a uniform-index constant-bank read, no per-CTA table load)
-__constant__ double c_disc_prefix[129];
+// (summed in fp64 and rounded once by ltr_fill_disc_prefix; a uniform-index constant-bank read, no per-CTA table
+// load).  The reference sums these terms in fp32; four rounded table entries are well inside its own error.
+__constant__ float c_disc_prefix[129];
 
 struct ApproxParams {
     const float* s;
@@ -74,7 +75,7 @@ struct SymShared {
     float u[SYM_N];               // 2^(t - c)   (direct form: raw score)
     float v[SYM_N];               // 2^-(t - c)
     float c[SYM_N];               // d loss / d pos_i
-    float part[4][2][SYM_N];      // per-warp row / column partial sums (ranks, then gradients)
+    float part[4][SYM_N];         // per-warp partial sums of every doc (ranks, then gradients): row side and column side combined
     float sortbuf[SYM_N];
     int4 wstat[4];                // per warp: {valid count | bad-label flag << 16, min key, max key, packed label counts}
     float red[4];
@@ -268,14 +269,18 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
     const int role = (warp + b) & 3;
     const int d_lo = 1 + ((role * S) >> 2);
     const int d_hi = 1 + (((role + 1) * S) >> 2);
+    const int steps = d_hi - d_lo;
+    // for even T the antipodal step D = T/2 meets every pair twice and is weighted 1/2: it is the last step of role 3
+    const bool anti = ((T & 1) == 0) && (role == 3) && (steps > 0);
+    const int full = steps - (anti ? 1 : 0);
     const bool active = lane < T;
     const int src = active ? ((lane + 1 == T) ? 0 : lane + 1) : lane;
     int cb = lane + d_lo;
     if (cb >= T) cb -= T;
     if (!active) cb = 0;
-    int cb_last = lane + d_hi - 1;
-    if (cb_last >= T) cb_last -= T;
-    if (d_hi == d_lo || !active) cb_last = lane;   // nothing accumulated: the column sums are zero
+    int ret = lane - (d_hi - 1);              // the lane that ends up holding this lane's column accumulators
+    if (ret < 0) ret += T;
+    if (steps == 0 || !active) ret = lane;    // nothing accumulated: the column sums are zero
 
     float urow[R], vcol[R], acc_r[R], acc_r_hi[R], acc_c[R];
 #pragma unroll
@@ -304,37 +309,44 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
         }
     }
 #pragma unroll 1
-    for (int D = d_lo; D < d_hi; ++D) {
-        rank_tile<R>(urow, vcol, (2 * D == T) ? 0.5f : 1.0f, acc_r, acc_r_hi, acc_c);   // antipodal: pairs met twice
-        if (D + 1 < d_hi) {
+    for (int i = 0; i < full; ++i) {
+        if (i) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
                 acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
             }
         }
+        rank_tile<R>(urow, vcol, 1.0f, acc_r, acc_r_hi, acc_c);
     }
-    if (active) {
+    if (anti) {
+        if (full) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            sh.part[warp][0][lane * R + r] = acc_r[r] + acc_r_hi[r];
-            sh.part[warp][1][cb_last * R + r] = acc_c[r];
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
         }
+        rank_tile<R>(urow, vcol, 0.5f, acc_r, acc_r_hi, acc_c);
+    }
+    // the column accumulators go home; a doc's partial is (sum sigma_ij as a row) - (sum sigma_ij as a column)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) - cols;
     }
     __syncthreads();
 
     // ---------------- per doc: soft rank, slate value, d loss / d pos --------------------------
     float sum = 0.f;
     if (doc.valid) {
-        float rows = 0.f, cols = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rows += sh.part[k][0][doc.dst], cols += sh.part[k][1][doc.dst];
+        const float parts = (sh.part[0][doc.dst] + sh.part[1][doc.dst]) + (sh.part[2][doc.dst] + sh.part[3][doc.dst]);
         // column side: sum sigma_ji = (#rows met, antipodal ones at 1/2) - sum sigma_ij = R (T-1)/2 - cols.
         // padded tail of the last block (u = v = 0): as a column it reads sigma_ij = 1 on the row side.
         const int npadc = T * R - m;
         const int e = T - 1 - doc.dst / R;               // circulant distance to the last block
         const float f = (2 * e == T) ? 0.5f : ((2 * e < T) ? 1.0f : 0.0f);
-        sum = (rows - f * (float)npadc) + (0.5f * (float)(R * (T - 1)) - cols);
+        sum = (parts - f * (float)npadc) + 0.5f * (float)(R * (T - 1));
     }
     slate_middle(p, sh, b, doc, sum, cy, next_s, next_y, next_b);
     if (p.grad == nullptr) {
@@ -370,16 +382,8 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
         }
     }
 #pragma unroll 1
-    for (int D = d_lo; D < d_hi; ++D) {
-        if (2 * D == T) {                       // antipodal step: weight 1/2 goes onto the c differences
-            float ch[R], cch[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) ch[r] = 0.5f * crow[r], cch[r] = 0.5f * ccol[r];
-            grad_tile<R>(urow, vcol, ch, cch, acc_r, acc_r_hi, acc_c);
-        } else {
-            grad_tile<R>(urow, vcol, crow, ccol, acc_r, acc_r_hi, acc_c);
-        }
-        if (D + 1 < d_hi) {
+    for (int i = 0; i < full; ++i) {
+        if (i) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
@@ -387,21 +391,31 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
                 acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
             }
         }
+        grad_tile<R>(urow, vcol, crow, ccol, acc_r, acc_r_hi, acc_c);
     }
-    if (active) {
+    if (anti) {                                 // weight 1/2 goes onto the c differences
+        if (full) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            sh.part[warp][0][lane * R + r] = acc_r[r] + acc_r_hi[r];
-            sh.part[warp][1][cb_last * R + r] = acc_c[r];
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                ccol[r] = __shfl_sync(LTR_FULL_MASK, ccol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
         }
+        float ch[R], cch[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ch[r] = 0.5f * crow[r], cch[r] = 0.5f * ccol[r];
+        grad_tile<R>(urow, vcol, ch, cch, acc_r, acc_r_hi, acc_c);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) + cols;
     }
     __syncthreads();
     if (tid < p.n) {
         float sum2 = 0.f;
-        if (doc.valid) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sum2 += sh.part[k][0][doc.dst] + sh.part[k][1][doc.dst];
-        }
+        if (doc.valid) sum2 = (sh.part[0][doc.dst] + sh.part[1][doc.dst]) + (sh.part[2][doc.dst] + sh.part[3][doc.dst]);
         p.grad[(size_t)b * p.n + tid] = p.alpha * sum2;          // padded docs: exactly 0
     }
 }
@@ -497,8 +511,8 @@ __global__ void __launch_bounds__(SYM_THREADS, SYM_MIN_CTAS) approx_ndcg_sym_ker
                 const int e3 = e4 + ((packed >> 16) & 255);
                 const int e2 = e3 + ((packed >> 8) & 255);
                 const int e1 = e2 + (packed & 255);
-                const double dcg = 8.0 * c_disc_prefix[e4] + 4.0 * c_disc_prefix[e3] + 2.0 * c_disc_prefix[e2] + c_disc_prefix[e1];
-                maxdcg = fmaxf((float)dcg, p.eps);
+                const float dcg = fmaf(8.0f, c_disc_prefix[e4], fmaf(4.0f, c_disc_prefix[e3], fmaf(2.0f, c_disc_prefix[e2], c_disc_prefix[e1])));
+                maxdcg = fmaxf(dcg, p.eps);
                 gain = (float)((1 << lvl) - 1);
             } else {
                 // general labels: bitonic sort (descending) of the clamped labels

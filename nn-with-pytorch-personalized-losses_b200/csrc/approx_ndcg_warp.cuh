@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(WPS_THREADS, WPS_MIN_CTAS) approx_ndcg_warp_ke
                 const int e3 = e4 + ((packed >> 16) & 255);
                 const int e2 = e3 + ((packed >> 8) & 255);
                 const int e1 = e2 + (packed & 255);
-                const double dcg = 8.0 * c_disc_prefix[e4] + 4.0 * c_disc_prefix[e3] + 2.0 * c_disc_prefix[e2] + c_disc_prefix[e1];
-                maxdcg = fmaxf((float)dcg, p.eps);
+                const float dcg = fmaf(8.0f, c_disc_prefix[e4], fmaf(4.0f, c_disc_prefix[e3], fmaf(2.0f, c_disc_prefix[e2], c_disc_prefix[e1])));
+                maxdcg = fmaxf(dcg, p.eps);
             } else {
                 // general labels: every doc finds its ideal rank by counting (rare path)
 #pragma unroll

@@ -76,24 +76,42 @@ def bench_listnet(iters=200, B=65536, n=128):
     sec = _time(step, iters)
     return {"metric": "ListNet fwd+bwd slates/s", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
             "config": {"workload": f"{B} slates x {n} docs, no padding, ring of {ring} batches"},
-            "roofline": dict(_roof(12.0 * n * B, sec), kernel="listnet_kernel<4>", algorithmic="12 n bytes per slate")}
+            "roofline": dict(_roof(12.0 * n * B, sec), kernel="listnet_vec_kernel<1>", algorithmic="12 n bytes per slate")}
 
 
-def bench_ndcg(iters=100, Q=65536, n=128, ks=(1, 5, 10)):
-    """NDCG@{1,5,10} evaluation sweep: one read + one sort per query.  8 n + 4 |ks| bytes per query."""
-    from ltr_b200 import ops
-    ring = 3
+def bench_ndcg(iters=100, Q=65536, n=128, ks=(1, 5, 10), ring=3):
+    """NDCG@{1,5,10} evaluation sweep through the C-ABI (preallocated outputs): one read of the query, no sort unless
+    tied scores reach the first k + 1 ranks.  8 n + 4 |ks| bytes per query."""
+    import ctypes
+    from ltr_b200 import _lib, ops, _runtime as rt
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
     data = [_slates(Q, n, 200 + i, pad=False) for i in range(ring)]
+    d32, _ = ops._disc_tables(n, dev)
+    out = torch.empty(Q, len(ks), device=dev)
+    marks = [torch.empty(Q + 1, dtype=torch.int32, device=dev) for _ in range(ring)]
+    karr = (ctypes.c_int * len(ks))(*ks)
 
     def step(i):
         s, y = data[i % ring]
-        ops.ndcg_at_k(y, s, list(ks), ops.TIES_STDSORT)
+        lib.ltr_ndcg_at_k(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(), out.data_ptr(),
+                          marks[i % ring].data_ptr(), rt.stream_ptr())
 
     sec = _time(step, iters)
+    marked = [int((m[1:] != 0).sum()) for m in marks]
+    kern = "ndcg_tpq_kernel<false> + ndcg_kernel<false> (marked queries only)" if n <= 128 and max(ks) <= 10 else \
+        "ndcg_topk_wide_kernel<false> + ndcg_kernel<false> (marked queries only)"
     return {"metric": f"NDCG@{{{','.join(map(str, ks))}}} eval queries/s (n={n})", "value": Q / sec, "unit": "queries/s",
-            "us_per_call": sec * 1e6, "config": {"workload": f"{Q} queries x {n} docs, k sweep {list(ks)}, torchNdcg arithmetic"},
-            "roofline": dict(_roof((8.0 * n + 4.0 * len(ks)) * Q, sec), kernel="ndcg_kernel<false>",
+            "us_per_call": sec * 1e6,
+            "config": {"workload": f"{Q} queries x {n} docs, k sweep {list(ks)}, torchNdcg arithmetic, ring of {ring} batches",
+                       "queries_with_tied_top_scores_per_batch": marked},
+            "roofline": dict(_roof((8.0 * n + 4.0 * len(ks)) * Q, sec), kernel=kern,
                              algorithmic="8 n + 4 |ks| bytes per query")}
+
+
+def bench_ndcg_large(iters=20):
+    """The same sweep on an evaluation set of 2^20 queries (tile granularity and launch gaps amortised)."""
+    return bench_ndcg(iters, Q=1 << 20, n=128, ring=2)
 
 
 def bench_lambda(iters=50, B=1024, n=256):
@@ -208,7 +226,7 @@ def bench_approx_large(iters=30, B=65536, n=128):
     return {"metric": "approxNDCG fwd+bwd slates/s (n=128, 65536 slates per launch)", "value": B / sec, "unit": "slates/s",
             "us_per_call": sec * 1e6, "config": {"workload": f"{B} slates x {n} docs, valid len U{{64..128}}, alpha=10"},
             "roofline": {"bound": "sfu", "achieved": 2.0 * (sum(pairs) / ring) / sec / 1e12, "unit": "TSFU-op/s",
-                         "algorithmic": "2 SFU ops per ordered valid pair", "kernel": "approx_ndcg_sym_kernel"}}
+                         "algorithmic": "2 SFU ops per ordered valid pair", "kernel": "approx_ndcg_warp_kernel"}}
 
 
 def bench_ndcg_1024(iters=30):
@@ -216,7 +234,7 @@ def bench_ndcg_1024(iters=30):
     return bench_ndcg(iters, Q=8192, n=1024)
 
 
-ALL = {"listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg1024": bench_ndcg_1024, "lambda": bench_lambda,
+ALL = {"listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg_large": bench_ndcg_large, "ndcg1024": bench_ndcg_1024, "lambda": bench_lambda,
        "georisk": bench_georisk, "approx1024": bench_approx_1024, "approx_large_batch": bench_approx_large}
 
 
