@@ -215,6 +215,17 @@ int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int inve
                    float* gq, float* gmat, void* stream);
 
 /*
+ * geoRisk / zRisk / tRisk ListNet loss, forward + backward in one call on one GPU (no exchange between the phases).
+ * replaces losses/riskLosses/riskLosses.py:8-60, 128-180, 247-291 end to end: ltr_risk_listnet_rows, the three
+ * ltr_risk_phase launches and ltr_risk_listnet_rows_bwd, with the same arguments.
+ *   mat : [B, 1 + S + add_ideal] out; state : 32 device doubles of scratch; gq : [B] scratch; grad : [B, n] or NULL.
+ */
+int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
+                            int transformation, int add_ideal, int kind, int invert, int return_strategy,
+                            int precedence_quirk, float alpha, float negative, float* mat, double* state, float* loss,
+                            float* gq, float* grad, void* stream);
+
+/*
  * Roofline probes (measurement only): a pure ex2.approx loop and a pure FFMA loop, 8 CTAs of
  * 256 threads per SM.  *ops_out (host pointer, may be NULL) receives the number of SFU ops /
  * FP32 FMA lane-ops one launch executes; `out` is one device float that is never written.

@@ -63,6 +63,7 @@ __device__ __forceinline__ float effectiveness(const RowRegs<ITEMS>& pt, const R
 
 template <int ITEMS>
 __global__ void __launch_bounds__(STREAM_THREADS) risk_rows_kernel(const RiskRowsParams p) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * STREAM_WARPS;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) risk_rows_kernel(const RiskRow
 // K6c: grad[b, :] = gq[b] * d mat[b, 0] / d y_pred[b, :]
 template <int ITEMS>
 __global__ void __launch_bounds__(STREAM_THREADS) risk_rows_bwd_kernel(const RiskRowsParams p) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * STREAM_WARPS;
@@ -187,6 +189,7 @@ __device__ __forceinline__ double rf_block_max(double v, double* red) {
 // phase 1 (local): state1 = {max(mat), sum_q mat[q,0], sum_q mat[q,C-1], sum of all entries, Q,
 //                            t-risk: sum_q d_q, 0...} where d_q = mat[q,1] - mat[q,0] needs no max at all.
 __global__ void __launch_bounds__(RISKF_THREADS) risk_stats1_kernel(const RiskFinalParams p) {
+    pdl_prologue();
     __shared__ double red[32];
     double mx = -1.0e300, s0 = 0.0, sl = 0.0, sa = 0.0;
     for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
@@ -254,6 +257,7 @@ __device__ __forceinline__ ZCol make_zcol(const RiskFinalParams& p, const double
 // phase 2 (local, needs global state1): per used column {sum z c, sum A T, sum A e, sum c / sqrt(e), sum A}, count of
 // entries equal to the global max;  t-risk: {sum d', sum d'^2} with d' = d (1 + alpha [d < 0]).
 __global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskFinalParams p) {
+    pdl_prologue();
     __shared__ double red[32];
     const double* g1 = p.state1;
     double a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -298,6 +302,7 @@ __device__ __forceinline__ double std_normal_cdf(double x) { return 0.5 * erfc(-
 
 // phase 3 (local, needs global state1 and state2): loss value and gq[q] = d loss / d mat[q, 0].
 __global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskFinalParams p) {
+    pdl_prologue();
     const double* g1 = p.state1;
     const double* g2 = p.state2;
     const double f = (double)p.negative;
@@ -398,15 +403,14 @@ static int risk_grid(int B) {
 template <bool BWD>
 static int launch_rows(const RiskRowsParams& p, cudaStream_t st) {
     const int grid = risk_grid(p.B);
-#define LTR_ROWS(ITEMS)                                                                   \
-    if (BWD) risk_rows_bwd_kernel<ITEMS><<<grid, STREAM_THREADS, 0, st>>>(p);              \
-    else risk_rows_kernel<ITEMS><<<grid, STREAM_THREADS, 0, st>>>(p)
+#define LTR_ROWS(ITEMS) \
+    return BWD ? launch_pdl(risk_rows_bwd_kernel<ITEMS>, grid, STREAM_THREADS, 0, st, p) \
+               : launch_pdl(risk_rows_kernel<ITEMS>, grid, STREAM_THREADS, 0, st, p)
     if (p.n <= 128) { LTR_ROWS(4); }
     else if (p.n <= 256) { LTR_ROWS(8); }
     else if (p.n <= 512) { LTR_ROWS(16); }
     else { LTR_ROWS(32); }
 #undef LTR_ROWS
-    return (int)cudaGetLastError();
 }
 
 }  // namespace ltr
@@ -448,9 +452,27 @@ LTR_API int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, 
     RiskFinalParams p{mat, Q, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state1, state2, loss, gq,
                       gmat};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (phase == 1) risk_stats1_kernel<<<1, RISKF_THREADS, 0, st>>>(p);
-    else if (phase == 2) risk_stats2_kernel<<<1, RISKF_THREADS, 0, st>>>(p);
-    else risk_final_kernel<<<1, RISKF_THREADS, 0, st>>>(p);
-    const int rc = (int)cudaGetLastError();
+    const int rc = phase == 1 ? launch_pdl(risk_stats1_kernel, 1, RISKF_THREADS, 0, st, p)
+                 : phase == 2 ? launch_pdl(risk_stats2_kernel, 1, RISKF_THREADS, 0, st, p)
+                              : launch_pdl(risk_final_kernel, 1, RISKF_THREADS, 0, st, p);
     return rc ? set_cuda_error(rc, "ltr_risk_phase") : 0;
+}
+
+// Single-GPU fused call: rows -> phase 1 -> phase 2 -> phase 3 -> backward rows, five dependent launches issued from
+// one host call (each starts its ramp-up under the previous one's tail).  Query-sharded callers use the separate
+// entry points above and all-reduce the two state blocks between the phases.
+LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
+                                    int transformation, int add_ideal, int kind, int invert, int return_strategy,
+                                    int precedence_quirk, float alpha, float negative, float* mat, double* state,
+                                    float* loss, float* gq, float* grad, void* stream) {
+    using namespace ltr;
+    if (!state || !loss || (grad && !gq)) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad arguments");
+    const int t_variant = (kind == 2) ? 1 : 0;
+    const int C = 1 + S + (add_ideal ? 1 : 0);
+    int rc = ltr_risk_listnet_rows(y_pred, y_true, y_baselines, B, n, S, transformation, add_ideal, t_variant, mat, stream);
+    for (int phase = 1; phase <= 3 && !rc; ++phase)
+        rc = ltr_risk_phase(phase, mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state,
+                            state + 16, loss, gq, nullptr, stream);
+    if (!rc && grad) rc = ltr_risk_listnet_rows_bwd(y_pred, y_true, B, n, transformation, t_variant, gq, grad, stream);
+    return rc;
 }

@@ -43,6 +43,8 @@ _SIGNATURES = {
                                        _P, _P]),
     "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
                                _P, _P]),
+    "ltr_risk_listnet_fwdbwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                        c_float, _P, _P, _P, _P, _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
     "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
 }

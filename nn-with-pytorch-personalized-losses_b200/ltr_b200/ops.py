@@ -312,12 +312,25 @@ class _RiskListnet(torch.autograd.Function):
         tvar = 1 if kind == KIND_T else 0
         C = 1 + S + (1 if add_ideal else 0)
         mat = torch.empty(B, C, dtype=torch.float32, device=dev)
-        _lib.check(lib.ltr_risk_listnet_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
-                                             int(bool(add_ideal)), tvar, mat.data_ptr(), rt.stream_ptr()),
-                   "ltr_risk_listnet_rows")
         # mat <- max(mat) - mat: riskLosses.py:49-50 (lt 1, 3) and :274-275 (t-risk: lt 1 only)
         invert = (lt == 1) if kind == KIND_T else (lt in (1, 3))
         need = ctx.needs_input_grad[0]
+        if not sharding.is_sharded(group):
+            # one GPU: the five dependent launches are issued by one library call
+            scratch = torch.empty(32 * 2 + 1 + B, dtype=torch.float32, device=dev)   # 32 doubles | loss | gq
+            state, loss, gq = scratch[:64].view(torch.float64), scratch[64:65], scratch[65:]
+            grad = torch.empty_like(y_pred) if need else None
+            _lib.check(lib.ltr_risk_listnet_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
+                                                   int(bool(add_ideal)), int(kind), int(invert), int(strategy), int(quirk),
+                                                   float(alpha), float(negative), mat.data_ptr(), state.data_ptr(),
+                                                   loss.data_ptr(), gq.data_ptr(), _ptr(grad), rt.stream_ptr()),
+                       "ltr_risk_listnet_fwdbwd")
+            ctx.grad = grad
+            ctx.mat = mat
+            return loss
+        _lib.check(lib.ltr_risk_listnet_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
+                                             int(bool(add_ideal)), tvar, mat.data_ptr(), rt.stream_ptr()),
+                   "ltr_risk_listnet_rows")
         loss, gq, _ = _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, need, False, group)
         grad = None
         if need:
