@@ -509,21 +509,34 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int cap = device_sm_count() * 8;
     bool marked_only = false;
-    if (kmax <= TPQ_K - 1 && p.n <= TPQ_N && p.n % 4 == 0 && p.flags &&
+    if (kmax <= TPQ_K - 1 && p.n % 4 == 0 && p.flags &&
         (reinterpret_cast<uintptr_t>(p.y_true) | reinterpret_cast<uintptr_t>(p.y_pred)) % 16 == 0) {
         // one thread per query (ndcg_stream.cuh), then the full sort for the queries it marked
         static bool attr_done = false;
         if (!attr_done) {
-            LTR_CUDA(cudaFuncSetAttribute(ndcg_tpq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
-            LTR_CUDA(cudaFuncSetAttribute(ndcg_tpq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM));
+#define LTR_TPQ_ATTR(KERNEL) \
+    LTR_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM))
+            LTR_TPQ_ATTR(ndcg_tpq_kernel<false>); LTR_TPQ_ATTR(ndcg_tpq_kernel<true>);
+            LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<false, 2>)); LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<true, 2>));
+            LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<false, 4>)); LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<true, 4>));
+#undef LTR_TPQ_ATTR
             attr_done = true;
         }
+        // warps per tile of 32 queries: long rows are split chunk-wise over the warps of a CTA
+        const int share = p.n <= TPQ_N ? 1 : (p.n <= 2 * TPQ_N ? 2 : 4);
         const int tiles = (p.B + 31) / 32;
-        int g = (tiles + TPQ_WARPS - 1) / TPQ_WARPS;
-        const int gcap = device_sm_count() * TPQ_CTAS;
+        int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
+        const int gcap = device_sm_count() * (share == 1 ? TPQ_CTAS : 2);
         g = g < gcap ? g : gcap;
-        const int rc = f64 ? launch_pdl(ndcg_tpq_kernel<true>, g, TPQ_THREADS, TPQ_SMEM, st, p)
-                           : launch_pdl(ndcg_tpq_kernel<false>, g, TPQ_THREADS, TPQ_SMEM, st, p);
+        int rc;
+#define LTR_TPQ(C) \
+    rc = f64 ? launch_pdl(ndcg_tpq_wide_kernel<true, C>, g, TPQ_THREADS, TPQ_SMEM, st, p) \
+             : launch_pdl(ndcg_tpq_wide_kernel<false, C>, g, TPQ_THREADS, TPQ_SMEM, st, p)
+        if (share == 1) {
+            rc = f64 ? launch_pdl(ndcg_tpq_kernel<true>, g, TPQ_THREADS, TPQ_SMEM, st, p)
+                     : launch_pdl(ndcg_tpq_kernel<false>, g, TPQ_THREADS, TPQ_SMEM, st, p);
+        } else if (share == 2) { LTR_TPQ(2); } else { LTR_TPQ(4); }
+#undef LTR_TPQ
         if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (one thread per query)");
         marked_only = true;
     } else if (kmax <= 31 && p.n <= 1024 && p.flags) {
