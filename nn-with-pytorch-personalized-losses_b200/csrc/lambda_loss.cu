@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[32];
     __shared__ int sh_m;
+    __shared__ int sh_lvl[5];                               // [0]: a label that is not an integer 0..4; [L]: #docs with label L
     const int n = p.n, len = p.len;
     float* K = reinterpret_cast<float*>(smem_raw);          // scores in rank order
     int* I = reinterpret_cast<int*>(K + len);               // permutation
@@ -185,8 +186,10 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
     const float ninf = __int_as_float(0xff800000);
     const int tid = threadIdx.x;
 
+    pdl_prologue();
     for (int r = tid; r < n; r += LAMBDA_THREADS) invD[r] = 1.0f / log2f(2.0f + (float)r);
     __syncthreads();
+
     for (int t = tid; t < n; t += LAMBDA_THREADS) dtab[t] = (t == 0) ? 0.f : fabsf(invD[t - 1] - invD[t]);   // lambdaL.py:101-104
     const float sig_scale = p.sigma * kLog2e;
     const float log_eps2 = log2f(p.eps);
@@ -198,29 +201,57 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
         const float* sp = p.y_pred + (size_t)b * n;
         const float* yp = p.y_true + (size_t)b * n;
         int cnt_valid = 0;
+        unsigned lvl_lo = 0, lvl_hi = 0;                       // counts of labels 1, 2 (16 bits each) and 3, 4
+        bool odd = false;
         for (int i = tid; i < n; i += LAMBDA_THREADS) {
             const float y = yp[i];
             const bool pad = (y == p.pad);
             K[i] = pad ? ninf : sp[i];
             cnt_valid += pad ? 0 : 1;
+            const int lv = (int)fminf(fmaxf(y, -1.f), 5.f);
+            odd = odd || (!pad && !((float)lv == y && lv >= 0 && lv <= 4));
+            if (!pad) {
+                lvl_lo += (lv == 1) ? 1u : ((lv == 2) ? 0x10000u : 0u);
+                lvl_hi += (lv == 3) ? 1u : ((lv == 4) ? 0x10000u : 0u);
+            }
         }
         if (tid == 0) sh_m = 0;
+        if (tid < 5) sh_lvl[tid] = 0;
         __syncthreads();
         cnt_valid = (int)warp_sum((float)cnt_valid);
-        if ((tid & 31) == 0) atomicAdd(&sh_m, cnt_valid);
+        lvl_lo = __reduce_add_sync(LTR_FULL_MASK, lvl_lo);
+        lvl_hi = __reduce_add_sync(LTR_FULL_MASK, lvl_hi);
+        odd = __any_sync(LTR_FULL_MASK, odd);
+        if ((tid & 31) == 0) {
+            atomicAdd(&sh_m, cnt_valid);
+            atomicAdd(&sh_lvl[1], (int)(lvl_lo & 0xffffu));
+            atomicAdd(&sh_lvl[2], (int)(lvl_lo >> 16));
+            atomicAdd(&sh_lvl[3], (int)(lvl_hi & 0xffffu));
+            atomicAdd(&sh_lvl[4], (int)(lvl_hi >> 16));
+            if (odd) atomicOr(&sh_lvl[0], 1);
+        }
         __syncthreads();
         const int m = sh_m;
         block_sort_desc(K, I, Y, n, len, TIES_STDSORT, m);
-        // labels: ideal order (values only) -> ideal DCG@k; rank order -> gains
-        for (int i = tid; i < len; i += LAMBDA_THREADS) {
-            float y = (i < n) ? yp[i] : ninf;
-            if (y == p.pad) y = ninf;
-            G[i] = y;
-        }
-        block_bitonic_desc(G, len);
         const int kk = (p.k > 0 && p.k < n) ? p.k : n;
+        const bool hist = !sh_lvl[0];
+        // labels 0..4: level L fills the ideal ranks [e_{L+1}, e_L), e_L = #docs with label >= L, so the label at ideal
+        // rank r is the number of levels with e_L > r; other labels: ideal order by a bitonic sort of the label values
+        const int e4 = sh_lvl[4], e3 = e4 + sh_lvl[3], e2 = e3 + sh_lvl[2], e1 = e2 + sh_lvl[1];
+        if (!hist) {
+            for (int i = tid; i < len; i += LAMBDA_THREADS) {
+                float y = (i < n) ? yp[i] : ninf;
+                if (y == p.pad) y = ninf;
+                G[i] = y;
+            }
+            block_bitonic_desc(G, len);
+        }
         float part = 0.f;
-        for (int r = tid; r < kk; r += LAMBDA_THREADS) part += (exp2f(fmaxf(G[r], 0.f)) - 1.0f) * invD[r];
+        for (int r = tid; r < kk; r += LAMBDA_THREADS) {            // ideal DCG@k (lambdaL.py:39)
+            const float gain = hist ? (float)((1 << ((e4 > r) + (e3 > r) + (e2 > r) + (e1 > r))) - 1)
+                                    : exp2f(fmaxf(G[r], 0.f)) - 1.0f;
+            part += gain * invD[r];
+        }
         __syncthreads();
         if ((tid & 31) == 0) red[tid >> 5] = 0.f;
         part = warp_sum(part);
@@ -332,8 +363,7 @@ template <int SCHEME>
 static int launch_lambda(const LambdaParams& p, size_t smem, int grid, cudaStream_t st) {
     if (smem > 48 * 1024)
         LTR_CUDA(cudaFuncSetAttribute(lambda_kernel<SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lambda_kernel<SCHEME><<<grid, LAMBDA_THREADS, smem, st>>>(p);
-    return 0;
+    return launch_pdl(lambda_kernel<SCHEME>, grid, LAMBDA_THREADS, smem, st, p);
 }
 
 }  // namespace ltr
