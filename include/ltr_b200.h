@@ -109,9 +109,11 @@ int ltr_sort_desc(const float* keys, int B, int n, int tie_rule, int* perm, floa
  *   y_true, y_pred : [Q, n]; ks : nk <= 32 HOST ints (k <= 0 or k > n: no truncation); out : [Q, nk]
  *   disc32 : n device floats, disc32[r] = (float)log2(2 + r) (the reference divides by np.log2(1 + i) rounded to fp32)
  *   gains 2^l - 1, sequential fp32 accumulation, 0/0 = NaN (the 'tensor' return type maps NaN to 0 in the caller).
- *   All k of a sweep are served by one read of the query.  flags: Q + 1 device ints of scratch or NULL; with it, sweeps
- *   whose largest k is <= 31 take the top-k path (one warp per query, no sort) and only queries with tied keys
- *   among their first k + 1 ranks are sorted in full.
+ *   All k of a sweep are served by one read of the query.  flags: Q + 1 device ints of scratch or NULL (no
+ *   initialisation needed; on return flags[1 + q] != 0 marks the queries that took the full sort).  With it, sweeps
+ *   whose largest k is <= 10 (n % 4 == 0, 16-byte aligned rows) take the one-thread-per-query path, sweeps up to k = 31
+ *   and n <= 1024 the warp-per-query top-k path; neither sorts, and only queries with tied keys among their first
+ *   k + 1 ranks (or a NaN score, or labels that are not small integers) are sorted in full with `tie_rule`.
  */
 int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
                   const float* disc32, float* out, int* flags, void* stream);
