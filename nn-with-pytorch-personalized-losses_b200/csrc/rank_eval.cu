@@ -526,13 +526,19 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         const int share = p.n <= TPQ_N ? 1 : (p.n <= 2 * TPQ_N ? 2 : 4);
         const int tiles = (p.B + 31) / 32;
         int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
-        const int gcap = device_sm_count() * (share == 1 ? TPQ_CTAS : 2);
+        // rows of one chunk: a batch that fits one resident wave of the quad-maxima kernel (16 warps per SM) takes it;
+        // larger batches take the score-tile kernel, whose whole-tile asynchronous copies keep more bytes in flight
+        const bool qmax = share == 1 && tiles <= device_sm_count() * QMX_CTAS * TPQ_WARPS;
+        const int gcap = device_sm_count() * (share == 1 ? (qmax ? QMX_CTAS : TPQ_CTAS) : 2);
         g = g < gcap ? g : gcap;
         int rc;
 #define LTR_TPQ(C) \
     rc = f64 ? launch_pdl(ndcg_tpq_wide_kernel<true, C>, g, TPQ_THREADS, TPQ_SMEM, st, p) \
              : launch_pdl(ndcg_tpq_wide_kernel<false, C>, g, TPQ_THREADS, TPQ_SMEM, st, p)
-        if (share == 1) {
+        if (qmax) {
+            rc = f64 ? launch_pdl(ndcg_qmax_kernel<true>, g, TPQ_THREADS, QMX_SMEM, st, p)
+                     : launch_pdl(ndcg_qmax_kernel<false>, g, TPQ_THREADS, QMX_SMEM, st, p);
+        } else if (share == 1) {
             rc = f64 ? launch_pdl(ndcg_tpq_kernel<true>, g, TPQ_THREADS, TPQ_SMEM, st, p)
                      : launch_pdl(ndcg_tpq_kernel<false>, g, TPQ_THREADS, TPQ_SMEM, st, p);
         } else if (share == 2) { LTR_TPQ(2); } else { LTR_TPQ(4); }
