@@ -161,3 +161,48 @@ def test_forward_only_and_errors():
     assert_loss_close(loss.cpu().numpy(), rloss)
     with pytest.raises(LtrError):
         approxNDCGLoss(torch.zeros(1, 100000, device="cuda"), torch.zeros(1, 100000, device="cuda"))
+
+
+# ---- batches of >= 16,384 slates take the one-warp-per-slate kernel (approx_ndcg_warp.cuh) ---------------------
+@pytest.mark.parametrize("n,min_len,kw", [
+    (128, 64, {}),
+    (128, 1, dict(pad_anywhere=True)),
+    (100, 30, {}),
+    (37, 1, {}),
+    (128, 64, dict(ties=True)),
+    (128, 64, dict(score_scale=25.0)),       # direct form for the slates whose range is too wide
+])
+def test_large_batch_kernel_matches_small_batch_kernel_and_oracle(n, min_len, kw):
+    """The same slates through the large-batch kernel (one call of 16,640 slates) and through the four-warps-per-slate
+    kernel (calls of 4,160 slates): per-slate gradients agree to a few ulp (they are scaled by 1/B, so the small
+    calls are rescaled), the batch loss is the mean; a slice is checked against the oracle itself."""
+    B, parts = 16640, 4
+    s, y = make_slates(B, n, seed=77, min_len=min_len, **kw)
+    if min_len == 1:
+        y[5] = -1.0                                       # a fully padded slate
+    loss, grad = _run_gpu(s, y, alpha=10.0)
+    step = B // parts
+    losses, grads = [], []
+    for i in range(parts):
+        l, g = _run_gpu(s[i * step:(i + 1) * step], y[i * step:(i + 1) * step], alpha=10.0)
+        losses.append(float(l))
+        grads.append(g / parts)
+    assert_loss_close(loss, np.float32(np.mean(losses)), rtol=2e-6)
+    ref = np.concatenate(grads)
+    assert np.all(np.isfinite(grad))
+    assert np.abs(grad - ref).max() <= 2e-5 * np.abs(ref).max()
+    # oracle on the first 256 slates (its gradient is scaled by 1/256 instead of 1/B)
+    _, rgrad = _run_oracle(s[:256], y[:256], alpha=10.0)
+    _, rgrad64 = _run_oracle(s[:256], y[:256], dtype=torch.float64, alpha=10.0)
+    assert_grad_close(grad[:256] * (B / 256.0), rgrad, ref64=rgrad64)
+
+
+def test_large_batch_kernel_is_bitwise_repeatable_and_flags_nan():
+    B, n = 16384, 128
+    s, y = make_slates(B, n, seed=78, min_len=64)
+    l1, g1 = _run_gpu(s, y, alpha=10.0)
+    l2, g2 = _run_gpu(s, y, alpha=10.0)
+    assert l1.tobytes() == l2.tobytes() and g1.tobytes() == g2.tobytes()
+    s[123, 7] = float("nan")
+    l3, _ = _run_gpu(s, y, alpha=10.0)
+    assert np.isnan(l3)

@@ -391,3 +391,59 @@ def test_validation_epilogue_matches_driver_block():
         mean, geo = validation_scores(y.cuda(), pred.cuda(), base.cuda(), k=k, alpha=5)
         assert abs(mean - float(np.mean(cols[0]))) < 1e-12
         assert abs(geo - ref_geo) <= 2e-6 * abs(ref_geo)
+
+
+# ---- NDCG@k sweep: every fast-path kernel against the oracle and against the full-sort path ---------------------
+@pytest.mark.parametrize("Q,n,ks,kw", [
+    (257, 128, (1, 5, 10), {}),                       # quad-maxima kernel (one resident wave)
+    (257, 128, (10,), dict(ties=True)),               # every query marked -> std::sort replay
+    (100, 64, (1, 3, 10), {}),                        # fewer than 11 quads with >= 11 docs
+    (100, 40, (5, 10), {}),                           # L = -inf: every doc is a candidate
+    (50, 8, (1, 5, 10), {}),                          # k > n clips to n
+    (33, 4, (1, 2), {}),
+    (64, 256, (1, 5, 10), {}),                        # two warps per tile, two chunks
+    (64, 1000, (1, 5, 10), {}),                       # four warps per tile, last chunk partial
+    (20, 2048, (10,), {}),
+    (64, 512, (1, 5, 10), dict(ties=True)),
+    (64, 128, (1, 5, 20), {}),                        # k > 10: warp-per-query tournament kernel
+])
+def test_ndcg_sweep_kernels_vs_oracle(Q, n, ks, kw):
+    from ltr_b200.utils.metrics import ndcg_sweep
+    from oracle import ltr_oracle as O
+    s, y = make_slates(Q, n, seed=1000 + n, **kw)
+    got = ndcg_sweep(y.cuda(), s.cuda(), ks=ks).cpu().numpy()
+    for j, k in enumerate(ks):
+        ref = O.torch_ndcg(y, s, k=k, return_type="tensor").numpy()
+        np.testing.assert_allclose(np.nan_to_num(got[:, j]), ref, rtol=2e-6, atol=1e-7, err_msg=f"k={k}")
+
+
+def test_ndcg_sweep_special_rows():
+    """NaN / inf scores, fractional and large labels, all-zero labels: such queries leave the fast path (marked) and
+    must still match the oracle; an exact score tie inside the top 10 next to distinct rows as well."""
+    from ltr_b200.utils.metrics import ndcg_sweep
+    from oracle import ltr_oracle as O
+    s, y = make_slates(96, 128, seed=4242)
+    s[1, 5] = float("inf")
+    s[2, 9] = float("-inf")
+    s[3, 17] = s[3].max()                               # exact tie at rank 0 / 1
+    y[4, 3] = 2.5
+    y[5, 11] = 7.0
+    y[6] = 0.0
+    y[7, 0] = 31.0
+    s[8, :] = 0.25                                      # all scores equal
+    got = ndcg_sweep(y.cuda(), s.cuda(), ks=(1, 5, 10)).cpu().numpy()
+    for j, k in enumerate((1, 5, 10)):
+        ref = O.torch_ndcg(y, s, k=k, return_type="tensor").numpy()
+        np.testing.assert_allclose(np.nan_to_num(got[:, j]), ref, rtol=2e-6, atol=1e-7, err_msg=f"k={k}")
+
+
+def test_ndcg_sweep_large_eval_set_matches_small_batches():
+    """More queries than one resident wave of the quad-maxima kernel (75,776): the score-tile kernel takes the whole
+    set; it must reproduce, bit for bit, what the quad-maxima kernel returns for the same queries in slices."""
+    from ltr_b200.utils.metrics import ndcg_sweep
+    Q, n = 90000, 128
+    s, y = make_slates(Q, n, seed=99)
+    sd, yd = s.cuda(), y.cuda()
+    whole = ndcg_sweep(yd, sd, ks=(1, 5, 10))
+    parts = torch.cat([ndcg_sweep(yd[i:i + 30000], sd[i:i + 30000], ks=(1, 5, 10)) for i in range(0, Q, 30000)])
+    assert torch.equal(torch.nan_to_num(whole), torch.nan_to_num(parts))
