@@ -13,8 +13,8 @@ N(0,1), alpha = 10), per GPU.  Slates are independent, so N GPUs each take their
   value        slates/s, inputs resident in HBM, CUDA events around K back-to-back launches of the
                C-ABI entry `ltr_approx_ndcg_fwdbwd`, max over ranks.
   e2e          same metric through the host-buffer C-ABI call (`ltr_approx_ndcg_fwdbwd_host`):
-               pinned host y_pred/y_true -> H2D -> kernel -> D2H of loss and gradient, all inside
-               the timed region.
+               pinned host y_pred/y_true -> (PCIe, read by the kernel itself) -> kernel -> (PCIe) loss and
+               gradient in pinned host memory, every step, all inside the timed region.
   roofline     SFU (MUFU) roofline of the pairwise kernel: algorithmic 2 SFU ops per ordered valid
                pair / measured kernel time, against the SFU peak measured on this GPU by
                a pure ex2.approx loop in the same run; `roofline_hbm` gives the HBM view.
@@ -341,7 +341,8 @@ def run_b200_arm(args, rank, local_rank, world):
                             if graph is not None else "direct launches"),
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "path": "ltr_approx_ndcg_fwdbwd_host (pinned host buffers, 3 streams in flight)"},
+                "steps": e2e_steps, "path": "ltr_approx_ndcg_fwdbwd_host: pinned host y_pred/y_true read by the kernel over PCIe, gradient and loss "
+                        "written back to pinned host memory by the kernel (no staging copies), 3 streams in flight"},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": {

@@ -515,6 +515,27 @@ LTR_API int ltr_approx_ndcg_fwdbwd_host(const float* h_y_pred, const float* h_y_
     float* d_loss = d_slate + b4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t bytes = (size_t)B * n * sizeof(float);
+#ifndef LTR_HOST_ZERO_COPY
+#define LTR_HOST_ZERO_COPY 1
+#endif
+    if (LTR_HOST_ZERO_COPY) {
+        // Pinned, device-mapped host buffers (cudaHostAlloc / torch pin_memory under unified addressing): the kernel
+        // reads the scores and labels and writes the gradient and the loss over PCIe itself -- one launch, no staging
+        // copies, the transfers of a step overlap its pair arithmetic slate by slate.  Buffers that are not mapped
+        // fall through to the staged path below.
+        void *ms = nullptr, *my = nullptr, *ml = nullptr, *mg = nullptr, *mv = nullptr;
+        bool mapped = cudaHostGetDevicePointer(&ms, const_cast<float*>(h_y_pred), 0) == cudaSuccess &&
+                      cudaHostGetDevicePointer(&my, const_cast<float*>(h_y_true), 0) == cudaSuccess &&
+                      cudaHostGetDevicePointer(&ml, h_loss, 0) == cudaSuccess;
+        if (mapped && h_grad) mapped = cudaHostGetDevicePointer(&mg, h_grad, 0) == cudaSuccess;
+        if (mapped && h_slate_ndcg) mapped = cudaHostGetDevicePointer(&mv, h_slate_ndcg, 0) == cudaSuccess;
+        if (mapped)
+            return ltr_approx_ndcg_fwdbwd(reinterpret_cast<const float*>(ms), reinterpret_cast<const float*>(my), B, n, alpha,
+                                          eps, pad_value, disc_prefix, disc_len,
+                                          mv ? reinterpret_cast<float*>(mv) : d_slate, reinterpret_cast<float*>(ml),
+                                          reinterpret_cast<float*>(mg), nullptr, 0, workspace, stream);
+        (void)cudaGetLastError();                          // not mapped: clear the sticky "invalid value"
+    }
     LTR_CUDA(cudaMemcpyAsync(d_pred, h_y_pred, bytes, cudaMemcpyHostToDevice, st));
     LTR_CUDA(cudaMemcpyAsync(d_true, h_y_true, bytes, cudaMemcpyHostToDevice, st));
     int rc = ltr_approx_ndcg_fwdbwd(d_pred, d_true, B, n, alpha, eps, pad_value, disc_prefix, disc_len, d_slate, d_loss,

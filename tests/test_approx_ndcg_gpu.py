@@ -206,3 +206,21 @@ def test_large_batch_kernel_is_bitwise_repeatable_and_flags_nan():
     s[123, 7] = float("nan")
     l3, _ = _run_gpu(s, y, alpha=10.0)
     assert np.isnan(l3)
+
+
+# ---- host-buffer entry (ltr_approx_ndcg_fwdbwd_host): pinned buffers are read / written by the kernel over PCIe,
+#      pageable ones take the staged copies; both must give what the device-resident call gives ---------------------
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_entry_matches_device_entry(pinned):
+    from ltr_b200.host import ApproxNDCGHost
+    B, n = 512, 128
+    s, y = make_slates(B, n, seed=31, min_len=40)
+    loss, grad = _run_gpu(s, y, alpha=10.0)
+    plan = ApproxNDCGHost(B, n, alpha=10.0, depth=2)
+    hs, hy = (s.pin_memory(), y.pin_memory()) if pinned else (s.clone(), y.clone())
+    for _ in range(3):                                    # slots are reused: results must not depend on the slot
+        slot, hloss, hgrad = plan.submit(hs, hy)
+        plan.wait(slot)
+        assert hloss.numpy().tobytes() == np.float32(loss).tobytes()
+        assert np.array_equal(hgrad.numpy(), grad)
+    assert np.array_equal(hs.numpy(), s.numpy()) and np.array_equal(hy.numpy(), y.numpy())     # inputs untouched
