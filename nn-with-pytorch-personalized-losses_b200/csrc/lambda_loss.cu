@@ -40,20 +40,46 @@ struct LambdaParams {
 // the larger label is the "hi" side, one evaluation gives the loss term and both gradient contributions.
 // Steps are split over the 4 warps; partial gradients meet in shared memory.
 struct LDoc {
-    float s, y, g, d;      // score, label (NaN: not a doc of the block), gain, 1 / log2(1 + rank)
+    float s, v, y, g, d;   // score (FACT: u = 2^(t - c)), v = 2^-(t - c) (FACT only), label (NaN: not a doc of the
+                           // block), gain, 1 / log2(1 + rank);  t = sigma log2(e) s
 };
 
-template <int SCHEME>
+// log2-probability of one pair from e = exp(-sigma (s_first - s_second)) and its derivative w.r.t. that difference
+// (lambdaL.py:51-55 without the final log-base factor, which the caller applies once per slate)
+__device__ __forceinline__ void pair_from_e(float e, float w, float log_eps2, float& lw, float& dl) {
+    const float q = 1.0f + e;
+    const float sig = rcp_approx(q);
+    float l2 = -lg2_approx(q);                                    // log2 sigmoid
+    bool open = l2 >= log_eps2;                                   // inner clamp(min=eps) inactive
+    l2 = fmaxf(l2, log_eps2);
+    lw = w * l2;                                                  // log2 of (.)^w
+    open = open && (lw >= log_eps2);                              // outer clamp inactive
+    lw = fmaxf(lw, log_eps2);
+    dl = open ? w * (e * sig) : 0.f;                              // w sigma (1 - sig); 1 - sig = e sig
+}
+
+// e = exp(-sigma (s_a - s_b)).  FACT: the slate's scaled score range fits the fp32 exponent budget, e is the product
+// of two per-doc factors (no MUFU.EX2, no subtraction, no NaN / range handling per pair); otherwise the direct form
+// with the reference's clamp (+-1e8, subsumed by the exponent cap) and NaN -> 0 (lambdaL.py:49-50).
+template <bool FACT>
+__device__ __forceinline__ float pair_e(const LDoc& a, const LDoc& b, float sig_scale) {
+    if (FACT) return a.v * b.s;
+    float delta = a.s - b.s;
+    delta = (delta != delta) ? 0.f : delta;
+    return ex2_approx(fminf(-sig_scale * delta, 126.0f));
+}
+
+template <int SCHEME, bool FACT>
 __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b, int ib, float h, const float* dtab,
-                                            float mu, float sig_scale, float log_eps2, float out_scale, float& loss,
-                                            float& cnt, float& ga, float& gb) {
+                                            float mu, float sig_scale, float log_eps2, float& loss, float& cnt,
+                                            float& ga, float& gb) {
     // docs outside the block carry y = NaN: every ordered comparison with them is false
     if (SCHEME == SCHEME_NDCG1) {
         if (!(a.y == a.y) || !(b.y == b.y)) return;
         // no label condition: both ordered pairs are in the mask, weight G_i / D_i of the FIRST doc (lambdaL.py:96-97)
         float l1, d1, l2, d2;
-        pair_logprob(a.s - b.s, a.g * a.d, sig_scale, log_eps2, out_scale, l1, d1);
-        pair_logprob(b.s - a.s, b.g * b.d, sig_scale, log_eps2, out_scale, l2, d2);
+        pair_from_e(pair_e<FACT>(a, b, sig_scale), a.g * a.d, log_eps2, l1, d1);
+        pair_from_e(pair_e<FACT>(b, a, sig_scale), b.g * b.d, log_eps2, l2, d2);
         loss = fmaf(h, l1 + l2, loss);
         cnt = fmaf(h, 2.0f, cnt);
         const float dd = h * (d2 - d1);
@@ -64,7 +90,7 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b
     // branch-free: every slot is evaluated and masked (equal labels and non-docs get weight 0), which costs ~20 %
     // more MUFU work than skipping them but removes a divergent branch + reconvergence per pair
     const bool a_hi = a.y > b.y;
-    const float hv = (a_hi || (a.y < b.y)) ? h : 0.f;
+    const bool differ = a_hi || (a.y < b.y);
     float w;
     if (SCHEME == SCHEME_NONE) w = 1.0f;
     else if (SCHEME == SCHEME_GTDIFF) w = fabsf(fmaxf(a.y, 0.f) - fmaxf(b.y, 0.f));
@@ -78,22 +104,24 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b
         else if (SCHEME == SCHEME_LAMBDARANK) w = fabsf(a.d - b.d) * dg;
         else w = dg * fmaf(mu, dtab[gap], fabsf(a.d - b.d));
     }
-    const float d0 = a.s - b.s;
-    float l, dl;
-    pair_logprob(a_hi ? d0 : -d0, (hv != 0.f) ? w : 0.f, sig_scale, log_eps2, out_scale, l, dl);
-    loss = fmaf(hv, l, loss);
-    cnt += hv;
-    dl *= a_hi ? -hv : hv;                    // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
+    // the better-labelled doc is the first one of the pair
+    const float e = FACT ? (a_hi ? a.v * b.s : b.v * a.s) : (a_hi ? pair_e<false>(a, b, sig_scale) : pair_e<false>(b, a, sig_scale));
+    float lw, dl;
+    pair_from_e(e, differ ? w : 0.f, log_eps2, lw, dl);           // weight 0: lw = 0, dl = 0
+    loss = fmaf(h, lw, loss);
+    cnt += differ ? h : 0.f;
+    dl *= a_hi ? -h : h;                      // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
     ga += dl;
     gb -= dl;
 }
 
 // K, Y, G, invD: the slate in rank order (Y = -inf beyond the block); gpart: [4][2][256] floats of shared memory.
 // On exit gpart holds the per-warp row / column partial gradients of positions 0 .. lim-1 (after a barrier).
-template <int SCHEME, int R>
-__device__ __forceinline__ void lambda_sym_slate(const float* K, const float* Y, const float* G, const float* invD,
-                                                 const float* dtab, int lim, int b, float mu, float sig_scale,
-                                                 float log_eps2, float out_scale, float* gpart, float& loss, float& cnt) {
+// FACT: K holds u = 2^(t - c) and V holds 2^-(t - c) of the block's docs; otherwise K holds the scores (V unused).
+template <int SCHEME, int R, bool FACT>
+__device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V, const float* Y, const float* G,
+                                                 const float* invD, const float* dtab, int lim, int b, float mu,
+                                                 float sig_scale, float log_eps2, float* gpart, float& loss, float& cnt) {
     const float ninf = __int_as_float(0x7fc00000);           // (a quiet NaN marks "not a doc of the block")
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = (lim + R - 1) / R;
@@ -114,6 +142,8 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* Y,
         const bool vi = active && i < lim, vj = active && j < lim;
         row[r].s = vi ? K[i] : 0.f; row[r].y = vi ? Y[i] : ninf; row[r].g = vi ? G[i] : 0.f; row[r].d = vi ? invD[i] : 0.f;
         col[r].s = vj ? K[j] : 0.f; col[r].y = vj ? Y[j] : ninf; col[r].g = vj ? G[j] : 0.f; col[r].d = vj ? invD[j] : 0.f;
+        row[r].v = (FACT && vi) ? V[i] : 0.f;
+        col[r].v = (FACT && vj) ? V[j] : 0.f;
         g_r[r] = 0.f;
         g_c[r] = 0.f;
     }
@@ -122,14 +152,14 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* Y,
         for (int r = 0; r < R; ++r) {
             if (SCHEME == SCHEME_NDCG1 && row[r].y == row[r].y) {
                 float l, dl;
-                pair_logprob(0.f, row[r].g * row[r].d, sig_scale, log_eps2, out_scale, l, dl);
+                pair_from_e(1.0f, row[r].g * row[r].d, log_eps2, l, dl);   // the diagonal: delta = 0
                 loss += l;
                 cnt += 1.0f;
             }
 #pragma unroll
             for (int c = r + 1; c < R; ++c)
-                lambda_pair<SCHEME>(row[r], lane * R + r, row[c], lane * R + c, 1.0f, dtab, mu, sig_scale, log_eps2,
-                                    out_scale, loss, cnt, g_r[r], g_r[c]);
+                lambda_pair<SCHEME, FACT>(row[r], lane * R + r, row[c], lane * R + c, 1.0f, dtab, mu, sig_scale, log_eps2,
+                                          loss, cnt, g_r[r], g_r[c]);
         }
     }
 #pragma unroll 1
@@ -142,13 +172,14 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* Y,
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int c = 0; c < R; ++c)
-                lambda_pair<SCHEME>(row[r], lane * R + r, col[c], j0 + c, h, dtab, mu, sig_scale, log_eps2, out_scale, loss,
-                                    cnt, g_r[r], g_c[c]);
+                lambda_pair<SCHEME, FACT>(row[r], lane * R + r, col[c], j0 + c, h, dtab, mu, sig_scale, log_eps2, loss, cnt,
+                                          g_r[r], g_c[c]);
         }
         if (D + 1 < d_hi) {
 #pragma unroll
             for (int c = 0; c < R; ++c) {
                 col[c].s = __shfl_sync(LTR_FULL_MASK, col[c].s, src);
+                if (FACT) col[c].v = __shfl_sync(LTR_FULL_MASK, col[c].v, src);
                 col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
                 col[c].g = __shfl_sync(LTR_FULL_MASK, col[c].g, src);
                 col[c].d = __shfl_sync(LTR_FULL_MASK, col[c].d, src);
@@ -169,6 +200,124 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* Y,
     __syncthreads();
 }
 
+// Blocks of 65..256 docs with 4 docs per lane (80-odd registers, one small pair tile that stays in the instruction
+// cache): the rank positions are split into group A = [0, 128) and group B = [128, lim).  Three circulant phases run
+// the SAME tile code:  A x A and B x B are symmetric (steps 1..T/2 of a ring of T = ceil(group/4) lanes + the
+// in-block triangle);  A x B is a full ring of 32 lanes, rows from A, columns from B (blocks beyond B are non-docs).
+// The steps of every phase are split over the 4 warps; a lane's row accumulators stay in registers across phases.
+template <int SCHEME, bool FACT>
+__device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V, const float* Y, const float* G,
+                                                  const float* invD, const float* dtab, int lim, int b, float mu,
+                                                  float sig_scale, float log_eps2, float* gpart, float& loss, float& cnt) {
+    constexpr int R = 4;
+    const float qnan = __int_as_float(0x7fc00000);            // (a quiet NaN marks "not a doc of the block")
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int role = (warp + b) & 3;
+    const int nA = lim < 128 ? lim : 128;
+    const int TA = (nA + R - 1) / R, TB = (lim - nA + R - 1) / R;
+    auto load_doc = [&](LDoc& d, int i) {
+        const bool ok = i < lim;
+        d.s = ok ? K[i] : 0.f;
+        d.v = (FACT && ok) ? V[i] : 0.f;
+        d.y = ok ? Y[i] : qnan;
+        d.g = ok ? G[i] : 0.f;
+        d.d = ok ? invD[i] : 0.f;
+    };
+    // this warp's column partials are accumulated over the phases: start from zero
+    float* colpart = gpart + (warp * 2 + 1) * 256;
+    float* rowpart = gpart + (warp * 2 + 0) * 256;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) colpart[lane + 32 * k] = 0.f;
+    __syncwarp();
+    LDoc row[R], col[R];
+    float g_r[R], g_c[R];
+    // phases in the order A x A, A x B, B x B: the row group changes once
+#pragma unroll 1
+    for (int phase = 0; phase < 3; ++phase) {
+        if (phase > 0 && TB == 0) break;
+        const bool cross = phase == 1;
+        const int T = cross ? 32 : (phase == 0 ? TA : TB);      // ring size
+        const int rbase = phase == 2 ? 128 : 0;                 // first rank position of the row group
+        const int cbase = phase == 0 ? 0 : 128;                 //                       of the column group
+        const int TR = phase == 2 ? TB : TA;                    // lanes that own a row block
+        const int S = T >> 1;
+        // symmetric: steps 1 .. S; cross: steps 0 .. 31
+        const int d_lo = cross ? role * 8 : 1 + ((role * S) >> 2);
+        const int d_hi = cross ? role * 8 + 8 : 1 + (((role + 1) * S) >> 2);
+        const bool active = lane < T;
+        const int src = active ? ((lane + 1 == T) ? 0 : lane + 1) : lane;
+        int cb = lane + d_lo;
+        if (cb >= T) cb -= T;
+        if (!active) cb = 0;
+        if (phase != 1) {                          // (A x B keeps the rows and row accumulators of A x A)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                load_doc(row[r], lane < TR ? rbase + lane * R + r : lim);
+                g_r[r] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            load_doc(col[r], active ? cbase + cb * R + r : lim);
+            g_c[r] = 0.f;
+        }
+        if (!cross && role == 0) {                // pairs inside the lane's own block (+ the diagonal of ndcgLoss1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (SCHEME == SCHEME_NDCG1 && row[r].y == row[r].y) {
+                    float l, dl;
+                    pair_from_e(1.0f, row[r].g * row[r].d, log_eps2, l, dl);   // the diagonal: delta = 0
+                    loss += l;
+                    cnt += 1.0f;
+                }
+#pragma unroll
+                for (int c = r + 1; c < R; ++c)
+                    lambda_pair<SCHEME, FACT>(row[r], rbase + lane * R + r, row[c], rbase + lane * R + c, 1.0f, dtab, mu,
+                                              sig_scale, log_eps2, loss, cnt, g_r[r], g_r[c]);
+            }
+        }
+#pragma unroll 1
+        for (int D = d_lo; D < d_hi; ++D) {
+            const float h = (!cross && 2 * D == T) ? 0.5f : 1.0f;
+            int cblk = lane + D;                   // block visiting this lane at step D
+            if (cblk >= T) cblk -= T;
+            const int j0 = cbase + cblk * R;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int c = 0; c < R; ++c)
+                    lambda_pair<SCHEME, FACT>(row[r], rbase + lane * R + r, col[c], j0 + c, h, dtab, mu, sig_scale, log_eps2,
+                                              loss, cnt, g_r[r], g_c[c]);
+            }
+            if (D + 1 < d_hi) {
+#pragma unroll
+                for (int c = 0; c < R; ++c) {
+                    col[c].s = __shfl_sync(LTR_FULL_MASK, col[c].s, src);
+                    if (FACT) col[c].v = __shfl_sync(LTR_FULL_MASK, col[c].v, src);
+                    col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
+                    col[c].g = __shfl_sync(LTR_FULL_MASK, col[c].g, src);
+                    col[c].d = __shfl_sync(LTR_FULL_MASK, col[c].d, src);
+                    g_c[c] = __shfl_sync(LTR_FULL_MASK, g_c[c], src);
+                }
+            }
+        }
+        // column partials of the block whose accumulators ended up in this lane (same warp: the phases are ordered)
+        if (active && d_hi > d_lo) {
+            int cblk = lane + d_hi - 1;
+            if (cblk >= T) cblk -= T;
+#pragma unroll
+            for (int r = 0; r < R; ++r) colpart[cbase + cblk * R + r] += g_c[r];
+        }
+        __syncwarp();
+        // row partials: group A after A x B (or after A x A when there is no group B), group B after B x B
+        if ((phase == 1 || phase == 2 || TB == 0) && lane < TR) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) rowpart[rbase + lane * R + r] = g_r[r];
+        }
+    }
+    __syncthreads();
+}
+
 template <int SCHEME>
 __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -183,6 +332,8 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
     float* invD = G + len;                                  // 1 / log2(1 + r), r = 1..n
     float* dtab = invD + len;                               // |1/D_t - 1/D_{t+1}| by rank gap t (0 on the diagonal)
     float* gpart = dtab + len;                              // [4 warps][row / column][256] partial gradients (symmetric path)
+    float* U = gpart + 8 * 256;                             // factorised pair exponent: 2^(t - c) of the block's docs
+    float* V = U + 256;                                     //                           2^-(t - c)
     const float ninf = __int_as_float(0xff800000);
     const int tid = threadIdx.x;
 
@@ -272,9 +423,30 @@ __global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaPara
         const int lim = kk < m ? kk : m;
         float loss_part = 0.f, cnt_part = 0.f;
         if (lim <= 256) {
-            if (lim > 128) lambda_sym_slate<SCHEME, 8>(K, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, out_scale, gpart, loss_part, cnt_part);
-            else if (lim > 64) lambda_sym_slate<SCHEME, 4>(K, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, out_scale, gpart, loss_part, cnt_part);
-            else lambda_sym_slate<SCHEME, 2>(K, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, out_scale, gpart, loss_part, cnt_part);
+            // e = exp(-sigma (s_i - s_j)) = 2^-(t_i - c) 2^(t_j - c), t = sigma log2(e) s, while the block's scaled score
+            // range keeps both factors inside fp32 (K is sorted, NaN first: a NaN / inf range takes the direct form)
+            const float range = (lim > 0) ? (K[0] - K[lim - 1]) * sig_scale : 0.f;
+            const bool fact = (lim > 0) && fabsf(range) < 126.0f;
+            if (fact) {
+                const float mid = 0.5f * K[0] + 0.5f * K[lim - 1];
+                for (int i = tid; i < lim; i += LAMBDA_THREADS) {
+                    const float t = (K[i] - mid) * sig_scale;
+                    U[i] = ex2_approx(t);
+                    V[i] = ex2_approx(-t);
+                }
+                __syncthreads();
+            }
+#define LTR_SYM(R)                                                                                                      \
+    if (fact) lambda_sym_slate<SCHEME, R, true>(U, V, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part); \
+    else lambda_sym_slate<SCHEME, R, false>(K, nullptr, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part)
+            if (lim > 64) {
+                if (fact) lambda_sym_slate4<SCHEME, true>(U, V, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part);
+                else lambda_sym_slate4<SCHEME, false>(K, nullptr, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part);
+            } else {
+                LTR_SYM(2);
+            }
+#undef LTR_SYM
+            loss_part *= out_scale;                               // log base: 1 (binary) or ln 2 (natural)
             if (p.grad) {
                 for (int i = tid; i < n; i += LAMBDA_THREADS) {
                     float g = 0.f;
@@ -383,7 +555,7 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
     while (p.len < n) p.len <<= 1;
     p.eps = eps; p.pad = pad_value; p.sigma = sigma; p.mu = mu; p.natural_log = natural_log;
     p.slate_sum = slate_sum; p.slate_cnt = slate_count; p.grad = grad;
-    const size_t smem = ((size_t)p.len * 6 + 8 * 256) * sizeof(float);
+    const size_t smem = ((size_t)p.len * 6 + 10 * 256) * sizeof(float);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int cap = device_sm_count() * 8;
     const int grid = B < cap ? B : cap;
