@@ -318,8 +318,11 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
     __syncthreads();
 }
 
+#ifndef LAMBDA_MIN_CTAS
+#define LAMBDA_MIN_CTAS 4       // resident CTAs per SM the register allocation is tuned for
+#endif
 template <int SCHEME>
-__global__ void __launch_bounds__(LAMBDA_THREADS) lambda_kernel(const LambdaParams p) {
+__global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel(const LambdaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[32];
     __shared__ int sh_m;
