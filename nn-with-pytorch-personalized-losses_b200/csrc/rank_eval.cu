@@ -125,7 +125,9 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
 }
 
 // Without flags: every query.  With flags (a top-k fast path ran in front): only the queries q it marked with
-// flags[1 + q] != 0; a CTA looks at 32 flags at a time, so a batch without marked queries costs one read per CTA.
+// flags[1 + q] != 0; a CTA looks at NDCG_MARK_CHUNK flags at a time (small chunks spread a heavily marked batch over
+// every CTA; a batch without marked queries costs a few reads per CTA).
+constexpr int NDCG_MARK_CHUNK = 8;
 template <bool F64>
 __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,10 +138,10 @@ __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) 
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) ndcg_sorted_query<F64>(p, sm, b);
         return;
     }
-    for (int base = (int)blockIdx.x * 32; base < p.B; base += (int)gridDim.x * 32) {
+    for (int base = (int)blockIdx.x * NDCG_MARK_CHUNK; base < p.B; base += (int)gridDim.x * NDCG_MARK_CHUNK) {
         if (threadIdx.x < 32) {
             const int q = base + (int)threadIdx.x;
-            const unsigned m = __ballot_sync(LTR_FULL_MASK, q < p.B && p.flags[1 + q] != 0);
+            const unsigned m = __ballot_sync(LTR_FULL_MASK, (int)threadIdx.x < NDCG_MARK_CHUNK && q < p.B && p.flags[1 + q] != 0);
             if (threadIdx.x == 0) marked = m;
         }
         __syncthreads();
@@ -566,7 +568,7 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     }
     int gs = rank_grid(p.B);
     if (marked_only) {
-        const int chunks = (p.B + 31) / 32;
+        const int chunks = (p.B + NDCG_MARK_CHUNK - 1) / NDCG_MARK_CHUNK;
         gs = chunks < cap ? chunks : cap;
     }
     if (f64) {

@@ -59,6 +59,36 @@ __device__ __forceinline__ void block_bitonic_pairs(float* K, int* I, int len) {
     __syncthreads();
 }
 
+// The same network on ONE 64-bit word per entry: (order-preserving key << 32) | tie-break, sorted descending as an
+// unsigned integer -- one compare and two 64-bit shared-memory accesses per side instead of the two-array version's
+// four loads, NaN-aware float compares and four stores.  key: NaN = 0xffffffff (first), -0 = +0, sentinel entries
+// (index >= n) = 0 (last, below -inf); tie-break: ~index (ascending index first) or index (descending).
+__device__ __forceinline__ unsigned sort_key_bits(float f) {
+    if (f != f) return 0xffffffffu;
+    const unsigned b = __float_as_uint(f + 0.0f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ void block_bitonic_packed(unsigned long long* P, int len) {
+#pragma unroll 1
+    for (int k = 2; k <= len; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const unsigned long long a = P[lo], c = P[hi];
+                const bool up = ((lo & k) == 0);                 // this run ends up in descending order
+                if (up ? (c > a) : (c < a)) {
+                    P[lo] = c;
+                    P[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // ---- libstdc++ std::sort, replayed by ONE thread on (K, I) in their original order ---------------------
 struct StdSortEmu {
     float* K;
@@ -203,6 +233,47 @@ struct StdSortEmu {
 __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int n, int len, int tie_rule,
                                                 int tie_limit = 1 << 30) {
     const float ninf = __int_as_float(0xff800000);
+    if (reinterpret_cast<void*>(I) == reinterpret_cast<void*>(K + len) && (reinterpret_cast<uintptr_t>(K) & 7) == 0 &&
+        len <= 8 * (int)blockDim.x) {
+        // K and I are adjacent: sort ONE packed 64-bit word per entry, in place over both arrays.  Every thread first
+        // holds its (at most 8) entries in registers, so the in-place repacking cannot overwrite an unread entry.
+        unsigned long long* P = reinterpret_cast<unsigned long long*>(K);
+        const bool rev = tie_rule == TIES_REVERSED;
+        float mine[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            mine[e] = (i < n) ? K[i] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            if (i < n) K0[i] = mine[e];
+            if (i < len) {
+                const unsigned kb = (i < n) ? sort_key_bits(mine[e]) : 0u;
+                P[i] = ((unsigned long long)kb << 32) | (unsigned)(rev ? i : ~i);
+            }
+        }
+        block_bitonic_packed(P, len);                                 // (starts and ends with a barrier)
+        int idx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            const unsigned low = (i < len) ? (unsigned)P[i] : 0u;
+            idx[e] = (int)(rev ? low : ~low);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = threadIdx.x + e * blockDim.x;
+            if (i < len) {
+                K[i] = (idx[e] < n) ? K0[idx[e]] : ninf;              // sentinels: -inf, index >= n, i.e. last
+                I[i] = idx[e];
+            }
+        }
+        __syncthreads();
+    } else {
     for (int i = threadIdx.x; i < len; i += blockDim.x) {
         if (i < n) K0[i] = K[i];
         else K[i] = ninf;
@@ -215,6 +286,7 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
         block_bitonic_pairs<true>(K, I, len);
     } else {
         block_bitonic_pairs<false>(K, I, len);
+    }
     }
     if (tie_rule != TIES_STDSORT || n <= 16) return;
     int tie = 0;
