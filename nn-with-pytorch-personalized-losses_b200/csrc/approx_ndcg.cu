@@ -13,6 +13,7 @@
 // The B x n x n tensors of the reference never exist.
 #include "approx_ndcg_sym.cuh"
 #include "approx_ndcg_warp.cuh"
+#include "approx_ndcg_cluster.cuh"
 #include "ltr_common.cuh"
 #include "ltr_host.h"
 
@@ -422,6 +423,23 @@ static int launch_persistent(Kernel kernel, int threads, int slates_per_cta, int
 #endif
 }
 
+// long slates: one cluster of CL_CTAS CTAs per slate (approx_ndcg_cluster.cuh)
+static int launch_approx_cluster(const ApproxParams& p, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.B * CL_CTAS);
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL_CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, approx_ndcg_cluster_kernel<true>, p);
+}
+
 static int launch_approx_sym(const ApproxParams& p, cudaStream_t st) {
     static int occ_warp = 0, occ_sym = 0;
     if (p.B >= WPS_MIN_BATCH)
@@ -483,6 +501,12 @@ LTR_API int ltr_approx_ndcg_fwdbwd(const float* y_pred, const float* y_true, int
     int rc;
     if (n <= SYM_N && !p.clamp && p.disc_prefix != nullptr && p.disc_len > SYM_N && B <= (1 << 22))
         rc = launch_approx_sym(p, st);                                 // symmetric pair schedule, 4 warps per slate
+#ifndef APPROX_CLUSTER
+#define APPROX_CLUSTER 1
+#endif
+    else if (APPROX_CLUSTER && n > SYM_N && n <= CL_MAXN && !p.clamp && alpha > 0.f && p.disc_prefix != nullptr &&
+             p.disc_len > n && (long long)B * CL_CTAS <= 0x7fffffffLL)
+        rc = launch_approx_cluster(p, st);                             // one cluster of 8 CTAs per slate
     else if (n > 256 && scratch != nullptr && scratch_bytes >= ltr_approx_ndcg_scratch_bytes(B, n) &&
              B < 8 * device_sm_count())
         rc = launch_approx_split(p, st);                               // few long slates: several CTAs per slate

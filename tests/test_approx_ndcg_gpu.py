@@ -224,3 +224,35 @@ def test_host_buffer_entry_matches_device_entry(pinned):
         assert hloss.numpy().tobytes() == np.float32(loss).tobytes()
         assert np.array_equal(hgrad.numpy(), grad)
     assert np.array_equal(hs.numpy(), s.numpy()) and np.array_equal(hy.numpy(), y.numpy())     # inputs untouched
+
+
+# ---- 128 < n <= 1024: one cluster of 8 CTAs per slate (approx_ndcg_cluster.cuh) -------------------------------
+@pytest.mark.parametrize("B,n,min_len,alpha,kw", [
+    (5, 129, 129, 10.0, {}),                              # one full group + one doc
+    (7, 132, 1, 10.0, dict(pad_anywhere=True)),
+    (9, 200, 100, 10.0, {}),
+    (4, 256, 256, 1.0, {}),
+    (6, 516, 300, 10.0, dict(pad_anywhere=True)),
+    (3, 1000, 900, 10.0, {}),
+    (3, 1024, 1024, 10.0, {}),                            # 8 full groups
+    (5, 640, 320, 10.0, dict(ties=True)),
+    (4, 512, 256, 10.0, dict(score_scale=25.0)),          # direct form
+    (300, 260, 130, 5.0, {}),                             # more clusters than fit the GPU at once
+])
+def test_cluster_kernel_vs_oracle(B, n, min_len, alpha, kw):
+    s, y = make_slates(B, n, seed=5000 + n, min_len=min_len, **kw)
+    if B >= 5:
+        y[1] = -1.0                                       # a fully padded slate
+        y[2, 3:] = -1.0                                   # three docs
+        y[3] = torch.where(y[3] >= 0, y[3] * 1.5, y[3])  # fractional labels: ideal ranks by counting
+    _check(s, y, alpha=alpha)
+
+
+def test_cluster_kernel_is_bitwise_repeatable_and_propagates_nan():
+    s, y = make_slates(40, 1024, seed=6001, min_len=512)
+    l1, g1 = _run_gpu(s, y, alpha=10.0)
+    l2, g2 = _run_gpu(s, y, alpha=10.0)
+    assert l1.tobytes() == l2.tobytes() and g1.tobytes() == g2.tobytes()
+    s[7, 11] = float("nan")
+    l3, _ = _run_gpu(s, y, alpha=10.0)
+    assert np.isnan(l3)
