@@ -428,8 +428,14 @@ static int launch_approx_cluster(const ApproxParams& p, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.B * CL_CTAS);
     cfg.blockDim = dim3(CL_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = sizeof(ClShared);
     cfg.stream = st;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(ClShared)));
+        attr_done = true;
+    }
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL_CTAS;

@@ -167,7 +167,7 @@ def bench_georisk(iters=100, B=8192, n=128, S=2):
 
 
 def bench_approx_1024(iters=50, B=64, n=1024):
-    """BASELINE configs[4] loss: approxNDCG on 1024-doc slates (general kernel, one CTA per slate)."""
+    """BASELINE configs[4] loss: approxNDCG on 1024-doc slates (one thread-block cluster per slate)."""
     from ltr_b200 import _lib, _runtime as rt
     lib = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -193,7 +193,7 @@ def bench_approx_1024(iters=50, B=64, n=1024):
             "config": {"workload": f"{B} slates x {n} docs, valid len U{{512..1024}}, alpha=10"},
             "roofline": {"bound": "sfu", "achieved": 2.0 * pairs / sec / 1e12, "unit": "TSFU-op/s",
                          "algorithmic": f"2 SFU ops per ordered valid pair, {pairs} pairs per launch",
-                         "kernel": "approx_ndcg_kernel<128, 1> + <128, 2> (rows of a slate split over 8 CTAs)"}}
+                         "kernel": "approx_ndcg_cluster_kernel (one cluster of 8 CTAs per slate, partial sums over distributed shared memory)"}}
 
 
 def bench_approx_large(iters=30, B=65536, n=128):
