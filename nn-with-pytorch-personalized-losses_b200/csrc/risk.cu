@@ -188,8 +188,7 @@ __device__ __forceinline__ double rf_block_max(double v, double* red) {
 
 // phase 1 (local): state1 = {max(mat), sum_q mat[q,0], sum_q mat[q,C-1], sum of all entries, Q,
 //                            t-risk: sum_q d_q, 0...} where d_q = mat[q,1] - mat[q,0] needs no max at all.
-__global__ void __launch_bounds__(RISKF_THREADS) risk_stats1_kernel(const RiskFinalParams p) {
-    pdl_prologue();
+__device__ __forceinline__ void risk_stats1_body(const RiskFinalParams& p) {
     __shared__ double red[32];
     double mx = -1.0e300, s0 = 0.0, sl = 0.0, sa = 0.0;
     for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
@@ -256,8 +255,7 @@ __device__ __forceinline__ ZCol make_zcol(const RiskFinalParams& p, const double
 
 // phase 2 (local, needs global state1): per used column {sum z c, sum A T, sum A e, sum c / sqrt(e), sum A}, count of
 // entries equal to the global max;  t-risk: {sum d', sum d'^2} with d' = d (1 + alpha [d < 0]).
-__global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskFinalParams p) {
-    pdl_prologue();
+__device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p) {
     __shared__ double red[32];
     const double* g1 = p.state1;
     double a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -301,8 +299,7 @@ __global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskFi
 __device__ __forceinline__ double std_normal_cdf(double x) { return 0.5 * erfc(-x * 0.7071067811865476); }
 
 // phase 3 (local, needs global state1 and state2): loss value and gq[q] = d loss / d mat[q, 0].
-__global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskFinalParams p) {
-    pdl_prologue();
+__device__ __forceinline__ void risk_final_body(const RiskFinalParams& p) {
     const double* g1 = p.state1;
     const double* g2 = p.state2;
     const double f = (double)p.negative;
@@ -393,6 +390,31 @@ __global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskFin
     }
 }
 
+__global__ void __launch_bounds__(RISKF_THREADS) risk_stats1_kernel(const RiskFinalParams p) {
+    pdl_prologue();
+    risk_stats1_body(p);
+}
+__global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskFinalParams p) {
+    pdl_prologue();
+    risk_stats2_body(p);
+}
+__global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskFinalParams p) {
+    pdl_prologue();
+    risk_final_body(p);
+}
+// one GPU, no exchange between the phases: the single CTA runs them back to back (the state blocks written by
+// thread 0 of one phase are read by every thread of the next: fence + barrier in between)
+__global__ void __launch_bounds__(RISKF_THREADS) risk_phases_fused_kernel(const RiskFinalParams p) {
+    pdl_prologue();
+    risk_stats1_body(p);
+    __threadfence_block();
+    __syncthreads();
+    risk_stats2_body(p);
+    __threadfence_block();
+    __syncthreads();
+    risk_final_body(p);
+}
+
 static int risk_grid(int B) {
     long long g = ((long long)B + STREAM_WARPS - 1) / STREAM_WARPS;
     const long long cap = (long long)device_sm_count() * 8;
@@ -458,8 +480,8 @@ LTR_API int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, 
     return rc ? set_cuda_error(rc, "ltr_risk_phase") : 0;
 }
 
-// Single-GPU fused call: rows -> phase 1 -> phase 2 -> phase 3 -> backward rows, five dependent launches issued from
-// one host call (each starts its ramp-up under the previous one's tail).  Query-sharded callers use the separate
+// Single-GPU fused call: rows -> the three risk phases in one single-CTA kernel -> backward rows: three dependent
+// launches issued from one host call (each starts its ramp-up under the previous one's tail).  Query-sharded callers use the separate
 // entry points above and all-reduce the two state blocks between the phases.
 LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
                                     int transformation, int add_ideal, int kind, int invert, int return_strategy,
@@ -470,9 +492,14 @@ LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, co
     const int t_variant = (kind == 2) ? 1 : 0;
     const int C = 1 + S + (add_ideal ? 1 : 0);
     int rc = ltr_risk_listnet_rows(y_pred, y_true, y_baselines, B, n, S, transformation, add_ideal, t_variant, mat, stream);
-    for (int phase = 1; phase <= 3 && !rc; ++phase)
-        rc = ltr_risk_phase(phase, mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state,
-                            state + 16, loss, gq, nullptr, stream);
+    if (!rc) {
+        if (kind < 0 || kind > 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad kind");
+        if (kind == 2 && C < 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: t-risk needs the model and a baseline column");
+        RiskFinalParams fp{mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state, state + 16,
+                           loss, gq, nullptr};
+        rc = launch_pdl(risk_phases_fused_kernel, 1, RISKF_THREADS, 0, reinterpret_cast<cudaStream_t>(stream), fp);
+        if (rc) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd");
+    }
     if (!rc && grad) rc = ltr_risk_listnet_rows_bwd(y_pred, y_true, B, n, transformation, t_variant, gq, grad, stream);
     return rc;
 }
