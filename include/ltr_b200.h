@@ -220,7 +220,7 @@ int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int inve
  * geoRisk / zRisk / tRisk ListNet loss, forward + backward in one call on one GPU (no exchange between the phases).
  * replaces losses/riskLosses/riskLosses.py:8-60, 128-180, 247-291 end to end: ltr_risk_listnet_rows, the three
  * ltr_risk_phase launches and ltr_risk_listnet_rows_bwd, with the same arguments.
- *   mat : [B, 1 + S + add_ideal] out; state : 32 device doubles of scratch; gq : [B] scratch; grad : [B, n] or NULL.
+ *   mat : [B, 1 + S + add_ideal] out; state : 2080 device doubles of scratch; gq : [B] scratch; grad : [B, n] or NULL.
  */
 int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
                             int transformation, int add_ideal, int kind, int invert, int return_strategy,

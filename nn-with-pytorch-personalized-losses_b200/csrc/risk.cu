@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) risk_rows_bwd_kernel(const Ris
 // K6b.  One CTA of 1024 threads walks the [Q, C] matrix (a few KB .. MB); all arithmetic in fp64.
 // ---------------------------------------------------------------------------------------------------
 constexpr int RISKF_THREADS = 1024;
+constexpr int RISK_STATE = 16;           // doubles per state block
 
 struct RiskFinalParams {
     const float* mat;        // [Q, C] local rows (raw effectiveness, before the max - mat inversion)
@@ -166,15 +167,17 @@ struct RiskFinalParams {
     float* gmat;             // [Q, C] d loss / d mat (full), or null
 };
 
+template <int THREADS>
 __device__ __forceinline__ double rf_block_sum(double v, double* red) {
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
-    for (int w = 0; w < RISKF_THREADS / 32; ++w) t += red[w];
+    for (int w = 0; w < THREADS / 32; ++w) t += red[w];
     return t;
 }
+template <int THREADS>
 __device__ __forceinline__ double rf_block_max(double v, double* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(LTR_FULL_MASK, v, o));
@@ -182,16 +185,19 @@ __device__ __forceinline__ double rf_block_max(double v, double* red) {
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = red[0];
-    for (int w = 1; w < RISKF_THREADS / 32; ++w) t = fmax(t, red[w]);
+    for (int w = 1; w < THREADS / 32; ++w) t = fmax(t, red[w]);
     return t;
 }
 
 // phase 1 (local): state1 = {max(mat), sum_q mat[q,0], sum_q mat[q,C-1], sum of all entries, Q,
 //                            t-risk: sum_q d_q, 0...} where d_q = mat[q,1] - mat[q,0] needs no max at all.
-__device__ __forceinline__ void risk_stats1_body(const RiskFinalParams& p) {
+// `q0`, `dq`: first row and row stride of this thread (one CTA: threadIdx.x, RISKF_THREADS); `out`: where the block sums
+// go (state1 itself, or this CTA's slot of the cluster's partials)
+template <int THREADS>
+__device__ __forceinline__ void risk_stats1_body(const RiskFinalParams& p, int q0, int dq, double* out) {
     __shared__ double red[32];
     double mx = -1.0e300, s0 = 0.0, sl = 0.0, sa = 0.0;
-    for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
+    for (int q = q0; q < p.Q; q += dq) {
         const float* row = p.mat + (size_t)q * p.C;
         for (int i = 0; i < p.C; ++i) {
             const double x = (double)row[i];
@@ -201,16 +207,16 @@ __device__ __forceinline__ void risk_stats1_body(const RiskFinalParams& p) {
         s0 += (double)row[0];
         sl += (double)row[p.C - 1];
     }
-    mx = rf_block_max(mx, red);
-    s0 = rf_block_sum(s0, red);
-    sl = rf_block_sum(sl, red);
-    sa = rf_block_sum(sa, red);
+    mx = rf_block_max<THREADS>(mx, red);
+    s0 = rf_block_sum<THREADS>(s0, red);
+    sl = rf_block_sum<THREADS>(sl, red);
+    sa = rf_block_sum<THREADS>(sa, red);
     if (threadIdx.x == 0) {
-        p.state1[0] = mx;
-        p.state1[1] = s0;
-        p.state1[2] = sl;
-        p.state1[3] = sa;
-        p.state1[4] = (double)p.Q;
+        out[0] = mx;
+        out[1] = s0;
+        out[2] = sl;
+        out[3] = sa;
+        out[4] = (double)p.Q;
     }
 }
 
@@ -255,13 +261,14 @@ __device__ __forceinline__ ZCol make_zcol(const RiskFinalParams& p, const double
 
 // phase 2 (local, needs global state1): per used column {sum z c, sum A T, sum A e, sum c / sqrt(e), sum A}, count of
 // entries equal to the global max;  t-risk: {sum d', sum d'^2} with d' = d (1 + alpha [d < 0]).
-__device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p) {
+template <int THREADS>
+__device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p, int q0, int dq, double* out) {
     __shared__ double red[32];
     const double* g1 = p.state1;
     double a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double nmax = 0.0, td = 0.0, td2 = 0.0;
     if (p.kind == 2) {
-        for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
+        for (int q = q0; q < p.Q; q += dq) {
             const float* row = p.mat + (size_t)q * p.C;
             // ours - base after the (optional) inversion; the max cancels
             double d = p.invert ? (double)row[1] - (double)row[0] : (double)row[0] - (double)row[1];
@@ -271,7 +278,7 @@ __device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p) {
         }
     } else {
         const ZCol z0 = make_zcol(p, g1, false), zl = make_zcol(p, g1, true);
-        for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
+        for (int q = q0; q < p.Q; q += dq) {
             const float* row = p.mat + (size_t)q * p.C;
             double z, c, A, e, t;
             z0.eval(row, z, c, A, e, t);
@@ -284,22 +291,22 @@ __device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p) {
                 for (int i = 0; i < p.C; ++i) nmax += ((double)row[i] == g1[0]) ? 1.0 : 0.0;
         }
     }
-    for (int j = 0; j < 10; ++j) a[j] = rf_block_sum(a[j], red);
-    nmax = rf_block_sum(nmax, red);
-    td = rf_block_sum(td, red);
-    td2 = rf_block_sum(td2, red);
+    for (int j = 0; j < 10; ++j) a[j] = rf_block_sum<THREADS>(a[j], red);
+    nmax = rf_block_sum<THREADS>(nmax, red);
+    td = rf_block_sum<THREADS>(td, red);
+    td2 = rf_block_sum<THREADS>(td2, red);
     if (threadIdx.x == 0) {
-        for (int j = 0; j < 10; ++j) p.state2[j] = a[j];
-        p.state2[10] = nmax;
-        p.state2[11] = td;
-        p.state2[12] = td2;
+        for (int j = 0; j < 10; ++j) out[j] = a[j];
+        out[10] = nmax;
+        out[11] = td;
+        out[12] = td2;
     }
 }
 
 __device__ __forceinline__ double std_normal_cdf(double x) { return 0.5 * erfc(-x * 0.7071067811865476); }
 
 // phase 3 (local, needs global state1 and state2): loss value and gq[q] = d loss / d mat[q, 0].
-__device__ __forceinline__ void risk_final_body(const RiskFinalParams& p) {
+__device__ __forceinline__ void risk_final_body(const RiskFinalParams& p, int q0, int dq, bool write_loss) {
     const double* g1 = p.state1;
     const double* g2 = p.state2;
     const double f = (double)p.negative;
@@ -309,8 +316,8 @@ __device__ __forceinline__ void risk_final_body(const RiskFinalParams& p) {
         const double mu = g2[11] / Qg;
         const double var = (g2[12] - Qg * mu * mu) / (Qg - 1.0);
         const double sd = sqrt(var);
-        if (threadIdx.x == 0) p.loss[0] = (float)(f * mu / sd);
-        for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
+        if (write_loss && threadIdx.x == 0) p.loss[0] = (float)(f * mu / sd);
+        for (int q = q0; q < p.Q; q += dq) {
             const float* row = p.mat + (size_t)q * p.C;
             double d = p.invert ? (double)row[1] - (double)row[0] : (double)row[0] - (double)row[1];
             const double c = (d < 0.0) ? 1.0 + (double)p.alpha : 1.0;
@@ -353,7 +360,7 @@ __device__ __forceinline__ void risk_final_body(const RiskFinalParams& p) {
         const double d = val[1] - val[0];
         loss = f * d * d; coef[1] = 2.0 * f * d; coef[0] = -coef[1];
     }
-    if (threadIdx.x == 0) p.loss[0] = (float)loss;
+    if (write_loss && threadIdx.x == 0) p.loss[0] = (float)loss;
     if (!p.gq && !p.gmat) return;
     // d loss / d X[q', i'] = sum_u coef_u { dz_u ( [i' == col_u] (c/sqrt(e) + sum(A T)/N) + A_q' S_u / N - sum(A e)/N )
     //                                       + dS_u [i' == col_u] }
@@ -368,7 +375,7 @@ __device__ __forceinline__ void risk_final_body(const RiskFinalParams& p) {
                           dS[u] * Qg);
     }
     const double share = p.invert ? all / g2[10] : 0.0;
-    for (int q = threadIdx.x; q < p.Q; q += RISKF_THREADS) {
+    for (int q = q0; q < p.Q; q += dq) {
         const float* row = p.mat + (size_t)q * p.C;
         double own[2], shared[2];
         for (int u = 0; u < nu; ++u) {
@@ -392,27 +399,63 @@ __device__ __forceinline__ void risk_final_body(const RiskFinalParams& p) {
 
 __global__ void __launch_bounds__(RISKF_THREADS) risk_stats1_kernel(const RiskFinalParams p) {
     pdl_prologue();
-    risk_stats1_body(p);
+    risk_stats1_body<RISKF_THREADS>(p, threadIdx.x, RISKF_THREADS, p.state1);
 }
 __global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskFinalParams p) {
     pdl_prologue();
-    risk_stats2_body(p);
+    risk_stats2_body<RISKF_THREADS>(p, threadIdx.x, RISKF_THREADS, p.state2);
 }
 __global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskFinalParams p) {
     pdl_prologue();
-    risk_final_body(p);
+    risk_final_body(p, threadIdx.x, RISKF_THREADS, true);
 }
-// one GPU, no exchange between the phases: the single CTA runs them back to back (the state blocks written by
-// thread 0 of one phase are read by every thread of the next: fence + barrier in between)
-__global__ void __launch_bounds__(RISKF_THREADS) risk_phases_fused_kernel(const RiskFinalParams p) {
+
+// One GPU, no exchange between the phases: three launches of RISK_MC_BLOCKS small CTAs (one row per thread at 8192
+// rows) instead of one CTA that does all the fp64 divisions and square roots of the matrix on a single SM.  A phase
+// leaves its block sums in `part` (global scratch, [phase][block][RISK_STATE]); EVERY block of the next phase adds
+// them up in block order into its own shared-memory copy of the state (deterministic, no counters, no atomics:
+// the kernel boundary is the barrier), block 0 also publishes the state blocks.
+constexpr int RISK_MC_BLOCKS = 64;
+constexpr int RISK_MC_THREADS = 128;
+struct RiskMcParams {
+    RiskFinalParams f;
+    double* part;            // [2][RISK_MC_BLOCKS][RISK_STATE]
+};
+__device__ __forceinline__ void risk_mc_gather(const double* part, int phase, double* dst, bool is_max0) {
+    // thread j < RISK_STATE adds entry j of every block, in block order
+    if (threadIdx.x < RISK_STATE) {
+        const double* src = part + (size_t)phase * RISK_MC_BLOCKS * RISK_STATE + threadIdx.x;
+        double t = src[0];
+        for (int b = 1; b < RISK_MC_BLOCKS; ++b) {
+            const double v = src[(size_t)b * RISK_STATE];
+            t = (is_max0 && threadIdx.x == 0) ? fmax(t, v) : t + v;
+        }
+        dst[threadIdx.x] = t;
+    }
+}
+template <int PHASE>
+__global__ void __launch_bounds__(RISK_MC_THREADS) risk_mc_kernel(const RiskMcParams mp) {
+    __shared__ double st1[RISK_STATE], st2[RISK_STATE];
+    RiskFinalParams p = mp.f;
+    const int q0 = (int)blockIdx.x * RISK_MC_THREADS + (int)threadIdx.x, dq = RISK_MC_BLOCKS * RISK_MC_THREADS;
     pdl_prologue();
-    risk_stats1_body(p);
-    __threadfence_block();
-    __syncthreads();
-    risk_stats2_body(p);
-    __threadfence_block();
-    __syncthreads();
-    risk_final_body(p);
+    if (PHASE >= 2) {
+        risk_mc_gather(mp.part, 0, st1, true);
+        __syncthreads();
+        if (threadIdx.x == 0) st1[4] = (double)p.Q;              // (every block reported Q: not a sum)
+        if (PHASE == 3) risk_mc_gather(mp.part, 1, st2, false);
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < RISK_STATE) {
+            if (PHASE == 2) p.state1[threadIdx.x] = st1[threadIdx.x];
+            else p.state2[threadIdx.x] = st2[threadIdx.x];
+        }
+        p.state1 = st1;
+        p.state2 = st2;
+    }
+    double* mine = mp.part + ((size_t)(PHASE - 1) * RISK_MC_BLOCKS + blockIdx.x) * RISK_STATE;
+    if (PHASE == 1) risk_stats1_body<RISK_MC_THREADS>(p, q0, dq, mine);
+    else if (PHASE == 2) risk_stats2_body<RISK_MC_THREADS>(p, q0, dq, mine);
+    else risk_final_body(p, q0, dq, blockIdx.x == 0);
 }
 
 static int risk_grid(int B) {
@@ -480,8 +523,9 @@ LTR_API int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, 
     return rc ? set_cuda_error(rc, "ltr_risk_phase") : 0;
 }
 
-// Single-GPU fused call: rows -> the three risk phases in one single-CTA kernel -> backward rows: three dependent
-// launches issued from one host call (each starts its ramp-up under the previous one's tail).  Query-sharded callers use the separate
+// Single-GPU fused call: rows -> the three risk phases, 64 CTAs each -> backward rows: five dependent launches issued
+// from one host call (each starts its ramp-up under the previous one's tail).
+// state: 32 + 2 * 64 * 16 = 2080 device doubles of scratch.  Query-sharded callers use the separate
 // entry points above and all-reduce the two state blocks between the phases.
 LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
                                     int transformation, int add_ideal, int kind, int invert, int return_strategy,
@@ -497,7 +541,11 @@ LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, co
         if (kind == 2 && C < 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: t-risk needs the model and a baseline column");
         RiskFinalParams fp{mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state, state + 16,
                            loss, gq, nullptr};
-        rc = launch_pdl(risk_phases_fused_kernel, 1, RISKF_THREADS, 0, reinterpret_cast<cudaStream_t>(stream), fp);
+        RiskMcParams mp{fp, state + 32};
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        rc = launch_pdl(risk_mc_kernel<1>, RISK_MC_BLOCKS, RISK_MC_THREADS, 0, st, mp);
+        if (!rc) rc = launch_pdl(risk_mc_kernel<2>, RISK_MC_BLOCKS, RISK_MC_THREADS, 0, st, mp);
+        if (!rc) rc = launch_pdl(risk_mc_kernel<3>, RISK_MC_BLOCKS, RISK_MC_THREADS, 0, st, mp);
         if (rc) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd");
     }
     if (!rc && grad) rc = ltr_risk_listnet_rows_bwd(y_pred, y_true, B, n, transformation, t_variant, gq, grad, stream);

@@ -317,8 +317,8 @@ class _RiskListnet(torch.autograd.Function):
         need = ctx.needs_input_grad[0]
         if not sharding.is_sharded(group):
             # one GPU: the five dependent launches are issued by one library call
-            scratch = torch.empty(32 * 2 + 1 + B, dtype=torch.float32, device=dev)   # 32 doubles | loss | gq
-            state, loss, gq = scratch[:64].view(torch.float64), scratch[64:65], scratch[65:]
+            scratch = torch.empty(2080 * 2 + 1 + B, dtype=torch.float32, device=dev)   # 2080 doubles | loss | gq
+            state, loss, gq = scratch[:4160].view(torch.float64), scratch[4160:4161], scratch[4161:]
             grad = torch.empty_like(y_pred) if need else None
             _lib.check(lib.ltr_risk_listnet_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
                                                    int(bool(add_ideal)), int(kind), int(invert), int(strategy), int(quirk),
