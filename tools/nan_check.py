@@ -1,3 +1,4 @@
+"""A NaN or inf score must turn the batch loss into NaN (as in the reference), and the next clean call must be unaffected."""
 import sys, os
 sys.path[:0] = ["/root/repo", "/root/repo/nn-with-pytorch-personalized-losses_b200"]
 import torch
