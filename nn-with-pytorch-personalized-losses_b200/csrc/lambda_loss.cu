@@ -236,17 +236,25 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
     for (int phase = 0; phase < 3; ++phase) {
         if (phase > 0 && TB == 0) break;
         const bool cross = phase == 1;
-        const int T = cross ? 32 : (phase == 0 ? TA : TB);      // ring size
+        // ring size.  A x B: the smallest power of two >= TB; the 32 lanes form 32 / T independent rings, each carrying
+        // its own copy of group B's blocks past its lanes' rows, so no step is spent on blocks that do not exist
+        int T = phase == 0 ? TA : TB;
+        if (cross) {
+            T = 1;
+            while (T < TB) T <<= 1;
+        }
         const int rbase = phase == 2 ? 128 : 0;                 // first rank position of the row group
         const int cbase = phase == 0 ? 0 : 128;                 //                       of the column group
         const int TR = phase == 2 ? TB : TA;                    // lanes that own a row block
         const int S = T >> 1;
-        // symmetric: steps 1 .. S; cross: steps 0 .. 31
-        const int d_lo = cross ? role * 8 : 1 + ((role * S) >> 2);
-        const int d_hi = cross ? role * 8 + 8 : 1 + (((role + 1) * S) >> 2);
-        const bool active = lane < T;
-        const int src = active ? ((lane + 1 == T) ? 0 : lane + 1) : lane;
-        int cb = lane + d_lo;
+        // symmetric: steps 1 .. S; cross: steps 0 .. T - 1
+        const int d_lo = cross ? (role * T) >> 2 : 1 + ((role * S) >> 2);
+        const int d_hi = cross ? ((role + 1) * T) >> 2 : 1 + (((role + 1) * S) >> 2);
+        const bool active = cross || lane < T;
+        const int ring0 = cross ? (lane & ~(T - 1)) : 0;        // first lane of this lane's ring
+        const int pos = lane - ring0;                           // position inside the ring
+        const int src = active ? ring0 + ((pos + 1 == T) ? 0 : pos + 1) : lane;
+        int cb = pos + d_lo;
         if (cb >= T) cb -= T;
         if (!active) cb = 0;
         if (phase != 1) {                          // (A x B keeps the rows and row accumulators of A x A)
@@ -279,7 +287,7 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
 #pragma unroll 1
         for (int D = d_lo; D < d_hi; ++D) {
             const float h = (!cross && 2 * D == T) ? 0.5f : 1.0f;
-            int cblk = lane + D;                   // block visiting this lane at step D
+            int cblk = pos + D;                    // block visiting this lane at step D
             if (cblk >= T) cblk -= T;
             const int j0 = cbase + cblk * R;
 #pragma unroll
@@ -301,14 +309,20 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
                 }
             }
         }
-        // column partials of the block whose accumulators ended up in this lane (same warp: the phases are ordered)
-        if (active && d_hi > d_lo) {
-            int cblk = lane + d_hi - 1;
+        // column partials of the block whose accumulators ended up in this lane (same warp: the phases are ordered,
+        // and so are the rings of A x B, which all hold a copy of the same blocks)
+        {
+            int cblk = pos + d_hi - 1;
             if (cblk >= T) cblk -= T;
+            const int nrings = cross ? 32 / T : 1;
+            for (int ring = 0; ring < nrings; ++ring) {
+                if (active && d_hi > d_lo && ring0 == ring * T && cblk < (cross ? TB : T)) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) colpart[cbase + cblk * R + r] += g_c[r];
+                    for (int r = 0; r < R; ++r) colpart[cbase + cblk * R + r] += g_c[r];
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
         // row partials: group A after A x B (or after A x A when there is no group B), group B after B x B
         if ((phase == 1 || phase == 2 || TB == 0) && lane < TR) {
 #pragma unroll
