@@ -157,10 +157,11 @@ int ltr_order_score_fwdbwd(const float* y_true, const float* y_pred, int B, int 
  *   loss       : [1] out, -sum (reduction_mean = 0) or -sum/count over the whole batch (lambdaL.py:86-89)
  *   pair_count : [1] out or NULL, number of masked pairs in the batch
  *   grad       : [B, n] out or NULL, d loss / d y_pred (0 for padded docs)
+ *   workspace  : LTR_WORKSPACE_BYTES of zero-filled device memory per stream (slates are handed out dynamically), or NULL
  */
 int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value, int scheme,
                       int k, float sigma, float mu, int reduction_mean, int natural_log, float* slate_sum,
-                      float* slate_count, float* loss, float* pair_count, float* grad, void* stream);
+                      float* slate_count, float* loss, float* pair_count, float* grad, void* workspace, void* stream);
 
 /*
  * Risk-sensitive losses, ListNet family.      replaces losses/riskLosses/riskLosses.py:8-60, 128-180, 247-291

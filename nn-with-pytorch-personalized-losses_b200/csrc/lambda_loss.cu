@@ -30,6 +30,7 @@ struct LambdaParams {
     float* slate_sum;           // [B] sum of the masked pair log-probabilities of the slate
     float* slate_cnt;           // [B] number of masked pairs
     float* grad;                // [B, n] d(-sum)/d y_pred, unscaled; null = forward only
+    unsigned* next;             // next-slate counter in the caller's workspace (left at 0), or null: static assignment
 };
 
 // ---- symmetric pair schedule for top-k blocks of up to 256 docs --------------------------------------
@@ -365,7 +366,11 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
     // d/d delta of log_b: w sigma (1-sig) / ln b -> binary: / ln 2, natural: 1
     const float grad_scale = p.natural_log ? p.sigma : p.sigma / kLn2;
 
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    // slates cost up to 4x each other (the pair work grows with the square of their length): CTAs take the next slate
+    // from a counter as they finish instead of a fixed share
+    __shared__ int sh_next;
+    int b = blockIdx.x;
+    while (b < p.B) {
         const float* sp = p.y_pred + (size_t)b * n;
         const float* yp = p.y_true + (size_t)b * n;
         int cnt_valid = 0;
@@ -516,14 +521,18 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         if (tid == 0) {
             p.slate_sum[b] = (red[0] + red[1]) + (red[2] + red[3]);
             p.slate_cnt[b] = (red[8] + red[9]) + (red[10] + red[11]);
+            sh_next = p.next ? (int)(gridDim.x + atomicAdd(p.next, 1u)) : b + (int)gridDim.x;
         }
         __syncthreads();
+        b = sh_next;
     }
 }
 
 // loss = -sum (reduction "sum") or -sum / count ("mean"); for "mean" the gradient is scaled by 1/count too.
 __global__ void __launch_bounds__(256) lambda_finish_kernel(const float* slate_sum, const float* slate_cnt, int B, int mean,
-                                                            float* loss, float* count_out, float* grad, long long total) {
+                                                            float* loss, float* count_out, float* grad, long long total,
+                                                            unsigned* next) {
+    if (next && blockIdx.x == 0 && threadIdx.x == 0) *next = 0u;      // (lambda_kernel is complete: same stream)
     __shared__ double red[2][8];
     __shared__ float sh_inv;
     double s = 0.0, c = 0.0;
@@ -560,7 +569,7 @@ static int launch_lambda(const LambdaParams& p, size_t smem, int grid, cudaStrea
 LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value,
                               int scheme, int k, float sigma, float mu, int reduction_mean, int natural_log,
                               float* slate_sum, float* slate_count, float* loss, float* pair_count, float* grad,
-                              void* stream) {
+                              void* workspace, void* stream) {
     using namespace ltr;
     if (!y_pred || !y_true || !slate_sum || !slate_count || !loss || B <= 0 || n <= 0)
         return set_error(LTR_EINVAL, "ltr_lambda_fwdbwd: null pointer or non-positive B/n");
@@ -572,6 +581,7 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
     while (p.len < n) p.len <<= 1;
     p.eps = eps; p.pad = pad_value; p.sigma = sigma; p.mu = mu; p.natural_log = natural_log;
     p.slate_sum = slate_sum; p.slate_cnt = slate_count; p.grad = grad;
+    p.next = workspace ? ws_counter(workspace, LTR_WS_LAMBDA_COUNTER) : nullptr;
     const size_t smem = ((size_t)p.len * 6 + 10 * 256) * sizeof(float);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int cap = device_sm_count() * 8;
@@ -591,7 +601,7 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
     int fgrid = reduction_mean && grad ? (int)((total + 256 * 8 - 1) / (256 * 8)) : 1;
     if (fgrid > cap) fgrid = cap;
     if (fgrid < 1) fgrid = 1;
-    lambda_finish_kernel<<<fgrid, 256, 0, st>>>(slate_sum, slate_count, B, reduction_mean, loss, pair_count, grad, total);
+    lambda_finish_kernel<<<fgrid, 256, 0, st>>>(slate_sum, slate_count, B, reduction_mean, loss, pair_count, grad, total, p.next);
     rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_lambda_fwdbwd") : 0;
 }

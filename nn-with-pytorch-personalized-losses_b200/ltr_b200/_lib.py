@@ -34,7 +34,7 @@ _SIGNATURES = {
     "ltr_exact_ndcg": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "ltr_order_score_fwdbwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     "ltr_lambda_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, c_int,
-                                  _P, _P, _P, _P, _P, _P]),
+                                  _P, _P, _P, _P, _P, _P, _P]),
     "ltr_risk_listnet_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "ltr_risk_listnet_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "ltr_risk_lambda_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),

@@ -139,7 +139,7 @@ class _Lambda(torch.autograd.Function):
         _lib.check(lib.ltr_lambda_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, float(eps), float(pad), int(scheme),
                                          int(k), float(sigma), float(mu), int(mean), int(natural), sums[0].data_ptr(),
                                          sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), _ptr(grad),
-                                         rt.stream_ptr()), "ltr_lambda_fwdbwd")
+                                         rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_lambda_fwdbwd")
         ctx.grad = grad
         ctx.slate_sums = sums
         return out[0].reshape(())

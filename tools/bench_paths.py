@@ -133,10 +133,12 @@ def bench_lambda(iters=50, B=1024, n=256):
     sums = torch.empty(2, B, device="cuda")
     out = torch.empty(2, device="cuda")
     grad = torch.empty(B, n, device="cuda")
+    ws = rt.workspace(torch.device("cuda", torch.cuda.current_device()))
 
     def step(i):
         lib.ltr_lambda_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 1e-10, -1.0, 4, 0, 1.0, 10.0, 0, 0, sums[0].data_ptr(),
-                              sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), grad.data_ptr(), rt.stream_ptr())
+                              sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), grad.data_ptr(),
+                              ws.data_ptr(), rt.stream_ptr())
 
     sec = _time(step, iters)
     return {"metric": "LambdaLoss ndcgLoss2PP fwd+bwd slates/s (n=256)", "value": B / sec, "unit": "slates/s",
