@@ -242,7 +242,7 @@ __device__ __forceinline__ float ideal_label_from_counts(const int (&cnt)[8]) {
 }
 
 }  // namespace ltr
-#include "ndcg_stream.cuh"
+#include "ndcg_keys.cuh"
 namespace ltr {
 
 template <bool F64>
@@ -519,6 +519,8 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
 #define LTR_TPQ_ATTR(KERNEL) \
     LTR_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM))
             LTR_TPQ_ATTR(ndcg_tpq_kernel<false>); LTR_TPQ_ATTR(ndcg_tpq_kernel<true>);
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
             LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<false, 2>)); LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<true, 2>));
             LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<false, 4>)); LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<true, 4>));
 #undef LTR_TPQ_ATTR
@@ -530,14 +532,23 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
         // rows of one chunk: a batch that fits one resident wave of the quad-maxima kernel (16 warps per SM) takes it;
         // larger batches take the score-tile kernel, whose whole-tile asynchronous copies keep more bytes in flight
+#ifdef LTR_NDCG_KEYS
+        const bool keys = share == 1;          // label-in-key kernel (ndcg_keys.cuh), experimental: see DESIGN.md
+#else
+        const bool keys = false;
+#endif
         const bool qmax = share == 1 && tiles <= device_sm_count() * QMX_CTAS * TPQ_WARPS;
-        const int gcap = device_sm_count() * (share == 1 ? (qmax ? QMX_CTAS : TPQ_CTAS) : 2);
+        const int gcap = device_sm_count() * (share == 1 ? (keys ? KEY_CTAS : (qmax ? QMX_CTAS : TPQ_CTAS)) : 2);
         g = g < gcap ? g : gcap;
+        if (keys) g = tiles < gcap ? tiles : gcap;     // tile t -> CTA t % g: every SM gets its share of a small batch
         int rc;
 #define LTR_TPQ(C) \
     rc = f64 ? launch_pdl(ndcg_tpq_wide_kernel<true, C>, g, TPQ_THREADS, TPQ_SMEM, st, p) \
              : launch_pdl(ndcg_tpq_wide_kernel<false, C>, g, TPQ_THREADS, TPQ_SMEM, st, p)
-        if (qmax) {
+        if (keys) {
+            rc = f64 ? launch_pdl(ndcg_key_kernel<true>, g, TPQ_THREADS, KEY_SMEM, st, p)
+                     : launch_pdl(ndcg_key_kernel<false>, g, TPQ_THREADS, KEY_SMEM, st, p);
+        } else if (qmax) {
             rc = f64 ? launch_pdl(ndcg_qmax_kernel<true>, g, TPQ_THREADS, QMX_SMEM, st, p)
                      : launch_pdl(ndcg_qmax_kernel<false>, g, TPQ_THREADS, QMX_SMEM, st, p);
         } else if (share == 1) {
@@ -571,6 +582,19 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         const int chunks = (p.B + NDCG_MARK_CHUNK - 1) / NDCG_MARK_CHUNK;
         gs = chunks < cap ? chunks : cap;
     }
+#ifdef LTR_NDCG_SKIP_MARKED
+    if (marked_only) return 0;                 // timing experiments only: the marked queries are left unsorted
+#endif
+#ifdef LTR_NDCG_CARVEOUT
+    {
+        static bool carve_done = false;
+        if (!carve_done) {
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            carve_done = true;
+        }
+    }
+#endif
     if (f64) {
         if (int rc = rank_prepare(ndcg_kernel<true>, smem)) return rc;
         const int rc = launch_pdl(ndcg_kernel<true>, gs, RANK_THREADS, smem, st, p);

@@ -437,6 +437,44 @@ def test_ndcg_sweep_special_rows():
         np.testing.assert_allclose(np.nan_to_num(got[:, j]), ref, rtol=2e-6, atol=1e-7, err_msg=f"k={k}")
 
 
+def test_ndcg_sweep_near_ties_and_crowded_quads():
+    """Label-in-key kernel (ndcg_keys.cuh): scores that differ only in their last three mantissa bits inside the top
+    ranks (the thread redoes such a query with exact compares), three and four of the best docs in ONE quad (second /
+    third / rebuilt fourth key), -0 against +0, and rows whose best scores are negative or denormal."""
+    from ltr_b200.utils.metrics import ndcg_sweep
+    from oracle import ltr_oracle as O
+    Q, n = 160, 128
+    s, y = make_slates(Q, n, seed=777)
+    g = torch.Generator().manual_seed(778)
+    for q in range(0, 64):                              # near ties: top docs one to seven ulps apart, labels all differ
+        top = float(s[q].max()) + 1.0
+        pos = torch.randperm(n, generator=g)[:6]
+        vals = torch.tensor([top], dtype=torch.float32).repeat(6)
+        bits = vals.view(torch.int32) + torch.randperm(8, generator=g)[:6].to(torch.int32)
+        s[q, pos] = bits.view(torch.float32)
+        y[q, pos] = torch.tensor([0., 4., 1., 3., 2., 4.])
+    for q in range(64, 96):                             # the best docs crowd into one or two quads
+        j = int(torch.randint(0, n // 4, (1,), generator=g))
+        s[q, 4 * j:4 * j + 4] = float(s[q].max()) + torch.tensor([4., 2., 3., 1.])
+        j2 = (j + 5) % (n // 4)
+        s[q, 4 * j2:4 * j2 + 3] = float(s[q].max()) + torch.tensor([.5, .25, .75])
+    s[96, :] = -s[96].abs() - 1.0                       # all negative
+    s[97, :] = s[97] * 1e-41                            # denormals
+    s[98, :8] = torch.tensor([0., -0., 0., -0., 1e-45, -1e-45, 0., 0.])
+    s[98, 8:] = -1.0
+    s[99, :] = s[99].abs() * 1e30                       # large magnitudes
+    got = ndcg_sweep(y.cuda(), s.cuda(), ks=(1, 5, 10)).cpu().numpy()
+    for j, k in enumerate((1, 5, 10)):
+        ref = O.torch_ndcg(y, s, k=k, return_type="tensor").numpy()
+        np.testing.assert_allclose(np.nan_to_num(got[:, j]), ref, rtol=2e-6, atol=1e-7, err_msg=f"k={k}")
+    # fp64 arithmetic of mNdcg on the same rows (linear and exponential gains)
+    from ltr_b200.utils.metrics import mNdcg
+    for gains in ("linear", "exponential"):
+        ref = np.asarray(O.m_ndcg(y.numpy(), s.numpy(), k=10, gains=gains))
+        out = np.asarray(mNdcg(y.numpy(), s.numpy(), k=10, gains=gains))
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12, err_msg=gains)
+
+
 def test_ndcg_sweep_large_eval_set_matches_small_batches():
     """More queries than one resident wave of the quad-maxima kernel (75,776): the score-tile kernel takes the whole
     set; it must reproduce, bit for bit, what the quad-maxima kernel returns for the same queries in slices."""
