@@ -192,13 +192,26 @@ __device__ __forceinline__ int next_pow2(int v) {
 // In-shared-memory bitonic sort, DESCENDING by key, all threads of the block participate.
 // `len` must be a power of two. Keys only (used for ideal-DCG label order, where ties are
 // value-identical and so order-free).
+// ---- "group" = the CTA (default) or one warp: the shared-memory sorts below run at either scope ----------------
+template <bool WARP> __device__ __forceinline__ int grp_tid() { return WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+template <bool WARP> __device__ __forceinline__ int grp_size() { return WARP ? 32 : (int)blockDim.x; }
+template <bool WARP> __device__ __forceinline__ void grp_sync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
+}
+template <bool WARP> __device__ __forceinline__ int grp_or(int v) {
+    if (WARP) return __any_sync(0xffffffffu, v);
+    return __syncthreads_or(v);
+}
+
+template <bool WARP = false>
 __device__ __forceinline__ void block_bitonic_desc(float* keys, int len) {
 #pragma unroll 1
     for (int k = 2; k <= len; k <<= 1) {
 #pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+            grp_sync<WARP>();
+            for (int t = grp_tid<WARP>(); t < (len >> 1); t += grp_size<WARP>()) {
                 // index of the lower element of the t-th compare-exchange pair
                 int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 int hi = lo | j;
@@ -212,7 +225,7 @@ __device__ __forceinline__ void block_bitonic_desc(float* keys, int len) {
             }
         }
     }
-    __syncthreads();
+    grp_sync<WARP>();
 }
 
 }  // namespace ltr

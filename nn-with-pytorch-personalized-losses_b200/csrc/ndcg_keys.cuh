@@ -41,7 +41,7 @@ constexpr int KEY_AB_STRIDE = 36;          // floats per row of A / B: conflict-
 constexpr int KEY_C_STRIDE = 33;           // floats per row of C: read one word at a time
 constexpr int KEY_LUT = 625;               // label histogram of a quad by its base-5 code
 #ifndef LTR_KEY_AHEAD
-#define LTR_KEY_AHEAD 16
+#define LTR_KEY_AHEAD 8
 #endif
 constexpr int KEY_AHEAD = LTR_KEY_AHEAD;   // rows between the L2 prefetch and the demand loads of a warp (a multiple of KEY_BATCH)
 
@@ -52,6 +52,7 @@ struct KeyTile {
 };
 constexpr size_t KEY_LUT_BYTES = (KEY_LUT * 4 + 15) / 16 * 16;
 constexpr size_t KEY_SMEM = KEY_LUT_BYTES + sizeof(KeyTile) * TPQ_WARPS;
+static_assert(sizeof(float) * 32 * KEY_AB_STRIDE >= (4 * 128 + 3 * 48) * sizeof(float), "a marked row is sorted inside the A array");
 static_assert(KEY_LUT_BYTES + sizeof(KeyTile) >= 4096, "a 10-bit quad code read stays inside the CTA's shared memory");
 
 // HBM -> L2 only: the demand loads that follow find the rows in L2, so the few rows a warp can keep in flight in its
@@ -80,8 +81,15 @@ __device__ __forceinline__ void key_insert(float (&v)[K], float x) {
     v[0] = fmaxf(v[0], x);
 }
 
+// the full sort of a marked query by one warp, out of line: it is rare, and the hot loops stay compact
 template <bool F64>
-__global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const NdcgParams p) {
+__device__ __noinline__ void key_full_sort(const NdcgParams& p, float* scratch, int b) {
+    RankSmem rs(scratch, p.len);
+    ndcg_sorted_query<F64, true>(p, rs, b);
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const __grid_constant__ NdcgParams p) {
     extern __shared__ __align__(16) unsigned char tpq_smem[];
     // term[r][l] = gain(l) / discount(r) for ranks r < 10 and labels l <= 4, divided exactly as the reference divides
     __shared__ double term64[F64 ? (TPQ_K - 1) * 8 : 1];
@@ -100,14 +108,10 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
     const bool lane_in = 4 * lane < n;                     // this lane's quad exists (n % 4 == 0)
     unsigned kends = 0;                                    // bit r: some k of the sweep equals r + 1
     for (int j = 0; j < p.nk; ++j) kends |= 1u << (p.ks[j] - 1);
-    pdl_prologue();
-    if ((int)threadIdx.x < (TPQ_K - 1) * 8) {
-        const int r = (int)threadIdx.x >> 3, l = (int)threadIdx.x & 7;
-        if (r < p.kmax && l <= 4) {
-            if (F64) term64[threadIdx.x] = (p.exp_gains ? (double)((1 << l) - 1) : (double)l) / p.disc64[r];
-            else term32[threadIdx.x] = (float)((1 << l) - 1) / p.disc32[r];
-        }
-    }
+    // Before the programmatic dependency is resolved (the previous kernel on the stream may still run): nothing is read
+    // or written yet -- the histogram table is pure arithmetic, and the first rows only move from HBM to L2, where a late
+    // write of the previous kernel would still be seen by the loads below.
+    asm volatile("griddepcontrol.launch_dependents;");
     // quad code c = l0 + 5 l1 + 25 l2 + 125 l3 -> its label histogram: level L counts in byte L - 1; level 0: nothing
     if ((int)threadIdx.x < 125) {
         const int l0 = (int)threadIdx.x % 5, l1 = ((int)threadIdx.x / 5) % 5, l2 = (int)threadIdx.x / 25;
@@ -116,7 +120,22 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
 #pragma unroll
         for (int l3 = 1; l3 < 5; ++l3) lut[threadIdx.x + 125 * l3] = h + (1u << (8 * (l3 - 1)));
     }
-    __syncthreads();
+    // rows [q, q + KEY_BATCH) of both arrays -> L2 (one lane, two instructions)
+    auto prefetch_rows = [&](int q) {
+        const int rows = min(KEY_BATCH, p.B - q);
+        if (KEY_AHEAD > 0 && lane == 0 && rows > 0) {
+            prefetch_l2_bulk(p.y_pred + (size_t)q * n, (unsigned)(rows * n * 4));
+            prefetch_l2_bulk(p.y_true + (size_t)q * n, (unsigned)(rows * n * 4));
+        }
+    };
+    if (gwarp < ntiles) {
+        const int rows = min(KEY_AHEAD + KEY_BATCH, p.B - (gwarp << 5));
+        if (KEY_AHEAD > 0 && lane == 0) {
+            prefetch_l2_bulk(p.y_pred + (size_t)(gwarp << 5) * n, (unsigned)(rows * n * 4));
+            prefetch_l2_bulk(p.y_true + (size_t)(gwarp << 5) * n, (unsigned)(rows * n * 4));
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // KEY_BATCH rows in flight, reissued slot by slot.  Lanes beyond n keep (SENT, 0); rows beyond B keep the
     // values of an earlier row (their queries are never written).
@@ -131,23 +150,18 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
     };
     const float* sbase = p.y_pred + (size_t)min(gwarp, ntiles - 1) * 32 * n + 4 * lane;     // rows of the current tile
     const float* ybase = p.y_true + (size_t)min(gwarp, ntiles - 1) * 32 * n + 4 * lane;
-    // rows [q, q + KEY_BATCH) of both arrays -> L2 (one lane, two instructions)
-    auto prefetch_rows = [&](int q) {
-        const int rows = min(KEY_BATCH, p.B - q);
-        if (KEY_AHEAD > 0 && lane == 0 && rows > 0) {
-            prefetch_l2_bulk(p.y_pred + (size_t)q * n, (unsigned)(rows * n * 4));
-            prefetch_l2_bulk(p.y_true + (size_t)q * n, (unsigned)(rows * n * 4));
-        }
-    };
     if (gwarp < ntiles) {
-        const int rows = min(KEY_AHEAD, p.B - (gwarp << 5));
-        if (KEY_AHEAD > 0 && lane == 0) {
-            prefetch_l2_bulk(p.y_pred + (size_t)(gwarp << 5) * n, (unsigned)(rows * n * 4));
-            prefetch_l2_bulk(p.y_true + (size_t)(gwarp << 5) * n, (unsigned)(rows * n * 4));
-        }
 #pragma unroll
         for (int i = 0; i < KEY_BATCH; ++i) issue_row(s4[i], y4[i], sbase, ybase, (gwarp << 5) + i, (unsigned)(i * n));
     }
+    if ((int)threadIdx.x < (TPQ_K - 1) * 8) {
+        const int r = (int)threadIdx.x >> 3, l = (int)threadIdx.x & 7;
+        if (r < p.kmax && l <= 4) {
+            if (F64) term64[threadIdx.x] = (p.exp_gains ? (double)((1 << l) - 1) : (double)l) / p.disc64[r];
+            else term32[threadIdx.x] = (float)((1 << l) - 1) / p.disc32[r];
+        }
+    }
+    __syncthreads();
 
     for (int t = gwarp; t < ntiles; t += nwarps) {
         const int q0 = t << 5;
@@ -189,21 +203,21 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
             myhist = (lane == r) ? rowhist : myhist;
         };
 #pragma unroll 1
-        for (int rb = 0; rb < 32 - KEY_BATCH; rb += KEY_BATCH) {
-            prefetch_rows(rb + KEY_AHEAD < 32 ? q0 + rb + KEY_AHEAD : qnext + rb + KEY_AHEAD - 32);
+        for (int rb = 0; rb < 32; rb += KEY_BATCH) {
+            // rows entering L2 now: KEY_AHEAD + KEY_BATCH rows ahead of the row in hand, in this tile or the warp's next
+            const int ahead = rb + KEY_AHEAD + KEY_BATCH;
+            prefetch_rows(ahead < 32 ? q0 + ahead : qnext + ahead - 32);
+            // the slot a row leaves is reissued with the row KEY_BATCH further on, or a first row of the next tile
+            const bool last = rb + KEY_BATCH >= 32;
+            const float* sb = last ? snext : sbase;
+            const float* yb = last ? ynext : ybase;
+            const int qb = last ? qnext : q0 + rb + KEY_BATCH;
+            const unsigned ob = last ? 0u : (unsigned)((rb + KEY_BATCH) * n);
 #pragma unroll
             for (int i = 0; i < KEY_BATCH; ++i) {
                 do_row(rb + i, s4[i], y4[i]);
-                // the slot is free: the row KEY_BATCH further on
-                issue_row(s4[i], y4[i], sbase, ybase, q0 + rb + i + KEY_BATCH, (unsigned)((rb + i + KEY_BATCH) * n));
+                issue_row(s4[i], y4[i], sb, yb, qb + i, ob + (unsigned)(i * n));
             }
-        }
-        prefetch_rows(qnext + KEY_AHEAD - KEY_BATCH);
-#pragma unroll
-        for (int i = 0; i < KEY_BATCH; ++i) {
-            do_row(32 - KEY_BATCH + i, s4[i], y4[i]);
-            // the slot is free: a first row of this warp's next tile
-            issue_row(s4[i], y4[i], snext, ynext, qnext + i, (unsigned)(i * n));
         }
         sbase = snext;
         ybase = ynext;
@@ -265,6 +279,10 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
         // (the warp stages such a row in its tile, which no lane needs any more, and the query's lane scans it)
         __syncwarp();
         unsigned redo = __ballot_sync(LTR_FULL_MASK, near && !bad && q < p.B);
+        if (__popc(redo) > 4) {                  // tie-heavy scores: no point in looking, the full sort takes them all
+            bad |= (int)((redo >> lane) & 1u);
+            redo = 0;
+        }
         while (redo) {
             const int f = __ffs((int)redo) - 1;
             redo &= redo - 1;
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
                 int xl[TPQ_K];
 #pragma unroll
                 for (int j = 0; j < TPQ_K; ++j) xs[j] = ninf, xl[j] = 0;
-#pragma unroll 2
+#pragma unroll 1
                 for (int d = 0; d < n; d += 4) {
                     const float4 sx = *reinterpret_cast<const float4*>(&tile.a[d]);
                     const float4 yx = *reinterpret_cast<const float4*>(&tile.b[d]);
@@ -298,6 +316,22 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
             }
             __syncwarp();
         }
+        // a marked query (exact tie among the ranks the sweep reads, label outside 0..4, NaN / infinite score) is sorted in
+        // full right here, by the warp, in the tile it no longer needs: bitonic network + std::sort replay (sort_common.cuh)
+        {
+            __syncwarp();
+            unsigned todo = __ballot_sync(LTR_FULL_MASK, bad && q < p.B);
+            while (todo) {
+                const int f = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+#ifdef LTR_KEY_INLINE_SORT
+                RankSmem rs(tile.a, p.len);
+                ndcg_sorted_query<F64, true>(p, rs, q0 + f);
+#else
+                key_full_sort<F64>(p, tile.a, q0 + f);
+#endif
+            }
+        }
         if (q < p.B) {
             p.flags[1 + q] = bad;
             if (!bad) {
@@ -308,34 +342,33 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const N
                 const unsigned ONES = 0x09249249u;                       // bit 3 r, r < 10
                 const unsigned ideal_lab = (((1u << (3 * min(c4, 10))) - 1u) & ONES) + (((1u << (3 * min(c3, 10))) - 1u) & ONES) +
                                            (((1u << (3 * min(c2, 10))) - 1u) & ONES) + (((1u << (3 * min(c1, 10))) - 1u) & ONES);
+                unsigned pred_lab = 0;
+#pragma unroll
+                for (int r = 0; r < TPQ_K - 1; ++r) pred_lab |= (__float_as_uint(top[r]) & 7u) << (3 * r);
                 if (!F64) {
                     float got = 0.f, ideal = 0.f;
                     float* out = p.out32 + (size_t)q * p.nk;
-#pragma unroll
-                    for (int r = 0; r < TPQ_K - 1; ++r) {
-                        if (r < p.kmax) {
-                            got += term32[8 * r + (__float_as_uint(top[r]) & 7u)];
-                            ideal += term32[8 * r + ((ideal_lab >> (3 * r)) & 7u)];
-                            if ((kends >> r) & 1u) {
-                                const float val = got / ideal;
-                                for (int j = 0; j < p.nk; ++j)
-                                    if (p.ks[j] == r + 1) out[j] = val;
-                            }
+#pragma unroll 1
+                    for (int r = 0; r < p.kmax; ++r) {
+                        got += term32[8 * r + ((pred_lab >> (3 * r)) & 7u)];
+                        ideal += term32[8 * r + ((ideal_lab >> (3 * r)) & 7u)];
+                        if ((kends >> r) & 1u) {
+                            const float val = got / ideal;
+                            for (int j = 0; j < p.nk; ++j)
+                                if (p.ks[j] == r + 1) out[j] = val;
                         }
                     }
                 } else {
                     double got = 0.0, ideal = 0.0;
                     double* out = p.out64 + (size_t)q * p.nk;
-#pragma unroll
-                    for (int r = 0; r < TPQ_K - 1; ++r) {
-                        if (r < p.kmax) {
-                            got += term64[8 * r + (__float_as_uint(top[r]) & 7u)];
-                            ideal += term64[8 * r + ((ideal_lab >> (3 * r)) & 7u)];
-                            if ((kends >> r) & 1u) {
-                                const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
-                                for (int j = 0; j < p.nk; ++j)
-                                    if (p.ks[j] == r + 1) out[j] = val;
-                            }
+#pragma unroll 1
+                    for (int r = 0; r < p.kmax; ++r) {
+                        got += term64[8 * r + ((pred_lab >> (3 * r)) & 7u)];
+                        ideal += term64[8 * r + ((ideal_lab >> (3 * r)) & 7u)];
+                        if ((kends >> r) & 1u) {
+                            const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
+                            for (int j = 0; j < p.nk; ++j)
+                                if (p.ks[j] == r + 1) out[j] = val;
                         }
                     }
                 }

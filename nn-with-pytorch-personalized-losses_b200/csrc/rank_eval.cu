@@ -86,21 +86,22 @@ struct NdcgParams {
 };
 
 // one query: full sort with the caller's tie rule, labels in predicted and in ideal order, all k of the sweep
-template <bool F64>
+template <bool F64, bool WARP = false>
 __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b) {
     const float ninf = __int_as_float(0xff800000);
     const float* yt = p.y_true + (size_t)b * p.n;
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
-    __syncthreads();
-    block_sort_desc(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1);   // ranks >= kmax are never read
+    for (int i = grp_tid<WARP>(); i < p.n; i += grp_size<WARP>()) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
+    grp_sync<WARP>();
+    block_sort_desc<WARP>(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1,
+                          WARP ? reinterpret_cast<int*>(sm.L + p.len) : nullptr);   // ranks >= kmax are never read
     // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
-    for (int i = threadIdx.x; i < p.len; i += blockDim.x) {
+    for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
         sm.L[i] = (i < p.n) ? yt[i] : ninf;
         if (i < p.n) sm.K0[i] = yt[sm.I[i]];
     }
-    block_bitonic_desc(sm.L, p.len);
-    if ((int)threadIdx.x < p.nk) {
-        int k = p.ks[threadIdx.x];
+    block_bitonic_desc<WARP>(sm.L, p.len);
+    if (grp_tid<WARP>() < p.nk) {
+        int k = p.ks[grp_tid<WARP>()];
         if (k <= 0 || k > p.n) k = p.n;
         if (!F64) {
             float got = 0.f, ideal = 0.f;
@@ -109,7 +110,7 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
                 got += (exp2f(sm.K0[r]) - 1.0f) / d;
                 ideal += (exp2f(sm.L[r]) - 1.0f) / d;
             }
-            p.out32[(size_t)b * p.nk + threadIdx.x] = got / ideal;
+            p.out32[(size_t)b * p.nk + grp_tid<WARP>()] = got / ideal;
         } else {
             double got = 0.0, ideal = 0.0;
             for (int r = 0; r < k; ++r) {
@@ -118,40 +119,49 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
                 got += (p.exp_gains ? exp2(lg) - 1.0 : lg) / d;
                 ideal += (p.exp_gains ? exp2(li) - 1.0 : li) / d;
             }
-            p.out64[(size_t)b * p.nk + threadIdx.x] = (ideal == 0.0) ? p.empty_value : got / ideal;
+            p.out64[(size_t)b * p.nk + grp_tid<WARP>()] = (ideal == 0.0) ? p.empty_value : got / ideal;
         }
     }
-    __syncthreads();
+    grp_sync<WARP>();
 }
 
 // Without flags: every query.  With flags (a top-k fast path ran in front): only the queries q it marked with
-// flags[1 + q] != 0; a CTA looks at NDCG_MARK_CHUNK flags at a time (small chunks spread a heavily marked batch over
-// every CTA; a batch without marked queries costs a few reads per CTA).
-constexpr int NDCG_MARK_CHUNK = 8;
+// flags[1 + q] != 0.  CTA c owns the contiguous range of ceil(B / grid) flags [c R, (c + 1) R): its threads read them
+// coalesced, the marked ones are collected in a shared list (in index order: the list is filled range by range of
+// NDCG_MARK_LIST flags) and sorted one after the other.  A CTA whose range holds no mark (every CTA, on scores without
+// ties) leaves after one read per thread and one barrier; a heavily marked batch is spread over every CTA.
+constexpr int NDCG_MARK_LIST = 4 * RANK_THREADS;        // flags looked at per pass
 template <bool F64>
 __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned marked;
+    __shared__ int list[NDCG_MARK_LIST];
+    __shared__ int nlist;
     RankSmem sm(smem_raw, p.len);
     pdl_prologue();
     if (!p.flags) {
         for (int b = blockIdx.x; b < p.B; b += gridDim.x) ndcg_sorted_query<F64>(p, sm, b);
         return;
     }
-    for (int base = (int)blockIdx.x * NDCG_MARK_CHUNK; base < p.B; base += (int)gridDim.x * NDCG_MARK_CHUNK) {
-        if (threadIdx.x < 32) {
-            const int q = base + (int)threadIdx.x;
-            const unsigned m = __ballot_sync(LTR_FULL_MASK, (int)threadIdx.x < NDCG_MARK_CHUNK && q < p.B && p.flags[1 + q] != 0);
-            if (threadIdx.x == 0) marked = m;
+    const int per = (p.B + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * per, hi = min(p.B, lo + per);
+    for (int base = lo; base < hi; base += NDCG_MARK_LIST) {
+        int mine[NDCG_MARK_LIST / RANK_THREADS];
+        int any = 0;
+#pragma unroll
+        for (int j = 0; j < NDCG_MARK_LIST / RANK_THREADS; ++j) {
+            const int q = base + j * RANK_THREADS + (int)threadIdx.x;
+            mine[j] = (q < hi) ? __ldcg(p.flags + 1 + q) : 0;
+            any |= mine[j];
         }
+        if (!__syncthreads_or(any)) continue;
+        if (threadIdx.x == 0) nlist = 0;
         __syncthreads();
-        unsigned m = marked;
+#pragma unroll
+        for (int j = 0; j < NDCG_MARK_LIST / RANK_THREADS; ++j)
+            if (mine[j]) list[atomicAdd(&nlist, 1)] = base + j * RANK_THREADS + (int)threadIdx.x;
         __syncthreads();
-        while (m) {
-            const int b = base + __ffs((int)m) - 1;
-            m &= m - 1;
-            ndcg_sorted_query<F64>(p, sm, b);
-        }
+        const int cnt = nlist;
+        for (int i = 0; i < cnt; ++i) ndcg_sorted_query<F64>(p, sm, list[i]);     // (any order: one output row per query)
     }
 }
 
@@ -510,7 +520,7 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     const size_t smem = rank_smem(p.len);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int cap = device_sm_count() * 8;
-    bool marked_only = false;
+    bool marked_only = false, keys_done = false;
     if (kmax <= TPQ_K - 1 && p.n % 4 == 0 && p.flags &&
         (reinterpret_cast<uintptr_t>(p.y_true) | reinterpret_cast<uintptr_t>(p.y_pred)) % 16 == 0) {
         // one thread per query (ndcg_stream.cuh), then the full sort for the queries it marked
@@ -532,10 +542,11 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
         // rows of one chunk: a batch that fits one resident wave of the quad-maxima kernel (16 warps per SM) takes it;
         // larger batches take the score-tile kernel, whose whole-tile asynchronous copies keep more bytes in flight
-#ifdef LTR_NDCG_KEYS
-        const bool keys = share == 1;          // label-in-key kernel (ndcg_keys.cuh), experimental: see DESIGN.md
+#ifdef LTR_NDCG_NO_KEYS
+        const bool keys = false;               // (A/B builds: the earlier quad-maxima / score-tile kernels of ndcg_stream.cuh)
 #else
-        const bool keys = false;
+        const bool keys = share == 1;          // rows of one chunk: label-in-key kernel (ndcg_keys.cuh), which also sorts
+                                               // the queries it marks -- no second launch
 #endif
         const bool qmax = share == 1 && tiles <= device_sm_count() * QMX_CTAS * TPQ_WARPS;
         const int gcap = device_sm_count() * (share == 1 ? (keys ? KEY_CTAS : (qmax ? QMX_CTAS : TPQ_CTAS)) : 2);
@@ -558,6 +569,7 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
 #undef LTR_TPQ
         if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (one thread per query)");
         marked_only = true;
+        keys_done = keys;
     } else if (kmax <= 31 && p.n <= 1024 && p.flags) {
         // top-k fast path (one warp per query), then the full sort for the queries it marked
         int g = (p.B + 7) / 8;
@@ -579,12 +591,13 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     }
     int gs = rank_grid(p.B);
     if (marked_only) {
-        const int chunks = (p.B + NDCG_MARK_CHUNK - 1) / NDCG_MARK_CHUNK;
-        gs = chunks < cap ? chunks : cap;
+        const int ranges = (p.B + 7) / 8;              // a small, heavily marked batch still spreads over many CTAs
+        gs = ranges < cap ? ranges : cap;
     }
 #ifdef LTR_NDCG_SKIP_MARKED
     if (marked_only) return 0;                 // timing experiments only: the marked queries are left unsorted
 #endif
+    if (keys_done) return 0;                   // the label-in-key kernel sorts the queries it marks itself
 #ifdef LTR_NDCG_CARVEOUT
     {
         static bool carve_done = false;

@@ -35,14 +35,14 @@ __device__ __forceinline__ bool pair_before(float ka, int ia, float kb, int ib) 
 }
 
 // Bitonic sort of len (power of two) (key, index) pairs in shared memory by all threads of the CTA.
-template <bool IDX_DESC>
+template <bool IDX_DESC, bool WARP = false>
 __device__ __forceinline__ void block_bitonic_pairs(float* K, int* I, int len) {
 #pragma unroll 1
     for (int k = 2; k <= len; k <<= 1) {
 #pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+            grp_sync<WARP>();
+            for (int t = grp_tid<WARP>(); t < (len >> 1); t += grp_size<WARP>()) {
                 const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int hi = lo | j;
                 const bool up = ((lo & k) == 0);                 // this run ends up in "before" order
@@ -56,7 +56,7 @@ __device__ __forceinline__ void block_bitonic_pairs(float* K, int* I, int len) {
             }
         }
     }
-    __syncthreads();
+    grp_sync<WARP>();
 }
 
 // The same network on ONE 64-bit word per entry: (order-preserving key << 32) | tie-break, sorted descending as an
@@ -68,13 +68,14 @@ __device__ __forceinline__ unsigned sort_key_bits(float f) {
     const unsigned b = __float_as_uint(f + 0.0f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+template <bool WARP = false>
 __device__ __forceinline__ void block_bitonic_packed(unsigned long long* P, int len) {
 #pragma unroll 1
     for (int k = 2; k <= len; k <<= 1) {
 #pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+            grp_sync<WARP>();
+            for (int t = grp_tid<WARP>(); t < (len >> 1); t += grp_size<WARP>()) {
                 const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int hi = lo | j;
                 const unsigned long long a = P[lo], c = P[hi];
@@ -86,7 +87,7 @@ __device__ __forceinline__ void block_bitonic_packed(unsigned long long* P, int 
             }
         }
     }
-    __syncthreads();
+    grp_sync<WARP>();
 }
 
 // ---- libstdc++ std::sort, replayed by ONE thread on (K, I) in their original order ---------------------
@@ -185,14 +186,17 @@ struct StdSortEmu {
     // disjoint, and in the final insertion sort an element can only move left past keys that sort strictly after
     // it, so nothing from such a part can enter a position below cut.  Positions >= the returned bound are left
     // unsorted (bound >= min(limit, n); bound == n when limit >= n: the complete sort).
-    __device__ int sort(int n, int limit) {
+    // stk: 3 x 48 ints of scratch (local memory for the CTA-level callers, shared memory for the warp-level one)
+    __device__ int sort(int n, int limit, int* stk) {
         if (n <= 1) return n;
         int depth0 = 0;
         for (int t = n; t > 1; t >>= 1) ++depth0;                 // __lg(n)
         depth0 *= 2;
         int bound = n;
         // __introsort_loop with an explicit stack (sub-ranges are disjoint, so their order is immaterial)
-        int stk_first[48], stk_last[48], stk_depth[48];
+        int* stk_first = stk;
+        int* stk_last = stk + 48;
+        int* stk_depth = stk + 96;
         int sp = 0;
         stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = depth0; sp = 1;
         while (sp > 0) {
@@ -230,11 +234,12 @@ struct StdSortEmu {
 // `tie_limit`: the caller only reads the first tie_limit entries of the result (callers whose trailing entries
 // are -inf padding that no output depends on pass the number of real docs; NDCG@k passes kmax + 1).  Only ties
 // among those entries trigger the replay, and after a replay entries at and beyond tie_limit may be in any order.
+template <bool WARP = false>
 __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int n, int len, int tie_rule,
-                                                int tie_limit = 1 << 30) {
+                                                int tie_limit = 1 << 30, int* warp_stack = nullptr) {
     const float ninf = __int_as_float(0xff800000);
     if (reinterpret_cast<void*>(I) == reinterpret_cast<void*>(K + len) && (reinterpret_cast<uintptr_t>(K) & 7) == 0 &&
-        len <= 8 * (int)blockDim.x) {
+        len <= 8 * grp_size<WARP>()) {
         // K and I are adjacent: sort ONE packed 64-bit word per entry, in place over both arrays.  Every thread first
         // holds its (at most 8) entries in registers, so the in-place repacking cannot overwrite an unread entry.
         unsigned long long* P = reinterpret_cast<unsigned long long*>(K);
@@ -242,63 +247,69 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
         float mine[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int i = threadIdx.x + e * blockDim.x;
+            const int i = grp_tid<WARP>() + e * grp_size<WARP>();
             mine[e] = (i < n) ? K[i] : 0.f;
         }
-        __syncthreads();
+        grp_sync<WARP>();
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int i = threadIdx.x + e * blockDim.x;
+            const int i = grp_tid<WARP>() + e * grp_size<WARP>();
             if (i < n) K0[i] = mine[e];
             if (i < len) {
                 const unsigned kb = (i < n) ? sort_key_bits(mine[e]) : 0u;
                 P[i] = ((unsigned long long)kb << 32) | (unsigned)(rev ? i : ~i);
             }
         }
-        block_bitonic_packed(P, len);                                 // (starts and ends with a barrier)
+        block_bitonic_packed<WARP>(P, len);                                 // (starts and ends with a barrier)
         int idx[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int i = threadIdx.x + e * blockDim.x;
+            const int i = grp_tid<WARP>() + e * grp_size<WARP>();
             const unsigned low = (i < len) ? (unsigned)P[i] : 0u;
             idx[e] = (int)(rev ? low : ~low);
         }
-        __syncthreads();
+        grp_sync<WARP>();
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int i = threadIdx.x + e * blockDim.x;
+            const int i = grp_tid<WARP>() + e * grp_size<WARP>();
             if (i < len) {
                 K[i] = (idx[e] < n) ? K0[idx[e]] : ninf;              // sentinels: -inf, index >= n, i.e. last
                 I[i] = idx[e];
             }
         }
-        __syncthreads();
+        grp_sync<WARP>();
     } else {
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    for (int i = grp_tid<WARP>(); i < len; i += grp_size<WARP>()) {
         if (i < n) K0[i] = K[i];
         else K[i] = ninf;
         I[i] = i;                                                 // sentinels: -inf with index >= n, i.e. last
     }
-    __syncthreads();
+    grp_sync<WARP>();
     if (tie_rule == TIES_REVERSED) {
         // sentinels must stay last among -inf keys although indices now sort descending
-        for (int i = n + threadIdx.x; i < len; i += blockDim.x) I[i] = -1 - i;
-        block_bitonic_pairs<true>(K, I, len);
+        for (int i = n + grp_tid<WARP>(); i < len; i += grp_size<WARP>()) I[i] = -1 - i;
+        block_bitonic_pairs<true, WARP>(K, I, len);
     } else {
-        block_bitonic_pairs<false>(K, I, len);
+        block_bitonic_pairs<false, WARP>(K, I, len);
     }
     }
     if (tie_rule != TIES_STDSORT || n <= 16) return;
     int tie = 0;
     const int lim = tie_limit < n ? tie_limit : n;
-    for (int i = threadIdx.x; i + 1 < lim; i += blockDim.x) tie |= key_equiv(K[i], K[i + 1]) ? 1 : 0;
-    if (!__syncthreads_or(tie)) return;
-    if (threadIdx.x == 0) {
+    for (int i = grp_tid<WARP>(); i + 1 < lim; i += grp_size<WARP>()) tie |= key_equiv(K[i], K[i + 1]) ? 1 : 0;
+    if (!grp_or<WARP>(tie)) return;
+    if (grp_tid<WARP>() == 0) {
         for (int i = 0; i < n; ++i) { K[i] = K0[i]; I[i] = i; }
         StdSortEmu emu{K, I};
-        emu.sort(n, lim);                                         // entries at and beyond `lim` may stay unsorted
+        // entries at and beyond `lim` may stay unsorted
+        if constexpr (WARP) {
+            emu.sort(n, lim, warp_stack);                         // (a warp-level caller keeps the kernel free of a stack frame)
+        } else {
+            int stk[3 * 48];
+            emu.sort(n, lim, stk);
+        }
     }
-    __syncthreads();
+    grp_sync<WARP>();
 }
 
 }  // namespace ltr

@@ -99,7 +99,7 @@ def bench_ndcg(iters=100, Q=65536, n=128, ks=(1, 5, 10), ring=3):
 
     sec = _time(step, iters)
     marked = [int((m[1:] != 0).sum()) for m in marks]
-    kern = "ndcg_tpq_kernel<false> + ndcg_kernel<false> (marked queries only)" if n <= 128 and max(ks) <= 10 else \
+    kern = "ndcg_key_kernel<false> (sorts the queries it marks itself)" if n <= 128 and max(ks) <= 10 else \
         "ndcg_topk_wide_kernel<false> + ndcg_kernel<false> (marked queries only)"
     return {"metric": f"NDCG@{{{','.join(map(str, ks))}}} eval queries/s (n={n})", "value": Q / sec, "unit": "queries/s",
             "us_per_call": sec * 1e6,
