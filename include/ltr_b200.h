@@ -113,7 +113,9 @@ int ltr_sort_desc(const float* keys, int B, int n, int tie_rule, int* perm, floa
  *   initialisation needed; on return flags[1 + q] != 0 marks the queries that took the full sort).  With it, sweeps
  *   whose largest k is <= 10 (n % 4 == 0, 16-byte aligned rows) take the one-thread-per-query path, sweeps up to k = 31
  *   and n <= 1024 the warp-per-query top-k path; neither sorts, and only queries with tied keys among their first
- *   k + 1 ranks (or a NaN score, or labels that are not small integers) are sorted in full with `tie_rule`.
+ *   k + 1 ranks (or a NaN / infinite score, or labels that are not small integers) are sorted in full with `tie_rule`:
+ *   rows of at most 128 docs inside the same launch (by the warp that finds them), longer rows by a second launch over
+ *   the marked queries.
  */
 int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
                   const float* disc32, float* out, int* flags, void* stream);

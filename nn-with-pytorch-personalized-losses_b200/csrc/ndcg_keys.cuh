@@ -83,9 +83,9 @@ __device__ __forceinline__ void key_insert(float (&v)[K], float x) {
 
 // the full sort of a marked query by one warp, out of line: it is rare, and the hot loops stay compact
 template <bool F64>
-__device__ __noinline__ void key_full_sort(const NdcgParams& p, float* scratch, int b) {
+__device__ __noinline__ void key_full_sort(const NdcgParams& p, float* scratch, int b, bool known_tie) {
     RankSmem rs(scratch, p.len);
-    ndcg_sorted_query<F64, true>(p, rs, b);
+    ndcg_sorted_query<F64, true>(p, rs, b, known_tie);
 }
 
 template <bool F64>
@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
         }
         // keys that agree in their upper 29 bits among the ranks the sweep reads: exact compares on the row itself
         int bad = mybad;
+        int tied = 0;                                    // an exact tie seen by the exact path below
         bool near = false;
 #pragma unroll
         for (int j = 0; j + 1 < TPQ_K; ++j) near = near || (j < p.kmax && j + 1 < n && key_near(top[j], top[j + 1]));
@@ -312,7 +313,8 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
 #pragma unroll
                 for (int j = 0; j < TPQ_K; ++j) top[j] = __uint_as_float((unsigned)xl[j]);     // only the label bits are read below
 #pragma unroll
-                for (int j = 0; j + 1 < TPQ_K; ++j) bad |= (j < p.kmax && j + 1 < n && xs[j] == xs[j + 1]) ? 1 : 0;
+                for (int j = 0; j + 1 < TPQ_K; ++j) tied |= (j < p.kmax && j + 1 < n && xs[j] == xs[j + 1]) ? 1 : 0;
+                bad |= tied;
             }
             __syncwarp();
         }
@@ -321,15 +323,11 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
         {
             __syncwarp();
             unsigned todo = __ballot_sync(LTR_FULL_MASK, bad && q < p.B);
+            const unsigned ties = __ballot_sync(LTR_FULL_MASK, tied);       // these go straight to the std::sort replay
             while (todo) {
                 const int f = __ffs((int)todo) - 1;
                 todo &= todo - 1;
-#ifdef LTR_KEY_INLINE_SORT
-                RankSmem rs(tile.a, p.len);
-                ndcg_sorted_query<F64, true>(p, rs, q0 + f);
-#else
-                key_full_sort<F64>(p, tile.a, q0 + f);
-#endif
+                key_full_sort<F64>(p, tile.a, q0 + f, (ties >> f) & 1u);
             }
         }
         if (q < p.B) {

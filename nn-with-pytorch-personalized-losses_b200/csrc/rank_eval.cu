@@ -87,13 +87,13 @@ struct NdcgParams {
 
 // one query: full sort with the caller's tie rule, labels in predicted and in ideal order, all k of the sweep
 template <bool F64, bool WARP = false>
-__device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b) {
+__device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b, bool known_tie = false) {
     const float ninf = __int_as_float(0xff800000);
     const float* yt = p.y_true + (size_t)b * p.n;
     for (int i = grp_tid<WARP>(); i < p.n; i += grp_size<WARP>()) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
     grp_sync<WARP>();
     block_sort_desc<WARP>(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1,
-                          WARP ? reinterpret_cast<int*>(sm.L + p.len) : nullptr);   // ranks >= kmax are never read
+                          WARP ? reinterpret_cast<int*>(sm.L + p.len) : nullptr, known_tie);   // ranks >= kmax are never read
     // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
     for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
         sm.L[i] = (i < p.n) ? yt[i] : ninf;

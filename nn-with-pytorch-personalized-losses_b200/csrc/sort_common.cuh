@@ -236,8 +236,25 @@ struct StdSortEmu {
 // among those entries trigger the replay, and after a replay entries at and beyond tie_limit may be in any order.
 template <bool WARP = false>
 __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int n, int len, int tie_rule,
-                                                int tie_limit = 1 << 30, int* warp_stack = nullptr) {
+                                                int tie_limit = 1 << 30, int* warp_stack = nullptr, bool known_tie = false) {
     const float ninf = __int_as_float(0xff800000);
+    if (known_tie && tie_rule == TIES_STDSORT && n > 16) {
+        // the caller has seen equal keys among the first tie_limit ranks: the network's result would be thrown away
+        const int lim = tie_limit < n ? tie_limit : n;
+        for (int i = grp_tid<WARP>(); i < n; i += grp_size<WARP>()) I[i] = i;
+        grp_sync<WARP>();
+        if (grp_tid<WARP>() == 0) {
+            StdSortEmu emu{K, I};
+            if constexpr (WARP) {
+                emu.sort(n, lim, warp_stack);
+            } else {
+                int stk[3 * 48];
+                emu.sort(n, lim, stk);
+            }
+        }
+        grp_sync<WARP>();
+        return;
+    }
     if (reinterpret_cast<void*>(I) == reinterpret_cast<void*>(K + len) && (reinterpret_cast<uintptr_t>(K) & 7) == 0 &&
         len <= 8 * grp_size<WARP>()) {
         // K and I are adjacent: sort ONE packed 64-bit word per entry, in place over both arrays.  Every thread first
@@ -298,8 +315,10 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
     const int lim = tie_limit < n ? tie_limit : n;
     for (int i = grp_tid<WARP>(); i + 1 < lim; i += grp_size<WARP>()) tie |= key_equiv(K[i], K[i + 1]) ? 1 : 0;
     if (!grp_or<WARP>(tie)) return;
+    grp_sync<WARP>();
+    for (int i = grp_tid<WARP>(); i < n; i += grp_size<WARP>()) { K[i] = K0[i]; I[i] = i; }      // back to the original order
+    grp_sync<WARP>();
     if (grp_tid<WARP>() == 0) {
-        for (int i = 0; i < n; ++i) { K[i] = K0[i]; I[i] = i; }
         StdSortEmu emu{K, I};
         // entries at and beyond `lim` may stay unsorted
         if constexpr (WARP) {
