@@ -83,9 +83,10 @@ __device__ __forceinline__ void key_insert(float (&v)[K], float x) {
 
 // the full sort of a marked query by one warp, out of line: it is rare, and the hot loops stay compact
 template <bool F64>
-__device__ __noinline__ void key_full_sort(const NdcgParams& p, float* scratch, int b, bool known_tie) {
+__device__ __noinline__ void key_full_sort(const NdcgParams& p, float* scratch, int b, bool known_tie, bool have_hist,
+                                           unsigned hist) {
     RankSmem rs(scratch, p.len);
-    ndcg_sorted_query<F64, true>(p, rs, b, known_tie);
+    ndcg_sorted_query<F64, true>(p, rs, b, known_tie, have_hist, hist);
 }
 
 template <bool F64>
@@ -327,7 +328,8 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
             while (todo) {
                 const int f = __ffs((int)todo) - 1;
                 todo &= todo - 1;
-                key_full_sort<F64>(p, tile.a, q0 + f, (ties >> f) & 1u);
+                // (a tile that passed the label check has its rows' histograms: the ideal order needs no second sort)
+                key_full_sort<F64>(p, tile.a, q0 + f, (ties >> f) & 1u, mybad == 0, __shfl_sync(LTR_FULL_MASK, myhist, f));
             }
         }
         if (q < p.B) {

@@ -86,8 +86,11 @@ struct NdcgParams {
 };
 
 // one query: full sort with the caller's tie rule, labels in predicted and in ideal order, all k of the sweep
+// known_tie: the caller has seen equal keys among the first kmax + 1 ranks.  have_hist: every label of the row is an
+// integer 0..4 and level L occurs (hist >> 8 (L - 1)) & 255 times -- the ideal order is then written down directly.
 template <bool F64, bool WARP = false>
-__device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b, bool known_tie = false) {
+__device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b, bool known_tie = false,
+                                                  bool have_hist = false, unsigned hist = 0) {
     const float ninf = __int_as_float(0xff800000);
     const float* yt = p.y_true + (size_t)b * p.n;
     for (int i = grp_tid<WARP>(); i < p.n; i += grp_size<WARP>()) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
@@ -95,11 +98,20 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
     block_sort_desc<WARP>(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1,
                           WARP ? reinterpret_cast<int*>(sm.L + p.len) : nullptr, known_tie);   // ranks >= kmax are never read
     // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
-    for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
-        sm.L[i] = (i < p.n) ? yt[i] : ninf;
-        if (i < p.n) sm.K0[i] = yt[sm.I[i]];
+    if (have_hist) {
+        const int c4 = hist >> 24, c3 = c4 + ((hist >> 16) & 255), c2 = c3 + ((hist >> 8) & 255), c1 = c2 + (hist & 255);
+        for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
+            sm.L[i] = (i < p.n) ? (float)((c4 > i) + (c3 > i) + (c2 > i) + (c1 > i)) : ninf;
+            if (i < p.n) sm.K0[i] = yt[sm.I[i]];
+        }
+        grp_sync<WARP>();
+    } else {
+        for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
+            sm.L[i] = (i < p.n) ? yt[i] : ninf;
+            if (i < p.n) sm.K0[i] = yt[sm.I[i]];
+        }
+        block_bitonic_desc<WARP>(sm.L, p.len);
     }
-    block_bitonic_desc<WARP>(sm.L, p.len);
     if (grp_tid<WARP>() < p.nk) {
         int k = p.ks[grp_tid<WARP>()];
         if (k <= 0 || k > p.n) k = p.n;
