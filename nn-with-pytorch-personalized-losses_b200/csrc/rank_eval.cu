@@ -610,16 +610,6 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     if (marked_only) return 0;                 // timing experiments only: the marked queries are left unsorted
 #endif
     if (keys_done) return 0;                   // the label-in-key kernel sorts the queries it marks itself
-#ifdef LTR_NDCG_CARVEOUT
-    {
-        static bool carve_done = false;
-        if (!carve_done) {
-            LTR_CUDA(cudaFuncSetAttribute(ndcg_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            LTR_CUDA(cudaFuncSetAttribute(ndcg_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            carve_done = true;
-        }
-    }
-#endif
     if (f64) {
         if (int rc = rank_prepare(ndcg_kernel<true>, smem)) return rc;
         const int rc = launch_pdl(ndcg_kernel<true>, gs, RANK_THREADS, smem, st, p);
