@@ -410,6 +410,12 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs off stdout: rank 0 prints ONE JSON line
+        # NCCL's version banner is a C-level printf that ignores NCCL_DEBUG_FILE: file descriptor 1 goes to stderr for
+        # native code, Python's own stdout (the JSON line) keeps the original descriptor
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
