@@ -176,6 +176,24 @@ def run_reference_arm(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run (and first-touch the pinned e2e buffers) on the CPUs NVML lists as local to this GPU, so
+    that the kernel's PCIe reads of host memory do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda._get_nvml_device_index(local_rank)
+                                              if hasattr(torch.cuda, "_get_nvml_device_index") else local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:                                   # no NVML / restricted container: keep the default placement
+        print(f"bench.py: NUMA binding skipped ({type(e).__name__}: {e})", file=sys.stderr)
+
+
 def run_b200_arm(args, rank, local_rank, world):
     import ctypes
 
@@ -187,6 +205,8 @@ def run_b200_arm(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world > 1:
+        _bind_to_gpu_numa_node(local_rank)
     lib = _lib.load()
     B, n = B_PER_GPU, N_DOCS
 
