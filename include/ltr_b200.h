@@ -87,10 +87,12 @@ int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, int n, i
  * Ordinal loss, fused forward + backward.     replaces losses/ordinal.py:9-53
  *   y_pred : [B, n, levels] probabilities, y_true : [B, n]; loss [1]; grad [B, n, levels] or NULL.
  *   A label of -1 makes all targets of the doc -1 (with_ordinals' default); entries whose TARGET equals
- *   pad_indicator are masked (ordinal.py:41).  The caller raises, as torch's BCELoss does, when a -1 target survives.
+ *   pad_indicator are masked (ordinal.py:41).  status : [1] device int out or NULL: bit 0 = a target below 0 reached the
+ *   BCE (a -1 label: with_ordinals is called with its default padding value), bit 1 = an element of
+ *   y_pred lies outside [0, 1] (or is NaN) -- the two conditions torch's BCELoss raises on; the caller raises.
  */
 int ltr_ordinal_fwdbwd(const float* y_pred, const float* y_true, int B, int n, int levels, float pad_indicator,
-                       float* loss, float* grad, void* workspace, void* stream);
+                       float* loss, int* status, float* grad, void* workspace, void* stream);
 
 /* tie rules of the sorting entry points */
 #define LTR_TIES_STABLE 0   /* equal keys in ascending index order: python sorted(reverse=True), metrics.py:51 */
@@ -130,6 +132,14 @@ int ltr_ndcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, co
                       void* stream);
 
 /*
+ * DCG@k, fp64 (the un-normalised sum).        replaces utils/metrics.py:48-66 (dcg)
+ *   out[q, j] = sum_{r < min(k_j, n)} gain(y_true[q, order_r]) / log2(2 + r), order = y_pred sorted descending with
+ *   `tie_rule`; same arguments as ltr_ndcg_at_k_f64 (no empty_value: nothing is divided).
+ */
+int ltr_dcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
+                     int exponential_gains, const double* disc64, double* out, int* flags, void* stream);
+
+/*
  * exactNDCG "loss", forward only.             replaces losses/exactNDCG.py:5-29 (ndcgLoss; y_true FIRST)
  *   slate_value [B] = -dcg/idcg on softmaxed labels ordered by softmax(y_pred), discount ln(r) + 1; loss [1] = mean.
  */
@@ -154,7 +164,8 @@ int ltr_order_score_fwdbwd(const float* y_true, const float* y_pred, int B, int 
 
 /*
  * LambdaLoss framework, fused forward + backward.   replaces losses/lambdaL.py:7-93 (lambdaMask + lambdaLoss)
- *   y_pred, y_true : [B, n], n <= 2048; k <= 0: no NDCG@k truncation
+ *   y_pred, y_true : [B, n], n <= 2048; k < 0 (the reference's k=None) or k >= n: no NDCG@k truncation; k = 0: no pair
+ *   lies inside the truncation (sum 0, mean NaN), as the reference's [:0, :0] mask gives (lambdaL.py:29-30)
  *   slate_sum, slate_count : [B] out, sum / number of the masked pair log-probabilities of each slate
  *   loss       : [1] out, -sum (reduction_mean = 0) or -sum/count over the whole batch (lambdaL.py:86-89)
  *   pair_count : [1] out or NULL, number of masked pairs in the batch
@@ -200,10 +211,16 @@ int ltr_risk_lambda_rows_bwd(const float* y_pred, const float* y_true, int B, in
  * lambdaMask.                                 replaces losses/lambdaL.py:7-64
  *   logp : [B, n, n] out, log-probability of every pair of rank positions (the return_losses=True result);
  *   mask : [B, n, n] bytes out or NULL, 1 where the pair enters lambdaLoss (label_i > label_j, both real, both < k).
+ *   k as in ltr_lambda_fwdbwd (k < 0: none).
+ * ltr_lambda_pair_matrix_bwd: grad [B, n] = d L / d y_pred given grad_logp [B, n, n] = d L / d logp (rank order); the
+ *   weights carry no gradient (lambdaL.py:44-47), padded docs get 0.
  */
 int ltr_lambda_pair_matrix(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value, int scheme,
                            int k, float sigma, float mu, int natural_log, float* logp, unsigned char* mask,
                            void* stream);
+int ltr_lambda_pair_matrix_bwd(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value,
+                               int scheme, int k, float sigma, float mu, int natural_log, const float* grad_logp,
+                               float* grad, void* stream);
 
 /*
  * zRisk / geoRisk / tRisk over a query x system matrix.   replaces losses/riskLosses/riskFunctions.py:4-33 and the
@@ -218,6 +235,13 @@ int ltr_lambda_pair_matrix(const float* y_pred, const float* y_true, int B, int 
 int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int invert, int return_strategy,
                    int precedence_quirk, float alpha, float negative, double* state1, double* state2, float* loss,
                    float* gq, float* gmat, void* stream);
+
+/*
+ * GeoRisk of every system column, fp64.       replaces utils/metrics.py:8-45 (getGeoRiskDefault)
+ *   mat : [Q, C] device DOUBLES (queries x systems); out : [C] device doubles.  An entry whose expected value
+ *   S_i T_q / N is 0 contributes z = 0 (the reference's guard, :31-34); z is scaled by 1 + alpha where x < e.
+ */
+int ltr_georisk_default_f64(const double* mat, int Q, int C, double alpha, double* out, void* stream);
 
 /*
  * geoRisk / zRisk / tRisk ListNet loss, forward + backward in one call on one GPU (no exchange between the phases).

@@ -328,14 +328,11 @@ __global__ void __launch_bounds__(THREADS) approx_ndcg_kernel(const ApproxParams
 template <int THREADS>
 static int launch_approx(const ApproxParams& p, cudaStream_t st) {
     const size_t smem = (size_t)p.npad * 5 * sizeof(float);
-    static size_t attr_smem = 0;
-    static int occ_cached = 0;
+    static int occ_cached = 0;               // (occupancy is a property of the kernel image: the same on every B200)
     static size_t occ_smem = (size_t)-1;
-    if (smem > 48 * 1024 && smem > attr_smem) {
+    if (smem > 48 * 1024)                    // a per-device function attribute: set per call, not cached per process
         LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_kernel<THREADS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        attr_smem = smem;
-    }
     if (occ_smem != smem) {
         LTR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, approx_ndcg_kernel<THREADS, 0>, THREADS,
                                                                smem));
@@ -430,12 +427,9 @@ static int launch_approx_cluster(const ApproxParams& p, cudaStream_t st) {
     cfg.blockDim = dim3(CL_THREADS);
     cfg.dynamicSmemBytes = sizeof(ClShared);
     cfg.stream = st;
-    static bool attr_done = false;
-    if (!attr_done) {
-        LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(ClShared)));
-        attr_done = true;
-    }
+    // a per-device function attribute: set on every call (cheap), never cached in a process-wide flag
+    LTR_CUDA(cudaFuncSetAttribute(approx_ndcg_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(ClShared)));
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL_CTAS;

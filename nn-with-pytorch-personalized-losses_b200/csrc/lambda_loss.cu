@@ -24,7 +24,7 @@ constexpr int LAMBDA_MAX_N = 2048;
 struct LambdaParams {
     const float* y_pred;
     const float* y_true;
-    int B, n, len, k;           // k <= 0: no truncation
+    int B, n, len, k;           // k < 0: no truncation; k = 0: nothing inside the truncation (lambdaL.py:29-30)
     float eps, pad, sigma, mu;
     int natural_log;            // 0: log2, 1: ln
     float* slate_sum;           // [B] sum of the masked pair log-probabilities of the slate
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         __syncthreads();
         const int m = sh_m;
         block_sort_desc(K, I, Y, n, len, TIES_STDSORT, m);
-        const int kk = (p.k > 0 && p.k < n) ? p.k : n;
+        const int kk = (p.k >= 0 && p.k < n) ? p.k : n;
         const bool hist = !sh_lvl[0];
         // labels 0..4: level L fills the ideal ranks [e_{L+1}, e_L), e_L = #docs with label >= L, so the label at ideal
         // rank r is the number of levels with e_L > r; other labels: ideal order by a bitonic sort of the label values

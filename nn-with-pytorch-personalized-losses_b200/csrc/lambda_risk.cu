@@ -244,7 +244,39 @@ struct PairMatrixParams {
     int natural_log;
     float* logp;           // [B, n, n]
     unsigned char* mask;   // [B, n, n] or null
+    const float* glogp;    // backward: [B, n, n] upstream d L / d logp (rank order)
+    float* grad;           // backward: [B, n] d L / d y_pred
 };
+
+// ranking prologue of lambdaMask (lambdaL.py:10-40) for slate b: scores / labels with the padded docs at -inf, sort with
+// torch.sort's tie order, ideal DCG@k, labels and gains in rank order.  On exit K = scores in rank order, I = permutation,
+// Y = labels in rank order, G = gains / maxDCG.  k < 0 (or >= n): no truncation; k = 0: maxDCG = eps (an empty sum).
+__device__ __forceinline__ float pm_rank_prologue(LrSmem& sm, const PairMatrixParams& p, int b, float* red) {
+    const int n = p.n;
+    const float ninf = __int_as_float(0xff800000);
+    const float* yp = p.y_true + (size_t)b * n;
+    for (int i = threadIdx.x; i < n; i += LR_THREADS) {
+        const bool pad = (yp[i] == p.pad);
+        sm.K[i] = pad ? ninf : p.y_pred[(size_t)b * n + i];
+        sm.pt[i] = pad ? ninf : yp[i];
+    }
+    __syncthreads();
+    block_sort_desc(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
+    for (int i = threadIdx.x; i < p.len; i += LR_THREADS) sm.G[i] = (i < n) ? sm.pt[i] : ninf;
+    block_bitonic_desc(sm.G, p.len);
+    const int kk = (p.k >= 0 && p.k < n) ? p.k : n;
+    float part = 0.f;
+    for (int r = threadIdx.x; r < kk; r += LR_THREADS) part += (exp2f(fmaxf(sm.G[r], 0.f)) - 1.0f) * sm.invD[r];
+    const float maxdcg = fmaxf(lr_block_sum(part, red), p.eps);
+    __syncthreads();
+    for (int r = threadIdx.x; r < n; r += LR_THREADS) {
+        const float y = sm.pt[sm.I[r]];
+        sm.Y[r] = y;
+        sm.G[r] = (exp2f(fmaxf(y, 0.f)) - 1.0f) / maxdcg;
+    }
+    __syncthreads();
+    return maxdcg;
+}
 
 template <int SCHEME>
 __global__ void __launch_bounds__(LR_THREADS) lambda_pair_matrix_kernel(const PairMatrixParams p) {
@@ -258,28 +290,9 @@ __global__ void __launch_bounds__(LR_THREADS) lambda_pair_matrix_kernel(const Pa
     const float out_scale = p.natural_log ? kLn2 : 1.0f;
     lr_tables(sm, n);
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        const float* yp = p.y_true + (size_t)b * n;
-        for (int i = threadIdx.x; i < n; i += LR_THREADS) {
-            const bool pad = (yp[i] == p.pad);
-            sm.K[i] = pad ? ninf : p.y_pred[(size_t)b * n + i];
-            sm.pt[i] = pad ? ninf : yp[i];
-        }
-        __syncthreads();
-        // same ranking prologue as lambda_kernel, with the raw labels as "pt"
-        block_sort_desc(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
-        for (int i = threadIdx.x; i < p.len; i += LR_THREADS) sm.G[i] = (i < n) ? sm.pt[i] : ninf;
-        block_bitonic_desc(sm.G, p.len);
-        const int kk = (p.k > 0 && p.k < n) ? p.k : n;
-        float part = 0.f;
-        for (int r = threadIdx.x; r < kk; r += LR_THREADS) part += (exp2f(fmaxf(sm.G[r], 0.f)) - 1.0f) * sm.invD[r];
-        const float maxdcg = fmaxf(lr_block_sum(part, red), p.eps);
-        __syncthreads();
-        for (int r = threadIdx.x; r < n; r += LR_THREADS) {
-            const float y = sm.pt[sm.I[r]];
-            sm.Y[r] = y;
-            sm.G[r] = (exp2f(fmaxf(y, 0.f)) - 1.0f) / maxdcg;
-        }
-        __syncthreads();
+        const float maxdcg = pm_rank_prologue(sm, p, b, red);
+        const int kk = (p.k >= 0 && p.k < n) ? p.k : n;
+        (void)maxdcg;
         for (int idx = threadIdx.x; idx < n * n; idx += LR_THREADS) {
             const int i = idx / n, j = idx - i * n;
             float l, dl;
@@ -293,6 +306,45 @@ __global__ void __launch_bounds__(LR_THREADS) lambda_pair_matrix_kernel(const Pa
                 ok = ok && (i < kk) && (j < kk);                                          // :29-30
                 p.mask[((size_t)b * n + i) * n + j] = ok ? 1 : 0;
             }
+        }
+        __syncthreads();
+    }
+}
+
+// backward of lambdaMask w.r.t. y_pred: logp[i, j] depends on the scores through delta = s_i - s_j only (the weights are
+// functions of the labels and the rank positions, lambdaL.py:44-47 carry no gradient), so with u = glogp * d logp / d delta
+//   d L / d s_(rank r) = sum_j u[r, j] - sum_i u[i, r];   padded docs get 0 (their scores are overwritten, :13).
+// Thread r owns rank r.
+template <int SCHEME>
+__global__ void __launch_bounds__(LR_THREADS) lambda_pair_matrix_bwd_kernel(const PairMatrixParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[32];
+    LrSmem sm(smem_raw, p.len);
+    const int n = p.n;
+    const float ninf = __int_as_float(0xff800000);
+    const float sig_scale = p.sigma * kLog2e;
+    const float log_eps2 = log2f(p.eps);
+    const float out_scale = p.natural_log ? kLn2 : 1.0f;
+    const float dscale = p.sigma * (p.natural_log ? 1.0f : 1.0f / kLn2);    // d log_b(sig^w) / d delta = w sigma (1 - sig) / ln b
+    lr_tables(sm, n);
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        pm_rank_prologue(sm, p, b, red);
+        const float* g = p.glogp + (size_t)b * n * n;
+        for (int r = threadIdx.x; r < n; r += LR_THREADS) {
+            float acc = 0.f;
+            const float sr = sm.K[r];
+            if (sr != ninf) {
+                for (int j = 0; j < n; ++j) {
+                    float l, dl;
+                    pair_logprob<true>(sr - sm.K[j], pair_weight<SCHEME>(r, j, sm.G, sm.invD, sm.dtab, sm.Y, p.mu), sig_scale,
+                                       log_eps2, out_scale, l, dl);
+                    acc = fmaf(g[(size_t)r * n + j], dl, acc);
+                    pair_logprob<true>(sm.K[j] - sr, pair_weight<SCHEME>(j, r, sm.G, sm.invD, sm.dtab, sm.Y, p.mu), sig_scale,
+                                       log_eps2, out_scale, l, dl);
+                    acc = fmaf(-g[(size_t)j * n + r], dl, acc);
+                }
+            }
+            p.grad[(size_t)b * n + sm.I[r]] = acc * dscale;
         }
         __syncthreads();
     }
@@ -330,9 +382,32 @@ static int lr_dispatch(int scheme, int which, const LambdaRiskParams& p, size_t 
 
 template <int SCHEME>
 static int pm_launch(const PairMatrixParams& p, size_t smem, int grid, cudaStream_t st) {
+    if (p.grad) {
+        if (int rc = lr_prepare(lambda_pair_matrix_bwd_kernel<SCHEME>, smem)) return rc;
+        lambda_pair_matrix_bwd_kernel<SCHEME><<<grid, LR_THREADS, smem, st>>>(p);
+        return 0;
+    }
     if (int rc = lr_prepare(lambda_pair_matrix_kernel<SCHEME>, smem)) return rc;
     lambda_pair_matrix_kernel<SCHEME><<<grid, LR_THREADS, smem, st>>>(p);
     return 0;
+}
+
+static int pm_dispatch(int scheme, const PairMatrixParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)p.len * LR_ARRAYS * sizeof(float);
+    const int cap = device_sm_count() * 8;
+    const int grid = p.B < cap ? p.B : cap;
+    int rc;
+    switch (scheme) {
+        case SCHEME_NONE: rc = pm_launch<SCHEME_NONE>(p, smem, grid, st); break;
+        case SCHEME_NDCG1: rc = pm_launch<SCHEME_NDCG1>(p, smem, grid, st); break;
+        case SCHEME_NDCG2: rc = pm_launch<SCHEME_NDCG2>(p, smem, grid, st); break;
+        case SCHEME_LAMBDARANK: rc = pm_launch<SCHEME_LAMBDARANK>(p, smem, grid, st); break;
+        case SCHEME_NDCG2PP: rc = pm_launch<SCHEME_NDCG2PP>(p, smem, grid, st); break;
+        case SCHEME_GTDIFF: rc = pm_launch<SCHEME_GTDIFF>(p, smem, grid, st); break;
+        default: rc = pm_launch<SCHEME_GTDIFF_POW>(p, smem, grid, st); break;
+    }
+    if (rc) return rc;
+    return (int)cudaGetLastError();
 }
 
 static int lr_len(int n) {
@@ -384,22 +459,19 @@ LTR_API int ltr_lambda_pair_matrix(const float* y_pred, const float* y_true, int
     if (!y_pred || !y_true || !logp || B <= 0 || n <= 0 || scheme < 0 || scheme > 6)
         return set_error(LTR_EINVAL, "ltr_lambda_pair_matrix: bad arguments");
     if (n > LR_MAX_N) return set_error(LTR_ETOOBIG, "ltr_lambda_pair_matrix: slate too long");
-    PairMatrixParams p{y_pred, y_true, B, n, lr_len(n), k, eps, pad_value, sigma, mu, natural_log, logp, mask};
-    const size_t smem = (size_t)p.len * LR_ARRAYS * sizeof(float);
-    const int cap = device_sm_count() * 8;
-    const int grid = B < cap ? B : cap;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int rc;
-    switch (scheme) {
-        case SCHEME_NONE: rc = pm_launch<SCHEME_NONE>(p, smem, grid, st); break;
-        case SCHEME_NDCG1: rc = pm_launch<SCHEME_NDCG1>(p, smem, grid, st); break;
-        case SCHEME_NDCG2: rc = pm_launch<SCHEME_NDCG2>(p, smem, grid, st); break;
-        case SCHEME_LAMBDARANK: rc = pm_launch<SCHEME_LAMBDARANK>(p, smem, grid, st); break;
-        case SCHEME_NDCG2PP: rc = pm_launch<SCHEME_NDCG2PP>(p, smem, grid, st); break;
-        case SCHEME_GTDIFF: rc = pm_launch<SCHEME_GTDIFF>(p, smem, grid, st); break;
-        default: rc = pm_launch<SCHEME_GTDIFF_POW>(p, smem, grid, st); break;
-    }
-    if (rc) return rc;
-    rc = (int)cudaGetLastError();
+    PairMatrixParams p{y_pred, y_true, B, n, lr_len(n), k, eps, pad_value, sigma, mu, natural_log, logp, mask, nullptr, nullptr};
+    const int rc = pm_dispatch(scheme, p, reinterpret_cast<cudaStream_t>(stream));
     return rc ? set_cuda_error(rc, "ltr_lambda_pair_matrix") : 0;
+}
+
+LTR_API int ltr_lambda_pair_matrix_bwd(const float* y_pred, const float* y_true, int B, int n, float eps, float pad_value,
+                                       int scheme, int k, float sigma, float mu, int natural_log, const float* grad_logp,
+                                       float* grad, void* stream) {
+    using namespace ltr;
+    if (!y_pred || !y_true || !grad_logp || !grad || B <= 0 || n <= 0 || scheme < 0 || scheme > 6)
+        return set_error(LTR_EINVAL, "ltr_lambda_pair_matrix_bwd: bad arguments");
+    if (n > LR_MAX_N) return set_error(LTR_ETOOBIG, "ltr_lambda_pair_matrix_bwd: slate too long");
+    PairMatrixParams p{y_pred, y_true, B, n, lr_len(n), k, eps, pad_value, sigma, mu, natural_log, nullptr, nullptr, grad_logp, grad};
+    const int rc = pm_dispatch(scheme, p, reinterpret_cast<cudaStream_t>(stream));
+    return rc ? set_cuda_error(rc, "ltr_lambda_pair_matrix_bwd") : 0;
 }

@@ -178,13 +178,14 @@ struct OrdinalParams {
     int L;
     float pad_indicator;
     float* grad;         // [B, n, L] or null (unscaled on exit of ordinal_kernel)
-    float* sums;         // [2]: BCE sum, valid docs
+    float* sums;         // [4]: BCE sum, valid docs, #targets < 0, #inputs outside [0, 1]
     double* partials;
     unsigned* counter;
 };
 
 __global__ void __launch_bounds__(STREAM_THREADS) ordinal_kernel(const OrdinalParams p) {
     double bce = 0.0, cnt = 0.0;
+    int bad_t = 0, bad_in = 0;
     const long long stride = (long long)gridDim.x * STREAM_THREADS;
     for (long long d = (long long)blockIdx.x * STREAM_THREADS + threadIdx.x; d < p.docs; d += stride) {
         const float y = p.y_true[d];
@@ -193,8 +194,11 @@ __global__ void __launch_bounds__(STREAM_THREADS) ordinal_kernel(const OrdinalPa
         float doc = 0.f;
         int any = 0;
         for (int l = 0; l < p.L; ++l) {
+            // torch's BCELoss validates EVERY element before the mask is applied (ordinal.py:44-47)
+            bad_in += !(pr[l] >= 0.0f && pr[l] <= 1.0f);
             float t = (y >= (float)(l + 1)) ? 1.0f : 0.0f;
             if (y == -1.0f) t = -1.0f;                               // with_ordinals' own padding value
+            bad_t += (t < 0.0f);                                     // a -1 target reaches BCELoss
             const bool masked = (t == p.pad_indicator);
             const float x = pr[l];
             float gl = 0.f;
@@ -209,15 +213,18 @@ __global__ void __launch_bounds__(STREAM_THREADS) ordinal_kernel(const OrdinalPa
         bce += (double)doc;
         cnt += (double)any;
     }
-    double vals[STREAM_MAX_OUT] = {bce, cnt, 0.0, 0.0};
+    double vals[STREAM_MAX_OUT] = {bce, cnt, (double)bad_t, (double)bad_in};
     const double scale[STREAM_MAX_OUT] = {1.0, 1.0, 1.0, 1.0};
-    stream_finish(vals, 2, p.partials, p.counter, p.sums, scale, nullptr);
+    stream_finish(vals, 4, p.partials, p.counter, p.sums, scale, nullptr);
 }
 
-// loss[0] = sums[0] / sums[1]; grad *= 1 / sums[1]
-__global__ void ordinal_scale_kernel(const float* sums, float* loss, float* grad, long long total) {
+// loss[0] = sums[0] / sums[1]; grad *= 1 / sums[1]; status[0] = 1 (a target < 0) | 2 (an input outside [0, 1])
+__global__ void ordinal_scale_kernel(const float* sums, float* loss, int* status, float* grad, long long total) {
     const float inv = 1.0f / sums[1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) loss[0] = sums[0] / sums[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        loss[0] = sums[0] / sums[1];
+        if (status) status[0] = (sums[2] > 0.f ? 1 : 0) | (sums[3] > 0.f ? 2 : 0);
+    }
     if (!grad) return;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) grad[i] *= inv;
@@ -274,7 +281,7 @@ LTR_API int ltr_listnet_fwdbwd(const float* y_true, const float* y_pred, int B, 
 }
 
 LTR_API int ltr_ordinal_fwdbwd(const float* y_pred, const float* y_true, int B, int n, int levels, float pad_indicator,
-                               float* loss, float* grad, void* workspace, void* stream) {
+                               float* loss, int* status, float* grad, void* workspace, void* stream) {
     using namespace ltr;
     if (!y_pred || !y_true || !loss || !workspace || B <= 0 || n <= 0 || levels <= 0)
         return set_error(LTR_EINVAL, "ltr_ordinal_fwdbwd: null pointer or non-positive size");
@@ -284,7 +291,7 @@ LTR_API int ltr_ordinal_fwdbwd(const float* y_pred, const float* y_true, int B, 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = stream_grid(((long long)B * n + 31) / 32);
     ordinal_kernel<<<grid, STREAM_THREADS, 0, st>>>(p);
-    ordinal_scale_kernel<<<grid, STREAM_THREADS, 0, st>>>(sums, loss, grad, (long long)B * n * levels);
+    ordinal_scale_kernel<<<grid, STREAM_THREADS, 0, st>>>(sums, loss, status, grad, (long long)B * n * levels);
     const int rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_ordinal_fwdbwd") : 0;
 }

@@ -16,7 +16,7 @@ int upload_disc_prefix_constant();                   // P[0..128] -> the constan
 //   u32 [0..4]    approxNDCG: next-slate counter, finished-CTA counter, 64-bit fixed-point loss sum, non-finite flag
 //   u32 [16]      streaming kernels: finished-CTA counter
 //   u32 [18]      LambdaLoss: next-slate counter
-//   f32 [32..33]  ordinal: BCE sum, number of valid docs
+//   f32 [32..35]  ordinal: BCE sum, number of valid docs, #targets < 0, #inputs outside [0, 1]
 //   byte 1024 ..  streaming kernels: per-CTA fp64 partial sums, [grid <= 2048][4]
 constexpr int LTR_WS_STREAM_COUNTER = 16;
 constexpr int LTR_WS_LAMBDA_COUNTER = 18;             // LambdaLoss: next-slate counter

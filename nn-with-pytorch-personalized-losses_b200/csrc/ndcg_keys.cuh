@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
                         got += term64[8 * r + ((pred_lab >> (3 * r)) & 7u)];
                         ideal += term64[8 * r + ((ideal_lab >> (3 * r)) & 7u)];
                         if ((kends >> r) & 1u) {
-                            const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
+                            const double val = p.raw_dcg ? got : ((ideal == 0.0) ? p.empty_value : got / ideal);
                             for (int j = 0; j < p.nk; ++j)
                                 if (p.ks[j] == r + 1) out[j] = val;
                         }

@@ -79,403 +79,6 @@ __device__ __forceinline__ float tpq_select11(float (&v)[32]) {
     return v[TPQ_K - 1];
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Rows of one chunk (n <= 128), third generation: the scores never go to shared memory.
-//   phase 1 (lane = 4 docs of one row): only the quad MAXIMA of the row (32 floats) and the 4-bit label codes are
-//     kept (6.8 KB per tile instead of 19 KB: 16 warps per SM, so 65,536 queries are one resident wave);
-//   phase 2 (lane = one query): a Batcher network (pruned to its first 11 outputs) sorts the 32 (quad maximum, quad
-//     index) pairs; the 11th is the bound L; the top-11 docs of the row live in those 11 quads, which the lane reads
-//     back from L2 (11 independent 16-byte loads): the maximum of each is already in its sorted place, and only the
-//     other docs >= L of those quads (1.6 per query on average) are inserted.
-constexpr int QMX_CTAS = 4;
-constexpr int QMX_BATCH = 4;               // rows per load batch, double buffered (two 128-bit loads per row and lane)
-
-struct QmxTile {
-    float qm[32 * TPQ_Q_STRIDE];
-    unsigned short lab[32 * TPQ_L_STRIDE];
-};
-constexpr size_t QMX_SMEM = sizeof(QmxTile) * TPQ_WARPS;
-
-template <bool F64>
-__global__ void __launch_bounds__(TPQ_THREADS, QMX_CTAS) ndcg_qmax_kernel(const NdcgParams p) {
-    extern __shared__ __align__(16) unsigned char tpq_smem[];
-    // term[r][l] = gain(l) / discount(r) for ranks r < 10 and labels l <= 4, divided exactly as the reference divides
-    __shared__ double term64[F64 ? (TPQ_K - 1) * 5 : 1];
-    __shared__ float term32[F64 ? 1 : (TPQ_K - 1) * 5];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    QmxTile& tile = reinterpret_cast<QmxTile*>(tpq_smem)[warp];
-    const int gwarp = (int)blockIdx.x * TPQ_WARPS + warp;
-    const int nwarps = (int)gridDim.x * TPQ_WARPS;
-    const int ntiles = (p.B + 31) >> 5;
-    const int n = p.n;
-    const float ninf = __int_as_float(0xff800000);
-    const bool lane_in = 4 * lane < n;                     // this lane's quad exists (n % 4 == 0)
-    unsigned kends = 0;                                    // bit r: some k of the sweep equals r + 1
-    for (int j = 0; j < p.nk; ++j) kends |= 1u << (p.ks[j] - 1);
-    pdl_prologue();
-    if ((int)threadIdx.x < (TPQ_K - 1) * 5) {
-        const int r = (int)threadIdx.x / 5, l = (int)threadIdx.x % 5;
-        if (r < p.kmax) {
-            if (F64) term64[threadIdx.x] = (p.exp_gains ? (double)((1 << l) - 1) : (double)l) / p.disc64[r];
-            else term32[threadIdx.x] = (float)((1 << l) - 1) / p.disc32[r];
-        }
-    }
-    __syncthreads();
-
-    float4 s4[QMX_BATCH], y4[QMX_BATCH];
-    auto issue_batch = [&](int qbase) {
-        const float* sp = p.y_pred + (size_t)qbase * n + 4 * lane;
-        const float* yp = p.y_true + (size_t)qbase * n + 4 * lane;
-#pragma unroll
-        for (int i = 0; i < QMX_BATCH; ++i) {
-            s4[i] = make_float4(ninf, ninf, ninf, ninf);
-            y4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (qbase + i < p.B && lane_in) {
-                s4[i] = ld_stream4(sp + i * n);
-                y4[i] = ld_stream4(yp + i * n);
-            }
-        }
-    };
-    if (gwarp < ntiles) issue_batch(gwarp << 5);
-
-    for (int t = gwarp; t < ntiles; t += nwarps) {
-        const int q0 = t << 5;
-        // ---------------- phase 1: quad maxima and label codes -> shared memory, per-row histogram and flag -------
-        unsigned myhist = 0;
-        int mybad = 0;
-#pragma unroll 1
-        for (int rb = 0; rb < 32; rb += QMX_BATCH) {
-            float4 sc[QMX_BATCH], yc[QMX_BATCH];
-#pragma unroll
-            for (int i = 0; i < QMX_BATCH; ++i) sc[i] = s4[i], yc[i] = y4[i];
-            // next batch of this tile, or the first batch of this warp's next tile (B bounds it)
-            issue_batch(rb < 32 - QMX_BATCH ? q0 + rb + QMX_BATCH : ((t + nwarps < ntiles) ? ((t + nwarps) << 5) : p.B));
-            unsigned badbits = 0;
-#pragma unroll
-            for (int i = 0; i < QMX_BATCH; ++i) {
-                const int r = rb + i;
-                const float qmax = max_nan(max_nan(sc[i].x, sc[i].y), max_nan(sc[i].z, sc[i].w));
-                tile.qm[r * TPQ_Q_STRIDE + lane] = qmax;
-                const float ys[4] = {yc[i].x, yc[i].y, yc[i].z, yc[i].w};
-                unsigned hist = 0, word = 0;
-                bool ok = !(qmax != qmax);                                    // a NaN score sends the query to the full sort
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const unsigned v = __float2uint_rz(ys[c]);                // negative / NaN -> 0, huge -> 2^32 - 1
-                    ok = ok && ((float)v == ys[c]) && (v <= 4u);
-                    hist += shr_clamp(0x01000000u, 32u - 8u * v);            // level L counts in byte L - 1; level 0: nothing
-                    word += (v & 0xfu) << (4 * c);
-                }
-                tile.lab[r * TPQ_L_STRIDE + lane] = (unsigned short)word;
-                badbits |= ok ? 0u : (1u << i);
-                const unsigned rowhist = __reduce_add_sync(LTR_FULL_MASK, hist);
-                myhist = (lane == r) ? rowhist : myhist;
-            }
-            badbits = __reduce_or_sync(LTR_FULL_MASK, badbits);      // one vote per batch
-            if (lane / QMX_BATCH == rb / QMX_BATCH) mybad = (int)((badbits >> (lane % QMX_BATCH)) & 1u);
-        }
-        __syncwarp();
-
-        // ---------------- phase 2: one query per lane --------------------------------------------------
-        const int q = q0 + lane;
-        const float* row = p.y_pred + (size_t)min(q, p.B - 1) * n;
-        float v[32];
-        int id[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 m4 = *reinterpret_cast<const float4*>(&tile.qm[lane * TPQ_Q_STRIDE + 4 * j]);
-            v[4 * j] = m4.x; v[4 * j + 1] = m4.y; v[4 * j + 2] = m4.z; v[4 * j + 3] = m4.w;
-            id[4 * j] = 4 * j; id[4 * j + 1] = 4 * j + 1; id[4 * j + 2] = 4 * j + 2; id[4 * j + 3] = 4 * j + 3;
-        }
-#define TPQ_CEP(a, b)                                   \
-    {                                                   \
-        const bool sw_ = v[b] > v[a];                   \
-        const float hi_ = sw_ ? v[b] : v[a];            \
-        const float lo_ = sw_ ? v[a] : v[b];            \
-        const int ih_ = sw_ ? id[b] : id[a];            \
-        const int il_ = sw_ ? id[a] : id[b];            \
-        v[a] = hi_; v[b] = lo_; id[a] = ih_; id[b] = il_; \
-    }
-#include "ndcg_top11_32.inc"
-#undef TPQ_CEP
-        const float L = v[TPQ_K - 1];
-        // the 11 quads back from L2: their maxima are top[0..10] already; everything else >= L in them is an "extra"
-        float4 x[TPQ_K];
-#pragma unroll
-        for (int i = 0; i < TPQ_K; ++i) {
-            x[i] = make_float4(ninf, ninf, ninf, ninf);
-            if (4 * id[i] < n) x[i] = *reinterpret_cast<const float4*>(row + 4 * id[i]);
-        }
-        float top[TPQ_K];
-        int lab[TPQ_K];
-        unsigned long long extras = 0;                   // bit 4 i + c: doc c of the i-th quad is >= L and not its maximum
-        unsigned qlo = 0, qhi = 0;                       // the quad indices again, 5 bits each (slots 0..5 | 6..10)
-#pragma unroll
-        for (int i = 0; i < TPQ_K; ++i) {
-            const float mx = v[i];
-            const int c = (x[i].x == mx) ? 0 : ((x[i].y == mx) ? 1 : ((x[i].z == mx) ? 2 : 3));
-            const unsigned word = tile.lab[lane * TPQ_L_STRIDE + id[i]];
-            top[i] = mx + 0.0f;                                              // -0 -> +0
-            lab[i] = (4 * id[i] < n) ? (int)((word >> (4 * c)) & 0xfu) : 0;
-            unsigned e = 0;
-            e |= (x[i].x >= L) ? 1u : 0u;
-            e |= (x[i].y >= L) ? 2u : 0u;
-            e |= (x[i].z >= L) ? 4u : 0u;
-            e |= (x[i].w >= L) ? 8u : 0u;
-            e &= ~(1u << c);
-            if (4 * id[i] >= n) e = 0;
-            extras |= (unsigned long long)e << (4 * i);
-            if (i < 6) qlo += (unsigned)id[i] << (5 * i);
-            else qhi += (unsigned)id[i] << (5 * (i - 6));
-        }
-        while (extras) {
-            const int bit = __ffsll((long long)extras) - 1;
-            extras &= extras - 1;
-            const int slot = bit >> 2, c = bit & 3;
-            const int j = (int)(((slot < 6) ? (qlo >> (5 * slot)) : (qhi >> (5 * (slot - 6)))) & 31u);
-            const float xv = row[4 * j + c] + 0.0f;
-            const unsigned word = tile.lab[lane * TPQ_L_STRIDE + j];
-            tpq_insert<TPQ_K>(top, lab, xv, (int)((word >> (4 * c)) & 0xfu));
-        }
-        // a tie group that reaches into the first kmax ranks needs the reference's sort order
-        int bad = mybad;
-#pragma unroll
-        for (int j = 0; j + 1 < TPQ_K; ++j)
-            bad |= (j < p.kmax && j + 1 < n && top[j] == top[j + 1]) ? 1 : 0;
-        if (q < p.B) {
-            p.flags[1 + q] = bad;
-            if (!bad) {
-                // ideal order from the histogram: level L fills the ranks below #docs with label >= L
-                const int c4 = myhist >> 24, c3 = c4 + ((myhist >> 16) & 255), c2 = c3 + ((myhist >> 8) & 255),
-                          c1 = c2 + (myhist & 255);
-                if (!F64) {
-                    float got = 0.f, ideal = 0.f;
-                    float* out = p.out32 + (size_t)q * p.nk;
-#pragma unroll
-                    for (int r = 0; r < TPQ_K - 1; ++r) {
-                        if (r < p.kmax) {
-                            const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
-                            got += term32[5 * r + lab[r]];
-                            ideal += term32[5 * r + li];
-                            if ((kends >> r) & 1u) {
-                                const float val = got / ideal;
-                                for (int j = 0; j < p.nk; ++j)
-                                    if (p.ks[j] == r + 1) out[j] = val;
-                            }
-                        }
-                    }
-                } else {
-                    double got = 0.0, ideal = 0.0;
-                    double* out = p.out64 + (size_t)q * p.nk;
-#pragma unroll
-                    for (int r = 0; r < TPQ_K - 1; ++r) {
-                        if (r < p.kmax) {
-                            const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
-                            got += term64[5 * r + lab[r]];
-                            ideal += term64[5 * r + li];
-                            if ((kends >> r) & 1u) {
-                                const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
-                                for (int j = 0; j < p.nk; ++j)
-                                    if (p.ks[j] == r + 1) out[j] = val;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();                                            // the tile is free for the next phase 1
-    }
-}
-
-// Rows of one chunk (n <= 128): four independent tiles per CTA, three CTAs per SM.  (Kept separate from the chunked
-// kernel below: carrying the per-query state across chunks costs registers this one does not have to spare.)
-template <bool F64>
-__global__ void __launch_bounds__(TPQ_THREADS, TPQ_CTAS) ndcg_tpq_kernel(const NdcgParams p) {
-    extern __shared__ __align__(16) unsigned char tpq_smem[];
-    // term[r][l] = gain(l) / discount(r) for ranks r < 10 and labels l <= 4, divided exactly as the reference divides
-    __shared__ double term64[F64 ? (TPQ_K - 1) * 5 : 1];
-    __shared__ float term32[F64 ? 1 : (TPQ_K - 1) * 5];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TpqTile& tile = reinterpret_cast<TpqTile*>(tpq_smem)[warp];
-    const int gwarp = (int)blockIdx.x * TPQ_WARPS + warp;
-    const int nwarps = (int)gridDim.x * TPQ_WARPS;
-    const int ntiles = (p.B + 31) >> 5;
-    const int n = p.n;
-    const float ninf = __int_as_float(0xff800000);
-    const bool lane_in = 4 * lane < n;                     // this lane's quad exists (n % 4 == 0)
-    unsigned long long nmask[2];                           // docs < n, per 64-doc word
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        const int left = n - 64 * w;
-        nmask[w] = left >= 64 ? ~0ull : (left <= 0 ? 0ull : ((1ull << left) - 1ull));
-    }
-    unsigned kends = 0;                                    // bit r: some k of the sweep equals r + 1
-    for (int j = 0; j < p.nk; ++j) kends |= 1u << (p.ks[j] - 1);
-    pdl_prologue();
-    if ((int)threadIdx.x < (TPQ_K - 1) * 5) {
-        const int r = (int)threadIdx.x / 5, l = (int)threadIdx.x % 5;
-        if (r < p.kmax) {
-            if (F64) term64[threadIdx.x] = (p.exp_gains ? (double)((1 << l) - 1) : (double)l) / p.disc64[r];
-            else term32[threadIdx.x] = (float)((1 << l) - 1) / p.disc32[r];
-        }
-    }
-    __syncthreads();
-
-    // labels go through registers in batches of TPQ_BATCH rows, the next batch (of the next tile during phase 2)
-    // always in flight; scores go straight to shared memory with 16-byte asynchronous copies, a whole tile at once
-    float4 y4[TPQ_BATCH];
-    auto issue_labels = [&](int qbase) {
-        const float* yp = p.y_true + (size_t)qbase * n + 4 * lane;
-#pragma unroll
-        for (int i = 0; i < TPQ_BATCH; ++i) {
-            y4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (qbase + i < p.B && lane_in) y4[i] = ld_stream4(yp + i * n);
-        }
-    };
-    if (gwarp < ntiles) issue_labels(gwarp << 5);
-
-    for (int t = gwarp; t < ntiles; t += nwarps) {
-        const int q0 = t << 5;
-        // ---------------- phase 1: rows -> shared memory, per-row histogram and flag ----------------
-        {
-            const float* sp = p.y_pred + (size_t)q0 * n + 4 * lane;
-            const unsigned dst = smem_u32(&tile.s[4 * lane]);
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                if (q0 + r < p.B && lane_in)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * TPQ_S_STRIDE * 4), "l"(sp + r * n)
-                                 : "memory");
-                else
-                    *reinterpret_cast<float4*>(&tile.s[r * TPQ_S_STRIDE + 4 * lane]) = make_float4(ninf, ninf, ninf, ninf);
-            }
-        }
-        unsigned myhist = 0;
-        int mybad = 0;
-#pragma unroll 1
-        for (int rb = 0; rb < 32; rb += TPQ_BATCH) {
-            float4 yc[TPQ_BATCH];
-#pragma unroll
-            for (int i = 0; i < TPQ_BATCH; ++i) yc[i] = y4[i];
-            // next batch of this tile, or the first batch of this warp's next tile (B bounds it)
-            issue_labels(rb < 32 - TPQ_BATCH ? q0 + rb + TPQ_BATCH : ((t + nwarps < ntiles) ? ((t + nwarps) << 5) : p.B));
-            unsigned badbits = 0;
-#pragma unroll
-            for (int i = 0; i < TPQ_BATCH; ++i) {
-                const int r = rb + i;
-                const float ys[4] = {yc[i].x, yc[i].y, yc[i].z, yc[i].w};
-                unsigned hist = 0, word = 0;
-                bool ok = true;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const unsigned v = __float2uint_rz(ys[c]);                  // negative / NaN -> 0, huge -> 2^32 - 1
-                    ok = ok && ((float)v == ys[c]) && (v <= 4u);
-                    hist += shr_clamp(0x01000000u, 32u - 8u * v);              // level L counts in byte L - 1; level 0: nothing
-                    word |= (v & 0xfu) << (4 * c);
-                }
-                tile.lab[r * TPQ_L_STRIDE + lane] = (unsigned short)word;
-                badbits |= ok ? 0u : (1u << i);
-                const unsigned rowhist = __reduce_add_sync(LTR_FULL_MASK, hist);
-                myhist = (lane == r) ? rowhist : myhist;
-            }
-            badbits = __reduce_or_sync(LTR_FULL_MASK, badbits);      // one vote per batch
-            if (lane / TPQ_BATCH == rb / TPQ_BATCH) mybad = (int)((badbits >> (lane % TPQ_BATCH)) & 1u);
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncwarp();
-
-        // ---------------- phase 2: one query per lane --------------------------------------------------
-        const int q = q0 + lane;
-        const float* srow = &tile.s[lane * TPQ_S_STRIDE];
-        // lower bound of the TPQ_K-th largest score: the TPQ_K-th largest of the 32 quad maxima
-        float qm[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(srow + 4 * j);
-            qm[j] = max_nan(max_nan(x.x, x.y), max_nan(x.z, x.w));       // a NaN score sends the query to the full sort
-        }
-        bool anynan = false;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) anynan = anynan || (qm[j] != qm[j]);
-        const float L = tpq_select11(qm);
-        asm volatile("" ::: "memory");          // read the row again below rather than keeping 128 scores in registers
-        // candidate docs: score >= L
-        unsigned cand[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(srow + 4 * j);
-            unsigned& w = cand[j >> 3];
-            const int b0 = 4 * (j & 7);
-            w |= (x.x >= L) ? (1u << b0) : 0u;
-            w |= (x.y >= L) ? (2u << b0) : 0u;
-            w |= (x.z >= L) ? (4u << b0) : 0u;
-            w |= (x.w >= L) ? (8u << b0) : 0u;
-        }
-        float top[TPQ_K];
-        int lab[TPQ_K];
-#pragma unroll
-        for (int j = 0; j < TPQ_K; ++j) top[j] = ninf, lab[j] = 0;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            unsigned long long m = (((unsigned long long)cand[2 * w + 1] << 32) | cand[2 * w]) & nmask[w];
-            while (m) {
-                const int d = 64 * w + (__ffsll((long long)m) - 1);
-                m &= m - 1;
-                const float x = srow[d] + 0.0f;                                  // -0 -> +0
-                const unsigned word = tile.lab[lane * TPQ_L_STRIDE + (d >> 2)];
-                tpq_insert<TPQ_K>(top, lab, x, (int)((word >> (4 * (d & 3))) & 0xfu));
-            }
-        }
-        // a tie group that reaches into the first kmax ranks needs the reference's sort order
-        int bad = mybad | (anynan ? 1 : 0);
-#pragma unroll
-        for (int j = 0; j + 1 < TPQ_K; ++j)
-            bad |= (j < p.kmax && j + 1 < n && top[j] == top[j + 1]) ? 1 : 0;
-        if (q < p.B) {
-            p.flags[1 + q] = bad;
-            if (!bad) {
-                // ideal order from the histogram: level L fills the ranks below #docs with label >= L
-                const int c4 = myhist >> 24, c3 = c4 + ((myhist >> 16) & 255), c2 = c3 + ((myhist >> 8) & 255),
-                          c1 = c2 + (myhist & 255);
-                if (!F64) {
-                    float got = 0.f, ideal = 0.f;
-                    float* out = p.out32 + (size_t)q * p.nk;
-#pragma unroll
-                    for (int r = 0; r < TPQ_K - 1; ++r) {
-                        if (r < p.kmax) {
-                            const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
-                            got += term32[5 * r + lab[r]];
-                            ideal += term32[5 * r + li];
-                            if ((kends >> r) & 1u) {
-                                const float val = got / ideal;
-                                for (int j = 0; j < p.nk; ++j)
-                                    if (p.ks[j] == r + 1) out[j] = val;
-                            }
-                        }
-                    }
-                } else {
-                    double got = 0.0, ideal = 0.0;
-                    double* out = p.out64 + (size_t)q * p.nk;
-#pragma unroll
-                    for (int r = 0; r < TPQ_K - 1; ++r) {
-                        if (r < p.kmax) {
-                            const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
-                            got += term64[5 * r + lab[r]];
-                            ideal += term64[5 * r + li];
-                            if ((kends >> r) & 1u) {
-                                const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
-                                for (int j = 0; j < p.nk; ++j)
-                                    if (p.ks[j] == r + 1) out[j] = val;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();                                            // the tile is free for the next phase 1
-    }
-}
-
-
 // Rows longer than one 128-doc chunk (same two phases per chunk; the top-11 list and the label counts of a query are
 // carried from chunk to chunk).  C = warps that share one tile of 32 queries: the chunks of its rows are dealt chunk by chunk to the C
 // warps (C = 1: four independent tiles per CTA; C = 4: one tile per CTA, 8 chunks of a 1024-doc row = 2 per warp);
@@ -724,7 +327,7 @@ __global__ void __launch_bounds__(TPQ_THREADS, C == 1 ? TPQ_CTAS : 2) ndcg_tpq_w
                             got += term64[5 * r + lab[r]];
                             ideal += term64[5 * r + li];
                             if ((kends >> r) & 1u) {
-                                const double val = (ideal == 0.0) ? p.empty_value : got / ideal;
+                                const double val = p.raw_dcg ? got : ((ideal == 0.0) ? p.empty_value : got / ideal);
                                 for (int j = 0; j < p.nk; ++j)
                                     if (p.ks[j] == r + 1) out[j] = val;
                             }

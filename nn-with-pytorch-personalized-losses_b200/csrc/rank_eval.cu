@@ -74,6 +74,7 @@ struct NdcgParams {
     const float* y_true;
     const float* y_pred;
     int B, n, len, nk, tie_rule, exp_gains;
+    int raw_dcg;             // F64 only: write the DCG itself instead of DCG / ideal DCG (metrics.dcg, :48-66)
     int ks[RANK_MAX_K];
     const float* disc32;
     const double* disc64;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
                 got += (p.exp_gains ? exp2(lg) - 1.0 : lg) / d;
                 ideal += (p.exp_gains ? exp2(li) - 1.0 : li) / d;
             }
-            p.out64[(size_t)b * p.nk + grp_tid<WARP>()] = (ideal == 0.0) ? p.empty_value : got / ideal;
+            p.out64[(size_t)b * p.nk + grp_tid<WARP>()] = p.raw_dcg ? got : ((ideal == 0.0) ? p.empty_value : got / ideal);
         }
     }
     grp_sync<WARP>();
@@ -296,7 +297,7 @@ __device__ __forceinline__ void write_ndcg_sums(const NdcgParams& p, int b, int 
             got_k = mine ? got : got_k;
             ideal_k = mine ? ideal : ideal_k;
         }
-        if (myk > 0) p.out64[(size_t)b * p.nk + lane] = (ideal_k == 0.0) ? p.empty_value : got_k / ideal_k;
+        if (myk > 0) p.out64[(size_t)b * p.nk + lane] = p.raw_dcg ? got_k : ((ideal_k == 0.0) ? p.empty_value : got_k / ideal_k);
     }
 }
 
@@ -535,48 +536,39 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
     bool marked_only = false, keys_done = false;
     if (kmax <= TPQ_K - 1 && p.n % 4 == 0 && p.flags &&
         (reinterpret_cast<uintptr_t>(p.y_true) | reinterpret_cast<uintptr_t>(p.y_pred)) % 16 == 0) {
-        // one thread per query (ndcg_stream.cuh), then the full sort for the queries it marked
-        static bool attr_done = false;
-        if (!attr_done) {
-#define LTR_TPQ_ATTR(KERNEL) \
-    LTR_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TPQ_SMEM))
-            LTR_TPQ_ATTR(ndcg_tpq_kernel<false>); LTR_TPQ_ATTR(ndcg_tpq_kernel<true>);
-            LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
-            LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
-            LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<false, 2>)); LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<true, 2>));
-            LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<false, 4>)); LTR_TPQ_ATTR((ndcg_tpq_wide_kernel<true, 4>));
-#undef LTR_TPQ_ATTR
-            attr_done = true;
-        }
+        // one thread per query (ndcg_keys.cuh / ndcg_stream.cuh), then the full sort for the queries it marked.
+        // The opt-in shared-memory size is a per-device function attribute: set on every call (cheap), never cached
+        // in a process-wide flag (a second device in one process would otherwise launch without it).
         // warps per tile of 32 queries: long rows are split chunk-wise over the warps of a CTA
         const int share = p.n <= TPQ_N ? 1 : (p.n <= 2 * TPQ_N ? 2 : 4);
         const int tiles = (p.B + 31) / 32;
-        int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
-        // rows of one chunk: a batch that fits one resident wave of the quad-maxima kernel (16 warps per SM) takes it;
-        // larger batches take the score-tile kernel, whose whole-tile asynchronous copies keep more bytes in flight
-#ifdef LTR_NDCG_NO_KEYS
-        const bool keys = false;               // (A/B builds: the earlier quad-maxima / score-tile kernels of ndcg_stream.cuh)
-#else
         const bool keys = share == 1;          // rows of one chunk: label-in-key kernel (ndcg_keys.cuh), which also sorts
                                                // the queries it marks -- no second launch
-#endif
-        const bool qmax = share == 1 && tiles <= device_sm_count() * QMX_CTAS * TPQ_WARPS;
-        const int gcap = device_sm_count() * (share == 1 ? (keys ? KEY_CTAS : (qmax ? QMX_CTAS : TPQ_CTAS)) : 2);
+        const int gcap = device_sm_count() * (keys ? KEY_CTAS : 2);
+        int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
         g = g < gcap ? g : gcap;
         if (keys) g = tiles < gcap ? tiles : gcap;     // tile t -> CTA t % g: every SM gets its share of a small batch
         int rc;
-#define LTR_TPQ(C) \
-    rc = f64 ? launch_pdl(ndcg_tpq_wide_kernel<true, C>, g, TPQ_THREADS, TPQ_SMEM, st, p) \
-             : launch_pdl(ndcg_tpq_wide_kernel<false, C>, g, TPQ_THREADS, TPQ_SMEM, st, p)
+#define LTR_TPQ(C)                                                                                                      \
+    do {                                                                                                                \
+        if (f64) {                                                                                                      \
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_tpq_wide_kernel<true, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          (int)TPQ_SMEM));                                                              \
+            rc = launch_pdl(ndcg_tpq_wide_kernel<true, C>, g, TPQ_THREADS, TPQ_SMEM, st, p);                            \
+        } else {                                                                                                        \
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_tpq_wide_kernel<false, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          (int)TPQ_SMEM));                                                              \
+            rc = launch_pdl(ndcg_tpq_wide_kernel<false, C>, g, TPQ_THREADS, TPQ_SMEM, st, p);                           \
+        }                                                                                                               \
+    } while (0)
         if (keys) {
-            rc = f64 ? launch_pdl(ndcg_key_kernel<true>, g, TPQ_THREADS, KEY_SMEM, st, p)
-                     : launch_pdl(ndcg_key_kernel<false>, g, TPQ_THREADS, KEY_SMEM, st, p);
-        } else if (qmax) {
-            rc = f64 ? launch_pdl(ndcg_qmax_kernel<true>, g, TPQ_THREADS, QMX_SMEM, st, p)
-                     : launch_pdl(ndcg_qmax_kernel<false>, g, TPQ_THREADS, QMX_SMEM, st, p);
-        } else if (share == 1) {
-            rc = f64 ? launch_pdl(ndcg_tpq_kernel<true>, g, TPQ_THREADS, TPQ_SMEM, st, p)
-                     : launch_pdl(ndcg_tpq_kernel<false>, g, TPQ_THREADS, TPQ_SMEM, st, p);
+            if (f64) {
+                LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
+                rc = launch_pdl(ndcg_key_kernel<true>, g, TPQ_THREADS, KEY_SMEM, st, p);
+            } else {
+                LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
+                rc = launch_pdl(ndcg_key_kernel<false>, g, TPQ_THREADS, KEY_SMEM, st, p);
+            }
         } else if (share == 2) { LTR_TPQ(2); } else { LTR_TPQ(4); }
 #undef LTR_TPQ
         if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (one thread per query)");
@@ -640,6 +632,16 @@ LTR_API int ltr_ndcg_at_k_f64(const float* y_true, const float* y_pred, int Q, i
     p.flags = flags;
     p.exp_gains = exponential_gains; p.empty_value = empty_value;
     if (!disc64 || !out) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k_f64: null table / output");
+    return ndcg_common(p, ks, nk, true, stream);
+}
+
+LTR_API int ltr_dcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
+                             int exponential_gains, const double* disc64, double* out, int* flags, void* stream) {
+    ltr::NdcgParams p{};
+    p.y_true = y_true; p.y_pred = y_pred; p.B = Q; p.n = n; p.tie_rule = tie_rule; p.disc64 = disc64; p.out64 = out;
+    p.flags = flags;
+    p.exp_gains = exponential_gains; p.empty_value = 0.0; p.raw_dcg = 1;
+    if (!disc64 || !out) return ltr::set_error(LTR_EINVAL, "ltr_dcg_at_k_f64: null table / output");
     return ndcg_common(p, ks, nk, true, stream);
 }
 

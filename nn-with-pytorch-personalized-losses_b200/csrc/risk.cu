@@ -458,6 +458,38 @@ __global__ void __launch_bounds__(RISK_MC_THREADS) risk_mc_kernel(const RiskMcPa
     else risk_final_body(p, q0, dq, blockIdx.x == 0);
 }
 
+// getGeoRiskDefault (utils/metrics.py:8-45): GeoRisk of EVERY system column of an fp64 query x system matrix, fp64
+// throughout, with the reference's guard "expected value 0 -> z = 0" (:31-34) -- the driver builds this matrix with
+// no_relevant=False, so all-zero query rows occur (computeMetrics.py:94-97).  One CTA per column.
+__global__ void __launch_bounds__(RISKF_THREADS) georisk_default_kernel(const double* __restrict__ mat, int Q, int C,
+                                                                        double alpha, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int col = blockIdx.x;
+    double n_all = 0.0, s_col = 0.0;
+    for (int q = threadIdx.x; q < Q; q += RISKF_THREADS) {
+        const double* row = mat + (size_t)q * C;
+        double t = 0.0;
+        for (int i = 0; i < C; ++i) t += row[i];
+        n_all += t;
+        s_col += row[col];
+    }
+    const double N = rf_block_sum<RISKF_THREADS>(n_all, red);
+    const double S = rf_block_sum<RISKF_THREADS>(s_col, red);
+    double zs = 0.0;
+    for (int q = threadIdx.x; q < Q; q += RISKF_THREADS) {
+        const double* row = mat + (size_t)q * C;
+        double t = 0.0;
+        for (int i = 0; i < C; ++i) t += row[i];
+        const double e = S * (t / N);                            // :29
+        const double d = row[col] - e;
+        double z = (e != 0.0) ? d / sqrt(e) : 0.0;               // :31-34
+        if (d < 0.0) z *= 1.0 + alpha;                           // :35-36
+        zs += z;
+    }
+    const double Z = rf_block_sum<RISKF_THREADS>(zs, red);
+    if (threadIdx.x == 0) out[col] = sqrt((S / (double)Q) * std_normal_cdf(Z / (double)Q));   // :41-43
+}
+
 static int risk_grid(int B) {
     long long g = ((long long)B + STREAM_WARPS - 1) / STREAM_WARPS;
     const long long cap = (long long)device_sm_count() * 8;
@@ -550,4 +582,13 @@ LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, co
     }
     if (!rc && grad) rc = ltr_risk_listnet_rows_bwd(y_pred, y_true, B, n, transformation, t_variant, gq, grad, stream);
     return rc;
+}
+
+// getGeoRiskDefault: mat [Q, C] device doubles -> out [C] device doubles (GeoRisk of every column).
+LTR_API int ltr_georisk_default_f64(const double* mat, int Q, int C, double alpha, double* out, void* stream) {
+    using namespace ltr;
+    if (!mat || !out || Q <= 0 || C <= 0) return set_error(LTR_EINVAL, "ltr_georisk_default_f64: bad arguments");
+    georisk_default_kernel<<<C, RISKF_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mat, Q, C, alpha, out);
+    const int rc = (int)cudaGetLastError();
+    return rc ? set_cuda_error(rc, "ltr_georisk_default_f64") : 0;
 }

@@ -27,10 +27,11 @@ _SIGNATURES = {
     "ltr_approx_ndcg_fwdbwd_host": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P,
                                             c_size_t, _P, _P]),
     "ltr_listnet_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
-    "ltr_ordinal_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "ltr_ordinal_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "ltr_sort_desc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "ltr_ndcg_at_k": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P]),
     "ltr_ndcg_at_k_f64": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, c_int, c_double, _P, _P, _P, _P]),
+    "ltr_dcg_at_k_f64": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, c_int, _P, _P, _P, _P]),
     "ltr_exact_ndcg": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "ltr_order_score_fwdbwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     "ltr_lambda_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, c_int,
@@ -41,10 +42,13 @@ _SIGNATURES = {
     "ltr_risk_lambda_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ltr_lambda_pair_matrix": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, _P,
                                        _P, _P]),
+    "ltr_lambda_pair_matrix_bwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int,
+                                           _P, _P, _P]),
     "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
                                _P, _P]),
     "ltr_risk_listnet_fwdbwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_float, _P, _P, _P, _P, _P, _P]),
+    "ltr_georisk_default_f64": (c_int, [_P, c_int, c_int, c_double, _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
     "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
 }

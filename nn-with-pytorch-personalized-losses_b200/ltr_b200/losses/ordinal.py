@@ -22,15 +22,20 @@ def with_ordinals(y, n, padded_value_indicator=PADDED_Y_VALUE):
 def ordinalLoss(y_pred, y_true, n, padded_value_indicator=PADDED_Y_VALUE):
     """y_pred [batch, slate, n] probabilities of "label > level", y_true [batch, slate] labels, n ordinal levels;
     returns the masked BCE sum divided by the number of docs with an unmasked target (0-dim tensor).
-    Like the reference this raises ValueError when a label equals -1: `with_ordinals` is called
-    with its default padding value and torch's BCELoss rejects the resulting -1 targets (ordinal.py:39-44).
+    Like the reference on the installed torch this raises RuntimeError when a label equals -1
+    (`with_ordinals` is called with its default padding value and BCELoss rejects the resulting -1 targets,
+    ordinal.py:39-44) and when an element of y_pred lies outside [0, 1]; both conditions are detected inside the
+    loss kernel and read back as one status word.
     """
     yp = to_device(y_pred)
     yt = to_device(y_true.detach())
     if yp.dim() != 3 or yp.shape[2] != n or tuple(yp.shape[:2]) != tuple(yt.shape):
         raise ValueError(f"Using a target size ({tuple(yt.shape) + (n,)}) that is different to the input size "
                          f"({tuple(yp.shape)}) is deprecated. Please ensure they have the same size.")
-    if bool((yt == PADDED_Y_VALUE).any()):
-        raise ValueError("all elements of target should be between 0 and 1")
-    loss = ops.ordinal(yp, yt, n, float(padded_value_indicator))
+    loss, status = ops.ordinal(yp, yt, n, float(padded_value_indicator))
+    st = int(status)
+    if st & 2:
+        raise RuntimeError("all elements of input should be between 0 and 1")
+    if st & 1:
+        raise RuntimeError("all elements of target should be between 0 and 1")
     return back_to(loss, y_pred)

@@ -9,9 +9,11 @@ happens in libltr_b200.so.  There is no CPU fallback anywhere in this module.
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import numpy as np
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib, _runtime as rt, sharding
 
@@ -33,11 +35,27 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def _guard(fn):
+    """Run `fn` with the device of its first tensor argument current: streams, workspaces and launches follow the
+    data, not the caller's current device (the reference callables are device-agnostic)."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        first = next(a for a in args if isinstance(a, torch.Tensor))
+        with torch.cuda.device(first.device):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+def _scaled(stash, grad_out):
+    return stash * grad_out if stash is not None else None
+
+
 # ------------------------------------------------------------------------------------------------
 # approxNDCG                                                           losses/approxNDCG.py:7-53
 # ------------------------------------------------------------------------------------------------
 class _ApproxNDCG(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true, eps, pad, alpha):
         lib = _lib.load()
         B, n = y_pred.shape
@@ -59,6 +77,7 @@ class _ApproxNDCG(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         g = ctx.grad * grad_out if ctx.grad is not None else None
         return g, None, None, None, None
@@ -74,6 +93,7 @@ def approx_ndcg(y_pred, y_true, eps=1e-10, pad=-1.0, alpha=1.0):
 # ------------------------------------------------------------------------------------------------
 class _ListNet(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true, apply_sigmoid):
         lib = _lib.load()
         B, n = y_pred.shape
@@ -88,6 +108,7 @@ class _ListNet(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         return (ctx.grad * grad_out if ctx.grad is not None else None), None, None
 
@@ -101,25 +122,30 @@ def listnet(y_true, y_pred, apply_sigmoid=False):
 # ------------------------------------------------------------------------------------------------
 class _Ordinal(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true, levels, pad):
         lib = _lib.load()
         B, n, L = y_pred.shape
         dev = y_pred.device
         need_grad = ctx.needs_input_grad[0]
         loss = torch.empty(1, dtype=torch.float32, device=dev)
+        status = torch.empty(1, dtype=torch.int32, device=dev)
         grad = torch.empty_like(y_pred) if need_grad else None
         _lib.check(lib.ltr_ordinal_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, L, float(pad), loss.data_ptr(),
-                                          _ptr(grad), rt.workspace(dev).data_ptr(), rt.stream_ptr()),
+                                          status.data_ptr(), _ptr(grad), rt.workspace(dev).data_ptr(), rt.stream_ptr()),
                    "ltr_ordinal_fwdbwd")
         ctx.grad = grad
-        return loss.reshape(())
+        ctx.mark_non_differentiable(status)
+        return loss.reshape(()), status
 
     @staticmethod
-    def backward(ctx, grad_out):
+    @once_differentiable
+    def backward(ctx, grad_out, _grad_status):
         return (ctx.grad * grad_out if ctx.grad is not None else None), None, None, None
 
 
 def ordinal(y_pred, y_true, levels, pad=-1.0):
+    """Returns (loss 0-dim, status [1] int32 on the device: bit 0 a target < 0 reached the BCE, bit 1 an input outside [0, 1])."""
     return _Ordinal.apply(y_pred, y_true, levels, pad)
 
 
@@ -128,6 +154,7 @@ def ordinal(y_pred, y_true, levels, pad=-1.0):
 # ------------------------------------------------------------------------------------------------
 class _Lambda(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural):
         lib = _lib.load()
         B, n = y_pred.shape
@@ -145,6 +172,7 @@ class _Lambda(torch.autograd.Function):
         return out[0].reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 9
 
@@ -158,6 +186,7 @@ def lambda_loss(y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural):
 # ------------------------------------------------------------------------------------------------
 class _OrderScore(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true):
         lib = _lib.load()
         B, n = y_pred.shape
@@ -172,6 +201,7 @@ class _OrderScore(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         return (ctx.grad * grad_out if ctx.grad is not None else None), None
 
@@ -180,6 +210,7 @@ def order_score(y_true, y_pred):
     return _OrderScore.apply(y_pred, y_true)
 
 
+@_guard
 def exact_ndcg(y_true, y_pred):
     """Forward only: the reference's ndcgLoss gives y_pred no gradient (exactNDCG.py:7 'not differentiable')."""
     lib = _lib.load()
@@ -195,6 +226,7 @@ def exact_ndcg(y_true, y_pred):
 # ------------------------------------------------------------------------------------------------
 # sorting and NDCG@k                                                     utils/metrics.py:48-104
 # ------------------------------------------------------------------------------------------------
+@_guard
 def sort_desc(keys, tie_rule=TIES_STDSORT, want_values=True):
     """[B, n] CUDA fp32 -> (sorted values or None, int32 permutation) with the reference's tie order."""
     lib = _lib.load()
@@ -224,6 +256,7 @@ def _ks_array(ks):
     return arr
 
 
+@_guard
 def ndcg_at_k(y_true, y_pred, ks, tie_rule=TIES_STDSORT):
     """torchNdcg arithmetic (fp32, gains 2^l - 1).  Returns [Q, len(ks)] fp32 on the device (NaN for 0/0)."""
     lib = _lib.load()
@@ -236,6 +269,7 @@ def ndcg_at_k(y_true, y_pred, ks, tie_rule=TIES_STDSORT):
     return out
 
 
+@_guard
 def ndcg_at_k_f64(y_true, y_pred, ks, tie_rule=TIES_STABLE, exponential=False, empty_value=1.0):
     """metrics.dcg/ndcg arithmetic (fp64).  Returns [Q, len(ks)] fp64 on the device."""
     lib = _lib.load()
@@ -249,12 +283,42 @@ def ndcg_at_k_f64(y_true, y_pred, ks, tie_rule=TIES_STABLE, exponential=False, e
     return out
 
 
+@_guard
+def dcg_at_k_f64(y_true, y_pred, ks, tie_rule=TIES_STABLE, exponential=False):
+    """metrics.dcg arithmetic (fp64, un-normalised).  Returns [Q, len(ks)] fp64 on the device."""
+    lib = _lib.load()
+    Q, n = y_pred.shape
+    _, d64 = _disc_tables(n, y_pred.device)
+    out = torch.empty(Q, len(ks), dtype=torch.float64, device=y_pred.device)
+    flags = torch.empty(Q + 1, dtype=torch.int32, device=y_pred.device)
+    _lib.check(lib.ltr_dcg_at_k_f64(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
+                                    int(bool(exponential)), d64.data_ptr(), out.data_ptr(), flags.data_ptr(),
+                                    rt.stream_ptr()), "ltr_dcg_at_k_f64")
+    return out
+
+
+def georisk_default_f64(mat, alpha):
+    """getGeoRiskDefault (metrics.py:8-45): fp64 [Q, C] (any device) -> fp64 [C] on the GPU."""
+    lib = _lib.load()
+    rt.require_cuda()
+    if mat.device.type != "cuda":
+        mat = mat.to(torch.device("cuda", torch.cuda.current_device()))
+    mat = mat.to(torch.float64).contiguous()
+    Q, C = mat.shape
+    with torch.cuda.device(mat.device):
+        out = torch.empty(C, dtype=torch.float64, device=mat.device)
+        _lib.check(lib.ltr_georisk_default_f64(mat.data_ptr(), Q, C, float(alpha), out.data_ptr(), rt.stream_ptr()),
+                   "ltr_georisk_default_f64")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # risk functions and the ListNet-style risk losses       losses/riskLosses/riskFunctions.py, riskLosses.py
 # ------------------------------------------------------------------------------------------------
 KIND_Z, KIND_GEO, KIND_T = 0, 1, 2
 
 
+@_guard
 def _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, want_gq, want_gmat, group=None):
     """Runs the three phases of ltr_risk_phase on the local rows `mat` [Q, C]; with a process group the
     16-double state blocks are all-reduced between the phases (NCCL on the current stream): MAX for the
@@ -287,6 +351,7 @@ class _RiskFn(torch.autograd.Function):
     """zRisk / geoRisk of column 0 of `mat` (callers permute the requested column to the front)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, mat, kind, alpha):
         need = ctx.needs_input_grad[0]
         loss, _, gmat = _risk_phases(mat, kind, 0, 1, 0, alpha, 1.0, False, need)
@@ -294,6 +359,7 @@ class _RiskFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         return (ctx.gmat * grad_out if ctx.gmat is not None else None), None, None
 
@@ -304,6 +370,7 @@ def risk_fn(mat, kind, alpha):
 
 class _RiskListnet(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk, group):
         lib = _lib.load()
         B, n = y_pred.shape
@@ -343,6 +410,7 @@ class _RiskListnet(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 10
 
@@ -353,6 +421,7 @@ def risk_listnet(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, ad
 
 class _RiskLambda(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, scheme, group):
         lib = _lib.load()
         B, n = y_pred.shape
@@ -378,6 +447,7 @@ class _RiskLambda(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 10
 
@@ -386,14 +456,44 @@ def risk_lambda(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add
     return _RiskLambda.apply(y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, scheme, group)
 
 
+class _LambdaPairMatrix(torch.autograd.Function):
+    """lambdaMask's [B, n, n] pair log-probabilities (rank order), differentiable w.r.t. y_pred (lambdaL.py:7-64)."""
+
+    @staticmethod
+    @_guard
+    def forward(ctx, y_pred, y_true, eps, pad, scheme, k, sigma, mu, natural, want_mask):
+        lib = _lib.load()
+        B, n = y_pred.shape
+        dev = y_pred.device
+        logp = torch.empty(B, n, n, dtype=torch.float32, device=dev)
+        mask = torch.empty(B, n, n, dtype=torch.uint8, device=dev) if want_mask else None
+        _lib.check(lib.ltr_lambda_pair_matrix(y_pred.data_ptr(), y_true.data_ptr(), B, n, float(eps), float(pad), int(scheme),
+                                              int(k), float(sigma), float(mu), int(natural), logp.data_ptr(), _ptr(mask),
+                                              rt.stream_ptr()), "ltr_lambda_pair_matrix")
+        ctx.save_for_backward(y_pred, y_true)
+        ctx.args = (float(eps), float(pad), int(scheme), int(k), float(sigma), float(mu), int(natural))
+        if mask is None:
+            return logp
+        ctx.mark_non_differentiable(mask)
+        return logp, mask
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_logp, _grad_mask=None):
+        y_pred, y_true = ctx.saved_tensors
+        eps, pad, scheme, k, sigma, mu, natural = ctx.args
+        B, n = y_pred.shape
+        with torch.cuda.device(y_pred.device):
+            g = grad_logp.contiguous()
+            grad = torch.empty_like(y_pred)
+            _lib.check(_lib.load().ltr_lambda_pair_matrix_bwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, eps, pad, scheme, k,
+                                                              sigma, mu, natural, g.data_ptr(), grad.data_ptr(),
+                                                              rt.stream_ptr()), "ltr_lambda_pair_matrix_bwd")
+        return (grad,) + (None,) * 9
+
+
 def lambda_pair_matrix(y_pred, y_true, eps, pad, scheme, k, sigma, mu, natural, want_mask):
-    """[B, n, n] pair log-probabilities in rank order (+ the lambdaLoss pair mask as uint8)."""
-    lib = _lib.load()
-    B, n = y_pred.shape
-    dev = y_pred.device
-    logp = torch.empty(B, n, n, dtype=torch.float32, device=dev)
-    mask = torch.empty(B, n, n, dtype=torch.uint8, device=dev) if want_mask else None
-    _lib.check(lib.ltr_lambda_pair_matrix(y_pred.data_ptr(), y_true.data_ptr(), B, n, float(eps), float(pad), int(scheme),
-                                          int(k), float(sigma), float(mu), int(natural), logp.data_ptr(), _ptr(mask),
-                                          rt.stream_ptr()), "ltr_lambda_pair_matrix")
-    return logp, mask
+    """[B, n, n] pair log-probabilities in rank order (+ the lambdaLoss pair mask as uint8), attached to autograd."""
+    if want_mask:
+        return _LambdaPairMatrix.apply(y_pred, y_true, eps, pad, scheme, k, sigma, mu, natural, True)
+    return _LambdaPairMatrix.apply(y_pred, y_true, eps, pad, scheme, k, sigma, mu, natural, False), None

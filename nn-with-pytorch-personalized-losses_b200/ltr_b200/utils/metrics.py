@@ -48,6 +48,16 @@ def _f64(true_relevance, pred_relevance, k, gains, use_numpy, empty_value):
     return ops.ndcg_at_k_f64(yt, yp, [k], tie, gains == "exponential", empty_value)
 
 
+def dcg(true_relevance, pred_relevance, k=5, gains='linear', use_numpy=False):
+    """DCG@k of ONE query (metrics.py:48-66): sum over the first min(k, n) docs in predicted order of
+    gain(label) / log2(rank + 1), fp64; gains 'linear' (the default) or 'exponential' (2^l - 1).  Returns a float."""
+    if gains not in ("exponential", "linear"):
+        raise ValueError("Invalid gains option.")                                  # metrics.py:63
+    yt, yp = _as_2d(true_relevance), _as_2d(pred_relevance)
+    tie = ops.TIES_REVERSED if use_numpy else ops.TIES_STABLE
+    return float(ops.dcg_at_k_f64(yt, yp, [k], tie, gains == "exponential")[0, 0])
+
+
 def ndcg(true_relevance, pred_relevance, k=5, no_relevant=True, gains='linear', use_numpy=False):
     out = _f64(true_relevance, pred_relevance, k, gains, use_numpy, 1.0 if no_relevant else 0.0)
     return float(out[0, 0])
@@ -59,15 +69,10 @@ def mNdcg(true_relevance, pred_relevance, k=5, no_relevant=True, gains='linear',
 
 
 def getGeoRiskDefault(mat, alpha):
-    """GeoRisk of every system column (metrics.py:8-45), numpy fp64 in, numpy fp64 out.  Each column goes through
-    the device z-risk phases (fp64 reductions); zero-expectation entries are guarded as in the reference (:31-34)
-    by the caller-visible contract that effectiveness values are non-negative with positive totals."""
-    m = torch.as_tensor(np.asarray(mat, dtype=np.float64))
-    C = m.shape[1]
-    dev_m = to_device(m.float())
-    out = np.empty(C, dtype=np.float64)
-    for i in range(C):
-        idx = [i] + [c for c in range(C) if c != i]
-        loss = ops.risk_fn(dev_m[:, idx].contiguous(), ops.KIND_GEO, float(alpha))
-        out[i] = float(loss)
-    return out
+    """GeoRisk of every system column (metrics.py:8-45): numpy fp64 [queries, systems] in, numpy fp64 [systems] out.
+    fp64 end to end on the device (`ltr_georisk_default_f64`), including the reference's guard that an entry whose
+    expected value is 0 contributes z = 0 (:31-34; all-zero query rows occur with no_relevant=False)."""
+    m = torch.as_tensor(np.ascontiguousarray(np.asarray(mat, dtype=np.float64)))
+    if m.dim() != 2:
+        raise IndexError("tuple index out of range")                               # mat.shape[1] on a 1-D array (:9)
+    return ops.georisk_default_f64(m, float(alpha)).cpu().numpy()

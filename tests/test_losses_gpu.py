@@ -184,7 +184,11 @@ def test_ordinal_vs_oracle_and_padding_error():
     p = torch.rand(6, 30, 4, generator=g) * 0.98 + 0.01
     _check("ordinalLoss", {"y_pred": p, "y_true": y}, {"n": 4})
     y[0, 3] = -1.0
-    with pytest.raises(ValueError):
+    with pytest.raises(RuntimeError, match="target should be between 0 and 1"):    # what torch's BCELoss raises
+        ordinalLoss(p.cuda(), y.cuda(), 4)
+    y[0, 3] = 2.0
+    p[1, 2, 3] = 1.5
+    with pytest.raises(RuntimeError, match="input should be between 0 and 1"):
         ordinalLoss(p.cuda(), y.cuda(), 4)
 
 
