@@ -177,18 +177,53 @@ int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, int n, fl
                       float* slate_count, float* loss, float* pair_count, float* grad, void* workspace, void* stream);
 
 /*
- * Risk-sensitive losses, ListNet family.      replaces losses/riskLosses/riskLosses.py:8-60, 128-180, 247-291
+ * Risk-sensitive losses, ListNet family, fused forward + backward.
+ * replaces losses/riskLosses/riskLosses.py:8-60 (geoRiskListnetLoss), 128-180 (zRiskListnetLoss), 247-291 (tRiskListnetLoss)
  *
- * ltr_risk_listnet_rows: mat[b, :] = effectiveness of {model, S baseline systems, (ideal)} for query b
- *   transformation 1: sum_d (p_t p_s - p_t^2)^2   2: cosine(p_t, p_s)   3: (sum p_t p_s - sum p_t^2)^2,
- *   p = softmax over the docs; t_variant selects tRiskListnetLoss' cosine(p_t^2, p_t p_s) (riskLosses.py:262).
- *   y_baselines : [B, n, S] or NULL (S = 0); mat : [B, 1 + S + add_ideal]
- * ltr_risk_listnet_rows_bwd: grad[b, :] = gq[b] * d mat[b, 0] / d y_pred[b, :]
+ * Three launches, selected by the bits of `phases`:
+ *   1  rows:     mat[b, :] = effectiveness of {model, S baseline systems, (ideal)} for query b --
+ *                transformation 1: sum_d (p_t p_s - p_t^2)^2   2: cosine(p_t, p_s)   3: (sum p_t p_s - sum p_t^2)^2,
+ *                p = softmax over the docs; kind 2 (t-risk) uses cosine(p_t^2, p_t p_s) for transformation 2 (:262) --
+ *                and this rank's phase-1 state (matrix max, column totals, query count) -> exchange block, round 0;
+ *   2  stats:    (needs round 0 of every rank) z-risk sums -> exchange block, round 1; per-query gradient terms -> rowstate;
+ *   4  backward: (needs both rounds of every rank) loss[0]; grad[b, :] = d loss / d y_pred[b, :] (grad may be NULL).
+ * kind 0 zRisk, 1 geoRisk, 2 tRisk (columns 0 = model, 1 = baseline); invert: mat <- max(mat) - mat (:49-50);
+ * return_strategy 1: f r(0), 2: f (r(-1) - r(0)), 3: f (r(-1) - r(0))^2; precedence_quirk: strategy 2 is
+ * f r(-1) - r(0) (zRiskListnetLoss, :176); negative = f.
+ *   y_baselines : [B, n, S] or NULL (S = 0); mat : [B, 1 + S + add_ideal] out; rowstate : 3 B device doubles of scratch.
+ *   B = 0 is an empty shard: the rank contributes the neutral state (its data pointers may be NULL).
+ *
+ * Query sharding.  xchg: this rank's exchange block, LTR_RISK_XCHG_BYTES of device memory zero-filled
+ * once (one per stream): inbox[round][rank][16] doubles + flags.  world = 1: phases = 7, one call.  world > 1, either
+ *   - peer_xchg = NULL: call with phases = 1, all-gather row `rank` of round 0 (16 doubles at byte offset
+ *     (0 * LTR_RISK_MAX_WORLD + rank) * 128) into everybody's block, phases = 2, all-gather round 1 (offset
+ *     (1 * LTR_RISK_MAX_WORLD + rank) * 128), phases = 4: two collectives per step; or
+ *   - peer_xchg = HOST array of `world` device pointers, every rank's block as mapped into this process
+ *     (ltr_risk_xchg_alloc + ltr_ipc_export / ltr_ipc_open; peer_xchg[rank] == xchg), seq = number of this call (the
+ *     same on every rank, never 0, different from the previous call's): phases = 7, one call, no collective -- the
+ *     kernels store their states into the peers' inboxes over NVLink and spin (<= 4 s) on sequence-numbered flags.
  */
-int ltr_risk_listnet_rows(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
-                          int transformation, int add_ideal, int t_variant, float* mat, void* stream);
-int ltr_risk_listnet_rows_bwd(const float* y_pred, const float* y_true, int B, int n, int transformation, int t_variant,
-                              const float* gq, float* grad, void* stream);
+#define LTR_RISK_MAX_WORLD 16
+#define LTR_RISK_XCHG_BYTES 8192
+int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
+                            int transformation, int add_ideal, int kind, int invert, int return_strategy,
+                            int precedence_quirk, float alpha, float negative, float* mat, double* rowstate, float* loss,
+                            float* grad, int phases, void* xchg, int rank, int world, const void* const* peer_xchg,
+                            unsigned seq, void* workspace, void* stream);
+
+/*
+ * Exchange blocks in peer-mappable memory.  ltr_risk_xchg_alloc: cudaMalloc + zero fill of LTR_RISK_XCHG_BYTES on the
+ * current device (the one allocation this library makes: CUDA IPC needs the base of an allocation);
+ * ltr_ipc_export: the 64-byte cudaIpcMemHandle_t of a block; ltr_ipc_open: map a peer's block (another process, same
+ * or another GPU of the box; enables peer access); ltr_risk_xchg_status: 0, or 1 when a peer's state did not arrive
+ * within the spin limit (the loss of that call is NaN) -- synchronous, for diagnostics.
+ */
+int ltr_risk_xchg_alloc(void** xchg);
+int ltr_risk_xchg_free(void* xchg);
+int ltr_ipc_export(void* dptr, unsigned char* handle64);
+int ltr_ipc_open(const unsigned char* handle64, void** dptr);
+int ltr_ipc_close(void* dptr);
+int ltr_risk_xchg_status(const void* xchg, int* status);
 
 /*
  * Risk-sensitive losses, LambdaLoss family.   replaces losses/riskLosses/riskLosses.py:63-125, 183-244, 294-345
@@ -223,17 +258,16 @@ int ltr_lambda_pair_matrix_bwd(const float* y_pred, const float* y_true, int B, 
                                float* grad, void* stream);
 
 /*
- * zRisk / geoRisk / tRisk over a query x system matrix.   replaces losses/riskLosses/riskFunctions.py:4-33 and the
- * epilogues riskLosses.py:49-58, 274-291.  Three phases so that query-sharded callers can all-reduce in between:
- *   phase 1 (local)  state1 = {max(mat), sum mat[:,0], sum mat[:,C-1], sum(mat), Q}     -> MAX on [0], SUM on [1..4]
- *   phase 2          state2 = per used column {sum z c, sum A T, sum A e, sum c/sqrt(e), sum A}, #maxima, t-risk sums -> SUM
+ * zRisk / geoRisk / tRisk over a caller-provided query x system matrix.   replaces losses/riskLosses/riskFunctions.py:4-33
+ * and the epilogues riskLosses.py:49-58, 274-291 (used by zRisk / geoRisk themselves, the LambdaLoss-style risk losses and
+ * the validation epilogue).  The same three phases as above, one single-CTA launch each, states in the exchange block:
+ *   phase 1 (local)  round 0 <- {max(mat), sum mat[:,0], sum mat[:,C-1], sum(mat), Q}          (combined: MAX on [0], SUM)
+ *   phase 2          round 1 <- per used column {sum z c, sum A T, sum A e, sum c/sqrt(e), sum A}, #maxima, t-risk sums
  *   phase 3          loss[0], gq[q] = d loss / d mat[q, 0] and gmat[q, i] = d loss / d mat[q, i]   (either may be NULL)
- *   kind 0 zRisk, 1 geoRisk, 2 tRisk (columns 0 = model, 1 = baseline); invert: mat <- max(mat) - mat;
- *   return_strategy 1: f r(0), 2: f (r(-1) - r(0)), 3: f (r(-1) - r(0))^2; precedence_quirk: strategy 2 is
- *   f r(-1) - r(0) (zRiskListnetLoss, riskLosses.py:176); negative = f.  state1/state2: 16 device doubles each.
+ * Query-sharded callers all-gather the inbox rows between the phases as described above; Q = 0 is an empty shard.
  */
 int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int invert, int return_strategy,
-                   int precedence_quirk, float alpha, float negative, double* state1, double* state2, float* loss,
+                   int precedence_quirk, float alpha, float negative, void* xchg, int rank, int world, float* loss,
                    float* gq, float* gmat, void* stream);
 
 /*
@@ -242,17 +276,6 @@ int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int inve
  *   S_i T_q / N is 0 contributes z = 0 (the reference's guard, :31-34); z is scaled by 1 + alpha where x < e.
  */
 int ltr_georisk_default_f64(const double* mat, int Q, int C, double alpha, double* out, void* stream);
-
-/*
- * geoRisk / zRisk / tRisk ListNet loss, forward + backward in one call on one GPU (no exchange between the phases).
- * replaces losses/riskLosses/riskLosses.py:8-60, 128-180, 247-291 end to end: ltr_risk_listnet_rows, the three
- * ltr_risk_phase launches and ltr_risk_listnet_rows_bwd, with the same arguments.
- *   mat : [B, 1 + S + add_ideal] out; state : 2080 device doubles of scratch; gq : [B] scratch; grad : [B, n] or NULL.
- */
-int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
-                            int transformation, int add_ideal, int kind, int invert, int return_strategy,
-                            int precedence_quirk, float alpha, float negative, float* mat, double* state, float* loss,
-                            float* gq, float* grad, void* stream);
 
 /*
  * Roofline probes (measurement only): a pure ex2.approx loop and a pure FFMA loop, 8 CTAs of

@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(256) lambda_finish_kernel(const float* slate_s
             loss[0] = mean ? (float)(-ts / tc) : (float)(-ts);
             if (count_out) count_out[0] = (float)tc;
         }
-        sh_inv = (float)(1.0 / tc);
+        sh_inv = tc > 0.0 ? (float)(1.0 / tc) : 0.f;      // no masked pair at all: the mean is NaN, its gradient 0 (as autograd gives)
     }
     __syncthreads();
     if (!mean || !grad) return;

@@ -1,6 +1,7 @@
 // Host-side helpers shared by the C-ABI translation units (status codes, error text, device info).
 #pragma once
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "../../include/ltr_b200.h"
 
@@ -17,8 +18,17 @@ int upload_disc_prefix_constant();                   // P[0..128] -> the constan
 //   u32 [16]      streaming kernels: finished-CTA counter
 //   u32 [18]      LambdaLoss: next-slate counter
 //   f32 [32..35]  ordinal: BCE sum, number of valid docs, #targets < 0, #inputs outside [0, 1]
+//   u32 [20..21]  risk losses: finished-CTA counters of phases A and B
 //   byte 1024 ..  streaming kernels: per-CTA fp64 partial sums, [grid <= 2048][4]
+//   byte 66560 .. risk losses: per-CTA fp64 partials of phase A [grid <= 1184][4], then of phase B [grid <= 128][16]
 constexpr int LTR_WS_STREAM_COUNTER = 16;
+constexpr int LTR_WS_RISK_COUNTERS = 20;
+constexpr int LTR_WS_RISK_MAX_GRID = 1184;
+constexpr size_t LTR_WS_RISK_PART1 = 1024 + 2048 * 4 * 8;
+constexpr size_t LTR_WS_RISK_PART2 = LTR_WS_RISK_PART1 + (size_t)LTR_WS_RISK_MAX_GRID * 4 * 8;
+static_assert(LTR_WS_RISK_PART2 + 128 * 16 * 8 <= LTR_WORKSPACE_BYTES, "workspace layout overflows");
+inline double* ws_risk_part1(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + LTR_WS_RISK_PART1); }
+inline double* ws_risk_part2(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + LTR_WS_RISK_PART2); }
 constexpr int LTR_WS_LAMBDA_COUNTER = 18;             // LambdaLoss: next-slate counter
 constexpr int LTR_WS_ORDINAL_SUMS = 32;
 inline unsigned* ws_counter(void* ws, int idx) { return reinterpret_cast<unsigned*>(ws) + idx; }

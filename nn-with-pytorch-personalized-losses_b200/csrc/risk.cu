@@ -1,24 +1,118 @@
 // K6: risk-sensitive losses (replaces losses/riskLosses/riskFunctions.py:4-33 and the ListNet-style
 // family of losses/riskLosses/riskLosses.py:8-60,128-180,247-291).
 //
-//   K6a  risk_rows_kernel      per query: softmax(y_true), softmax(system) for the model and every baseline
-//                              system -> one row of the query x system effectiveness matrix  (streaming, HBM-bound:
-//                              4 n (2 + S) bytes read per query)
-//   K6b  risk_stats1 / risk_stats2 / risk_final   the global coupling of zRisk / geoRisk / tRisk: a matrix-wide max
-//                              (riskLosses.py:50), column sums S_i, row sums T_q, N, the z sums, and the analytic
-//                              gradient d loss / d mat[q, 0].  They are three tiny single-CTA kernels so that, when the
-//                              queries are sharded over GPUs, the two exchange rounds sit between them:
-//                              the 16-double state block of each phase is SUM/MAX all-reduced over NCCL by the host.
-//   K6c  risk_rows_bwd_kernel  per query: d loss / d y_pred = gq[b] * d mat[b, 0] / d y_pred (softmax backward)
+// The ListNet family is THREE launches (fwd + bwd), on one GPU and query-sharded alike:
+//   A  risk_fused_rows_kernel    per query (one warp): softmax(y_true), softmax(system) for the model and every
+//                                baseline system -> one row of the query x system effectiveness matrix (HBM-bound:
+//                                4 n (2 + S) bytes per query, all of a row's loads in flight together); the matrix-wide
+//                                max, the column totals and the query count are reduced on the way (per-CTA partials,
+//                                the last CTA adds them in index order) = phase-1 state
+//   B  risk_fused_stats2_kernel  one thread per query, fp64: z-risk sums and the per-query terms the gradient needs
+//                                (A_q, c_q / sqrt(e_q)) = phase-2 state + 3 doubles per query
+//   C  risk_fused_bwd_kernel     loss value; per query (one warp): d loss / d mat[q, 0] from the phase states and the
+//                                stored terms (a few fp64 FMAs), times d mat[q, 0] / d y_pred (softmax backward)
+// The phase states of the ranks of a query-sharded run meet in a small EXCHANGE BLOCK per rank (inbox[slot][rank][16]
+// doubles).  Either the caller all-gathers the inbox rows between the phase launches (NCCL / gloo: one collective per
+// round), or -- `peer_xchg` given -- the last CTA of A / B stores its state straight into every peer's inbox over
+// NVLink (peer memory mapped with CUDA IPC), then a sequence-numbered flag with release.sys; B / C spin on their own
+// flags with acquire.sys before they combine.  No collective call, no extra launch: the exchange rides in the kernels.
 //
+//   ltr_risk_phase      the same three phases over a caller-provided matrix (riskFunctions.zRisk / geoRisk, the
+//                       LambdaLoss-style risk losses, the validation epilogue): three single-CTA launches.
+//   ltr_georisk_default_f64   utils/metrics.py:8-45 in fp64.
 // Only column 0 (the model) depends on y_pred; baselines and the ideal column are constants.
 #include "ltr_host.h"
 #include "stream_common.cuh"
 
 namespace ltr {
 
+constexpr int RISK_STATE = 16;                       // doubles per phase state
+constexpr int RISK_MAX_WORLD = LTR_RISK_MAX_WORLD;   // ranks an exchange block has room for
+// exchange block: doubles inbox[2][RISK_MAX_WORLD][RISK_STATE]; then 32-bit words flag[2][RISK_MAX_WORLD], status
+constexpr int RISK_XCHG_WORDS_AT = 2 * RISK_MAX_WORLD * RISK_STATE;      // (in doubles)
+constexpr int RISK_W_STATUS = 2 * RISK_MAX_WORLD;
+constexpr unsigned long long RISK_SPIN_NS = 4000000000ull;               // give up on a peer after 4 s
+static_assert(RISK_XCHG_WORDS_AT * 8 + (RISK_W_STATUS + 1) * 4 <= LTR_RISK_XCHG_BYTES, "exchange block too small");
+
+struct RiskComm {
+    double* xchg;                       // this rank's exchange block
+    double* peer[RISK_MAX_WORLD];       // p2p: every rank's block as mapped into this process (peer[rank] == xchg)
+    int rank, world, p2p;
+    unsigned seq;                       // p2p: sequence number of this call (same on every rank, never 0)
+};
+
+__device__ __forceinline__ unsigned* xchg_words(double* x) { return reinterpret_cast<unsigned*>(x + RISK_XCHG_WORDS_AT); }
+__device__ __forceinline__ double* xchg_inbox(double* x, int slot, int r) {
+    return x + ((size_t)slot * RISK_MAX_WORLD + r) * RISK_STATE;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One CTA publishes its rank's state of round `slot` (st: RISK_STATE doubles in shared memory, complete before the call):
+// into the local inbox, or -- p2p -- into the inbox of EVERY rank (plain stores to peer memory over NVLink, a system
+// fence, a barrier, then one release store per peer of the call's sequence number).
+__device__ __forceinline__ void risk_publish(const RiskComm& c, int slot, const double* st) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (!c.p2p) {
+        if (tid < RISK_STATE) xchg_inbox(c.xchg, slot, c.rank)[tid] = st[tid];
+        return;
+    }
+    for (int idx = tid; idx < RISK_STATE * c.world; idx += nthr) {
+        const int r = idx / RISK_STATE, e = idx % RISK_STATE;
+        st_relaxed_sys(xchg_inbox(c.peer[r], slot, c.rank) + e, st[e]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int r = tid; r < c.world; r += nthr) st_release_sys(xchg_words(c.peer[r]) + slot * RISK_MAX_WORLD + c.rank, c.seq);
+}
+
+// Every CTA of the next phase: (p2p: wait until every rank's flag of round `slot` carries this call's sequence number,)
+// then combine the ranks' states in rank order -- entry 0 of round 0 is a MAX, everything else a SUM -- into dst
+// (RISK_STATE doubles of shared memory).  Ends with a barrier.
+__device__ __forceinline__ void risk_gather(const RiskComm& c, int slot, double* dst) {
+    const int tid = threadIdx.x;
+    if (c.p2p && c.world > 1) {
+        if (tid < c.world) {
+            const unsigned* f = xchg_words(c.xchg) + slot * RISK_MAX_WORLD + tid;
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_acquire_sys(f) != c.seq) {
+                if (globaltimer_ns() - t0 > RISK_SPIN_NS) {          // a peer never arrived: poison the result, say so
+                    atomicExch(xchg_words(c.xchg) + RISK_W_STATUS, 1u);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < RISK_STATE) {
+        const double* src = xchg_inbox(c.xchg, slot, 0) + tid;
+        double t = __ldcg(src);
+        for (int r = 1; r < c.world; ++r) {
+            const double v = __ldcg(src + (size_t)r * RISK_STATE);
+            t = (slot == 0 && tid == 0) ? fmax(t, v) : t + v;
+        }
+        if (c.p2p && __ldcg(xchg_words(c.xchg) + RISK_W_STATUS) != 0u) t = __longlong_as_double(0x7ff8000000000000ll);
+        dst[tid] = t;
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------
-// K6a
+// per-query effectiveness (phase A) and its derivative (phase C)
 // ---------------------------------------------------------------------------------------------------
 struct RiskRowsParams {
     const float* y_pred;     // [B, n]
@@ -26,8 +120,7 @@ struct RiskRowsParams {
     const float* y_base;     // [B, n, S] or null
     int B, n, S, lt, add_ideal, tmode;
     float* mat;              // [B, C], C = 1 + S + add_ideal
-    const float* gq;         // backward: [B] d loss / d mat[b, 0]
-    float* grad;             // backward: [B, n]
+    float* grad;             // backward: [B, n] or null
 };
 
 // effectiveness of one system against the label distribution pt (both softmaxed, padding lanes 0)
@@ -61,96 +154,53 @@ __device__ __forceinline__ float effectiveness(const RowRegs<ITEMS>& pt, const R
     return xy / (fmaxf(sqrtf(xx), 1e-8f) * fmaxf(sqrtf(yy), 1e-8f));
 }
 
-template <int ITEMS>
-__global__ void __launch_bounds__(STREAM_THREADS) risk_rows_kernel(const RiskRowsParams p) {
-    pdl_prologue();
-    const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * STREAM_WARPS;
-    const float ninf = __int_as_float(0xff800000);
-    const int C = 1 + p.S + p.add_ideal;
-    for (int b = gwarp; b < p.B; b += nwarps) {
-        RowRegs<ITEMS> pt, ps;
-        pt.load(p.y_true + (size_t)b * p.n, p.n, lane, ninf);
-        softmax_row(pt);
-        ps.load(p.y_pred + (size_t)b * p.n, p.n, lane, ninf);
-        softmax_row(ps);
-        float v = effectiveness(pt, ps, p.lt, p.tmode);
-        if (lane == 0) p.mat[(size_t)b * C] = v;
-        for (int j = 0; j < p.S; ++j) {
-            ps.load_strided(p.y_base + (size_t)b * p.n * p.S + j, p.n, p.S, lane, ninf);
-            softmax_row(ps);
-            v = effectiveness(pt, ps, p.lt, p.tmode);
-            if (lane == 0) p.mat[(size_t)b * C + 1 + j] = v;
-        }
-        if (p.add_ideal) {                             // the ideal ranking as one more system  (:35-41)
-            v = effectiveness(pt, pt, p.lt, p.tmode);
-            if (lane == 0) p.mat[(size_t)b * C + 1 + p.S] = v;
-        }
-    }
-}
 
-// K6c: grad[b, :] = gq[b] * d mat[b, 0] / d y_pred[b, :]
+// d value / d ps_d for the model column, then the softmax backward, times `up`: g <- up * d mat[b, 0] / d y_pred
 template <int ITEMS>
-__global__ void __launch_bounds__(STREAM_THREADS) risk_rows_bwd_kernel(const RiskRowsParams p) {
-    pdl_prologue();
-    const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * STREAM_WARPS;
-    const float ninf = __int_as_float(0xff800000);
-    for (int b = gwarp; b < p.B; b += nwarps) {
-        RowRegs<ITEMS> pt, ps, g;
-        pt.load(p.y_true + (size_t)b * p.n, p.n, lane, ninf);
-        softmax_row(pt);
-        ps.load(p.y_pred + (size_t)b * p.n, p.n, lane, ninf);
-        softmax_row(ps);
-        // g_d = d value / d ps_d
-        if (p.lt == 1) {
+__device__ __forceinline__ void effectiveness_bwd(const RowRegs<ITEMS>& pt, const RowRegs<ITEMS>& ps, int lt, int tmode,
+                                                  float up, RowRegs<ITEMS>& g) {
+    if (lt == 1) {
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) g.v[k] = 2.0f * (pt.v[k] * ps.v[k] - pt.v[k] * pt.v[k]) * pt.v[k];
-        } else if (p.lt == 3) {
-            float a = 0.f, c = 0.f;
+        for (int k = 0; k < ITEMS; ++k) g.v[k] = 2.0f * (pt.v[k] * ps.v[k] - pt.v[k] * pt.v[k]) * pt.v[k];
+    } else if (lt == 3) {
+        float a = 0.f, c = 0.f;
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) a = fmaf(pt.v[k], ps.v[k], a), c = fmaf(pt.v[k], pt.v[k], c);
-            const float u = warp_sum(a) - warp_sum(c);
+        for (int k = 0; k < ITEMS; ++k) a = fmaf(pt.v[k], ps.v[k], a), c = fmaf(pt.v[k], pt.v[k], c);
+        const float u = warp_sum(a) - warp_sum(c);
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) g.v[k] = 2.0f * u * pt.v[k];
-        } else {
-            float xy = 0.f, xx = 0.f, yy = 0.f;
+        for (int k = 0; k < ITEMS; ++k) g.v[k] = 2.0f * u * pt.v[k];
+    } else {
+        float xy = 0.f, xx = 0.f, yy = 0.f;
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                const float x = p.tmode ? pt.v[k] * pt.v[k] : pt.v[k];
-                const float y = p.tmode ? pt.v[k] * ps.v[k] : ps.v[k];
-                xy = fmaf(x, y, xy), xx = fmaf(x, x, xx), yy = fmaf(y, y, yy);
-            }
-            xy = warp_sum(xy), xx = warp_sum(xx), yy = warp_sum(yy);
-            const float nx = fmaxf(sqrtf(xx), 1e-8f), ny = fmaxf(sqrtf(yy), 1e-8f);
-            const float c = xy / (nx * ny);
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                const float x = p.tmode ? pt.v[k] * pt.v[k] : pt.v[k];
-                const float y = p.tmode ? pt.v[k] * ps.v[k] : ps.v[k];
-                const float dy = x / (nx * ny) - c * y / (ny * ny);      // d cos / d y_d
-                g.v[k] = p.tmode ? dy * pt.v[k] : dy;
-            }
+        for (int k = 0; k < ITEMS; ++k) {
+            const float x = tmode ? pt.v[k] * pt.v[k] : pt.v[k];
+            const float y = tmode ? pt.v[k] * ps.v[k] : ps.v[k];
+            xy = fmaf(x, y, xy), xx = fmaf(x, x, xx), yy = fmaf(y, y, yy);
         }
-        // softmax backward: d/d s_k = ps_k (g_k - sum_d g_d ps_d)
-        float dot = 0.f;
+        xy = warp_sum(xy), xx = warp_sum(xx), yy = warp_sum(yy);
+        const float nx = fmaxf(sqrtf(xx), 1e-8f), ny = fmaxf(sqrtf(yy), 1e-8f);
+        const float c = xy / (nx * ny);
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) dot = fmaf(g.v[k], ps.v[k], dot);
-        dot = warp_sum(dot);
-        const float up = p.gq[b];
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) g.v[k] = up * ps.v[k] * (g.v[k] - dot);
-        g.store(p.grad + (size_t)b * p.n, p.n, lane);
+        for (int k = 0; k < ITEMS; ++k) {
+            const float x = tmode ? pt.v[k] * pt.v[k] : pt.v[k];
+            const float y = tmode ? pt.v[k] * ps.v[k] : ps.v[k];
+            const float dy = x / (nx * ny) - c * y / (ny * ny);      // d cos / d y_d
+            g.v[k] = tmode ? dy * pt.v[k] : dy;
+        }
     }
+    // softmax backward: d/d s_k = ps_k (g_k - sum_d g_d ps_d)
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) dot = fmaf(g.v[k], ps.v[k], dot);
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) g.v[k] = up * ps.v[k] * (g.v[k] - dot);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K6b.  One CTA of 1024 threads walks the [Q, C] matrix (a few KB .. MB); all arithmetic in fp64.
+// the risk phases (fp64)
 // ---------------------------------------------------------------------------------------------------
-constexpr int RISKF_THREADS = 1024;
-constexpr int RISK_STATE = 16;           // doubles per state block
+constexpr int RISKF_THREADS = 1024;      // the single-CTA phase kernels of ltr_risk_phase
 
 struct RiskFinalParams {
     const float* mat;        // [Q, C] local rows (raw effectiveness, before the max - mat inversion)
@@ -160,8 +210,8 @@ struct RiskFinalParams {
     int strategy;            // return_strategy 1 / 2 / 3
     int quirk;               // zRiskListnetLoss: strategy 2 is factor * z(-1) - z(0)   (:176)
     float alpha, negative;
-    double* state1;          // [RISK_STATE] phase-1 state (max in [0], sums from [1])
-    double* state2;          // [RISK_STATE] phase-2 state
+    const double* state1;    // [RISK_STATE] GLOBAL phase-1 state (max in [0], sums from [1]); set by the kernels
+    const double* state2;    // [RISK_STATE] GLOBAL phase-2 state
     float* loss;             // [1]
     float* gq;               // [Q] d loss / d mat[q, 0]
     float* gmat;             // [Q, C] d loss / d mat (full), or null
@@ -262,7 +312,7 @@ __device__ __forceinline__ ZCol make_zcol(const RiskFinalParams& p, const double
 // phase 2 (local, needs global state1): per used column {sum z c, sum A T, sum A e, sum c / sqrt(e), sum A}, count of
 // entries equal to the global max;  t-risk: {sum d', sum d'^2} with d' = d (1 + alpha [d < 0]).
 template <int THREADS>
-__device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p, int q0, int dq, double* out) {
+__device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p, int q0, int dq, double* out, double* rowstate = nullptr) {
     __shared__ double red[32];
     const double* g1 = p.state1;
     double a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -282,10 +332,13 @@ __device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p, int q
             const float* row = p.mat + (size_t)q * p.C;
             double z, c, A, e, t;
             z0.eval(row, z, c, A, e, t);
-            a[0] += z * c; a[1] += A * t; a[2] += A * e; a[3] += c / sqrt(e); a[4] += A;
+            const double ce0 = c / sqrt(e);
+            a[0] += z * c; a[1] += A * t; a[2] += A * e; a[3] += ce0; a[4] += A;
+            if (rowstate) rowstate[(size_t)q * 3 + 0] = A, rowstate[(size_t)q * 3 + 1] = ce0;
             if (p.strategy != 1) {
                 zl.eval(row, z, c, A, e, t);
                 a[5] += z * c; a[6] += A * t; a[7] += A * e; a[8] += c / sqrt(e); a[9] += A;
+                if (rowstate) rowstate[(size_t)q * 3 + 2] = A;
             }
             if (p.invert)
                 for (int i = 0; i < p.C; ++i) nmax += ((double)row[i] == g1[0]) ? 1.0 : 0.0;
@@ -397,65 +450,317 @@ __device__ __forceinline__ void risk_final_body(const RiskFinalParams& p, int q0
     }
 }
 
-__global__ void __launch_bounds__(RISKF_THREADS) risk_stats1_kernel(const RiskFinalParams p) {
-    pdl_prologue();
-    risk_stats1_body<RISKF_THREADS>(p, threadIdx.x, RISKF_THREADS, p.state1);
-}
-__global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskFinalParams p) {
-    pdl_prologue();
-    risk_stats2_body<RISKF_THREADS>(p, threadIdx.x, RISKF_THREADS, p.state2);
-}
-__global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskFinalParams p) {
-    pdl_prologue();
-    risk_final_body(p, threadIdx.x, RISKF_THREADS, true);
+
+// ---- constants of phase C: everything about the loss and its gradient that does not depend on the query ------------
+// d loss / d X[q, 0] = k1[0] A0_q + k0[0] + ko ce0_q + kc (+ k1[1] A1_q + k0[1] with a second column in play); see
+// risk_final_body for the derivation.  With the max - mat inversion: d loss / d mat = -(that) + share [mat == max].
+struct RiskRowConsts {
+    double k1[2], k0[2], ko, kc, share, M;
+    double t_mu, t_var, t_sd, t_Q, t_f;     // t-risk
+    float loss;
+    int nu;
+};
+
+__device__ __forceinline__ void risk_row_consts(const RiskFinalParams& p, RiskRowConsts& k) {
+    const double* g1 = p.state1;
+    const double* g2 = p.state2;
+    const double f = (double)p.negative;
+    const double Qg = g1[4];
+    k.M = g1[0];
+    if (p.kind == 2) {
+        const double mu = g2[11] / Qg;
+        const double var = (g2[12] - Qg * mu * mu) / (Qg - 1.0);
+        k.t_mu = mu; k.t_var = var; k.t_sd = sqrt(var); k.t_Q = Qg; k.t_f = f;
+        k.loss = (float)(f * mu / k.t_sd);
+        k.nu = 0;
+        return;
+    }
+    const ZCol z0 = make_zcol(p, g1, false), zl = make_zcol(p, g1, true);
+    double val[2], dz[2], dS[2];
+    for (int u = 0; u < 2; ++u) {
+        const ZCol& zc = u ? zl : z0;
+        const double zsum = g2[5 * u];
+        if (p.kind == 0) {
+            val[u] = zsum; dz[u] = 1.0; dS[u] = 0.0;
+        } else {
+            const double arg = zsum / Qg;
+            const double cdf = std_normal_cdf(arg);
+            const double geo = sqrt(zc.S / Qg * cdf);
+            const double pdf = 0.3989422804014327 * exp(-0.5 * arg * arg);
+            val[u] = geo;
+            dz[u] = (zc.S / Qg) * pdf / Qg / (2.0 * geo);
+            dS[u] = cdf / Qg / (2.0 * geo);
+        }
+    }
+    double loss, coef[2];
+    if (p.strategy == 1) {
+        loss = f * val[0]; coef[0] = f; coef[1] = 0.0;
+    } else if (p.strategy == 2) {
+        if (p.quirk) { loss = f * val[1] - val[0]; coef[1] = f; coef[0] = -1.0; }
+        else { loss = f * (val[1] - val[0]); coef[1] = f; coef[0] = -f; }
+    } else {
+        const double d = val[1] - val[0];
+        loss = f * d * d; coef[1] = 2.0 * f * d; coef[0] = -coef[1];
+    }
+    k.loss = (float)loss;
+    const int nu = (p.strategy == 1) ? 1 : 2;
+    k.nu = nu;
+    double all = 0.0;
+    k.k1[1] = k.k0[1] = 0.0;
+    k.ko = k.kc = 0.0;
+    for (int u = 0; u < nu; ++u) {
+        const ZCol& zc = u ? zl : z0;
+        const double sAT = g2[5 * u + 1], sAe = g2[5 * u + 2], sce = g2[5 * u + 3], sA = g2[5 * u + 4];
+        all += coef[u] * (dz[u] * (sce + Qg * sAT / zc.N + (double)p.C * sA * zc.S / zc.N - Qg * (double)p.C * sAe / zc.N) +
+                          dS[u] * Qg);
+        k.k1[u] = coef[u] * dz[u] * zc.S / zc.N;
+        k.k0[u] = -coef[u] * dz[u] * sAe / zc.N;
+        if (zc.col == 0) {                                   // the column the risk is taken of IS the model column
+            k.ko += coef[u] * dz[u];
+            k.kc += coef[u] * (dz[u] * sAT / zc.N + dS[u]);
+        }
+    }
+    k.share = p.invert ? all / g2[10] : 0.0;
 }
 
-// One GPU, no exchange between the phases: three launches of RISK_MC_BLOCKS small CTAs (one row per thread at 8192
-// rows) instead of one CTA that does all the fp64 divisions and square roots of the matrix on a single SM.  A phase
-// leaves its block sums in `part` (global scratch, [phase][block][RISK_STATE]); EVERY block of the next phase adds
-// them up in block order into its own shared-memory copy of the state (deterministic, no counters, no atomics:
-// the kernel boundary is the barrier), block 0 also publishes the state blocks.
-constexpr int RISK_MC_BLOCKS = 64;
-constexpr int RISK_MC_THREADS = 128;
-struct RiskMcParams {
+// d loss / d mat[q, 0] of one query from the constants, its matrix row and the terms phase B stored
+__device__ __forceinline__ float risk_row_gq(const RiskFinalParams& p, const RiskRowConsts& k, const float* row,
+                                             const double* rs) {
+    if (p.kind == 2) {
+        double d = p.invert ? (double)row[1] - (double)row[0] : (double)row[0] - (double)row[1];
+        const double c = (d < 0.0) ? 1.0 + (double)p.alpha : 1.0;
+        d *= c;
+        const double gd = k.t_f * (1.0 / (k.t_Q * k.t_sd) - k.t_mu * (d - k.t_mu) / ((k.t_Q - 1.0) * k.t_var * k.t_sd));
+        return (float)(gd * c * (p.invert ? -1.0 : 1.0));
+    }
+    double g = k.k1[0] * rs[0] + k.k0[0] + k.ko * rs[1] + k.kc;
+    if (k.nu == 2) g += k.k1[1] * rs[2] + k.k0[1];
+    if (p.invert) g = -g + (((double)row[0] == k.M) ? k.share : 0.0);
+    return (float)g;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the fused three-launch pipeline of the ListNet family
+// ---------------------------------------------------------------------------------------------------
+constexpr int RISK_B_THREADS = 128;
+constexpr int RISK_B_MAX_GRID = 128;
+
+struct RiskFusedParams {
+    RiskRowsParams r;
     RiskFinalParams f;
-    double* part;            // [2][RISK_MC_BLOCKS][RISK_STATE]
+    RiskComm c;
+    double* part1;           // [grid A][4]   per-CTA partials of the phase-1 state
+    double* part2;           // [grid B][16]  per-CTA partials of the phase-2 state
+    double* rowstate;        // [B][3]        A0_q, c0_q / sqrt(e0_q), A1_q  (phase B -> phase C)
+    unsigned* done;          // [2] finished-CTA counters in the workspace (left at 0)
 };
-__device__ __forceinline__ void risk_mc_gather(const double* part, int phase, double* dst, bool is_max0) {
-    // thread j < RISK_STATE adds entry j of every block, in block order
-    if (threadIdx.x < RISK_STATE) {
-        const double* src = part + (size_t)phase * RISK_MC_BLOCKS * RISK_STATE + threadIdx.x;
-        double t = src[0];
-        for (int b = 1; b < RISK_MC_BLOCKS; ++b) {
-            const double v = src[(size_t)b * RISK_STATE];
-            t = (is_max0 && threadIdx.x == 0) ? fmax(t, v) : t + v;
+
+// loads all of a query's rows before any arithmetic (short slates: everything fits in registers)
+template <int ITEMS, int SV>
+__device__ __forceinline__ void risk_load_bases(const float* base, int n, int S, int lane, float fill, RowRegs<ITEMS> (&pb)[SV]) {
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int i = lane + 32 * k;
+        if (SV == 2) {
+            const float2 v = (i < n) ? __ldg(reinterpret_cast<const float2*>(base) + i) : make_float2(fill, fill);
+            pb[0].v[k] = v.x; pb[1 % SV].v[k] = v.y;
+        } else if (SV == 4) {
+            const float4 v = (i < n) ? __ldg(reinterpret_cast<const float4*>(base) + i) : make_float4(fill, fill, fill, fill);
+            pb[0].v[k] = v.x; pb[1 % SV].v[k] = v.y; pb[2 % SV].v[k] = v.z; pb[3 % SV].v[k] = v.w;
+        } else {
+            pb[0].v[k] = (i < n) ? __ldg(base + (size_t)i * S) : fill;
         }
-        dst[threadIdx.x] = t;
     }
 }
-template <int PHASE>
-__global__ void __launch_bounds__(RISK_MC_THREADS) risk_mc_kernel(const RiskMcParams mp) {
-    __shared__ double st1[RISK_STATE], st2[RISK_STATE];
-    RiskFinalParams p = mp.f;
-    const int q0 = (int)blockIdx.x * RISK_MC_THREADS + (int)threadIdx.x, dq = RISK_MC_BLOCKS * RISK_MC_THREADS;
+
+// SV = 2 / 4: the S = 2 / 4 baseline scores of a doc are one 8 / 16-byte load and every load of the query is issued
+// before the first softmax; SV = 0: any S, one strided pass per system.
+template <int ITEMS, int SV>
+__global__ void __launch_bounds__(STREAM_THREADS) risk_fused_rows_kernel(const RiskFusedParams p) {
+    __shared__ double red[STREAM_WARPS][4];
+    __shared__ double st[RISK_STATE];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarp = blockIdx.x * STREAM_WARPS + warp;
+    const int nwarps = gridDim.x * STREAM_WARPS;
+    const float ninf = __int_as_float(0xff800000);
+    const RiskRowsParams& r = p.r;
+    const int C = 1 + r.S + r.add_ideal;
     pdl_prologue();
-    if (PHASE >= 2) {
-        risk_mc_gather(mp.part, 0, st1, true);
-        __syncthreads();
-        if (threadIdx.x == 0) st1[4] = (double)p.Q;              // (every block reported Q: not a sum)
-        if (PHASE == 3) risk_mc_gather(mp.part, 1, st2, false);
-        __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x < RISK_STATE) {
-            if (PHASE == 2) p.state1[threadIdx.x] = st1[threadIdx.x];
-            else p.state2[threadIdx.x] = st2[threadIdx.x];
+    double mx = -1.0e300, s0 = 0.0, sl = 0.0, sa = 0.0;       // warp-uniform
+    for (int b = gwarp; b < r.B; b += nwarps) {
+        RowRegs<ITEMS> pt, ps;
+        RowRegs<ITEMS> pb[SV ? SV : 1];
+        pt.load(r.y_true + (size_t)b * r.n, r.n, lane, ninf);
+        ps.load(r.y_pred + (size_t)b * r.n, r.n, lane, ninf);
+        if (SV) risk_load_bases<ITEMS, (SV ? SV : 1)>(r.y_base + (size_t)b * r.n * r.S, r.n, r.S, lane, ninf, pb);
+        softmax_row(pt);
+        softmax_row(ps);
+        float* mrow = r.mat + (size_t)b * C;
+        float v = effectiveness(pt, ps, r.lt, r.tmode), vlast = v;
+        if (lane == 0) mrow[0] = v;
+        s0 += (double)v;
+        sa += (double)v;
+        mx = fmax(mx, (double)v);
+        for (int j = 0; j < r.S; ++j) {
+            if (SV) {
+#pragma unroll
+                for (int jj = 0; jj < (SV ? SV : 1); ++jj)
+                    if (jj == j) {
+                        softmax_row(pb[jj]);
+                        v = effectiveness(pt, pb[jj], r.lt, r.tmode);
+                    }
+            } else {
+                pb[0].load_strided(r.y_base + (size_t)b * r.n * r.S + j, r.n, r.S, lane, ninf);
+                softmax_row(pb[0]);
+                v = effectiveness(pt, pb[0], r.lt, r.tmode);
+            }
+            if (lane == 0) mrow[1 + j] = v;
+            sa += (double)v;
+            mx = fmax(mx, (double)v);
+            vlast = v;
         }
-        p.state1 = st1;
-        p.state2 = st2;
+        if (r.add_ideal) {                             // the ideal ranking as one more system  (riskLosses.py:35-41)
+            v = effectiveness(pt, pt, r.lt, r.tmode);
+            if (lane == 0) mrow[1 + r.S] = v;
+            sa += (double)v;
+            mx = fmax(mx, (double)v);
+            vlast = v;
+        }
+        sl += (double)vlast;
     }
-    double* mine = mp.part + ((size_t)(PHASE - 1) * RISK_MC_BLOCKS + blockIdx.x) * RISK_STATE;
-    if (PHASE == 1) risk_stats1_body<RISK_MC_THREADS>(p, q0, dq, mine);
-    else if (PHASE == 2) risk_stats2_body<RISK_MC_THREADS>(p, q0, dq, mine);
-    else risk_final_body(p, q0, dq, blockIdx.x == 0);
+    // phase-1 state: CTA partial -> global; the last CTA adds the partials in index order and publishes
+    if (lane == 0) red[warp][0] = mx, red[warp][1] = s0, red[warp][2] = sl, red[warp][3] = sa;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red[0][0], a = red[0][1], l = red[0][2], t = red[0][3];
+        for (int w = 1; w < STREAM_WARPS; ++w) m = fmax(m, red[w][0]), a += red[w][1], l += red[w][2], t += red[w][3];
+        double* mine = p.part1 + (size_t)blockIdx.x * 4;
+        mine[0] = m; mine[1] = a; mine[2] = l; mine[3] = t;
+        __threadfence();
+        is_last = (atomicAdd(p.done, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < 4) {
+        double t = (warp == 0) ? -1.0e300 : 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) {
+            const double v = __ldcg(p.part1 + (size_t)i * 4 + warp);
+            t = (warp == 0) ? fmax(t, v) : t + v;
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(LTR_FULL_MASK, t, o));
+        } else {
+            t = warp_sum(t);
+        }
+        if (lane == 0) st[warp] = t;
+    } else if (tid - 128 < RISK_STATE - 4) {
+        st[4 + tid - 128] = (tid == 128) ? (double)r.B : 0.0;
+    }
+    __syncthreads();
+    risk_publish(p.c, 0, st);
+    if (tid == 0) *p.done = 0u;
+}
+
+__global__ void __launch_bounds__(RISK_B_THREADS) risk_fused_stats2_kernel(const RiskFusedParams p) {
+    __shared__ double g1[RISK_STATE], st[RISK_STATE];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_prologue();
+    risk_gather(p.c, 0, g1);
+    RiskFinalParams f = p.f;
+    f.state1 = g1;
+    double* mine = p.part2 + (size_t)blockIdx.x * RISK_STATE;
+    risk_stats2_body<RISK_B_THREADS>(f, (int)blockIdx.x * RISK_B_THREADS + tid, (int)gridDim.x * RISK_B_THREADS, mine, p.rowstate);
+    if (tid == 0) {
+        __threadfence();
+        is_last = (atomicAdd(p.done + 1, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int j = warp; j < RISK_STATE; j += RISK_B_THREADS / 32) {
+        double t = 0.0;
+        if (j < 13)
+            for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(p.part2 + (size_t)i * RISK_STATE + j);
+        t = warp_sum(t);
+        if (lane == 0) st[j] = t;
+    }
+    __syncthreads();
+    risk_publish(p.c, 1, st);
+    if (tid == 0) p.done[1] = 0u;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(STREAM_THREADS) risk_fused_bwd_kernel(const RiskFusedParams p) {
+    __shared__ double g1[RISK_STATE], g2[RISK_STATE];
+    __shared__ RiskRowConsts k;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarp = blockIdx.x * STREAM_WARPS + warp;
+    const int nwarps = gridDim.x * STREAM_WARPS;
+    const float ninf = __int_as_float(0xff800000);
+    const RiskRowsParams& r = p.r;
+    pdl_prologue();
+    risk_gather(p.c, 0, g1);
+    risk_gather(p.c, 1, g2);
+    RiskFinalParams f = p.f;
+    f.state1 = g1;
+    f.state2 = g2;
+    if (tid == 0) {
+        risk_row_consts(f, k);
+        if (blockIdx.x == 0) f.loss[0] = k.loss;
+    }
+    __syncthreads();
+    if (!r.grad) return;
+    for (int b = gwarp; b < r.B; b += nwarps) {
+        RowRegs<ITEMS> pt, ps, g;
+        pt.load(r.y_true + (size_t)b * r.n, r.n, lane, ninf);
+        ps.load(r.y_pred + (size_t)b * r.n, r.n, lane, ninf);
+        const float up = risk_row_gq(f, k, f.mat + (size_t)b * f.C, p.rowstate + (size_t)b * 3);
+        softmax_row(pt);
+        softmax_row(ps);
+        effectiveness_bwd(pt, ps, r.lt, r.tmode, up, g);
+        g.store(r.grad + (size_t)b * r.n, r.n, lane);
+    }
+}
+
+// ---- the single-CTA phase kernels of ltr_risk_phase ------------------------------------------------
+struct RiskPhaseParams {
+    RiskFinalParams f;
+    RiskComm c;
+};
+__global__ void __launch_bounds__(RISKF_THREADS) risk_stats1_kernel(const RiskPhaseParams p) {
+    __shared__ double st[RISK_STATE];
+    pdl_prologue();
+    if (threadIdx.x < RISK_STATE) st[threadIdx.x] = 0.0;
+    __syncthreads();
+    risk_stats1_body<RISKF_THREADS>(p.f, threadIdx.x, RISKF_THREADS, st);
+    __syncthreads();
+    risk_publish(p.c, 0, st);
+}
+__global__ void __launch_bounds__(RISKF_THREADS) risk_stats2_kernel(const RiskPhaseParams p) {
+    __shared__ double g1[RISK_STATE], st[RISK_STATE];
+    pdl_prologue();
+    risk_gather(p.c, 0, g1);
+    if (threadIdx.x < RISK_STATE) st[threadIdx.x] = 0.0;
+    __syncthreads();
+    RiskFinalParams f = p.f;
+    f.state1 = g1;
+    risk_stats2_body<RISKF_THREADS>(f, threadIdx.x, RISKF_THREADS, st);
+    __syncthreads();
+    risk_publish(p.c, 1, st);
+}
+__global__ void __launch_bounds__(RISKF_THREADS) risk_final_kernel(const RiskPhaseParams p) {
+    __shared__ double g1[RISK_STATE], g2[RISK_STATE];
+    pdl_prologue();
+    risk_gather(p.c, 0, g1);
+    risk_gather(p.c, 1, g2);
+    RiskFinalParams f = p.f;
+    f.state1 = g1;
+    f.state2 = g2;
+    risk_final_body(f, threadIdx.x, RISKF_THREADS, true);
 }
 
 // getGeoRiskDefault (utils/metrics.py:8-45): GeoRisk of EVERY system column of an fp64 query x system matrix, fp64
@@ -490,64 +795,49 @@ __global__ void __launch_bounds__(RISKF_THREADS) georisk_default_kernel(const do
     if (threadIdx.x == 0) out[col] = sqrt((S / (double)Q) * std_normal_cdf(Z / (double)Q));   // :41-43
 }
 
-static int risk_grid(int B) {
+
+static int risk_rows_grid(int B) {
     long long g = ((long long)B + STREAM_WARPS - 1) / STREAM_WARPS;
-    const long long cap = (long long)device_sm_count() * 8;
+    const long long cap = (long long)device_sm_count() * 8;              // 8 resident CTAs of 256 threads per SM
     if (g > cap) g = cap;
+    if (g > LTR_WS_RISK_MAX_GRID) g = LTR_WS_RISK_MAX_GRID;
     return (int)(g < 1 ? 1 : g);
 }
 
-template <bool BWD>
-static int launch_rows(const RiskRowsParams& p, cudaStream_t st) {
-    const int grid = risk_grid(p.B);
-#define LTR_ROWS(ITEMS) \
-    return BWD ? launch_pdl(risk_rows_bwd_kernel<ITEMS>, grid, STREAM_THREADS, 0, st, p) \
-               : launch_pdl(risk_rows_kernel<ITEMS>, grid, STREAM_THREADS, 0, st, p)
-    if (p.n <= 128) { LTR_ROWS(4); }
-    else if (p.n <= 256) { LTR_ROWS(8); }
-    else if (p.n <= 512) { LTR_ROWS(16); }
-    else { LTR_ROWS(32); }
-#undef LTR_ROWS
+static int fill_comm(RiskComm& c, void* xchg, int rank, int world, const void* const* peer_xchg, unsigned seq, const char* who) {
+    if (!xchg || world < 1 || world > RISK_MAX_WORLD || rank < 0 || rank >= world) return set_error(LTR_EINVAL, who);
+    c.xchg = static_cast<double*>(xchg);
+    c.rank = rank;
+    c.world = world;
+    c.p2p = (peer_xchg != nullptr && world > 1) ? 1 : 0;
+    c.seq = seq;
+    for (int r = 0; r < RISK_MAX_WORLD; ++r)
+        c.peer[r] = (c.p2p && r < world) ? static_cast<double*>(const_cast<void*>(peer_xchg[r])) : nullptr;
+    if (c.p2p) {
+        if (seq == 0) return set_error(LTR_EINVAL, who);
+        for (int r = 0; r < world; ++r)
+            if (!c.peer[r]) return set_error(LTR_EINVAL, who);
+        if (c.peer[rank] != c.xchg) return set_error(LTR_EINVAL, who);
+    }
+    return 0;
 }
 
 }  // namespace ltr
 
-LTR_API int ltr_risk_listnet_rows(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
-                                  int transformation, int add_ideal, int t_variant, float* mat, void* stream) {
-    using namespace ltr;
-    if (!y_pred || !y_true || !mat || B <= 0 || n <= 0 || S < 0 || (S > 0 && !y_baselines))
-        return set_error(LTR_EINVAL, "ltr_risk_listnet_rows: bad arguments");
-    if (transformation < 1 || transformation > 3) return set_error(LTR_EINVAL, "ltr_risk_listnet_rows: transformation must be 1..3");
-    if (n > 1024) return set_error(LTR_ETOOBIG, "ltr_risk_listnet_rows: slate longer than 1024");
-    RiskRowsParams p{y_pred, y_true, y_baselines, B, n, S, transformation, add_ideal ? 1 : 0, t_variant ? 1 : 0, mat,
-                     nullptr, nullptr};
-    const int rc = launch_rows<false>(p, reinterpret_cast<cudaStream_t>(stream));
-    return rc ? set_cuda_error(rc, "ltr_risk_listnet_rows") : 0;
-}
-
-LTR_API int ltr_risk_listnet_rows_bwd(const float* y_pred, const float* y_true, int B, int n, int transformation,
-                                      int t_variant, const float* gq, float* grad, void* stream) {
-    using namespace ltr;
-    if (!y_pred || !y_true || !gq || !grad || B <= 0 || n <= 0)
-        return set_error(LTR_EINVAL, "ltr_risk_listnet_rows_bwd: bad arguments");
-    if (transformation < 1 || transformation > 3) return set_error(LTR_EINVAL, "ltr_risk_listnet_rows_bwd: transformation must be 1..3");
-    if (n > 1024) return set_error(LTR_ETOOBIG, "ltr_risk_listnet_rows_bwd: slate longer than 1024");
-    RiskRowsParams p{y_pred, y_true, nullptr, B, n, 0, transformation, 0, t_variant ? 1 : 0, nullptr, gq, grad};
-    const int rc = launch_rows<true>(p, reinterpret_cast<cudaStream_t>(stream));
-    return rc ? set_cuda_error(rc, "ltr_risk_listnet_rows_bwd") : 0;
-}
-
-// phase = 1, 2, 3 (see K6b above); state1 / state2: RISK_STATE doubles each, on the device.
+// phase = 1, 2, 3 over a caller-provided matrix.  Query-sharded callers all-gather the inbox rows of the exchange block
+// between the phases (ltr_b200/sharding.py); Q = 0 (an empty shard) is fine: the rank contributes the neutral state.
 LTR_API int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int invert, int return_strategy,
-                           int precedence_quirk, float alpha, float negative, double* state1, double* state2,
+                           int precedence_quirk, float alpha, float negative, void* xchg, int rank, int world,
                            float* loss, float* gq, float* gmat, void* stream) {
     using namespace ltr;
-    if (!mat || Q <= 0 || C <= 0 || !state1 || !state2 || kind < 0 || kind > 2 || phase < 1 || phase > 3)
+    if ((!mat && Q > 0) || Q < 0 || C <= 0 || kind < 0 || kind > 2 || phase < 1 || phase > 3)
         return set_error(LTR_EINVAL, "ltr_risk_phase: bad arguments");
     if (kind == 2 && C < 2) return set_error(LTR_EINVAL, "ltr_risk_phase: t-risk needs the model and a baseline column");
     if (phase == 3 && !loss) return set_error(LTR_EINVAL, "ltr_risk_phase: phase 3 needs the loss pointer");
-    RiskFinalParams p{mat, Q, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state1, state2, loss, gq,
-                      gmat};
+    RiskPhaseParams p;
+    p.f = RiskFinalParams{mat, Q, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, nullptr, nullptr,
+                          loss, gq, gmat};
+    if (int rc = fill_comm(p.c, xchg, rank, world, nullptr, 0, "ltr_risk_phase: bad exchange block / rank / world")) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int rc = phase == 1 ? launch_pdl(risk_stats1_kernel, 1, RISKF_THREADS, 0, st, p)
                  : phase == 2 ? launch_pdl(risk_stats2_kernel, 1, RISKF_THREADS, 0, st, p)
@@ -555,33 +845,111 @@ LTR_API int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, 
     return rc ? set_cuda_error(rc, "ltr_risk_phase") : 0;
 }
 
-// Single-GPU fused call: rows -> the three risk phases, 64 CTAs each -> backward rows: five dependent launches issued
-// from one host call (each starts its ramp-up under the previous one's tail).
-// state: 32 + 2 * 64 * 16 = 2080 device doubles of scratch.  Query-sharded callers use the separate
-// entry points above and all-reduce the two state blocks between the phases.
+// geoRisk / zRisk / tRisk ListNet loss, forward + backward: launches A / B / C (those selected by `phases`).
 LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
                                     int transformation, int add_ideal, int kind, int invert, int return_strategy,
-                                    int precedence_quirk, float alpha, float negative, float* mat, double* state,
-                                    float* loss, float* gq, float* grad, void* stream) {
+                                    int precedence_quirk, float alpha, float negative, float* mat, double* rowstate,
+                                    float* loss, float* grad, int phases, void* xchg, int rank, int world,
+                                    const void* const* peer_xchg, unsigned seq, void* workspace, void* stream) {
     using namespace ltr;
-    if (!state || !loss || (grad && !gq)) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad arguments");
-    const int t_variant = (kind == 2) ? 1 : 0;
+    if (B < 0 || n <= 0 || S < 0 || !loss || !workspace || (phases & ~7) || !phases)
+        return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad arguments");
+    if (B > 0 && (!y_pred || !y_true || !mat || !rowstate || (S > 0 && !y_baselines)))
+        return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: null pointer");
+    if (transformation < 1 || transformation > 3) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: transformation must be 1..3");
+    if (n > 1024) return set_error(LTR_ETOOBIG, "ltr_risk_listnet_fwdbwd: slate longer than 1024");
+    if (kind < 0 || kind > 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad kind");
     const int C = 1 + S + (add_ideal ? 1 : 0);
-    int rc = ltr_risk_listnet_rows(y_pred, y_true, y_baselines, B, n, S, transformation, add_ideal, t_variant, mat, stream);
-    if (!rc) {
-        if (kind < 0 || kind > 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad kind");
-        if (kind == 2 && C < 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: t-risk needs the model and a baseline column");
-        RiskFinalParams fp{mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, state, state + 16,
-                           loss, gq, nullptr};
-        RiskMcParams mp{fp, state + 32};
-        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-        rc = launch_pdl(risk_mc_kernel<1>, RISK_MC_BLOCKS, RISK_MC_THREADS, 0, st, mp);
-        if (!rc) rc = launch_pdl(risk_mc_kernel<2>, RISK_MC_BLOCKS, RISK_MC_THREADS, 0, st, mp);
-        if (!rc) rc = launch_pdl(risk_mc_kernel<3>, RISK_MC_BLOCKS, RISK_MC_THREADS, 0, st, mp);
-        if (rc) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd");
+    if (kind == 2 && C < 2) return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: t-risk needs the model and a baseline column");
+    RiskFusedParams p;
+    p.r = RiskRowsParams{y_pred, y_true, y_baselines, B, n, S, transformation, add_ideal ? 1 : 0, (kind == 2) ? 1 : 0, mat, grad};
+    p.f = RiskFinalParams{mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, nullptr, nullptr, loss,
+                          nullptr, nullptr};
+    if (int rc = fill_comm(p.c, xchg, rank, world, peer_xchg, seq, "ltr_risk_listnet_fwdbwd: bad exchange block / rank / world / seq"))
+        return rc;
+    p.part1 = ws_risk_part1(workspace);
+    p.part2 = ws_risk_part2(workspace);
+    p.rowstate = rowstate;
+    p.done = ws_counter(workspace, LTR_WS_RISK_COUNTERS);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = risk_rows_grid(B);
+    int rc = 0;
+    if (phases & 1) {
+        const bool v2 = S == 2 && n <= 256 && reinterpret_cast<uintptr_t>(y_baselines) % 8 == 0;
+        const bool v4 = S == 4 && n <= 128 && reinterpret_cast<uintptr_t>(y_baselines) % 16 == 0;
+#define LTR_ROWS(ITEMS)                                                                                   \
+    rc = v2 ? launch_pdl(risk_fused_rows_kernel<ITEMS, 2>, grid, STREAM_THREADS, 0, st, p)                \
+       : v4 ? launch_pdl(risk_fused_rows_kernel<ITEMS, 4>, grid, STREAM_THREADS, 0, st, p)                \
+            : launch_pdl(risk_fused_rows_kernel<ITEMS, 0>, grid, STREAM_THREADS, 0, st, p)
+        if (n <= 128) { LTR_ROWS(4); }
+        else if (n <= 256) { LTR_ROWS(8); }
+        else if (n <= 512) { rc = launch_pdl(risk_fused_rows_kernel<16, 0>, grid, STREAM_THREADS, 0, st, p); }
+        else { rc = launch_pdl(risk_fused_rows_kernel<32, 0>, grid, STREAM_THREADS, 0, st, p); }
+#undef LTR_ROWS
+        if (rc) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd (rows)");
     }
-    if (!rc && grad) rc = ltr_risk_listnet_rows_bwd(y_pred, y_true, B, n, transformation, t_variant, gq, grad, stream);
-    return rc;
+    if (phases & 2) {
+        int g2 = (B + RISK_B_THREADS - 1) / RISK_B_THREADS;
+        g2 = g2 < 1 ? 1 : (g2 > RISK_B_MAX_GRID ? RISK_B_MAX_GRID : g2);
+        rc = launch_pdl(risk_fused_stats2_kernel, g2, RISK_B_THREADS, 0, st, p);
+        if (rc) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd (stats)");
+    }
+    if (phases & 4) {
+        const int g3 = grad ? grid : 1;
+        if (n <= 128) rc = launch_pdl(risk_fused_bwd_kernel<4>, g3, STREAM_THREADS, 0, st, p);
+        else if (n <= 256) rc = launch_pdl(risk_fused_bwd_kernel<8>, g3, STREAM_THREADS, 0, st, p);
+        else if (n <= 512) rc = launch_pdl(risk_fused_bwd_kernel<16>, g3, STREAM_THREADS, 0, st, p);
+        else rc = launch_pdl(risk_fused_bwd_kernel<32>, g3, STREAM_THREADS, 0, st, p);
+        if (rc) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd (backward)");
+    }
+    return 0;
+}
+
+// ---- exchange blocks in peer-mappable memory (CUDA IPC) ----------------------------------------------
+LTR_API int ltr_risk_xchg_alloc(void** xchg) {
+    using namespace ltr;
+    if (!xchg) return set_error(LTR_EINVAL, "ltr_risk_xchg_alloc: null pointer");
+    LTR_CUDA(cudaMalloc(xchg, LTR_RISK_XCHG_BYTES));
+    LTR_CUDA(cudaMemset(*xchg, 0, LTR_RISK_XCHG_BYTES));
+    LTR_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+LTR_API int ltr_risk_xchg_free(void* xchg) {
+    using namespace ltr;
+    LTR_CUDA(cudaFree(xchg));
+    return 0;
+}
+LTR_API int ltr_ipc_export(void* dptr, unsigned char* handle64) {
+    using namespace ltr;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!dptr || !handle64) return set_error(LTR_EINVAL, "ltr_ipc_export: null pointer");
+    cudaIpcMemHandle_t h;
+    LTR_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+LTR_API int ltr_ipc_open(const unsigned char* handle64, void** dptr) {
+    using namespace ltr;
+    if (!dptr || !handle64) return set_error(LTR_EINVAL, "ltr_ipc_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    LTR_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+LTR_API int ltr_ipc_close(void* dptr) {
+    using namespace ltr;
+    LTR_CUDA(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+// status word of an exchange block (0 = fine, 1 = a peer's state never arrived within the spin limit); synchronous
+LTR_API int ltr_risk_xchg_status(const void* xchg, int* status) {
+    using namespace ltr;
+    if (!xchg || !status) return set_error(LTR_EINVAL, "ltr_risk_xchg_status: null pointer");
+    unsigned v = 0;
+    LTR_CUDA(cudaMemcpy(&v, reinterpret_cast<const unsigned*>(static_cast<const double*>(xchg) + RISK_XCHG_WORDS_AT) + RISK_W_STATUS,
+                        sizeof(v), cudaMemcpyDeviceToHost));
+    *status = (int)v;
+    return 0;
 }
 
 // getGeoRiskDefault: mat [Q, C] device doubles -> out [C] device doubles (GeoRisk of every column).

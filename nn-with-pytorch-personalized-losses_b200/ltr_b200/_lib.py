@@ -6,12 +6,14 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LTR_B200_LIB") or os.path.join(_HERE, "lib", "libltr_b200.so")   # (override: A/B builds)
 
 WORKSPACE_BYTES = 131072
+RISK_XCHG_BYTES = 8192
+RISK_MAX_WORLD = 16
 
 _P = c_void_p
 _SIGNATURES = {
@@ -36,18 +38,22 @@ _SIGNATURES = {
     "ltr_order_score_fwdbwd": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     "ltr_lambda_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, c_int,
                                   _P, _P, _P, _P, _P, _P, _P]),
-    "ltr_risk_listnet_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
-    "ltr_risk_listnet_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "ltr_risk_lambda_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "ltr_risk_lambda_rows_bwd": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ltr_lambda_pair_matrix": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int, _P,
                                        _P, _P]),
     "ltr_lambda_pair_matrix_bwd": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_float, c_int,
                                            _P, _P, _P]),
-    "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
-                               _P, _P]),
+    "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, c_int,
+                               _P, _P, _P, _P]),
     "ltr_risk_listnet_fwdbwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                        c_float, _P, _P, _P, _P, _P, _P]),
+                                        c_float, _P, _P, _P, _P, c_int, _P, c_int, c_int, POINTER(c_void_p), c_uint, _P, _P]),
+    "ltr_risk_xchg_alloc": (c_int, [POINTER(c_void_p)]),
+    "ltr_risk_xchg_free": (c_int, [_P]),
+    "ltr_ipc_export": (c_int, [_P, _P]),
+    "ltr_ipc_open": (c_int, [_P, POINTER(c_void_p)]),
+    "ltr_ipc_close": (c_int, [_P]),
+    "ltr_risk_xchg_status": (c_int, [_P, POINTER(c_int)]),
     "ltr_georisk_default_f64": (c_int, [_P, c_int, c_int, c_double, _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
     "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),

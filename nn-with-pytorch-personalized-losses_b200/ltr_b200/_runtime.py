@@ -10,6 +10,7 @@ from . import _lib
 
 _DISC_LEN = 16384 + 1
 _workspaces = {}
+_risk_blocks = {}
 _disc_tables = {}
 
 
@@ -30,6 +31,17 @@ def workspace(device: torch.device) -> torch.Tensor:
         ws = torch.zeros(_lib.WORKSPACE_BYTES // 4, dtype=torch.int32, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def risk_xchg(device: torch.device) -> torch.Tensor:
+    """Zero-initialised exchange block of the risk phases (include/ltr_b200.h: LTR_RISK_XCHG_BYTES) owned by one
+    (device, stream), as fp64 words: [0 : 2*16*16] is inbox[round][rank][16]."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr())
+    blk = _risk_blocks.get(key)
+    if blk is None:
+        blk = torch.zeros(_lib.RISK_XCHG_BYTES // 8, dtype=torch.float64, device=device)
+        _risk_blocks[key] = blk
+    return blk
 
 
 def disc_prefix(device: torch.device) -> torch.Tensor:

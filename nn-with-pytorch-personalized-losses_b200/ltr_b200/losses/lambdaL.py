@@ -46,19 +46,30 @@ def lambdaMask(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_
 
 
 def lambdaLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, weighing_scheme=None, k=None,
-               sigma=1., mu=10., reduction="sum", reduction_log="binary"):
+               sigma=1., mu=10., reduction="sum", reduction_log="binary", process_group=None):
     """LambdaLoss (Wang et al., "The LambdaLoss Framework for Ranking Metric Optimization"): -sum / -mean over the
     pairs (i, j) of real docs with label_i > label_j and both rank positions < k of log_b(sigmoid(sigma (s_i - s_j))^w_ij),
     w_ij given by `weighing_scheme` (None, ndcgLoss1_scheme, ndcgLoss2_scheme, lamdbaRank_scheme, ndcgLoss2PP_scheme
     with weight `mu`, rankNet_scheme, rankNetWeightedByGTDiff_scheme, rankNetWeightedByGTDiffPowed_scheme).
     y_pred, y_true: [batch, slate]; labels equal to `padded_value_indicator` mark padding; `reduction` is "sum" or
     "mean", `reduction_log` "binary" or "natural".  Returns a 0-dim tensor attached to autograd.
+    `process_group` (extension, query-sharded runs): with reduction="mean" the reference divides by the
+    number of masked pairs of the WHOLE batch (lambdaL.py:88-89); every rank then returns its own sum divided by the
+    all-reduced global pair count, so that the ranks' values (and gradients) add up to the single-process ones.
+    With reduction="sum" the ranks' values add up as they are (under DistributedDataParallel, which AVERAGES
+    gradients, scale the loss by the world size in both cases).
     """
     scheme = _scheme_id(weighing_scheme)
     if reduction_log not in ("natural", "binary"):
         raise ValueError("Reduction logarithm base can be either natural or binary")      # lambdaL.py:57
     if reduction not in ("sum", "mean"):
         raise ValueError("Reduction method can be either sum or mean")                    # lambdaL.py:91
+    from .. import sharding
+    if reduction == "mean" and sharding.is_sharded(process_group):
+        total, pairs = ops.lambda_loss_and_count(to_device(y_pred), to_device(y_true.detach()), eps,
+                                                 float(padded_value_indicator), scheme, _k_arg(k), sigma, mu,
+                                                 reduction_log == "natural")
+        return back_to(total / sharding.global_sum(pairs, process_group), y_pred)
     loss = ops.lambda_loss(to_device(y_pred), to_device(y_true.detach()), eps, float(padded_value_indicator), scheme,
                            _k_arg(k), sigma, mu, reduction == "mean", reduction_log == "natural")
     return back_to(loss, y_pred)

@@ -169,16 +169,23 @@ class _Lambda(torch.autograd.Function):
                                          rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_lambda_fwdbwd")
         ctx.grad = grad
         ctx.slate_sums = sums
-        return out[0].reshape(())
+        count = out[1].reshape(())
+        ctx.mark_non_differentiable(count)
+        return out[0].reshape(()), count
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _grad_count):
         return ((ctx.grad * grad_out if ctx.grad is not None else None),) + (None,) * 9
 
 
 def lambda_loss(y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural):
-    return _Lambda.apply(y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural)
+    return _Lambda.apply(y_pred, y_true, eps, pad, scheme, k, sigma, mu, mean, natural)[0]
+
+
+def lambda_loss_and_count(y_pred, y_true, eps, pad, scheme, k, sigma, mu, natural):
+    """(-sum of the masked pair log-probabilities, attached to autograd; number of masked pairs) of the local slates."""
+    return _Lambda.apply(y_pred, y_true, eps, pad, scheme, k, sigma, mu, False, natural)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,29 +327,31 @@ KIND_Z, KIND_GEO, KIND_T = 0, 1, 2
 
 @_guard
 def _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, want_gq, want_gmat, group=None):
-    """Runs the three phases of ltr_risk_phase on the local rows `mat` [Q, C]; with a process group the
-    16-double state blocks are all-reduced between the phases (NCCL on the current stream): MAX for the
-    matrix-wide max, SUM for everything else.  Returns (loss[1], gq[Q] or None, gmat[Q, C] or None)."""
+    """Runs the three phases of ltr_risk_phase on the local rows `mat` [Q, C] (Q = 0: an empty shard); with a process
+    group the ranks' phase states are all-gathered between the phases (one collective per round, on the current
+    stream) and every rank combines them in rank order.  Returns (loss[1], gq[Q] or None, gmat[Q, C] or None)."""
     lib = _lib.load()
     Q, C = mat.shape
     dev = mat.device
-    state = torch.zeros(2, 16, dtype=torch.float64, device=dev)
+    xchg = rt.risk_xchg(dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     gq = torch.empty(Q, dtype=torch.float32, device=dev) if want_gq else None
     gmat = torch.empty(Q, C, dtype=torch.float32, device=dev) if want_gmat else None
     sharded = sharding.is_sharded(group)
+    rank, world = sharding.rank_world(group)
 
     def phase(i):
-        _lib.check(lib.ltr_risk_phase(i, mat.data_ptr(), Q, C, int(kind), int(invert), int(strategy), int(quirk),
-                                      float(alpha), float(negative), state[0].data_ptr(), state[1].data_ptr(),
-                                      loss.data_ptr(), _ptr(gq), _ptr(gmat), rt.stream_ptr()), "ltr_risk_phase")
+        _lib.check(lib.ltr_risk_phase(i, mat.data_ptr() if Q else None, Q, C, int(kind), int(invert), int(strategy),
+                                      int(quirk), float(alpha), float(negative), xchg.data_ptr(), rank, world,
+                                      loss.data_ptr(), _ptr(gq) if Q else None, _ptr(gmat) if Q else None,
+                                      rt.stream_ptr()), "ltr_risk_phase")
 
     phase(1)
     if sharded:
-        sharding.allreduce_risk_state1(state[0], group)
+        sharding.allgather_risk_round(xchg, 0, group)
     phase(2)
     if sharded:
-        sharding.allreduce_risk_state2(state[1], group)
+        sharding.allgather_risk_round(xchg, 1, group)
     phase(3)
     return loss, gq, gmat
 
@@ -369,6 +378,11 @@ def risk_fn(mat, kind, alpha):
 
 
 class _RiskListnet(torch.autograd.Function):
+    """geoRisk / zRisk / tRisk ListNet losses: `ltr_risk_listnet_fwdbwd`, three launches (rows + phase-1 state, z-risk
+    sums, loss + backward rows).  Query-sharded (`group`): the ranks' phase states are exchanged either inside the
+    kernels over NVLink peer memory (sharding.RiskPeerExchange: no collective, one library call) or, when peer
+    memory is not available, by one all-gather per round between the launches."""
+
     @staticmethod
     @_guard
     def forward(ctx, y_pred, y_true, y_base, kind, alpha, lt, strategy, negative, add_ideal, quirk, group):
@@ -376,35 +390,37 @@ class _RiskListnet(torch.autograd.Function):
         B, n = y_pred.shape
         dev = y_pred.device
         S = 0 if y_base is None else y_base.shape[2]
-        tvar = 1 if kind == KIND_T else 0
         C = 1 + S + (1 if add_ideal else 0)
         mat = torch.empty(B, C, dtype=torch.float32, device=dev)
+        rowstate = torch.empty(max(B, 1), 3, dtype=torch.float64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
         # mat <- max(mat) - mat: riskLosses.py:49-50 (lt 1, 3) and :274-275 (t-risk: lt 1 only)
         invert = (lt == 1) if kind == KIND_T else (lt in (1, 3))
         need = ctx.needs_input_grad[0]
-        if not sharding.is_sharded(group):
-            # one GPU: the five dependent launches are issued by one library call
-            scratch = torch.empty(2080 * 2 + 1 + B, dtype=torch.float32, device=dev)   # 2080 doubles | loss | gq
-            state, loss, gq = scratch[:4160].view(torch.float64), scratch[4160:4161], scratch[4161:]
-            grad = torch.empty_like(y_pred) if need else None
-            _lib.check(lib.ltr_risk_listnet_fwdbwd(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
-                                                   int(bool(add_ideal)), int(kind), int(invert), int(strategy), int(quirk),
-                                                   float(alpha), float(negative), mat.data_ptr(), state.data_ptr(),
-                                                   loss.data_ptr(), gq.data_ptr(), _ptr(grad), rt.stream_ptr()),
-                       "ltr_risk_listnet_fwdbwd")
-            ctx.grad = grad
-            ctx.mat = mat
-            return loss
-        _lib.check(lib.ltr_risk_listnet_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
-                                             int(bool(add_ideal)), tvar, mat.data_ptr(), rt.stream_ptr()),
-                   "ltr_risk_listnet_rows")
-        loss, gq, _ = _risk_phases(mat, kind, invert, strategy, quirk, alpha, negative, need, False, group)
-        grad = None
-        if need:
-            grad = torch.empty_like(y_pred)
-            _lib.check(lib.ltr_risk_listnet_rows_bwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, int(lt), tvar,
-                                                     gq.data_ptr(), grad.data_ptr(), rt.stream_ptr()),
-                       "ltr_risk_listnet_rows_bwd")
+        grad = torch.empty_like(y_pred) if need else None
+        sharded = sharding.is_sharded(group)
+        rank, world = sharding.rank_world(group)
+        peers = sharding.risk_peer_exchange(group, dev) if sharded else None
+
+        def call(phases, xchg_ptr, peer_ptrs, seq):
+            _lib.check(lib.ltr_risk_listnet_fwdbwd(
+                y_pred.data_ptr() if B else None, y_true.data_ptr() if B else None, _ptr(y_base) if B else None, B, n, S,
+                int(lt), int(bool(add_ideal)), int(kind), int(invert), int(strategy), int(quirk), float(alpha),
+                float(negative), mat.data_ptr() if B else None, rowstate.data_ptr(), loss.data_ptr(),
+                _ptr(grad) if B else None, phases, xchg_ptr, rank, world, peer_ptrs, seq,
+                rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_risk_listnet_fwdbwd")
+
+        if peers is not None:
+            call(7, peers.local_ptr, peers.peer_ptrs, peers.next_seq())
+        elif sharded:
+            xchg = rt.risk_xchg(dev)
+            call(1, xchg.data_ptr(), None, 0)
+            sharding.allgather_risk_round(xchg, 0, group)
+            call(2, xchg.data_ptr(), None, 0)
+            sharding.allgather_risk_round(xchg, 1, group)
+            call(4, xchg.data_ptr(), None, 0)
+        else:
+            call(7, rt.risk_xchg(dev).data_ptr(), None, 0)
         ctx.grad = grad
         ctx.mat = mat
         return loss
@@ -431,14 +447,16 @@ class _RiskLambda(torch.autograd.Function):
         need = ctx.needs_input_grad[0]
         mat = torch.empty(B, C, dtype=torch.float32, device=dev)
         dvec = torch.empty(B, n, dtype=torch.float32, device=dev) if need else None
-        _lib.check(lib.ltr_risk_lambda_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
-                                            int(bool(add_ideal)), int(kind == KIND_GEO), int(scheme), mat.data_ptr(),
-                                            _ptr(dvec), rt.stream_ptr()), "ltr_risk_lambda_rows")
+        if B > 0:                                            # (B = 0: an empty shard still joins both exchange rounds)
+            _lib.check(lib.ltr_risk_lambda_rows(y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), B, n, S, int(lt),
+                                                int(bool(add_ideal)), int(kind == KIND_GEO), int(scheme), mat.data_ptr(),
+                                                _ptr(dvec), rt.stream_ptr()), "ltr_risk_lambda_rows")
         invert = (lt == 1)                                   # riskLosses.py:114-115, :335
         loss, gq, _ = _risk_phases(mat, kind, invert, strategy, 0, alpha, negative, need, False, group)
         grad = None
         if need:
             grad = torch.empty_like(y_pred)
+        if need and B > 0:
             _lib.check(lib.ltr_risk_lambda_rows_bwd(y_pred.data_ptr(), y_true.data_ptr(), B, n, int(scheme),
                                                     gq.data_ptr(), dvec.data_ptr(), grad.data_ptr(), rt.stream_ptr()),
                        "ltr_risk_lambda_rows_bwd")

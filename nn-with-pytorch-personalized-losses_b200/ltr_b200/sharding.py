@@ -2,25 +2,34 @@
 
 Slates are independent, so every loss / metric kernel runs on a contiguous range of queries per rank with no
 data-path collective.  The only exchange steps on the path are
-  * the risk losses' matrix-wide statistics: two tiny all-reduces between the three phases of `ltr_risk_phase`
-    (MAX of the matrix maximum, SUM of the column / row totals and of the z-risk partial sums), and
-  * scalar bookkeeping when a global value is wanted (mean of per-rank means, global pair count of
+  * the risk losses' matrix-wide statistics: two rounds of 16 doubles per rank (round 0: MAX of the matrix maximum,
+    SUM of the column / row totals and the query count; round 1: SUM of the z-risk partial sums).  Either the
+    kernels exchange them themselves over NVLink peer memory (`RiskPeerExchange`: every rank's exchange block is
+    mapped into every process with CUDA IPC, the last CTA of a phase stores its state into all peers' inboxes and
+    the next phase spins on sequence-numbered flags -- no collective call at all), or, without peer memory, ONE
+    all-gather per round between the phase launches (`allgather_risk_round`: NCCL on the GPUs, gloo in the CPU tests);
+  * scalar bookkeeping when a global value is wanted (mean of per-rank means, the global pair count of
     lambdaLoss(reduction="mean")).
-Everything here is host-side plumbing over `torch.distributed` (NCCL on the GPUs, gloo in the CPU tests).
+Everything here is host-side plumbing over `torch.distributed` and the C-ABI.
 """
 from __future__ import annotations
+
+import ctypes
+import os
 
 import torch
 import torch.distributed as dist
 
-# layout of the two 16-double state blocks of ltr_risk_phase (include/ltr_b200.h)
-STATE1_MAX = slice(0, 1)      # max(mat)                                  -> MAX
-STATE1_SUMS = slice(1, 5)     # sum mat[:,0], sum mat[:,C-1], sum(mat), Q -> SUM
-STATE2_SUMS = slice(0, 13)    # z-risk partial sums, #maxima, t-risk sums -> SUM
+from . import _lib
+
+RISK_STATE = 16                       # doubles per phase state (include/ltr_b200.h)
+RISK_MAX_WORLD = _lib.RISK_MAX_WORLD  # ranks an exchange block has room for
 
 
 def shard_bounds(total: int, rank: int, world: int):
-    """Contiguous, balanced range [lo, hi) of `total` queries owned by `rank` (first `total % world` ranks get one more)."""
+    """Contiguous, balanced range [lo, hi) of `total` queries owned by `rank` (first `total % world` ranks get one
+    more).  With total < world the last ranks get an EMPTY range: the risk losses accept it (the rank contributes the
+    neutral state to both exchange rounds), every other loss is simply not called for it."""
     base, extra = divmod(total, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
@@ -30,14 +39,108 @@ def is_sharded(group) -> bool:
     return group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
-def allreduce_risk_state1(state1: torch.Tensor, group) -> None:
-    """In place: phase-1 state of every rank -> the global one."""
-    dist.all_reduce(state1[STATE1_MAX], op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(state1[STATE1_SUMS], op=dist.ReduceOp.SUM, group=group)
+def rank_world(group):
+    if not is_sharded(group):
+        return 0, 1
+    world = dist.get_world_size(group)
+    if world > RISK_MAX_WORLD:
+        raise ValueError(f"the risk exchange block has room for {RISK_MAX_WORLD} ranks, got {world}")
+    return dist.get_rank(group), world
 
 
-def allreduce_risk_state2(state2: torch.Tensor, group) -> None:
-    dist.all_reduce(state2[STATE2_SUMS], op=dist.ReduceOp.SUM, group=group)
+def risk_inbox(xchg: torch.Tensor, slot: int) -> torch.Tensor:
+    """[RISK_MAX_WORLD, 16] view of round `slot` of an exchange block (fp64 words)."""
+    n = RISK_MAX_WORLD * RISK_STATE
+    return xchg[slot * n:(slot + 1) * n].view(RISK_MAX_WORLD, RISK_STATE)
+
+
+def allgather_risk_round(xchg: torch.Tensor, slot: int, group) -> None:
+    """In place: row `rank` of round `slot` of every rank's exchange block -> rows 0..world-1 of everybody's.
+    One collective (the kernels of the next phase combine the rows themselves, MAX / SUM in rank order, so every
+    rank gets bit-identical totals)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    inbox = risk_inbox(xchg, slot)
+    mine = inbox[rank]
+    if xchg.device.type != "cuda":
+        mine = mine.clone()                       # (gloo copies the input into the output first: no aliasing there)
+    dist.all_gather_into_tensor(inbox[:world].reshape(-1), mine, group=group)
+
+
+class RiskPeerExchange:
+    """Every rank's exchange block mapped into this process (CUDA IPC over NVLink / PCIe peer access), so that
+    `ltr_risk_listnet_fwdbwd` exchanges the phase states inside its kernels.  Collective constructor: every rank of
+    `group` must build it at the same point (the 64-byte IPC handles travel by all_gather_object, any backend)."""
+
+    def __init__(self, group, device: torch.device):
+        lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        self._lib = lib
+        local = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.ltr_risk_xchg_alloc(ctypes.byref(local)), "ltr_risk_xchg_alloc")
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.ltr_ipc_export(local, handle), "ltr_ipc_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self.local_ptr = local.value
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(local.value)
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                peer = ctypes.c_void_p()
+                _lib.check(lib.ltr_ipc_open(buf, ctypes.byref(peer)), "ltr_ipc_open")
+                ptrs.append(peer.value)
+        self._ptrs = ptrs
+        self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.seq = 0
+        dist.barrier(group=group)                 # nobody publishes before everybody has mapped everybody
+
+    def next_seq(self) -> int:
+        self.seq = self.seq % 0x7FFFFFFF + 1      # never 0, never equal to the previous call's
+        return self.seq
+
+    def status(self) -> int:
+        st = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ltr_risk_xchg_status(self.local_ptr, ctypes.byref(st)), "ltr_risk_xchg_status")
+        return st.value
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for r, p in enumerate(self._ptrs):
+                if r != self.rank and p:
+                    self._lib.ltr_ipc_close(p)
+            self._lib.ltr_risk_xchg_free(self.local_ptr)
+        self._ptrs = []
+
+
+_peer_exchanges = {}
+
+
+def risk_peer_exchange(group, device: torch.device):
+    """The (cached) peer exchange of `group` on `device`, or None when in-kernel exchange is switched off
+    (LTR_RISK_P2P=0) or the peers' memory cannot be mapped -- the callers then all-gather between the phases.
+    The first call per group is collective."""
+    if os.environ.get("LTR_RISK_P2P", "1") == "0":
+        return None
+    key = (id(group), device.index)
+    if key not in _peer_exchanges:
+        try:
+            ok, ex = 1, RiskPeerExchange(group, device)
+        except _lib.LtrError:
+            ok, ex = 0, None
+        # all or nothing: one rank without peer access sends everybody to the all-gather path
+        flag = torch.tensor([ok], dtype=torch.int32, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) == 0 and ex is not None:
+            ex.close()
+            ex = None
+        _peer_exchanges[key] = ex
+    return _peer_exchanges[key]
 
 
 def global_mean(local_mean: torch.Tensor, local_count: int, group) -> torch.Tensor:
@@ -53,3 +156,12 @@ def global_sum(local: torch.Tensor, group) -> torch.Tensor:
     buf = local.detach().clone()
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf
+
+
+def global_pair_mean(local_sum: torch.Tensor, local_pairs: torch.Tensor, group) -> torch.Tensor:
+    """lambdaLoss(reduction="mean") over query-sharded slates (lambdaL.py:88-89 divides by the GLOBAL number of masked
+    pairs): from every rank's (-sum of pair log-probabilities, number of masked pairs) -> the global mean loss.
+    One all-reduce of two doubles."""
+    buf = torch.stack([local_sum.detach().reshape(()).double(), local_pairs.detach().reshape(()).double()])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return (buf[0] / buf[1]).to(local_sum.dtype)

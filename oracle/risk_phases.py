@@ -2,7 +2,7 @@
 
 numpy fp64 version of what `ltr_risk_phase` (csrc/risk.cu) computes from a shard of the query x system matrix,
 with the same 16-double state layout, so that the query-sharded exchange (ltr_b200/sharding.py) can be exercised
-on CPU with gloo: per-rank phase-1 / phase-2 states, all-reduced, must give the value the reference's
+on CPU with gloo: per-rank phase-1 / phase-2 states, all-gathered and combined in rank order, must give the value the reference's
 riskFunctions.zRisk / geoRisk (losses/riskLosses/riskFunctions.py:4-33) give on the unsharded matrix.
 Forward values only; imported by tests/ only.
 """
@@ -14,12 +14,29 @@ import numpy as np
 def state1(mat):
     mat = np.asarray(mat, dtype=np.float64)
     s = np.zeros(16)
+    if mat.shape[0] == 0:                      # an empty shard: the neutral state
+        s[0] = -1.0e300
+        return s
     s[0] = mat.max()
     s[1] = mat[:, 0].sum()
     s[2] = mat[:, -1].sum()
     s[3] = mat.sum()
     s[4] = mat.shape[0]
     return s
+
+
+def combine(rows, slot):
+    """The ranks' states of one exchange round -> the global state, as the kernels combine them (csrc/risk.cu
+    risk_gather): in rank order, entry 0 of round 0 is a MAX (an empty shard contributes -1e300), everything else a SUM."""
+    rows = np.asarray(rows, dtype=np.float64)
+    out = rows[0].copy()
+    for r in rows[1:]:
+        if slot == 0:
+            out[0] = max(out[0], r[0])
+            out[1:] += r[1:]
+        else:
+            out += r
+    return out
 
 
 def _zcol(mat, g1, last, invert, alpha):
@@ -40,6 +57,8 @@ def _zcol(mat, g1, last, invert, alpha):
 
 def state2(mat, g1, invert, alpha, strategy):
     s = np.zeros(16)
+    if np.asarray(mat).shape[0] == 0:
+        return s
     _, z, c = _zcol(mat, g1, False, invert, alpha)
     s[0] = (z * c).sum()
     if strategy != 1:

@@ -18,14 +18,17 @@ def pytest_configure(config):
 
 
 class Golden:
-    """Golden vectors produced by tests/golden/make_golden.py from the unmodified reference."""
+    """Golden vectors produced by tests/golden/make_golden.py and make_golden_v2.py from the unmodified reference."""
 
     def __init__(self):
         here = os.path.join(ROOT, "tests", "golden")
-        with open(os.path.join(here, "golden_v1.json")) as f:
-            self.meta = json.load(f)
-        self.arrays = np.load(os.path.join(here, "golden_v1.npz"))
-        self.cases = {c["name"]: c for c in self.meta["cases"]}
+        self.cases, self.arrays = {}, {}
+        for version in ("golden_v1", "golden_v2"):        # v2: round-2 additions (make_golden_v2.py), v1 untouched
+            with open(os.path.join(here, version + ".json")) as f:
+                meta = json.load(f)
+            npz = np.load(os.path.join(here, version + ".npz"))
+            self.arrays.update({k: npz[k] for k in npz.files})
+            self.cases.update({c["name"]: c for c in meta["cases"]})
 
     def names(self, prefix):
         return [n for n in self.cases if n.startswith(prefix)]

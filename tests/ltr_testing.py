@@ -34,10 +34,12 @@ def assert_loss_close(got, ref, rtol=LOSS_RTOL, atol=1e-7, ref64=None):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape, (got.shape, ref.shape)
-    err = np.abs(got - ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), f"NaN pattern differs: got {got}, ref {ref}"
+    err = np.where(np.isnan(ref), 0.0, np.abs(got - ref))
     tol = rtol * np.abs(ref) + atol
     if ref64 is not None:
-        tol = tol + 2.0 * np.abs(ref - np.asarray(ref64, dtype=np.float64))
+        tol = tol + 2.0 * np.nan_to_num(np.abs(ref - np.asarray(ref64, dtype=np.float64)))
+    tol = np.nan_to_num(tol)
     assert np.all(err <= tol), f"loss mismatch: got {got}, ref {ref}, rel {err / (np.abs(ref) + 1e-30)}"
 
 

@@ -399,7 +399,7 @@ def test_validation_epilogue_matches_driver_block():
 
 # ---- NDCG@k sweep: every fast-path kernel against the oracle and against the full-sort path ---------------------
 @pytest.mark.parametrize("Q,n,ks,kw", [
-    (257, 128, (1, 5, 10), {}),                       # quad-maxima kernel (one resident wave)
+    (257, 128, (1, 5, 10), {}),                       # label-in-key kernel (rows of one chunk)
     (257, 128, (10,), dict(ties=True)),               # every query marked -> std::sort replay
     (100, 64, (1, 3, 10), {}),                        # fewer than 11 quads with >= 11 docs
     (100, 40, (5, 10), {}),                           # L = -inf: every doc is a candidate
@@ -480,8 +480,9 @@ def test_ndcg_sweep_near_ties_and_crowded_quads():
 
 
 def test_ndcg_sweep_large_eval_set_matches_small_batches():
-    """More queries than one resident wave of the quad-maxima kernel (75,776): the score-tile kernel takes the whole
-    set; it must reproduce, bit for bit, what the quad-maxima kernel returns for the same queries in slices."""
+    """More tiles than the label-in-key kernel's resident grid (148 x 4 CTAs x 4 warps): tiles wrap around the grid
+    (tile t -> CTA t % grid); the result must equal, bit for bit, the same queries evaluated in slices, and an oracle
+    sample (the 2^20-query case with an oracle sample is tests/test_round2_gpu.py)."""
     from ltr_b200.utils.metrics import ndcg_sweep
     Q, n = 90000, 128
     s, y = make_slates(Q, n, seed=99)
@@ -489,3 +490,8 @@ def test_ndcg_sweep_large_eval_set_matches_small_batches():
     whole = ndcg_sweep(yd, sd, ks=(1, 5, 10))
     parts = torch.cat([ndcg_sweep(yd[i:i + 30000], sd[i:i + 30000], ks=(1, 5, 10)) for i in range(0, Q, 30000)])
     assert torch.equal(torch.nan_to_num(whole), torch.nan_to_num(parts))
+    from oracle import ltr_oracle as O
+    idx = torch.arange(0, Q, 353)
+    ref = np.array([float(v) for v in O.torch_ndcg(y[idx], s[idx], k=10, return_type="list")], dtype=np.float32)
+    got = whole[idx.cuda(), 2].cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(got)], ref[~np.isnan(ref)])

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_q):
+def _worker(rank, world, port, p2p, out_q):
     import sys
     for p in (ROOT, PKG_ROOT):
         if p not in sys.path:
@@ -31,6 +31,7 @@ def _worker(rank, world, port, out_q):
     from ltr_b200.losses.riskLosses import riskLosses as RL
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["LTR_RISK_P2P"] = "1" if p2p else "0"      # in-kernel exchange over NVLink peer memory / one all-gather per round
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -57,13 +58,19 @@ def _worker(rank, world, port, out_q):
         res["approx_mean"] = float(sharding.global_mean(la, hi - lo, dist.group.WORLD))
         ll = lambdaLoss(sl, yl, weighing_scheme="ndcgLoss2PP_scheme")
         res["lambda_sum"] = float(sharding.global_sum(ll, dist.group.WORLD))
+        lm = lambdaLoss(sl, yl, weighing_scheme="ndcgLoss2PP_scheme", reduction="mean", process_group=dist.group.WORLD)
+        res["lambda_mean"] = float(sharding.global_sum(lm, dist.group.WORLD))
+        ex = sharding.risk_peer_exchange(dist.group.WORLD, torch.device("cuda", rank))
+        res["p2p_used"] = ex is not None
+        res["status"] = ex.status() if ex is not None else 0
         out_q.put((rank, (lo, hi), res))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_query_sharded_losses_match_single_gpu():
+@pytest.mark.parametrize("p2p", [True, False])
+def test_query_sharded_losses_match_single_gpu(p2p):
     import torch.multiprocessing as mp
     from ltr_b200.losses.approxNDCG import approxNDCGLoss
     from ltr_b200.losses.lambdaL import lambdaLoss
@@ -73,7 +80,7 @@ def test_query_sharded_losses_match_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, p2p, q)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=300) for _ in procs])
@@ -103,3 +110,6 @@ def test_query_sharded_losses_match_single_gpu():
         assert abs(res["approx_mean"] - float(a)) <= 1e-6 * abs(float(a))
         ls = lambdaLoss(s.cuda(), y.cuda(), weighing_scheme="ndcgLoss2PP_scheme")
         assert abs(res["lambda_sum"] - float(ls)) <= 1e-5 * abs(float(ls))
+        lm = lambdaLoss(s.cuda(), y.cuda(), weighing_scheme="ndcgLoss2PP_scheme", reduction="mean")
+        assert abs(res["lambda_mean"] - float(lm)) <= 1e-5 * abs(float(lm))     # global pair count (lambdaL.py:88-89)
+        assert res["p2p_used"] == p2p and res["status"] == 0

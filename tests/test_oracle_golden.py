@@ -94,6 +94,32 @@ def test_m_ndcg(name):
     np.testing.assert_allclose(out, G.out(name), rtol=1e-12, atol=0)
 
 
+# ---- round-2 goldens (tests/golden/make_golden_v2.py) ----------------------------------------------------
+@pytest.mark.parametrize("name", G.names("dcg/"))
+def test_dcg(name):
+    ins = G.inputs(name)
+    out = O.dcg(ins["true"], ins["pred"], **G.kwargs(name))
+    np.testing.assert_allclose(out, G.out(name), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", [n for n in G.names("georisk_default/") if n != "georisk_default/known5x8"])
+def test_georisk_default_with_zero_rows(name):
+    out = O.geo_risk_default(G.inputs(name)["mat"], **G.kwargs(name))
+    np.testing.assert_allclose(out, G.out(name), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", G.names("lambda_mask/"))
+def test_lambda_mask_values_and_gradient(name):
+    ins = G.inputs(name)
+    sp = torch.from_numpy(ins["y_pred"].copy()).requires_grad_(True)
+    out = O.lambda_mask(sp, torch.from_numpy(ins["y_true"]), **G.kwargs(name))
+    np.testing.assert_allclose(out.detach().numpy(), G.out(name), rtol=2e-6, atol=1e-7)
+    (out * torch.from_numpy(ins["w"])).sum().backward()
+    gref = G.grad(name, "y_pred")
+    scale = max(float(np.abs(gref).max()), 1e-30)
+    np.testing.assert_allclose(sp.grad.numpy() / scale, gref / scale, rtol=1e-4, atol=2e-6)
+
+
 def test_error_behaviour():
     s = torch.randn(2, 6)
     y = torch.randint(0, 3, (2, 6)).float()

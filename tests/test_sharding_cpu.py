@@ -1,5 +1,6 @@
-"""N > 1 host logic on CPU: world_size-2 gloo process groups exercise the query partition and the risk losses'
-two exchange rounds (ltr_b200/sharding.py) against the unsharded oracle."""
+"""N > 1 host logic on CPU: world_size-2 / -3 gloo process groups exercise the query partition and the risk losses'
+two exchange rounds (ltr_b200/sharding.py: one all-gather per round, states combined in rank order) against the
+unsharded oracle -- including a rank whose shard is EMPTY."""
 import os
 import socket
 
@@ -33,15 +34,20 @@ def _worker(rank, world, port, mat, alpha, kind, invert, strategy, out_q):
         assert sharding.is_sharded(group)
         lo, hi = sharding.shard_bounds(mat.shape[0], rank, world)
         local = mat[lo:hi]
-        s1 = torch.from_numpy(RP.state1(local))
-        sharding.allreduce_risk_state1(s1, group)
-        s2 = torch.from_numpy(RP.state2(local, s1.numpy(), invert, alpha, strategy))
-        sharding.allreduce_risk_state2(s2, group)
-        val = RP.final_value(s1.numpy(), s2.numpy(), kind, invert, strategy, 1.0, C=mat.shape[1])
+        # the exchange block of this rank (fp64 words): inbox[round][rank][16]; one all-gather per round
+        xchg = torch.zeros(1024, dtype=torch.float64)
+        sharding.risk_inbox(xchg, 0)[rank] = torch.from_numpy(RP.state1(local))
+        sharding.allgather_risk_round(xchg, 0, group)
+        g1 = RP.combine(sharding.risk_inbox(xchg, 0)[:world].numpy(), 0)
+        sharding.risk_inbox(xchg, 1)[rank] = torch.from_numpy(RP.state2(local, g1, invert, alpha, strategy))
+        sharding.allgather_risk_round(xchg, 1, group)
+        g2 = RP.combine(sharding.risk_inbox(xchg, 1)[:world].numpy(), 1)
+        val = RP.final_value(g1, g2, kind, invert, strategy, 1.0, C=mat.shape[1])
+        pair_mean = sharding.global_pair_mean(torch.tensor(float(local.sum())), torch.tensor(float(local.size)), group)
         # scalar helpers
-        mean = sharding.global_mean(torch.tensor(float(local[:, 0].mean())), hi - lo, group)
+        mean = sharding.global_mean(torch.tensor(float(local[:, 0].mean()) if hi > lo else 0.0), hi - lo, group)
         total = sharding.global_sum(torch.tensor(float(local.sum())), group)
-        out_q.put((rank, float(val), float(mean), float(total), (lo, hi)))
+        out_q.put((rank, float(val), float(mean), float(total), (lo, hi), float(pair_mean)))
     finally:
         dist.destroy_process_group()
 
@@ -83,8 +89,22 @@ def test_risk_exchange_rounds_match_unsharded_reference(kind, invert, strategy):
     fn = O.geo_risk if kind == 1 else O.z_risk
     r0, rl = float(fn(X, alpha, i=0)), float(fn(X, alpha, i=-1))
     ref = r0 if strategy == 1 else (rl - r0 if strategy == 2 else (rl - r0) ** 2)
-    for rank, val, mean, total, span in res:
+    for rank, val, mean, total, span, pair_mean in res:
         assert abs(val - ref) <= 2e-5 * max(1.0, abs(ref)), (rank, val, ref)
+        assert abs(pair_mean - raw.mean()) < 1e-6
         assert abs(mean - raw[:, 0].mean()) < 1e-7         # returned in the dtype of the local mean (fp32)
         assert abs(total - raw.sum()) < 1e-4          # fp32 scalar round trip
     assert res[0][4] == (0, 19) and res[1][4] == (19, 37)
+
+
+def test_risk_exchange_with_an_empty_shard():
+    """3 ranks, 2 queries: the last rank owns nothing, contributes the neutral state and still joins both rounds."""
+    from oracle import ltr_oracle as O
+    rng = np.random.default_rng(11)
+    raw = rng.random((2, 3)) * 0.5 + 0.05
+    res = _run(3, raw, 2.0, 1, True, 1)
+    X = torch.from_numpy(raw.max() - raw).float()
+    ref = float(O.geo_risk(X, 2.0, i=0))
+    assert [r[4] for r in res] == [(0, 1), (1, 2), (2, 2)]
+    for r in res:
+        assert abs(r[1] - ref) <= 2e-5 * max(1.0, abs(ref)), (r[0], r[1], ref)
