@@ -123,6 +123,15 @@ int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const 
                   const float* disc32, float* out, int* flags, void* stream);
 
 /*
+ * The same sweep from HOST buffers (pinned for asynchrony): H2D of y_true / y_pred, ltr_ndcg_at_k, D2H of out, all
+ * queued on `stream`.  d_scratch: ltr_ndcg_at_k_host_scratch_bytes(Q, n, nk) bytes of device memory; disc32 stays a
+ * device table.  This is the call a CPU-resident evaluation loop (main.py:145) makes once per epoch.
+ */
+size_t ltr_ndcg_at_k_host_scratch_bytes(int Q, int n, int nk);
+int ltr_ndcg_at_k_host(const float* h_y_true, const float* h_y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
+                       const float* disc32, float* h_out, void* d_scratch, size_t scratch_bytes, void* stream);
+
+/*
  * NDCG@k, fp64.                               replaces utils/metrics.py:48-80 (dcg / ndcg / mNdcg)
  *   gains linear (exponential_gains = 0) or 2^l - 1; disc64[r] = log2(2 + r); k clipped to n; a query whose
  *   ideal DCG is 0 gets empty_value (1.0 for no_relevant=True, 0.0 otherwise); out : [Q, nk] doubles.

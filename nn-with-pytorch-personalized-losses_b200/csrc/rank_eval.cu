@@ -635,6 +635,37 @@ LTR_API int ltr_ndcg_at_k_f64(const float* y_true, const float* y_pred, int Q, i
     return ndcg_common(p, ks, nk, true, stream);
 }
 
+// NDCG@k sweep from HOST buffers (pinned for asynchrony): H2D of both [Q, n] arrays, the sweep kernel, D2H of [Q, nk].
+LTR_API size_t ltr_ndcg_at_k_host_scratch_bytes(int Q, int n, int nk) {
+    if (Q <= 0 || n <= 0 || nk <= 0) return 0;
+    const size_t qn = (((size_t)Q * n + 3) & ~(size_t)3);
+    const size_t qk = (((size_t)Q * nk + 3) & ~(size_t)3);
+    return (2 * qn + qk + (((size_t)Q + 1 + 3) & ~(size_t)3)) * sizeof(float);
+}
+
+LTR_API int ltr_ndcg_at_k_host(const float* h_y_true, const float* h_y_pred, int Q, int n, const int* ks, int nk,
+                               int tie_rule, const float* disc32, float* h_out, void* d_scratch, size_t scratch_bytes,
+                               void* stream) {
+    using namespace ltr;
+    if (!h_y_true || !h_y_pred || !h_out || !d_scratch || Q <= 0 || n <= 0 || nk <= 0)
+        return set_error(LTR_EINVAL, "ltr_ndcg_at_k_host: null pointer or non-positive size");
+    if (scratch_bytes < ltr_ndcg_at_k_host_scratch_bytes(Q, n, nk))
+        return set_error(LTR_EINVAL, "ltr_ndcg_at_k_host: scratch too small");
+    const size_t qn = (((size_t)Q * n + 3) & ~(size_t)3);
+    const size_t qk = (((size_t)Q * nk + 3) & ~(size_t)3);
+    float* d_true = reinterpret_cast<float*>(d_scratch);
+    float* d_pred = d_true + qn;
+    float* d_out = d_pred + qn;
+    int* d_flags = reinterpret_cast<int*>(d_out + qk);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)Q * n * sizeof(float);
+    LTR_CUDA(cudaMemcpyAsync(d_true, h_y_true, bytes, cudaMemcpyHostToDevice, st));
+    LTR_CUDA(cudaMemcpyAsync(d_pred, h_y_pred, bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = ltr_ndcg_at_k(d_true, d_pred, Q, n, ks, nk, tie_rule, disc32, d_out, d_flags, stream)) return rc;
+    LTR_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)Q * nk * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 LTR_API int ltr_dcg_at_k_f64(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
                              int exponential_gains, const double* disc64, double* out, int* flags, void* stream) {
     ltr::NdcgParams p{};
