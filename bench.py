@@ -20,6 +20,14 @@ N(0,1), alpha = 10), per GPU.  Slates are independent, so N GPUs each take their
                a pure ex2.approx loop in the same run; `roofline_hbm` gives the HBM view.
   cpu_baseline the oracle port of the reference's CPU algorithm (oracle/ltr_oracle.py, torch CPU,
                all host threads) on a bounded sample of the same workload.
+  ndcg_eval    the second half of BASELINE.json's metric, NDCG@{1,5,10} evaluation queries/s: device-resident value,
+               roofline, e2e through `ltr_ndcg_at_k_host` (pinned host labels / scores in, pinned NDCG out) and the
+               CPU port of torchNdcg on all host cores.  The driver's parser keeps `config`, `roofline`, `e2e` and
+               `cpu_baseline`: the block is `config.ndcg_eval`, with its roofline / e2e / cpu numbers repeated as
+               `roofline.ndcg_eval`, `e2e.ndcg_eval`, `cpu_baseline.ndcg_eval`.
+  georisk_sharded (N > 1) `config.georisk_sharded`: BASELINE configs[3], 8192 queries over the N ranks, S in {2, 4}:
+               us per fwd+bwd step with the in-kernel NVLink exchange and with one all-gather per round, the latency
+               of one such all-gather, and a parity flag against the unsharded call on rank 0.
 
 `--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to
 the GPU box; the port is pinned to it by tests/golden).
@@ -140,6 +148,40 @@ def cpu_throughput(sample_slates: int, reps: int, seed: int = SEED):
     return sample_slates / best, cores
 
 
+def _ndcg_cpu_worker(job):
+    """One host process: the oracle port of torchNdcg (utils/metrics.py:83-104) at k = 10 over its chunk of queries."""
+    seed, q, n = job
+    from oracle import ltr_oracle as O
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, 5, (q, n), generator=g).float()
+    s = torch.randn(q, n, generator=g)
+    t0 = time.perf_counter()
+    out = O.torch_ndcg(y, s, k=10, return_type="tensor")
+    return time.perf_counter() - t0, float(out.sum())
+
+
+def ndcg_cpu_throughput(queries_per_core: int = 768, n: int = N_DOCS):
+    """torchNdcg@10 on every host core at once (the reference's evaluator is a Python loop per query: one process per
+    core, fork -- call this BEFORE the CUDA context exists).  Returns (queries/s, cores, sample description)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    jobs = [(SEED + 7 * i, queries_per_core, n) for i in range(cores)]
+    from oracle import ltr_oracle  # noqa: F401                            (imported once in the parent, forked along)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_ndcg_cpu_worker, [(SEED, 8, n)] * cores)                # workers up
+        t0 = time.perf_counter()
+        pool.map(_ndcg_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    total = queries_per_core * cores
+    return total / wall, cores, (f"{total} queries x {n} docs, NDCG@10 only (the GPU sweep computes @1, @5 and @10), "
+                                 f"{cores} processes x 1 thread (oracle/ltr_oracle.py port of utils/metrics.py:83-104 torchNdcg)")
+
+
+WORKLOAD = ("approxNDCG alpha=10 fused fwd+bwd, 4096 slates x 128 docs per GPU per step (BASELINE configs[1]), "
+            "labels U{0..4}, valid len U{64..128} (-1 padding), scores N(0,1)")
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -161,9 +203,8 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"approxNDCG alpha=10 fwd+bwd, {sample} slates x {N_DOCS} docs per step "
-                               f"(bounded sample of the 4096 x 128 batch), labels U{{0..4}}, len U{{64..128}}, scores N(0,1)",
-                   "device": "host CPU"},
+        "config": {"workload": WORKLOAD, "device": "host CPU",
+                   "sample": f"{sample} slates x {N_DOCS} docs per step (bounded sample of the 4096 x 128 batch)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} slates x {N_DOCS} docs per step, {args.steps} steps, torch CPU fp32, "
                                    f"{cores} threads (oracle/ltr_oracle.py port of losses/approxNDCG.py)"},
@@ -199,7 +240,18 @@ def run_b200_arm(args, rank, local_rank, world):
 
     import torch.distributed as dist
     from ltr_b200 import _lib, _runtime as rt
-    from ltr_b200.host import ApproxNDCGHost
+    from ltr_b200.host import ApproxNDCGHost, NdcgEvalHost
+
+    # ---- CPU baselines first (rank 0 of a single-GPU run): the NDCG one forks worker processes, which must happen
+    #      before this process owns a CUDA context
+    cpu = {}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample = ndcg_cpu_throughput()
+        cpu["ndcg"] = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        rate, cores = cpu_throughput(1024, 3)
+        cpu["approx"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1024 slates x 128 docs fwd+bwd, best of 3, torch CPU fp32 "
+                                   "(oracle/ltr_oracle.py port of losses/approxNDCG.py)"}
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
@@ -243,15 +295,15 @@ def run_b200_arm(args, rank, local_rank, world):
         return ms
 
     # ---- device-resident throughput (`value`) --------------------------------------------------------
-    # The kernel (~10 us) is shorter than a Python->ctypes->cudaLaunchKernel round trip, so the timed
-    # launches are replayed from a CUDA graph holding one pass over the ring (RING launches of the
-    # same C-ABI entry, captured on the launching stream); the remainder is launched directly.
+    # The kernel (~20 us) is shorter than a Python->ctypes->cudaLaunchKernel round trip, so the timed launches are
+    # replayed from a CUDA graph of min(steps, RING) launches of the same C-ABI entry over distinct batches, captured on
+    # the launching stream (the driver's 20-step run is ONE replay of a 20-launch graph); a remainder is launched directly.
     sampler = ClockSampler(local_rank)
     for i in range(args.warmup):
         launch(i)
     barrier()
-    graph, n_replays = None, 0
-    if args.steps >= RING and not args.no_graph:
+    graph, n_replays, g_len = None, 0, min(args.steps, RING)
+    if g_len >= 2 and not args.no_graph:
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(side):
@@ -260,19 +312,20 @@ def run_b200_arm(args, rank, local_rank, world):
             launch(0)                                   # warm this stream's workspace outside the capture
             side.synchronize()
             with torch.cuda.graph(graph, stream=side):
-                for i in range(RING):
+                for i in range(g_len):
                     launch(args.warmup + i)
         stream = rt.stream_ptr()
         ws = rt.workspace(dev)
-        n_replays = args.steps // RING
-        graph.replay()                                  # one untimed replay (graph upload)
+        n_replays = args.steps // g_len
+        for _ in range(3):
+            graph.replay()                              # untimed replays (graph upload, clocks up)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(n_replays):
         graph.replay()
-    for i in range(n_replays * RING, args.steps):
+    for i in range(n_replays * g_len, args.steps):
         launch(args.warmup + i)
     ev1.record()
     barrier()
@@ -298,29 +351,7 @@ def run_b200_arm(args, rank, local_rank, world):
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
     h2d = 2 * B * n * 4
     d2h = B * n * 4 + 4
-
-    if rank != 0:
-        return
-
-    # ---- roofline denominators measured here: SFU (ex2 loop), FP32 (FFMA loop) ------------------------
-    probe_out = torch.zeros(1, device=dev)
-    ops = ctypes.c_longlong(0)
-
-    def probe(fn, iters):
-        fn(probe_out.data_ptr(), iters, ctypes.byref(ops), stream)
-        torch.cuda.synchronize()
-        best = float("inf")
-        for _ in range(5):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn(probe_out.data_ptr(), iters, ctypes.byref(ops), stream)
-            b.record()
-            torch.cuda.synchronize()
-            best = min(best, a.elapsed_time(b))
-        return ops.value / (best * 1e-3)
-
-    sfu_peak = probe(lib.ltr_probe_sfu, 4096)
-    fma_peak = probe(lib.ltr_probe_fma, 4096)
+    del plan, h_s, h_y
 
     peaks = {}
     try:
@@ -329,7 +360,37 @@ def run_b200_arm(args, rank, local_rank, world):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    hbm_src = "MEASURED_PEAKS.json (burst: the kernel is timed alone)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    # ---- NDCG@{1,5,10} evaluation (the second half of BASELINE.json's metric), every rank its own queries ------------
+    ndcg = bench_ndcg_eval(lib, rt, dev, rank, world, barrier, max_over_ranks, NdcgEvalHost, hbm_peak, hbm_src,
+                           steps=max(10, min(args.steps, 100)))
+
+    # ---- GeoRisk, query-sharded (BASELINE configs[3]) -----------------------------------------------------------------
+    georisk = bench_georisk_sharded(dev, rank, world, barrier, max_over_ranks) if world > 1 else None
+
+    if rank != 0:
+        return
+
+    # ---- roofline denominators measured here: SFU (ex2 loop), FP32 (FFMA loop) ------------------------
+    probe_out = torch.zeros(1, device=dev)
+    ops_count = ctypes.c_longlong(0)
+
+    def probe(fn, iters):
+        fn(probe_out.data_ptr(), iters, ctypes.byref(ops_count), stream)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(probe_out.data_ptr(), iters, ctypes.byref(ops_count), stream)
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return ops_count.value / (best * 1e-3)
+
+    sfu_peak = probe(lib.ltr_probe_sfu, 4096)
+    fma_peak = probe(lib.ltr_probe_fma, 4096)
 
     # kernel time per launch = ms / steps (one launch per step, nothing else on the stream)
     t_launch = ms * 1e-3 / args.steps
@@ -345,24 +406,26 @@ def run_b200_arm(args, rank, local_rank, world):
     except Exception:
         pass
 
-    cpu_rate, cores = cpu_throughput(1024, 3) if world == 1 else (None, None)
-
+    config = {
+        "workload": WORKLOAD,
+        "global_batch": world * B, "slate_len": n, "parallelism": f"query-sharded x{world}, no data-path collective",
+        "l2_policy": f"inputs larger than L2: ring of {RING} distinct batches ({RING * 3 * B * n * 4 // 2**20} MB of s/y/grad) cycled",
+        "loss_check": loss_value,
+        "launch_mode": (f"CUDA graph of {g_len} launches replayed {n_replays}x + {args.steps - n_replays * g_len} direct"
+                        if graph is not None else "direct launches"),
+        "ndcg_eval": ndcg,
+    }
+    if georisk is not None:
+        config["georisk_sharded"] = georisk
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": f"approxNDCG alpha=10 fused fwd+bwd, {B} slates x {n} docs per GPU per step "
-                        "(BASELINE configs[1]), labels U{0..4}, valid len U{64..128} (-1 padding), scores N(0,1)",
-            "global_batch": world * B, "slate_len": n, "parallelism": f"query-sharded x{world}, no data-path collective",
-            "l2_policy": f"inputs larger than L2: ring of {RING} distinct batches ({RING * 3 * B * n * 4 // 2**20} MB of s/y/grad) cycled",
-            "loss_check": loss_value,
-            "launch_mode": (f"CUDA graph of {RING} launches replayed {n_replays}x + {args.steps - n_replays * RING} direct"
-                            if graph is not None else "direct launches"),
-        },
+        "config": config,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "ltr_approx_ndcg_fwdbwd_host: pinned host y_pred/y_true read by the kernel over PCIe, gradient and loss "
-                        "written back to pinned host memory by the kernel (no staging copies), 3 streams in flight"},
+                        "written back to pinned host memory by the kernel (no staging copies), 3 streams in flight",
+                "ndcg_eval": ndcg["e2e"]},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": {
@@ -377,25 +440,161 @@ def run_b200_arm(args, rank, local_rank, world):
             "peak_source": "measured in this run: pure ex2.approx loop (ltr_probe_sfu)",
             "peak_nominal": 148 * 16 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12,
             "fp32_peak_measured_tflane_ops": fma_peak / 1e12,
+            "ndcg_eval": ndcg["roofline"],
         },
         "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_bytes / t_launch / 1e9 / hbm_peak, "peak_source": hbm_src,
                          "note": "pairwise kernel is SFU/issue bound; HBM view shown for completeness"},
     }
     if world == 1 and not args.no_secondary:
-        # the other kernel families of the path (ListNet, NDCG@k sweep, LambdaLoss, GeoRisk, approxNDCG n=1024):
-        # measured by tools/bench_paths.py with CUDA events; reported beside the headline, never mixed into it
+        # the other kernel families of the path (ListNet, NDCG@k sweeps, LambdaLoss, GeoRisk, approxNDCG n=1024):
+        # measured by tools/bench_paths.py with CUDA events; reported beside the headline, never mixed into it.
+        # Their rooflines (achieved / peak / frac each) are repeated under roofline.others, which the driver keeps.
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_paths
-            line["secondary"] = bench_paths.run_all()
+            line["secondary"] = bench_paths.run_all(sfu_peak=sfu_peak)
+            line["roofline"]["others"] = {k: dict(v["roofline"], us_per_call=v["us_per_call"], value=v["value"], unit_value=v["unit"])
+                                          for k, v in line["secondary"].items() if isinstance(v, dict) and "roofline" in v}
         except Exception as exc:                      # the headline line must still be printed
             line["secondary"] = {"error": repr(exc)}
-    if cpu_rate is not None:
-        line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "1024 slates x 128 docs fwd+bwd, best of 3, torch CPU fp32 "
-                                          "(oracle/ltr_oracle.py port of losses/approxNDCG.py)"}
+    if "approx" in cpu:
+        line["cpu_baseline"] = dict(cpu["approx"], ndcg_eval=cpu["ndcg"])
+        ndcg["cpu_baseline"] = cpu["ndcg"]
     print(json.dumps(line), flush=True)
+
+
+def bench_ndcg_eval(lib, rt, dev, rank, world, barrier, max_over_ranks, NdcgEvalHost, hbm_peak, hbm_src, steps):
+    """NDCG@{1,5,10} sweep, torchNdcg arithmetic (utils/metrics.py:83-104), 65,536 queries x 128 docs per GPU per step.
+    value: queries resident in HBM, CUDA events over `steps` calls of `ltr_ndcg_at_k` cycling 3 distinct batches
+    (201 MB > L2); e2e: pinned host labels / scores -> `ltr_ndcg_at_k_host` -> pinned NDCG, 3 streams in flight."""
+    import ctypes
+    from ltr_b200 import ops
+    Q, n, ks, ring = 65536, N_DOCS, (1, 5, 10), 3
+    host = []
+    for i in range(ring):
+        g = torch.Generator().manual_seed(SEED + 500 + 10 * rank + i)
+        host.append((torch.randint(0, 5, (Q, n), generator=g).float(), torch.randn(Q, n, generator=g)))
+    d = [(y.to(dev), s.to(dev)) for y, s in host]
+    d32, _ = ops._disc_tables(n, dev)
+    out = torch.empty(Q, len(ks), device=dev)
+    marks = [torch.empty(Q + 1, dtype=torch.int32, device=dev) for _ in range(ring)]
+    karr = (ctypes.c_int * len(ks))(*ks)
+    stream = rt.stream_ptr()
+
+    def step(i):
+        y, s = d[i % ring]
+        rc = lib.ltr_ndcg_at_k(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(),
+                               out.data_ptr(), marks[i % ring].data_ptr(), stream)
+        if rc:
+            from ltr_b200 import _lib
+            _lib.check(rc, "ltr_ndcg_at_k")
+
+    for i in range(5):
+        step(i)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(5 + i)
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    sec = ms * 1e-3 / steps
+    check = float(torch.nan_to_num(out).sum().cpu())
+    # e2e
+    plan = NdcgEvalHost(Q, n, ks=ks, device=dev, depth=3)
+    pinned = [(y.pin_memory(), s.pin_memory()) for y, s in host]
+    e_steps = max(6, min(steps, 30))
+    for i in range(3):
+        plan.submit(*pinned[i % ring])
+    plan.wait_all()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        plan.submit(*pinned[i % ring])
+    plan.wait_all()
+    e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    del plan, pinned
+    alg = (8.0 * n + 4.0 * len(ks)) * Q
+    gbs = alg / sec / 1e9
+    return {
+        "metric": "NDCG@{1,5,10} eval queries/s (n=128)", "value": world * Q / sec, "unit": "queries/s", "n_gpus": world,
+        "us_per_call": sec * 1e6, "steps": steps,
+        "workload": f"{Q} queries x {n} docs per GPU per step, k sweep {list(ks)}, torchNdcg arithmetic, labels U{{0..4}}, "
+                    f"scores N(0,1), ring of {ring} batches ({ring * 2 * Q * n * 4 // 2**20} MB > L2); query-sharded x{world}",
+        "check_sum_of_ndcg": check,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                     "peak_source": hbm_src, "kernel": "ndcg_key_kernel<false>", "kernel_us": sec * 1e6,
+                     "algorithmic": "8 n + 4 |ks| bytes per query"},
+        "e2e": {"value": world * Q * e_steps / (e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": 2 * Q * n * 4,
+                "d2h_bytes_per_step": Q * len(ks) * 4, "steps": e_steps,
+                "path": "ltr_ndcg_at_k_host: pinned host labels/scores -> cudaMemcpyAsync -> sweep kernel -> cudaMemcpyAsync "
+                        "-> pinned [Q, 3] NDCG, 3 streams in flight"},
+    }
+
+
+def bench_georisk_sharded(dev, rank, world, barrier, max_over_ranks, Q_total=8192, n=N_DOCS, iters=200):
+    """BASELINE configs[3]: geoRiskListnetLoss (lt=1, rs=1, alpha=5) fwd+bwd, `Q_total` queries sharded over the ranks,
+    S baseline systems.  us per step (CUDA events, max over ranks) for the two exchange mechanisms, the latency of one
+    all-gather of a phase state, and parity of the sharded loss / gradient with the unsharded call."""
+    import torch.distributed as dist
+    from ltr_b200 import ops, sharding
+    group = dist.group.WORLD
+    lo, hi = sharding.shard_bounds(Q_total, rank, world)
+    out = {"workload": f"geoRiskListnetLoss lt=1 rs=1 alpha=5 fwd+bwd, {Q_total} queries x {n} docs over {world} ranks "
+                       f"({hi - lo} per rank), through the drop-in callable's autograd Function", "iters": iters}
+
+    def timed(fn, reps):
+        for _ in range(10):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / reps * 1e3            # us
+
+    for S in (2, 4):
+        g = torch.Generator().manual_seed(SEED + 40 + S)                 # every rank draws the whole batch, keeps its rows
+        s = torch.randn(Q_total, n, generator=g)
+        y = torch.randint(0, 5, (Q_total, n), generator=g).float()
+        base = torch.randn(Q_total, n, S, generator=g)
+        sl = s[lo:hi].to(dev).requires_grad_(True)
+        yl, bl = y[lo:hi].to(dev), base[lo:hi].to(dev)
+        res = {}
+        for mode in ("p2p", "allgather"):
+            os.environ["LTR_RISK_P2P"] = "1" if mode == "p2p" else "0"
+            used_p2p = sharding.risk_peer_exchange(group, dev) is not None
+            res[mode + "_us"] = timed(lambda: ops.risk_listnet(sl, yl, bl, ops.KIND_GEO, 5.0, 1, 1, 1.0, False, False, group), iters)
+            if mode == "p2p":
+                res["p2p_available"] = used_p2p
+            sl.grad = None
+            loss = ops.risk_listnet(sl, yl, bl, ops.KIND_GEO, 5.0, 1, 1, 1.0, False, False, group)
+            loss.sum().backward()
+            res[mode + "_loss"] = float(loss)
+            if rank == 0:                                                 # the unsharded call on the whole batch
+                sf = s.to(dev).requires_grad_(True)
+                lf = ops.risk_listnet(sf, y.to(dev), base.to(dev), ops.KIND_GEO, 5.0, 1, 1, 1.0, False, False, None)
+                lf.sum().backward()
+                gref = sf.grad[lo:hi]
+                res[mode + "_loss_rel_err"] = abs(float(loss) - float(lf)) / abs(float(lf))
+                res[mode + "_grad_rel_err"] = float((sl.grad - gref).abs().max() / gref.abs().max())
+                ok = res[mode + "_loss_rel_err"] < 1e-5 and res[mode + "_grad_rel_err"] < 1e-4
+            else:
+                ok = True
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            res[mode + "_parity_ok"] = bool(int(flag))
+        os.environ["LTR_RISK_P2P"] = "1"
+        out[f"S{S}"] = res
+    blk = torch.zeros(1024, dtype=torch.float64, device=dev)
+    out["allgather_16_doubles_us"] = timed(lambda: sharding.allgather_risk_round(blk, 0, group), iters)
+    one = torch.zeros(1, device=dev)
+    out["allreduce_1_float_us"] = timed(lambda: dist.all_reduce(one), iters)
+    return out
 
 
 def main():
@@ -406,6 +605,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python (no CUDA graph)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary kernel-family measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baselines (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LTR_WORKSPACE_BYTES 131072
+#define LTR_WORKSPACE_BYTES 262144
 
 #define LTR_EINVAL (-1)  /* bad argument (null pointer, n out of range, unknown enum) */
 #define LTR_ETOOBIG (-2) /* slate longer than the shared-memory capacity supports   */
@@ -208,17 +208,18 @@ int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, int n, fl
  *     (0 * LTR_RISK_MAX_WORLD + rank) * 128) into everybody's block, phases = 2, all-gather round 1 (offset
  *     (1 * LTR_RISK_MAX_WORLD + rank) * 128), phases = 4: two collectives per step; or
  *   - peer_xchg = HOST array of `world` device pointers, every rank's block as mapped into this process
- *     (ltr_risk_xchg_alloc + ltr_ipc_export / ltr_ipc_open; peer_xchg[rank] == xchg), seq = number of this call (the
- *     same on every rank, never 0, different from the previous call's): phases = 7, one call, no collective -- the
- *     kernels store their states into the peers' inboxes over NVLink and spin (<= 4 s) on sequence-numbered flags.
+ *     (ltr_risk_xchg_alloc + ltr_ipc_export / ltr_ipc_open; peer_xchg[rank] == xchg): phases = 7, one call, no
+ *     collective -- the kernels store their states into the peers' inboxes over NVLink and spin (<= 4 s) on flags
+ *     carrying the call's sequence number, which the kernels keep in the exchange block themselves (every rank must
+ *     make the same sequence of calls on its block; the three launches are CUDA-graph capturable).
  */
 #define LTR_RISK_MAX_WORLD 16
-#define LTR_RISK_XCHG_BYTES 8192
+#define LTR_RISK_XCHG_BYTES 16384
 int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, const float* y_baselines, int B, int n, int S,
                             int transformation, int add_ideal, int kind, int invert, int return_strategy,
                             int precedence_quirk, float alpha, float negative, float* mat, double* rowstate, float* loss,
                             float* grad, int phases, void* xchg, int rank, int world, const void* const* peer_xchg,
-                            unsigned seq, void* workspace, void* stream);
+                            void* workspace, void* stream);
 
 /*
  * Exchange blocks in peer-mappable memory.  ltr_risk_xchg_alloc: cudaMalloc + zero fill of LTR_RISK_XCHG_BYTES on the

@@ -18,15 +18,20 @@ int upload_disc_prefix_constant();                   // P[0..128] -> the constan
 //   u32 [16]      streaming kernels: finished-CTA counter
 //   u32 [18]      LambdaLoss: next-slate counter
 //   f32 [32..35]  ordinal: BCE sum, number of valid docs, #targets < 0, #inputs outside [0, 1]
-//   u32 [20..21]  risk losses: finished-CTA counters of phases A and B
+//   u32 [20..22]  risk losses: finished-CTA counters of phases A and B (three-launch form); cooperative kernel: generation
 //   byte 1024 ..  streaming kernels: per-CTA fp64 partial sums, [grid <= 2048][4]
+//   byte 256 ..   risk losses, cooperative kernel: the combined states of the two rounds, [2][16] stamped slots of 16 bytes
+//   byte 768 ..   risk losses, cooperative kernel: 7 globaltimer stamps of CTA 0 (diagnostics)
 //   byte 66560 .. risk losses: per-CTA fp64 partials of phase A [grid <= 1184][4], then of phase B [grid <= 128][16]
+//                 (cooperative kernel: the same two regions hold stamped 16-byte slots, [grid <= 592][4] and [grid <= 592][16])
 constexpr int LTR_WS_STREAM_COUNTER = 16;
 constexpr int LTR_WS_RISK_COUNTERS = 20;
 constexpr int LTR_WS_RISK_MAX_GRID = 1184;
 constexpr size_t LTR_WS_RISK_PART1 = 1024 + 2048 * 4 * 8;
 constexpr size_t LTR_WS_RISK_PART2 = LTR_WS_RISK_PART1 + (size_t)LTR_WS_RISK_MAX_GRID * 4 * 8;
-static_assert(LTR_WS_RISK_PART2 + 128 * 16 * 8 <= LTR_WORKSPACE_BYTES, "workspace layout overflows");
+constexpr int LTR_WS_RISK_COOP_MAX_GRID = 592;           // cooperative kernel: 4 CTAs per SM at most
+static_assert(LTR_WS_RISK_PART2 + (size_t)LTR_WS_RISK_COOP_MAX_GRID * 16 * 16 <= LTR_WORKSPACE_BYTES, "workspace layout overflows");
+static_assert((size_t)LTR_WS_RISK_COOP_MAX_GRID * 4 * 16 <= LTR_WS_RISK_PART2 - LTR_WS_RISK_PART1, "workspace layout overflows");
 inline double* ws_risk_part1(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + LTR_WS_RISK_PART1); }
 inline double* ws_risk_part2(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + LTR_WS_RISK_PART2); }
 constexpr int LTR_WS_LAMBDA_COUNTER = 18;             // LambdaLoss: next-slate counter

@@ -31,14 +31,14 @@ constexpr int RISK_MAX_WORLD = LTR_RISK_MAX_WORLD;   // ranks an exchange block 
 // exchange block: doubles inbox[2][RISK_MAX_WORLD][RISK_STATE]; then 32-bit words flag[2][RISK_MAX_WORLD], status
 constexpr int RISK_XCHG_WORDS_AT = 2 * RISK_MAX_WORLD * RISK_STATE;      // (in doubles)
 constexpr int RISK_W_STATUS = 2 * RISK_MAX_WORLD;
+constexpr int RISK_W_SEQ = RISK_W_STATUS + 1;      // p2p: number of the call in flight (kept on the device: graph-capturable)
 constexpr unsigned long long RISK_SPIN_NS = 4000000000ull;               // give up on a peer after 4 s
-static_assert(RISK_XCHG_WORDS_AT * 8 + (RISK_W_STATUS + 1) * 4 <= LTR_RISK_XCHG_BYTES, "exchange block too small");
+static_assert(RISK_XCHG_WORDS_AT * 8 + (RISK_W_SEQ + 1) * 4 <= LTR_RISK_XCHG_BYTES, "exchange block too small");
 
 struct RiskComm {
     double* xchg;                       // this rank's exchange block
     double* peer[RISK_MAX_WORLD];       // p2p: every rank's block as mapped into this process (peer[rank] == xchg)
     int rank, world, p2p;
-    unsigned seq;                       // p2p: sequence number of this call (same on every rank, never 0)
 };
 
 __device__ __forceinline__ unsigned* xchg_words(double* x) { return reinterpret_cast<unsigned*>(x + RISK_XCHG_WORDS_AT); }
@@ -64,20 +64,26 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // One CTA publishes its rank's state of round `slot` (st: RISK_STATE doubles in shared memory, complete before the call):
 // into the local inbox, or -- p2p -- into the inbox of EVERY rank (plain stores to peer memory over NVLink, a system
-// fence, a barrier, then one release store per peer of the call's sequence number).
+// fence, a barrier, then one release store per peer of the call's sequence number).  The sequence number lives in the
+// exchange block: round 0 of a call advances it (every rank makes the same calls, so the ranks' numbers agree), round 1
+// and the consumers read it -- nothing per call comes from the host, so the three launches can sit in a CUDA graph.
 __device__ __forceinline__ void risk_publish(const RiskComm& c, int slot, const double* st) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (!c.p2p) {
         if (tid < RISK_STATE) xchg_inbox(c.xchg, slot, c.rank)[tid] = st[tid];
         return;
     }
+    unsigned* words = xchg_words(c.xchg);
+    unsigned seq = __ldcg(words + RISK_W_SEQ);
+    if (slot == 0) seq = (seq == 0xffffffffu) ? 1u : seq + 1u;           // (never 0: the flags start at 0)
     for (int idx = tid; idx < RISK_STATE * c.world; idx += nthr) {
         const int r = idx / RISK_STATE, e = idx % RISK_STATE;
         st_relaxed_sys(xchg_inbox(c.peer[r], slot, c.rank) + e, st[e]);
     }
     __threadfence_system();
     __syncthreads();
-    for (int r = tid; r < c.world; r += nthr) st_release_sys(xchg_words(c.peer[r]) + slot * RISK_MAX_WORLD + c.rank, c.seq);
+    if (slot == 0 && tid == 0) words[RISK_W_SEQ] = seq;                  // visible to the next launch on this stream
+    for (int r = tid; r < c.world; r += nthr) st_release_sys(xchg_words(c.peer[r]) + slot * RISK_MAX_WORLD + c.rank, seq);
 }
 
 // Every CTA of the next phase: (p2p: wait until every rank's flag of round `slot` carries this call's sequence number,)
@@ -88,8 +94,9 @@ __device__ __forceinline__ void risk_gather(const RiskComm& c, int slot, double*
     if (c.p2p && c.world > 1) {
         if (tid < c.world) {
             const unsigned* f = xchg_words(c.xchg) + slot * RISK_MAX_WORLD + tid;
+            const unsigned seq = __ldcg(xchg_words(c.xchg) + RISK_W_SEQ);   // advanced by this rank's own round 0
             const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_sys(f) != c.seq) {
+            while (ld_acquire_sys(f) != seq) {
                 if (globaltimer_ns() - t0 > RISK_SPIN_NS) {          // a peer never arrived: poison the result, say so
                     atomicExch(xchg_words(c.xchg) + RISK_W_STATUS, 1u);
                     break;
@@ -272,7 +279,7 @@ __device__ __forceinline__ void risk_stats1_body(const RiskFinalParams& p, int q
 
 // Everything phase 2/3 need about the z-risk of column `col` given the GLOBAL phase-1 state.
 struct ZCol {
-    double S, N, Qg, M;
+    double S, N, SN, Qg, M;      // SN = S / N
     int col, invert, C;
     float alpha;
     __device__ __forceinline__ double X(const float* row, int i) const {
@@ -283,15 +290,16 @@ struct ZCol {
         for (int i = 0; i < C; ++i) t += X(row, i);
         return t;
     }
-    // z_q, c_q = 1 + alpha [z < 0], A_q = c_q dz/de, e_q
-    __device__ __forceinline__ void eval(const float* row, double& z, double& c, double& A, double& e, double& t) const {
+    // z_q, c_q = 1 + alpha [z < 0], A_q = c_q dz/de, e_q; rse = 1 / sqrt(e_q).  One rsqrt, no division: e = (S / N) T,
+    // z = (x - e) rse, A = -c (x + e) / (2 e sqrt(e)) = -c (x + e) rse^3 / 2  (e <= 0 gives inf / NaN as sqrt + division do)
+    __device__ __forceinline__ void eval(const float* row, double& z, double& c, double& A, double& e, double& t, double& rse) const {
         t = T(row);
-        e = S * t / N;
+        e = SN * t;
         const double x = X(row, col);
-        const double se = sqrt(e);
-        z = (x - e) / se;
+        rse = rsqrt(e);
+        z = (x - e) * rse;
         c = (z < 0.0) ? 1.0 + (double)alpha : 1.0;
-        A = -c * (x + e) / (2.0 * e * se);
+        A = -0.5 * c * (x + e) * (rse * rse * rse);
     }
 };
 
@@ -306,54 +314,51 @@ __device__ __forceinline__ ZCol make_zcol(const RiskFinalParams& p, const double
     const double sraw = last ? g1[2] : g1[1];
     zc.S = p.invert ? zc.Qg * zc.M - sraw : sraw;
     zc.N = p.invert ? zc.Qg * (double)p.C * zc.M - g1[3] : g1[3];
+    zc.SN = zc.S / zc.N;
     return zc;
 }
 
 // phase 2 (local, needs global state1): per used column {sum z c, sum A T, sum A e, sum c / sqrt(e), sum A}, count of
 // entries equal to the global max;  t-risk: {sum d', sum d'^2} with d' = d (1 + alpha [d < 0]).
+// One query: adds its terms to acc[0..12]; rs[0..2] <- A0_q, c0_q / sqrt(e0_q), A1_q (what phase 3 needs of the query).
+__device__ __forceinline__ void risk_stats2_row(const RiskFinalParams& p, const ZCol& z0, const ZCol& zl, const float* row,
+                                                double (&acc)[13], double (&rs)[3]) {
+    if (p.kind == 2) {
+        // ours - base after the (optional) inversion; the max cancels
+        double d = p.invert ? (double)row[1] - (double)row[0] : (double)row[0] - (double)row[1];
+        d = (d < 0.0) ? d * (1.0 + (double)p.alpha) : d;
+        acc[11] += d;
+        acc[12] += d * d;
+        return;
+    }
+    double z, c, A, e, t, rse;
+    z0.eval(row, z, c, A, e, t, rse);
+    const double ce0 = c * rse;
+    acc[0] += z * c; acc[1] += A * t; acc[2] += A * e; acc[3] += ce0; acc[4] += A;
+    rs[0] = A; rs[1] = ce0;
+    if (p.strategy != 1) {
+        zl.eval(row, z, c, A, e, t, rse);
+        acc[5] += z * c; acc[6] += A * t; acc[7] += A * e; acc[8] += c * rse; acc[9] += A;
+        rs[2] = A;
+    }
+    if (p.invert)
+        for (int i = 0; i < p.C; ++i) acc[10] += ((double)row[i] == z0.M) ? 1.0 : 0.0;
+}
+
 template <int THREADS>
 __device__ __forceinline__ void risk_stats2_body(const RiskFinalParams& p, int q0, int dq, double* out, double* rowstate = nullptr) {
     __shared__ double red[32];
     const double* g1 = p.state1;
-    double a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double nmax = 0.0, td = 0.0, td2 = 0.0;
-    if (p.kind == 2) {
-        for (int q = q0; q < p.Q; q += dq) {
-            const float* row = p.mat + (size_t)q * p.C;
-            // ours - base after the (optional) inversion; the max cancels
-            double d = p.invert ? (double)row[1] - (double)row[0] : (double)row[0] - (double)row[1];
-            d = (d < 0.0) ? d * (1.0 + (double)p.alpha) : d;
-            td += d;
-            td2 += d * d;
-        }
-    } else {
-        const ZCol z0 = make_zcol(p, g1, false), zl = make_zcol(p, g1, true);
-        for (int q = q0; q < p.Q; q += dq) {
-            const float* row = p.mat + (size_t)q * p.C;
-            double z, c, A, e, t;
-            z0.eval(row, z, c, A, e, t);
-            const double ce0 = c / sqrt(e);
-            a[0] += z * c; a[1] += A * t; a[2] += A * e; a[3] += ce0; a[4] += A;
-            if (rowstate) rowstate[(size_t)q * 3 + 0] = A, rowstate[(size_t)q * 3 + 1] = ce0;
-            if (p.strategy != 1) {
-                zl.eval(row, z, c, A, e, t);
-                a[5] += z * c; a[6] += A * t; a[7] += A * e; a[8] += c / sqrt(e); a[9] += A;
-                if (rowstate) rowstate[(size_t)q * 3 + 2] = A;
-            }
-            if (p.invert)
-                for (int i = 0; i < p.C; ++i) nmax += ((double)row[i] == g1[0]) ? 1.0 : 0.0;
-        }
+    double acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const ZCol z0 = make_zcol(p, g1, false), zl = make_zcol(p, g1, true);
+    for (int q = q0; q < p.Q; q += dq) {
+        double rs[3] = {0.0, 0.0, 0.0};
+        risk_stats2_row(p, z0, zl, p.mat + (size_t)q * p.C, acc, rs);
+        if (rowstate) rowstate[(size_t)q * 3 + 0] = rs[0], rowstate[(size_t)q * 3 + 1] = rs[1], rowstate[(size_t)q * 3 + 2] = rs[2];
     }
-    for (int j = 0; j < 10; ++j) a[j] = rf_block_sum<THREADS>(a[j], red);
-    nmax = rf_block_sum<THREADS>(nmax, red);
-    td = rf_block_sum<THREADS>(td, red);
-    td2 = rf_block_sum<THREADS>(td2, red);
-    if (threadIdx.x == 0) {
-        for (int j = 0; j < 10; ++j) out[j] = a[j];
-        out[10] = nmax;
-        out[11] = td;
-        out[12] = td2;
-    }
+    for (int j = 0; j < 13; ++j) acc[j] = rf_block_sum<THREADS>(acc[j], red);
+    if (threadIdx.x == 0)
+        for (int j = 0; j < 13; ++j) out[j] = acc[j];
 }
 
 __device__ __forceinline__ double std_normal_cdf(double x) { return 0.5 * erfc(-x * 0.7071067811865476); }
@@ -433,11 +438,11 @@ __device__ __forceinline__ void risk_final_body(const RiskFinalParams& p, int q0
         double own[2], shared[2];
         for (int u = 0; u < nu; ++u) {
             const ZCol& zc = u ? zl : z0;
-            double z, c, A, e, t;
-            zc.eval(row, z, c, A, e, t);
+            double z, c, A, e, t, rse;
+            zc.eval(row, z, c, A, e, t, rse);
             const double sAT = g2[5 * u + 1], sAe = g2[5 * u + 2];
             shared[u] = coef[u] * dz[u] * (A * zc.S / zc.N - sAe / zc.N);   // reaches every column through T_q and N
-            own[u] = coef[u] * (dz[u] * (c / sqrt(e) + sAT / zc.N) + dS[u]); // only the column the risk is taken of
+            own[u] = coef[u] * (dz[u] * (c * rse + sAT / zc.N) + dS[u]);     // only the column the risk is taken of
         }
         for (int i = 0; i < p.C; ++i) {
             if (i > 0 && !p.gmat) break;
@@ -476,20 +481,23 @@ __device__ __forceinline__ void risk_row_consts(const RiskFinalParams& p, RiskRo
         return;
     }
     const ZCol z0 = make_zcol(p, g1, false), zl = make_zcol(p, g1, true);
-    double val[2], dz[2], dS[2];
-    for (int u = 0; u < 2; ++u) {
+    const double rQ = 1.0 / Qg, rN = 1.0 / z0.N;                // (N is the same for both columns; few divisions: this is a
+    const int nu = (p.strategy == 1) ? 1 : 2;                  //  serial stretch every CTA waits for)
+    double val[2] = {0.0, 0.0}, dz[2] = {0.0, 0.0}, dS[2] = {0.0, 0.0};
+    for (int u = 0; u < nu; ++u) {
         const ZCol& zc = u ? zl : z0;
         const double zsum = g2[5 * u];
         if (p.kind == 0) {
             val[u] = zsum; dz[u] = 1.0; dS[u] = 0.0;
         } else {
-            const double arg = zsum / Qg;
+            const double arg = zsum * rQ;
             const double cdf = std_normal_cdf(arg);
-            const double geo = sqrt(zc.S / Qg * cdf);
+            const double geo2 = zc.S * rQ * cdf;
+            const double rgeo = rsqrt(geo2);                       // 1 / geoRisk
             const double pdf = 0.3989422804014327 * exp(-0.5 * arg * arg);
-            val[u] = geo;
-            dz[u] = (zc.S / Qg) * pdf / Qg / (2.0 * geo);
-            dS[u] = cdf / Qg / (2.0 * geo);
+            val[u] = geo2 * rgeo;
+            dz[u] = 0.5 * (zc.S * rQ) * pdf * rQ * rgeo;
+            dS[u] = 0.5 * cdf * rQ * rgeo;
         }
     }
     double loss, coef[2];
@@ -503,7 +511,6 @@ __device__ __forceinline__ void risk_row_consts(const RiskFinalParams& p, RiskRo
         loss = f * d * d; coef[1] = 2.0 * f * d; coef[0] = -coef[1];
     }
     k.loss = (float)loss;
-    const int nu = (p.strategy == 1) ? 1 : 2;
     k.nu = nu;
     double all = 0.0;
     k.k1[1] = k.k0[1] = 0.0;
@@ -511,13 +518,12 @@ __device__ __forceinline__ void risk_row_consts(const RiskFinalParams& p, RiskRo
     for (int u = 0; u < nu; ++u) {
         const ZCol& zc = u ? zl : z0;
         const double sAT = g2[5 * u + 1], sAe = g2[5 * u + 2], sce = g2[5 * u + 3], sA = g2[5 * u + 4];
-        all += coef[u] * (dz[u] * (sce + Qg * sAT / zc.N + (double)p.C * sA * zc.S / zc.N - Qg * (double)p.C * sAe / zc.N) +
-                          dS[u] * Qg);
-        k.k1[u] = coef[u] * dz[u] * zc.S / zc.N;
-        k.k0[u] = -coef[u] * dz[u] * sAe / zc.N;
+        all += coef[u] * (dz[u] * (sce + rN * (Qg * sAT + (double)p.C * (sA * zc.S - Qg * sAe))) + dS[u] * Qg);
+        k.k1[u] = coef[u] * dz[u] * zc.S * rN;
+        k.k0[u] = -coef[u] * dz[u] * sAe * rN;
         if (zc.col == 0) {                                   // the column the risk is taken of IS the model column
             k.ko += coef[u] * dz[u];
-            k.kc += coef[u] * (dz[u] * sAT / zc.N + dS[u]);
+            k.kc += coef[u] * (dz[u] * sAT * rN + dS[u]);
         }
     }
     k.share = p.invert ? all / g2[10] : 0.0;
@@ -537,6 +543,42 @@ __device__ __forceinline__ float risk_row_gq(const RiskFinalParams& p, const Ris
     if (k.nu == 2) g += k.k1[1] * rs[2] + k.k0[1];
     if (p.invert) g = -g + (((double)row[0] == k.M) ? k.share : 0.0);
     return (float)g;
+}
+
+// Deterministic reduction of per-CTA partials part[count][STRIDE] (components 0..NC-1) by one CTA of THREADS threads:
+// thread t adds partials t, t + THREADS, ... (independent loads), then a fixed shuffle tree per warp and the warps in
+// order.  max0: component 0 is a maximum.  out[NC] and scratch[(THREADS / 32) * NC] are shared memory.  Ends with a barrier.
+template <int THREADS, int NC, int STRIDE>
+__device__ __forceinline__ void risk_reduce_partials(const double* part, int count, bool max0, double* out, double* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = (max0 && j == 0) ? -1.0e300 : 0.0;
+    for (int i = tid; i < count; i += THREADS) {
+        double v[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] = __ldcg(part + (size_t)i * STRIDE + j);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[j] = (max0 && j == 0) ? fmax(acc[j], v[j]) : acc[j] + v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        double w = acc[j];
+        if (max0 && j == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(LTR_FULL_MASK, w, o));
+        } else {
+            w = warp_sum(w);
+        }
+        if (lane == 0) scratch[warp * NC + j] = w;
+    }
+    __syncthreads();
+    if (tid < NC) {
+        double t = scratch[tid];
+        for (int w = 1; w < THREADS / 32; ++w) t = (max0 && tid == 0) ? fmax(t, scratch[w * NC + tid]) : t + scratch[w * NC + tid];
+        out[tid] = t;
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -643,22 +685,9 @@ __global__ void __launch_bounds__(STREAM_THREADS) risk_fused_rows_kernel(const R
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (warp < 4) {
-        double t = (warp == 0) ? -1.0e300 : 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) {
-            const double v = __ldcg(p.part1 + (size_t)i * 4 + warp);
-            t = (warp == 0) ? fmax(t, v) : t + v;
-        }
-        if (warp == 0) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(LTR_FULL_MASK, t, o));
-        } else {
-            t = warp_sum(t);
-        }
-        if (lane == 0) st[warp] = t;
-    } else if (tid - 128 < RISK_STATE - 4) {
-        st[4 + tid - 128] = (tid == 128) ? (double)r.B : 0.0;
-    }
+    __shared__ double scratch[STREAM_WARPS * 4];
+    risk_reduce_partials<STREAM_THREADS, 4, 4>(p.part1, (int)gridDim.x, true, st, scratch);
+    if (tid >= 4 && tid < RISK_STATE) st[tid] = (tid == 4) ? (double)r.B : 0.0;
     __syncthreads();
     risk_publish(p.c, 0, st);
     if (tid == 0) *p.done = 0u;
@@ -667,7 +696,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) risk_fused_rows_kernel(const R
 __global__ void __launch_bounds__(RISK_B_THREADS) risk_fused_stats2_kernel(const RiskFusedParams p) {
     __shared__ double g1[RISK_STATE], st[RISK_STATE];
     __shared__ int is_last;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     pdl_prologue();
     risk_gather(p.c, 0, g1);
     RiskFinalParams f = p.f;
@@ -681,13 +710,9 @@ __global__ void __launch_bounds__(RISK_B_THREADS) risk_fused_stats2_kernel(const
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int j = warp; j < RISK_STATE; j += RISK_B_THREADS / 32) {
-        double t = 0.0;
-        if (j < 13)
-            for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(p.part2 + (size_t)i * RISK_STATE + j);
-        t = warp_sum(t);
-        if (lane == 0) st[j] = t;
-    }
+    __shared__ double scratch[(RISK_B_THREADS / 32) * 13];
+    risk_reduce_partials<RISK_B_THREADS, 13, RISK_STATE>(p.part2, (int)gridDim.x, false, st, scratch);
+    if (tid >= 13 && tid < RISK_STATE) st[tid] = 0.0;
     __syncthreads();
     risk_publish(p.c, 1, st);
     if (tid == 0) p.done[1] = 0u;
@@ -724,6 +749,263 @@ __global__ void __launch_bounds__(STREAM_THREADS) risk_fused_bwd_kernel(const Ri
         effectiveness_bwd(pt, ps, r.lt, r.tmode, up, g);
         g.store(r.grad + (size_t)b * r.n, r.n, lane);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ONE launch: the three phases in a cooperative grid (every CTA resident), two grid-wide rendezvous instead of two
+// kernel boundaries.  A rendezvous costs two one-way trips through L2 and nothing else -- no atomics, no fences, no
+// separate flags: every value travels in a STAMPED SLOT, 16 bytes = two 8-byte words {32 bits of the double | the
+// call's generation number}, each written with one store (8-byte accesses are single-copy atomic), so a reader that
+// sees the generation in both words has the value.  Every CTA writes its partial state into its slots; CTA 0 polls
+// all of them (one warp per component, lanes striding over the CTAs, a fixed shuffle tree: deterministic), exchanges
+// the rank's state with the peers through stamped slots in their exchange blocks (NVLink stores, polled locally) when
+// the run is query-sharded, and writes the combined state into 16 stamped slots every CTA polls.
+// Warp w keeps its queries gwarp, gwarp + nwarps, ... across the phases; phase B and the per-query part of phase C
+// run one query per THREAD of the CTA (the fp64 code runs in as few warps as the CTA has rounds of queries).
+// ---------------------------------------------------------------------------------------------------
+constexpr int RISK_COOP_MAX_ROWS_PER_WARP = 16;   // (rounds of queries a CTA keeps: thread (k, wi) owns round k of warp wi)
+constexpr int RISK_XCHG_SLOTS_AT = 8192;          // byte offset of the stamped inbox [2][RISK_MAX_WORLD][RISK_STATE] in an exchange block
+static_assert(RISK_XCHG_SLOTS_AT + 2 * RISK_MAX_WORLD * RISK_STATE * 16 <= LTR_RISK_XCHG_BYTES, "exchange block too small");
+
+struct __align__(16) Slot {
+    unsigned long long w0, w1;
+};
+__device__ __forceinline__ void slot_write(Slot* s, double v, unsigned gen) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), g = (unsigned long long)gen << 32;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(s), "l"((b & 0xffffffffull) | g), "l"((b >> 32) | g) : "memory");
+}
+__device__ __forceinline__ bool slot_try(const Slot* s, unsigned gen, double& v) {
+    unsigned long long w0, w1;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(s) : "memory");
+    v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    return (unsigned)(w0 >> 32) == gen && (unsigned)(w1 >> 32) == gen;
+}
+__device__ __forceinline__ double slot_wait(const Slot* s, unsigned gen) {
+    double v;
+    while (!slot_try(s, gen, v)) {}
+    return v;
+}
+__device__ __forceinline__ Slot* xchg_slots(double* x, int slot, int r) {
+    return reinterpret_cast<Slot*>(reinterpret_cast<char*>(x) + RISK_XCHG_SLOTS_AT) + ((size_t)slot * RISK_MAX_WORLD + r) * RISK_STATE;
+}
+
+struct RiskCoopParams {
+    RiskFusedParams p;
+    Slot* slots1;            // workspace: [grid][4]  stamped CTA partials of the phase-1 state
+    Slot* slots2;            // workspace: [grid][16] stamped CTA partials of the phase-2 state
+    Slot* gslots;            // workspace: [2][RISK_STATE] stamped combined states of the two rounds
+    unsigned* gen_word;      // workspace: generation of the last completed call on this workspace
+    unsigned long long* stamps;   // workspace: 7 globaltimer stamps of CTA 0 (phase boundaries; diagnostics)
+};
+
+// CTA 0: component w of the CTAs' partials -> st[w] (warp w, w < NC), in a fixed order.  max0: component 0 is a maximum.
+template <int NC, int STRIDE>
+__device__ __forceinline__ void coop_collect(const Slot* slots, int count, unsigned gen, bool max0, double* st) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < NC) {
+        const bool is_max = max0 && warp == 0;
+        double t = is_max ? -1.0e300 : 0.0;
+        for (int i = lane; i < count; i += 32) {
+            const double v = slot_wait(slots + (size_t)i * STRIDE + warp, gen);
+            t = is_max ? fmax(t, v) : t + v;
+        }
+        if (is_max) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(LTR_FULL_MASK, t, o));
+        } else {
+            t = warp_sum(t);
+        }
+        if (lane == 0) st[warp] = t;
+    }
+    __syncthreads();
+}
+
+// CTA 0: the rank's state st[RISK_STATE] of round `slot` -> the combined state of all ranks in gs (in place when the run
+// is not sharded in-kernel), then into the 16 stamped slots every CTA polls.  `tmp`: RISK_MAX_WORLD * RISK_STATE doubles.
+__device__ __forceinline__ void coop_exchange(const RiskComm& c, int slot, unsigned gen, unsigned genx, const double* st,
+                                              double* gs, double* tmp, Slot* gdst) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (c.p2p && c.world > 1) {
+        for (int idx = tid; idx < RISK_STATE * c.world; idx += nthr) {             // my state into every rank's stamped inbox
+            const int r = idx / RISK_STATE, e = idx % RISK_STATE;
+            slot_write(xchg_slots(c.peer[r], slot, c.rank) + e, st[e], genx);
+        }
+        for (int idx = tid; idx < RISK_STATE * c.world; idx += nthr) {             // every rank's state out of mine
+            const int r = idx / RISK_STATE, e = idx % RISK_STATE;
+            const Slot* sp = xchg_slots(c.xchg, slot, r) + e;
+            double v;
+            const unsigned long long t0 = globaltimer_ns();
+            while (!slot_try(sp, genx, v)) {
+                if (globaltimer_ns() - t0 > RISK_SPIN_NS) {                        // a peer never arrived: poison, say so
+                    atomicExch(xchg_words(c.xchg) + RISK_W_STATUS, 1u);
+                    v = __longlong_as_double(0x7ff8000000000000ll);
+                    break;
+                }
+            }
+            tmp[idx] = v;
+        }
+        __syncthreads();
+        if (tid < RISK_STATE) {
+            double t = tmp[tid];
+            for (int r = 1; r < c.world; ++r) t = (slot == 0 && tid == 0) ? fmax(t, tmp[r * RISK_STATE + tid]) : t + tmp[r * RISK_STATE + tid];
+            gs[tid] = t;
+        }
+    } else if (tid < RISK_STATE) {
+        gs[tid] = st[tid];
+    }
+    __syncthreads();
+    if (tid < RISK_STATE) slot_write(gdst + tid, gs[tid], gen);
+}
+
+template <int ITEMS, int SV, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) risk_coop_kernel(const RiskCoopParams cp) {
+    constexpr int WARPS = THREADS / 32;
+    __shared__ double red[WARPS][RISK_STATE];
+    __shared__ double st[RISK_STATE], g1[RISK_STATE], g2[RISK_STATE];
+    __shared__ double tmp[RISK_MAX_WORLD * RISK_STATE];
+    __shared__ float gq_s[THREADS];
+    __shared__ RiskRowConsts k;
+    __shared__ unsigned sh_gen, sh_genx;
+    const RiskFusedParams& p = cp.p;
+    const RiskRowsParams& r = p.r;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarp = blockIdx.x * WARPS + warp;
+    const int nwarps = gridDim.x * WARPS;
+    const float ninf = __int_as_float(0xff800000);
+    const int C = 1 + r.S + r.add_ideal;
+    // generations of this call: one more than the last completed call on this workspace / on this exchange block (never
+    // 0; every rank makes the same calls on its exchange block, so the ranks' numbers agree).  CTA 0 stores them back at the end -- by then every CTA has
+    // read the old value (CTA 0 cannot pass the first rendezvous before every CTA has written its partial).
+    if (tid == 0) {
+        const unsigned g = __ldcg(cp.gen_word), gx = __ldcg(xchg_words(p.c.xchg) + RISK_W_SEQ);
+        sh_gen = (g == 0xffffffffu) ? 1u : g + 1u;           // stamps of the slots in this stream's workspace
+        sh_genx = (gx == 0xffffffffu) ? 1u : gx + 1u;        // stamps of the slots in the ranks' exchange blocks
+    }
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[0] = globaltimer_ns();
+    // ---- phase A: this warp's queries -> matrix rows; CTA partial of the phase-1 state --------------------------
+    double mx = -1.0e300, s0 = 0.0, sl = 0.0, sa = 0.0;       // warp-uniform
+    for (int b = gwarp; b < r.B; b += nwarps) {
+        RowRegs<ITEMS> pt, ps;
+        RowRegs<ITEMS> pb[SV ? SV : 1];
+        pt.load(r.y_true + (size_t)b * r.n, r.n, lane, ninf);
+        ps.load(r.y_pred + (size_t)b * r.n, r.n, lane, ninf);
+        if (SV) risk_load_bases<ITEMS, (SV ? SV : 1)>(r.y_base + (size_t)b * r.n * r.S, r.n, r.S, lane, ninf, pb);
+        softmax_row(pt);
+        softmax_row(ps);
+        float* mrow = r.mat + (size_t)b * C;
+        float v = effectiveness(pt, ps, r.lt, r.tmode), vlast = v;
+        if (lane == 0) mrow[0] = v;
+        s0 += (double)v;
+        sa += (double)v;
+        mx = fmax(mx, (double)v);
+        for (int j = 0; j < r.S; ++j) {
+            if (SV) {
+#pragma unroll
+                for (int jj = 0; jj < (SV ? SV : 1); ++jj)
+                    if (jj == j) {
+                        softmax_row(pb[jj]);
+                        v = effectiveness(pt, pb[jj], r.lt, r.tmode);
+                    }
+            } else {
+                pb[0].load_strided(r.y_base + (size_t)b * r.n * r.S + j, r.n, r.S, lane, ninf);
+                softmax_row(pb[0]);
+                v = effectiveness(pt, pb[0], r.lt, r.tmode);
+            }
+            if (lane == 0) mrow[1 + j] = v;
+            sa += (double)v;
+            mx = fmax(mx, (double)v);
+            vlast = v;
+        }
+        if (r.add_ideal) {
+            v = effectiveness(pt, pt, r.lt, r.tmode);
+            if (lane == 0) mrow[1 + r.S] = v;
+            sa += (double)v;
+            mx = fmax(mx, (double)v);
+            vlast = v;
+        }
+        sl += (double)vlast;
+    }
+    if (lane == 0) red[warp][0] = mx, red[warp][1] = s0, red[warp][2] = sl, red[warp][3] = sa;
+    __syncthreads();                                          // (also: this CTA's matrix rows are written)
+    const unsigned gen = sh_gen, genx = sh_genx;
+    if (tid < 4) {
+        double t = red[0][tid];
+        for (int w = 1; w < WARPS; ++w) t = (tid == 0) ? fmax(t, red[w][0]) : t + red[w][tid];
+        slot_write(cp.slots1 + (size_t)blockIdx.x * 4 + tid, t, gen);
+    }
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[1] = globaltimer_ns();
+    if (blockIdx.x == 0) {
+        coop_collect<4, 4>(cp.slots1, (int)gridDim.x, gen, true, st);
+        if (tid >= 4 && tid < RISK_STATE) st[tid] = (tid == 4) ? (double)r.B : 0.0;
+        __syncthreads();
+        coop_exchange(p.c, 0, gen, genx, st, g1, tmp, cp.gslots);
+    } else if (tid < RISK_STATE) {
+        g1[tid] = slot_wait(cp.gslots + tid, gen);
+    }
+    __syncthreads();
+    // ---- phase B: one query per THREAD of the CTA (thread (k, wi) = round k of warp wi's queries) ---------------------
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[2] = globaltimer_ns();
+    RiskFinalParams f = p.f;
+    f.state1 = g1;
+    double acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double rs[3] = {0.0, 0.0, 0.0};
+    const int myrow = (int)blockIdx.x * WARPS + (tid % WARPS) + (tid / WARPS) * nwarps;
+    const bool warp_has_rows = __any_sync(LTR_FULL_MASK, myrow < r.B);
+    if (warp_has_rows) {
+        const ZCol z0 = make_zcol(f, g1, false), zl = make_zcol(f, g1, true);
+        if (myrow < r.B) risk_stats2_row(f, z0, zl, f.mat + (size_t)myrow * C, acc, rs);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            const double w = warp_sum(acc[j]);
+            if (lane == 0) red[warp][j] = w;
+        }
+    } else if (lane < 13) {
+        red[warp][lane] = 0.0;
+    }
+    __syncthreads();
+    if (tid < 13) {
+        double t = 0.0;
+        for (int w = 0; w < WARPS; ++w) t += red[w][tid];
+        slot_write(cp.slots2 + (size_t)blockIdx.x * RISK_STATE + tid, t, gen);
+    }
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[3] = globaltimer_ns();
+    if (blockIdx.x == 0) {
+        coop_collect<13, RISK_STATE>(cp.slots2, (int)gridDim.x, gen, false, st);
+        if (tid >= 13 && tid < RISK_STATE) st[tid] = 0.0;
+        __syncthreads();
+        coop_exchange(p.c, 1, gen, genx, st, g2, tmp, cp.gslots + RISK_STATE);
+    } else if (tid < RISK_STATE) {
+        g2[tid] = slot_wait(cp.gslots + RISK_STATE + tid, gen);
+    }
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[4] = globaltimer_ns();
+    // ---- phase C: loss; d loss / d mat[q, 0] per thread; backward rows per warp -------------------------------------
+    f.state2 = g2;
+    if (tid == 0) {
+        risk_row_consts(f, k);
+        if (blockIdx.x == 0) {
+            f.loss[0] = k.loss;
+            *cp.gen_word = gen;                              // the call is through both rendezvous everywhere on this GPU
+            if (p.c.p2p) xchg_words(p.c.xchg)[RISK_W_SEQ] = genx;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[5] = globaltimer_ns();
+    if (!r.grad) return;
+    gq_s[tid] = (myrow < r.B) ? risk_row_gq(f, k, f.mat + (size_t)myrow * C, rs) : 0.f;
+    __syncthreads();
+    int li = 0;
+    for (int b = gwarp; b < r.B; b += nwarps, ++li) {
+        RowRegs<ITEMS> pt, ps, g;
+        pt.load(r.y_true + (size_t)b * r.n, r.n, lane, ninf);
+        ps.load(r.y_pred + (size_t)b * r.n, r.n, lane, ninf);
+        const float up = gq_s[li * WARPS + warp];
+        softmax_row(pt);
+        softmax_row(ps);
+        effectiveness_bwd(pt, ps, r.lt, r.tmode, up, g);
+        g.store(r.grad + (size_t)b * r.n, r.n, lane);
+    }
+    if (tid == 0 && blockIdx.x == 0) cp.stamps[6] = globaltimer_ns();
 }
 
 // ---- the single-CTA phase kernels of ltr_risk_phase ------------------------------------------------
@@ -804,22 +1086,56 @@ static int risk_rows_grid(int B) {
     return (int)(g < 1 ? 1 : g);
 }
 
-static int fill_comm(RiskComm& c, void* xchg, int rank, int world, const void* const* peer_xchg, unsigned seq, const char* who) {
+static int fill_comm(RiskComm& c, void* xchg, int rank, int world, const void* const* peer_xchg, const char* who) {
     if (!xchg || world < 1 || world > RISK_MAX_WORLD || rank < 0 || rank >= world) return set_error(LTR_EINVAL, who);
     c.xchg = static_cast<double*>(xchg);
     c.rank = rank;
     c.world = world;
     c.p2p = (peer_xchg != nullptr && world > 1) ? 1 : 0;
-    c.seq = seq;
     for (int r = 0; r < RISK_MAX_WORLD; ++r)
         c.peer[r] = (c.p2p && r < world) ? static_cast<double*>(const_cast<void*>(peer_xchg[r])) : nullptr;
     if (c.p2p) {
-        if (seq == 0) return set_error(LTR_EINVAL, who);
         for (int r = 0; r < world; ++r)
             if (!c.peer[r]) return set_error(LTR_EINVAL, who);
         if (c.peer[rank] != c.xchg) return set_error(LTR_EINVAL, who);
     }
     return 0;
+}
+
+constexpr int LTR_COOP_UNFIT = -1000;    // (internal) the batch does not fit the cooperative grid: use the three launches
+
+// grid = resident CTAs of the kernel on this device (occupancy x SMs), at most one warp per query; every warp keeps at
+// most RISK_COOP_MAX_ROWS_PER_WARP queries
+template <int THREADS, typename Kern>
+static int launch_coop(Kern kern, const RiskCoopParams& cp, int B, cudaStream_t st) {
+    constexpr int WARPS = THREADS / 32;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0) != cudaSuccess || occ < 1) {
+        (void)cudaGetLastError();
+        return LTR_COOP_UNFIT;
+    }
+    if (occ > 2) occ = 2;
+    long long grid = (long long)device_sm_count() * occ;
+    const long long need = ((long long)B + WARPS - 1) / WARPS;
+    if (grid > need) grid = need < 1 ? 1 : need;
+    if (grid > LTR_WS_RISK_COOP_MAX_GRID) grid = LTR_WS_RISK_COOP_MAX_GRID;
+    if ((long long)B > grid * WARPS * RISK_COOP_MAX_ROWS_PER_WARP) return LTR_COOP_UNFIT;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, cp);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        (void)cudaGetLastError();
+        return LTR_COOP_UNFIT;
+    }
+    return (int)e;
 }
 
 }  // namespace ltr
@@ -837,7 +1153,7 @@ LTR_API int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, 
     RiskPhaseParams p;
     p.f = RiskFinalParams{mat, Q, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, nullptr, nullptr,
                           loss, gq, gmat};
-    if (int rc = fill_comm(p.c, xchg, rank, world, nullptr, 0, "ltr_risk_phase: bad exchange block / rank / world")) return rc;
+    if (int rc = fill_comm(p.c, xchg, rank, world, nullptr, "ltr_risk_phase: bad exchange block / rank / world")) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int rc = phase == 1 ? launch_pdl(risk_stats1_kernel, 1, RISKF_THREADS, 0, st, p)
                  : phase == 2 ? launch_pdl(risk_stats2_kernel, 1, RISKF_THREADS, 0, st, p)
@@ -850,7 +1166,7 @@ LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, co
                                     int transformation, int add_ideal, int kind, int invert, int return_strategy,
                                     int precedence_quirk, float alpha, float negative, float* mat, double* rowstate,
                                     float* loss, float* grad, int phases, void* xchg, int rank, int world,
-                                    const void* const* peer_xchg, unsigned seq, void* workspace, void* stream) {
+                                    const void* const* peer_xchg, void* workspace, void* stream) {
     using namespace ltr;
     if (B < 0 || n <= 0 || S < 0 || !loss || !workspace || (phases & ~7) || !phases)
         return set_error(LTR_EINVAL, "ltr_risk_listnet_fwdbwd: bad arguments");
@@ -865,7 +1181,7 @@ LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, co
     p.r = RiskRowsParams{y_pred, y_true, y_baselines, B, n, S, transformation, add_ideal ? 1 : 0, (kind == 2) ? 1 : 0, mat, grad};
     p.f = RiskFinalParams{mat, B, C, kind, invert, return_strategy, precedence_quirk, alpha, negative, nullptr, nullptr, loss,
                           nullptr, nullptr};
-    if (int rc = fill_comm(p.c, xchg, rank, world, peer_xchg, seq, "ltr_risk_listnet_fwdbwd: bad exchange block / rank / world / seq"))
+    if (int rc = fill_comm(p.c, xchg, rank, world, peer_xchg, "ltr_risk_listnet_fwdbwd: bad exchange block / rank / world"))
         return rc;
     p.part1 = ws_risk_part1(workspace);
     p.part2 = ws_risk_part2(workspace);
@@ -874,6 +1190,24 @@ LTR_API int ltr_risk_listnet_fwdbwd(const float* y_pred, const float* y_true, co
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = risk_rows_grid(B);
     int rc = 0;
+    if (phases == 7 && n <= 256 && (world == 1 || peer_xchg)) {
+        // one cooperative launch (every CTA resident); anything it cannot take falls through to the three launches
+        const bool v2 = S == 2 && reinterpret_cast<uintptr_t>(y_baselines) % 8 == 0;
+        const bool v4 = S == 4 && n <= 128 && reinterpret_cast<uintptr_t>(y_baselines) % 16 == 0;
+        char* wsb = reinterpret_cast<char*>(workspace);
+        RiskCoopParams cp{p, reinterpret_cast<Slot*>(wsb + LTR_WS_RISK_PART1), reinterpret_cast<Slot*>(wsb + LTR_WS_RISK_PART2),
+                          reinterpret_cast<Slot*>(wsb + 256), ws_counter(workspace, LTR_WS_RISK_COUNTERS + 2),
+                          reinterpret_cast<unsigned long long*>(wsb + 768)};
+        // short slates: one CTA of 1024 threads per SM (64 registers); n <= 256: 512 threads
+        rc = n <= 128 ? (v2 ? launch_coop<1024>(risk_coop_kernel<4, 2, 1024>, cp, B, st)
+                            : v4 ? launch_coop<1024>(risk_coop_kernel<4, 4, 1024>, cp, B, st)
+                                 : launch_coop<1024>(risk_coop_kernel<4, 0, 1024>, cp, B, st))
+                      : (v2 ? launch_coop<512>(risk_coop_kernel<8, 2, 512>, cp, B, st)
+                            : launch_coop<512>(risk_coop_kernel<8, 0, 512>, cp, B, st));
+        if (rc == 0) return 0;
+        if (rc != LTR_COOP_UNFIT) return set_cuda_error(rc, "ltr_risk_listnet_fwdbwd (cooperative launch)");
+        rc = 0;
+    }
     if (phases & 1) {
         const bool v2 = S == 2 && n <= 256 && reinterpret_cast<uintptr_t>(y_baselines) % 8 == 0;
         const bool v4 = S == 4 && n <= 128 && reinterpret_cast<uintptr_t>(y_baselines) % 16 == 0;

@@ -11,8 +11,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LTR_B200_LIB") or os.path.join(_HERE, "lib", "libltr_b200.so")   # (override: A/B builds)
 
-WORKSPACE_BYTES = 131072
-RISK_XCHG_BYTES = 8192
+WORKSPACE_BYTES = 262144
+RISK_XCHG_BYTES = 16384
 RISK_MAX_WORLD = 16
 
 _P = c_void_p
@@ -49,7 +49,7 @@ _SIGNATURES = {
     "ltr_risk_phase": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, c_int,
                                _P, _P, _P, _P]),
     "ltr_risk_listnet_fwdbwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                        c_float, _P, _P, _P, _P, c_int, _P, c_int, c_int, POINTER(c_void_p), c_uint, _P, _P]),
+                                        c_float, _P, _P, _P, _P, c_int, _P, c_int, c_int, POINTER(c_void_p), _P, _P]),
     "ltr_risk_xchg_alloc": (c_int, [POINTER(c_void_p)]),
     "ltr_risk_xchg_free": (c_int, [_P]),
     "ltr_ipc_export": (c_int, [_P, _P]),

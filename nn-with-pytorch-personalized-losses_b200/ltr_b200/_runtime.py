@@ -44,6 +44,31 @@ def risk_xchg(device: torch.device) -> torch.Tensor:
     return blk
 
 
+_risk_scratch = {}
+
+
+def risk_scratch(device: torch.device, stream: int, B: int, C: int):
+    """(workspace, exchange block, mat [B, C] fp32, rowstate [max(B, 1), 3] fp64) of the fused risk losses for one
+    (device, stream): pure scratch between the launches of one call, so calls on the same stream may share it."""
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev_index, stream)
+    ent = _risk_scratch.get(key)
+    if ent is None or ent[2].shape[0] < B or ent[2].shape[1] != C:
+        ws = _workspaces.get(key)
+        if ws is None:
+            ws = torch.zeros(_lib.WORKSPACE_BYTES // 4, dtype=torch.int32, device=device)
+            _workspaces[key] = ws
+        blk = _risk_blocks.get(key)
+        if blk is None:
+            blk = torch.zeros(_lib.RISK_XCHG_BYTES // 8, dtype=torch.float64, device=device)
+            _risk_blocks[key] = blk
+        rows = max(B, 1)
+        ent = (ws, blk, torch.empty(rows, C, dtype=torch.float32, device=device),
+               torch.empty(rows, 3, dtype=torch.float64, device=device))
+        _risk_scratch[key] = ent
+    return ent
+
+
 def disc_prefix(device: torch.device) -> torch.Tensor:
     """fp64 table P[r] = sum_{q<=r} 1/log2(1+q), built on the device by the library."""
     key = device.index if device.index is not None else torch.cuda.current_device()

@@ -40,7 +40,9 @@ def _guard(fn):
     data, not the caller's current device (the reference callables are device-agnostic)."""
     @functools.wraps(fn)
     def wrapped(*args, **kwargs):
-        first = next(a for a in args if isinstance(a, torch.Tensor))
+        first = args[0] if isinstance(args[0], torch.Tensor) else args[1]      # (ctx, tensor, ...) or (tensor, ...)
+        if first.device.index == torch.cuda.current_device():                 # the common case: nothing to switch
+            return fn(*args, **kwargs)
         with torch.cuda.device(first.device):
             return fn(*args, **kwargs)
     return wrapped
@@ -391,38 +393,37 @@ class _RiskListnet(torch.autograd.Function):
         dev = y_pred.device
         S = 0 if y_base is None else y_base.shape[2]
         C = 1 + S + (1 if add_ideal else 0)
-        mat = torch.empty(B, C, dtype=torch.float32, device=dev)
-        rowstate = torch.empty(max(B, 1), 3, dtype=torch.float64, device=dev)
+        stream = rt.stream_ptr()
+        ws, xchg, mat, rowstate = rt.risk_scratch(dev, stream, B, C)   # per (device, stream): stream-ordered reuse is safe
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         # mat <- max(mat) - mat: riskLosses.py:49-50 (lt 1, 3) and :274-275 (t-risk: lt 1 only)
         invert = (lt == 1) if kind == KIND_T else (lt in (1, 3))
         need = ctx.needs_input_grad[0]
         grad = torch.empty_like(y_pred) if need else None
         sharded = sharding.is_sharded(group)
-        rank, world = sharding.rank_world(group)
+        rank, world = sharding.rank_world(group) if sharded else (0, 1)
         peers = sharding.risk_peer_exchange(group, dev) if sharded else None
+        ptrs = (y_pred.data_ptr(), y_true.data_ptr(), _ptr(y_base), mat.data_ptr(), _ptr(grad)) if B else (None,) * 5
+        args = (B, n, S, int(lt), int(bool(add_ideal)), int(kind), int(invert), int(strategy), int(quirk), float(alpha),
+                float(negative), ptrs[3], rowstate.data_ptr(), loss.data_ptr(), ptrs[4])
 
-        def call(phases, xchg_ptr, peer_ptrs, seq):
-            _lib.check(lib.ltr_risk_listnet_fwdbwd(
-                y_pred.data_ptr() if B else None, y_true.data_ptr() if B else None, _ptr(y_base) if B else None, B, n, S,
-                int(lt), int(bool(add_ideal)), int(kind), int(invert), int(strategy), int(quirk), float(alpha),
-                float(negative), mat.data_ptr() if B else None, rowstate.data_ptr(), loss.data_ptr(),
-                _ptr(grad) if B else None, phases, xchg_ptr, rank, world, peer_ptrs, seq,
-                rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_risk_listnet_fwdbwd")
+        def call(phases, xchg_ptr, peer_ptrs):
+            rc = lib.ltr_risk_listnet_fwdbwd(ptrs[0], ptrs[1], ptrs[2], *args, phases, xchg_ptr, rank, world, peer_ptrs,
+                                             ws.data_ptr(), stream)
+            if rc:
+                _lib.check(rc, "ltr_risk_listnet_fwdbwd")
 
         if peers is not None:
-            call(7, peers.local_ptr, peers.peer_ptrs, peers.next_seq())
+            call(7, peers.local_ptr, peers.peer_ptrs)
         elif sharded:
-            xchg = rt.risk_xchg(dev)
-            call(1, xchg.data_ptr(), None, 0)
+            call(1, xchg.data_ptr(), None)
             sharding.allgather_risk_round(xchg, 0, group)
-            call(2, xchg.data_ptr(), None, 0)
+            call(2, xchg.data_ptr(), None)
             sharding.allgather_risk_round(xchg, 1, group)
-            call(4, xchg.data_ptr(), None, 0)
+            call(4, xchg.data_ptr(), None)
         else:
-            call(7, rt.risk_xchg(dev).data_ptr(), None, 0)
+            call(7, xchg.data_ptr(), None)
         ctx.grad = grad
-        ctx.mat = mat
         return loss
 
     @staticmethod

@@ -95,12 +95,7 @@ class RiskPeerExchange:
                 ptrs.append(peer.value)
         self._ptrs = ptrs
         self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
-        self.seq = 0
         dist.barrier(group=group)                 # nobody publishes before everybody has mapped everybody
-
-    def next_seq(self) -> int:
-        self.seq = self.seq % 0x7FFFFFFF + 1      # never 0, never equal to the previous call's
-        return self.seq
 
     def status(self) -> int:
         st = ctypes.c_int(0)

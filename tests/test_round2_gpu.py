@@ -231,7 +231,7 @@ def test_sharded_risk_listnet_emulated_ranks(kind, lt, rs, ideal, world):
         p = (lambda x: x.data_ptr() if t["B"] else None)
         _lib.check(lib.ltr_risk_listnet_fwdbwd(p(t["s"]), p(t["y"]), p(t["base"]), t["B"], n, Sx, lt, add_ideal, kind_id, invert,
                                                strategy, quirk, 5.0, 1.0, p(t["mat"]), t["rows"].data_ptr(), t["loss"].data_ptr(),
-                                               p(t["grad"]), phases, blocks[r].data_ptr(), r, world, None, 0,
+                                               p(t["grad"]), phases, blocks[r].data_ptr(), r, world, None,
                                                rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_risk_listnet_fwdbwd")
 
     for r in range(world):

@@ -58,6 +58,35 @@ def _roof(alg_bytes, sec):
     return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src}
 
 
+_SFU_PEAK = [None]          # SFU-op/s measured by the caller (bench.py: ltr_probe_sfu) or here on first use
+
+
+def _sfu_peak():
+    if _SFU_PEAK[0] is None:
+        import ctypes
+        from ltr_b200 import _lib, _runtime as rt
+        lib = _lib.load()
+        out = torch.zeros(1, device="cuda")
+        ops_count = ctypes.c_longlong(0)
+        best = float("inf")
+        for i in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib.ltr_probe_sfu(out.data_ptr(), 4096, ctypes.byref(ops_count), rt.stream_ptr())
+            b.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, a.elapsed_time(b))
+        _SFU_PEAK[0] = ops_count.value / (best * 1e-3)
+    return _SFU_PEAK[0]
+
+
+def _roof_sfu(sfu_ops, sec, **extra):
+    peak = _sfu_peak()
+    return dict({"bound": "sfu", "achieved": sfu_ops / sec / 1e12, "peak": peak / 1e12, "unit": "TSFU-op/s",
+                 "frac": sfu_ops / sec / peak, "peak_source": "pure ex2.approx loop (ltr_probe_sfu), measured in this run"}, **extra)
+
+
 def bench_listnet(iters=200, B=65536, n=128):
     """BASELINE configs[0] loss: ListNet fwd+bwd, no padding.  12 n bytes per slate."""
     from ltr_b200 import _lib, _runtime as rt
@@ -136,7 +165,7 @@ def bench_lambda(iters=50, B=1024, n=256):
     ws = rt.workspace(torch.device("cuda", torch.cuda.current_device()))
 
     def step(i):
-        lib.ltr_lambda_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 1e-10, -1.0, 4, 0, 1.0, 10.0, 0, 0, sums[0].data_ptr(),
+        lib.ltr_lambda_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 1e-10, -1.0, 4, -1, 1.0, 10.0, 0, 0, sums[0].data_ptr(),
                               sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), grad.data_ptr(),
                               ws.data_ptr(), rt.stream_ptr())
 
@@ -144,14 +173,18 @@ def bench_lambda(iters=50, B=1024, n=256):
     return {"metric": "LambdaLoss ndcgLoss2PP fwd+bwd slates/s (n=256)", "value": B / sec, "unit": "slates/s",
             "us_per_call": sec * 1e6,
             "config": {"workload": f"{B} slates x {n} docs, valid len U{{128..256}}, sigma=1, mu=10, sum, binary"},
-            "roofline": {"bound": "sfu", "achieved": 3.0 * pairs / sec / 1e12, "unit": "TSFU-op/s",
-                         "algorithmic": f"3 SFU ops per masked ordered pair, {pairs} pairs per launch (SURVEY 8d)",
-                         "kernel": "lambda_kernel<4>"}}
+            "roofline": _roof_sfu(3.0 * pairs, sec,
+                                  algorithmic=f"3 SFU ops per masked ordered pair, {pairs} pairs per launch (SURVEY 8d)",
+                                  kernel="lambda_kernel<4>")}
 
 
-def bench_georisk(iters=100, B=8192, n=128, S=2):
-    """BASELINE configs[3] on one GPU: geoRiskListnetLoss lt=1, rs=1, alpha=5, fwd+bwd (rows + 3 phases + bwd)."""
-    from ltr_b200 import ops
+def bench_georisk(iters=200, B=8192, n=128, S=2):
+    """BASELINE configs[3] on one GPU: geoRiskListnetLoss lt=1, rs=1, alpha=5, fwd+bwd = three launches (rows + phase-1
+    state, z-risk sums, loss + backward rows).  Timed twice: through the drop-in callable's autograd Function (what a
+    training step pays, Python included) and as the bare C-ABI call replayed from a CUDA graph (the kernels alone)."""
+    from ltr_b200 import _lib, _runtime as rt, ops
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
     g = torch.Generator().manual_seed(400)
     s = torch.randn(B, n, generator=g).cuda().requires_grad_(True)
     y = torch.randint(0, 5, (B, n), generator=g).float().cuda()
@@ -161,10 +194,40 @@ def bench_georisk(iters=100, B=8192, n=128, S=2):
         ops.risk_listnet(s, y, base, ops.KIND_GEO, 5.0, 1, 1, 1.0, False)
 
     sec = _time(step, iters)
+    # bare C-ABI call, captured: 20 calls per graph
+    mat = torch.empty(B, 1 + S, device=dev)
+    rows = torch.empty(B, 3, dtype=torch.float64, device=dev)
+    loss, grad = torch.empty(1, device=dev), torch.empty(B, n, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    graph = torch.cuda.CUDAGraph()
+    sd = s.detach()
+    with torch.cuda.stream(side):
+        xchg, ws, st = rt.risk_xchg(dev), rt.workspace(dev), rt.stream_ptr()
+
+        def raw(phases=7):
+            _lib.check(lib.ltr_risk_listnet_fwdbwd(sd.data_ptr(), y.data_ptr(), base.data_ptr(), B, n, S, 1, 0, ops.KIND_GEO, 1, 1,
+                                                   0, 5.0, 1.0, mat.data_ptr(), rows.data_ptr(), loss.data_ptr(), grad.data_ptr(),
+                                                   phases, xchg.data_ptr(), 0, 1, None, ws.data_ptr(), st), "ltr_risk_listnet_fwdbwd")
+        raw()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(20):
+                raw()
+        graph3 = torch.cuda.CUDAGraph()                       # the three-launch form (what all-gather sharding uses)
+        with torch.cuda.graph(graph3, stream=side):
+            for _ in range(20):
+                raw(1), raw(2), raw(4)
+    sec_graph = _time(lambda i: graph.replay(), max(5, iters // 20)) / 20
+    sec_graph3 = _time(lambda i: graph3.replay(), max(5, iters // 20)) / 20
     alg = (4.0 * n * (2 + S) + 4.0 * n) * B + 8.0 * n * B      # rows read + grad write + backward re-read of s, y
-    return {"metric": "geoRiskListnetLoss fwd+bwd queries/s (n=128, S=2)", "value": B / sec, "unit": "queries/s",
-            "us_per_call": sec * 1e6, "config": {"workload": f"{B} queries x {n} docs x {S} baseline systems, lt=1, rs=1"},
-            "roofline": dict(_roof(alg, sec), kernel="risk_rows_kernel<4> + risk phases + risk_rows_bwd_kernel<4>",
+    return {"metric": "geoRiskListnetLoss fwd+bwd queries/s (n=128, S=2)", "value": B / sec_graph, "unit": "queries/s",
+            "us_per_call": sec_graph * 1e6, "us_per_call_three_launches": sec_graph3 * 1e6,
+            "us_per_call_python_callable": sec * 1e6,
+            "config": {"workload": f"{B} queries x {n} docs x {S} baseline systems, lt=1, rs=1; value / us_per_call: the C-ABI "
+                                   "call (ONE cooperative launch) replayed from a CUDA graph of 20 calls; "
+                                   "us_per_call_three_launches: the same call phase by phase; us_per_call_python_callable: the "
+                                   "drop-in callable's autograd Function, one call per step"},
+            "roofline": dict(_roof(alg, sec_graph), kernel="risk_coop_kernel<4,2> (one cooperative launch, two grid rendezvous)",
                              algorithmic="4 n (2+S) read + 4 n written + 8 n re-read per query")}
 
 
@@ -193,9 +256,9 @@ def bench_approx_1024(iters=50, B=64, n=1024):
     sec = _time(step, iters)
     return {"metric": "approxNDCG fwd+bwd slates/s (n=1024)", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
             "config": {"workload": f"{B} slates x {n} docs, valid len U{{512..1024}}, alpha=10"},
-            "roofline": {"bound": "sfu", "achieved": 2.0 * pairs / sec / 1e12, "unit": "TSFU-op/s",
-                         "algorithmic": f"2 SFU ops per ordered valid pair, {pairs} pairs per launch",
-                         "kernel": "approx_ndcg_cluster_kernel (one cluster of 8 CTAs per slate, partial sums over distributed shared memory)"}}
+            "roofline": _roof_sfu(2.0 * pairs, sec, algorithmic=f"2 SFU ops per ordered valid pair, {pairs} pairs per launch",
+                                  kernel="approx_ndcg_cluster_kernel (one cluster of 8 CTAs per slate, partial sums over "
+                                         "distributed shared memory)")}
 
 
 def bench_approx_large(iters=30, B=65536, n=128):
@@ -227,8 +290,9 @@ def bench_approx_large(iters=30, B=65536, n=128):
     sec = _time(step, iters)
     return {"metric": "approxNDCG fwd+bwd slates/s (n=128, 65536 slates per launch)", "value": B / sec, "unit": "slates/s",
             "us_per_call": sec * 1e6, "config": {"workload": f"{B} slates x {n} docs, valid len U{{64..128}}, alpha=10"},
-            "roofline": {"bound": "sfu", "achieved": 2.0 * (sum(pairs) / ring) / sec / 1e12, "unit": "TSFU-op/s",
-                         "algorithmic": "2 SFU ops per ordered valid pair", "kernel": "approx_ndcg_warp_kernel"}}
+            "roofline": _roof_sfu(2.0 * (sum(pairs) / ring), sec,
+                                  algorithmic="2 SFU ops per ordered valid pair (the kernel issues one MUFU per UNORDERED pair "
+                                              "and pass: frac can exceed 1)", kernel="approx_ndcg_warp_kernel")}
 
 
 def bench_ndcg_1024(iters=30):
@@ -240,7 +304,9 @@ ALL = {"listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg_large": bench_ndcg_la
        "georisk": bench_georisk, "approx1024": bench_approx_1024, "approx_large_batch": bench_approx_large}
 
 
-def run_all(only=None, iters=None):
+def run_all(only=None, iters=None, sfu_peak=None):
+    if sfu_peak is not None:
+        _SFU_PEAK[0] = sfu_peak
     out = {}
     for name, fn in ALL.items():
         if only and name not in only:
