@@ -288,6 +288,28 @@ int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int inve
 int ltr_georisk_default_f64(const double* mat, int Q, int C, double alpha, double* out, void* stream);
 
 /*
+ * Slate ingestion (HOST code, host pointers).  replaces utils/dataset.py:33-101 (get_data, load_baseline_file)
+ *
+ * svmlight / LETOR text "label qid:ID idx:val ... # comment" -> query-major padded arrays.  A new query starts wherever
+ * the qid of consecutive lines CHANGES (as the reference groups them, dataset.py:52-65).
+ *   ltr_svmlight_scan: counts[5] = {lines, queries, docs in the longest query, smallest feature index, largest}.
+ *   ltr_svmlight_load: queries [first_query, first_query + num_queries) -- a rank's shard -- into
+ *     X [num_queries, n_docs, n_features] (dense, zero-filled), y [num_queries, n_docs] (pad_value beyond a query's
+ *     docs), qids [num_queries] and lens [num_queries] (docs of the query before truncation to n_docs; either may be
+ *     NULL).  index_base 1 (LETOR), 0, or -1 = sklearn's zero_based="auto" (zero-based iff an index 0 occurs).
+ *     `threads` host threads parse the lines (0 = all cores).  Buffers are the caller's (pinned for an async H2D copy).
+ * Baseline scores "qid,score_1,...,score_S" per doc:
+ *   ltr_baseline_csv_scan: counts[4] = {lines, queries, docs in the longest query, S}.
+ *   ltr_baseline_csv_load: scores [num_queries, n_docs, S] (zero beyond a query's docs), lens [num_queries] or NULL.
+ */
+int ltr_svmlight_scan(const char* path, int threads, long long* counts);
+int ltr_svmlight_load(const char* path, long long first_query, long long num_queries, int n_docs, int n_features,
+                      int index_base, float pad_value, float* X, float* y, long long* qids, int* lens, int threads);
+int ltr_baseline_csv_scan(const char* path, long long* counts);
+int ltr_baseline_csv_load(const char* path, long long first_query, long long num_queries, int n_docs, int S, float* scores,
+                          int* lens);
+
+/*
  * Roofline probes (measurement only): a pure ex2.approx loop and a pure FFMA loop, 8 CTAs of
  * 256 threads per SM.  *ops_out (host pointer, may be NULL) receives the number of SFU ops /
  * FP32 FMA lane-ops one launch executes; `out` is one device float that is never written.

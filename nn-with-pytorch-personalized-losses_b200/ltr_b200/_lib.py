@@ -57,6 +57,10 @@ _SIGNATURES = {
     "ltr_ipc_close": (c_int, [_P]),
     "ltr_risk_xchg_status": (c_int, [_P, POINTER(c_int)]),
     "ltr_georisk_default_f64": (c_int, [_P, c_int, c_int, c_double, _P, _P]),
+    "ltr_svmlight_scan": (c_int, [c_char_p, c_int, POINTER(c_longlong)]),
+    "ltr_svmlight_load": (c_int, [c_char_p, c_longlong, c_longlong, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int]),
+    "ltr_baseline_csv_scan": (c_int, [c_char_p, POINTER(c_longlong)]),
+    "ltr_baseline_csv_load": (c_int, [c_char_p, c_longlong, c_longlong, c_int, c_int, _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
     "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
 }
