@@ -288,6 +288,25 @@ int ltr_risk_phase(int phase, const float* mat, int Q, int C, int kind, int inve
 int ltr_georisk_default_f64(const double* mat, int Q, int C, double alpha, double* out, void* stream);
 
 /*
+ * Fused ranker tail + loss: TripleLayerNet forward, approxNDCG forward + backward and the ranker's weight
+ * gradients in one pass over the features.   replaces, for BASELINE configs[1], the step
+ *   architeture/tripleLayer.py:5-17 (forward) -> losses/approxNDCG.py:7-53 -> loss.backward()  (main_batch_execution.py:128-170)
+ * l1 (no activation) and l2 are folded by the caller: Wc = W2 W1 [32, F], bc = W2 b1 + b2; z = x Wc^T + bc, a = sigmoid(z),
+ * score = a . w3 + b3.  tcgen05 tf32 tensor-core MMAs (fp32 accumulation in tensor memory), feature tiles by TMA.
+ *   X : [B, 128, F] features (F <= 160, F % 4 == 0, 16-byte aligned), y_true : [B, 128] (pad_value marks padding)
+ *   scores [B, 128], slate_ndcg [B], loss [1] out;  gWc [32, F], gbc [32], gw3 [32], gb3 [1] out:
+ *   d loss / d {Wc, bc, w3, b3}; the caller unfolds them into the six parameter gradients
+ *   (dW1 = W2^T gWc, db1 = W2^T gbc, dW2 = gWc W1^T + gbc b1^T, db2 = gbc, dW3 = gw3, db3 = gb3).
+ *   scratch : ltr_triple_scratch_bytes(B, 128, F) bytes of device memory (per-CTA partial gradients).
+ */
+size_t ltr_triple_scratch_bytes(int B, int n, int F);
+int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, const float* Wc, const float* bc, const float* w3,
+                                  float b3, int B, int n, int F, float alpha, float eps, float pad_value,
+                                  const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg, float* loss,
+                                  float* gWc, float* gbc, float* gw3, float* gb3, void* scratch, size_t scratch_bytes,
+                                  void* workspace, void* stream);
+
+/*
  * Slate ingestion (HOST code, host pointers).  replaces utils/dataset.py:33-101 (get_data, load_baseline_file)
  *
  * svmlight / LETOR text "label qid:ID idx:val ... # comment" -> query-major padded arrays.  A new query starts wherever

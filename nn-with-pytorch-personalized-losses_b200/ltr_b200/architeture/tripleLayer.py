@@ -1,0 +1,92 @@
+"""TripleLayerNet -- drop-in for reference architeture/tripleLayer.py:5-17 (same module: l1 136->64 with NO activation,
+sigmoid(l2) 64->32, l3 32->1; `forward(x, mask, indices)` returns [B, n, 1]) -- plus the fused training step of BASELINE
+configs[1]: ranker forward, approxNDCG forward + backward and all six parameter gradients from ONE pass over the
+feature tensor (`ltr_triple_approx_ndcg_fwdbwd`: TMA-fed tcgen05 tf32 MMAs, the loss in registers in between).
+
+    net = TripleLayerNet(136).cuda()
+    loss = net.approx_ndcg_loss(X, y_true, alpha=10.)       # == approxNDCGLoss(net(X, None, None).squeeze(-1), y_true, alpha=10.)
+    loss.backward()                                           # l1 / l2 / l3 .weight / .bias gradients
+
+The dense layers of `forward` stay stock `torch.nn` (cuBLAS), as north_star asks; only the fused step is custom.
+Operands are rounded to tf32 (10-bit mantissa) inside the tensor cores: scores / loss / gradients agree with the
+fp32 modules to ~1e-3 relative.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd.function import once_differentiable
+
+from .. import _lib, _runtime as rt
+
+SLATE = 128          # docs per slate of the fused path (one MMA tile)
+MAX_FEATURES = 160   # the fused kernel stages up to 5 chunks of 32 features (MSLR-WEB10K: 136)
+
+
+class _FusedTripleApproxNDCG(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, y_true, W1, b1, W2, b2, W3, b3, eps, pad, alpha):
+        lib = _lib.load()
+        B, n, F = X.shape
+        dev = X.device
+        with torch.cuda.device(dev):
+            # the linear part of the net folded once per step (64 x 136 and 32 x 64: microseconds of cuBLAS)
+            Wc = (W2.detach() @ W1.detach()).contiguous()
+            bc = (W2.detach() @ b1.detach() + b2.detach()).contiguous()
+            w3 = W3.detach().reshape(-1).contiguous()
+            scores = torch.empty(B, n, dtype=torch.float32, device=dev)
+            slate = torch.empty(B, dtype=torch.float32, device=dev)
+            out = torch.empty(1 + 32 * F + 32 + 32 + 1, dtype=torch.float32, device=dev)
+            loss, gWc, gbc, gw3, gb3 = out[0:1], out[1:1 + 32 * F], out[1 + 32 * F:33 + 32 * F], out[33 + 32 * F:65 + 32 * F], out[65 + 32 * F:]
+            nscratch = lib.ltr_triple_scratch_bytes(B, n, F)
+            scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+            tab = rt.disc_prefix(dev)
+            _lib.check(lib.ltr_triple_approx_ndcg_fwdbwd(
+                X.data_ptr(), y_true.data_ptr(), Wc.data_ptr(), bc.data_ptr(), w3.data_ptr(), float(b3.detach().reshape(-1)[0]),
+                B, n, F, float(alpha), float(eps), float(pad), tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(),
+                loss.data_ptr(), gWc.data_ptr(), gbc.data_ptr(), gw3.data_ptr(), gb3.data_ptr(), scratch.data_ptr(), nscratch,
+                rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_approx_ndcg_fwdbwd")
+            gWc = gWc.view(32, F)
+            # unfold: z = x (W2 W1)^T + (W2 b1 + b2)
+            ctx.grads = (W2.detach().t() @ gWc, W2.detach().t() @ gbc, gWc @ W1.detach().t() + torch.outer(gbc, b1.detach()),
+                         gbc.clone(), gw3.view(1, 32).clone(), gb3.clone())
+        ctx.scores = scores
+        ctx.slate_ndcg = slate
+        ctx.mark_non_differentiable(scores)
+        return loss.reshape(()).clone(), scores
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loss, _grad_scores):
+        g = [t * grad_loss for t in ctx.grads]
+        return (None, None, g[0], g[1], g[2], g[3], g[4], g[5], None, None, None)
+
+
+def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1., return_scores=False):
+    """approxNDCGLoss(net(X), y_true) with its backward through `net` (a TripleLayerNet-shaped module: l1, l2, l3), fused.
+    X: [batch, 128, F <= 160] CUDA fp32, y_true: [batch, 128]; returns the 0-dim loss (and the [batch, 128] scores)."""
+    rt.require_cuda()
+    if X.dim() != 3 or X.shape[1] != SLATE or X.shape[2] > MAX_FEATURES or X.shape[2] % 4:
+        raise ValueError(f"the fused step takes [batch, {SLATE}, F] features with F <= {MAX_FEATURES}, F % 4 == 0; got {tuple(X.shape)}")
+    if X.device.type != "cuda" or X.dtype != torch.float32:
+        raise ValueError("the fused step takes CUDA fp32 features")
+    X = X.detach().contiguous()
+    y = y_true.detach().to(X.device, dtype=torch.float32).contiguous()
+    loss, scores = _FusedTripleApproxNDCG.apply(X, y, net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight,
+                                                net.l3.bias, eps, float(padded_value_indicator), alpha)
+    return (loss, scores) if return_scores else loss
+
+
+class TripleLayerNet(nn.Module):
+    def __init__(self, N_features):
+        super().__init__()
+        self.l1 = nn.Linear(N_features, 64)
+        self.l2 = nn.Linear(64, 32)
+        self.l3 = nn.Linear(32, 1)
+
+    def forward(self, x, mask=None, indices=None):
+        return self.l3(torch.sigmoid(self.l2(self.l1(x))))
+
+    def approx_ndcg_loss(self, x, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1.):
+        """The fused training step (extension): same value as approxNDCGLoss(self(x).squeeze(-1), y_true, ...)."""
+        return fused_triple_approx_ndcg(self, x, y_true, eps, padded_value_indicator, alpha)
