@@ -12,29 +12,39 @@
 //       dWc = dZ^T X,  dbc = sum dZ,  dw3 = A^T ds,  db3 = sum ds,      dZ = (ds w3^T) * a (1 - a)
 //       dW1 = W2^T dWc,  db1 = W2^T dbc,  dW2 = dWc W1^T + dbc b1^T,  db2 = dbc.
 //
-// One persistent CTA per SM (4 warps; thread = doc) walks its slates of 128 docs = one 128-row MMA tile:
-//   TMA      the slate's feature tile X[128, F] -> shared memory TWICE (5 boxes of 128 x 32 floats each): with the 128-byte
-//            swizzle of 16-byte atoms for the forward MMA (X is its K-major A operand) and with the 128-byte swizzle of
-//            32-byte atoms for the gradient MMA, which reads the same tile MN-major (docs are its K dimension) -- the only
-//            layout the tensor core transposes 32-bit operands from.  The next slate's copies are in flight while this
-//            one is worked on (the forward copy as soon as the forward MMA is done, the other after the gradient MMA);
-//            the second copy of a tile comes out of L2: X is read from HBM ONCE.
-//   MMA 1    tcgen05.mma kind::tf32, M = 128, N = 32, K = F: Z[128, 32] in TMEM  (A = X tile, B = Wc, both K-major)
-//   epilogue tcgen05.ld: thread d owns row d of Z: sigmoid, dot with w3 -> the doc's score, a[32] stays in registers
-//   loss     approxNDCG of the slate on the 128 scores (factorised pair sigmoid: one MUFU.RCP per ordered pair and
-//            pass; direct form when the score range is too wide), gradient d loss / d s in the same registers
-//   MMA 2    tcgen05.mma kind::tf32, M = 64, N = 160, K = 128 docs, ACCUMULATING over the CTA's slates in TMEM:
-//            rows 0..31 = dZ^T (written to shared memory in the swizzled K-major layout, rows 32..63 stay zero);
-//            B = the X tile read MN-major.  dbc = sum dZ and dw3 = sum a ds are sums of terms that cancel almost
-//            completely (sum ds = 0 for approxNDCG), so they do NOT go through tf32: every thread accumulates its own
-//            doc position's terms over the CTA's slates in fp32 registers, one shuffle reduction at the very end.
-//   end      the CTA's accumulators -> partials in global memory; a second small kernel adds the partials in CTA order.
+// One persistent, warp-specialised CTA per SM; a slate of 128 docs = one 128-row MMA tile.  The CTA's slates are dealt
+// round robin to G compute groups of 4 warps (thread = doc, warp = one TMEM lane quarter), so G slates are in different
+// phases at any time and their latencies hide each other; three single-thread roles feed them:
+//   loader      TMA: the features arrive in chunks of [128 docs][32 features] = 16 KB through two rings of slots --
+//               the F ring (forward copies, 128-byte swizzle of 16-byte atoms: X is the K-major A operand of the forward
+//               MMA; these are the HBM reads) and the D ring (the same chunk again, out of L2, with the 128-byte swizzle
+//               of 32-byte atoms: the gradient MMA reads it MN-major -- docs are its K dimension -- and that is the only
+//               layout the tensor core transposes 32-bit operands from).  X is read from HBM ONCE.
+//   F issuer    tcgen05.mma kind::tf32, M = 128, N = 32, K = F: Z[128, 32] of the slate into its group's TMEM columns as
+//               soon as the group has taken the previous Z out; every chunk's slot is released by tcgen05.commit.
+//   D issuer    tcgen05.mma kind::tf32, M = 64, N = 32 per feature chunk, K = 128 docs, ACCUMULATING over all of the
+//               CTA's slates in TMEM (in slate order: bitwise reproducible): A = dZ^T of the slate (rows 0..31, K-major,
+//               written by the group; rows 32..63 of the M = 64 tile alias whatever follows and land in accumulator rows
+//               nobody reads), B = the X chunk read MN-major.
+//   group       tcgen05.ld: thread d owns row d of Z: sigmoid, dot with w3 -> the doc's score (a[32] stays in registers);
+//               approxNDCG of the slate exactly as the K1 kernel computes it (approx_pair_tiles.cuh: factorised pair
+//               sigmoid, every unordered pair once per pass, block-circulant pair schedule over the group's 4 warps;
+//               direct form when the score range is too wide or the eps clamp matters); dZ of the doc -> shared memory
+//               for the D issuer.  dbc = sum dZ and dw3 = sum a ds are sums of terms that cancel almost completely
+//               (sum ds = 0 for approxNDCG), so they do NOT go through tf32: a butterfly of warp shuffles leaves lane j
+//               with the warp's sum for hidden unit j, accumulated in fp32 over the group's slates.
+//   end         the CTA's accumulators -> partials in global memory; a second small kernel adds the partials in CTA order.
 // Precision: tf32 operands (10-bit mantissa), fp32 accumulation: scores agree with the fp32 torch modules to ~1e-3
 // relative (the tolerance the tests state), the loss arithmetic itself is the fp32 / MUFU arithmetic of K1.
 #include <cuda.h>
 
+#include "approx_pair_tiles.cuh"
 #include "ltr_common.cuh"
 #include "ltr_host.h"
+
+#ifndef RF_GROUPS
+#define RF_GROUPS 4          // compute groups per CTA (A/B knob: 3 leaves 136 registers per thread, 4 leaves 104)
+#endif
 
 namespace ltr {
 
@@ -43,17 +53,18 @@ constexpr int RF_H = 32;               // hidden units after the folded layers
 constexpr int RF_CHUNK = 32;           // floats per 128-byte swizzle row
 constexpr int RF_MAX_F = 160;          // features: at most 5 chunks of 32
 constexpr int RF_KCHUNKS = 5;
-constexpr int RF_X_CHUNK_BYTES = RF_DOCS * 128;                 // 16 KB: [128 docs][32 floats]
-constexpr int RF_X_BYTES = RF_KCHUNKS * RF_X_CHUNK_BYTES;       // 80 KB per copy
+constexpr int RF_SLOT_BYTES = RF_DOCS * 128;                    // 16 KB: [128 docs][32 floats]
 constexpr int RF_W_CHUNK_BYTES = RF_H * 128;                    // 4 KB: [32 rows][32 floats]
 constexpr int RF_W_BYTES = RF_KCHUNKS * RF_W_CHUNK_BYTES;       // 20 KB
-constexpr int RF_DZ_ROWS = 64;                                  // rows of the second MMA's A operand
-constexpr int RF_DZ_CHUNK_BYTES = RF_DZ_ROWS * 128;             // 8 KB: [64 rows][32 docs]
-constexpr int RF_DZ_BYTES = 4 * RF_DZ_CHUNK_BYTES;              // 32 KB
-constexpr int RF_N2 = 160;                                      // columns of the gradient accumulator: the 5 feature chunks (MN-major B: whole 32-float atoms)
-constexpr int RF_TMEM_COLS = 256;                               // 32 (Z) + 144 (gradients) -> next power of two
-constexpr int RF_THREADS = 128;
-constexpr size_t RF_SMEM = 1024 + 2 * (size_t)RF_X_BYTES + RF_W_BYTES + RF_DZ_BYTES + 4096;
+constexpr int RF_DZ_CHUNK_BYTES = RF_H * 128;                   // 4 KB: [32 hidden units][32 docs]
+constexpr int RF_DZ_GROUP_BYTES = 4 * RF_DZ_CHUNK_BYTES;        // 16 KB per compute group
+constexpr int RF_N2 = RF_KCHUNKS * RF_CHUNK;                    // columns of the gradient accumulator
+constexpr int RF_G = RF_GROUPS;
+constexpr int RF_NSF = 5;                                       // F ring: one slate of forward chunks in flight (HBM latency)
+constexpr int RF_NSD = (RF_G >= 4) ? 2 : 3;                     // D ring: L2 hits
+constexpr int RF_THREADS = RF_G * 128 + 96;                     // compute groups + loader, F issuer, D issuer warps
+constexpr int RF_TMEM_COLS = (RF_G * RF_H + RF_N2 <= 256) ? 256 : 512;
+constexpr int RF_PART = RF_H * RF_N2;                           // floats of one CTA's gradient partial
 
 struct RankerFusedParams {
     const float* y_true;     // [B, 128]
@@ -66,10 +77,9 @@ struct RankerFusedParams {
     float* scores;           // [B, 128] out
     float* slate_ndcg;       // [B] out
     float* loss;             // [1] out
-    float* part;             // [grid][64 * 144] per-CTA gradient accumulators
+    float* part;             // [grid][32 * 160] per-CTA gradient accumulators
     float* part_misc;        // [grid][2]: sum of slate values, sum of ds
     float* part_bias;        // [grid][64]: dbc (32), dw3 (32) in fp32
-    unsigned* counter;       // finished-CTA ticket (workspace, left at 0)
     int grid;
 };
 
@@ -152,338 +162,633 @@ __device__ __forceinline__ unsigned sw128_offset(int row, int col) {
     return (unsigned)row * 128u + ((((unsigned)col >> 2) ^ ((unsigned)row & 7u)) << 4) + (((unsigned)col & 3u) << 2);
 }
 
-struct RfShared {
-    uint64_t fullk;          // TMA landed the forward copy of the slate's X tile
-    uint64_t fullm;          // TMA landed the gradient-MMA copy
-    uint64_t wfull;          // TMA landed Wc
-    uint64_t mma1;           // the forward MMAs of the slate are complete (the forward copy is free)
-    uint64_t mma2;           // the gradient MMAs of the slate are complete (the other copy and the dZ tile are free)
-    unsigned tmem_base;
-    int is_last;
-    float s[RF_DOCS];        // compacted per-doc values of the loss: u, v, c
-    float u[RF_DOCS];
-    float v[RF_DOCS];
-    float c[RF_DOCS];
-    float red[8];
-    float w3[RF_H], bc[RF_H];
-    float fold[4][2 * RF_H];
-    int wcount[4];
-    int lvl[8];
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+// per compute group: the slate state of the loss (the layout of the K1 kernel's SymShared)
+struct RfGroup {
+    float u[RF_DOCS];             // 2^(t - c)   (direct form: raw score)
+    float v[RF_DOCS];             // 2^-(t - c)
+    float c[RF_DOCS];             // d loss / d pos_i
+    float part[4][RF_DOCS];       // per-warp partial sums of every doc (ranks, then gradients)
+    int4 wstat[4];                // per warp: {valid count | bad-label flag << 16, min key, max key, packed label counts}
+    float red[4];
+    float pad_[12];
 };
 
-__device__ __forceinline__ float rf_block_sum(float x, float* red) {
-    x = warp_sum(x);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
-    __syncthreads();
-    return (red[0] + red[1]) + (red[2] + red[3]);
-}
-__device__ __forceinline__ float rf_block_max(float x, float* red) {
-    x = warp_max(x);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
-    __syncthreads();
-    return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+struct RfCtl {
+    uint64_t full_f[RF_NSF], empty_f[RF_NSF];     // F ring: TMA landed / the chunk's MMAs are complete
+    uint64_t full_d[RF_NSD], empty_d[RF_NSD];     // D ring
+    uint64_t wfull;                               // TMA landed Wc
+    uint64_t zfull[RF_G];                         // the forward MMAs of the group's slate are complete
+    uint64_t zfree[RF_G];                         // the group has taken Z out of tensor memory (128 arrivals)
+    uint64_t dzfull[RF_G];                        // the group has written dZ of its slate (128 arrivals)
+    uint64_t dzfree[RF_G];                        // the gradient MMAs of the group's slate are complete
+    uint64_t alldone;                             // every MMA of the CTA is complete
+    unsigned tmem_base;
+    float w3[RF_H], bc[RF_H];
+    float disc[RF_DOCS + 1];                      // discount prefix sums, rounded once to fp32 (as K1's constant table)
+};
+
+// sum over the warp's lanes of v[j], left in lane j: 31 exchanges (16 + 8 + 4 + 2 + 1); v is destroyed
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool hi = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = hi ? v[i] : v[i + s];
+            const float keep = hi ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(LTR_FULL_MASK, send, s);
+        }
+    }
+    return v[0];
 }
 
-__global__ void __launch_bounds__(RF_THREADS, 1)
+// soft rank -> slate value and d loss / d pos (sh.c); one group barrier.  `sum` = sum_{j != i} sigma_ij of this thread's doc.
+__device__ __forceinline__ float rf_middle(RfGroup& sh, int bar, int lane, int warp, bool valid, int dst, float gain, float coef,
+                                           float sum) {
+    float ndcg_part = 0.f;
+    if (valid) {
+        const float pos1 = 2.0f + sum;                       // 1 + pos_i
+        const float l2 = lg2_approx(pos1);
+        const float il2 = rcp_approx(l2);
+        ndcg_part = gain * il2;
+        sh.c[dst] = coef * gain * il2 * il2 * rcp_approx(pos1);
+    }
+    ndcg_part = warp_sum(ndcg_part);
+    if (lane == 0) sh.red[warp] = ndcg_part;
+    named_bar_sync(bar, 128);
+    return (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
+}
+
+// One slate in the factorised form, R docs per lane (the schedule of sym_slate in approx_ndcg_sym.cuh, on a group of 4 warps
+// with a named barrier).  Returns sum_j w_ij (c_j - c_i) of this thread's doc; slate_val = the slate's approxNDCG.
+template <int R>
+__device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int rot, int m, bool valid, int dst, float gain,
+                                              float coef, float& slate_val) {
+    const int lane = gt & 31, warp = gt >> 5;
+    const int T = (m + R - 1) / R;            // active lanes = row blocks
+    const int S = T >> 1;                     // circulant steps D = 1 .. T/2 (D = 0 is the in-block triangle)
+    const int role = (warp + rot) & 3;
+    const int d_lo = 1 + ((role * S) >> 2);
+    const int d_hi = 1 + (((role + 1) * S) >> 2);
+    const int steps = d_hi - d_lo;
+    // for even T the antipodal step D = T/2 meets every pair twice and is weighted 1/2: it is the last step of role 3
+    const bool anti = ((T & 1) == 0) && (role == 3) && (steps > 0);
+    const int full = steps - (anti ? 1 : 0);
+    const bool active = lane < T;
+    const int src = active ? ((lane + 1 == T) ? 0 : lane + 1) : lane;
+    int cb = lane + d_lo;
+    if (cb >= T) cb -= T;
+    if (!active) cb = 0;
+    int ret = lane - (d_hi - 1);              // the lane that ends up holding this lane's column accumulators
+    if (ret < 0) ret += T;
+    if (steps == 0 || !active) ret = lane;    // nothing accumulated: the column sums are zero
+
+    float urow[R], vcol[R], acc_r[R], acc_r_hi[R], acc_c[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        urow[r] = sh.u[lane * R + r];
+        vcol[r] = sh.v[cb * R + r];
+        acc_r[r] = 0.f;
+        acc_r_hi[r] = 0.f;
+        acc_c[r] = 0.f;
+    }
+    // ---------------- rank pass: one MUFU.RCP per unordered pair -----------------------------
+    if (role == 0) {                          // pairs inside the lane's own block
+        float vrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int c = r + 1; c < R; ++c) {
+                const float pp = urow[r] * vrow[c];
+                const float rr = rcp_approx(pp + 1.0f);
+                acc_r[r] += rr;
+                acc_r[c] = fmaf(pp, rr, acc_r[c]);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < full; ++i) {
+        if (i) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
+        }
+        rank_tile<R>(urow, vcol, 1.0f, acc_r, acc_r_hi, acc_c);
+    }
+    if (anti) {
+        if (full) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
+        }
+        rank_tile<R>(urow, vcol, 0.5f, acc_r, acc_r_hi, acc_c);
+    }
+    // the column accumulators go home; a doc's partial is (sum sigma_ij as a row) - (sum sigma_ij as a column)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) - cols;
+    }
+    named_bar_sync(bar, 128);
+
+    // ---------------- per doc: soft rank, slate value, d loss / d pos --------------------------
+    float sum = 0.f;
+    if (valid) {
+        const float parts = (sh.part[0][dst] + sh.part[1][dst]) + (sh.part[2][dst] + sh.part[3][dst]);
+        // column side: sum sigma_ji = (#rows met, antipodal ones at 1/2) - sum sigma_ij = R (T-1)/2 - cols.
+        // padded tail of the last block (u = v = 0): as a column it reads sigma_ij = 1 on the row side.
+        const int npadc = T * R - m;
+        const int e = T - 1 - dst / R;                   // circulant distance to the last block
+        const float f = (2 * e == T) ? 0.5f : ((2 * e < T) ? 1.0f : 0.0f);
+        sum = (parts - f * (float)npadc) + 0.5f * (float)(R * (T - 1));
+    }
+    slate_val = rf_middle(sh, bar, lane, warp, valid, dst, gain, coef, sum);
+
+    // ---------------- gradient pass: sigma recomputed, one MUFU.RCP per unordered pair ---------
+    float crow[R], ccol[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        crow[r] = sh.c[lane * R + r];
+        ccol[r] = sh.c[cb * R + r];
+        vcol[r] = sh.v[cb * R + r];
+        acc_r[r] = 0.f;
+        acc_r_hi[r] = 0.f;
+        acc_c[r] = 0.f;
+    }
+    if (role == 0) {
+        float vrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int c = r + 1; c < R; ++c) {
+                const float pp = urow[r] * vrow[c];
+                const float rr = rcp_approx(pp + 1.0f);
+                const float e = (rr * (pp * rr)) * (crow[c] - crow[r]);
+                acc_r[r] += e;
+                acc_r[c] -= e;
+            }
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < full; ++i) {
+        if (i) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                ccol[r] = __shfl_sync(LTR_FULL_MASK, ccol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
+        }
+        grad_tile<R>(urow, vcol, crow, ccol, acc_r, acc_r_hi, acc_c);
+    }
+    if (anti) {                                 // weight 1/2 goes onto the c differences
+        if (full) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
+                ccol[r] = __shfl_sync(LTR_FULL_MASK, ccol[r], src);
+                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
+            }
+        }
+        float ch[R], cch[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ch[r] = 0.5f * crow[r], cch[r] = 0.5f * ccol[r];
+        grad_tile<R>(urow, vcol, ch, cch, acc_r, acc_r_hi, acc_c);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) + cols;
+    }
+    named_bar_sync(bar, 128);
+    float sum2 = 0.f;
+    if (valid) sum2 = (sh.part[0][dst] + sh.part[1][dst]) + (sh.part[2][dst] + sh.part[3][dst]);
+    return sum2;
+}
+
+// Slates whose scaled score range does not fit the factorised form, or whose eps clamp is above fp32 resolution (both
+// rare): one doc per thread, p = ex2(min(alpha log2e (s_i - s_j), 126)) per ordered pair, recomputed in the gradient
+// pass.  sh.u holds the raw scores of the m compacted docs.  Out of line: keeps the common path's code small.
+__device__ __noinline__ float rf_direct_rank_sum(const float* raw, int m, float scale, float si, float eps, int clamp) {
+    float sum = 0.f;
+    for (int j = 0; j < m; ++j) {
+        const float rr = rcp_approx(ex2_capped((si - raw[j]) * scale) + 1.0f);
+        sum += clamp ? fmaxf(rr, eps) : rr;
+    }
+    return sum - (clamp ? fmaxf(0.5f, eps) : 0.5f);             // the j == i term is exactly 1/2 (approxNDCG.py:34 drops it)
+}
+__device__ __noinline__ float rf_direct_grad_sum(const float* raw, const float* c, int m, float scale, float si, float ci,
+                                                 float eps, int clamp) {
+    const float pinf = __int_as_float(0x7f800000);
+    float acc = 0.f;
+    for (int j = 0; j < m; ++j) {
+        const float pp = ex2_capped((si - raw[j]) * scale);
+        const float rr = rcp_approx(pp + 1.0f);
+        float w = rr * (pp * rr);
+        w = (pp == pinf) ? 0.f : w;
+        if (clamp && !(rr > eps)) w = 0.f;                       // the clamp is active: no gradient through this pair
+        acc = fmaf(w, c[j] - ci, acc);
+    }
+    return acc;
+}
+
+template <int G>
+__global__ void __launch_bounds__(G * 128 + 96, 1)
 ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xm,
                     const __grid_constant__ CUtensorMap map_w, const RankerFusedParams p) {
     extern __shared__ unsigned char rf_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rf_smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* Xk = base;                     // forward copy: 128-byte swizzle, 16-byte atoms
-    unsigned char* Xm = base + RF_X_BYTES;        // gradient copy: 128-byte swizzle, 32-byte atoms
-    unsigned char* wsm = base + 2 * RF_X_BYTES;
+    unsigned char* fring = base;                                  // forward copies: 128-byte swizzle, 16-byte atoms
+    unsigned char* dring = fring + RF_NSF * RF_SLOT_BYTES;        // gradient copies: 128-byte swizzle, 32-byte atoms
+    unsigned char* wsm = dring + RF_NSD * RF_SLOT_BYTES;
     unsigned char* dz = wsm + RF_W_BYTES;
-    RfShared& sh = *reinterpret_cast<RfShared*>(dz + RF_DZ_BYTES);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nslates = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // slates blockIdx.x, + grid, ...
+    RfGroup* groups = reinterpret_cast<RfGroup*>(dz + G * RF_DZ_GROUP_BYTES);
+    RfCtl& ctl = *reinterpret_cast<RfCtl*>(groups + G);
+    const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
+    const int nsl = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;          // slates blockIdx.x, + grid, ...
+    const int nch = (p.F + RF_CHUNK - 1) / RF_CHUNK;              // feature chunks
+    const int ksteps = (p.F + 7) / 8;                             // forward k steps of 8 features
 
     if (tid == 0) {
-        mbar_init(&sh.fullk, 1);
-        mbar_init(&sh.fullm, 1);
-        mbar_init(&sh.wfull, 1);
-        mbar_init(&sh.mma1, 1);
-        mbar_init(&sh.mma2, 1);
+        for (int i = 0; i < RF_NSF; ++i) mbar_init(&ctl.full_f[i], 1), mbar_init(&ctl.empty_f[i], 1);
+        for (int i = 0; i < RF_NSD; ++i) mbar_init(&ctl.full_d[i], 1), mbar_init(&ctl.empty_d[i], 1);
+        mbar_init(&ctl.wfull, 1);
+        for (int g = 0; g < G; ++g) {
+            mbar_init(&ctl.zfull[g], 1);
+            mbar_init(&ctl.zfree[g], 128);
+            mbar_init(&ctl.dzfull[g], 128);
+            mbar_init(&ctl.dzfree[g], 1);
+        }
+        mbar_init(&ctl.alldone, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+    if (warp_id == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)),
                      "n"(RF_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (tid < RF_H) ctl.w3[tid] = __ldg(p.w3 + tid), ctl.bc[tid] = __ldg(p.bc + tid);
+    for (int i = tid; i <= RF_DOCS; i += blockDim.x) ctl.disc[i] = (float)p.disc_prefix[i];
+    asm volatile("griddepcontrol.launch_dependents;");           // the reduce kernel's blocks may become resident (they wait)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tmem = sh.tmem_base;
-    const unsigned tmem_z = tmem, tmem_g = tmem + RF_H;          // columns [0, 32): Z; [32, 176): gradients
+    const unsigned tmem = ctl.tmem_base;
+    const unsigned tmem_g = tmem + G * RF_H;                      // columns [0, 32 G): Z of the groups; then the gradients
 
-    // first tiles in flight: Wc (once) and the first slate
-    if (tid == 0 && nslates > 0) {
-        mbar_expect_tx(&sh.wfull, RF_W_BYTES);
-        for (int ck = 0; ck < RF_KCHUNKS; ++ck) tma_load_2d(wsm + ck * RF_W_CHUNK_BYTES, &map_w, ck * RF_CHUNK, 0, &sh.wfull);
-        mbar_expect_tx(&sh.fullk, RF_X_BYTES);
-        for (int ck = 0; ck < RF_KCHUNKS; ++ck)
-            tma_load_2d(Xk + ck * RF_X_CHUNK_BYTES, &map_x, ck * RF_CHUNK, (int)blockIdx.x * RF_DOCS, &sh.fullk);
-        mbar_expect_tx(&sh.fullm, RF_X_BYTES);
-        for (int ck = 0; ck < RF_KCHUNKS; ++ck)
-            tma_load_2d(Xm + ck * RF_X_CHUNK_BYTES, &map_xm, ck * RF_CHUNK, (int)blockIdx.x * RF_DOCS, &sh.fullm);
-    }
-    if (tid < RF_H) sh.w3[tid] = __ldg(p.w3 + tid), sh.bc[tid] = __ldg(p.bc + tid);
-    // rows 32..63 of the gradient MMA's A tile are never written again: zero once
-    for (int i = tid; i < RF_DZ_BYTES / 16; i += RF_THREADS) reinterpret_cast<float4*>(dz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float gdz[RF_H], gaw[RF_H];                                  // fp32: this doc position's share of dbc and dw3
+    if (warp_id < 4 * G) {
+        // ================= compute group: thread = doc =====================================================================
+        const int g = warp_id >> 2, w = warp_id & 3, gt = tid & 127;
+        RfGroup& sh = groups[g];
+        const int bar = 1 + g;
+        unsigned char* dzw = dz + g * RF_DZ_GROUP_BYTES + w * RF_DZ_CHUNK_BYTES;      // this warp's chunk of 32 docs
+        unsigned dzoff[8];                                        // swizzled byte offset of column `lane` in a row of class j & 7
 #pragma unroll
-    for (int j = 0; j < RF_H; ++j) gdz[j] = 0.f, gaw[j] = 0.f;
-    __syncthreads();
-    const float scale = p.alpha * kLog2e;
-    const bool clamp_pairs = (float)RF_DOCS * p.eps > 2e-7f;     // (below that the eps clamp of approxNDCG.py:49 is under fp32 resolution)
-    const float invB = 1.0f / (float)p.B;
-    const int ksteps1 = (p.F + 7) / 8;                           // k steps of 8 features
-    constexpr unsigned IDESC1 = umma_idesc_tf32(128, RF_H, 0, 0);
-    constexpr unsigned IDESC2 = umma_idesc_tf32(64, RF_N2, 0, 1);
-    float val_sum = 0.f, ds_sum = 0.f;                           // thread 0: sum of slate values; all: own ds (reduced at the end)
-
-    for (int it = 0; it < nslates; ++it) {
-        const int slate = (int)blockIdx.x + it * (int)gridDim.x;
-        const unsigned ph = (unsigned)it & 1u;
-        const float y = __ldg(p.y_true + (size_t)slate * RF_DOCS + tid);
-        // ---- forward MMA ----------------------------------------------------------------------------------------------
-        if (it == 0) mbar_wait_bounded(&sh.wfull, 0);
-        mbar_wait_bounded(&sh.fullk, ph);
-        if (tid == 0) {
+        for (int jj = 0; jj < 8; ++jj) dzoff[jj] = ((((unsigned)lane >> 2) ^ (unsigned)jj) << 4) + (((unsigned)lane & 3u) << 2);
+        const float scale = p.alpha * kLog2e;
+        const int clamp_pairs = ((float)RF_DOCS * p.eps > 2e-7f) ? 1 : 0;   // (below that the eps clamp of approxNDCG.py:49 is under fp32 resolution)
+        const float coef = (1.0f / (float)p.B) * (1.0f / kLn2);
+        float acc_bc = 0.f, acc_w3 = 0.f;                         // lane j: this warp's share of dbc[j], dw3[j]
+        float ds_sum = 0.f, val_sum = 0.f;
+        float ynext = p.pad;
+        if (g < nsl) ynext = ld_stream(p.y_true + (size_t)((int)blockIdx.x + g * (int)gridDim.x) * RF_DOCS + gt);
+        int it = 0;
+        for (int k = g; k < nsl; k += G, ++it) {
+            const int slate = (int)blockIdx.x + k * (int)gridDim.x;
+            const float yv = ynext;
+            if (k + G < nsl) ynext = ld_stream(p.y_true + (size_t)(slate + G * (int)gridDim.x) * RF_DOCS + gt);
+            // ---- epilogue of the forward MMA: row `gt` of Z -> a[32], score ---------------------------------------------
+            mbar_wait_bounded(&ctl.zfull[g], (unsigned)it & 1u);
             tc_fence_after();
-            const unsigned xa = smem_u32(Xk), wa = smem_u32(wsm);
-            for (int ks = 0; ks < ksteps1; ++ks) {
-                const unsigned off = (unsigned)(ks & 3) * 32u;
-                tc_mma_tf32(tmem_z, umma_desc_sw128(xa + (ks >> 2) * RF_X_CHUNK_BYTES + off, 16, 1024),
-                            umma_desc_sw128(wa + (ks >> 2) * RF_W_CHUNK_BYTES + off, 16, 1024), IDESC1, ks > 0);
-            }
-            tc_commit(&sh.mma1);
-            // the next slate's gradient copy: its buffer was last read by the gradient MMAs of the previous iteration
-            if (it >= 1) {
-                mbar_wait_bounded(&sh.mma2, ph ^ 1u);
-                mbar_expect_tx(&sh.fullm, RF_X_BYTES);
-                for (int ck = 0; ck < RF_KCHUNKS; ++ck)
-                    tma_load_2d(Xm + ck * RF_X_CHUNK_BYTES, &map_xm, ck * RF_CHUNK, slate * RF_DOCS, &sh.fullm);
-            }
-        }
-        // ---- epilogue 1: row `tid` of Z -> a[32], score --------------------------------------------------------------
-        mbar_wait_bounded(&sh.mma1, ph);
-        tc_fence_after();
-        if (tid == 0 && it + 1 < nslates) {                   // the forward copy is free: the next slate's goes in flight now
-            mbar_expect_tx(&sh.fullk, RF_X_BYTES);
-            for (int ck = 0; ck < RF_KCHUNKS; ++ck)
-                tma_load_2d(Xk + ck * RF_X_CHUNK_BYTES, &map_x, ck * RF_CHUNK, (slate + (int)gridDim.x) * RF_DOCS, &sh.fullk);
-        }
-        float a[RF_H];
-        tmem_ld32(tmem_z + ((unsigned)(warp * 32) << 16), a);
-        float score = p.b3;
+            float a[RF_H];
+            tmem_ld32(tmem + (unsigned)(g * RF_H) + ((unsigned)(w * 32) << 16), a);
+            tc_fence_before();
+            mbar_arrive(&ctl.zfree[g]);                           // Z is in registers: the next forward MMA of the group may go
+            float sv = p.b3;
 #pragma unroll
-        for (int j = 0; j < RF_H; ++j) {
-            const float z = a[j] + sh.bc[j];
-            a[j] = 1.0f / (1.0f + __expf(-z));
-            score = fmaf(a[j], sh.w3[j], score);
-        }
-        p.scores[(size_t)slate * RF_DOCS + tid] = score;
-        // ---- approxNDCG of the slate (losses/approxNDCG.py:7-53) -------------------------------------------
-        const bool valid = (y != p.pad);
-        const unsigned vb = __ballot_sync(LTR_FULL_MASK, valid);
-        const int lv = (int)fminf(fmaxf(y, -1.f), 5.f);
-        const bool odd = valid && !((float)lv == y && lv >= 0 && lv <= 4);
-        if (lane == 0) sh.wcount[warp] = __popc(vb);
-        if (tid < 8) sh.lvl[tid] = 0;
-        __syncthreads();
-        if (odd) atomicOr(&sh.lvl[0], 1);
+            for (int j = 0; j < RF_H; ++j) {
+                const float z = a[j] + ctl.bc[j];
+                a[j] = rcp_approx(1.0f + ex2_approx(-kLog2e * z));
+                sv = fmaf(a[j], ctl.w3[j], sv);
+            }
+            p.scores[(size_t)slate * RF_DOCS + gt] = sv;
+            // ---- approxNDCG of the slate (losses/approxNDCG.py:7-53; the K1 kernel's steps) --------------------------------
+            const bool valid = (yv != p.pad);
+            const float yc = fmaxf(yv, 0.f);                      // approxNDCG.py:37-38 clamp
+            const int lvl = (int)fminf(yc, 100.f);
+            const bool small_int = (yc == (float)lvl) && (lvl <= 4);
+            const unsigned bal = __ballot_sync(LTR_FULL_MASK, valid);
+            const unsigned bad = __ballot_sync(LTR_FULL_MASK, valid && !small_int);
+            const int key = float_order_key(sv);
+            const int kmin = __reduce_min_sync(LTR_FULL_MASK, valid ? key : 0x7fffffff);
+            const int kmax = __reduce_max_sync(LTR_FULL_MASK, valid ? key : (int)0x80000000);
+            const unsigned field = (valid && small_int && lvl >= 1) ? (1u << (8 * (lvl - 1))) : 0u;
+            const unsigned cnts = __reduce_add_sync(LTR_FULL_MASK, field);
+            if (lane == 0) sh.wstat[w] = make_int4(__popc(bal) | (bad ? 0x10000 : 0), kmin, kmax, (int)cnts);
+            named_bar_sync(bar, 128);
+            int m = 0, off = 0, any_bad = 0;
+            int gmin = 0x7fffffff, gmax = (int)0x80000000;
+            unsigned packed = 0;
 #pragma unroll
-        for (int L = 1; L <= 4; ++L) {
-            const unsigned bl = __ballot_sync(LTR_FULL_MASK, valid && lv == L);
-            if (lane == 0 && bl) atomicAdd(&sh.lvl[L], __popc(bl));
-        }
-        __syncthreads();
-        int before = __popc(vb & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) before += sh.wcount[w];
-        const int m = sh.wcount[0] + sh.wcount[1] + sh.wcount[2] + sh.wcount[3];
-        // ideal DCG over all positions: integer labels 0..4 -> level L fills the ranks [e_{L+1}, e_L)
-        float maxdcg;
-        if (!sh.lvl[0]) {
-            const int e4 = sh.lvl[4], e3 = e4 + sh.lvl[3], e2 = e3 + sh.lvl[2], e1 = e2 + sh.lvl[1];
-            const double P4 = p.disc_prefix[e4], P3 = p.disc_prefix[e3], P2 = p.disc_prefix[e2], P1 = p.disc_prefix[e1];
-            maxdcg = (float)(15.0 * P4 + 7.0 * (P3 - P4) + 3.0 * (P2 - P3) + (P1 - P2));
-        } else {
-            // other labels: ideal order by a bitonic sort of the (clamped) label values
-            sh.s[tid] = valid ? fmaxf(y, 0.f) : 0.f;
-            __syncthreads();
-            block_bitonic_desc(sh.s, RF_DOCS);
-            const float term = (exp2f(sh.s[tid]) - 1.0f) / log2f(2.0f + (float)tid);
-            maxdcg = rf_block_sum(term, sh.red);
-            __syncthreads();
-        }
-        maxdcg = fmaxf(maxdcg, p.eps);
-        const float G = valid ? (exp2f(fmaxf(y, 0.f)) - 1.0f) / maxdcg : 0.f;
-        const float t = score * scale;
-        const float ninf = __int_as_float(0xff800000), pinf = __int_as_float(0x7f800000);
-        const float tmax = rf_block_max(valid ? t : ninf, sh.red);
-        const float tmin = -rf_block_max(valid ? -t : ninf, sh.red);
-        const bool fact = (tmax - tmin) < 120.0f;               // u v stays inside fp32; NaN / inf scores take the direct form
-        const float mid = 0.5f * tmax + 0.5f * tmin;
-        float myu = 0.f;
-        if (valid) {
-            myu = fact ? ex2_approx(t - mid) : t;
-            sh.u[before] = myu;
-            sh.v[before] = fact ? ex2_approx(mid - t) : t;
-        }
-        __syncthreads();
-        float sum = 0.f;                                         // sum over ALL valid j (self included) of sigma_ij
-        if (valid) {
-            if (fact) {
-                if (!clamp_pairs) {
-#pragma unroll 4
-                    for (int j = 0; j < m; ++j) sum += rcp_approx(fmaf(myu, sh.v[j], 1.0f));
+            for (int q = 0; q < 4; ++q) {
+                const int4 st = sh.wstat[q];
+                const int cnt = st.x & 0xffff;
+                off += (q < w) ? cnt : 0;
+                m += cnt;
+                any_bad |= st.x >> 16;
+                gmin = min(gmin, st.y);
+                gmax = max(gmax, st.z);
+                packed += (unsigned)st.w;
+            }
+            const int dst = off + __popc(bal & ((1u << lane) - 1u));
+            float ds = 0.f, slate_val = 0.f;
+            if (m > 0) {
+                // ideal DCG over ALL positions (approxNDCG.py:41-43)
+                float maxdcg, gain;
+                if (!any_bad) {
+                    // labels 0..4: maxDCG = sum_L (2^L - 1)(P[e_L] - P[e_{L+1}]) = 8 P[e4] + 4 P[e3] + 2 P[e2] + P[e1]
+                    const int e4 = packed >> 24;
+                    const int e3 = e4 + ((packed >> 16) & 255);
+                    const int e2 = e3 + ((packed >> 8) & 255);
+                    const int e1 = e2 + (packed & 255);
+                    maxdcg = fmaf(8.0f, ctl.disc[e4], fmaf(4.0f, ctl.disc[e3], fmaf(2.0f, ctl.disc[e2], ctl.disc[e1])));
+                    gain = (float)((1 << lvl) - 1);
                 } else {
-                    for (int j = 0; j < m; ++j) sum += fmaxf(rcp_approx(fmaf(myu, sh.v[j], 1.0f)), p.eps);
-                }
-            } else {
-                for (int j = 0; j < m; ++j) {
-                    const float r = rcp_approx(1.0f + ex2_capped(t - sh.v[j]));
-                    sum += clamp_pairs ? fmaxf(r, p.eps) : r;
-                }
-            }
-        }
-        // pos_i = 1 + sum_{j != i}: the self term is sigma(0) = 1/2
-        const float pos = 1.0f + sum - (clamp_pairs ? fmaxf(0.5f, p.eps) : 0.5f);
-        const float lg = log2f(1.0f + pos);
-        const float val = valid ? G / lg : 0.f;
-        const float c = valid ? invB * G / (kLn2 * (1.0f + pos) * lg * lg) : 0.f;
-        const float slate_val = rf_block_sum(val, sh.red);
-        if (valid) sh.c[before] = c;
-        __syncthreads();
-        if (tid == 0) {
-            p.slate_ndcg[slate] = slate_val;
-            val_sum += slate_val;
-        }
-        float gacc = 0.f;                                        // sum_j w_ij (c_j - c_i)
-        if (valid) {
-            if (fact) {
-                if (!clamp_pairs) {
-#pragma unroll 4
-                    for (int j = 0; j < m; ++j) {
-                        const float pq = myu * sh.v[j];
-                        const float r = rcp_approx(1.0f + pq);
-                        gacc = fmaf(r * r * pq, sh.c[j] - c, gacc);
+                    // other labels: a doc's ideal rank = how many clamped labels are larger (equal ones: by position)
+                    sh.part[0][gt] = valid ? yc : -1.0f;
+                    named_bar_sync(bar, 128);
+                    const float mine = sh.part[0][gt];
+                    int rank = 0;
+                    for (int j = 0; j < RF_DOCS; ++j) {
+                        const float o = sh.part[0][j];
+                        rank += (o > mine || (o == mine && j < gt)) ? 1 : 0;
                     }
-                } else {
-                    for (int j = 0; j < m; ++j) {
-                        const float pq = myu * sh.v[j];
-                        const float r = rcp_approx(1.0f + pq);
-                        gacc = fmaf((r > p.eps) ? r * r * pq : 0.f, sh.c[j] - c, gacc);
+                    float term = (mine >= 0.f) ? gain_exp2(mine) / log2f(2.0f + (float)rank) : 0.f;
+                    term = warp_sum(term);
+                    if (lane == 0) sh.red[w] = term;
+                    named_bar_sync(bar, 128);
+                    maxdcg = (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
+                    gain = gain_exp2(yc);
+                    named_bar_sync(bar, 128);
+                }
+                maxdcg = fmaxf(maxdcg, p.eps);
+                gain = valid ? __fdividef(gain, maxdcg) : 0.f;    // G_i (approxNDCG.py:44)
+                // compacted per-doc quantities
+                const float smin = float_from_key(gmin), smax = float_from_key(gmax);
+                const float range = (smax - smin) * scale;
+                const bool fact = (fabsf(range) < 126.0f) && !clamp_pairs;   // false for inf / NaN ranges too
+                const float smid = 0.5f * smin + 0.5f * smax;
+                if (valid) {
+                    if (fact) {
+                        const float tc = (sv - smid) * scale;
+                        sh.u[dst] = ex2_approx(tc);
+                        sh.v[dst] = ex2_approx(-tc);
+                    } else {
+                        sh.u[dst] = sv;
                     }
                 }
-            } else {
-                for (int j = 0; j < m; ++j) {
-                    const float pq = ex2_capped(t - sh.v[j]);
-                    const float r = rcp_approx(1.0f + pq);
-                    float w = r * (pq * r);
-                    w = (pq == pinf) ? 0.f : w;
-                    if (clamp_pairs && !(r > p.eps)) w = 0.f;
-                    gacc = fmaf(w, sh.c[j] - c, gacc);
+                if (gt >= m) {                                    // zero tail: p = 0, w = 0 for padding
+                    sh.u[gt] = 0.f;
+                    sh.v[gt] = 0.f;
+                    sh.c[gt] = 0.f;
                 }
+                named_bar_sync(bar, 128);
+                float gsum;
+                if (!fact) {
+                    const float si = valid ? sh.u[dst] : 0.f;
+                    float sum = 0.f;
+                    if (valid) sum = rf_direct_rank_sum(sh.u, m, scale, si, p.eps, clamp_pairs);
+                    slate_val = rf_middle(sh, bar, lane, w, valid, dst, gain, coef, sum);
+                    gsum = 0.f;
+                    if (valid) gsum = rf_direct_grad_sum(sh.u, sh.c, m, scale, si, sh.c[dst], p.eps, clamp_pairs);
+                } else if (m > 96) {
+                    gsum = rf_sym_slate<4>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
+                } else if (m > 64) {
+                    gsum = rf_sym_slate<3>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
+                } else {
+                    gsum = rf_sym_slate<2>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
+                }
+                ds = valid ? p.alpha * gsum : 0.f;                // d loss / d score of this doc
             }
-        }
-        const float ds = valid ? p.alpha * gacc : 0.f;           // d loss / d score of this doc
-        ds_sum += ds;
-#ifdef RF_DEBUG_DS
-        p.scores[(size_t)slate * RF_DOCS + tid] = ds;
-#endif
-        // ---- gradient MMA: rows 0..31 = dZ^T, rows 32..63 = (a ds)^T, K = the 128 docs of the slate ------------------------
-        if (it >= 1) mbar_wait_bounded(&sh.mma2, ph ^ 1u);       // the dZ tile is free again
-        mbar_wait_bounded(&sh.fullm, ph);                        // the gradient copy of this slate has landed
-        {
-            unsigned char* dzc = dz + (tid >> 5) * RF_DZ_CHUNK_BYTES;    // chunk of 32 docs
-            const int col = tid & 31;
+            ds_sum += ds;
+            if (gt == 0) {
+                p.slate_ndcg[slate] = slate_val;
+                val_sum += slate_val;
+            }
+            // ---- dZ of this doc -> the group's A tile of the gradient MMA (K-major: row = hidden unit, column = doc) -----------
+            if (it >= 1) mbar_wait_bounded(&ctl.dzfree[g], (unsigned)(it - 1) & 1u);  // the previous slate's gradient MMAs are done
+            float dzv[RF_H];
 #pragma unroll
             for (int j = 0; j < RF_H; ++j) {
                 const float aj = a[j];
-                const float dzj = ds * sh.w3[j] * aj * (1.0f - aj);
-                *reinterpret_cast<float*>(dzc + sw128_offset(j, col)) = dzj;
-                gdz[j] += dzj;
-                gaw[j] = fmaf(aj, ds, gaw[j]);
+                const float dzj = (ds * ctl.w3[j]) * fmaf(-aj, aj, aj);
+                *reinterpret_cast<float*>(dzw + j * 128 + dzoff[j & 7]) = dzj;
+                dzv[j] = dzj;
+                a[j] = aj * ds;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
+            mbar_arrive(&ctl.dzfull[g]);
+            acc_bc += warp_transpose_sum(dzv, lane);
+            acc_w3 += warp_transpose_sum(a, lane);
+        }
+        // the group's fp32 sums -> its own shared arrays (read after the CTA barrier below)
+        const float ds_w = warp_sum(ds_sum);
+        sh.part[w][lane] = acc_bc;
+        sh.part[w][32 + lane] = acc_w3;
+        if (lane == 0) sh.part[w][64] = ds_w, sh.part[w][65] = val_sum;       // (val_sum: thread 0 of the group only)
+    } else if (warp_id == 4 * G) {
+        // ================= loader: one thread, two rings, polled ==========================================================
+        if (lane == 0) {
+            mbar_expect_tx(&ctl.wfull, (unsigned)nch * RF_W_CHUNK_BYTES);
+            for (int ck = 0; ck < nch; ++ck) tma_load_2d(wsm + ck * RF_W_CHUNK_BYTES, &map_w, ck * RF_CHUNK, 0, &ctl.wfull);
+            const int total = nsl * nch;
+            int fn = 0, fk = 0, fc = 0, fslot = 0, fuse = 0;      // F ring: chunk counter, slate, chunk, slot, use of the slot
+            int dn = 0, dk = 0, dc = 0, dslot = 0, duse = 0;
+            unsigned idle = 0;
+            while (fn < total || dn < total) {
+                bool did = false;
+                if (fn < total && (fuse == 0 || mbar_test(&ctl.empty_f[fslot], (unsigned)(fuse - 1) & 1u))) {
+                    mbar_expect_tx(&ctl.full_f[fslot], RF_SLOT_BYTES);
+                    tma_load_2d(fring + fslot * RF_SLOT_BYTES, &map_x, fc * RF_CHUNK, ((int)blockIdx.x + fk * (int)gridDim.x) * RF_DOCS,
+                                &ctl.full_f[fslot]);
+                    ++fn;
+                    if (++fc == nch) fc = 0, ++fk;
+                    if (++fslot == RF_NSF) fslot = 0, ++fuse;
+                    did = true;
+                }
+                // the gradient copy of a slate goes after its forward copy (it is meant to hit L2)
+                if (dn < total && (fk > dk || fn == total) &&
+                    (duse == 0 || mbar_test(&ctl.empty_d[dslot], (unsigned)(duse - 1) & 1u))) {
+                    mbar_expect_tx(&ctl.full_d[dslot], RF_SLOT_BYTES);
+                    tma_load_2d(dring + dslot * RF_SLOT_BYTES, &map_xm, dc * RF_CHUNK, ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS,
+                                &ctl.full_d[dslot]);
+                    ++dn;
+                    if (++dc == nch) dc = 0, ++dk;
+                    if (++dslot == RF_NSD) dslot = 0, ++duse;
+                    did = true;
+                }
+                if (did) idle = 0;
+                else if (++idle > (1u << 28)) __trap();           // a ring that never drains traps instead of hanging the GPU
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const unsigned da = smem_u32(dz), xa = smem_u32(Xm);
-            for (int ks = 0; ks < RF_DOCS / 8; ++ks) {
-                // A: K-major, 8 docs = 32 bytes inside the 128-byte row of chunk ks / 4; B: the X tile MN-major: 8 docs = two
-                // groups of 4 rows (512 bytes apart), feature chunks 16 KB apart (the leading-dimension offset)
-                tc_mma_tf32(tmem_g, umma_desc_sw128(da + (ks >> 2) * RF_DZ_CHUNK_BYTES + (unsigned)(ks & 3) * 32u, 16, 1024),
-                            umma_desc(xa + (unsigned)ks * 1024u, RF_X_CHUNK_BYTES, 512, 1u), IDESC2, (it > 0 || ks > 0));
-            }
-            tc_commit(&sh.mma2);
-        }
-    }
-    // ---- the CTA's accumulators -> global partials --------------------------------------------------------------------
-    if (nslates > 0) {
-        mbar_wait_bounded(&sh.mma2, (unsigned)(nslates - 1) & 1u);
-        tc_fence_after();
-        // M = 64 accumulator: row r lives in lane (r % 16) + 32 (r / 16): lanes 0..15 of every warp's sub-partition
-        float* mine = p.part + (size_t)blockIdx.x * (RF_DZ_ROWS * RF_N2);
-        for (int c0 = 0; c0 < RF_N2; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_g + ((unsigned)(warp * 32) << 16) + (unsigned)c0, v);
-            if (lane < 16) {
-                const int row = warp * 16 + lane;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < RF_N2) mine[(size_t)row * RF_N2 + c0 + i] = v[i];
+    } else if (warp_id == 4 * G + 1) {
+        // ================= F issuer: forward MMAs, in slate order ========================================================
+        if (lane == 0) {
+            constexpr unsigned IDESC1 = umma_idesc_tf32(128, RF_H, 0, 0);
+            mbar_wait_bounded(&ctl.wfull, 0);
+            const unsigned wa = smem_u32(wsm);
+            int slot = 0, use = 0;
+            for (int k = 0; k < nsl; ++k) {
+                const int g = k % G, it = k / G;
+                if (it >= 1) mbar_wait_bounded(&ctl.zfree[g], (unsigned)(it - 1) & 1u);
+                tc_fence_after();
+                for (int ck = 0; ck < nch; ++ck) {
+                    mbar_wait_bounded(&ctl.full_f[slot], (unsigned)use & 1u);
+                    tc_fence_after();
+                    const unsigned xa = smem_u32(fring + slot * RF_SLOT_BYTES);
+                    const int steps = min(4, ksteps - 4 * ck);
+                    for (int s = 0; s < steps; ++s)
+                        tc_mma_tf32(tmem + (unsigned)(g * RF_H), umma_desc_sw128(xa + (unsigned)s * 32u, 16, 1024),
+                                    umma_desc_sw128(wa + (unsigned)ck * RF_W_CHUNK_BYTES + (unsigned)s * 32u, 16, 1024), IDESC1,
+                                    (ck | s) != 0);
+                    tc_commit(&ctl.empty_f[slot]);
+                    if (++slot == RF_NSF) slot = 0, ++use;
+                }
+                tc_commit(&ctl.zfull[g]);
             }
         }
     } else {
-        float* mine = p.part + (size_t)blockIdx.x * (RF_DZ_ROWS * RF_N2);
-        for (int i = tid; i < RF_DZ_ROWS * RF_N2; i += RF_THREADS) mine[i] = 0.f;
+        // ================= D issuer: gradient MMAs, accumulating in slate order ==============================================
+        if (lane == 0) {
+            constexpr unsigned IDESC2 = umma_idesc_tf32(64, RF_CHUNK, 0, 1);
+            int slot = 0, use = 0;
+            for (int k = 0; k < nsl; ++k) {
+                const int g = k % G, it = k / G;
+                mbar_wait_bounded(&ctl.dzfull[g], (unsigned)it & 1u);
+                tc_fence_after();
+                const unsigned da = smem_u32(dz + g * RF_DZ_GROUP_BYTES);
+                for (int ck = 0; ck < nch; ++ck) {
+                    mbar_wait_bounded(&ctl.full_d[slot], (unsigned)use & 1u);
+                    tc_fence_after();
+                    const unsigned xa = smem_u32(dring + slot * RF_SLOT_BYTES);
+                    for (int ks = 0; ks < RF_DOCS / 8; ++ks) {
+                        // A: K-major, 8 docs = 32 bytes inside the 128-byte row of doc chunk ks / 4 (rows 32..63 of the tile:
+                        // whatever follows, never read back); B: the X chunk MN-major: 8 docs = two groups of 4 rows
+                        tc_mma_tf32(tmem_g + (unsigned)(ck * RF_CHUNK),
+                                    umma_desc_sw128(da + (unsigned)(ks >> 2) * RF_DZ_CHUNK_BYTES + (unsigned)(ks & 3) * 32u, 16, 1024),
+                                    umma_desc(xa + (unsigned)ks * 1024u, RF_SLOT_BYTES, 512, 1u), IDESC2, (k > 0 || ks > 0));
+                    }
+                    tc_commit(&ctl.empty_d[slot]);
+                    if (++slot == RF_NSD) slot = 0, ++use;
+                }
+                tc_commit(&ctl.dzfree[g]);
+            }
+            tc_commit(&ctl.alldone);
+        }
     }
-    const float ds_tot = rf_block_sum(ds_sum, sh.red);
+    // ---- the CTA's accumulators -> global partials --------------------------------------------------------------------
+    if (warp_id < 2) {
+        // M = 64 accumulator: row r lives in lane (r % 16) + 32 (r / 16): lanes 0..15 of warps 0 and 1 hold rows 0..31
+        mbar_wait_bounded(&ctl.alldone, 0);
+        tc_fence_after();
+        float* mine = p.part + (size_t)blockIdx.x * RF_PART;
+        for (int c0 = 0; c0 < RF_N2; c0 += 32) {
+            float v[32];
+            if (c0 < nch * RF_CHUNK) {
+                tmem_ld32(tmem_g + ((unsigned)(warp_id * 32) << 16) + (unsigned)c0, v);
+            } else {
 #pragma unroll
-    for (int j = 0; j < RF_H; ++j) {
-        const float x = warp_sum(gdz[j]), w = warp_sum(gaw[j]);
-        if (lane == 0) sh.fold[warp][j] = x, sh.fold[warp][RF_H + j] = w;
-    }
-    __syncthreads();
-    if (tid < 2 * RF_H)
-        p.part_bias[(size_t)blockIdx.x * (2 * RF_H) + tid] = (sh.fold[0][tid] + sh.fold[1][tid]) + (sh.fold[2][tid] + sh.fold[3][tid]);
-    if (tid == 0) {
-        p.part_misc[2 * blockIdx.x + 0] = val_sum;
-        p.part_misc[2 * blockIdx.x + 1] = ds_tot;
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (lane < 16) {
+                const int row = warp_id * 16 + lane;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(mine + (size_t)row * RF_N2 + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(RF_TMEM_COLS) : "memory");
+    if (tid < 2 * RF_H + 2) {
+        float t = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const RfGroup& sg = groups[g];
+            if (tid < 2 * RF_H + 1) t += (sg.part[0][tid] + sg.part[1][tid]) + (sg.part[2][tid] + sg.part[3][tid]);
+            else t += sg.part[0][tid];                            // sum of slate values: thread 0 of the group
+        }
+        if (tid < 2 * RF_H) p.part_bias[(size_t)blockIdx.x * (2 * RF_H) + tid] = t;
+        else p.part_misc[2 * blockIdx.x + (tid == 2 * RF_H ? 1 : 0)] = t;
+    }
+    if (warp_id == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(RF_TMEM_COLS) : "memory");
 }
 
-// partials of the CTAs, added in CTA order: gWc [32, F], gbc [32], gw3 [32], gb3 [1], loss [1]
-__global__ void __launch_bounds__(256) ranker_fused_reduce_kernel(const RankerFusedParams p, float* gWc, float* gbc, float* gw3,
-                                                                  float* gb3) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    const int total = RF_DZ_ROWS * RF_N2;
-    if (idx < total) {
-        float t = 0.f;
-        for (int g = 0; g < p.grid; ++g) t += p.part[(size_t)g * total + idx];
-        const int row = idx / RF_N2, col = idx % RF_N2;
-        if (row < RF_H && col < p.F) gWc[row * p.F + col] = t;
-    }
-    if (idx < 2 * RF_H) {
-        float t = 0.f;
-        for (int g = 0; g < p.grid; ++g) t += p.part_bias[(size_t)g * (2 * RF_H) + idx];
-        if (idx < RF_H) gbc[idx] = t;
-        else gw3[idx - RF_H] = t;
-    }
-    if (idx == 0) {
+// partials of the CTAs, added in a fixed order: gWc [32, F], gbc [32], gw3 [32], gb3 [1], loss [1].
+// A block owns 32 consecutive entries; its 8 warps add up every 8th CTA's partial (independent coalesced loads) and the
+// eight sums meet in shared memory.
+constexpr int RF_RED_WARPS = 8;
+__global__ void __launch_bounds__(32 * RF_RED_WARPS) ranker_fused_reduce_kernel(const RankerFusedParams p, float* gWc, float* gbc,
+                                                                                float* gw3, float* gb3) {
+    __shared__ float sums[RF_RED_WARPS][33];
+    __shared__ double dsum[RF_RED_WARPS][2];
+    pdl_prologue();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nblk_w = RF_PART / 32;                             // blocks over the weight gradient, then 2 over dbc / dw3, then 1
+    const int blk = (int)blockIdx.x;
+    float t = 0.f;
+    if (blk < nblk_w + 2) {
+        const float* src = (blk < nblk_w) ? p.part + (size_t)blk * 32 + lane : p.part_bias + (size_t)(blk - nblk_w) * 32 + lane;
+        const size_t stride = (blk < nblk_w) ? (size_t)RF_PART : (size_t)(2 * RF_H);
+#pragma unroll 4
+        for (int g = warp; g < p.grid; g += RF_RED_WARPS) t += src[(size_t)g * stride];
+        sums[warp][lane] = t;
+    } else {
         double v = 0.0, d = 0.0;
-        for (int g = 0; g < p.grid; ++g) v += (double)p.part_misc[2 * g], d += (double)p.part_misc[2 * g + 1];
+        for (int g = (int)threadIdx.x; g < p.grid; g += 32 * RF_RED_WARPS) v += (double)p.part_misc[2 * g], d += (double)p.part_misc[2 * g + 1];
+        v = warp_sum(v);
+        d = warp_sum(d);
+        if (lane == 0) dsum[warp][0] = v, dsum[warp][1] = d;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    if (blk < nblk_w + 2) {
+        float tot = 0.f;
+#pragma unroll
+        for (int q = 0; q < RF_RED_WARPS; ++q) tot += sums[q][lane];
+        if (blk < nblk_w) {
+            const int idx = blk * 32 + lane, row = idx / RF_N2, col = idx % RF_N2;
+            if (col < p.F) gWc[row * p.F + col] = tot;
+        } else if (blk == nblk_w) {
+            gbc[lane] = tot;
+        } else {
+            gw3[lane] = tot;
+        }
+    } else if (lane == 0) {
+        double v = 0.0, d = 0.0;
+        for (int q = 0; q < RF_RED_WARPS; ++q) v += dsum[q][0], d += dsum[q][1];
         p.loss[0] = (float)(-v / (double)p.B);
         gb3[0] = (float)d;
     }
@@ -527,7 +832,7 @@ LTR_API size_t ltr_triple_scratch_bytes(int B, int n, int F) {
     (void)F;
     if (B <= 0) return 0;
     const size_t grid = (size_t)ltr::device_sm_count();
-    return grid * (ltr::RF_DZ_ROWS * ltr::RF_N2 + 2 + 2 * ltr::RF_H) * sizeof(float);
+    return grid * (ltr::RF_PART + 2 + 2 * ltr::RF_H) * sizeof(float);
 }
 
 LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, const float* Wc, const float* bc, const float* w3,
@@ -558,16 +863,31 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     p.alpha = alpha; p.eps = eps; p.pad = pad_value; p.disc_prefix = disc_prefix;
     p.scores = scores; p.slate_ndcg = slate_ndcg; p.loss = loss;
     p.part = reinterpret_cast<float*>(scratch);
-    p.part_misc = p.part + (size_t)device_sm_count() * (RF_DZ_ROWS * RF_N2);
+    p.part_misc = p.part + (size_t)device_sm_count() * RF_PART;
     p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
-    p.counter = nullptr;
     p.grid = grid;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    LTR_CUDA(cudaFuncSetAttribute(ranker_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM));
-    ranker_fused_kernel<<<grid, RF_THREADS, RF_SMEM, st>>>(map_x, map_xm, map_w, p);
+    constexpr size_t RF_SMEM = 1024 + (size_t)(RF_NSF + RF_NSD) * RF_SLOT_BYTES + RF_W_BYTES + (size_t)RF_G * RF_DZ_GROUP_BYTES +
+                               (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
+    static_assert(RF_SMEM <= 232448, "ranker_fused_kernel: shared memory of one CTA");
+    static_assert((size_t)RF_G * sizeof(RfGroup) >= RF_DZ_CHUNK_BYTES, "rows 32..63 of the last dZ chunk alias the group structs");
+    LTR_CUDA(cudaFuncSetAttribute(ranker_fused_kernel<RF_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM));
+    ranker_fused_kernel<RF_G><<<grid, RF_THREADS, RF_SMEM, st>>>(map_x, map_xm, map_w, p);
     int rc = (int)cudaGetLastError();
     if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd");
-    ranker_fused_reduce_kernel<<<(RF_DZ_ROWS * RF_N2 + 255) / 256, 256, 0, st>>>(p, gWc, gbc, gw3, gb3);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(RF_PART / 32 + 3);
+        cfg.blockDim = dim3(32 * RF_RED_WARPS);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        rc = (int)cudaLaunchKernelEx(&cfg, ranker_fused_reduce_kernel, p, gWc, gbc, gw3, gb3);
+    }
+    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)");
     rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)") : 0;
 }

@@ -90,3 +90,109 @@ def test_fused_step_full_config2_batch_properties():
     assert abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss))
     for a, b in zip(grads, [p.grad for p in net.parameters()]):
         assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+
+
+def _fused_vs_reference(net, X, y, alpha, eps=1e-10, s_tol=2e-3, l_tol=2e-3, g_tol=1e-2):
+    """Run the fused step and the fp32 torch modules + oracle loss on the same inputs; return the measured errors."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet, fused_triple_approx_ndcg
+    from oracle import ltr_oracle as O
+    for prm in net.parameters():
+        prm.grad = None
+    s_ref = net(X, None, None).squeeze(-1)
+    l_ref = O.approx_ndcg_loss(s_ref, y, eps=eps, alpha=alpha)
+    l_ref.backward()
+    g_ref = {k: v.grad.clone() for k, v in net.named_parameters()}
+    dev_net = TripleLayerNet(X.shape[2]).cuda()
+    dev_net.load_state_dict(net.state_dict())
+    loss, scores = fused_triple_approx_ndcg(dev_net, X.cuda(), y.cuda(), eps=eps, alpha=alpha, return_scores=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    valid = y != -1
+    s = scores.cpu()
+    if bool(valid.any()):
+        assert float((s - s_ref.detach())[valid].abs().max()) <= s_tol * float(s_ref.detach()[valid].abs().max())
+    assert abs(float(loss) - float(l_ref)) <= l_tol * abs(float(l_ref)) + 1e-7, (float(loss), float(l_ref))
+    for name, prm in dev_net.named_parameters():
+        gr = g_ref[name]
+        scale = g_ref["l3.weight"].abs().max() if name == "l3.bias" else gr.abs().max()
+        err = float((prm.grad.cpu() - gr).abs().max())
+        assert err <= g_tol * float(scale) + 1e-9, (name, err, float(scale))
+    return float(loss)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("F", [8, 64, 132, 160])
+def test_fused_step_feature_widths(F):
+    """1, 2 and 5 feature chunks, a width that is not a multiple of 8 (the last k step is half zero fill)."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    torch.manual_seed(F)
+    net = TripleLayerNet(F)
+    g = torch.Generator().manual_seed(F)
+    B = 37
+    X = torch.rand(B, 128, F, generator=g)
+    _, y = make_slates(B, 128, seed=F, min_len=70)
+    _fused_vs_reference(net, X, y, alpha=10.0)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("B", [2, 3, 149, 600, 1500])
+def test_fused_step_slate_counts(B):
+    """Fewer slates than compute groups, one CTA with two slates, several rounds of every group; short slates
+    (2 and 3 docs per lane), single-doc and fully padded slates in the batch."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    torch.manual_seed(B)
+    net = TripleLayerNet(136)
+    g = torch.Generator().manual_seed(B)
+    X = torch.rand(B, 128, 136, generator=g)
+    _, y = make_slates(B, 128, seed=B, min_len=1)
+    y[0, 1:] = -1.0                                              # one doc
+    if B > 2:
+        y[B // 2] = -1.0                                         # no doc at all: slate value 0, no gradient
+    _fused_vs_reference(net, X, y, alpha=10.0)
+
+
+@pytest.mark.timeout(300)
+def test_fused_step_padding_anywhere_and_fractional_labels():
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    torch.manual_seed(5)
+    net = TripleLayerNet(136)
+    g = torch.Generator().manual_seed(5)
+    B = 64
+    X = torch.rand(B, 128, 136, generator=g)
+    _, y = make_slates(B, 128, seed=5, min_len=30, pad_anywhere=True)
+    frac = torch.rand(B, 128, generator=g) * 4.0
+    y[::2] = torch.where(y[::2] == -1, y[::2], frac[::2])        # every other slate: labels off the 0..4 grid
+    y[1, :10] = 7.0                                              # integer labels above 4
+    _fused_vs_reference(net, X, y, alpha=10.0)
+
+
+@pytest.mark.timeout(300)
+def test_fused_step_wide_score_range_takes_direct_form():
+    """alpha * log2(e) * (max - min score) >= 126: the factorised pair sigmoid would overflow; the direct form runs."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    torch.manual_seed(6)
+    net = TripleLayerNet(136)
+    with torch.no_grad():
+        net.l3.weight.mul_(150.0)
+    g = torch.Generator().manual_seed(6)
+    B = 48
+    X = torch.rand(B, 128, 136, generator=g)
+    _, y = make_slates(B, 128, seed=6, min_len=64)
+    s = net(X, None, None).squeeze(-1)
+    assert float((s.max(dim=1).values - s.min(dim=1).values).max()) * 10.0 * 1.4427 > 126.0
+    # saturated sigmoids: gradients of both implementations are tiny differences of O(1) terms
+    _fused_vs_reference(net, X, y, alpha=10.0, g_tol=3e-2)
+
+
+@pytest.mark.timeout(300)
+def test_fused_step_large_eps_clamps_pairs():
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    torch.manual_seed(8)
+    net = TripleLayerNet(136)
+    with torch.no_grad():
+        net.l3.weight.mul_(4.0)
+    g = torch.Generator().manual_seed(8)
+    B = 40
+    X = torch.rand(B, 128, 136, generator=g)
+    _, y = make_slates(B, 128, seed=8, min_len=64)
+    _fused_vs_reference(net, X, y, alpha=10.0, eps=1e-3, g_tol=3e-2)

@@ -295,12 +295,56 @@ def bench_approx_large(iters=30, B=65536, n=128):
                                               "and pass: frac can exceed 1)", kernel="approx_ndcg_warp_kernel")}
 
 
+def bench_ranker_step(iters=30, B=4096, n=128, F=136):
+    """BASELINE configs[1] as a TRAINING STEP: TripleLayerNet forward + approxNDCG (alpha=10) + backward to all six
+    parameter gradients.  fused: `ltr_triple_approx_ndcg_fwdbwd` (one TMA + tcgen05 kernel, X read once);
+    torch+K1: stock torch.nn modules (cuBLAS, fp32 or tf32 matmuls) with the fused approxNDCG loss kernel; both through
+    autograd, CUDA events over `iters` steps on 3 distinct feature batches (3 x 285 MB > L2)."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet, fused_triple_approx_ndcg
+    from ltr_b200.losses.approxNDCG import approxNDCGLoss
+    torch.manual_seed(0)
+    net = TripleLayerNet(F).cuda()
+    ring = 3
+    data = []
+    for i in range(ring):
+        g = torch.Generator().manual_seed(700 + i)
+        X = torch.rand(B, n, F, generator=g).cuda()
+        _, y = _slates(B, n, 710 + i)
+        data.append((X, y))
+
+    def fused(i):
+        X, y = data[i % ring]
+        net.zero_grad(set_to_none=True)
+        fused_triple_approx_ndcg(net, X, y, alpha=10.0).backward()
+
+    def stock(i):
+        X, y = data[i % ring]
+        net.zero_grad(set_to_none=True)
+        approxNDCGLoss(net(X, None, None).squeeze(-1), y, alpha=10.0).backward()
+
+    sec = _time(fused, iters)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sec_fp32 = _time(stock, max(5, iters // 3))
+    torch.backends.cuda.matmul.allow_tf32 = True
+    sec_tf32 = _time(stock, max(5, iters // 3))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    alg = (4.0 * F * n + 8.0 * n) * B                       # features once, labels in, scores out
+    return {"metric": "TripleLayerNet + approxNDCG training step slates/s (n=128, F=136)", "value": B / sec, "unit": "slates/s",
+            "us_per_call": sec * 1e6, "us_per_step_torch_modules_fp32_plus_K1": sec_fp32 * 1e6,
+            "us_per_step_torch_modules_tf32_plus_K1": sec_tf32 * 1e6,
+            "speedup_vs_torch_fp32": sec_fp32 / sec, "speedup_vs_torch_tf32": sec_tf32 / sec,
+            "config": {"workload": f"{B} slates x {n} docs x {F} features, valid len U{{64..128}}, alpha=10; forward + backward "
+                                   "to l1/l2/l3 weight and bias gradients, through autograd, zero_grad included"},
+            "roofline": dict(_roof(alg, sec), kernel="ranker_fused_kernel (TMA + tcgen05 tf32, 1 CTA per SM) + ranker_fused_reduce_kernel",
+                             algorithmic="4 F n + 8 n bytes per slate (features read once, labels, scores)")}
+
+
 def bench_ndcg_1024(iters=30):
     """BASELINE configs[4] evaluation sweep: 8192 queries x 1024 docs."""
     return bench_ndcg(iters, Q=8192, n=1024)
 
 
-ALL = {"listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg_large": bench_ndcg_large, "ndcg1024": bench_ndcg_1024, "lambda": bench_lambda,
+ALL = {"ranker_step": bench_ranker_step, "listnet": bench_listnet, "ndcg": bench_ndcg, "ndcg_large": bench_ndcg_large, "ndcg1024": bench_ndcg_1024, "lambda": bench_lambda,
        "georisk": bench_georisk, "approx1024": bench_approx_1024, "approx_large_batch": bench_approx_large}
 
 
