@@ -57,11 +57,13 @@ constexpr int RF_SLOT_BYTES = RF_DOCS * 128;                    // 16 KB: [128 d
 constexpr int RF_W_CHUNK_BYTES = RF_H * 128;                    // 4 KB: [32 rows][32 floats]
 constexpr int RF_W_BYTES = RF_KCHUNKS * RF_W_CHUNK_BYTES;       // 20 KB
 constexpr int RF_DZ_CHUNK_BYTES = RF_H * 128;                   // 4 KB: [32 hidden units][32 docs]
-constexpr int RF_DZ_GROUP_BYTES = 4 * RF_DZ_CHUNK_BYTES;        // 16 KB per compute group
+constexpr int RF_DZ_TILE_BYTES = 4 * RF_DZ_CHUNK_BYTES;         // 16 KB: dZ^T of one slate
+static_assert(RF_GROUPS <= 4, "the dZ tile hand-over needs G <= 2 RF_NDZ");
+constexpr int RF_NDZ = 2;                                       // dZ tiles, used in slate order by whichever group owns the slate
 constexpr int RF_N2 = RF_KCHUNKS * RF_CHUNK;                    // columns of the gradient accumulator
 constexpr int RF_G = RF_GROUPS;
 constexpr int RF_NSF = 5;                                       // F ring: one slate of forward chunks in flight (HBM latency)
-constexpr int RF_NSD = (RF_G >= 4) ? 2 : 3;                     // D ring: L2 hits
+constexpr int RF_NSD = 4;                                       // D ring: L2 hits, but a gradient job is on the critical path of the D issuer
 constexpr int RF_THREADS = RF_G * 128 + 96;                     // compute groups + loader, F issuer, D issuer warps
 constexpr int RF_TMEM_COLS = (RF_G * RF_H + RF_N2 <= 256) ? 256 : 512;
 constexpr int RF_PART = RF_H * RF_N2;                           // floats of one CTA's gradient partial
@@ -108,6 +110,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
             smem_u32(smem_dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// with an L2 eviction-priority hint (createpolicy)
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -192,9 +202,10 @@ struct RfCtl {
     uint64_t full_d[RF_NSD], empty_d[RF_NSD];     // D ring
     uint64_t wfull;                               // TMA landed Wc
     uint64_t zfull[RF_G];                         // the forward MMAs of the group's slate are complete
-    uint64_t zfree[RF_G];                         // the group has taken Z out of tensor memory (128 arrivals)
-    uint64_t dzfull[RF_G];                        // the group has written dZ of its slate (128 arrivals)
-    uint64_t dzfree[RF_G];                        // the gradient MMAs of the group's slate are complete
+    uint64_t zfree[RF_G];                         // the group is done with its slate: its next forward MMA may go (128 arrivals)
+    uint64_t dzfull[RF_NDZ];                      // dZ of a slate has been written to the tile (128 arrivals)
+    uint64_t dzfree[RF_NDZ];                      // the gradient MMAs reading the tile are complete
+    uint64_t dzmine[RF_G];                        // the gradient MMAs of the group's latest slate are complete
     uint64_t alldone;                             // every MMA of the CTA is complete
     unsigned tmem_base;
     float w3[RF_H], bc[RF_H];
@@ -424,7 +435,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     unsigned char* dring = fring + RF_NSF * RF_SLOT_BYTES;        // gradient copies: 128-byte swizzle, 32-byte atoms
     unsigned char* wsm = dring + RF_NSD * RF_SLOT_BYTES;
     unsigned char* dz = wsm + RF_W_BYTES;
-    RfGroup* groups = reinterpret_cast<RfGroup*>(dz + G * RF_DZ_GROUP_BYTES);
+    RfGroup* groups = reinterpret_cast<RfGroup*>(dz + RF_NDZ * RF_DZ_TILE_BYTES);
     RfCtl& ctl = *reinterpret_cast<RfCtl*>(groups + G);
     const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
     const int nsl = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;          // slates blockIdx.x, + grid, ...
@@ -435,12 +446,8 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         for (int i = 0; i < RF_NSF; ++i) mbar_init(&ctl.full_f[i], 1), mbar_init(&ctl.empty_f[i], 1);
         for (int i = 0; i < RF_NSD; ++i) mbar_init(&ctl.full_d[i], 1), mbar_init(&ctl.empty_d[i], 1);
         mbar_init(&ctl.wfull, 1);
-        for (int g = 0; g < G; ++g) {
-            mbar_init(&ctl.zfull[g], 1);
-            mbar_init(&ctl.zfree[g], 128);
-            mbar_init(&ctl.dzfull[g], 128);
-            mbar_init(&ctl.dzfree[g], 1);
-        }
+        for (int g = 0; g < G; ++g) mbar_init(&ctl.zfull[g], 1), mbar_init(&ctl.zfree[g], 128), mbar_init(&ctl.dzmine[g], 1);
+        for (int t = 0; t < RF_NDZ; ++t) mbar_init(&ctl.dzfull[t], 128), mbar_init(&ctl.dzfree[t], 1);
         mbar_init(&ctl.alldone, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -464,7 +471,6 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int g = warp_id >> 2, w = warp_id & 3, gt = tid & 127;
         RfGroup& sh = groups[g];
         const int bar = 1 + g;
-        unsigned char* dzw = dz + g * RF_DZ_GROUP_BYTES + w * RF_DZ_CHUNK_BYTES;      // this warp's chunk of 32 docs
         unsigned dzoff[8];                                        // swizzled byte offset of column `lane` in a row of class j & 7
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) dzoff[jj] = ((((unsigned)lane >> 2) ^ (unsigned)jj) << 4) + (((unsigned)lane & 3u) << 2);
@@ -486,7 +492,6 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             float a[RF_H];
             tmem_ld32(tmem + (unsigned)(g * RF_H) + ((unsigned)(w * 32) << 16), a);
             tc_fence_before();
-            mbar_arrive(&ctl.zfree[g]);                           // Z is in registers: the next forward MMA of the group may go
             float sv = p.b3;
 #pragma unroll
             for (int j = 0; j < RF_H; ++j) {
@@ -599,7 +604,13 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 val_sum += slate_val;
             }
             // ---- dZ of this doc -> the group's A tile of the gradient MMA (K-major: row = hidden unit, column = doc) -----------
-            if (it >= 1) mbar_wait_bounded(&ctl.dzfree[g], (unsigned)(it - 1) & 1u);  // the previous slate's gradient MMAs are done
+            const int tile = k % RF_NDZ, tuse = k / RF_NDZ;       // tiles go round in slate order
+            // A parity wait is only sound within one phase of the barrier.  The tile's barrier is shared with the other groups,
+            // so first make sure that the gradient job of this group's OWN previous slate is complete (jobs complete in slate
+            // order, and G <= 2 RF_NDZ: every use of the tile but the latest is then complete), then wait for the latest.
+            if (it >= 1) mbar_wait_bounded(&ctl.dzmine[g], (unsigned)(it - 1) & 1u);
+            if (tuse >= 1) mbar_wait_bounded(&ctl.dzfree[tile], (unsigned)(tuse - 1) & 1u);
+            unsigned char* dzw = dz + tile * RF_DZ_TILE_BYTES + w * RF_DZ_CHUNK_BYTES;        // this warp's chunk of 32 docs
             float dzv[RF_H];
 #pragma unroll
             for (int j = 0; j < RF_H; ++j) {
@@ -610,7 +621,10 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 a[j] = aj * ds;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
-            mbar_arrive(&ctl.dzfull[g]);
+            mbar_arrive(&ctl.dzfull[tile]);
+            // only now may the group's next forward MMA go: run earlier, its feature chunks would be read from HBM so long
+            // before their second (L2) read by the gradient job that they are evicted in between
+            mbar_arrive(&ctl.zfree[g]);
             acc_bc += warp_transpose_sum(dzv, lane);
             acc_w3 += warp_transpose_sum(a, lane);
         }
@@ -624,6 +638,11 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (lane == 0) {
             mbar_expect_tx(&ctl.wfull, (unsigned)nch * RF_W_CHUNK_BYTES);
             for (int ck = 0; ck < nch; ++ck) tma_load_2d(wsm + ck * RF_W_CHUNK_BYTES, &map_w, ck * RF_CHUNK, 0, &ctl.wfull);
+            // the forward copy of a chunk is read again (by the gradient job) some 50 MB of traffic later: keep it in L2
+            // until then, and let the second read release it
+            uint64_t keep, drop;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(drop));
             const int total = nsl * nch;
             int fn = 0, fk = 0, fc = 0, fslot = 0, fuse = 0;      // F ring: chunk counter, slate, chunk, slot, use of the slot
             int dn = 0, dk = 0, dc = 0, dslot = 0, duse = 0;
@@ -632,8 +651,8 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 bool did = false;
                 if (fn < total && (fuse == 0 || mbar_test(&ctl.empty_f[fslot], (unsigned)(fuse - 1) & 1u))) {
                     mbar_expect_tx(&ctl.full_f[fslot], RF_SLOT_BYTES);
-                    tma_load_2d(fring + fslot * RF_SLOT_BYTES, &map_x, fc * RF_CHUNK, ((int)blockIdx.x + fk * (int)gridDim.x) * RF_DOCS,
-                                &ctl.full_f[fslot]);
+                    tma_load_2d_hint(fring + fslot * RF_SLOT_BYTES, &map_x, fc * RF_CHUNK, ((int)blockIdx.x + fk * (int)gridDim.x) * RF_DOCS,
+                                     &ctl.full_f[fslot], keep);
                     ++fn;
                     if (++fc == nch) fc = 0, ++fk;
                     if (++fslot == RF_NSF) fslot = 0, ++fuse;
@@ -643,8 +662,8 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (dn < total && (fk > dk || fn == total) &&
                     (duse == 0 || mbar_test(&ctl.empty_d[dslot], (unsigned)(duse - 1) & 1u))) {
                     mbar_expect_tx(&ctl.full_d[dslot], RF_SLOT_BYTES);
-                    tma_load_2d(dring + dslot * RF_SLOT_BYTES, &map_xm, dc * RF_CHUNK, ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS,
-                                &ctl.full_d[dslot]);
+                    tma_load_2d_hint(dring + dslot * RF_SLOT_BYTES, &map_xm, dc * RF_CHUNK, ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS,
+                                     &ctl.full_d[dslot], drop);
                     ++dn;
                     if (++dc == nch) dc = 0, ++dk;
                     if (++dslot == RF_NSD) dslot = 0, ++duse;
@@ -686,10 +705,10 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             constexpr unsigned IDESC2 = umma_idesc_tf32(64, RF_CHUNK, 0, 1);
             int slot = 0, use = 0;
             for (int k = 0; k < nsl; ++k) {
-                const int g = k % G, it = k / G;
-                mbar_wait_bounded(&ctl.dzfull[g], (unsigned)it & 1u);
+                const int tile = k % RF_NDZ, tuse = k / RF_NDZ;
+                mbar_wait_bounded(&ctl.dzfull[tile], (unsigned)tuse & 1u);
                 tc_fence_after();
-                const unsigned da = smem_u32(dz + g * RF_DZ_GROUP_BYTES);
+                const unsigned da = smem_u32(dz + tile * RF_DZ_TILE_BYTES);
                 for (int ck = 0; ck < nch; ++ck) {
                     mbar_wait_bounded(&ctl.full_d[slot], (unsigned)use & 1u);
                     tc_fence_after();
@@ -704,7 +723,8 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     tc_commit(&ctl.empty_d[slot]);
                     if (++slot == RF_NSD) slot = 0, ++use;
                 }
-                tc_commit(&ctl.dzfree[g]);
+                tc_commit(&ctl.dzfree[tile]);
+                tc_commit(&ctl.dzmine[k % G]);
             }
             tc_commit(&ctl.alldone);
         }
@@ -867,7 +887,7 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
     p.grid = grid;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    constexpr size_t RF_SMEM = 1024 + (size_t)(RF_NSF + RF_NSD) * RF_SLOT_BYTES + RF_W_BYTES + (size_t)RF_G * RF_DZ_GROUP_BYTES +
+    constexpr size_t RF_SMEM = 1024 + (size_t)(RF_NSF + RF_NSD) * RF_SLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
                                (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
     static_assert(RF_SMEM <= 232448, "ranker_fused_kernel: shared memory of one CTA");
     static_assert((size_t)RF_G * sizeof(RfGroup) >= RF_DZ_CHUNK_BYTES, "rows 32..63 of the last dZ chunk alias the group structs");
