@@ -172,6 +172,21 @@ __device__ __forceinline__ unsigned sw128_offset(int row, int col) {
     return (unsigned)row * 128u + ((((unsigned)col >> 2) ^ ((unsigned)row & 7u)) << 4) + (((unsigned)col & 3u) << 2);
 }
 
+// one lane of a converged warp (warp-uniform code around it keeps the MMA operands in uniform registers: a branch on
+// lane == 0 makes the compiler wrap every tcgen05 instruction in a ~14-instruction R2UR / vote loop)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
     unsigned done;
     asm volatile(
@@ -674,59 +689,64 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
         }
     } else if (warp_id == 4 * G + 1) {
-        // ================= F issuer: forward MMAs, in slate order ========================================================
-        if (lane == 0) {
-            constexpr unsigned IDESC1 = umma_idesc_tf32(128, RF_H, 0, 0);
-            mbar_wait_bounded(&ctl.wfull, 0);
-            const unsigned wa = smem_u32(wsm);
-            int slot = 0, use = 0;
-            for (int k = 0; k < nsl; ++k) {
-                const int g = k % G, it = k / G;
-                if (it >= 1) mbar_wait_bounded(&ctl.zfree[g], (unsigned)(it - 1) & 1u);
+        // ================= F issuer: forward MMAs, in slate order (the whole warp walks the loop, one lane issues) ==========
+        constexpr unsigned IDESC1 = umma_idesc_tf32(128, RF_H, 0, 0);
+        mbar_wait_bounded(&ctl.wfull, 0);
+        const unsigned wa = smem_u32(wsm), fa = smem_u32(fring);
+        int slot = 0, use = 0;
+        for (int k = 0; k < nsl; ++k) {
+            const int g = k % G, it = k / G;
+            if (it >= 1) mbar_wait_bounded(&ctl.zfree[g], (unsigned)(it - 1) & 1u);
+            tc_fence_after();
+            for (int ck = 0; ck < nch; ++ck) {
+                mbar_wait_bounded(&ctl.full_f[slot], (unsigned)use & 1u);
                 tc_fence_after();
-                for (int ck = 0; ck < nch; ++ck) {
-                    mbar_wait_bounded(&ctl.full_f[slot], (unsigned)use & 1u);
-                    tc_fence_after();
-                    const unsigned xa = smem_u32(fring + slot * RF_SLOT_BYTES);
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(fa + (unsigned)slot * RF_SLOT_BYTES, 16, 1024);
+                    const uint64_t bdesc = umma_desc_sw128(wa + (unsigned)ck * RF_W_CHUNK_BYTES, 16, 1024);
                     const int steps = min(4, ksteps - 4 * ck);
-                    for (int s = 0; s < steps; ++s)
-                        tc_mma_tf32(tmem + (unsigned)(g * RF_H), umma_desc_sw128(xa + (unsigned)s * 32u, 16, 1024),
-                                    umma_desc_sw128(wa + (unsigned)ck * RF_W_CHUNK_BYTES + (unsigned)s * 32u, 16, 1024), IDESC1,
-                                    (ck | s) != 0);
+                    for (int s = 0; s < steps; ++s)           // a k step = 32 bytes = 2 units of the descriptor's start address
+                        tc_mma_tf32(tmem + (unsigned)(g * RF_H), adesc + (uint64_t)(2 * s), bdesc + (uint64_t)(2 * s), IDESC1, (ck | s) != 0);
                     tc_commit(&ctl.empty_f[slot]);
-                    if (++slot == RF_NSF) slot = 0, ++use;
+                    if (ck == nch - 1) tc_commit(&ctl.zfull[g]);
                 }
-                tc_commit(&ctl.zfull[g]);
+                __syncwarp();
+                if (++slot == RF_NSF) slot = 0, ++use;
             }
         }
     } else {
         // ================= D issuer: gradient MMAs, accumulating in slate order ==============================================
-        if (lane == 0) {
-            constexpr unsigned IDESC2 = umma_idesc_tf32(64, RF_CHUNK, 0, 1);
-            int slot = 0, use = 0;
-            for (int k = 0; k < nsl; ++k) {
-                const int tile = k % RF_NDZ, tuse = k / RF_NDZ;
-                mbar_wait_bounded(&ctl.dzfull[tile], (unsigned)tuse & 1u);
+        constexpr unsigned IDESC2 = umma_idesc_tf32(64, RF_CHUNK, 0, 1);
+        const unsigned dza = smem_u32(dz), dra = smem_u32(dring);
+        int slot = 0, use = 0;
+        for (int k = 0; k < nsl; ++k) {
+            const int tile = k % RF_NDZ, tuse = k / RF_NDZ;
+            mbar_wait_bounded(&ctl.dzfull[tile], (unsigned)tuse & 1u);
+            tc_fence_after();
+            for (int ck = 0; ck < nch; ++ck) {
+                mbar_wait_bounded(&ctl.full_d[slot], (unsigned)use & 1u);
                 tc_fence_after();
-                const unsigned da = smem_u32(dz + tile * RF_DZ_TILE_BYTES);
-                for (int ck = 0; ck < nch; ++ck) {
-                    mbar_wait_bounded(&ctl.full_d[slot], (unsigned)use & 1u);
-                    tc_fence_after();
-                    const unsigned xa = smem_u32(dring + slot * RF_SLOT_BYTES);
-                    for (int ks = 0; ks < RF_DOCS / 8; ++ks) {
-                        // A: K-major, 8 docs = 32 bytes inside the 128-byte row of doc chunk ks / 4 (rows 32..63 of the tile:
-                        // whatever follows, never read back); B: the X chunk MN-major: 8 docs = two groups of 4 rows
-                        tc_mma_tf32(tmem_g + (unsigned)(ck * RF_CHUNK),
-                                    umma_desc_sw128(da + (unsigned)(ks >> 2) * RF_DZ_CHUNK_BYTES + (unsigned)(ks & 3) * 32u, 16, 1024),
-                                    umma_desc(xa + (unsigned)ks * 1024u, RF_SLOT_BYTES, 512, 1u), IDESC2, (k > 0 || ks > 0));
-                    }
+                if (elect_one()) {
+                    // A: K-major, 8 docs = 32 bytes (2 address units) inside the 128-byte row of doc chunk ks / 4, chunks 4 KB
+                    // (256 units) apart (rows 32..63 of the tile: whatever follows, never read back); B: the X chunk MN-major:
+                    // 8 docs = two groups of 4 rows = 1 KB (64 units)
+                    const uint64_t adesc = umma_desc_sw128(dza + (unsigned)tile * RF_DZ_TILE_BYTES, 16, 1024);
+                    const uint64_t bdesc = umma_desc(dra + (unsigned)slot * RF_SLOT_BYTES, RF_SLOT_BYTES, 512, 1u);
+                    const unsigned dcol = tmem_g + (unsigned)(ck * RF_CHUNK);
+#pragma unroll
+                    for (int ks = 0; ks < RF_DOCS / 8; ++ks)
+                        tc_mma_tf32(dcol, adesc + (uint64_t)((ks >> 2) * (RF_DZ_CHUNK_BYTES >> 4) + (ks & 3) * 2), bdesc + (uint64_t)(ks * 64),
+                                    IDESC2, (k > 0 || ks > 0));
                     tc_commit(&ctl.empty_d[slot]);
-                    if (++slot == RF_NSD) slot = 0, ++use;
+                    if (ck == nch - 1) {
+                        tc_commit(&ctl.dzfree[tile]);
+                        tc_commit(&ctl.dzmine[k % G]);
+                        if (k == nsl - 1) tc_commit(&ctl.alldone);
+                    }
                 }
-                tc_commit(&ctl.dzfree[tile]);
-                tc_commit(&ctl.dzmine[k % G]);
+                __syncwarp();
+                if (++slot == RF_NSD) slot = 0, ++use;
             }
-            tc_commit(&ctl.alldone);
         }
     }
     // ---- the CTA's accumulators -> global partials --------------------------------------------------------------------
