@@ -43,7 +43,7 @@
 #include "ltr_host.h"
 
 #ifndef RF_GROUPS
-#define RF_GROUPS 4          // compute groups per CTA (A/B knob: 3 leaves 136 registers per thread, 4 leaves 104)
+#define RF_GROUPS 3          // compute groups per CTA (A/B knob; measured 4096 x 128 x 136: 2 groups .. us, 3 .. us, 4 .. us)
 #endif
 
 namespace ltr {
@@ -58,12 +58,23 @@ constexpr int RF_W_CHUNK_BYTES = RF_H * 128;                    // 4 KB: [32 row
 constexpr int RF_W_BYTES = RF_KCHUNKS * RF_W_CHUNK_BYTES;       // 20 KB
 constexpr int RF_DZ_CHUNK_BYTES = RF_H * 128;                   // 4 KB: [32 hidden units][32 docs]
 constexpr int RF_DZ_TILE_BYTES = 4 * RF_DZ_CHUNK_BYTES;         // 16 KB: dZ^T of one slate
-static_assert(RF_GROUPS <= 4, "the dZ tile hand-over needs G <= 2 RF_NDZ");
-constexpr int RF_NDZ = 2;                                       // dZ tiles, used in slate order by whichever group owns the slate
+// dZ tiles, used in slate order by whichever group owns the slate
+constexpr int RF_NDZ = (RF_GROUPS <= 3) ? 3 : 2;
+static_assert(RF_GROUPS <= 2 * RF_NDZ, "the dZ tile hand-over needs G <= 2 RF_NDZ");
 constexpr int RF_N2 = RF_KCHUNKS * RF_CHUNK;                    // columns of the gradient accumulator
 constexpr int RF_G = RF_GROUPS;
 constexpr int RF_NSF = 5;                                       // F ring: one slate of forward chunks in flight (HBM latency)
-constexpr int RF_NSD = 4;                                       // D ring: L2 hits, but a gradient job is on the critical path of the D issuer
+constexpr int RF_QDOCS = 32;                                    // D ring: a slot = 32 docs x ALL feature chunks ...
+constexpr int RF_QBOX_BYTES = RF_QDOCS * 128;                   // ... 4 KB per chunk: [32 docs][32 floats] ...
+constexpr int RF_QSLOT_BYTES = RF_KCHUNKS * RF_QBOX_BYTES;      // ... 20 KB per slot, so that one MMA spans all N = 160 features
+constexpr int RF_NSD = (RF_GROUPS <= 3) ? 3 : 4;                // D ring of doc quarters (L2 hits); shared memory decides
+#ifndef RF_EARLY_F
+#define RF_EARLY_F 1
+#endif
+#ifndef RF_STAGGER_NS
+#define RF_STAGGER_NS 2500   // group g starts g x this late: the groups then stay out of phase, and the tensor / TMA work of one
+                             // overlaps the arithmetic of the others (in lockstep they alternate between the two)
+#endif
 constexpr int RF_THREADS = RF_G * 128 + 96;                     // compute groups + loader, F issuer, D issuer warps
 constexpr int RF_TMEM_COLS = (RF_G * RF_H + RF_N2 <= 256) ? 256 : 512;
 constexpr int RF_PART = RF_H * RF_N2;                           // floats of one CTA's gradient partial
@@ -89,20 +100,21 @@ struct RankerFusedParams {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait: a barrier that never completes traps instead of hanging the GPU
+// bounded wait: a barrier that never completes traps instead of hanging the GPU.  The suspend-time hint lets the
+// hardware park the warp (up to ~4 us per try) instead of spinning through issue slots the compute groups need.
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity) {
     unsigned done = 0;
     for (unsigned spin = 0; !done; ++spin) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
             : "memory");
-        if (spin > (1u << 24)) __trap();
+        if (spin > (1u << 21)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -202,7 +214,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
 }
 
 // per compute group: the slate state of the loss (the layout of the K1 kernel's SymShared)
-struct RfGroup {
+struct __align__(16) RfGroup {
     float u[RF_DOCS];             // 2^(t - c)   (direct form: raw score)
     float v[RF_DOCS];             // 2^-(t - c)
     float c[RF_DOCS];             // d loss / d pos_i
@@ -259,6 +271,33 @@ __device__ __forceinline__ float rf_middle(RfGroup& sh, int bar, int lane, int w
     return (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
 }
 
+// R consecutive floats of a shared array at a multiple of R: one 64- / 128-bit access for R = 2 / 4 (a lane stride of 2 or 4
+// words is a 2- / 4-way bank conflict with scalar accesses; R = 3 is conflict-free as it is)
+template <int R>
+__device__ __forceinline__ void lds_vec(const float* p, float (&out)[R]) {
+    if (R == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        out[0] = t.x, out[1] = t.y, out[2] = t.z, out[3 % R] = t.w;
+    } else if (R == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        out[0] = t.x, out[1] = t.y;
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r] = p[r];
+    }
+}
+template <int R>
+__device__ __forceinline__ void sts_vec(float* p, const float (&in)[R]) {
+    if (R == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3 % R]);
+    } else if (R == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(in[0], in[1]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r] = in[r];
+    }
+}
+
 // One slate in the factorised form, R docs per lane (the schedule of sym_slate in approx_ndcg_sym.cuh, on a group of 4 warps
 // with a named barrier).  Returns sum_j w_ij (c_j - c_i) of this thread's doc; slate_val = the slate's approxNDCG.
 template <int R>
@@ -284,10 +323,10 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
     if (steps == 0 || !active) ret = lane;    // nothing accumulated: the column sums are zero
 
     float urow[R], vcol[R], acc_r[R], acc_r_hi[R], acc_c[R];
+    lds_vec<R>(sh.u + lane * R, urow);
+    lds_vec<R>(sh.v + cb * R, vcol);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        urow[r] = sh.u[lane * R + r];
-        vcol[r] = sh.v[cb * R + r];
         acc_r[r] = 0.f;
         acc_r_hi[r] = 0.f;
         acc_c[r] = 0.f;
@@ -295,8 +334,7 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
     // ---------------- rank pass: one MUFU.RCP per unordered pair -----------------------------
     if (role == 0) {                          // pairs inside the lane's own block
         float vrow[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+        lds_vec<R>(sh.v + lane * R, vrow);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -308,8 +346,10 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
             }
         }
     }
+    // ONE copy of the tile code per pass (the antipodal step is the loop's last iteration with weight 1/2): the kernel's
+    // instruction footprint, not its arithmetic, is what the SMs run out of first
 #pragma unroll 1
-    for (int i = 0; i < full; ++i) {
+    for (int i = 0; i < steps; ++i) {
         if (i) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -317,23 +357,14 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
                 acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
             }
         }
-        rank_tile<R>(urow, vcol, 1.0f, acc_r, acc_r_hi, acc_c);
-    }
-    if (anti) {
-        if (full) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
-                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
-            }
-        }
-        rank_tile<R>(urow, vcol, 0.5f, acc_r, acc_r_hi, acc_c);
+        rank_tile<R>(urow, vcol, (anti && i == full) ? 0.5f : 1.0f, acc_r, acc_r_hi, acc_c);
     }
     // the column accumulators go home; a doc's partial is (sum sigma_ij as a row) - (sum sigma_ij as a column)
+    {
+        float out[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
-        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) - cols;
+        for (int r = 0; r < R; ++r) out[r] = (acc_r[r] + acc_r_hi[r]) - __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sts_vec<R>(sh.part[warp] + lane * R, out);
     }
     named_bar_sync(bar, 128);
 
@@ -352,19 +383,18 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
 
     // ---------------- gradient pass: sigma recomputed, one MUFU.RCP per unordered pair ---------
     float crow[R], ccol[R];
+    lds_vec<R>(sh.c + lane * R, crow);
+    lds_vec<R>(sh.c + cb * R, ccol);
+    lds_vec<R>(sh.v + cb * R, vcol);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        crow[r] = sh.c[lane * R + r];
-        ccol[r] = sh.c[cb * R + r];
-        vcol[r] = sh.v[cb * R + r];
         acc_r[r] = 0.f;
         acc_r_hi[r] = 0.f;
         acc_c[r] = 0.f;
     }
     if (role == 0) {
         float vrow[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+        lds_vec<R>(sh.v + lane * R, vrow);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -378,7 +408,7 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
         }
     }
 #pragma unroll 1
-    for (int i = 0; i < full; ++i) {
+    for (int i = 0; i < steps; ++i) {
         if (i) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -387,26 +417,17 @@ __device__ __forceinline__ float rf_sym_slate(RfGroup& sh, int bar, int gt, int 
                 acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
             }
         }
+        if (anti && i == full) {                // the antipodal step: weight 1/2 goes onto the c differences (last step)
+#pragma unroll
+            for (int r = 0; r < R; ++r) crow[r] *= 0.5f, ccol[r] *= 0.5f;
+        }
         grad_tile<R>(urow, vcol, crow, ccol, acc_r, acc_r_hi, acc_c);
     }
-    if (anti) {                                 // weight 1/2 goes onto the c differences
-        if (full) {
+    {
+        float out[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                vcol[r] = __shfl_sync(LTR_FULL_MASK, vcol[r], src);
-                ccol[r] = __shfl_sync(LTR_FULL_MASK, ccol[r], src);
-                acc_c[r] = __shfl_sync(LTR_FULL_MASK, acc_c[r], src);
-            }
-        }
-        float ch[R], cch[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) ch[r] = 0.5f * crow[r], cch[r] = 0.5f * ccol[r];
-        grad_tile<R>(urow, vcol, ch, cch, acc_r, acc_r_hi, acc_c);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
-        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) + cols;
+        for (int r = 0; r < R; ++r) out[r] = (acc_r[r] + acc_r_hi[r]) + __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sts_vec<R>(sh.part[warp] + lane * R, out);
     }
     named_bar_sync(bar, 128);
     float sum2 = 0.f;
@@ -445,10 +466,11 @@ __global__ void __launch_bounds__(G * 128 + 96, 1)
 ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xm,
                     const __grid_constant__ CUtensorMap map_w, const RankerFusedParams p) {
     extern __shared__ unsigned char rf_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rf_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (aligned by an offset on the __shared__ array itself: a round trip through uintptr_t makes every access a generic LD / ST)
+    unsigned char* base = rf_smem_raw + ((1024u - (smem_u32(rf_smem_raw) & 1023u)) & 1023u);
     unsigned char* fring = base;                                  // forward copies: 128-byte swizzle, 16-byte atoms
     unsigned char* dring = fring + RF_NSF * RF_SLOT_BYTES;        // gradient copies: 128-byte swizzle, 32-byte atoms
-    unsigned char* wsm = dring + RF_NSD * RF_SLOT_BYTES;
+    unsigned char* wsm = dring + RF_NSD * RF_QSLOT_BYTES;
     unsigned char* dz = wsm + RF_W_BYTES;
     RfGroup* groups = reinterpret_cast<RfGroup*>(dz + RF_NDZ * RF_DZ_TILE_BYTES);
     RfCtl& ctl = *reinterpret_cast<RfCtl*>(groups + G);
@@ -497,6 +519,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         float ynext = p.pad;
         if (g < nsl) ynext = ld_stream(p.y_true + (size_t)((int)blockIdx.x + g * (int)gridDim.x) * RF_DOCS + gt);
         int it = 0;
+        if (RF_STAGGER_NS > 0 && g > 0 && nsl > G) __nanosleep((unsigned)(g * RF_STAGGER_NS));
         for (int k = g; k < nsl; k += G, ++it) {
             const int slate = (int)blockIdx.x + k * (int)gridDim.x;
             const float yv = ynext;
@@ -507,6 +530,12 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             float a[RF_H];
             tmem_ld32(tmem + (unsigned)(g * RF_H) + ((unsigned)(w * 32) << 16), a);
             tc_fence_before();
+#if RF_EARLY_F
+            // Z is in registers: the group's next forward MMA may go.  The F ring then drains as fast as HBM delivers instead of
+            // at the pace of the groups; the price is the distance in L2 between a chunk's first read and its second (by the
+            // gradient job, (2 G + 1) slates x 148 SMs later), which the eviction hints of the loader have to carry.
+            mbar_arrive(&ctl.zfree[g]);
+#endif
             float sv = p.b3;
 #pragma unroll
             for (int j = 0; j < RF_H; ++j) {
@@ -597,6 +626,9 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 }
                 named_bar_sync(bar, 128);
                 float gsum;
+#ifdef RF_EXP_NO_LOSS
+                if (m > 0) { gsum = sv; slate_val = 0.f; } else
+#endif
                 if (!fact) {
                     const float si = valid ? sh.u[dst] : 0.f;
                     float sum = 0.f;
@@ -606,13 +638,16 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     if (valid) gsum = rf_direct_grad_sum(sh.u, sh.c, m, scale, si, sh.c[dst], p.eps, clamp_pairs);
                 } else if (m > 96) {
                     gsum = rf_sym_slate<4>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
-                } else if (m > 64) {
+                } else {                                          // (no R = 2 copy for short slates: code size)
                     gsum = rf_sym_slate<3>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
-                } else {
-                    gsum = rf_sym_slate<2>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
                 }
                 ds = valid ? p.alpha * gsum : 0.f;                // d loss / d score of this doc
             }
+#if !RF_EARLY_F
+            // The group's next forward MMA may go (it then runs while dZ is written, ahead of this slate's gradient job in
+            // the tensor pipe).
+            mbar_arrive(&ctl.zfree[g]);
+#endif
             ds_sum += ds;
             if (gt == 0) {
                 p.slate_ndcg[slate] = slate_val;
@@ -637,11 +672,12 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
             mbar_arrive(&ctl.dzfull[tile]);
-            // only now may the group's next forward MMA go: run earlier, its feature chunks would be read from HBM so long
-            // before their second (L2) read by the gradient job that they are evicted in between
-            mbar_arrive(&ctl.zfree[g]);
+#ifdef RF_EXP_NO_BFLY
+            acc_bc += dzv[lane & 31 & 0] + dzv[7]; acc_w3 += a[3];
+#else
             acc_bc += warp_transpose_sum(dzv, lane);
             acc_w3 += warp_transpose_sum(a, lane);
+#endif
         }
         // the group's fp32 sums -> its own shared arrays (read after the CTA barrier below)
         const float ds_w = warp_sum(ds_sum);
@@ -649,43 +685,62 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         sh.part[w][32 + lane] = acc_w3;
         if (lane == 0) sh.part[w][64] = ds_w, sh.part[w][65] = val_sum;       // (val_sum: thread 0 of the group only)
     } else if (warp_id == 4 * G) {
-        // ================= loader: one thread, two rings, polled ==========================================================
-        if (lane == 0) {
+        // ================= loader: two rings, polled (the whole warp walks the loop, one lane issues the copies) =============
+        if (elect_one()) {
             mbar_expect_tx(&ctl.wfull, (unsigned)nch * RF_W_CHUNK_BYTES);
             for (int ck = 0; ck < nch; ++ck) tma_load_2d(wsm + ck * RF_W_CHUNK_BYTES, &map_w, ck * RF_CHUNK, 0, &ctl.wfull);
-            // the forward copy of a chunk is read again (by the gradient job) some 50 MB of traffic later: keep it in L2
-            // until then, and let the second read release it
-            uint64_t keep, drop;
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(drop));
-            const int total = nsl * nch;
-            int fn = 0, fk = 0, fc = 0, fslot = 0, fuse = 0;      // F ring: chunk counter, slate, chunk, slot, use of the slot
-            int dn = 0, dk = 0, dc = 0, dslot = 0, duse = 0;
-            unsigned idle = 0;
-            while (fn < total || dn < total) {
-                bool did = false;
-                if (fn < total && (fuse == 0 || mbar_test(&ctl.empty_f[fslot], (unsigned)(fuse - 1) & 1u))) {
+        }
+        __syncwarp();
+        // the forward copy of a chunk is read again (by the gradient job) some 50 MB of traffic later: keep it in L2
+        // until then, and let the second read release it
+        uint64_t keep, drop;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(drop));
+        const int total = nsl * nch, total_d = nsl * (RF_DOCS / RF_QDOCS);
+        int fn = 0, fk = 0, fc = 0, fslot = 0, fuse = 0;          // F ring: chunk counter, slate, chunk, slot, use of the slot
+        int dn = 0, dk = 0, dc = 0, dslot = 0, duse = 0;
+        unsigned idle = 0;
+        while (fn < total || dn < total_d) {
+            bool did = false;
+            // forward chunks first: they are the HBM reads, and a late one stalls a compute group at its next slate
+            while (fn < total && (fuse == 0 || __all_sync(LTR_FULL_MASK, mbar_test(&ctl.empty_f[fslot], (unsigned)(fuse - 1) & 1u)))) {
+                if (elect_one()) {
                     mbar_expect_tx(&ctl.full_f[fslot], RF_SLOT_BYTES);
                     tma_load_2d_hint(fring + fslot * RF_SLOT_BYTES, &map_x, fc * RF_CHUNK, ((int)blockIdx.x + fk * (int)gridDim.x) * RF_DOCS,
                                      &ctl.full_f[fslot], keep);
-                    ++fn;
-                    if (++fc == nch) fc = 0, ++fk;
-                    if (++fslot == RF_NSF) fslot = 0, ++fuse;
-                    did = true;
                 }
-                // the gradient copy of a slate goes after its forward copy (it is meant to hit L2)
-                if (dn < total && (fk > dk || fn == total) &&
-                    (duse == 0 || mbar_test(&ctl.empty_d[dslot], (unsigned)(duse - 1) & 1u))) {
-                    mbar_expect_tx(&ctl.full_d[dslot], RF_SLOT_BYTES);
-                    tma_load_2d_hint(dring + dslot * RF_SLOT_BYTES, &map_xm, dc * RF_CHUNK, ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS,
-                                     &ctl.full_d[dslot], drop);
-                    ++dn;
-                    if (++dc == nch) dc = 0, ++dk;
-                    if (++dslot == RF_NSD) dslot = 0, ++duse;
-                    did = true;
+                __syncwarp();
+                ++fn;
+                if (++fc == nch) fc = 0, ++fk;
+                if (++fslot == RF_NSF) fslot = 0, ++fuse;
+                did = true;
+            }
+            // the gradient copy of a slate goes after its forward copy (it is meant to hit L2): 32 docs x all chunks per slot
+            if (dn < total_d && (fk > dk || fn == total) &&
+                (duse == 0 || __all_sync(LTR_FULL_MASK, mbar_test(&ctl.empty_d[dslot], (unsigned)(duse - 1) & 1u)))) {
+                if (elect_one()) {
+                    mbar_expect_tx(&ctl.full_d[dslot], (unsigned)nch * RF_QBOX_BYTES);
+                    const int row0 = ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS + dc * RF_QDOCS;
+#ifdef RF_EXP_NO_DLOAD
+                    for (int ck = 1; ck < nch; ++ck) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&ctl.full_d[dslot])), "r"(RF_QBOX_BYTES) : "memory");
+                    tma_load_2d_hint(dring + dslot * RF_QSLOT_BYTES, &map_xm, 0, 0, &ctl.full_d[dslot], drop);
+#else
+                    for (int ck = 0; ck < nch; ++ck)
+                        tma_load_2d_hint(dring + dslot * RF_QSLOT_BYTES + ck * RF_QBOX_BYTES, &map_xm, ck * RF_CHUNK, row0,
+                                         &ctl.full_d[dslot], drop);
+#endif
                 }
-                if (did) idle = 0;
-                else if (++idle > (1u << 28)) __trap();           // a ring that never drains traps instead of hanging the GPU
+                __syncwarp();
+                ++dn;
+                if (++dc == RF_DOCS / RF_QDOCS) dc = 0, ++dk;
+                if (++dslot == RF_NSD) dslot = 0, ++duse;
+                did = true;
+            }
+            if (did) {
+                idle = 0;
+            } else {
+                __nanosleep(64);                                  // nothing to load: leave the issue slots to the compute groups
+                if (++idle > (1u << 24)) __trap();                // a ring that never drains traps instead of hanging the GPU
             }
         }
     } else if (warp_id == 4 * G + 1) {
@@ -704,9 +759,19 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_sw128(fa + (unsigned)slot * RF_SLOT_BYTES, 16, 1024);
                     const uint64_t bdesc = umma_desc_sw128(wa + (unsigned)ck * RF_W_CHUNK_BYTES, 16, 1024);
+                    // a k step = 32 bytes = 2 units of the descriptor's start address; straight-line code (a loop here costs
+                    // ~100 cycles of single-thread bookkeeping per MMA, and the forward job is on every group's critical path)
                     const int steps = min(4, ksteps - 4 * ck);
-                    for (int s = 0; s < steps; ++s)           // a k step = 32 bytes = 2 units of the descriptor's start address
-                        tc_mma_tf32(tmem + (unsigned)(g * RF_H), adesc + (uint64_t)(2 * s), bdesc + (uint64_t)(2 * s), IDESC1, (ck | s) != 0);
+                    const unsigned zc = tmem + (unsigned)(g * RF_H);
+                    tc_mma_tf32(zc, adesc, bdesc, IDESC1, ck != 0);
+                    if (steps == 4) {
+                        tc_mma_tf32(zc, adesc + 2, bdesc + 2, IDESC1, 1);
+                        tc_mma_tf32(zc, adesc + 4, bdesc + 4, IDESC1, 1);
+                        tc_mma_tf32(zc, adesc + 6, bdesc + 6, IDESC1, 1);
+                    } else {
+                        if (steps > 1) tc_mma_tf32(zc, adesc + 2, bdesc + 2, IDESC1, 1);
+                        if (steps > 2) tc_mma_tf32(zc, adesc + 4, bdesc + 4, IDESC1, 1);
+                    }
                     tc_commit(&ctl.empty_f[slot]);
                     if (ck == nch - 1) tc_commit(&ctl.zfull[g]);
                 }
@@ -716,29 +781,32 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
     } else {
         // ================= D issuer: gradient MMAs, accumulating in slate order ==============================================
-        constexpr unsigned IDESC2 = umma_idesc_tf32(64, RF_CHUNK, 0, 1);
+        const unsigned idesc2 = umma_idesc_tf32(64, nch * RF_CHUNK, 0, 1);       // N = all feature chunks at once
         const unsigned dza = smem_u32(dz), dra = smem_u32(dring);
         int slot = 0, use = 0;
         for (int k = 0; k < nsl; ++k) {
             const int tile = k % RF_NDZ, tuse = k / RF_NDZ;
             mbar_wait_bounded(&ctl.dzfull[tile], (unsigned)tuse & 1u);
             tc_fence_after();
-            for (int ck = 0; ck < nch; ++ck) {
+            for (int q = 0; q < RF_DOCS / RF_QDOCS; ++q) {
                 mbar_wait_bounded(&ctl.full_d[slot], (unsigned)use & 1u);
                 tc_fence_after();
                 if (elect_one()) {
-                    // A: K-major, 8 docs = 32 bytes (2 address units) inside the 128-byte row of doc chunk ks / 4, chunks 4 KB
-                    // (256 units) apart (rows 32..63 of the tile: whatever follows, never read back); B: the X chunk MN-major:
-                    // 8 docs = two groups of 4 rows = 1 KB (64 units)
-                    const uint64_t adesc = umma_desc_sw128(dza + (unsigned)tile * RF_DZ_TILE_BYTES, 16, 1024);
-                    const uint64_t bdesc = umma_desc(dra + (unsigned)slot * RF_SLOT_BYTES, RF_SLOT_BYTES, 512, 1u);
-                    const unsigned dcol = tmem_g + (unsigned)(ck * RF_CHUNK);
+                    // A: dZ^T K-major, doc quarter q = one 4 KB chunk of the tile, 8 docs = 32 bytes (2 address units) inside its
+                    // 128-byte rows (rows 32..63 of the M = 64 tile: whatever follows, never read back).  Read ONCE per k step:
+                    // the MMA spans all feature chunks (operand reads from shared memory are what bounds this kernel).
+                    // B: the X quarter MN-major: feature chunks 4 KB apart (leading-dimension offset), 8 docs = two groups of
+                    // 4 rows = 1 KB (64 units).
+                    const uint64_t adesc = umma_desc_sw128(dza + (unsigned)tile * RF_DZ_TILE_BYTES + (unsigned)q * RF_DZ_CHUNK_BYTES, 16, 1024);
+                    const uint64_t bdesc = umma_desc(dra + (unsigned)slot * RF_QSLOT_BYTES, RF_QBOX_BYTES, 512, 1u);
 #pragma unroll
-                    for (int ks = 0; ks < RF_DOCS / 8; ++ks)
-                        tc_mma_tf32(dcol, adesc + (uint64_t)((ks >> 2) * (RF_DZ_CHUNK_BYTES >> 4) + (ks & 3) * 2), bdesc + (uint64_t)(ks * 64),
-                                    IDESC2, (k > 0 || ks > 0));
+                    for (int s = 0; s < RF_QDOCS / 8; ++s)
+#ifdef RF_EXP_NO_DMMA
+                        if (k < 0)
+#endif
+                        tc_mma_tf32(tmem_g, adesc + (uint64_t)(s * 2), bdesc + (uint64_t)(s * 64), idesc2, (k > 0 || q > 0 || s > 0));
                     tc_commit(&ctl.empty_d[slot]);
-                    if (ck == nch - 1) {
+                    if (q == RF_DOCS / RF_QDOCS - 1) {
                         tc_commit(&ctl.dzfree[tile]);
                         tc_commit(&ctl.dzmine[k % G]);
                         if (k == nsl - 1) tc_commit(&ctl.alldone);
@@ -834,6 +902,53 @@ __global__ void __launch_bounds__(32 * RF_RED_WARPS) ranker_fused_reduce_kernel(
     }
 }
 
+// Measurement probe: what the TMA stream of feature tiles delivers on its own (no MMA, no consumer): every CTA keeps
+// `slots` copies in flight over its slates.  mode 0: [128 docs][32 floats] boxes through a tensor map (the F ring's copies),
+// mode 1: the same bytes as contiguous 4 KB bulk copies (what a layout-free stream of the same tensor reaches).
+__global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant__ CUtensorMap map, const float* X, int B, int F, int slots,
+                                                          int mode) {
+    extern __shared__ unsigned char rf_smem_raw[];
+    // (aligned by an offset on the __shared__ array itself: a round trip through uintptr_t makes every access a generic LD / ST)
+    unsigned char* base = rf_smem_raw + ((1024u - (smem_u32(rf_smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int nsl = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nch = (F + RF_CHUNK - 1) / RF_CHUNK;
+    const int slate_bytes = RF_DOCS * F * 4;
+    const int per = mode == 0 ? nch : (slate_bytes + 4095) / 4096;        // copies per slate
+    const int total = nsl * per;
+    int slot = 0, use = 0, k = 0, c = 0;
+    for (int n = 0; n < total; ++n) {
+        if (use >= 1) mbar_wait_bounded(&full[slot], (unsigned)(use - 1) & 1u);
+        if (elect_one()) {
+            const int slate = (int)blockIdx.x + k * (int)gridDim.x;
+            if (mode == 0) {
+                mbar_expect_tx(&full[slot], RF_SLOT_BYTES);
+                tma_load_2d(base + slot * RF_SLOT_BYTES, &map, c * RF_CHUNK, slate * RF_DOCS, &full[slot]);
+            } else {
+                const int off = c * 4096, len = min(4096, slate_bytes - off);
+                mbar_expect_tx(&full[slot], (unsigned)len);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(base + slot * RF_SLOT_BYTES)),
+                             "l"(reinterpret_cast<const unsigned char*>(X) + (size_t)slate * slate_bytes + off), "r"(len),
+                             "r"(smem_u32(&full[slot]))
+                             : "memory");
+            }
+        }
+        __syncwarp();
+        if (++c == per) c = 0, ++k;
+        if (++slot == slots) slot = 0, ++use;
+    }
+    for (int i = 0; i < slots && i < total; ++i) {                   // drain: the last copy into every slot
+        const int uses = (total - i + slots - 1) / slots;
+        mbar_wait_bounded(&full[i], (unsigned)(uses - 1) & 1u);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -896,7 +1011,7 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     if (grid > B) grid = B;
     CUtensorMap map_x, map_xm, map_w;
     if (int rc = make_map(&map_x, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map(&map_xm, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    if (int rc = make_map(&map_xm, X, (unsigned long long)B * RF_DOCS, F, RF_QDOCS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     if (int rc = make_map(&map_w, Wc, RF_H, F, RF_H, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     RankerFusedParams p;
     p.y_true = y_true; p.bc = bc; p.w3 = w3; p.b3 = b3; p.B = B; p.F = F;
@@ -907,7 +1022,7 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
     p.grid = grid;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    constexpr size_t RF_SMEM = 1024 + (size_t)(RF_NSF + RF_NSD) * RF_SLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
+    constexpr size_t RF_SMEM = 1024 + (size_t)RF_NSF * RF_SLOT_BYTES + (size_t)RF_NSD * RF_QSLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
                                (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
     static_assert(RF_SMEM <= 232448, "ranker_fused_kernel: shared memory of one CTA");
     static_assert((size_t)RF_G * sizeof(RfGroup) >= RF_DZ_CHUNK_BYTES, "rows 32..63 of the last dZ chunk alias the group structs");
@@ -930,4 +1045,20 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)");
     rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)") : 0;
+}
+
+// Feature-tile TMA stream on its own (measurement; see probe_tma_kernel): bytes moved = B * 128 * F * 4.
+LTR_API int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mode, void* stream) {
+    using namespace ltr;
+    if (!X || B <= 0 || F < 4 || F > RF_MAX_F || F % 4 || slots < 1 || slots > 13 || mode < 0 || mode > 1)
+        return set_error(LTR_EINVAL, "ltr_probe_tma_stream: bad arguments");
+    CUtensorMap map;
+    if (int rc = make_map(&map, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    int grid = device_sm_count();
+    if (grid > B) grid = B;
+    const int smem = 1024 + slots * RF_SLOT_BYTES;
+    LTR_CUDA(cudaFuncSetAttribute(probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_tma_kernel<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map, X, B, F, slots, mode);
+    const int rc = (int)cudaGetLastError();
+    return rc ? set_cuda_error(rc, "ltr_probe_tma_stream") : 0;
 }
