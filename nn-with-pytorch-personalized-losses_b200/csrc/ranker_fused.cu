@@ -14,18 +14,19 @@
 //
 // One persistent, warp-specialised CTA per SM; a slate of 128 docs = one 128-row MMA tile.  The CTA's slates are dealt
 // round robin to G compute groups of 4 warps (thread = doc, warp = one TMEM lane quarter), so G slates are in different
-// phases at any time and their latencies hide each other; three single-thread roles feed them:
-//   loader      TMA: the features arrive in chunks of [128 docs][32 features] = 16 KB through two rings of slots --
-//               the F ring (forward copies, 128-byte swizzle of 16-byte atoms: X is the K-major A operand of the forward
-//               MMA; these are the HBM reads) and the D ring (the same chunk again, out of L2, with the 128-byte swizzle
-//               of 32-byte atoms: the gradient MMA reads it MN-major -- docs are its K dimension -- and that is the only
-//               layout the tensor core transposes 32-bit operands from).  X is read from HBM ONCE.
-//   F issuer    tcgen05.mma kind::tf32, M = 128, N = 32, K = F: Z[128, 32] of the slate into its group's TMEM columns as
-//               soon as the group has taken the previous Z out; every chunk's slot is released by tcgen05.commit.
-//   D issuer    tcgen05.mma kind::tf32, M = 64, N = 32 per feature chunk, K = 128 docs, ACCUMULATING over all of the
+// phases at any time; three warp-uniform roles (one elected lane issues) feed them:
+//   loader      TMA through two rings.  F ring: chunks of [128 docs][32 features] = 16 KB with the 128-byte swizzle of
+//               16-byte atoms: X is the K-major A operand of the forward MMA; these are the HBM reads (L2 evict_last).
+//               D ring: the same bytes again, out of L2 (evict_first), as slots of [32 docs][all feature chunks] = 5 x 4 KB
+//               with the 128-byte swizzle of 32-byte atoms: the gradient MMA reads them MN-major -- docs are its K
+//               dimension -- and that is the only layout the tensor core transposes 32-bit operands from.  X is read from
+//               HBM ONCE (ncu: 290 MB for 285 MB of features).
+//   F issuer    tcgen05.mma kind::tf32, M = 128, N = 32, K = F: Z[128, 32] of the slate into its group's TMEM columns, when
+//               the group is through with the loss of its previous slate; every chunk's slot is released by tcgen05.commit.
+//   D issuer    tcgen05.mma kind::tf32, M = 64, N = 32 x chunks (160), K = 32 docs per slot, ACCUMULATING over all of the
 //               CTA's slates in TMEM (in slate order: bitwise reproducible): A = dZ^T of the slate (rows 0..31, K-major,
 //               written by the group; rows 32..63 of the M = 64 tile alias whatever follows and land in accumulator rows
-//               nobody reads), B = the X chunk read MN-major.
+//               nobody reads), B = the X slot read MN-major.  One MMA spans all features, so A is read once per k step.
 //   group       tcgen05.ld: thread d owns row d of Z: sigmoid, dot with w3 -> the doc's score (a[32] stays in registers);
 //               approxNDCG of the slate exactly as the K1 kernel computes it (approx_pair_tiles.cuh: factorised pair
 //               sigmoid, every unordered pair once per pass, block-circulant pair schedule over the group's 4 warps;
@@ -34,6 +35,9 @@
 //               (sum ds = 0 for approxNDCG), so they do NOT go through tf32: a butterfly of warp shuffles leaves lane j
 //               with the warp's sum for hidden unit j, accumulated in fp32 over the group's slates.
 //   end         the CTA's accumulators -> partials in global memory; a second small kernel adds the partials in CTA order.
+// The barrier protocol (mbarrier parity waits are only sound within one phase) is modelled in tests/test_ranker_protocol_cpu.py.
+// Bound: every feature byte crosses L2 -> SM twice (570 MB per 4096 x 128 x 136 batch; `ltr_probe_tma_stream` measures
+// 6.4 TB/s for the HBM pass and 11.5 TB/s for an L2-resident pass on this part), see DESIGN.md.
 // Precision: tf32 operands (10-bit mantissa), fp32 accumulation: scores agree with the fp32 torch modules to ~1e-3
 // relative (the tolerance the tests state), the loss arithmetic itself is the fp32 / MUFU arithmetic of K1.
 #include <cuda.h>
@@ -43,7 +47,7 @@
 #include "ltr_host.h"
 
 #ifndef RF_GROUPS
-#define RF_GROUPS 3          // compute groups per CTA (A/B knob; measured 4096 x 128 x 136: 2 groups .. us, 3 .. us, 4 .. us)
+#define RF_GROUPS 3          // compute groups per CTA (A/B knob; measured 4096 x 128 x 136: 2 groups 85.3 us, 3: 84.6 us, 4: 86.5 us)
 #endif
 
 namespace ltr {
@@ -67,13 +71,10 @@ constexpr int RF_NSF = 5;                                       // F ring: one s
 constexpr int RF_QDOCS = 32;                                    // D ring: a slot = 32 docs x ALL feature chunks ...
 constexpr int RF_QBOX_BYTES = RF_QDOCS * 128;                   // ... 4 KB per chunk: [32 docs][32 floats] ...
 constexpr int RF_QSLOT_BYTES = RF_KCHUNKS * RF_QBOX_BYTES;      // ... 20 KB per slot, so that one MMA spans all N = 160 features
-constexpr int RF_NSD = (RF_GROUPS <= 3) ? 3 : 4;                // D ring of doc quarters (L2 hits); shared memory decides
+constexpr int RF_NSD = 3;                                       // D ring of doc quarters (L2 hits); shared memory decides
 #ifndef RF_EARLY_F
-#define RF_EARLY_F 1
-#endif
-#ifndef RF_STAGGER_NS
-#define RF_STAGGER_NS 2500   // group g starts g x this late: the groups then stay out of phase, and the tensor / TMA work of one
-                             // overlaps the arithmetic of the others (in lockstep they alternate between the two)
+#define RF_EARLY_F 0          // 1: the group's next forward MMA goes as soon as Z is in registers (measured: same time, 25 % of
+                             // the gradient job's second reads then miss L2)
 #endif
 constexpr int RF_THREADS = RF_G * 128 + 96;                     // compute groups + loader, F issuer, D issuer warps
 constexpr int RF_TMEM_COLS = (RF_G * RF_H + RF_N2 <= 256) ? 256 : 512;
@@ -519,7 +520,6 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         float ynext = p.pad;
         if (g < nsl) ynext = ld_stream(p.y_true + (size_t)((int)blockIdx.x + g * (int)gridDim.x) * RF_DOCS + gt);
         int it = 0;
-        if (RF_STAGGER_NS > 0 && g > 0 && nsl > G) __nanosleep((unsigned)(g * RF_STAGGER_NS));
         for (int k = g; k < nsl; k += G, ++it) {
             const int slate = (int)blockIdx.x + k * (int)gridDim.x;
             const float yv = ynext;
@@ -626,9 +626,6 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 }
                 named_bar_sync(bar, 128);
                 float gsum;
-#ifdef RF_EXP_NO_LOSS
-                if (m > 0) { gsum = sv; slate_val = 0.f; } else
-#endif
                 if (!fact) {
                     const float si = valid ? sh.u[dst] : 0.f;
                     float sum = 0.f;
@@ -672,12 +669,8 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
             mbar_arrive(&ctl.dzfull[tile]);
-#ifdef RF_EXP_NO_BFLY
-            acc_bc += dzv[lane & 31 & 0] + dzv[7]; acc_w3 += a[3];
-#else
             acc_bc += warp_transpose_sum(dzv, lane);
             acc_w3 += warp_transpose_sum(a, lane);
-#endif
         }
         // the group's fp32 sums -> its own shared arrays (read after the CTA barrier below)
         const float ds_w = warp_sum(ds_sum);
@@ -721,14 +714,9 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (elect_one()) {
                     mbar_expect_tx(&ctl.full_d[dslot], (unsigned)nch * RF_QBOX_BYTES);
                     const int row0 = ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS + dc * RF_QDOCS;
-#ifdef RF_EXP_NO_DLOAD
-                    for (int ck = 1; ck < nch; ++ck) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&ctl.full_d[dslot])), "r"(RF_QBOX_BYTES) : "memory");
-                    tma_load_2d_hint(dring + dslot * RF_QSLOT_BYTES, &map_xm, 0, 0, &ctl.full_d[dslot], drop);
-#else
                     for (int ck = 0; ck < nch; ++ck)
                         tma_load_2d_hint(dring + dslot * RF_QSLOT_BYTES + ck * RF_QBOX_BYTES, &map_xm, ck * RF_CHUNK, row0,
                                          &ctl.full_d[dslot], drop);
-#endif
                 }
                 __syncwarp();
                 ++dn;
@@ -801,9 +789,6 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     const uint64_t bdesc = umma_desc(dra + (unsigned)slot * RF_QSLOT_BYTES, RF_QBOX_BYTES, 512, 1u);
 #pragma unroll
                     for (int s = 0; s < RF_QDOCS / 8; ++s)
-#ifdef RF_EXP_NO_DMMA
-                        if (k < 0)
-#endif
                         tc_mma_tf32(tmem_g, adesc + (uint64_t)(s * 2), bdesc + (uint64_t)(s * 64), idesc2, (k > 0 || q > 0 || s > 0));
                     tc_commit(&ctl.empty_d[slot]);
                     if (q == RF_DOCS / RF_QDOCS - 1) {
@@ -906,7 +891,7 @@ __global__ void __launch_bounds__(32 * RF_RED_WARPS) ranker_fused_reduce_kernel(
 // `slots` copies in flight over its slates.  mode 0: [128 docs][32 floats] boxes through a tensor map (the F ring's copies),
 // mode 1: the same bytes as contiguous 4 KB bulk copies (what a layout-free stream of the same tensor reaches).
 __global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant__ CUtensorMap map, const float* X, int B, int F, int slots,
-                                                          int mode) {
+                                                          int mode, int reps) {
     extern __shared__ unsigned char rf_smem_raw[];
     // (aligned by an offset on the __shared__ array itself: a round trip through uintptr_t makes every access a generic LD / ST)
     unsigned char* base = rf_smem_raw + ((1024u - (smem_u32(rf_smem_raw) & 1023u)) & 1023u);
@@ -920,7 +905,7 @@ __global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant_
     const int nch = (F + RF_CHUNK - 1) / RF_CHUNK;
     const int slate_bytes = RF_DOCS * F * 4;
     const int per = mode == 0 ? nch : (slate_bytes + 4095) / 4096;        // copies per slate
-    const int total = nsl * per;
+    const int total = nsl * per * reps;                               // reps > 1: the same slates again (L2-resident runs)
     int slot = 0, use = 0, k = 0, c = 0;
     for (int n = 0; n < total; ++n) {
         if (use >= 1) mbar_wait_bounded(&full[slot], (unsigned)(use - 1) & 1u);
@@ -940,7 +925,7 @@ __global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant_
             }
         }
         __syncwarp();
-        if (++c == per) c = 0, ++k;
+        if (++c == per) c = 0, k = (k + 1 == nsl) ? 0 : k + 1;
         if (++slot == slots) slot = 0, ++use;
     }
     for (int i = 0; i < slots && i < total; ++i) {                   // drain: the last copy into every slot
@@ -1047,10 +1032,10 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     return rc ? set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)") : 0;
 }
 
-// Feature-tile TMA stream on its own (measurement; see probe_tma_kernel): bytes moved = B * 128 * F * 4.
-LTR_API int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mode, void* stream) {
+// Feature-tile TMA stream on its own (measurement; see probe_tma_kernel): bytes moved = reps * B * 128 * F * 4.
+LTR_API int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mode, int reps, void* stream) {
     using namespace ltr;
-    if (!X || B <= 0 || F < 4 || F > RF_MAX_F || F % 4 || slots < 1 || slots > 13 || mode < 0 || mode > 1)
+    if (!X || B <= 0 || F < 4 || F > RF_MAX_F || F % 4 || slots < 1 || slots > 13 || mode < 0 || mode > 1 || reps < 1)
         return set_error(LTR_EINVAL, "ltr_probe_tma_stream: bad arguments");
     CUtensorMap map;
     if (int rc = make_map(&map, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
@@ -1058,7 +1043,7 @@ LTR_API int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mo
     if (grid > B) grid = B;
     const int smem = 1024 + slots * RF_SLOT_BYTES;
     LTR_CUDA(cudaFuncSetAttribute(probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    probe_tma_kernel<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map, X, B, F, slots, mode);
+    probe_tma_kernel<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map, X, B, F, slots, mode, reps);
     const int rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_probe_tma_stream") : 0;
 }

@@ -66,7 +66,7 @@ _SIGNATURES = {
     "ltr_baseline_csv_load": (c_int, [c_char_p, c_longlong, c_longlong, c_int, c_int, _P, _P]),
     "ltr_probe_sfu": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
     "ltr_probe_fma": (c_int, [_P, c_int, POINTER(c_longlong), _P]),
-    "ltr_probe_tma_stream": (c_int, [_P, c_int, c_int, c_int, c_int, _P]),
+    "ltr_probe_tma_stream": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 
 _lib = None
