@@ -307,6 +307,20 @@ int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, const flo
                                   void* workspace, void* stream);
 
 /*
+ * The same step from the module's own six parameters, in one call: the fold (Wc = W2 W1, bc = W2 b1 + b2), the fused
+ * kernel and the unfold of the gradients all run on the device (four launches chained by programmatic stream
+ * serialization); nothing is read back to the host.      architeture/tripleLayer.py:8-10 (l1: F -> 64, l2: 64 -> 32, l3: 32 -> 1)
+ *   W1 [64, F], b1 [64], W2 [32, 64], b2 [32], W3 [1, 32], b3 [1] device pointers; gW1 .. gb3 the matching gradients (out).
+ *   scratch : ltr_triple_step_scratch_bytes(B, 128, F) bytes, 16-byte aligned.
+ */
+size_t ltr_triple_step_scratch_bytes(int B, int n, int F);
+int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const float* W3, const float* b3, int B, int n, int F, float alpha, float eps,
+                                float pad_value, const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg,
+                                float* loss, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                                void* scratch, size_t scratch_bytes, void* workspace, void* stream);
+
+/*
  * Slate ingestion (HOST code, host pointers).  replaces utils/dataset.py:33-101 (get_data, load_baseline_file)
  *
  * svmlight / LETOR text "label qid:ID idx:val ... # comment" -> query-major padded arrays.  A new query starts wherever

@@ -84,7 +84,8 @@ struct RankerFusedParams {
     const float* y_true;     // [B, 128]
     const float* bc;         // [32]
     const float* w3;         // [32]
-    float b3;
+    float b3;                // used when b3_ptr is null
+    const float* b3_ptr;     // [1] (the whole-step entry: the bias stays on the device)
     int B, F;
     float alpha, eps, pad;
     const double* disc_prefix;   // P[r] = sum_{q<=r} 1/log2(1+q), r = 0..128
@@ -495,9 +496,10 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    asm volatile("griddepcontrol.launch_dependents;");           // the reduce kernel's blocks may become resident (they wait)
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // (whole-step entry: Wc / bc come from the fold kernel before us)
     if (tid < RF_H) ctl.w3[tid] = __ldg(p.w3 + tid), ctl.bc[tid] = __ldg(p.bc + tid);
     for (int i = tid; i <= RF_DOCS; i += blockDim.x) ctl.disc[i] = (float)p.disc_prefix[i];
-    asm volatile("griddepcontrol.launch_dependents;");           // the reduce kernel's blocks may become resident (they wait)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -517,6 +519,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const float coef = (1.0f / (float)p.B) * (1.0f / kLn2);
         float acc_bc = 0.f, acc_w3 = 0.f;                         // lane j: this warp's share of dbc[j], dw3[j]
         float ds_sum = 0.f, val_sum = 0.f;
+        const float b3 = p.b3_ptr ? __ldg(p.b3_ptr) : p.b3;
         float ynext = p.pad;
         if (g < nsl) ynext = ld_stream(p.y_true + (size_t)((int)blockIdx.x + g * (int)gridDim.x) * RF_DOCS + gt);
         int it = 0;
@@ -536,7 +539,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             // gradient job, (2 G + 1) slates x 148 SMs later), which the eviction hints of the loader have to carry.
             mbar_arrive(&ctl.zfree[g]);
 #endif
-            float sv = p.b3;
+            float sv = b3;
 #pragma unroll
             for (int j = 0; j < RF_H; ++j) {
                 const float z = a[j] + ctl.bc[j];
@@ -887,6 +890,60 @@ __global__ void __launch_bounds__(32 * RF_RED_WARPS) ranker_fused_reduce_kernel(
     }
 }
 
+// ---- the linear part of the net, folded and unfolded on the device (whole-step entry) -----------------------------------------
+constexpr int RF_H1 = 64;                                        // l1: F -> 64, l2: 64 -> 32 (architeture/tripleLayer.py:8-10)
+// Wc = W2 W1 [32, F], bc = W2 b1 + b2 [32]; one thread per entry, sums in index order
+__global__ void __launch_bounds__(256) ranker_fold_kernel(const float* W1, const float* b1, const float* W2, const float* b2, int F,
+                                                          float* Wc, float* bc) {
+    pdl_prologue();
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx < RF_H * F) {
+        const int j = idx / F, f = idx % F;
+        float t = 0.f;
+#pragma unroll 8
+        for (int h = 0; h < RF_H1; ++h) t = fmaf(W2[j * RF_H1 + h], W1[h * F + f], t);
+        Wc[idx] = t;
+    } else if (idx < RF_H * F + RF_H) {
+        const int j = idx - RF_H * F;
+        float t = b2[j];
+#pragma unroll 8
+        for (int h = 0; h < RF_H1; ++h) t = fmaf(W2[j * RF_H1 + h], b1[h], t);
+        bc[j] = t;
+    }
+}
+// dW1 = W2^T gWc [64, F], db1 = W2^T gbc [64], dW2 = gWc W1^T + gbc b1^T [32, 64], db2 = gbc [32], dW3 = gw3 [32]
+__global__ void __launch_bounds__(256) ranker_unfold_kernel(const float* W1, const float* b1, const float* W2, const float* gWc,
+                                                            const float* gbc, const float* gw3, int F, float* gW1, float* gb1,
+                                                            float* gW2, float* gb2, float* gW3) {
+    pdl_prologue();
+    int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx < RF_H1 * F) {
+        const int h = idx / F, f = idx % F;
+        float t = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < RF_H; ++j) t = fmaf(W2[j * RF_H1 + h], gWc[j * F + f], t);
+        gW1[idx] = t;
+        return;
+    }
+    idx -= RF_H1 * F;
+    if (idx < RF_H * RF_H1) {
+        const int j = idx / RF_H1, h = idx % RF_H1;
+        float t = gbc[j] * b1[h];
+        for (int f = 0; f < F; ++f) t = fmaf(gWc[j * F + f], W1[h * F + f], t);
+        gW2[idx] = t;
+        return;
+    }
+    idx -= RF_H * RF_H1;
+    if (idx < RF_H1) {
+        float t = 0.f;
+        for (int j = 0; j < RF_H; ++j) t = fmaf(W2[j * RF_H1 + idx], gbc[j], t);
+        gb1[idx] = t;
+        return;
+    }
+    idx -= RF_H1;
+    if (idx < RF_H) gb2[idx] = gbc[idx], gW3[idx] = gw3[idx];
+}
+
 // Measurement probe: what the TMA stream of feature tiles delivers on its own (no MMA, no consumer): every CTA keeps
 // `slots` copies in flight over its slates.  mode 0: [128 docs][32 floats] boxes through a tensor map (the F ring's copies),
 // mode 1: the same bytes as contiguous 4 KB bulk copies (what a layout-free stream of the same tensor reaches).
@@ -975,6 +1032,76 @@ LTR_API size_t ltr_triple_scratch_bytes(int B, int n, int F) {
     return grid * (ltr::RF_PART + 2 + 2 * ltr::RF_H) * sizeof(float);
 }
 
+namespace ltr {
+
+template <typename... Args>
+static int launch_pdl_args(void (*kernel)(Args...), int grid, int threads, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// argument checks + the main kernel + the partial reduce, shared by the two entries.  `pdl`: the main kernel is launched
+// with programmatic stream serialization (its griddepcontrol.wait then covers the fold kernel before it).
+static int triple_core(const char* who, const float* X, const float* y_true, const float* Wc, const float* bc, const float* w3,
+                       float b3, const float* b3_ptr, int B, int n, int F, float alpha, float eps, float pad_value,
+                       const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg, float* loss, float* gWc, float* gbc,
+                       float* gw3, float* gb3, void* scratch, size_t scratch_bytes, cudaStream_t st, bool pdl) {
+    (void)who;
+    if (n != RF_DOCS) return set_error(LTR_EINVAL, "fused ranker step: slates of exactly 128 docs (one MMA tile)");
+    if (F < 4 || F > RF_MAX_F || F % 4)
+        return set_error(LTR_EINVAL, "fused ranker step: 4 <= F <= 160, F a multiple of 4 (16-byte rows for TMA)");
+    if (disc_len < RF_DOCS + 1) return set_error(LTR_EINVAL, "fused ranker step: discount table shorter than 129");
+    if (!(alpha > 0.f)) return set_error(LTR_EINVAL, "fused ranker step: alpha must be positive");
+    if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wc)) % 16)
+        return set_error(LTR_EINVAL, "fused ranker step: X and Wc must be 16-byte aligned");
+    if (scratch_bytes < ltr_triple_scratch_bytes(B, n, F)) return set_error(LTR_EINVAL, "fused ranker step: scratch too small");
+    int grid = device_sm_count();
+    if (grid > B) grid = B;
+    CUtensorMap map_x, map_xm, map_w;
+    if (int rc = make_map(&map_x, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&map_xm, X, (unsigned long long)B * RF_DOCS, F, RF_QDOCS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    if (int rc = make_map(&map_w, Wc, RF_H, F, RF_H, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    RankerFusedParams p;
+    p.y_true = y_true; p.bc = bc; p.w3 = w3; p.b3 = b3; p.b3_ptr = b3_ptr; p.B = B; p.F = F;
+    p.alpha = alpha; p.eps = eps; p.pad = pad_value; p.disc_prefix = disc_prefix;
+    p.scores = scores; p.slate_ndcg = slate_ndcg; p.loss = loss;
+    p.part = reinterpret_cast<float*>(scratch);
+    p.part_misc = p.part + (size_t)device_sm_count() * RF_PART;
+    p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
+    p.grid = grid;
+    constexpr size_t RF_SMEM = 1024 + (size_t)RF_NSF * RF_SLOT_BYTES + (size_t)RF_NSD * RF_QSLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
+                               (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
+    static_assert(RF_SMEM <= 232448, "ranker_fused_kernel: shared memory of one CTA");
+    static_assert((size_t)RF_G * sizeof(RfGroup) >= RF_DZ_CHUNK_BYTES, "rows 32..63 of the last dZ chunk alias the group structs");
+    LTR_CUDA(cudaFuncSetAttribute(ranker_fused_kernel<RF_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(RF_THREADS);
+    cfg.dynamicSmemBytes = RF_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    int rc = (int)cudaLaunchKernelEx(&cfg, ranker_fused_kernel<RF_G>, map_x, map_xm, map_w, p);
+    if (rc) return set_cuda_error(rc, "fused ranker step (main kernel)");
+    rc = launch_pdl_args(ranker_fused_reduce_kernel, RF_PART / 32 + 3, 32 * RF_RED_WARPS, st, p, gWc, gbc, gw3, gb3);
+    if (rc) return set_cuda_error(rc, "fused ranker step (reduce)");
+    rc = (int)cudaGetLastError();
+    return rc ? set_cuda_error(rc, "fused ranker step") : 0;
+}
+
+}  // namespace ltr
+
 LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, const float* Wc, const float* bc, const float* w3,
                                           float b3, int B, int n, int F, float alpha, float eps, float pad_value,
                                           const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg, float* loss,
@@ -984,52 +1111,47 @@ LTR_API int ltr_triple_approx_ndcg_fwdbwd(const float* X, const float* y_true, c
     if (!X || !y_true || !Wc || !bc || !w3 || !scores || !slate_ndcg || !loss || !gWc || !gbc || !gw3 || !gb3 || !scratch ||
         !workspace || !disc_prefix || B <= 0)
         return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: null pointer or empty batch");
-    if (n != RF_DOCS) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: slates of exactly 128 docs (one MMA tile)");
-    if (F < 4 || F > RF_MAX_F || F % 4)
-        return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: 4 <= F <= 160, F a multiple of 4 (16-byte rows for TMA)");
-    if (disc_len < RF_DOCS + 1) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: discount table shorter than 129");
-    if (!(alpha > 0.f)) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: alpha must be positive");
-    if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wc)) % 16)
-        return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: X and Wc must be 16-byte aligned");
-    if (scratch_bytes < ltr_triple_scratch_bytes(B, n, F)) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_fwdbwd: scratch too small");
-    int grid = device_sm_count();
-    if (grid > B) grid = B;
-    CUtensorMap map_x, map_xm, map_w;
-    if (int rc = make_map(&map_x, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map(&map_xm, X, (unsigned long long)B * RF_DOCS, F, RF_QDOCS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    if (int rc = make_map(&map_w, Wc, RF_H, F, RF_H, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    RankerFusedParams p;
-    p.y_true = y_true; p.bc = bc; p.w3 = w3; p.b3 = b3; p.B = B; p.F = F;
-    p.alpha = alpha; p.eps = eps; p.pad = pad_value; p.disc_prefix = disc_prefix;
-    p.scores = scores; p.slate_ndcg = slate_ndcg; p.loss = loss;
-    p.part = reinterpret_cast<float*>(scratch);
-    p.part_misc = p.part + (size_t)device_sm_count() * RF_PART;
-    p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
-    p.grid = grid;
+    return triple_core("ltr_triple_approx_ndcg_fwdbwd", X, y_true, Wc, bc, w3, b3, nullptr, B, n, F, alpha, eps, pad_value, disc_prefix,
+                       disc_len, scores, slate_ndcg, loss, gWc, gbc, gw3, gb3, scratch, scratch_bytes,
+                       reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+LTR_API size_t ltr_triple_step_scratch_bytes(int B, int n, int F) {
+    if (B <= 0 || F <= 0) return 0;
+    // per-CTA partials, then Wc [32, F], bc [32], gWc [32, F], gbc [32], gw3 [32] (each region 16-byte aligned)
+    return ltr_triple_scratch_bytes(B, n, F) + (size_t)(2 * ltr::RF_H * F + 3 * ltr::RF_H) * sizeof(float);
+}
+
+LTR_API int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, const float* W1, const float* b1, const float* W2,
+                                        const float* b2, const float* W3, const float* b3, int B, int n, int F, float alpha, float eps,
+                                        float pad_value, const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg,
+                                        float* loss, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                                        void* scratch, size_t scratch_bytes, void* workspace, void* stream) {
+    using namespace ltr;
+    if (!X || !y_true || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !scores || !slate_ndcg || !loss || !gW1 || !gb1 || !gW2 || !gb2 ||
+        !gW3 || !gb3 || !scratch || !workspace || !disc_prefix || B <= 0)
+        return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: null pointer or empty batch");
+    if (F < 4 || F > RF_MAX_F || F % 4) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: 4 <= F <= 160, F a multiple of 4");
+    if (scratch_bytes < ltr_triple_step_scratch_bytes(B, n, F)) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: scratch too small");
+    if (reinterpret_cast<uintptr_t>(scratch) % 16) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: scratch must be 16-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    constexpr size_t RF_SMEM = 1024 + (size_t)RF_NSF * RF_SLOT_BYTES + (size_t)RF_NSD * RF_QSLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
-                               (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
-    static_assert(RF_SMEM <= 232448, "ranker_fused_kernel: shared memory of one CTA");
-    static_assert((size_t)RF_G * sizeof(RfGroup) >= RF_DZ_CHUNK_BYTES, "rows 32..63 of the last dZ chunk alias the group structs");
-    LTR_CUDA(cudaFuncSetAttribute(ranker_fused_kernel<RF_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM));
-    ranker_fused_kernel<RF_G><<<grid, RF_THREADS, RF_SMEM, st>>>(map_x, map_xm, map_w, p);
+    const size_t core = ltr_triple_scratch_bytes(B, n, F);
+    float* Wc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + core);
+    float* bc = Wc + RF_H * F;
+    float* gWc = bc + RF_H;
+    float* gbc = gWc + RF_H * F;
+    float* gw3 = gbc + RF_H;
+    ranker_fold_kernel<<<(RF_H * F + RF_H + 255) / 256, 256, 0, st>>>(W1, b1, W2, b2, F, Wc, bc);
     int rc = (int)cudaGetLastError();
-    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd");
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(RF_PART / 32 + 3);
-        cfg.blockDim = dim3(32 * RF_RED_WARPS);
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        rc = (int)cudaLaunchKernelEx(&cfg, ranker_fused_reduce_kernel, p, gWc, gbc, gw3, gb3);
-    }
-    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)");
-    rc = (int)cudaGetLastError();
-    return rc ? set_cuda_error(rc, "ltr_triple_approx_ndcg_fwdbwd (reduce)") : 0;
+    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_step (fold)");
+    rc = triple_core("ltr_triple_approx_ndcg_step", X, y_true, Wc, bc, W3, 0.f, b3, B, n, F, alpha, eps, pad_value, disc_prefix, disc_len,
+                     scores, slate_ndcg, loss, gWc, gbc, gw3, gb3, scratch, core, st, true);
+    if (rc) return rc;
+    const int total = RF_H1 * F + RF_H * RF_H1 + RF_H1 + RF_H;
+    rc = launch_pdl_args(ranker_unfold_kernel, (total + 255) / 256, 256, st, W1, b1, W2, (const float*)gWc, (const float*)gbc,
+                         (const float*)gw3, F, gW1, gb1, gW2, gb2, gW3);
+    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_step (unfold)");
+    return 0;
 }
 
 // Feature-tile TMA stream on its own (measurement; see probe_tma_kernel): bytes moved = reps * B * 128 * F * 4.

@@ -23,43 +23,61 @@ SLATE = 128          # docs per slate of the fused path (one MMA tile)
 MAX_FEATURES = 160   # the fused kernel stages up to 5 chunks of 32 features (MSLR-WEB10K: 136)
 
 
+_scratch_cache = {}          # (device, batch, features) -> uint8 scratch of the step (partials, folded weights): reused, never returned
+
+
+def _scratch(lib, dev, B, n, F):
+    key = (dev, B, F)
+    buf = _scratch_cache.get(key)
+    if buf is None:
+        buf = torch.empty(lib.ltr_triple_step_scratch_bytes(B, n, F), dtype=torch.uint8, device=dev)
+        _scratch_cache.clear()                                # one shape at a time: a training loop has one
+        _scratch_cache[key] = buf
+    return buf
+
+
 class _FusedTripleApproxNDCG(torch.autograd.Function):
+    """forward = the whole step (`ltr_triple_approx_ndcg_step`: fold, fused kernel, unfold -- four launches, ONE library call,
+    nothing read back to the host); the six parameter gradients come out of one flat buffer and are scaled by the incoming
+    gradient of the loss in backward."""
+
     @staticmethod
     def forward(ctx, X, y_true, W1, b1, W2, b2, W3, b3, eps, pad, alpha):
         lib = _lib.load()
         B, n, F = X.shape
         dev = X.device
         with torch.cuda.device(dev):
-            # the linear part of the net folded once per step (64 x 136 and 32 x 64: microseconds of cuBLAS)
-            Wc = (W2.detach() @ W1.detach()).contiguous()
-            bc = (W2.detach() @ b1.detach() + b2.detach()).contiguous()
-            w3 = W3.detach().reshape(-1).contiguous()
+            prm = [t.detach() for t in (W1, b1, W2, b2, W3, b3)]
+            if any(t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev for t in prm):
+                prm = [t.to(dev, torch.float32).contiguous() for t in prm]
+            sizes = [t.numel() for t in prm]
+            # [loss | pad to 4 | gW1 | gb1 | gW2 | gb2 | gW3 | gb3]; scores and per-slate values separately
+            flat = torch.empty(4 + sum(sizes), dtype=torch.float32, device=dev)
+            offs, o = [], 4
+            for sz in sizes:
+                offs.append(o)
+                o += sz
             scores = torch.empty(B, n, dtype=torch.float32, device=dev)
             slate = torch.empty(B, dtype=torch.float32, device=dev)
-            out = torch.empty(1 + 32 * F + 32 + 32 + 1, dtype=torch.float32, device=dev)
-            loss, gWc, gbc, gw3, gb3 = out[0:1], out[1:1 + 32 * F], out[1 + 32 * F:33 + 32 * F], out[33 + 32 * F:65 + 32 * F], out[65 + 32 * F:]
-            nscratch = lib.ltr_triple_scratch_bytes(B, n, F)
-            scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+            scratch = _scratch(lib, dev, B, n, F)
             tab = rt.disc_prefix(dev)
-            _lib.check(lib.ltr_triple_approx_ndcg_fwdbwd(
-                X.data_ptr(), y_true.data_ptr(), Wc.data_ptr(), bc.data_ptr(), w3.data_ptr(), float(b3.detach().reshape(-1)[0]),
-                B, n, F, float(alpha), float(eps), float(pad), tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(),
-                loss.data_ptr(), gWc.data_ptr(), gbc.data_ptr(), gw3.data_ptr(), gb3.data_ptr(), scratch.data_ptr(), nscratch,
-                rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_approx_ndcg_fwdbwd")
-            gWc = gWc.view(32, F)
-            # unfold: z = x (W2 W1)^T + (W2 b1 + b2)
-            ctx.grads = (W2.detach().t() @ gWc, W2.detach().t() @ gbc, gWc @ W1.detach().t() + torch.outer(gbc, b1.detach()),
-                         gbc.clone(), gw3.view(1, 32).clone(), gb3.clone())
+            base = flat.data_ptr()
+            _lib.check(lib.ltr_triple_approx_ndcg_step(
+                X.data_ptr(), y_true.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, float(alpha), float(eps), float(pad),
+                tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(), base, *[base + 4 * o for o in offs],
+                scratch.data_ptr(), scratch.numel(), rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_approx_ndcg_step")
+        ctx.flat, ctx.offs, ctx.shapes = flat, offs, [t.shape for t in prm]
         ctx.scores = scores
         ctx.slate_ndcg = slate
         ctx.mark_non_differentiable(scores)
-        return loss.reshape(()).clone(), scores
+        return flat[0].clone(), scores
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_loss, _grad_scores):
-        g = [t * grad_loss for t in ctx.grads]
-        return (None, None, g[0], g[1], g[2], g[3], g[4], g[5], None, None, None)
+        g = ctx.flat * grad_loss                                  # one launch for all six
+        out = [g[o:o + s.numel()].view(s) for o, s in zip(ctx.offs, ctx.shapes)]
+        return (None, None, out[0], out[1], out[2], out[3], out[4], out[5], None, None, None)
 
 
 def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1., return_scores=False):

@@ -196,3 +196,49 @@ def test_fused_step_large_eps_clamps_pairs():
     X = torch.rand(B, 128, 136, generator=g)
     _, y = make_slates(B, 128, seed=8, min_len=64)
     _fused_vs_reference(net, X, y, alpha=10.0, eps=1e-3, g_tol=3e-2)
+
+
+@pytest.mark.timeout(300)
+def test_folded_entry_equals_whole_step_entry():
+    """`ltr_triple_approx_ndcg_fwdbwd` (caller folds l1 / l2 itself) against `ltr_triple_approx_ndcg_step` (fold and unfold on
+    the device): same scores bit for bit when fed the device-folded weights' torch equivalent to ~1e-6, and gradients that
+    unfold to the same six tensors."""
+    from ltr_b200 import _lib, _runtime as rt
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet, fused_triple_approx_ndcg
+    lib = _lib.load()
+    torch.manual_seed(21)
+    dev = torch.device("cuda", 0)
+    net = TripleLayerNet(136).cuda()
+    B, F = 333, 136
+    g = torch.Generator().manual_seed(21)
+    X = torch.rand(B, 128, F, generator=g).cuda()
+    _, y = make_slates(B, 128, seed=21, min_len=40)
+    y = y.cuda()
+    loss, scores = fused_triple_approx_ndcg(net, X, y, alpha=10.0, return_scores=True)
+    loss.backward()
+    W1, b1, W2, b2, W3, b3 = [p.detach() for p in (net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight, net.l3.bias)]
+    Wc = (W2 @ W1).contiguous()
+    bc = (W2 @ b1 + b2).contiguous()
+    w3 = W3.reshape(-1).contiguous()
+    sc2 = torch.empty(B, 128, device=dev)
+    slate = torch.empty(B, device=dev)
+    out = torch.zeros(1 + 32 * F + 65, device=dev)
+    nscr = lib.ltr_triple_scratch_bytes(B, 128, F)
+    scr = torch.zeros(nscr, dtype=torch.uint8, device=dev)
+    tab = rt.disc_prefix(dev)
+    rc = lib.ltr_triple_approx_ndcg_fwdbwd(
+        X.data_ptr(), y.data_ptr(), Wc.data_ptr(), bc.data_ptr(), w3.data_ptr(), float(b3), B, 128, F, 10.0, 1e-10, -1.0,
+        tab.data_ptr(), tab.numel(), sc2.data_ptr(), slate.data_ptr(), out[0:1].data_ptr(), out[1:1 + 32 * F].data_ptr(),
+        out[1 + 32 * F:33 + 32 * F].data_ptr(), out[33 + 32 * F:65 + 32 * F].data_ptr(), out[65 + 32 * F:].data_ptr(),
+        scr.data_ptr(), nscr, rt.workspace(dev).data_ptr(), rt.stream_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert float((sc2 - scores).abs().max()) <= 2e-5 * float(scores.abs().max())      # cuBLAS fold vs the fold kernel: fp32 rounding
+    assert abs(float(out[0]) - float(loss)) <= 1e-5 * abs(float(loss))
+    gWc, gbc, gw3 = out[1:1 + 32 * F].view(32, F), out[1 + 32 * F:33 + 32 * F], out[33 + 32 * F:65 + 32 * F]
+    want = {"l1.weight": W2.t() @ gWc, "l1.bias": W2.t() @ gbc, "l2.weight": gWc @ W1.t() + torch.outer(gbc, b1), "l2.bias": gbc,
+            "l3.weight": gw3.view(1, 32)}
+    for name, prm in net.named_parameters():
+        if name in want:
+            scale = float(want[name].abs().max())
+            assert float((prm.grad - want[name]).abs().max()) <= 2e-4 * scale, name

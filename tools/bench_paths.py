@@ -29,6 +29,13 @@ def _hbm_peak():
         return 6650.0, "fallback 6650 GB/s"
 
 
+def _ok(rc):
+    """A bench step that fails is not a fast step: every C-ABI call's status is checked."""
+    if rc != 0:
+        from ltr_b200 import _lib
+        raise RuntimeError(f"C-ABI call failed with status {rc}: {_lib.load().ltr_last_error().decode()}")
+
+
 def _time(fn, iters, warm=5):
     for i in range(warm):
         fn(i)
@@ -99,8 +106,8 @@ def bench_listnet(iters=200, B=65536, n=128):
 
     def step(i):
         s, y = data[i % ring]
-        lib.ltr_listnet_fwdbwd(y.data_ptr(), s.data_ptr(), B, n, 0, None, loss.data_ptr(), grads[i % ring].data_ptr(),
-                               ws.data_ptr(), rt.stream_ptr())
+        _ok(lib.ltr_listnet_fwdbwd(y.data_ptr(), s.data_ptr(), B, n, 0, None, loss.data_ptr(), grads[i % ring].data_ptr(),
+                               ws.data_ptr(), rt.stream_ptr()))
 
     sec = _time(step, iters)
     return {"metric": "ListNet fwd+bwd slates/s", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
@@ -123,8 +130,8 @@ def bench_ndcg(iters=100, Q=65536, n=128, ks=(1, 5, 10), ring=3):
 
     def step(i):
         s, y = data[i % ring]
-        lib.ltr_ndcg_at_k(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(), out.data_ptr(),
-                          marks[i % ring].data_ptr(), rt.stream_ptr())
+        _ok(lib.ltr_ndcg_at_k(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(), out.data_ptr(),
+                          marks[i % ring].data_ptr(), rt.stream_ptr()))
 
     sec = _time(step, iters)
     marked = [int((m[1:] != 0).sum()) for m in marks]
@@ -165,9 +172,9 @@ def bench_lambda(iters=50, B=1024, n=256):
     ws = rt.workspace(torch.device("cuda", torch.cuda.current_device()))
 
     def step(i):
-        lib.ltr_lambda_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 1e-10, -1.0, 4, -1, 1.0, 10.0, 0, 0, sums[0].data_ptr(),
+        _ok(lib.ltr_lambda_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 1e-10, -1.0, 4, -1, 1.0, 10.0, 0, 0, sums[0].data_ptr(),
                               sums[1].data_ptr(), out[0:1].data_ptr(), out[1:2].data_ptr(), grad.data_ptr(),
-                              ws.data_ptr(), rt.stream_ptr())
+                              ws.data_ptr(), rt.stream_ptr()))
 
     sec = _time(step, iters)
     return {"metric": "LambdaLoss ndcgLoss2PP fwd+bwd slates/s (n=256)", "value": B / sec, "unit": "slates/s",
@@ -249,9 +256,9 @@ def bench_approx_1024(iters=50, B=64, n=1024):
     scratch = torch.empty(max(nscratch, 1), dtype=torch.uint8, device="cuda")
 
     def step(i):
-        lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
+        _ok(lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
                                    slate.data_ptr(), loss.data_ptr(), grad.data_ptr(), scratch.data_ptr(), nscratch,
-                                   ws.data_ptr(), rt.stream_ptr())
+                                   ws.data_ptr(), rt.stream_ptr()))
 
     sec = _time(step, iters)
     return {"metric": "approxNDCG fwd+bwd slates/s (n=1024)", "value": B / sec, "unit": "slates/s", "us_per_call": sec * 1e6,
@@ -283,9 +290,9 @@ def bench_approx_large(iters=30, B=65536, n=128):
 
     def step(i):
         s, y = data[i % ring]
-        lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
+        _ok(lib.ltr_approx_ndcg_fwdbwd(s.data_ptr(), y.data_ptr(), B, n, 10.0, 1e-10, -1.0, tab.data_ptr(), tab.numel(),
                                    slate.data_ptr(), loss.data_ptr(), grad[i % ring].data_ptr(), None, 0, ws.data_ptr(),
-                                   rt.stream_ptr())
+                                   rt.stream_ptr()))
 
     sec = _time(step, iters)
     return {"metric": "approxNDCG fwd+bwd slates/s (n=128, 65536 slates per launch)", "value": B / sec, "unit": "slates/s",
@@ -323,20 +330,45 @@ def bench_ranker_step(iters=30, B=4096, n=128, F=136):
         approxNDCGLoss(net(X, None, None).squeeze(-1), y, alpha=10.0).backward()
 
     sec = _time(fused, iters)
+    # the same step through the C-ABI alone (what a training loop without Python in it pays): fold, fused kernel, reduce, unfold
+    from ltr_b200 import _lib, _runtime as rt
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    prm = [t.detach() for t in (net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight, net.l3.bias)]
+    outs = [torch.empty_like(t) for t in prm]
+    scores, slate, loss = torch.empty(B, n, device=dev), torch.empty(B, device=dev), torch.empty(1, device=dev)
+    nscr = lib.ltr_triple_step_scratch_bytes(B, n, F)
+    scr = torch.empty(nscr, dtype=torch.uint8, device=dev)
+    tab, ws = rt.disc_prefix(dev), rt.workspace(dev)
+
+    def cabi(i):
+        X, y = data[i % ring]
+        _ok(lib.ltr_triple_approx_ndcg_step(X.data_ptr(), y.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, 10.0, 1e-10, -1.0,
+                                            tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(), loss.data_ptr(),
+                                            *[t.data_ptr() for t in outs], scr.data_ptr(), nscr, ws.data_ptr(), rt.stream_ptr()))
+
+    sec_abi = _time(cabi, iters)
     torch.backends.cuda.matmul.allow_tf32 = False
     sec_fp32 = _time(stock, max(5, iters // 3))
     torch.backends.cuda.matmul.allow_tf32 = True
     sec_tf32 = _time(stock, max(5, iters // 3))
     torch.backends.cuda.matmul.allow_tf32 = False
     alg = (4.0 * F * n + 8.0 * n) * B                       # features once, labels in, scores out
-    return {"metric": "TripleLayerNet + approxNDCG training step slates/s (n=128, F=136)", "value": B / sec, "unit": "slates/s",
-            "us_per_call": sec * 1e6, "us_per_step_torch_modules_fp32_plus_K1": sec_fp32 * 1e6,
-            "us_per_step_torch_modules_tf32_plus_K1": sec_tf32 * 1e6,
-            "speedup_vs_torch_fp32": sec_fp32 / sec, "speedup_vs_torch_tf32": sec_tf32 / sec,
+    return {"metric": "TripleLayerNet + approxNDCG training step slates/s (n=128, F=136)", "value": B / sec_abi, "unit": "slates/s",
+            "us_per_call": sec_abi * 1e6, "us_per_step_through_autograd": sec * 1e6,
+            "us_per_step_torch_modules_fp32_plus_K1": sec_fp32 * 1e6, "us_per_step_torch_modules_tf32_plus_K1": sec_tf32 * 1e6,
+            "speedup_vs_torch_fp32": sec_fp32 / sec_abi, "speedup_vs_torch_tf32": sec_tf32 / sec_abi,
+            "speedup_through_autograd_vs_torch_fp32": sec_fp32 / sec, "speedup_through_autograd_vs_torch_tf32": sec_tf32 / sec,
+            "note": "us_per_call = ltr_triple_approx_ndcg_step through the C-ABI (4 launches: fold, fused kernel, reduce, unfold); through "
+                    "torch.autograd the same step is bound by ~200 us of Python / autograd-engine time per step, the torch-module steps "
+                    "are GPU-bound",
             "config": {"workload": f"{B} slates x {n} docs x {F} features, valid len U{{64..128}}, alpha=10; forward + backward "
                                    "to l1/l2/l3 weight and bias gradients, through autograd, zero_grad included"},
-            "roofline": dict(_roof(alg, sec), kernel="ranker_fused_kernel (TMA + tcgen05 tf32, 1 CTA per SM) + ranker_fused_reduce_kernel",
-                             algorithmic="4 F n + 8 n bytes per slate (features read once, labels, scores)")}
+            "roofline": dict(_roof(alg, sec_abi), kernel="ranker_fold_kernel + ranker_fused_kernel<3> (TMA + tcgen05 tf32, 1 CTA per SM) + "
+                                                         "ranker_fused_reduce_kernel + ranker_unfold_kernel",
+                             algorithmic="4 F n + 8 n bytes per slate (features read once, labels, scores)",
+                             second_bound="every feature byte crosses L2 -> SM twice (forward copy, gradient copy): 2 x 285 MB at the "
+                                          "11.5 TB/s an L2-resident TMA stream reaches (tools/probe_tma.py) = 50 us")}
 
 
 def bench_ndcg_1024(iters=30):
