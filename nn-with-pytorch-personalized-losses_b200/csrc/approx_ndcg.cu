@@ -15,6 +15,8 @@
 #include "approx_ndcg_warp.cuh"
 #include "approx_ndcg_cluster.cuh"
 #include "ltr_common.cuh"
+#include <stdlib.h>
+
 #include "ltr_host.h"
 
 namespace ltr {
@@ -542,10 +544,12 @@ LTR_API int ltr_approx_ndcg_fwdbwd_host(const float* h_y_pred, const float* h_y_
     float* d_loss = d_slate + b4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t bytes = (size_t)B * n * sizeof(float);
-#ifndef LTR_HOST_ZERO_COPY
-#define LTR_HOST_ZERO_COPY 1
-#endif
-    if (LTR_HOST_ZERO_COPY) {
+    // LTR_HOST_ZERO_COPY=0 in the environment forces the staged copies (A/B runs of the host path: tools/pcie_probe_multi.py)
+    static const bool zero_copy = [] {
+        const char* e = getenv("LTR_HOST_ZERO_COPY");
+        return !(e && e[0] == '0');
+    }();
+    if (zero_copy) {
         // Pinned, device-mapped host buffers (cudaHostAlloc / torch pin_memory under unified addressing): the kernel
         // reads the scores and labels and writes the gradient and the loss over PCIe itself -- one launch, no staging
         // copies, the transfers of a step overlap its pair arithmetic slate by slate.  Buffers that are not mapped

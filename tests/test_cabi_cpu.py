@@ -41,3 +41,37 @@ def test_no_cpu_fallback():
     from ltr_b200.losses.approxNDCG import approxNDCGLoss
     with pytest.raises(LtrError):
         approxNDCGLoss(torch.randn(2, 5, requires_grad=True), torch.ones(2, 5))
+
+
+def _header_arg_count(name):
+    text = open(os.path.join(ROOT, "include", "ltr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", text, flags=re.S)
+    assert m, name
+    args = m.group(1).strip()
+    return 0 if args in ("", "void") else args.count(",") + 1
+
+
+def test_ctypes_signatures_have_the_headers_arity():
+    from ltr_b200 import _lib
+    for name, (_, argtypes) in _lib._SIGNATURES.items():
+        assert len(argtypes) == _header_arg_count(name), name
+
+
+def test_integration_md_stub_matches_the_header():
+    """The binding a maintainer would copy out of INTEGRATION.md declares and passes as many arguments as the header
+    (round 1 shipped a 14-argument stub against a 16-argument entry point)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"ltr_approx_ndcg_fwdbwd\.argtypes = \[(.*?)\]", text, flags=re.S)
+    assert m
+    want = _header_arg_count("ltr_approx_ndcg_fwdbwd")
+    assert m.group(1).count("ctypes.") == want
+    call = re.search(r"rc = _lib\.ltr_approx_ndcg_fwdbwd\((.*?)\)\n\s+if rc", text, flags=re.S)
+    assert call
+    body = re.sub(r"#.*", "", call.group(1))
+    depth, n = 0, 1
+    for ch in body:
+        depth += ch in "([" 
+        depth -= ch in ")]"
+        n += (ch == "," and depth == 0)
+    assert n == want, (n, want)
