@@ -10,6 +10,7 @@ the arithmetic of the integration, not the transport:
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 
@@ -69,7 +70,7 @@ def _worker(rank, world, port, state, out_q):
             scores = ddp(X[lo:hi].cuda(), None, None).squeeze(-1)
             loss = fn(scores, y[lo:hi].cuda(), world, dist.group.WORLD)
             loss.backward()
-            res[name] = {k: v.grad.detach().cpu() for k, v in net.named_parameters()}
+            res[name] = {k: v.grad.detach().cpu().numpy() for k, v in net.named_parameters()}   # (by value through the queue)
         out_q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -99,9 +100,11 @@ def test_ddp_gradients_equal_the_single_process_whole_batch_gradients():
         scores = ref_net(X.cuda(), None, None).squeeze(-1)
         fn(scores, y.cuda(), 1, None).backward()                  # whole batch, one process, no scaling
         for k, v in ref_net.named_parameters():
-            want = v.grad.detach().cpu()
-            scale = float(want.abs().max())
+            want = v.grad.detach().cpu().numpy()
+            # l3.bias: d loss / d b3 = sum of d loss / d score = 0 up to rounding (these losses are shift invariant):
+            # measured against the scale of the neighbouring l3.weight gradient
+            scale = float(np.abs(want).max()) if k != "l3.bias" else float(ref_net.l3.weight.grad.abs().max())
             for r in range(world):
-                assert torch.equal(got[r][name][k], got[0][name][k]), "DDP leaves every rank with the same gradients"
-            err = float((got[0][name][k] - want).abs().max())
+                assert np.array_equal(got[r][name][k], got[0][name][k]), "DDP leaves every rank with the same gradients"
+            err = float(np.abs(got[0][name][k] - want).max())
             assert err <= 2e-4 * scale + 1e-9, (name, k, err, scale)
