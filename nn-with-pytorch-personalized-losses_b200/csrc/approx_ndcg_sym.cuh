@@ -202,10 +202,10 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
     if (steps == 0 || !active) ret = lane;    // nothing accumulated: the column sums are zero
 
     float urow[R], vcol[R], acc_r[R], acc_r_hi[R], acc_c[R];
+    lds_vec<R>(sh.u + lane * R, urow);
+    lds_vec<R>(sh.v + cb * R, vcol);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        urow[r] = sh.u[lane * R + r];
-        vcol[r] = sh.v[cb * R + r];
         acc_r[r] = 0.f;
         acc_r_hi[r] = 0.f;
         acc_c[r] = 0.f;
@@ -214,8 +214,7 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
     // ---------------- rank pass: one MUFU.RCP per unordered pair -----------------------------
     if (R > 1 && role == 0) {                 // pairs inside the lane's own block
         float vrow[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+        lds_vec<R>(sh.v + lane * R, vrow);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -249,10 +248,11 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
         rank_tile<R>(urow, vcol, 0.5f, acc_r, acc_r_hi, acc_c);
     }
     // the column accumulators go home; a doc's partial is (sum sigma_ij as a row) - (sum sigma_ij as a column)
+    {
+        float out[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
-        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) - cols;
+        for (int r = 0; r < R; ++r) out[r] = (acc_r[r] + acc_r_hi[r]) - __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sts_vec<R>(sh.part[warp] + lane * R, out);
     }
     __syncthreads();
 
@@ -275,19 +275,18 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
 
     // ---------------- gradient pass: sigma recomputed, one MUFU.RCP per unordered pair ---------
     float crow[R], ccol[R];
+    lds_vec<R>(sh.c + lane * R, crow);
+    lds_vec<R>(sh.c + cb * R, ccol);
+    lds_vec<R>(sh.v + cb * R, vcol);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        crow[r] = sh.c[lane * R + r];
-        ccol[r] = sh.c[cb * R + r];
-        vcol[r] = sh.v[cb * R + r];
         acc_r[r] = 0.f;
         acc_r_hi[r] = 0.f;
         acc_c[r] = 0.f;
     }
     if (R > 1 && role == 0) {
         float vrow[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vrow[r] = sh.v[lane * R + r];
+        lds_vec<R>(sh.v + lane * R, vrow);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -326,10 +325,11 @@ __device__ __forceinline__ void sym_slate(const ApproxParams& p, SymShared& sh, 
         for (int r = 0; r < R; ++r) ch[r] = 0.5f * crow[r], cch[r] = 0.5f * ccol[r];
         grad_tile<R>(urow, vcol, ch, cch, acc_r, acc_r_hi, acc_c);
     }
+    {
+        float out[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float cols = __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
-        if (active) sh.part[warp][lane * R + r] = (acc_r[r] + acc_r_hi[r]) + cols;
+        for (int r = 0; r < R; ++r) out[r] = (acc_r[r] + acc_r_hi[r]) + __shfl_sync(LTR_FULL_MASK, acc_c[r], ret);
+        if (active) sts_vec<R>(sh.part[warp] + lane * R, out);
     }
     __syncthreads();
     if (tid < p.n) {

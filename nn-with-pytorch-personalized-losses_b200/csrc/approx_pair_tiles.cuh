@@ -88,4 +88,31 @@ __device__ __forceinline__ void grad_tile(const float (&urow)[R], const float (&
     }
 }
 
+// R consecutive floats of a shared array at a multiple of R: one 64- / 128-bit access for R = 2 / 4 (a lane stride of 2 or 4
+// words is a 2- / 4-way bank conflict with scalar accesses; R = 3 is conflict-free as it is)
+template <int R>
+__device__ __forceinline__ void lds_vec(const float* p, float (&out)[R]) {
+    if (R == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        out[0] = t.x, out[1] = t.y, out[2] = t.z, out[3 % R] = t.w;
+    } else if (R == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        out[0] = t.x, out[1] = t.y;
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r] = p[r];
+    }
+}
+template <int R>
+__device__ __forceinline__ void sts_vec(float* p, const float (&in)[R]) {
+    if (R == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3 % R]);
+    } else if (R == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(in[0], in[1]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r] = in[r];
+    }
+}
+
 }  // namespace ltr

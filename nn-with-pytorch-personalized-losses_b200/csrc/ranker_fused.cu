@@ -67,11 +67,23 @@ constexpr int RF_NDZ = (RF_GROUPS <= 3) ? 3 : 2;
 static_assert(RF_GROUPS <= 2 * RF_NDZ, "the dZ tile hand-over needs G <= 2 RF_NDZ");
 constexpr int RF_N2 = RF_KCHUNKS * RF_CHUNK;                    // columns of the gradient accumulator
 constexpr int RF_G = RF_GROUPS;
-constexpr int RF_NSF = 5;                                       // F ring: one slate of forward chunks in flight (HBM latency)
+#ifndef RF_NSF_SLOTS
+#define RF_NSF_SLOTS 5
+#endif
+#ifndef RF_NSD_SLOTS
+#define RF_NSD_SLOTS 3
+#endif
+constexpr int RF_NSF = RF_NSF_SLOTS;                            // F ring: forward chunks in flight (HBM latency)
 constexpr int RF_QDOCS = 32;                                    // D ring: a slot = 32 docs x ALL feature chunks ...
 constexpr int RF_QBOX_BYTES = RF_QDOCS * 128;                   // ... 4 KB per chunk: [32 docs][32 floats] ...
 constexpr int RF_QSLOT_BYTES = RF_KCHUNKS * RF_QBOX_BYTES;      // ... 20 KB per slot, so that one MMA spans all N = 160 features
-constexpr int RF_NSD = 3;                                       // D ring of doc quarters (L2 hits); shared memory decides
+constexpr int RF_NSD = RF_NSD_SLOTS;                            // D ring of doc quarters (L2 hits); shared memory decides
+#ifndef RF_WAIT_HINT_NS
+#define RF_WAIT_HINT_NS 4000
+#endif
+#ifndef RF_LOADER_D_FIRST
+#define RF_LOADER_D_FIRST 0
+#endif
 #ifndef RF_EARLY_F
 #define RF_EARLY_F 0          // 1: the group's next forward MMA goes as soon as Z is in registers (measured: same time, 25 % of
                              // the gradient job's second reads then miss L2)
@@ -96,7 +108,22 @@ struct RankerFusedParams {
     float* part_misc;        // [grid][2]: sum of slate values, sum of ds
     float* part_bias;        // [grid][64]: dbc (32), dw3 (32) in fp32
     int grid;
+    unsigned long long* trace;   // RF_TRACE builds: [role][event][slate] globaltimer stamps of CTA 0 (diagnostics)
 };
+
+#ifdef RF_TRACE
+#define RF_TRACE_MAX_K 64
+#define RF_STAMP(role, ev, k)                                                                                  \
+    do {                                                                                                      \
+        if (p.trace && blockIdx.x == 0 && (k) < RF_TRACE_MAX_K) {                                            \
+            unsigned long long t_;                                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                           \
+            p.trace[((role) * 8 + (ev)) * RF_TRACE_MAX_K + (k)] = t_;                                         \
+        }                                                                                                     \
+    } while (0)
+#else
+#define RF_STAMP(role, ev, k) do {} while (0)
+#endif
 
 // ---- mbarrier / TMA / tcgen05 wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
@@ -114,7 +141,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity
             "selp.u32 %0, 1, 0, p;\n"
             "}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)RF_WAIT_HINT_NS)
             : "memory");
         if (spin > (1u << 21)) __trap();
     }
@@ -271,33 +298,6 @@ __device__ __forceinline__ float rf_middle(RfGroup& sh, int bar, int lane, int w
     if (lane == 0) sh.red[warp] = ndcg_part;
     named_bar_sync(bar, 128);
     return (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
-}
-
-// R consecutive floats of a shared array at a multiple of R: one 64- / 128-bit access for R = 2 / 4 (a lane stride of 2 or 4
-// words is a 2- / 4-way bank conflict with scalar accesses; R = 3 is conflict-free as it is)
-template <int R>
-__device__ __forceinline__ void lds_vec(const float* p, float (&out)[R]) {
-    if (R == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        out[0] = t.x, out[1] = t.y, out[2] = t.z, out[3 % R] = t.w;
-    } else if (R == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(p);
-        out[0] = t.x, out[1] = t.y;
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) out[r] = p[r];
-    }
-}
-template <int R>
-__device__ __forceinline__ void sts_vec(float* p, const float (&in)[R]) {
-    if (R == 4) {
-        *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3 % R]);
-    } else if (R == 2) {
-        *reinterpret_cast<float2*>(p) = make_float2(in[0], in[1]);
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) p[r] = in[r];
-    }
 }
 
 // One slate in the factorised form, R docs per lane (the schedule of sym_slate in approx_ndcg_sym.cuh, on a group of 4 warps
@@ -528,7 +528,9 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const float yv = ynext;
             if (k + G < nsl) ynext = ld_stream(p.y_true + (size_t)(slate + G * (int)gridDim.x) * RF_DOCS + gt);
             // ---- epilogue of the forward MMA: row `gt` of Z -> a[32], score ---------------------------------------------
+            if (gt == 0) RF_STAMP(g, 0, k);
             mbar_wait_bounded(&ctl.zfull[g], (unsigned)it & 1u);
+            if (gt == 0) RF_STAMP(g, 1, k);
             tc_fence_after();
             float a[RF_H];
             tmem_ld32(tmem + (unsigned)(g * RF_H) + ((unsigned)(w * 32) << 16), a);
@@ -547,6 +549,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 sv = fmaf(a[j], ctl.w3[j], sv);
             }
             p.scores[(size_t)slate * RF_DOCS + gt] = sv;
+            if (gt == 0) RF_STAMP(g, 2, k);
             // ---- approxNDCG of the slate (losses/approxNDCG.py:7-53; the K1 kernel's steps) --------------------------------
             const bool valid = (yv != p.pad);
             const float yc = fmaxf(yv, 0.f);                      // approxNDCG.py:37-38 clamp
@@ -658,8 +661,10 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             // A parity wait is only sound within one phase of the barrier.  The tile's barrier is shared with the other groups,
             // so first make sure that the gradient job of this group's OWN previous slate is complete (jobs complete in slate
             // order, and G <= 2 RF_NDZ: every use of the tile but the latest is then complete), then wait for the latest.
+            if (gt == 0) RF_STAMP(g, 3, k);
             if (it >= 1) mbar_wait_bounded(&ctl.dzmine[g], (unsigned)(it - 1) & 1u);
             if (tuse >= 1) mbar_wait_bounded(&ctl.dzfree[tile], (unsigned)(tuse - 1) & 1u);
+            if (gt == 0) RF_STAMP(g, 4, k);
             unsigned char* dzw = dz + tile * RF_DZ_TILE_BYTES + w * RF_DZ_CHUNK_BYTES;        // this warp's chunk of 32 docs
             float dzv[RF_H];
 #pragma unroll
@@ -672,8 +677,10 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
             mbar_arrive(&ctl.dzfull[tile]);
+            if (gt == 0) RF_STAMP(g, 5, k);
             acc_bc += warp_transpose_sum(dzv, lane);
             acc_w3 += warp_transpose_sum(a, lane);
+            if (gt == 0) RF_STAMP(g, 6, k);
         }
         // the group's fp32 sums -> its own shared arrays (read after the CTA barrier below)
         const float ds_w = warp_sum(ds_sum);
@@ -698,8 +705,13 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         unsigned idle = 0;
         while (fn < total || dn < total_d) {
             bool did = false;
+#if RF_LOADER_D_FIRST
+            for (int once = 0; once < 1; ++once)
+            if (fn < total && (fuse == 0 || __all_sync(LTR_FULL_MASK, mbar_test(&ctl.empty_f[fslot], (unsigned)(fuse - 1) & 1u)))) {
+#else
             // forward chunks first: they are the HBM reads, and a late one stalls a compute group at its next slate
             while (fn < total && (fuse == 0 || __all_sync(LTR_FULL_MASK, mbar_test(&ctl.empty_f[fslot], (unsigned)(fuse - 1) & 1u)))) {
+#endif
                 if (elect_one()) {
                     mbar_expect_tx(&ctl.full_f[fslot], RF_SLOT_BYTES);
                     tma_load_2d_hint(fring + fslot * RF_SLOT_BYTES, &map_x, fc * RF_CHUNK, ((int)blockIdx.x + fk * (int)gridDim.x) * RF_DOCS,
@@ -712,8 +724,13 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 did = true;
             }
             // the gradient copy of a slate goes after its forward copy (it is meant to hit L2): 32 docs x all chunks per slot
+#if RF_LOADER_D_FIRST
+            while (dn < total_d && (fk > dk || fn == total) &&
+                   (duse == 0 || __all_sync(LTR_FULL_MASK, mbar_test(&ctl.empty_d[dslot], (unsigned)(duse - 1) & 1u)))) {
+#else
             if (dn < total_d && (fk > dk || fn == total) &&
                 (duse == 0 || __all_sync(LTR_FULL_MASK, mbar_test(&ctl.empty_d[dslot], (unsigned)(duse - 1) & 1u)))) {
+#endif
                 if (elect_one()) {
                     mbar_expect_tx(&ctl.full_d[dslot], (unsigned)nch * RF_QBOX_BYTES);
                     const int row0 = ((int)blockIdx.x + dk * (int)gridDim.x) * RF_DOCS + dc * RF_QDOCS;
@@ -742,10 +759,13 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         int slot = 0, use = 0;
         for (int k = 0; k < nsl; ++k) {
             const int g = k % G, it = k / G;
+            if (lane == 0) RF_STAMP(4, 0, k);
             if (it >= 1) mbar_wait_bounded(&ctl.zfree[g], (unsigned)(it - 1) & 1u);
+            if (lane == 0) RF_STAMP(4, 1, k);
             tc_fence_after();
             for (int ck = 0; ck < nch; ++ck) {
                 mbar_wait_bounded(&ctl.full_f[slot], (unsigned)use & 1u);
+                if (lane == 0 && ck == nch - 1) RF_STAMP(4, 2, k);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_sw128(fa + (unsigned)slot * RF_SLOT_BYTES, 16, 1024);
@@ -767,6 +787,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     if (ck == nch - 1) tc_commit(&ctl.zfull[g]);
                 }
                 __syncwarp();
+                if (lane == 0 && ck == nch - 1) RF_STAMP(4, 3, k);
                 if (++slot == RF_NSF) slot = 0, ++use;
             }
         }
@@ -777,10 +798,13 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         int slot = 0, use = 0;
         for (int k = 0; k < nsl; ++k) {
             const int tile = k % RF_NDZ, tuse = k / RF_NDZ;
+            if (lane == 0) RF_STAMP(5, 0, k);
             mbar_wait_bounded(&ctl.dzfull[tile], (unsigned)tuse & 1u);
+            if (lane == 0) RF_STAMP(5, 1, k);
             tc_fence_after();
             for (int q = 0; q < RF_DOCS / RF_QDOCS; ++q) {
                 mbar_wait_bounded(&ctl.full_d[slot], (unsigned)use & 1u);
+                if (lane == 0) RF_STAMP(5, 2 + q, k);
                 tc_fence_after();
                 if (elect_one()) {
                     // A: dZ^T K-major, doc quarter q = one 4 KB chunk of the tile, 8 docs = 32 bytes (2 address units) inside its
@@ -801,6 +825,7 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     }
                 }
                 __syncwarp();
+                if (lane == 0 && q == RF_DOCS / RF_QDOCS - 1) RF_STAMP(5, 6, k);
                 if (++slot == RF_NSD) slot = 0, ++use;
             }
         }
@@ -1034,6 +1059,8 @@ LTR_API size_t ltr_triple_scratch_bytes(int B, int n, int F) {
 
 namespace ltr {
 
+static unsigned long long* g_rf_trace = nullptr;   // RF_TRACE builds: set by ltr_debug_ranker_trace
+
 template <typename... Args>
 static int launch_pdl_args(void (*kernel)(Args...), int grid, int threads, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -1077,6 +1104,7 @@ static int triple_core(const char* who, const float* X, const float* y_true, con
     p.part_misc = p.part + (size_t)device_sm_count() * RF_PART;
     p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
     p.grid = grid;
+    p.trace = g_rf_trace;
     constexpr size_t RF_SMEM = 1024 + (size_t)RF_NSF * RF_SLOT_BYTES + (size_t)RF_NSD * RF_QSLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
                                (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
     static_assert(RF_SMEM <= 232448, "ranker_fused_kernel: shared memory of one CTA");
@@ -1169,3 +1197,11 @@ LTR_API int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mo
     const int rc = (int)cudaGetLastError();
     return rc ? set_cuda_error(rc, "ltr_probe_tma_stream") : 0;
 }
+
+#ifdef RF_TRACE
+// diagnostics build only (tools/trace_ranker.py): globaltimer stamps of CTA 0 go to `buf` ([6][8][64] u64) from the next call on
+LTR_API int ltr_debug_ranker_trace(unsigned long long* buf) {
+    ltr::g_rf_trace = buf;
+    return 0;
+}
+#endif
