@@ -73,7 +73,26 @@ def risk(B, n, S):
     return run
 
 
+def ranker(B, F=136, min_len=64):
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet, fused_triple_approx_ndcg
+    torch.manual_seed(B)
+    net = TripleLayerNet(F).cuda()
+    g = torch.Generator().manual_seed(B)
+    X = torch.rand(B, 128, F, generator=g).cuda()
+    y = make_slates(B, 128, seed=B, min_len=min_len)[1].cuda()
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        loss, scores = fused_triple_approx_ndcg(net, X, y, alpha=10.0, return_scores=True)
+        loss.backward()
+        return [loss.detach(), scores] + [p.grad for p in net.parameters()]
+    return run
+
+
 bad = 0
+bad += repeat("fused ranker step 4096 x 128 x 136", ranker(4096))
+bad += repeat("fused ranker step 1500 x 128 x 136, short slates", ranker(1500, min_len=1))
+bad += repeat("fused ranker step 149 x 128 x 64", ranker(149, F=64))
 bad += repeat("approxNDCG 4096 x 128 (sym)", approx(4096, 128))
 bad += repeat("approxNDCG 20000 x 128 (warp per slate)", approx(20000, 128))
 bad += repeat("approxNDCG 64 x 1024 (cluster)", approx(64, 1024))
