@@ -291,11 +291,15 @@ __global__ void __launch_bounds__(TPQ_THREADS, C == 1 ? TPQ_CTAS : 2) ndcg_tpq_w
         }
 
         // a tie group that reaches into the first kmax ranks needs the reference's sort order
+        // flag 1: labels / scores the fast path does not handle; flag 2: only the tie (labels are integers 0..4): the full
+        // sort then skips its sorting network (the order is replayed anyway) and counts the ideal order off a histogram
+        int tie_top = 0;
 #pragma unroll
         for (int j = 0; j + 1 < TPQ_K; ++j)
-            bad |= (j < p.kmax && j + 1 < n && top[j] == top[j + 1]) ? 1 : 0;
+            tie_top |= (j < p.kmax && j + 1 < n && top[j] == top[j + 1]) ? 1 : 0;
         if (sub == 0 && t < ntiles && q < p.B) {
-            p.flags[1 + q] = bad;
+            p.flags[1 + q] = bad ? 1 : (tie_top ? 2 : 0);
+            bad |= tie_top;
             if (!bad) {
                 // ideal order from the histogram: level L fills the ranks below #docs with label >= L
                 c3 += c4;

@@ -91,7 +91,7 @@ struct NdcgParams {
 // integer 0..4 and level L occurs (hist >> 8 (L - 1)) & 255 times -- the ideal order is then written down directly.
 template <bool F64, bool WARP = false>
 __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem& sm, int b, bool known_tie = false,
-                                                  bool have_hist = false, unsigned hist = 0) {
+                                                  bool have_hist = false, unsigned hist = 0, bool count_hist = false) {
     const float ninf = __int_as_float(0xff800000);
     const float* yt = p.y_true + (size_t)b * p.n;
     for (int i = grp_tid<WARP>(); i < p.n; i += grp_size<WARP>()) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
@@ -99,7 +99,31 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
     block_sort_desc<WARP>(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1,
                           WARP ? reinterpret_cast<int*>(sm.L + p.len) : nullptr, known_tie);   // ranks >= kmax are never read
     // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
-    if (have_hist) {
+    if (count_hist) {
+        // every label of the row is an integer 0..4 (the caller's fast path checked): level counts by the group, then as below
+        int* cnt = reinterpret_cast<int*>(sm.L);                 // (L is written after the counts are read)
+        if (grp_tid<WARP>() < 4) cnt[grp_tid<WARP>()] = 0;
+        grp_sync<WARP>();
+        int c[4] = {0, 0, 0, 0};
+        for (int i = grp_tid<WARP>(); i < p.n; i += grp_size<WARP>()) {
+            const int lv = (int)yt[i];
+#pragma unroll
+            for (int L = 1; L <= 4; ++L) c[L - 1] += (lv == L) ? 1 : 0;
+        }
+#pragma unroll
+        for (int L = 0; L < 4; ++L) {
+            const int w = __reduce_add_sync(LTR_FULL_MASK, c[L]);
+            if ((grp_tid<WARP>() & 31) == 0 && w) atomicAdd(&cnt[L], w);
+        }
+        grp_sync<WARP>();
+        const int c4 = cnt[3], c3 = c4 + cnt[2], c2 = c3 + cnt[1], c1 = c2 + cnt[0];
+        grp_sync<WARP>();
+        for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
+            sm.L[i] = (i < p.n) ? (float)((c4 > i) + (c3 > i) + (c2 > i) + (c1 > i)) : ninf;
+            if (i < p.n) sm.K0[i] = yt[sm.I[i]];
+        }
+        grp_sync<WARP>();
+    } else if (have_hist) {
         const int c4 = hist >> 24, c3 = c4 + ((hist >> 16) & 255), c2 = c3 + ((hist >> 8) & 255), c1 = c2 + (hist & 255);
         for (int i = grp_tid<WARP>(); i < p.len; i += grp_size<WARP>()) {
             sm.L[i] = (i < p.n) ? (float)((c4 > i) + (c3 > i) + (c2 > i) + (c1 > i)) : ninf;
@@ -171,10 +195,14 @@ __global__ void __launch_bounds__(RANK_THREADS) ndcg_kernel(const NdcgParams p) 
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < NDCG_MARK_LIST / RANK_THREADS; ++j)
-            if (mine[j]) list[atomicAdd(&nlist, 1)] = base + j * RANK_THREADS + (int)threadIdx.x;
+            if (mine[j]) list[atomicAdd(&nlist, 1)] = (base + j * RANK_THREADS + (int)threadIdx.x) | ((mine[j] == 2) ? (1 << 30) : 0);
         __syncthreads();
         const int cnt = nlist;
-        for (int i = 0; i < cnt; ++i) ndcg_sorted_query<F64>(p, sm, list[i]);     // (any order: one output row per query)
+        for (int i = 0; i < cnt; ++i) {                                   // (any order: one output row per query)
+            // flag 2: the fast path saw a tie among the first kmax + 1 ranks of a row with integer labels 0..4
+            const bool tie_only = (list[i] >> 30) != 0;
+            ndcg_sorted_query<F64>(p, sm, list[i] & ~(1 << 30), tie_only, false, 0, tie_only);
+        }
     }
 }
 

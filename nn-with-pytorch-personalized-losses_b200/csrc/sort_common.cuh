@@ -181,6 +181,107 @@ struct StdSortEmu {
             ++lo;
         }
     }
+    // __unguarded_partition_pivot by a whole WARP (all 32 lanes call it with the same arguments; K / I in shared memory).
+    // The sequential loop pairs the t-th position from the left whose key does not sort before the pivot with the t-th
+    // position from the right whose key does not sort after it, swaps them while they have not met, and both scans only
+    // ever look at positions no swap has touched yet -- so the pairs follow from the ORIGINAL keys: ballots number the
+    // stoppers of both kinds into two position lists, the first pair that has met ends the loop, all pairs before it are
+    // swapped at once.  Same result as partition_pivot move for move (tests: torch CPU sort on heavy ties, and a Python
+    // model of both loops); O(range / 32) steps per lane instead of one thread walking the range.
+    // lists: 2 n 16-bit entries of scratch (n <= 65536).
+    __device__ int partition_pivot_warp(int first, int last, unsigned short* Ll, unsigned short* Rl, int lane) {
+        if (lane == 0) {
+            const int mid = first + (last - first) / 2;
+            const int a = first + 1, b = mid, c = last - 1;       // __move_median_to_first(first, a, b, c)
+            if (lt(a, b)) {
+                if (lt(b, c)) swp(first, b);
+                else if (lt(a, c)) swp(first, c);
+                else swp(first, a);
+            } else if (lt(a, c)) swp(first, a);
+            else if (lt(b, c)) swp(first, c);
+            else swp(first, b);
+        }
+        __syncwarp();
+        const float pk = K[first];
+        const unsigned below = (1u << lane) - 1u;
+        int nl = 0, nr = 0;
+        for (int base = first + 1; base < last; base += 32) {
+            const int pos = base + lane;
+            const bool in = pos < last;
+            const float x = in ? K[pos] : 0.f;
+            const bool ls = in && !key_before(x, pk);             // stops the scan from the left
+            const bool rs = in && !key_before(pk, x);             // stops the scan from the right
+            const unsigned bl = __ballot_sync(0xffffffffu, ls), br = __ballot_sync(0xffffffffu, rs);
+            if (ls) Ll[nl + __popc(bl & below)] = (unsigned short)pos;
+            if (rs) Rl[nr + __popc(br & below)] = (unsigned short)pos;      // ascending; the scan meets them from the end
+            nl += __popc(bl);
+            nr += __popc(br);
+        }
+        __syncwarp();
+        const int m = nl < nr ? nl : nr;
+        int tstar = m;                                            // first pair that has met
+        for (int t0 = 0; t0 < m; t0 += 32) {
+            const int t = t0 + lane;
+            const bool met = t < m && !((int)Ll[t] < (int)Rl[nr - 1 - t]);
+            const unsigned bm = __ballot_sync(0xffffffffu, met);
+            if (bm) {
+                tstar = t0 + __ffs(bm) - 1;
+                break;
+            }
+        }
+        for (int t = lane; t < tstar; t += 32) swp((int)Ll[t], (int)Rl[nr - 1 - t]);
+        const int lt_pos = tstar < nl ? (int)Ll[tstar] : 0x7fffffff;
+        const int r_prev = tstar > 0 ? (int)Rl[nr - tstar] : last;
+        __syncwarp();
+        return lt_pos < r_prev ? lt_pos : r_prev;
+    }
+    // sort() by a whole warp: the partitions cooperatively, the small sequential pieces (heap sort at the depth limit,
+    // the final insertion sort) by lane 0.  Every lane keeps the same control state (stk may be shared or per lane).
+    __device__ int sort_warp(int n, int limit, int* stk, unsigned short* lists, int lane) {
+        if (n <= 1) return n;
+        int depth0 = 0;
+        for (int t = n; t > 1; t >>= 1) ++depth0;                 // __lg(n)
+        depth0 *= 2;
+        int bound = n;
+        int* stk_first = stk;
+        int* stk_last = stk + 48;
+        int* stk_depth = stk + 96;
+        int sp = 0;
+        stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = depth0; sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            --sp;
+            const int first = stk_first[sp];
+            int last = stk_last[sp], depth = stk_depth[sp];
+            __syncwarp();                                         // (shared stack: everyone has read the entry)
+            while (last - first > 16) {
+                if (depth == 0) {
+                    if (lane == 0) heap_sort(first, last);
+                    __syncwarp();
+                    break;
+                }
+                --depth;
+                const int cut = partition_pivot_warp(first, last, lists, lists + n, lane);
+                if (cut < limit) {
+                    stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
+                } else if (cut < bound) {
+                    bound = cut;
+                }
+                last = cut;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (bound > 16) {                                     // __final_insertion_sort
+                insertion_sort(0, 16);
+                for (int i = 16; i < bound; ++i) unguarded_linear_insert(i);
+            } else {
+                insertion_sort(0, bound);
+            }
+        }
+        __syncwarp();
+        return bound;
+    }
     // Replays std::sort on n elements; only the first `limit` positions of the result are needed.
     // A partition's right part [cut, last) with cut >= limit is never looked at again: introsort's sub-ranges are
     // disjoint, and in the final insertion sort an element can only move left past keys that sort strictly after
@@ -243,13 +344,13 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
         const int lim = tie_limit < n ? tie_limit : n;
         for (int i = grp_tid<WARP>(); i < n; i += grp_size<WARP>()) I[i] = i;
         grp_sync<WARP>();
-        if (grp_tid<WARP>() == 0) {
+        if (grp_tid<WARP>() < 32) {                              // one warp replays std::sort (K0 is free: partition scratch)
             StdSortEmu emu{K, I};
             if constexpr (WARP) {
-                emu.sort(n, lim, warp_stack);
+                emu.sort_warp(n, lim, warp_stack, reinterpret_cast<unsigned short*>(K0), grp_tid<WARP>());
             } else {
                 int stk[3 * 48];
-                emu.sort(n, lim, stk);
+                emu.sort_warp(n, lim, stk, reinterpret_cast<unsigned short*>(K0), grp_tid<WARP>());
             }
         }
         grp_sync<WARP>();
@@ -318,14 +419,14 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
     grp_sync<WARP>();
     for (int i = grp_tid<WARP>(); i < n; i += grp_size<WARP>()) { K[i] = K0[i]; I[i] = i; }      // back to the original order
     grp_sync<WARP>();
-    if (grp_tid<WARP>() == 0) {
+    if (grp_tid<WARP>() < 32) {                                  // one warp replays std::sort; K0 (restored from above) is its scratch
         StdSortEmu emu{K, I};
         // entries at and beyond `lim` may stay unsorted
         if constexpr (WARP) {
-            emu.sort(n, lim, warp_stack);                         // (a warp-level caller keeps the kernel free of a stack frame)
+            emu.sort_warp(n, lim, warp_stack, reinterpret_cast<unsigned short*>(K0), grp_tid<WARP>());   // (no stack frame in the kernel)
         } else {
             int stk[3 * 48];
-            emu.sort(n, lim, stk);
+            emu.sort_warp(n, lim, stk, reinterpret_cast<unsigned short*>(K0), grp_tid<WARP>());
         }
     }
     grp_sync<WARP>();
