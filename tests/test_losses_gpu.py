@@ -409,6 +409,9 @@ def test_validation_epilogue_matches_driver_block():
     (64, 1000, (1, 5, 10), {}),                       # four warps per tile, last chunk partial
     (20, 2048, (10,), {}),
     (64, 512, (1, 5, 10), dict(ties=True)),
+    (48, 1024, (1, 5, 10), dict(ties=True)),          # tie-only marks: warp-cooperative std::sort replay, ideal order from level counts
+    (40, 1000, (10,), dict(ties=True)),
+    (30, 300, (1, 5, 10), dict(ties=True)),
     (64, 128, (1, 5, 20), {}),                        # k > 10: warp-per-query tournament kernel
 ])
 def test_ndcg_sweep_kernels_vs_oracle(Q, n, ks, kw):
