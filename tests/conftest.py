@@ -17,6 +17,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_terminal_summary(terminalreporter):
+    """How often the fp64 slack of assert_loss_close / assert_grad_close was needed in this session."""
+    try:
+        from ltr_testing import SLACK_STATS as st
+    except Exception:
+        return
+    if st["loss_checks_with_ref64"] or st["grad_checks_with_ref64"]:
+        terminalreporter.write_line(
+            "fp64-slack report: loss checks %d, of which %d would fail the plain 1e-5 gate; gradient checks %d, of which %d "
+            "(%d of %d elements) would fail the plain 1e-4 gate" % (
+                st["loss_checks_with_ref64"], st["loss_checks_that_needed_it"], st["grad_checks_with_ref64"],
+                st["grad_checks_that_needed_it"], st["grad_elements_that_needed_it"], st["grad_elements_with_ref64"]))
+
+
 class Golden:
     """Golden vectors produced by tests/golden/make_golden.py and make_golden_v2.py from the unmodified reference."""
 
