@@ -917,16 +917,19 @@ __global__ void __launch_bounds__(32 * RF_RED_WARPS) ranker_fused_reduce_kernel(
 
 // ---- the linear part of the net, folded and unfolded on the device (whole-step entry) -----------------------------------------
 constexpr int RF_H1 = 64;                                        // l1: F -> 64, l2: 64 -> 32 (architeture/tripleLayer.py:8-10)
-// Wc = W2 W1 [32, F], bc = W2 b1 + b2 [32]; one thread per entry, sums in index order
+// Wc = W2 W1 [32, F], bc = W2 b1 + b2 [32]; one thread per entry, sums in index order, all 64 loads of an entry in flight
 __global__ void __launch_bounds__(256) ranker_fold_kernel(const float* W1, const float* b1, const float* W2, const float* b2, int F,
                                                           float* Wc, float* bc) {
     pdl_prologue();
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx < RF_H * F) {
         const int j = idx / F, f = idx % F;
+        float w1[RF_H1];
+#pragma unroll
+        for (int h = 0; h < RF_H1; ++h) w1[h] = __ldg(W1 + h * F + f);          // coalesced over f
         float t = 0.f;
-#pragma unroll 8
-        for (int h = 0; h < RF_H1; ++h) t = fmaf(W2[j * RF_H1 + h], W1[h * F + f], t);
+#pragma unroll
+        for (int h = 0; h < RF_H1; ++h) t = fmaf(__ldg(W2 + j * RF_H1 + h), w1[h], t);
         Wc[idx] = t;
     } else if (idx < RF_H * F + RF_H) {
         const int j = idx - RF_H * F;
@@ -936,37 +939,42 @@ __global__ void __launch_bounds__(256) ranker_fold_kernel(const float* W1, const
         bc[j] = t;
     }
 }
-// dW1 = W2^T gWc [64, F], db1 = W2^T gbc [64], dW2 = gWc W1^T + gbc b1^T [32, 64], db2 = gbc [32], dW3 = gw3 [32]
+// dW1 = W2^T gWc [64, F], db1 = W2^T gbc [64], dW2 = gWc W1^T + gbc b1^T [32, 64], db2 = gbc [32], dW3 = gw3 [32].
+// Blocks [0, nb1): one thread per entry of dW1 (32 terms, loads in flight together); blocks [nb1, nb1 + 256): one WARP per
+// entry of dW2 (F terms, coalesced over the features, fixed shuffle tree); last block: the three small vectors.
 __global__ void __launch_bounds__(256) ranker_unfold_kernel(const float* W1, const float* b1, const float* W2, const float* gWc,
                                                             const float* gbc, const float* gw3, int F, float* gW1, float* gb1,
                                                             float* gW2, float* gb2, float* gW3) {
     pdl_prologue();
-    int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx < RF_H1 * F) {
+    const int nb1 = (RF_H1 * F + 255) / 256;
+    const int blk = (int)blockIdx.x, tid = (int)threadIdx.x;
+    if (blk < nb1) {
+        const int idx = blk * 256 + tid;
+        if (idx >= RF_H1 * F) return;
         const int h = idx / F, f = idx % F;
+        float g[RF_H];
+#pragma unroll
+        for (int j = 0; j < RF_H; ++j) g[j] = __ldg(gWc + j * F + f);           // coalesced over f
         float t = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < RF_H; ++j) t = fmaf(W2[j * RF_H1 + h], gWc[j * F + f], t);
+#pragma unroll
+        for (int j = 0; j < RF_H; ++j) t = fmaf(__ldg(W2 + j * RF_H1 + h), g[j], t);
         gW1[idx] = t;
-        return;
-    }
-    idx -= RF_H1 * F;
-    if (idx < RF_H * RF_H1) {
-        const int j = idx / RF_H1, h = idx % RF_H1;
-        float t = gbc[j] * b1[h];
-        for (int f = 0; f < F; ++f) t = fmaf(gWc[j * F + f], W1[h * F + f], t);
-        gW2[idx] = t;
-        return;
-    }
-    idx -= RF_H * RF_H1;
-    if (idx < RF_H1) {
+    } else if (blk < nb1 + RF_H * RF_H1 / 8) {
+        const int out = (blk - nb1) * 8 + (tid >> 5), lane = tid & 31;          // 8 warps per block, one entry each
+        const int j = out / RF_H1, h = out % RF_H1;
         float t = 0.f;
-        for (int j = 0; j < RF_H; ++j) t = fmaf(W2[j * RF_H1 + idx], gbc[j], t);
-        gb1[idx] = t;
-        return;
+        for (int f = lane; f < F; f += 32) t = fmaf(__ldg(gWc + j * F + f), __ldg(W1 + h * F + f), t);
+        t = warp_sum(t);
+        if (lane == 0) gW2[out] = fmaf(gbc[j], b1[h], t);
+    } else {
+        if (tid < RF_H1) {
+            float t = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < RF_H; ++j) t = fmaf(W2[j * RF_H1 + tid], gbc[j], t);
+            gb1[tid] = t;
+        }
+        if (tid < RF_H) gb2[tid] = gbc[tid], gW3[tid] = gw3[tid];
     }
-    idx -= RF_H1;
-    if (idx < RF_H) gb2[idx] = gbc[idx], gW3[idx] = gw3[idx];
 }
 
 // Measurement probe: what the TMA stream of feature tiles delivers on its own (no MMA, no consumer): every CTA keeps
@@ -1175,8 +1183,7 @@ LTR_API int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, con
     rc = triple_core("ltr_triple_approx_ndcg_step", X, y_true, Wc, bc, W3, 0.f, b3, B, n, F, alpha, eps, pad_value, disc_prefix, disc_len,
                      scores, slate_ndcg, loss, gWc, gbc, gw3, gb3, scratch, core, st, true);
     if (rc) return rc;
-    const int total = RF_H1 * F + RF_H * RF_H1 + RF_H1 + RF_H;
-    rc = launch_pdl_args(ranker_unfold_kernel, (total + 255) / 256, 256, st, W1, b1, W2, (const float*)gWc, (const float*)gbc,
+    rc = launch_pdl_args(ranker_unfold_kernel, (RF_H1 * F + 255) / 256 + RF_H * RF_H1 / 8 + 1, 256, st, W1, b1, W2, (const float*)gWc, (const float*)gbc,
                          (const float*)gw3, F, gW1, gb1, gW2, gb2, gW3);
     if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_step (unfold)");
     return 0;
