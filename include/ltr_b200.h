@@ -351,7 +351,7 @@ int ltr_probe_sfu(float* out, int iters, long long* ops_out, void* stream);
 int ltr_probe_fma(float* out, int iters, long long* ops_out, void* stream);
 /* the feature-tile TMA stream of the fused ranker step on its own: every CTA keeps `slots` (<= 13) 16 KB copies in flight
  * over its slates of X [B, 128, F], `reps` times over (a small B stays in L2); mode 0 = [128 docs][32 floats] tensor-map
- * boxes, 1 = contiguous 4 KB bulk copies */
+ * boxes, 1 = contiguous 4 KB bulk copies, 2 = [32 docs][all chunks] slots of 4 KB boxes with 32-byte swizzle atoms (slots <= 10) */
 int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mode, int reps, void* stream);
 
 #ifdef __cplusplus

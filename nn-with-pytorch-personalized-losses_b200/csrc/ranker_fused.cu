@@ -979,7 +979,8 @@ __global__ void __launch_bounds__(256) ranker_unfold_kernel(const float* W1, con
 
 // Measurement probe: what the TMA stream of feature tiles delivers on its own (no MMA, no consumer): every CTA keeps
 // `slots` copies in flight over its slates.  mode 0: [128 docs][32 floats] boxes through a tensor map (the F ring's copies),
-// mode 1: the same bytes as contiguous 4 KB bulk copies (what a layout-free stream of the same tensor reaches).
+// mode 1: the same bytes as contiguous 4 KB bulk copies (what a layout-free stream of the same tensor reaches),
+// mode 2: [32 docs][all chunks] slots of 4 KB boxes with the 32-byte-atom swizzle (the D ring's copies).
 __global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant__ CUtensorMap map, const float* X, int B, int F, int slots,
                                                           int mode, int reps) {
     extern __shared__ unsigned char rf_smem_raw[];
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant_
     const int nsl = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int nch = (F + RF_CHUNK - 1) / RF_CHUNK;
     const int slate_bytes = RF_DOCS * F * 4;
-    const int per = mode == 0 ? nch : (slate_bytes + 4095) / 4096;        // copies per slate
+    const int per = mode == 0 ? nch : mode == 2 ? RF_DOCS / RF_QDOCS : (slate_bytes + 4095) / 4096;        // copies per slate
     const int total = nsl * per * reps;                               // reps > 1: the same slates again (L2-resident runs)
     int slot = 0, use = 0, k = 0, c = 0;
     for (int n = 0; n < total; ++n) {
@@ -1004,6 +1005,11 @@ __global__ void __launch_bounds__(32, 1) probe_tma_kernel(const __grid_constant_
             if (mode == 0) {
                 mbar_expect_tx(&full[slot], RF_SLOT_BYTES);
                 tma_load_2d(base + slot * RF_SLOT_BYTES, &map, c * RF_CHUNK, slate * RF_DOCS, &full[slot]);
+            } else if (mode == 2) {
+                mbar_expect_tx(&full[slot], (unsigned)nch * RF_QBOX_BYTES);
+                for (int ck = 0; ck < nch; ++ck)
+                    tma_load_2d(base + slot * RF_QSLOT_BYTES + ck * RF_QBOX_BYTES, &map, ck * RF_CHUNK, slate * RF_DOCS + c * RF_QDOCS,
+                                &full[slot]);
             } else {
                 const int off = c * 4096, len = min(4096, slate_bytes - off);
                 mbar_expect_tx(&full[slot], (unsigned)len);
@@ -1192,13 +1198,15 @@ LTR_API int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, con
 // Feature-tile TMA stream on its own (measurement; see probe_tma_kernel): bytes moved = reps * B * 128 * F * 4.
 LTR_API int ltr_probe_tma_stream(const float* X, int B, int F, int slots, int mode, int reps, void* stream) {
     using namespace ltr;
-    if (!X || B <= 0 || F < 4 || F > RF_MAX_F || F % 4 || slots < 1 || slots > 13 || mode < 0 || mode > 1 || reps < 1)
+    if (!X || B <= 0 || F < 4 || F > RF_MAX_F || F % 4 || slots < 1 || slots > 13 || mode < 0 || mode > 2 || reps < 1 || (mode == 2 && slots > 10))
         return set_error(LTR_EINVAL, "ltr_probe_tma_stream: bad arguments");
     CUtensorMap map;
-    if (int rc = make_map(&map, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = mode == 2 ? make_map(&map, X, (unsigned long long)B * RF_DOCS, F, RF_QDOCS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                           : make_map(&map, X, (unsigned long long)B * RF_DOCS, F, RF_DOCS, CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
     int grid = device_sm_count();
     if (grid > B) grid = B;
-    const int smem = 1024 + slots * RF_SLOT_BYTES;
+    const int smem = 1024 + slots * (mode == 2 ? RF_QSLOT_BYTES : RF_SLOT_BYTES);
     LTR_CUDA(cudaFuncSetAttribute(probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     probe_tma_kernel<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map, X, B, F, slots, mode, reps);
     const int rc = (int)cudaGetLastError();

@@ -1,5 +1,6 @@
 """What the TMA stream of feature tiles delivers on its own (ltr_probe_tma_stream): GB/s against copies in flight per SM,
-tensor-map boxes ([128 docs][32 floats], the fused ranker's forward copies) against contiguous 4 KB bulk copies; from HBM
+tensor-map boxes (mode 0: [128 docs][32 floats], the fused ranker's forward copies; mode 2: [32 docs][5 x 32 floats] slots of 4 KB
+boxes, its gradient copies) against contiguous 4 KB bulk copies (mode 1); from HBM
 (4096 slates = 285 MB, three buffers cycled) and from L2 (296 slates = 20 MB read 14 times over)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,8 +11,8 @@ lib = _lib.load(); torch.cuda.set_device(0)
 F = 136
 for B, reps, what in ((4096, 1, "HBM"), (296, 14, "L2")):
     Xs = [torch.rand(B, 128, F, device="cuda") for _ in range(3 if reps == 1 else 1)]
-    for mode in (0, 1):
-        for slots in (2, 3, 5, 8, 13):
+    for mode in (0, 2, 1):
+        for slots in (2, 3, 5, 8, 13) if mode != 2 else (2, 3, 4, 6, 10):
             def run(i):
                 assert lib.ltr_probe_tma_stream(Xs[i % len(Xs)].data_ptr(), B, F, slots, mode, reps, rt.stream_ptr()) == 0
             for i in range(3): run(i)
