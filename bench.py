@@ -466,7 +466,7 @@ def run_b200_arm(args, rank, local_rank, world):
 
 def bench_ndcg_eval(lib, rt, dev, rank, world, barrier, max_over_ranks, NdcgEvalHost, hbm_peak, hbm_src, steps):
     """NDCG@{1,5,10} sweep, torchNdcg arithmetic (utils/metrics.py:83-104), 65,536 queries x 128 docs per GPU per step.
-    value: queries resident in HBM, CUDA events over `steps` calls of `ltr_ndcg_at_k` cycling 3 distinct batches
+    value: queries resident in HBM, CUDA events over a CUDA graph of `steps` calls of `ltr_ndcg_at_k` cycling 3 distinct batches
     (201 MB > L2); e2e: pinned host labels / scores -> `ltr_ndcg_at_k_host` -> pinned NDCG, 3 streams in flight."""
     import ctypes
     from ltr_b200 import ops
@@ -493,10 +493,24 @@ def bench_ndcg_eval(lib, rt, dev, rank, world, barrier, max_over_ranks, NdcgEval
     for i in range(5):
         step(i)
     barrier()
+    # like the headline: the ~20 us kernel is shorter than a Python -> ctypes -> launch round trip (and with several ranks on
+    # one host the launching threads compete for its cores), so the timed calls are ONE replay of a CUDA graph of `steps` calls
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        stream = rt.stream_ptr()
+        step(0)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(steps):
+                step(5 + i)
+    stream = rt.stream_ptr()
+    for _ in range(2):
+        graph.replay()
+    barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for i in range(steps):
-        step(5 + i)
+    graph.replay()
     b.record()
     barrier()
     ms = max_over_ranks(a.elapsed_time(b))
