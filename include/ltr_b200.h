@@ -321,6 +321,18 @@ int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, const float
                                 void* scratch, size_t scratch_bytes, void* workspace, void* stream);
 
 /*
+ * The same fused step with the ListNet loss instead of approxNDCG.   replaces, for a TripleLayerNet ranker,
+ *   architeture/tripleLayer.py:5-17 -> losses/listnet.py:5-16 (apply_sigmoid = False) -> loss.backward()
+ * loss = - sum over the batch of sum_i softmax(y_true)_i log softmax(score)_i over all 128 docs of a slate (the reference gives
+ * padding no special treatment); slate_loss [B]: the per-slate sums.  Arguments as ltr_triple_approx_ndcg_step.
+ */
+int ltr_triple_listnet_step(const float* X, const float* y_true, const float* W1, const float* b1, const float* W2,
+                            const float* b2, const float* W3, const float* b3, int B, int n, int F, const double* disc_prefix,
+                            int disc_len, float* scores, float* slate_loss, float* loss, float* gW1, float* gb1, float* gW2,
+                            float* gb2, float* gW3, float* gb3, void* scratch, size_t scratch_bytes, void* workspace,
+                            void* stream);
+
+/*
  * Slate ingestion (HOST code, host pointers).  replaces utils/dataset.py:33-101 (get_data, load_baseline_file)
  *
  * svmlight / LETOR text "label qid:ID idx:val ... # comment" -> query-major padded arrays.  A new query starts wherever

@@ -108,6 +108,7 @@ struct RankerFusedParams {
     float* part_misc;        // [grid][2]: sum of slate values, sum of ds
     float* part_bias;        // [grid][64]: dbc (32), dw3 (32) in fp32
     int grid;
+    int loss_kind;           // 0: approxNDCG (loss = - mean of the slate values), 1: ListNet (loss = - sum)
     unsigned long long* trace;   // RF_TRACE builds: [role][event][slate] globaltimer stamps of CTA 0 (diagnostics)
 };
 
@@ -249,8 +250,7 @@ struct __align__(16) RfGroup {
     float c[RF_DOCS];             // d loss / d pos_i
     float part[4][RF_DOCS];       // per-warp partial sums of every doc (ranks, then gradients)
     int4 wstat[4];                // per warp: {valid count | bad-label flag << 16, min key, max key, packed label counts}
-    float red[4];
-    float pad_[12];
+    float red[16];                // 4 slots of 4 per-warp values (the ListNet block runs several reductions per slate)
 };
 
 struct RfCtl {
@@ -550,101 +550,126 @@ ranker_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             p.scores[(size_t)slate * RF_DOCS + gt] = sv;
             if (gt == 0) RF_STAMP(g, 2, k);
-            // ---- approxNDCG of the slate (losses/approxNDCG.py:7-53; the K1 kernel's steps) --------------------------------
-            const bool valid = (yv != p.pad);
-            const float yc = fmaxf(yv, 0.f);                      // approxNDCG.py:37-38 clamp
-            const int lvl = (int)fminf(yc, 100.f);
-            const bool small_int = (yc == (float)lvl) && (lvl <= 4);
-            const unsigned bal = __ballot_sync(LTR_FULL_MASK, valid);
-            const unsigned bad = __ballot_sync(LTR_FULL_MASK, valid && !small_int);
-            const int key = float_order_key(sv);
-            const int kmin = __reduce_min_sync(LTR_FULL_MASK, valid ? key : 0x7fffffff);
-            const int kmax = __reduce_max_sync(LTR_FULL_MASK, valid ? key : (int)0x80000000);
-            const unsigned field = (valid && small_int && lvl >= 1) ? (1u << (8 * (lvl - 1))) : 0u;
-            const unsigned cnts = __reduce_add_sync(LTR_FULL_MASK, field);
-            if (lane == 0) sh.wstat[w] = make_int4(__popc(bal) | (bad ? 0x10000 : 0), kmin, kmax, (int)cnts);
-            named_bar_sync(bar, 128);
-            int m = 0, off = 0, any_bad = 0;
-            int gmin = 0x7fffffff, gmax = (int)0x80000000;
-            unsigned packed = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int4 st = sh.wstat[q];
-                const int cnt = st.x & 0xffff;
-                off += (q < w) ? cnt : 0;
-                m += cnt;
-                any_bad |= st.x >> 16;
-                gmin = min(gmin, st.y);
-                gmax = max(gmax, st.z);
-                packed += (unsigned)st.w;
-            }
-            const int dst = off + __popc(bal & ((1u << lane) - 1u));
             float ds = 0.f, slate_val = 0.f;
-            if (m > 0) {
-                // ideal DCG over ALL positions (approxNDCG.py:41-43)
-                float maxdcg, gain;
-                if (!any_bad) {
-                    // labels 0..4: maxDCG = sum_L (2^L - 1)(P[e_L] - P[e_{L+1}]) = 8 P[e4] + 4 P[e3] + 2 P[e2] + P[e1]
-                    const int e4 = packed >> 24;
-                    const int e3 = e4 + ((packed >> 16) & 255);
-                    const int e2 = e3 + ((packed >> 8) & 255);
-                    const int e1 = e2 + (packed & 255);
-                    maxdcg = fmaf(8.0f, ctl.disc[e4], fmaf(4.0f, ctl.disc[e3], fmaf(2.0f, ctl.disc[e2], ctl.disc[e1])));
-                    gain = (float)((1 << lvl) - 1);
-                } else {
-                    // other labels: a doc's ideal rank = how many clamped labels are larger (equal ones: by position)
-                    sh.part[0][gt] = valid ? yc : -1.0f;
-                    named_bar_sync(bar, 128);
-                    const float mine = sh.part[0][gt];
-                    int rank = 0;
-                    for (int j = 0; j < RF_DOCS; ++j) {
-                        const float o = sh.part[0][j];
-                        rank += (o > mine || (o == mine && j < gt)) ? 1 : 0;
-                    }
-                    float term = (mine >= 0.f) ? gain_exp2(mine) / log2f(2.0f + (float)rank) : 0.f;
-                    term = warp_sum(term);
-                    if (lane == 0) sh.red[w] = term;
-                    named_bar_sync(bar, 128);
-                    maxdcg = (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
-                    gain = gain_exp2(yc);
-                    named_bar_sync(bar, 128);
-                }
-                maxdcg = fmaxf(maxdcg, p.eps);
-                gain = valid ? __fdividef(gain, maxdcg) : 0.f;    // G_i (approxNDCG.py:44)
-                // compacted per-doc quantities
-                const float smin = float_from_key(gmin), smax = float_from_key(gmax);
-                const float range = (smax - smin) * scale;
-                const bool fact = (fabsf(range) < 126.0f) && !clamp_pairs;   // false for inf / NaN ranges too
-                const float smid = 0.5f * smin + 0.5f * smax;
-                if (valid) {
-                    if (fact) {
-                        const float tc = (sv - smid) * scale;
-                        sh.u[dst] = ex2_approx(tc);
-                        sh.v[dst] = ex2_approx(-tc);
-                    } else {
-                        sh.u[dst] = sv;
-                    }
-                }
-                if (gt >= m) {                                    // zero tail: p = 0, w = 0 for padding
-                    sh.u[gt] = 0.f;
-                    sh.v[gt] = 0.f;
-                    sh.c[gt] = 0.f;
-                }
+            if (p.loss_kind == 1) {
+                // ---- ListNet of the slate (losses/listnet.py:5-16): - sum_i softmax(y_true)_i log softmax(s)_i over ALL 128 docs --
+                // (the reference gives padding no special treatment: a label of -1 is a label);  d loss / d s = softmax(s) - softmax(y)
+                float* red = sh.red;                                 // 4 x 4 slots (red + pad_): one per reduction of the slate
+                float x = warp_max(sv), yx = warp_max(yv);
+                if (lane == 0) red[w] = x, red[4 + w] = yx;
                 named_bar_sync(bar, 128);
-                float gsum;
-                if (!fact) {
-                    const float si = valid ? sh.u[dst] : 0.f;
-                    float sum = 0.f;
-                    if (valid) sum = rf_direct_rank_sum(sh.u, m, scale, si, p.eps, clamp_pairs);
-                    slate_val = rf_middle(sh, bar, lane, w, valid, dst, gain, coef, sum);
-                    gsum = 0.f;
-                    if (valid) gsum = rf_direct_grad_sum(sh.u, sh.c, m, scale, si, sh.c[dst], p.eps, clamp_pairs);
-                } else if (m > 96) {
-                    gsum = rf_sym_slate<4>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
-                } else {                                          // (no R = 2 copy for short slates: code size)
-                    gsum = rf_sym_slate<3>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
+                const float smax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+                const float ymax = fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]));
+                const float es = ex2_approx((sv - smax) * kLog2e), ey = ex2_approx((yv - ymax) * kLog2e);
+                x = warp_sum(es), yx = warp_sum(ey);
+                if (lane == 0) red[8 + w] = x, red[12 + w] = yx;
+                named_bar_sync(bar, 128);
+                const float ssum = (red[8] + red[9]) + (red[10] + red[11]), ysum = (red[12] + red[13]) + (red[14] + red[15]);
+                const float pt = __fdividef(ey, ysum);
+                const float logp = (sv - smax) - lg2_approx(ssum) * kLn2;
+                x = warp_sum(pt * logp);
+                named_bar_sync(bar, 128);                            // (everyone has read slots 0..7)
+                if (lane == 0) red[w] = x;
+                named_bar_sync(bar, 128);
+                slate_val = (red[0] + red[1]) + (red[2] + red[3]);
+                ds = __fdividef(es, ssum) - pt;
+                named_bar_sync(bar, 128);                            // (the next slate's first reduction writes slot 0 again)
+            } else {
+                // ---- approxNDCG of the slate (losses/approxNDCG.py:7-53; the K1 kernel's steps) --------------------------------
+                const bool valid = (yv != p.pad);
+                const float yc = fmaxf(yv, 0.f);                      // approxNDCG.py:37-38 clamp
+                const int lvl = (int)fminf(yc, 100.f);
+                const bool small_int = (yc == (float)lvl) && (lvl <= 4);
+                const unsigned bal = __ballot_sync(LTR_FULL_MASK, valid);
+                const unsigned bad = __ballot_sync(LTR_FULL_MASK, valid && !small_int);
+                const int key = float_order_key(sv);
+                const int kmin = __reduce_min_sync(LTR_FULL_MASK, valid ? key : 0x7fffffff);
+                const int kmax = __reduce_max_sync(LTR_FULL_MASK, valid ? key : (int)0x80000000);
+                const unsigned field = (valid && small_int && lvl >= 1) ? (1u << (8 * (lvl - 1))) : 0u;
+                const unsigned cnts = __reduce_add_sync(LTR_FULL_MASK, field);
+                if (lane == 0) sh.wstat[w] = make_int4(__popc(bal) | (bad ? 0x10000 : 0), kmin, kmax, (int)cnts);
+                named_bar_sync(bar, 128);
+                int m = 0, off = 0, any_bad = 0;
+                int gmin = 0x7fffffff, gmax = (int)0x80000000;
+                unsigned packed = 0;
+    #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int4 st = sh.wstat[q];
+                    const int cnt = st.x & 0xffff;
+                    off += (q < w) ? cnt : 0;
+                    m += cnt;
+                    any_bad |= st.x >> 16;
+                    gmin = min(gmin, st.y);
+                    gmax = max(gmax, st.z);
+                    packed += (unsigned)st.w;
                 }
-                ds = valid ? p.alpha * gsum : 0.f;                // d loss / d score of this doc
+                const int dst = off + __popc(bal & ((1u << lane) - 1u));
+                if (m > 0) {
+                    // ideal DCG over ALL positions (approxNDCG.py:41-43)
+                    float maxdcg, gain;
+                    if (!any_bad) {
+                        // labels 0..4: maxDCG = sum_L (2^L - 1)(P[e_L] - P[e_{L+1}]) = 8 P[e4] + 4 P[e3] + 2 P[e2] + P[e1]
+                        const int e4 = packed >> 24;
+                        const int e3 = e4 + ((packed >> 16) & 255);
+                        const int e2 = e3 + ((packed >> 8) & 255);
+                        const int e1 = e2 + (packed & 255);
+                        maxdcg = fmaf(8.0f, ctl.disc[e4], fmaf(4.0f, ctl.disc[e3], fmaf(2.0f, ctl.disc[e2], ctl.disc[e1])));
+                        gain = (float)((1 << lvl) - 1);
+                    } else {
+                        // other labels: a doc's ideal rank = how many clamped labels are larger (equal ones: by position)
+                        sh.part[0][gt] = valid ? yc : -1.0f;
+                        named_bar_sync(bar, 128);
+                        const float mine = sh.part[0][gt];
+                        int rank = 0;
+                        for (int j = 0; j < RF_DOCS; ++j) {
+                            const float o = sh.part[0][j];
+                            rank += (o > mine || (o == mine && j < gt)) ? 1 : 0;
+                        }
+                        float term = (mine >= 0.f) ? gain_exp2(mine) / log2f(2.0f + (float)rank) : 0.f;
+                        term = warp_sum(term);
+                        if (lane == 0) sh.red[w] = term;
+                        named_bar_sync(bar, 128);
+                        maxdcg = (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
+                        gain = gain_exp2(yc);
+                        named_bar_sync(bar, 128);
+                    }
+                    maxdcg = fmaxf(maxdcg, p.eps);
+                    gain = valid ? __fdividef(gain, maxdcg) : 0.f;    // G_i (approxNDCG.py:44)
+                    // compacted per-doc quantities
+                    const float smin = float_from_key(gmin), smax = float_from_key(gmax);
+                    const float range = (smax - smin) * scale;
+                    const bool fact = (fabsf(range) < 126.0f) && !clamp_pairs;   // false for inf / NaN ranges too
+                    const float smid = 0.5f * smin + 0.5f * smax;
+                    if (valid) {
+                        if (fact) {
+                            const float tc = (sv - smid) * scale;
+                            sh.u[dst] = ex2_approx(tc);
+                            sh.v[dst] = ex2_approx(-tc);
+                        } else {
+                            sh.u[dst] = sv;
+                        }
+                    }
+                    if (gt >= m) {                                    // zero tail: p = 0, w = 0 for padding
+                        sh.u[gt] = 0.f;
+                        sh.v[gt] = 0.f;
+                        sh.c[gt] = 0.f;
+                    }
+                    named_bar_sync(bar, 128);
+                    float gsum;
+                    if (!fact) {
+                        const float si = valid ? sh.u[dst] : 0.f;
+                        float sum = 0.f;
+                        if (valid) sum = rf_direct_rank_sum(sh.u, m, scale, si, p.eps, clamp_pairs);
+                        slate_val = rf_middle(sh, bar, lane, w, valid, dst, gain, coef, sum);
+                        gsum = 0.f;
+                        if (valid) gsum = rf_direct_grad_sum(sh.u, sh.c, m, scale, si, sh.c[dst], p.eps, clamp_pairs);
+                    } else if (m > 96) {
+                        gsum = rf_sym_slate<4>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
+                    } else {                                          // (no R = 2 copy for short slates: code size)
+                        gsum = rf_sym_slate<3>(sh, bar, gt, k, m, valid, dst, gain, coef, slate_val);
+                    }
+                    ds = valid ? p.alpha * gsum : 0.f;                // d loss / d score of this doc
+                }
             }
 #if !RF_EARLY_F
             // The group's next forward MMA may go (it then runs while dZ is written, ahead of this slate's gradient job in
@@ -910,7 +935,7 @@ __global__ void __launch_bounds__(32 * RF_RED_WARPS) ranker_fused_reduce_kernel(
     } else if (lane == 0) {
         double v = 0.0, d = 0.0;
         for (int q = 0; q < RF_RED_WARPS; ++q) v += dsum[q][0], d += dsum[q][1];
-        p.loss[0] = (float)(-v / (double)p.B);
+        p.loss[0] = p.loss_kind == 1 ? (float)(-v) : (float)(-v / (double)p.B);
         gb3[0] = (float)d;
     }
 }
@@ -1094,13 +1119,13 @@ static int launch_pdl_args(void (*kernel)(Args...), int grid, int threads, cudaS
 static int triple_core(const char* who, const float* X, const float* y_true, const float* Wc, const float* bc, const float* w3,
                        float b3, const float* b3_ptr, int B, int n, int F, float alpha, float eps, float pad_value,
                        const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg, float* loss, float* gWc, float* gbc,
-                       float* gw3, float* gb3, void* scratch, size_t scratch_bytes, cudaStream_t st, bool pdl) {
+                       float* gw3, float* gb3, void* scratch, size_t scratch_bytes, cudaStream_t st, bool pdl, int loss_kind = 0) {
     (void)who;
     if (n != RF_DOCS) return set_error(LTR_EINVAL, "fused ranker step: slates of exactly 128 docs (one MMA tile)");
     if (F < 4 || F > RF_MAX_F || F % 4)
         return set_error(LTR_EINVAL, "fused ranker step: 4 <= F <= 160, F a multiple of 4 (16-byte rows for TMA)");
     if (disc_len < RF_DOCS + 1) return set_error(LTR_EINVAL, "fused ranker step: discount table shorter than 129");
-    if (!(alpha > 0.f)) return set_error(LTR_EINVAL, "fused ranker step: alpha must be positive");
+    if (loss_kind == 0 && !(alpha > 0.f)) return set_error(LTR_EINVAL, "fused ranker step: alpha must be positive");
     if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wc)) % 16)
         return set_error(LTR_EINVAL, "fused ranker step: X and Wc must be 16-byte aligned");
     if (scratch_bytes < ltr_triple_scratch_bytes(B, n, F)) return set_error(LTR_EINVAL, "fused ranker step: scratch too small");
@@ -1118,6 +1143,7 @@ static int triple_core(const char* who, const float* X, const float* y_true, con
     p.part_misc = p.part + (size_t)device_sm_count() * RF_PART;
     p.part_bias = p.part_misc + (size_t)device_sm_count() * 2;
     p.grid = grid;
+    p.loss_kind = loss_kind;
     p.trace = g_rf_trace;
     constexpr size_t RF_SMEM = 1024 + (size_t)RF_NSF * RF_SLOT_BYTES + (size_t)RF_NSD * RF_QSLOT_BYTES + RF_W_BYTES + (size_t)RF_NDZ * RF_DZ_TILE_BYTES +
                                (size_t)RF_G * sizeof(RfGroup) + sizeof(RfCtl);
@@ -1164,18 +1190,19 @@ LTR_API size_t ltr_triple_step_scratch_bytes(int B, int n, int F) {
     return ltr_triple_scratch_bytes(B, n, F) + (size_t)(2 * ltr::RF_H * F + 3 * ltr::RF_H) * sizeof(float);
 }
 
-LTR_API int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, const float* W1, const float* b1, const float* W2,
-                                        const float* b2, const float* W3, const float* b3, int B, int n, int F, float alpha, float eps,
-                                        float pad_value, const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg,
-                                        float* loss, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
-                                        void* scratch, size_t scratch_bytes, void* workspace, void* stream) {
-    using namespace ltr;
-    if (!X || !y_true || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !scores || !slate_ndcg || !loss || !gW1 || !gb1 || !gW2 || !gb2 ||
+namespace ltr {
+// fold -> fused kernel -> partial reduce -> unfold, for either loss
+static int triple_step(const char* who, int loss_kind, const float* X, const float* y_true, const float* W1, const float* b1,
+                       const float* W2, const float* b2, const float* W3, const float* b3, int B, int n, int F, float alpha, float eps,
+                       float pad_value, const double* disc_prefix, int disc_len, float* scores, float* slate_val, float* loss,
+                       float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, void* scratch, size_t scratch_bytes,
+                       void* workspace, void* stream) {
+    if (!X || !y_true || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !scores || !slate_val || !loss || !gW1 || !gb1 || !gW2 || !gb2 ||
         !gW3 || !gb3 || !scratch || !workspace || !disc_prefix || B <= 0)
-        return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: null pointer or empty batch");
-    if (F < 4 || F > RF_MAX_F || F % 4) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: 4 <= F <= 160, F a multiple of 4");
-    if (scratch_bytes < ltr_triple_step_scratch_bytes(B, n, F)) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: scratch too small");
-    if (reinterpret_cast<uintptr_t>(scratch) % 16) return set_error(LTR_EINVAL, "ltr_triple_approx_ndcg_step: scratch must be 16-byte aligned");
+        return set_error(LTR_EINVAL, "fused ranker step: null pointer or empty batch");
+    if (F < 4 || F > RF_MAX_F || F % 4) return set_error(LTR_EINVAL, "fused ranker step: 4 <= F <= 160, F a multiple of 4");
+    if (scratch_bytes < ltr_triple_step_scratch_bytes(B, n, F)) return set_error(LTR_EINVAL, "fused ranker step: scratch too small");
+    if (reinterpret_cast<uintptr_t>(scratch) % 16) return set_error(LTR_EINVAL, "fused ranker step: scratch must be 16-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t core = ltr_triple_scratch_bytes(B, n, F);
     float* Wc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + core);
@@ -1185,14 +1212,34 @@ LTR_API int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, con
     float* gw3 = gbc + RF_H;
     ranker_fold_kernel<<<(RF_H * F + RF_H + 255) / 256, 256, 0, st>>>(W1, b1, W2, b2, F, Wc, bc);
     int rc = (int)cudaGetLastError();
-    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_step (fold)");
-    rc = triple_core("ltr_triple_approx_ndcg_step", X, y_true, Wc, bc, W3, 0.f, b3, B, n, F, alpha, eps, pad_value, disc_prefix, disc_len,
-                     scores, slate_ndcg, loss, gWc, gbc, gw3, gb3, scratch, core, st, true);
+    if (rc) return set_cuda_error(rc, "fused ranker step (fold)");
+    rc = triple_core(who, X, y_true, Wc, bc, W3, 0.f, b3, B, n, F, alpha, eps, pad_value, disc_prefix, disc_len, scores, slate_val, loss,
+                     gWc, gbc, gw3, gb3, scratch, core, st, true, loss_kind);
     if (rc) return rc;
-    rc = launch_pdl_args(ranker_unfold_kernel, (RF_H1 * F + 255) / 256 + RF_H * RF_H1 / 8 + 1, 256, st, W1, b1, W2, (const float*)gWc, (const float*)gbc,
-                         (const float*)gw3, F, gW1, gb1, gW2, gb2, gW3);
-    if (rc) return set_cuda_error(rc, "ltr_triple_approx_ndcg_step (unfold)");
+    rc = launch_pdl_args(ranker_unfold_kernel, (RF_H1 * F + 255) / 256 + RF_H * RF_H1 / 8 + 1, 256, st, W1, b1, W2, (const float*)gWc,
+                         (const float*)gbc, (const float*)gw3, F, gW1, gb1, gW2, gb2, gW3);
+    if (rc) return set_cuda_error(rc, "fused ranker step (unfold)");
     return 0;
+}
+}  // namespace ltr
+
+LTR_API int ltr_triple_approx_ndcg_step(const float* X, const float* y_true, const float* W1, const float* b1, const float* W2,
+                                        const float* b2, const float* W3, const float* b3, int B, int n, int F, float alpha, float eps,
+                                        float pad_value, const double* disc_prefix, int disc_len, float* scores, float* slate_ndcg,
+                                        float* loss, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                                        void* scratch, size_t scratch_bytes, void* workspace, void* stream) {
+    return ltr::triple_step("ltr_triple_approx_ndcg_step", 0, X, y_true, W1, b1, W2, b2, W3, b3, B, n, F, alpha, eps, pad_value,
+                            disc_prefix, disc_len, scores, slate_ndcg, loss, gW1, gb1, gW2, gb2, gW3, gb3, scratch, scratch_bytes,
+                            workspace, stream);
+}
+
+LTR_API int ltr_triple_listnet_step(const float* X, const float* y_true, const float* W1, const float* b1, const float* W2,
+                                    const float* b2, const float* W3, const float* b3, int B, int n, int F, const double* disc_prefix,
+                                    int disc_len, float* scores, float* slate_loss, float* loss, float* gW1, float* gb1, float* gW2,
+                                    float* gb2, float* gW3, float* gb3, void* scratch, size_t scratch_bytes, void* workspace,
+                                    void* stream) {
+    return ltr::triple_step("ltr_triple_listnet_step", 1, X, y_true, W1, b1, W2, b2, W3, b3, B, n, F, 1.0f, 0.f, -1.0f, disc_prefix,
+                            disc_len, scores, slate_loss, loss, gW1, gb1, gW2, gb2, gW3, gb3, scratch, scratch_bytes, workspace, stream);
 }
 
 // Feature-tile TMA stream on its own (measurement; see probe_tma_kernel): bytes moved = reps * B * 128 * F * 4.

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "ltr_triple_step_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ltr_triple_approx_ndcg_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, _P, c_int,
                                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
+    "ltr_triple_listnet_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int,
+                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "ltr_svmlight_scan": (c_int, [c_char_p, c_int, POINTER(c_longlong)]),
     "ltr_svmlight_load": (c_int, [c_char_p, c_longlong, c_longlong, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int]),
     "ltr_baseline_csv_scan": (c_int, [c_char_p, POINTER(c_longlong)]),

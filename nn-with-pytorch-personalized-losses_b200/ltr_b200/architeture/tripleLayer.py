@@ -42,7 +42,7 @@ class _FusedTripleApproxNDCG(torch.autograd.Function):
     gradient of the loss in backward."""
 
     @staticmethod
-    def forward(ctx, X, y_true, W1, b1, W2, b2, W3, b3, eps, pad, alpha):
+    def forward(ctx, X, y_true, W1, b1, W2, b2, W3, b3, eps, pad, alpha, kind):
         lib = _lib.load()
         B, n, F = X.shape
         dev = X.device
@@ -62,10 +62,16 @@ class _FusedTripleApproxNDCG(torch.autograd.Function):
             scratch = _scratch(lib, dev, B, n, F)
             tab = rt.disc_prefix(dev)
             base = flat.data_ptr()
-            _lib.check(lib.ltr_triple_approx_ndcg_step(
-                X.data_ptr(), y_true.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, float(alpha), float(eps), float(pad),
-                tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(), base, *[base + 4 * o for o in offs],
-                scratch.data_ptr(), scratch.numel(), rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_approx_ndcg_step")
+            if kind == "listnet":
+                _lib.check(lib.ltr_triple_listnet_step(
+                    X.data_ptr(), y_true.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, tab.data_ptr(), tab.numel(),
+                    scores.data_ptr(), slate.data_ptr(), base, *[base + 4 * o for o in offs],
+                    scratch.data_ptr(), scratch.numel(), rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_listnet_step")
+            else:
+                _lib.check(lib.ltr_triple_approx_ndcg_step(
+                    X.data_ptr(), y_true.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, float(alpha), float(eps), float(pad),
+                    tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(), base, *[base + 4 * o for o in offs],
+                    scratch.data_ptr(), scratch.numel(), rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_approx_ndcg_step")
         ctx.flat, ctx.offs, ctx.shapes = flat, offs, [t.shape for t in prm]
         ctx.scores = scores
         ctx.slate_ndcg = slate
@@ -77,7 +83,7 @@ class _FusedTripleApproxNDCG(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_scores):
         g = ctx.flat * grad_loss                                  # one launch for all six
         out = [g[o:o + s.numel()].view(s) for o, s in zip(ctx.offs, ctx.shapes)]
-        return (None, None, out[0], out[1], out[2], out[3], out[4], out[5], None, None, None)
+        return (None, None, out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None)
 
 
 def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1., return_scores=False):
@@ -91,7 +97,24 @@ def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-
     X = X.detach().contiguous()
     y = y_true.detach().to(X.device, dtype=torch.float32).contiguous()
     loss, scores = _FusedTripleApproxNDCG.apply(X, y, net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight,
-                                                net.l3.bias, eps, float(padded_value_indicator), alpha)
+                                                net.l3.bias, eps, float(padded_value_indicator), alpha, "approx_ndcg")
+    return (loss, scores) if return_scores else loss
+
+
+def fused_triple_listnet(net, X, y_true, apply_sigmoid=False, return_scores=False):
+    """listnetLoss(y_true, net(X).squeeze(-1)) (losses/listnet.py:5-16, note the reference's argument order) with its backward
+    through `net`, fused like `fused_triple_approx_ndcg`.  X: [batch, 128, F <= 160] CUDA fp32, y_true: [batch, 128]."""
+    rt.require_cuda()
+    if apply_sigmoid:
+        raise NotImplementedError("the fused ListNet step implements the default apply_sigmoid=False (losses/listnet.py:16)")
+    if X.dim() != 3 or X.shape[1] != SLATE or X.shape[2] > MAX_FEATURES or X.shape[2] % 4:
+        raise ValueError(f"the fused step takes [batch, {SLATE}, F] features with F <= {MAX_FEATURES}, F % 4 == 0; got {tuple(X.shape)}")
+    if X.device.type != "cuda" or X.dtype != torch.float32:
+        raise ValueError("the fused step takes CUDA fp32 features")
+    X = X.detach().contiguous()
+    y = y_true.detach().to(X.device, dtype=torch.float32).contiguous()
+    loss, scores = _FusedTripleApproxNDCG.apply(X, y, net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight,
+                                                net.l3.bias, 0.0, -1.0, 1.0, "listnet")
     return (loss, scores) if return_scores else loss
 
 
@@ -108,3 +131,7 @@ class TripleLayerNet(nn.Module):
     def approx_ndcg_loss(self, x, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1.):
         """The fused training step (extension): same value as approxNDCGLoss(self(x).squeeze(-1), y_true, ...)."""
         return fused_triple_approx_ndcg(self, x, y_true, eps, padded_value_indicator, alpha)
+
+    def listnet_loss(self, x, y_true):
+        """The fused training step with ListNet: same value as listnetLoss(y_true, self(x).squeeze(-1))."""
+        return fused_triple_listnet(self, x, y_true)

@@ -242,3 +242,32 @@ def test_folded_entry_equals_whole_step_entry():
         if name in want:
             scale = float(want[name].abs().max())
             assert float((prm.grad - want[name]).abs().max()) <= 2e-4 * scale, name
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("B,F", [(1, 136), (7, 136), (450, 136), (64, 64)])
+def test_fused_listnet_step_matches_torch_modules(B, F):
+    """`ltr_triple_listnet_step` against the stock modules + the oracle's listnetLoss (losses/listnet.py:5-16: a SUM over the
+    batch, every doc of a slate counts, padding labels included) + torch autograd."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet, fused_triple_listnet
+    from oracle import ltr_oracle as O
+    torch.manual_seed(B + F)
+    net = TripleLayerNet(F)
+    g = torch.Generator().manual_seed(B)
+    X = torch.rand(B, 128, F, generator=g)
+    _, y = make_slates(B, 128, seed=B, min_len=64)
+    s_ref = net(X, None, None).squeeze(-1)
+    l_ref = O.listnet_loss(y, s_ref)
+    l_ref.backward()
+    dev_net = TripleLayerNet(F).cuda()
+    dev_net.load_state_dict(net.state_dict())
+    loss, scores = fused_triple_listnet(dev_net, X.cuda(), y.cuda(), return_scores=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert float((scores.cpu() - s_ref.detach()).abs().max()) <= 2e-3 * float(s_ref.detach().abs().max())
+    assert abs(float(loss) - float(l_ref)) <= 2e-3 * abs(float(l_ref))
+    for (name, prm), ref in zip(dev_net.named_parameters(), net.parameters()):
+        scale = net.l3.weight.grad.abs().max() if name == "l3.bias" else ref.grad.abs().max()
+        assert float((prm.grad.cpu() - ref.grad).abs().max()) <= 1e-2 * float(scale) + 1e-9, name
+    again = dev_net.listnet_loss(X.cuda(), y.cuda())
+    assert torch.equal(again.detach(), loss.detach()), "bitwise repeatable"

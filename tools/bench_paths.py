@@ -348,6 +348,14 @@ def bench_ranker_step(iters=30, B=4096, n=128, F=136):
                                             *[t.data_ptr() for t in outs], scr.data_ptr(), nscr, ws.data_ptr(), rt.stream_ptr()))
 
     sec_abi = _time(cabi, iters)
+
+    def cabi_listnet(i):                                    # the same step with the ListNet loss (losses/listnet.py:5-16)
+        X, y = data[i % ring]
+        _ok(lib.ltr_triple_listnet_step(X.data_ptr(), y.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, tab.data_ptr(), tab.numel(),
+                                        scores.data_ptr(), slate.data_ptr(), loss.data_ptr(), *[t.data_ptr() for t in outs],
+                                        scr.data_ptr(), nscr, ws.data_ptr(), rt.stream_ptr()))
+
+    sec_listnet = _time(cabi_listnet, iters)
     torch.backends.cuda.matmul.allow_tf32 = False
     sec_fp32 = _time(stock, max(5, iters // 3))
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -355,7 +363,7 @@ def bench_ranker_step(iters=30, B=4096, n=128, F=136):
     torch.backends.cuda.matmul.allow_tf32 = False
     alg = (4.0 * F * n + 8.0 * n) * B                       # features once, labels in, scores out
     return {"metric": "TripleLayerNet + approxNDCG training step slates/s (n=128, F=136)", "value": B / sec_abi, "unit": "slates/s",
-            "us_per_call": sec_abi * 1e6, "us_per_step_through_autograd": sec * 1e6,
+            "us_per_call": sec_abi * 1e6, "us_per_step_through_autograd": sec * 1e6, "us_per_call_listnet_variant": sec_listnet * 1e6,
             "us_per_step_torch_modules_fp32_plus_K1": sec_fp32 * 1e6, "us_per_step_torch_modules_tf32_plus_K1": sec_tf32 * 1e6,
             "speedup_vs_torch_fp32": sec_fp32 / sec_abi, "speedup_vs_torch_tf32": sec_tf32 / sec_abi,
             "speedup_through_autograd_vs_torch_fp32": sec_fp32 / sec, "speedup_through_autograd_vs_torch_tf32": sec_tf32 / sec,
