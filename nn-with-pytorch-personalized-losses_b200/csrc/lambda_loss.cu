@@ -71,7 +71,7 @@ __device__ __forceinline__ float pair_e(const LDoc& a, const LDoc& b, float sig_
 }
 
 template <int SCHEME, bool FACT>
-__device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b, int ib, float h, const float* dtab,
+__device__ __forceinline__ void lambda_pair(const LDoc& a, const LDoc& b, float h, float dt,
                                             float mu, float sig_scale, float log_eps2, float& loss, float& cnt,
                                             float& ga, float& gb) {
     // docs outside the block carry y = NaN: every ordered comparison with them is false
@@ -99,11 +99,12 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b
         const float u = fmaxf(a.y, 0.f), v = fmaxf(b.y, 0.f);
         w = fabsf(u * u - v * v);
     } else {
+        // dt = |1/D_t - 1/D_{t+1}| at the pair's rank gap t: loaded by the caller once per tile diagonal (the gap of (row r,
+        // column c) of a tile depends on r - c only), not looked up per pair
         const float dg = fabsf(a.g - b.g);
-        const int gap = ia > ib ? ia - ib : ib - ia;
-        if (SCHEME == SCHEME_NDCG2) w = dtab[gap] * dg;
+        if (SCHEME == SCHEME_NDCG2) w = dt * dg;
         else if (SCHEME == SCHEME_LAMBDARANK) w = fabsf(a.d - b.d) * dg;
-        else w = dg * fmaf(mu, dtab[gap], fabsf(a.d - b.d));
+        else w = dg * fmaf(mu, dt, fabsf(a.d - b.d));
     }
     // the better-labelled doc is the first one of the pair
     const float e = FACT ? (a_hi ? a.v * b.s : b.v * a.s) : (a_hi ? pair_e<false>(a, b, sig_scale) : pair_e<false>(b, a, sig_scale));
@@ -114,6 +115,24 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, int ia, const LDoc& b
     dl *= a_hi ? -h : h;                      // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
     ga += dl;
     gb -= dl;
+}
+
+// dtab values of a tile whose rows start at rank `r0` and whose columns start at rank `c0` (different blocks: |r0 - c0| >= R):
+// dv[r - c + R - 1] = dtab[|r0 + r - (c0 + c)|].  Only the schemes with a rank-gap weight read them.
+template <int SCHEME, int R>
+__device__ __forceinline__ void tile_dtab(const float* dtab, int r0, int c0, float (&dv)[2 * R - 1]) {
+    if (SCHEME == SCHEME_NDCG2 || SCHEME == SCHEME_NDCG2PP) {
+        const int bd = r0 - c0;
+        const int s0 = bd < 0 ? -bd : bd;
+#pragma unroll
+        for (int k = 0; k < 2 * R - 1; ++k) {
+            const int off = bd < 0 ? (R - 1 - k) : (k - (R - 1));
+            dv[k] = dtab[min(s0 + off, 255)];                  // (lanes beyond the block read anything: their pairs are masked)
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2 * R - 1; ++k) dv[k] = 0.f;
+    }
 }
 
 // K, Y, G, invD: the slate in rank order (Y = -inf beyond the block); gpart: [4][2][256] floats of shared memory.
@@ -159,8 +178,7 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
             }
 #pragma unroll
             for (int c = r + 1; c < R; ++c)
-                lambda_pair<SCHEME, FACT>(row[r], lane * R + r, row[c], lane * R + c, 1.0f, dtab, mu, sig_scale, log_eps2,
-                                          loss, cnt, g_r[r], g_r[c]);
+                lambda_pair<SCHEME, FACT>(row[r], row[c], 1.0f, dtab[c - r], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_r[c]);
         }
     }
 #pragma unroll 1
@@ -169,12 +187,13 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
         int cblk = lane + D;                   // block visiting this lane at step D
         if (cblk >= T) cblk -= T;
         const int j0 = cblk * R;
+        float dv[2 * R - 1];
+        tile_dtab<SCHEME, R>(dtab, lane * R, j0, dv);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int c = 0; c < R; ++c)
-                lambda_pair<SCHEME, FACT>(row[r], lane * R + r, col[c], j0 + c, h, dtab, mu, sig_scale, log_eps2, loss, cnt,
-                                          g_r[r], g_c[c]);
+                lambda_pair<SCHEME, FACT>(row[r], col[c], h, dv[r - c + R - 1], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_c[c]);
         }
         if (D + 1 < d_hi) {
 #pragma unroll
@@ -281,8 +300,7 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
                 }
 #pragma unroll
                 for (int c = r + 1; c < R; ++c)
-                    lambda_pair<SCHEME, FACT>(row[r], rbase + lane * R + r, row[c], rbase + lane * R + c, 1.0f, dtab, mu,
-                                              sig_scale, log_eps2, loss, cnt, g_r[r], g_r[c]);
+                    lambda_pair<SCHEME, FACT>(row[r], row[c], 1.0f, dtab[c - r], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_r[c]);
             }
         }
 #pragma unroll 1
@@ -291,12 +309,13 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
             int cblk = pos + D;                    // block visiting this lane at step D
             if (cblk >= T) cblk -= T;
             const int j0 = cbase + cblk * R;
+            float dv[2 * R - 1];
+            tile_dtab<SCHEME, R>(dtab, rbase + lane * R, j0, dv);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int c = 0; c < R; ++c)
-                    lambda_pair<SCHEME, FACT>(row[r], rbase + lane * R + r, col[c], j0 + c, h, dtab, mu, sig_scale, log_eps2,
-                                              loss, cnt, g_r[r], g_c[c]);
+                    lambda_pair<SCHEME, FACT>(row[r], col[c], h, dv[r - c + R - 1], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_c[c]);
             }
             if (D + 1 < d_hi) {
 #pragma unroll
