@@ -45,55 +45,45 @@ struct LDoc {
                            // block), gain, 1 / log2(1 + rank);  t = sigma log2(e) s
 };
 
-// log2-probability of one pair from e = exp(-sigma (s_first - s_second)) and its derivative w.r.t. that difference
+// The pair tiles run WITHOUT the two eps clamps of lambdaL.py:51 and only track the smallest log2-sigmoid (mn) and the
+// smallest weighted one (mn2) they produced: a slate none of whose pairs went below log2(eps) -- every slate of real
+// data with the default eps = 1e-10 -- has had no active clamp, so its sums are the reference's; a slate that did is done
+// again by the exact row-per-thread path (the kernel checks mn / mn2 once per slate).  Costs two FMNMX per pair instead
+// of two clamps, two compares and a select.
+// log2-probability of one pair from e = exp(-sigma (s_first - s_second)) = v_first u_second and its derivative
 // (lambdaL.py:51-55 without the final log-base factor, which the caller applies once per slate)
-__device__ __forceinline__ void pair_from_e(float e, float w, float log_eps2, float& lw, float& dl) {
+__device__ __forceinline__ void pair_from_e(float e, float w, float& lw, float& dl, float& mn, float& mn2) {
     const float q = 1.0f + e;
     const float sig = rcp_approx(q);
-    float l2 = -lg2_approx(q);                                    // log2 sigmoid
-    bool open = l2 >= log_eps2;                                   // inner clamp(min=eps) inactive
-    l2 = fmaxf(l2, log_eps2);
+    const float l2 = -lg2_approx(q);                              // log2 sigmoid
     lw = w * l2;                                                  // log2 of (.)^w
-    open = open && (lw >= log_eps2);                              // outer clamp inactive
-    lw = fmaxf(lw, log_eps2);
-    dl = open ? w * (e * sig) : 0.f;                              // w sigma (1 - sig); 1 - sig = e sig
+    mn = fminf(mn, l2);
+    mn2 = fminf(mn2, lw);
+    dl = w * (e * sig);                                           // w sigma (1 - sig); 1 - sig = e sig
 }
 
-// e = exp(-sigma (s_a - s_b)).  FACT: the slate's scaled score range fits the fp32 exponent budget, e is the product
-// of two per-doc factors (no MUFU.EX2, no subtraction, no NaN / range handling per pair); otherwise the direct form
-// with the reference's clamp (+-1e8, subsumed by the exponent cap) and NaN -> 0 (lambdaL.py:49-50).
-template <bool FACT>
-__device__ __forceinline__ float pair_e(const LDoc& a, const LDoc& b, float sig_scale) {
-    if (FACT) return a.v * b.s;
-    float delta = a.s - b.s;
-    delta = (delta != delta) ? 0.f : delta;
-    return ex2_approx(fminf(-sig_scale * delta, 126.0f));
-}
-
-template <int SCHEME, bool FACT>
-__device__ __forceinline__ void lambda_pair(const LDoc& a, const LDoc& b, float h, float dt,
-                                            float mu, float sig_scale, float log_eps2, float& loss, float& cnt,
-                                            float& ga, float& gb) {
-    // docs outside the block carry y = NaN: every ordered comparison with them is false
+// One unordered pair of the block in the factorised form (u = 2^(t - c) in .s, v = 2^-(t - c) in .v; docs outside the block
+// carry u = v = 0 and y = NaN: e = 0, so whatever their weight, they add 0 to the loss and to both gradients).
+// Equal labels: the gain-based weights and the label-difference weights are 0 by themselves; only the constant weight of
+// `None` needs the label comparison.  The number of masked pairs is not counted here (closed form, see the kernel).
+template <int SCHEME>
+__device__ __forceinline__ void lambda_pair(const LDoc& a, const LDoc& b, float h, float dt, float mu, float& loss, float& mn,
+                                            float& mn2, float& ga, float& gb) {
     if (SCHEME == SCHEME_NDCG1) {
         if (!(a.y == a.y) || !(b.y == b.y)) return;
         // no label condition: both ordered pairs are in the mask, weight G_i / D_i of the FIRST doc (lambdaL.py:96-97)
         float l1, d1, l2, d2;
-        pair_from_e(pair_e<FACT>(a, b, sig_scale), a.g * a.d, log_eps2, l1, d1);
-        pair_from_e(pair_e<FACT>(b, a, sig_scale), b.g * b.d, log_eps2, l2, d2);
+        pair_from_e(a.v * b.s, a.g * a.d, l1, d1, mn, mn2);
+        pair_from_e(b.v * a.s, b.g * b.d, l2, d2, mn, mn2);
         loss = fmaf(h, l1 + l2, loss);
-        cnt = fmaf(h, 2.0f, cnt);
         const float dd = h * (d2 - d1);
         ga += dd;
         gb -= dd;
         return;
     }
-    // branch-free: every slot is evaluated and masked (equal labels and non-docs get weight 0), which costs ~20 %
-    // more MUFU work than skipping them but removes a divergent branch + reconvergence per pair
     const bool a_hi = a.y > b.y;
-    const bool differ = a_hi || (a.y < b.y);
     float w;
-    if (SCHEME == SCHEME_NONE) w = 1.0f;
+    if (SCHEME == SCHEME_NONE) w = (a_hi || (a.y < b.y)) ? 1.0f : 0.f;
     else if (SCHEME == SCHEME_GTDIFF) w = fabsf(fmaxf(a.y, 0.f) - fmaxf(b.y, 0.f));
     else if (SCHEME == SCHEME_GTDIFF_POW) {
         const float u = fmaxf(a.y, 0.f), v = fmaxf(b.y, 0.f);
@@ -107,11 +97,10 @@ __device__ __forceinline__ void lambda_pair(const LDoc& a, const LDoc& b, float 
         else w = dg * fmaf(mu, dt, fabsf(a.d - b.d));
     }
     // the better-labelled doc is the first one of the pair
-    const float e = FACT ? (a_hi ? a.v * b.s : b.v * a.s) : (a_hi ? pair_e<false>(a, b, sig_scale) : pair_e<false>(b, a, sig_scale));
+    const float e = a_hi ? a.v * b.s : b.v * a.s;
     float lw, dl;
-    pair_from_e(e, differ ? w : 0.f, log_eps2, lw, dl);           // weight 0: lw = 0, dl = 0
+    pair_from_e(e, w, lw, dl, mn, mn2);
     loss = fmaf(h, lw, loss);
-    cnt += differ ? h : 0.f;
     dl *= a_hi ? -h : h;                      // d(-sum l)/d s_hi = -dl, d/d s_lo = +dl
     ga += dl;
     gb -= dl;
@@ -137,11 +126,12 @@ __device__ __forceinline__ void tile_dtab(const float* dtab, int r0, int c0, flo
 
 // K, Y, G, invD: the slate in rank order (Y = -inf beyond the block); gpart: [4][2][256] floats of shared memory.
 // On exit gpart holds the per-warp row / column partial gradients of positions 0 .. lim-1 (after a barrier).
-// FACT: K holds u = 2^(t - c) and V holds 2^-(t - c) of the block's docs; otherwise K holds the scores (V unused).
-template <int SCHEME, int R, bool FACT>
+// K holds u = 2^(t - c) and V holds 2^-(t - c) of the block's docs.  mn / mn2: see pair_from_e.
+template <int SCHEME, int R>
 __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V, const float* Y, const float* G,
                                                  const float* invD, const float* dtab, int lim, int b, float mu,
-                                                 float sig_scale, float log_eps2, float* gpart, float& loss, float& cnt) {
+                                                 float* gpart, float& loss, float& mn, float& mn2) {
+    constexpr bool FACT = true;
     const float ninf = __int_as_float(0x7fc00000);           // (a quiet NaN marks "not a doc of the block")
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = (lim + R - 1) / R;
@@ -172,13 +162,12 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
         for (int r = 0; r < R; ++r) {
             if (SCHEME == SCHEME_NDCG1 && row[r].y == row[r].y) {
                 float l, dl;
-                pair_from_e(1.0f, row[r].g * row[r].d, log_eps2, l, dl);   // the diagonal: delta = 0
+                pair_from_e(1.0f, row[r].g * row[r].d, l, dl, mn, mn2);    // the diagonal: delta = 0
                 loss += l;
-                cnt += 1.0f;
             }
 #pragma unroll
             for (int c = r + 1; c < R; ++c)
-                lambda_pair<SCHEME, FACT>(row[r], row[c], 1.0f, dtab[c - r], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_r[c]);
+                lambda_pair<SCHEME>(row[r], row[c], 1.0f, dtab[c - r], mu, loss, mn, mn2, g_r[r], g_r[c]);
         }
     }
 #pragma unroll 1
@@ -193,7 +182,7 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int c = 0; c < R; ++c)
-                lambda_pair<SCHEME, FACT>(row[r], col[c], h, dv[r - c + R - 1], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_c[c]);
+                lambda_pair<SCHEME>(row[r], col[c], h, dv[r - c + R - 1], mu, loss, mn, mn2, g_r[r], g_c[c]);
         }
         if (D + 1 < d_hi) {
 #pragma unroll
@@ -225,11 +214,12 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
 // the SAME tile code:  A x A and B x B are symmetric (steps 1..T/2 of a ring of T = ceil(group/4) lanes + the
 // in-block triangle);  A x B is a full ring of 32 lanes, rows from A, columns from B (blocks beyond B are non-docs).
 // The steps of every phase are split over the 4 warps; a lane's row accumulators stay in registers across phases.
-template <int SCHEME, bool FACT>
+template <int SCHEME>
 __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V, const float* Y, const float* G,
                                                   const float* invD, const float* dtab, int lim, int b, float mu,
-                                                  float sig_scale, float log_eps2, float* gpart, float& loss, float& cnt) {
+                                                  float* gpart, float& loss, float& mn, float& mn2) {
     constexpr int R = 4;
+    constexpr bool FACT = true;
     const float qnan = __int_as_float(0x7fc00000);            // (a quiet NaN marks "not a doc of the block")
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int role = (warp + b) & 3;
@@ -294,13 +284,12 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
             for (int r = 0; r < R; ++r) {
                 if (SCHEME == SCHEME_NDCG1 && row[r].y == row[r].y) {
                     float l, dl;
-                    pair_from_e(1.0f, row[r].g * row[r].d, log_eps2, l, dl);   // the diagonal: delta = 0
+                    pair_from_e(1.0f, row[r].g * row[r].d, l, dl, mn, mn2);    // the diagonal: delta = 0
                     loss += l;
-                    cnt += 1.0f;
                 }
 #pragma unroll
                 for (int c = r + 1; c < R; ++c)
-                    lambda_pair<SCHEME, FACT>(row[r], row[c], 1.0f, dtab[c - r], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_r[c]);
+                    lambda_pair<SCHEME>(row[r], row[c], 1.0f, dtab[c - r], mu, loss, mn, mn2, g_r[r], g_r[c]);
             }
         }
 #pragma unroll 1
@@ -315,7 +304,7 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int c = 0; c < R; ++c)
-                    lambda_pair<SCHEME, FACT>(row[r], col[c], h, dv[r - c + R - 1], mu, sig_scale, log_eps2, loss, cnt, g_r[r], g_c[c]);
+                    lambda_pair<SCHEME>(row[r], col[c], h, dv[r - c + R - 1], mu, loss, mn, mn2, g_r[r], g_c[c]);
             }
             if (D + 1 < d_hi) {
 #pragma unroll
@@ -463,31 +452,68 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         // ---- pair loop over the top-k block of real docs -------------------------------------------
         const int lim = kk < m ? kk : m;
         float loss_part = 0.f, cnt_part = 0.f;
-        if (lim <= 256) {
-            // e = exp(-sigma (s_i - s_j)) = 2^-(t_i - c) 2^(t_j - c), t = sigma log2(e) s, while the block's scaled score
-            // range keeps both factors inside fp32 (K is sorted, NaN first: a NaN / inf range takes the direct form)
-            const float range = (lim > 0) ? (K[0] - K[lim - 1]) * sig_scale : 0.f;
-            const bool fact = (lim > 0) && fabsf(range) < 126.0f;
-            if (fact) {
-                const float mid = 0.5f * K[0] + 0.5f * K[lim - 1];
+        // Fast path: blocks of up to 256 docs whose scaled score range keeps e = exp(-sigma (s_i - s_j)) = 2^-(t_i - c) 2^(t_j - c),
+        // t = sigma log2(e) s, inside fp32 as a product of two per-doc factors (K is sorted, NaN first: a NaN / inf range does not
+        // qualify).  The tiles leave the eps clamps out and report whether one would have been active (mn, mn2); such a slate,
+        // like the long and the wide ones, is done by the exact row-per-thread loop below.
+        const float range = (lim > 0) ? (K[0] - K[lim - 1]) * sig_scale : 0.f;
+        bool exact = !(lim > 0 && lim <= 256 && fabsf(range) < 126.0f);
+        if (!exact) {
+            const float mid = 0.5f * K[0] + 0.5f * K[lim - 1];
+            for (int i = tid; i < lim; i += LAMBDA_THREADS) {
+                const float t = (K[i] - mid) * sig_scale;
+                U[i] = ex2_approx(t);
+                V[i] = ex2_approx(-t);
+            }
+            __syncthreads();
+            float mn = 0.f, mn2 = 0.f;
+            if (lim > 64) lambda_sym_slate4<SCHEME>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
+            else lambda_sym_slate<SCHEME, 2>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
+            // (a NaN anywhere -- it cannot come from finite inputs here -- also sends the slate to the exact loop)
+            exact = __syncthreads_or(!(mn >= log_eps2) || !(mn2 >= log_eps2) || !(loss_part == loss_part)) != 0;
+        }
+        if (!exact) {
+            loss_part *= out_scale;                               // log base: 1 (binary) or ln 2 (natural)
+            // number of masked pairs of the block (lambdaL.py:24-30): every ordered pair for ndcgLoss1, otherwise the unordered
+            // pairs of docs with different labels = (lim^2 - sum over label values of count^2) / 2
+            if (SCHEME == SCHEME_NDCG1) {
+                if (tid == 0) cnt_part = (float)lim * (float)lim;
+            } else if (hist) {
+                if (tid < 5) sh_lvl[tid] = 0;
+                __syncthreads();
+                unsigned c01 = 0, c23 = 0, c4 = 0;               // per-thread counts (<= 2 docs per thread): 16-bit fields
                 for (int i = tid; i < lim; i += LAMBDA_THREADS) {
-                    const float t = (K[i] - mid) * sig_scale;
-                    U[i] = ex2_approx(t);
-                    V[i] = ex2_approx(-t);
+                    const int lv = (int)Y[i];
+                    c01 += (lv == 0) ? 1u : ((lv == 1) ? 0x10000u : 0u);
+                    c23 += (lv == 2) ? 1u : ((lv == 3) ? 0x10000u : 0u);
+                    c4 += (lv == 4) ? 1u : 0u;
+                }
+                c01 = __reduce_add_sync(LTR_FULL_MASK, c01);
+                c23 = __reduce_add_sync(LTR_FULL_MASK, c23);
+                c4 = __reduce_add_sync(LTR_FULL_MASK, c4);
+                if ((tid & 31) == 0) {
+                    atomicAdd(&sh_lvl[0], (int)(c01 & 0xffffu));
+                    atomicAdd(&sh_lvl[1], (int)(c01 >> 16));
+                    atomicAdd(&sh_lvl[2], (int)(c23 & 0xffffu));
+                    atomicAdd(&sh_lvl[3], (int)(c23 >> 16));
+                    atomicAdd(&sh_lvl[4], (int)c4);
                 }
                 __syncthreads();
-            }
-#define LTR_SYM(R)                                                                                                      \
-    if (fact) lambda_sym_slate<SCHEME, R, true>(U, V, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part); \
-    else lambda_sym_slate<SCHEME, R, false>(K, nullptr, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part)
-            if (lim > 64) {
-                if (fact) lambda_sym_slate4<SCHEME, true>(U, V, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part);
-                else lambda_sym_slate4<SCHEME, false>(K, nullptr, Y, G, invD, dtab, lim, b, p.mu, sig_scale, log_eps2, gpart, loss_part, cnt_part);
+                if (tid == 0) {
+                    int sq = 0;
+                    for (int L = 0; L < 5; ++L) sq += sh_lvl[L] * sh_lvl[L];
+                    cnt_part = (float)((lim * lim - sq) / 2);
+                }
             } else {
-                LTR_SYM(2);
+                // labels off the 0..4 grid: count the pairs with equal labels directly (rare)
+                int eq = 0;
+                for (int i = tid; i < lim; i += LAMBDA_THREADS) {
+                    const float yi = Y[i];
+                    for (int j = 0; j < i; ++j) eq += (Y[j] == yi) ? 1 : 0;
+                }
+                cnt_part = -(float)eq;
+                if (tid == 0) cnt_part += (float)(lim * (lim - 1) / 2);
             }
-#undef LTR_SYM
-            loss_part *= out_scale;                               // log base: 1 (binary) or ln 2 (natural)
             if (p.grad) {
                 for (int i = tid; i < n; i += LAMBDA_THREADS) {
                     float g = 0.f;
@@ -498,7 +524,8 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
                     p.grad[(size_t)b * n + I[i]] = g * grad_scale;     // docs outside the block / padding: 0
                 }
             }
-        } else
+        } else {
+            loss_part = 0.f;
         for (int i = tid; i < n; i += LAMBDA_THREADS) {
             float g = 0.f;
             if (i < lim) {
@@ -531,6 +558,7 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
                 }
             }
             if (p.grad) p.grad[(size_t)b * n + I[i]] = (i < m) ? g * grad_scale : 0.f;
+        }
         }
         loss_part = warp_sum(loss_part);
         cnt_part = warp_sum(cnt_part);

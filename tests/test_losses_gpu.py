@@ -147,6 +147,30 @@ def test_lambda_options_vs_oracle(kw):
     _check("lambdaLoss", {"y_pred": s, "y_true": y}, kw, f64_slack=True)
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("eps,scale,n", [(1e-3, 3.0, 100), (1e-2, 1.0, 200), (0.3, 0.5, 40)])
+def test_lambda_active_eps_clamps_take_the_exact_path(scheme, eps, scale, n):
+    """The pair tiles run without the two eps clamps of lambdaL.py:51 and hand a slate that WOULD have clamped to the exact
+    row-per-thread loop: large eps / wide scores make the clamps active for many pairs of every slate here."""
+    s, y = make_slates(7, n, seed=int(eps * 1e4) + n, min_len=n // 2, score_scale=scale)
+    _check("lambdaLoss", {"y_pred": s, "y_true": y}, {"weighing_scheme": scheme, "eps": eps}, f64_slack=True)
+    _check("lambdaLoss", {"y_pred": s, "y_true": y}, {"weighing_scheme": scheme, "eps": eps, "reduction": "mean", "k": 30}, f64_slack=True)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_lambda_pair_counts_mean_reduction(scheme):
+    """reduction="mean" divides by the number of masked pairs, which the fast path takes from label counts (integer labels 0..4),
+    from a direct count (fractional labels), or as lim^2 (ndcgLoss1); with and without truncation, with fully padded slates."""
+    s, y = make_slates(10, 130, seed=77, min_len=3, pad_anywhere=True)
+    y[3] = -1.0                                                   # no doc at all
+    y[4, :] = torch.where(y[4] == -1, y[4], torch.full_like(y[4], 2.0))     # one label value: no pair with different labels
+    for kw in (dict(), dict(k=17), dict(k=1)):
+        _check("lambdaLoss", {"y_pred": s, "y_true": y}, dict(weighing_scheme=scheme, reduction="mean", **kw), f64_slack=True)
+    g = torch.Generator().manual_seed(5)
+    yf = torch.where(y == -1, y, torch.round(torch.rand(y.shape, generator=g) * 6.0) / 2.0)        # 0, 0.5, ..., 3
+    _check("lambdaLoss", {"y_pred": s, "y_true": yf}, dict(weighing_scheme=scheme, reduction="mean"), f64_slack=True)
+
+
 def test_lambda_config3_shape_and_ties():
     """BASELINE config 3 shape (256-doc slates, ndcgLoss2PP) on a sample, plus a tie-heavy set where the rank
     positions depend on torch.sort's tie order (up to 1.3e-2 relative if the order were different)."""
