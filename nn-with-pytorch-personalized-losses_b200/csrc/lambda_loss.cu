@@ -342,7 +342,11 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
 }
 
 #ifndef LAMBDA_MIN_CTAS
-#define LAMBDA_MIN_CTAS 4       // resident CTAs per SM the register allocation is tuned for
+#define LAMBDA_MIN_CTAS 7       // resident CTAs per SM the register allocation is tuned for (72 registers, 200 bytes of spills).
+                                // Measured with the clamp-free pair tiles, us per call at 4 / 6 / 7 / 8 CTAs per SM:
+                                //   1024 x 256: 58.0 / 58.9 / 53.0 / 56.1 (7 x 148 = 1036 slots: the batch is ONE wave)
+                                //   4096 x 256: 225 / 170 / 180 / 188;   2048 x 128: 52.0 / 46.5 / 43.4 / 43.8;   1024 x 100: 28.8 / 28.3 / 24.5 / 24.3
+                                // (4 was best for the round-1 code, whose tiles needed 128 registers)
 #endif
 template <int SCHEME>
 __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel(const LambdaParams p) {
