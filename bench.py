@@ -18,8 +18,10 @@ N(0,1), alpha = 10), per GPU.  Slates are independent, so N GPUs each take their
   roofline     SFU (MUFU) roofline of the pairwise kernel: algorithmic 2 SFU ops per ordered valid
                pair / measured kernel time, against the SFU peak measured on this GPU by
                a pure ex2.approx loop in the same run; `roofline_hbm` gives the HBM view.
-  cpu_baseline the oracle port of the reference's CPU algorithm (oracle/ltr_oracle.py, torch CPU,
-               all host threads) on a bounded sample of the same workload.
+  cpu_baseline the reference's CPU algorithm on all host threads, on a bounded sample of the same workload: the UNMODIFIED
+               reference files when they travelled with the tree (baseline/_ref/, git-ignored, copied byte for byte by
+               oracle/install_reference.py in the build container: kind "reference"), else the oracle port
+               (oracle/ltr_oracle.py, pinned to the reference by tests/golden: kind "port").
   ndcg_eval    the second half of BASELINE.json's metric, NDCG@{1,5,10} evaluation queries/s: device-resident value,
                roofline, e2e through `ltr_ndcg_at_k_host` (pinned host labels / scores in, pinned NDCG out) and the
                CPU port of torchNdcg on all host cores.  The driver's parser keeps `config`, `roofline`, `e2e` and
@@ -29,8 +31,7 @@ N(0,1), alpha = 10), per GPU.  Slates are independent, so N GPUs each take their
                us per fwd+bwd step with the in-kernel NVLink exchange and with one all-gather per round, the latency
                of one such all-gather, and a parity flag against the unsharded call on rank 0.
 
-`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to
-the GPU box; the port is pinned to it by tests/golden).
+`--impl reference` times that CPU arm alone.
 """
 from __future__ import annotations
 
@@ -125,12 +126,47 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores
+# CPU arm: the reference's own code when its files travelled with the tree (baseline/_ref/, put there unmodified by
+# oracle/install_reference.py in the build container: kind "reference"), else the oracle port (kind "port")
 # ----------------------------------------------------------------------------------------------
+_REF_MODULES = {}
+
+
+def reference_module(rel):
+    """baseline/_ref/<rel> loaded by path under a private name (the reference's package names `losses` / `utils` are the
+    drop-in packages' names as well), or None when the file is not there."""
+    if rel not in _REF_MODULES:
+        import importlib.util
+        path = os.path.join(ROOT, "baseline", "_ref", rel)
+        mod = None
+        if os.path.exists(path):
+            try:
+                spec = importlib.util.spec_from_file_location("_ltr_ref_" + rel.replace("/", "_")[:-3], path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+            except Exception:
+                mod = None
+        _REF_MODULES[rel] = mod
+    return _REF_MODULES[rel]
+
+
+def cpu_kind():
+    return "reference" if reference_module("losses/approxNDCG.py") is not None else "port"
+
+
+def cpu_what():
+    return ("the UNMODIFIED reference losses/approxNDCG.py from baseline/_ref" if cpu_kind() == "reference"
+            else "oracle/ltr_oracle.py port of losses/approxNDCG.py")
+
+
 def cpu_step(s, y):
-    from oracle import ltr_oracle as O
     sc = s.clone().requires_grad_(True)
-    loss = O.approx_ndcg_loss(sc, y, alpha=ALPHA)
+    ref = reference_module("losses/approxNDCG.py")
+    if ref is not None:
+        loss = ref.approxNDCGLoss(sc, y, alpha=ALPHA)
+    else:
+        from oracle import ltr_oracle as O
+        loss = O.approx_ndcg_loss(sc, y, alpha=ALPHA)
     loss.backward()
     return float(loss)
 
@@ -151,13 +187,17 @@ def cpu_throughput(sample_slates: int, reps: int, seed: int = SEED):
 def _ndcg_cpu_worker(job):
     """One host process: the oracle port of torchNdcg (utils/metrics.py:83-104) at k = 10 over its chunk of queries."""
     seed, q, n = job
-    from oracle import ltr_oracle as O
     torch.set_num_threads(1)
     g = torch.Generator().manual_seed(seed)
     y = torch.randint(0, 5, (q, n), generator=g).float()
     s = torch.randn(q, n, generator=g)
+    ref = reference_module("utils/metrics.py")
     t0 = time.perf_counter()
-    out = O.torch_ndcg(y, s, k=10, return_type="tensor")
+    if ref is not None:
+        out = ref.torchNdcg(y, s, k=10, return_type="tensor")
+    else:
+        from oracle import ltr_oracle as O
+        out = O.torch_ndcg(y, s, k=10, return_type="tensor")
     return time.perf_counter() - t0, float(out.sum())
 
 
@@ -167,15 +207,19 @@ def ndcg_cpu_throughput(queries_per_core: int = 768, n: int = N_DOCS):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     jobs = [(SEED + 7 * i, queries_per_core, n) for i in range(cores)]
-    from oracle import ltr_oracle  # noqa: F401                            (imported once in the parent, forked along)
+    have_ref = reference_module("utils/metrics.py") is not None             # (loaded once in the parent, forked along)
+    if not have_ref:
+        from oracle import ltr_oracle  # noqa: F401
     with mp.get_context("fork").Pool(cores) as pool:
         pool.map(_ndcg_cpu_worker, [(SEED, 8, n)] * cores)                # workers up
         t0 = time.perf_counter()
         pool.map(_ndcg_cpu_worker, jobs, chunksize=1)
         wall = time.perf_counter() - t0
     total = queries_per_core * cores
+    what = ("the UNMODIFIED reference utils/metrics.py:83-104 torchNdcg from baseline/_ref" if have_ref
+            else "oracle/ltr_oracle.py port of utils/metrics.py:83-104 torchNdcg")
     return total / wall, cores, (f"{total} queries x {n} docs, NDCG@10 only (the GPU sweep computes @1, @5 and @10), "
-                                 f"{cores} processes x 1 thread (oracle/ltr_oracle.py port of utils/metrics.py:83-104 torchNdcg)")
+                                 f"{cores} processes x 1 thread ({what})")
 
 
 WORKLOAD = ("approxNDCG alpha=10 fused fwd+bwd, 4096 slates x 128 docs per GPU per step (BASELINE configs[1]), "
@@ -205,9 +249,9 @@ def run_reference_arm(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "device": "host CPU",
                    "sample": f"{sample} slates x {N_DOCS} docs per step (bounded sample of the 4096 x 128 batch)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                          "sample": f"{sample} slates x {N_DOCS} docs per step, {args.steps} steps, torch CPU fp32, "
-                                   f"{cores} threads (oracle/ltr_oracle.py port of losses/approxNDCG.py)"},
+                                   f"{cores} threads ({cpu_what()})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -247,11 +291,11 @@ def run_b200_arm(args, rank, local_rank, world):
     cpu = {}
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sample = ndcg_cpu_throughput()
-        cpu["ndcg"] = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        cpu["ndcg"] = {"value": rate, "unit": "queries/s", "cores": cores, "sample": sample,
+                       "kind": "reference" if reference_module("utils/metrics.py") is not None else "port"}
         rate, cores = cpu_throughput(1024, 3)
-        cpu["approx"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "1024 slates x 128 docs fwd+bwd, best of 3, torch CPU fp32 "
-                                   "(oracle/ltr_oracle.py port of losses/approxNDCG.py)"}
+        cpu["approx"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+                         "sample": f"1024 slates x 128 docs fwd+bwd, best of 3, torch CPU fp32 ({cpu_what()})"}
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
