@@ -271,3 +271,24 @@ def test_fused_listnet_step_matches_torch_modules(B, F):
         assert float((prm.grad.cpu() - ref.grad).abs().max()) <= 1e-2 * float(scale) + 1e-9, name
     again = dev_net.listnet_loss(X.cuda(), y.cuda())
     assert torch.equal(again.detach(), loss.detach()), "bitwise repeatable"
+
+
+@pytest.mark.timeout(300)
+def test_fused_step_propagates_nan_like_the_modules():
+    """A NaN feature of one doc makes that slate's scores NaN in the stock modules and the batch loss NaN in approxNDCGLoss;
+    the fused step must not hide it (and must not hang or trap: the direct-form path takes such a slate)."""
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet, fused_triple_approx_ndcg
+    torch.manual_seed(9)
+    net = TripleLayerNet(136).cuda()
+    g = torch.Generator().manual_seed(9)
+    X = torch.rand(20, 128, 136, generator=g).cuda()
+    _, y = make_slates(20, 128, seed=9, min_len=64)
+    X[3, 5, 17] = float("nan")
+    loss, scores = fused_triple_approx_ndcg(net, X, y.cuda(), alpha=10.0, return_scores=True)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(loss)) and bool(torch.isnan(scores[3, 5]))
+    assert bool(torch.isfinite(scores[0]).all()) and bool(torch.isfinite(scores[4]).all())
+    # and the next call on clean data is clean again
+    X[3, 5, 17] = 0.5
+    loss2 = fused_triple_approx_ndcg(net, X, y.cuda(), alpha=10.0)
+    assert bool(torch.isfinite(loss2))
