@@ -333,6 +333,24 @@ int ltr_triple_listnet_step(const float* X, const float* y_true, const float* W1
                             void* stream);
 
 /*
+ * Average of small tensors over the GPUs of one box through peer memory (no collective library call): the gradient
+ * exchange that follows the fused ranker step under data parallelism.   replaces DistributedDataParallel's gradient
+ * all-reduce in the reference's loop (main_batch_execution.py:120-171: ~13 k floats per step for TripleLayerNet)
+ *   ptrs / counts : nseg <= 8 device segments, at most ltr_peer_xchg_max_floats() floats in total; averaged IN PLACE,
+ *                   every rank gets the same bits.   xchg : this rank's block (ltr_peer_xchg_alloc: ltr_peer_xchg_bytes()
+ *   of cudaMalloc'd, zero-filled memory); peer_xchg[world] : every rank's block as mapped into this process (ltr_ipc_export /
+ *   ltr_ipc_open; peer_xchg[rank] == xchg).  Two launches (push, gather) on `stream`, capturable in a CUDA graph; every rank
+ *   must make the same sequence of calls.  ltr_peer_xchg_status: 1 after a peer failed to arrive within 4 s (results NaN).
+ */
+size_t ltr_peer_xchg_bytes(void);
+int ltr_peer_xchg_max_floats(void);
+int ltr_peer_xchg_alloc(void** xchg);
+int ltr_peer_xchg_free(void* xchg);
+int ltr_peer_xchg_status(const void* xchg, int* status);
+int ltr_peer_allreduce_avg(float* const* ptrs, const int* counts, int nseg, void* xchg, void* const* peer_xchg, int rank,
+                           int world, void* stream);
+
+/*
  * Slate ingestion (HOST code, host pointers).  replaces utils/dataset.py:33-101 (get_data, load_baseline_file)
  *
  * svmlight / LETOR text "label qid:ID idx:val ... # comment" -> query-major padded arrays.  A new query starts wherever

@@ -65,6 +65,12 @@ _SIGNATURES = {
                                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "ltr_triple_listnet_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int,
                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
+    "ltr_peer_xchg_bytes": (c_size_t, []),
+    "ltr_peer_xchg_max_floats": (c_int, []),
+    "ltr_peer_xchg_alloc": (c_int, [POINTER(_P)]),
+    "ltr_peer_xchg_free": (c_int, [_P]),
+    "ltr_peer_xchg_status": (c_int, [_P, POINTER(c_int)]),
+    "ltr_peer_allreduce_avg": (c_int, [POINTER(_P), POINTER(c_int), c_int, _P, POINTER(_P), c_int, c_int, _P]),
     "ltr_svmlight_scan": (c_int, [c_char_p, c_int, POINTER(c_longlong)]),
     "ltr_svmlight_load": (c_int, [c_char_p, c_longlong, c_longlong, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int]),
     "ltr_baseline_csv_scan": (c_int, [c_char_p, POINTER(c_longlong)]),

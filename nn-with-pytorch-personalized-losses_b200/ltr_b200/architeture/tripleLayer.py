@@ -42,7 +42,7 @@ class _FusedTripleApproxNDCG(torch.autograd.Function):
     gradient of the loss in backward."""
 
     @staticmethod
-    def forward(ctx, X, y_true, W1, b1, W2, b2, W3, b3, eps, pad, alpha, kind):
+    def forward(ctx, X, y_true, W1, b1, W2, b2, W3, b3, eps, pad, alpha, kind, group=None):
         lib = _lib.load()
         B, n, F = X.shape
         dev = X.device
@@ -72,6 +72,18 @@ class _FusedTripleApproxNDCG(torch.autograd.Function):
                     X.data_ptr(), y_true.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, float(alpha), float(eps), float(pad),
                     tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(), base, *[base + 4 * o for o in offs],
                     scratch.data_ptr(), scratch.numel(), rt.workspace(dev).data_ptr(), rt.stream_ptr()), "ltr_triple_approx_ndcg_step")
+            if group is not None:
+                # data parallel: the six gradients (one contiguous run of `flat`) are averaged over the ranks right behind the
+                # step -- through peer memory (two small launches, no collective call) or, without peer access, by NCCL
+                import torch.distributed as dist
+                from .. import sharding
+                if dist.get_world_size(group) > 1:
+                    ex = sharding.grad_peer_exchange(group, dev)
+                    if ex is not None and flat.numel() - 4 <= ex.max_floats:
+                        ex.average([flat[4:]])
+                    else:
+                        dist.all_reduce(flat[4:], group=group)
+                        flat[4:].mul_(1.0 / dist.get_world_size(group))
         ctx.flat, ctx.offs, ctx.shapes = flat, offs, [t.shape for t in prm]
         ctx.scores = scores
         ctx.slate_ndcg = slate
@@ -83,12 +95,16 @@ class _FusedTripleApproxNDCG(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_scores):
         g = ctx.flat * grad_loss                                  # one launch for all six
         out = [g[o:o + s.numel()].view(s) for o, s in zip(ctx.offs, ctx.shapes)]
-        return (None, None, out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None)
+        return (None, None, out[0], out[1], out[2], out[3], out[4], out[5], None, None, None, None, None)
 
 
-def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1., return_scores=False):
+def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1., return_scores=False,
+                             process_group=None):
     """approxNDCGLoss(net(X), y_true) with its backward through `net` (a TripleLayerNet-shaped module: l1, l2, l3), fused.
-    X: [batch, 128, F <= 160] CUDA fp32, y_true: [batch, 128]; returns the 0-dim loss (and the [batch, 128] scores)."""
+    X: [batch, 128, F <= 160] CUDA fp32, y_true: [batch, 128]; returns the 0-dim loss (and the [batch, 128] scores).
+    `process_group` (data parallel, extension): the parameter gradients that `backward()` delivers are already AVERAGED over
+    the group's ranks, as DistributedDataParallel would leave them -- use the plain module, not a DDP wrapper; the returned
+    loss stays this rank's own."""
     rt.require_cuda()
     if X.dim() != 3 or X.shape[1] != SLATE or X.shape[2] > MAX_FEATURES or X.shape[2] % 4:
         raise ValueError(f"the fused step takes [batch, {SLATE}, F] features with F <= {MAX_FEATURES}, F % 4 == 0; got {tuple(X.shape)}")
@@ -97,13 +113,15 @@ def fused_triple_approx_ndcg(net, X, y_true, eps=1e-10, padded_value_indicator=-
     X = X.detach().contiguous()
     y = y_true.detach().to(X.device, dtype=torch.float32).contiguous()
     loss, scores = _FusedTripleApproxNDCG.apply(X, y, net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight,
-                                                net.l3.bias, eps, float(padded_value_indicator), alpha, "approx_ndcg")
+                                                net.l3.bias, eps, float(padded_value_indicator), alpha, "approx_ndcg", process_group)
     return (loss, scores) if return_scores else loss
 
 
-def fused_triple_listnet(net, X, y_true, apply_sigmoid=False, return_scores=False):
+def fused_triple_listnet(net, X, y_true, apply_sigmoid=False, return_scores=False, process_group=None):
     """listnetLoss(y_true, net(X).squeeze(-1)) (losses/listnet.py:5-16, note the reference's argument order) with its backward
-    through `net`, fused like `fused_triple_approx_ndcg`.  X: [batch, 128, F <= 160] CUDA fp32, y_true: [batch, 128]."""
+    through `net`, fused like `fused_triple_approx_ndcg`.  X: [batch, 128, F <= 160] CUDA fp32, y_true: [batch, 128].
+    The loss is a SUM over slates: with `process_group=` the averaged gradients are 1 / world of the whole-batch ones (as under
+    DistributedDataParallel; scale the learning rate or the loss by the world size for the reference's single-process step)."""
     rt.require_cuda()
     if apply_sigmoid:
         raise NotImplementedError("the fused ListNet step implements the default apply_sigmoid=False (losses/listnet.py:16)")
@@ -114,7 +132,7 @@ def fused_triple_listnet(net, X, y_true, apply_sigmoid=False, return_scores=Fals
     X = X.detach().contiguous()
     y = y_true.detach().to(X.device, dtype=torch.float32).contiguous()
     loss, scores = _FusedTripleApproxNDCG.apply(X, y, net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight,
-                                                net.l3.bias, 0.0, -1.0, 1.0, "listnet")
+                                                net.l3.bias, 0.0, -1.0, 1.0, "listnet", process_group)
     return (loss, scores) if return_scores else loss
 
 
@@ -128,10 +146,10 @@ class TripleLayerNet(nn.Module):
     def forward(self, x, mask=None, indices=None):
         return self.l3(torch.sigmoid(self.l2(self.l1(x))))
 
-    def approx_ndcg_loss(self, x, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1.):
+    def approx_ndcg_loss(self, x, y_true, eps=1e-10, padded_value_indicator=-1, alpha=1., process_group=None):
         """The fused training step (extension): same value as approxNDCGLoss(self(x).squeeze(-1), y_true, ...)."""
-        return fused_triple_approx_ndcg(self, x, y_true, eps, padded_value_indicator, alpha)
+        return fused_triple_approx_ndcg(self, x, y_true, eps, padded_value_indicator, alpha, process_group=process_group)
 
-    def listnet_loss(self, x, y_true):
+    def listnet_loss(self, x, y_true, process_group=None):
         """The fused training step with ListNet: same value as listnetLoss(y_true, self(x).squeeze(-1))."""
-        return fused_triple_listnet(self, x, y_true)
+        return fused_triple_listnet(self, x, y_true, process_group=process_group)

@@ -108,3 +108,70 @@ def test_ddp_gradients_equal_the_single_process_whole_batch_gradients():
                 assert np.array_equal(got[r][name][k], got[0][name][k]), "DDP leaves every rank with the same gradients"
             err = float(np.abs(got[0][name][k] - want).max())
             assert err <= 2e-4 * scale + 1e-9, (name, k, err, scale)
+
+
+def _fused_worker(rank, world, port, state, out_q):
+    import sys
+    for p in (ROOT, PKG_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from ltr_b200 import sharding
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LTR_GRAD_P2P"] = "0"        # two processes time-slice ONE GPU here: the torch.distributed fallback of the average
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, y = _make()
+        lo, hi = sharding.shard_bounds(X.shape[0], rank, world)
+        net = TripleLayerNet(X.shape[2]).cuda()
+        net.load_state_dict(state)
+        res = {}
+        for kind in ("approx", "listnet"):
+            net.zero_grad(set_to_none=True)
+            if kind == "approx":
+                loss = net.approx_ndcg_loss(X[lo:hi].cuda(), y[lo:hi].cuda(), alpha=10.0, process_group=dist.group.WORLD)
+            else:
+                loss = net.listnet_loss(X[lo:hi].cuda(), y[lo:hi].cuda(), process_group=dist.group.WORLD)
+            loss.backward()
+            res[kind] = {k: v.grad.detach().cpu().numpy() for k, v in net.named_parameters()}
+        out_q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_fused_step_with_process_group_delivers_the_whole_batch_gradients():
+    """`net.approx_ndcg_loss(..., process_group=)`: the plain module, gradients averaged over the ranks inside the step (here by
+    torch.distributed; the NVLink peer-memory form needs two GPUs, tests/test_multigpu.py) == the one-process gradients of the
+    whole batch (approxNDCG is a mean over slates and the shards are equal; ListNet is a sum, so its average is 1 / world of it)."""
+    import torch.multiprocessing as mp
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    world = 2
+    torch.manual_seed(4)
+    ref_net = TripleLayerNet(136).cuda()
+    state = {k: v.detach().cpu() for k, v in ref_net.state_dict().items()}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, world, port, state, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=500) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X, y = _make()
+    for kind in ("approx", "listnet"):
+        ref_net.zero_grad(set_to_none=True)
+        loss = ref_net.approx_ndcg_loss(X.cuda(), y.cuda(), alpha=10.0) if kind == "approx" else ref_net.listnet_loss(X.cuda(), y.cuda())
+        loss.backward()
+        for k, v in ref_net.named_parameters():
+            want = v.grad.detach().cpu().numpy()
+            scale = float(np.abs(want).max()) if k != "l3.bias" else float(ref_net.l3.weight.grad.abs().max())
+            assert np.array_equal(got[0][kind][k], got[1][kind][k]), "every rank holds the same averaged gradients"
+            # listnetLoss is a SUM over slates (losses/listnet.py:16): the ranks' average is 1 / world of the whole-batch gradient
+            err = float(np.abs(got[0][kind][k] * (world if kind == "listnet" else 1) - want).max())
+            assert err <= 1e-4 * scale + 1e-9, (kind, k, err, scale)
