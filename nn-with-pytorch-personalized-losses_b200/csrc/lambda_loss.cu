@@ -12,6 +12,8 @@
 //      3 MUFU (ex2, rcp, lg2) + ~15 FP32; the B x n x n tensors of the reference never exist.
 // `ndcgLoss1_scheme` has no label condition (lambdaL.py:26): every ordered pair of real docs, the diagonal
 // included, is in the mask with weight G_i / D_i.
+#include <stdlib.h>
+
 #include "lambda_common.cuh"
 #include "ltr_host.h"
 #include "sort_common.cuh"
@@ -31,7 +33,21 @@ struct LambdaParams {
     float* slate_cnt;           // [B] number of masked pairs
     float* grad;                // [B, n] d(-sum)/d y_pred, unscaled; null = forward only
     unsigned* next;             // next-slate counter in the caller's workspace (left at 0), or null: static assignment
+    // longest-slate-first schedule (lambda_order_kernel), or null: slates in index order
+    const unsigned* order;      // [B] slate indices by decreasing pair work
+    unsigned* claimed;          // [B] one-wave form: claim flag of order[i]
+    unsigned* arrive;           // [LAMBDA_ARRIVE] one-wave form: CTAs that have started on SM (smid % nsm)
+    unsigned* cursor;           // one-wave form: steal cursor (from the short end of `order`)
+    int one_wave, nsm;          // every CTA takes exactly one slate (grid == B, all resident) / SMs of the device
+    // the last CTA to leave reduces the slates' sums (no second launch), or null: lambda_finish_kernel does
+    unsigned* finished;         // exited-CTA counter in the workspace (left at 0)
+    float* loss;                // [1] -sum, or -sum / count for reduction "mean"
+    float* count_out;           // [1] number of masked pairs, or null
+    int mean;
 };
+constexpr int LAMBDA_ORDER_MAX_B = 4096;        // batches the schedule is built for (its arrays live in the workspace)
+constexpr int LAMBDA_ARRIVE = 1024;
+constexpr int LAMBDA_KEYS = 512;                // work classes: block lengths 0..256 one by one, longer ones by eights
 
 // ---- symmetric pair schedule for top-k blocks of up to 256 docs --------------------------------------
 // Same block-circulant ownership as the approxNDCG fast path: lane a of every warp owns R consecutive
@@ -367,11 +383,12 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
     const float ninf = __int_as_float(0xff800000);
     const int tid = threadIdx.x;
 
-    pdl_prologue();
+    // (the tables depend on nothing the previous kernel on the stream wrote: built while it drains)
     for (int r = tid; r < n; r += LAMBDA_THREADS) invD[r] = 1.0f / log2f(2.0f + (float)r);
     __syncthreads();
 
     for (int t = tid; t < n; t += LAMBDA_THREADS) dtab[t] = (t == 0) ? 0.f : fabsf(invD[t - 1] - invD[t]);   // lambdaL.py:101-104
+    pdl_prologue();
     const float sig_scale = p.sigma * kLog2e;
     const float log_eps2 = log2f(p.eps);
     const float out_scale = p.natural_log ? kLn2 : 1.0f;
@@ -382,6 +399,37 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
     // from a counter as they finish instead of a fixed share
     __shared__ int sh_next;
     int b = blockIdx.x;
+    if (p.order) {
+        // Longest first.  Several waves: the resident CTAs start on the longest slates and take the next-longest from the
+        // counter as they finish, so the tail of the launch is made of the shortest ones.  One wave (every slate has its own
+        // resident CTA, nothing can be handed out later): what finishes last is the SM with the most pair work, so the k-th
+        // CTA to start on SM s takes entry k * nsm + (s or nsm - 1 - s, alternating with k) of the sorted list -- every SM gets
+        // one slate of every length class, in snake order, and the per-SM totals agree to a percent instead of +-25 %.
+        // Whatever the hardware's placement, claim flags keep it exact: an entry is taken once; a CTA whose entry does not
+        // exist or is gone steals from the short end.
+        if (tid == 0) {
+            int item = -1;
+            if (p.one_wave) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                const int s = (int)(smid % (unsigned)p.nsm);
+                const unsigned k = atomicAdd(p.arrive + (s & (LAMBDA_ARRIVE - 1)), 1u);
+                const long long pos = (long long)k * p.nsm + ((k & 1u) ? p.nsm - 1 - s : s);
+                if (pos < p.B && atomicCAS(p.claimed + pos, 0u, 1u) == 0u) item = (int)pos;
+                while (item < 0) {
+                    const unsigned q = atomicAdd(p.cursor, 1u);
+                    if (q >= (unsigned)p.B) break;
+                    if (atomicCAS(p.claimed + (p.B - 1 - (int)q), 0u, 1u) == 0u) item = p.B - 1 - (int)q;
+                }
+            } else {
+                item = blockIdx.x;
+            }
+            sh_next = (item >= 0 && item < p.B) ? (int)__ldcg(p.order + item) : p.B;
+        }
+        __syncthreads();
+        b = sh_next;
+        __syncthreads();
+    }
     while (b < p.B) {
         const float* sp = p.y_pred + (size_t)b * n;
         const float* yp = p.y_true + (size_t)b * n;
@@ -572,11 +620,121 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         if (tid == 0) {
             p.slate_sum[b] = (red[0] + red[1]) + (red[2] + red[3]);
             p.slate_cnt[b] = (red[8] + red[9]) + (red[10] + red[11]);
-            sh_next = p.next ? (int)(gridDim.x + atomicAdd(p.next, 1u)) : b + (int)gridDim.x;
+            if (p.order) {
+                const unsigned idx = p.one_wave ? (unsigned)p.B : gridDim.x + atomicAdd(p.next, 1u);
+                sh_next = idx < (unsigned)p.B ? (int)__ldcg(p.order + idx) : p.B;
+            } else {
+                sh_next = p.next ? (int)(gridDim.x + atomicAdd(p.next, 1u)) : b + (int)gridDim.x;
+            }
         }
         __syncthreads();
         b = sh_next;
     }
+    if (p.finished) {
+        __shared__ double fin[2][LAMBDA_THREADS / 32];
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            sh_m = (atomicAdd(p.finished, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!sh_m) return;
+        __threadfence();
+        double ts = 0.0, tc = 0.0;
+        for (int i = tid; i < p.B; i += LAMBDA_THREADS) ts += (double)__ldcg(p.slate_sum + i), tc += (double)__ldcg(p.slate_cnt + i);
+        ts = warp_sum(ts);
+        tc = warp_sum(tc);
+        if ((tid & 31) == 0) fin[0][tid >> 5] = ts, fin[1][tid >> 5] = tc;
+        __syncthreads();
+        if (tid == 0) {
+            ts = tc = 0.0;
+            for (int w = 0; w < LAMBDA_THREADS / 32; ++w) ts += fin[0][w], tc += fin[1][w];
+            p.loss[0] = p.mean ? (float)(-ts / tc) : (float)(-ts);
+            if (p.count_out) p.count_out[0] = (float)tc;
+            *p.finished = 0u;
+            if (p.next) *p.next = 0u;
+        }
+    }
+}
+
+// The schedule of lambda_kernel: slates by decreasing pair work (the length of the top-k block of real docs; the pair loop is
+// quadratic in it).  A warp counts one slate's real docs; the last CTA to finish counting-sorts the B keys (512 work classes)
+// and clears the claim flags / arrival counters of the one-wave form.  `words` = the schedule's corner of the workspace:
+// keys[LAMBDA_ORDER_MAX_B] | order[LAMBDA_ORDER_MAX_B] | claimed[LAMBDA_ORDER_MAX_B] | arrive[LAMBDA_ARRIVE] | cursor -- a region
+// other kernels use as scratch too, so everything in it is rewritten per call; `done` is a counter word that is left at 0.
+__device__ __forceinline__ void lambda_order_body(const float* __restrict__ y_true, int B, int n, int k, float pad, unsigned* words,
+                                                  unsigned* done) {
+    __shared__ unsigned hist[LAMBDA_KEYS], start[LAMBDA_KEYS], wtot[8];
+    __shared__ int sh_last;
+    unsigned* keys = words;
+    unsigned* order = words + LAMBDA_ORDER_MAX_B;
+    unsigned* claimed = order + LAMBDA_ORDER_MAX_B;
+    unsigned* arrive = claimed + LAMBDA_ORDER_MAX_B;
+    unsigned* cursor = arrive + LAMBDA_ARRIVE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The dependent launch (lambda_kernel, a grid that fills every SM) is released at the END of this kernel: released at the
+    // top, its CTAs pile onto the SMs while the sort below runs and the pair of launches takes 250 us instead of 50 (measured).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int b = blockIdx.x * 8 + warp;
+    if (b < B) {
+        const float* yp = y_true + (size_t)b * n;
+        int cnt = 0;
+        for (int i = lane; i < n; i += 32) cnt += (__ldg(yp + i) == pad) ? 0 : 1;
+        cnt = __reduce_add_sync(LTR_FULL_MASK, cnt);
+        const int kk = (k >= 0 && k < n) ? k : n;
+        const int lim = cnt < kk ? cnt : kk;
+        if (lane == 0) keys[b] = (unsigned)(lim <= 256 ? lim : 256 + (lim >> 3));       // < LAMBDA_KEYS for n <= 2048
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sh_last) return;                        // (an exited CTA counts as having released the dependent launch)
+    __threadfence();
+    for (int i = tid; i < LAMBDA_KEYS; i += 256) hist[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < B; i += 256) atomicAdd(&hist[__ldcg(keys + i)], 1u);
+    __syncthreads();
+    // start[c] = number of slates in classes above c: thread t owns classes 511 - 2t and 510 - 2t
+    const int c0 = LAMBDA_KEYS - 1 - 2 * tid, c1 = c0 - 1;
+    const unsigned h0 = hist[c0], h1 = hist[c1];
+    unsigned incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(LTR_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    unsigned base = incl - (h0 + h1);
+    for (int w = 0; w < warp; ++w) base += wtot[w];
+    start[c0] = base;
+    start[c1] = base + h0;
+    __syncthreads();
+    for (int i = tid; i < LAMBDA_KEYS; i += 256) hist[i] = 0u;                   // (now the fill counts of the classes)
+    __syncthreads();
+    for (int i = tid; i < B; i += 256) {
+        const unsigned c = __ldcg(keys + i);
+        order[start[c] + atomicAdd(&hist[c], 1u)] = (unsigned)i;
+        claimed[i] = 0u;
+    }
+    for (int i = tid; i < LAMBDA_ARRIVE; i += 256) arrive[i] = 0u;
+    if (tid == 0) {
+        *cursor = 0u;
+        *done = 0u;
+    }
+    asm volatile("griddepcontrol.launch_dependents;");
+}
+
+struct LambdaOrderArgs {
+    const float* y_true;
+    int B, n, k;
+    float pad;
+    unsigned* words;
+    unsigned* done;
+};
+__global__ void __launch_bounds__(256) lambda_order_kernel_p(const LambdaOrderArgs a) {
+    lambda_order_body(a.y_true, a.B, a.n, a.k, a.pad, a.words, a.done);
 }
 
 // loss = -sum (reduction "sum") or -sum / count ("mean"); for "mean" the gradient is scaled by 1/count too.
@@ -633,11 +791,33 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
     p.eps = eps; p.pad = pad_value; p.sigma = sigma; p.mu = mu; p.natural_log = natural_log;
     p.slate_sum = slate_sum; p.slate_cnt = slate_count; p.grad = grad;
     p.next = workspace ? ws_counter(workspace, LTR_WS_LAMBDA_COUNTER) : nullptr;
+    p.finished = workspace ? ws_counter(workspace, LTR_WS_LAMBDA_FINISHED) : nullptr;
+    p.loss = loss; p.count_out = pair_count; p.mean = reduction_mean;
     const size_t smem = ((size_t)p.len * 6 + 10 * 256) * sizeof(float);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int cap = device_sm_count() * 8;
-    const int grid = B < cap ? B : cap;
+    const int nsm = device_sm_count();
+    const int cap = nsm * 8;
+    int grid = B < cap ? B : cap;
     int rc = 0;
+    // Longest-first schedule.  It costs a launch of ~4 us and pays where the slates' pair work differs and several share an SM
+    // (us per call without / with it, valid lengths U{n/2..n}: 600 x 256: 49.8 / 39.0, 1500 x 256: 73.7 / 71.2,
+    // 4096 x 256: 171.3 / 164.5, 1024 x 256: 50.7 / 50.3; short slates lose: 2048 x 128: 40.8 / 44.6, 1024 x 100: 20.7 / 25.1)
+    p.order = nullptr; p.claimed = nullptr; p.arrive = nullptr; p.cursor = nullptr; p.one_wave = 0; p.nsm = nsm;
+    static const bool no_order = getenv("LTR_LAMBDA_NO_ORDER") != nullptr;
+    if (workspace && !no_order && n > 128 && B >= 2 * nsm && B <= LAMBDA_ORDER_MAX_B) {
+        unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + 1024);
+        static_assert(1024 + (3 * LAMBDA_ORDER_MAX_B + LAMBDA_ARRIVE + 2) * 4 <= LTR_WS_RISK_PART1, "schedule overflows its workspace corner");
+        const LambdaOrderArgs oa{y_true, B, n, k, pad_value, words, ws_counter(workspace, LTR_WS_LAMBDA_ORDER_DONE)};
+        rc = launch_pdl(lambda_order_kernel_p, (B + 7) / 8, 256, 0, st, oa);
+        if (rc) return set_cuda_error(rc, "ltr_lambda_fwdbwd (schedule)");
+        const int resident = nsm * LAMBDA_MIN_CTAS;
+        p.order = words + LAMBDA_ORDER_MAX_B;
+        p.claimed = words + 2 * LAMBDA_ORDER_MAX_B;
+        p.arrive = words + 3 * LAMBDA_ORDER_MAX_B;
+        p.cursor = p.arrive + LAMBDA_ARRIVE;
+        p.one_wave = B <= resident ? 1 : 0;
+        grid = B < resident ? B : resident;
+    }
     switch (scheme) {
         case SCHEME_NONE: rc = launch_lambda<SCHEME_NONE>(p, smem, grid, st); break;
         case SCHEME_NDCG1: rc = launch_lambda<SCHEME_NDCG1>(p, smem, grid, st); break;
@@ -648,6 +828,7 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
         default: rc = launch_lambda<SCHEME_GTDIFF_POW>(p, smem, grid, st); break;
     }
     if (rc) return rc;
+    if (p.finished && !(reduction_mean && grad)) return 0;         // (the mean's gradient scaling is the second launch)
     const long long total = (long long)B * n;
     int fgrid = reduction_mean && grad ? (int)((total + 256 * 8 - 1) / (256 * 8)) : 1;
     if (fgrid > cap) fgrid = cap;

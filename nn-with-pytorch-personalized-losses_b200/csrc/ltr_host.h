@@ -16,7 +16,8 @@ int upload_disc_prefix_constant();                   // P[0..128] -> the constan
 // ---- layout of the caller-provided workspace (LTR_WORKSPACE_BYTES, zero-filled once) -------------------------
 //   u32 [0..4]    approxNDCG: next-slate counter, finished-CTA counter, 64-bit fixed-point loss sum, non-finite flag
 //   u32 [16]      streaming kernels: finished-CTA counter
-//   u32 [18]      LambdaLoss: next-slate counter
+//   u32 [17..19]  LambdaLoss: exited-CTA counter, next-slate counter; schedule kernel: finished-CTA counter
+//   byte 1024 ..  LambdaLoss schedule (batches of 296..4096 slates): keys, order, claim flags, arrival counters (rewritten per call)
 //   f32 [32..35]  ordinal: BCE sum, number of valid docs, #targets < 0, #inputs outside [0, 1]
 //   u32 [20..22]  risk losses: finished-CTA counters of phases A and B (three-launch form); cooperative kernel: generation
 //   byte 1024 ..  streaming kernels: per-CTA fp64 partial sums, [grid <= 2048][4]
@@ -35,6 +36,8 @@ static_assert((size_t)LTR_WS_RISK_COOP_MAX_GRID * 4 * 16 <= LTR_WS_RISK_PART2 - 
 inline double* ws_risk_part1(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + LTR_WS_RISK_PART1); }
 inline double* ws_risk_part2(void* ws) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + LTR_WS_RISK_PART2); }
 constexpr int LTR_WS_LAMBDA_COUNTER = 18;             // LambdaLoss: next-slate counter
+constexpr int LTR_WS_LAMBDA_FINISHED = 17;            // LambdaLoss: exited-CTA counter (the last one reduces the slates' sums)
+constexpr int LTR_WS_LAMBDA_ORDER_DONE = 19;          // LambdaLoss schedule: finished-CTA counter
 constexpr int LTR_WS_ORDINAL_SUMS = 32;
 inline unsigned* ws_counter(void* ws, int idx) { return reinterpret_cast<unsigned*>(ws) + idx; }
 inline float* ws_floats(void* ws, int idx) { return reinterpret_cast<float*>(ws) + idx; }

@@ -147,6 +147,30 @@ def test_lambda_dynamic_slate_handout(B, scheme):
     assert torch.equal(a, lambdaLoss(s.cuda(), y.cuda(), weighing_scheme=scheme))
 
 
+@pytest.mark.parametrize("B,n,scheme,kw", [
+    (400, 200, "ndcgLoss2PP_scheme", {}),                         # one wave, fewer CTAs than SM slots: snake + steals
+    (1036, 160, "ndcgLoss1_scheme", {}),                          # one wave, every slot taken
+    (1300, 160, "ndcgLoss2PP_scheme", {}),                        # two waves: longest first through the counter
+    (700, 192, "lamdbaRank_scheme", {"reduction": "mean"}),       # the mean's second launch behind the in-kernel reduction
+    (500, 300, "ndcgLoss2PP_scheme", {"k": 40}),                  # long rows, short top-k blocks (work classes by k)
+])
+def test_lambda_longest_first_schedule(B, n, scheme, kw):
+    """Batches of 296..4096 slates of more than 128 docs run in the order lambda_order_kernel builds (longest top-k block
+    first; one wave: per-SM snake with claim flags): every slate exactly once -- loss and all gradients against the oracle --,
+    the schedule's corner of the workspace shared with the ListNet kernels' partial sums, the counters left at zero."""
+    from ltr_b200.losses.lambdaL import lambdaLoss
+    from ltr_b200.losses.listnet import listnetLoss
+    s, y = make_slates(B, n, seed=B + n, min_len=n // 3)
+    grad = _lambda_vs_oracle(s, y, weighing_scheme=scheme, **kw)
+    sd, yd = s.cuda(), y.cuda()
+    a = lambdaLoss(sd, yd, weighing_scheme=scheme, **kw)
+    listnetLoss(yd.clamp_min(0), sd)                                 # writes its per-CTA partials over the schedule's arrays
+    x = sd.clone().requires_grad_(True)
+    b = lambdaLoss(x, yd, weighing_scheme=scheme, **kw)
+    b.backward()
+    assert torch.equal(a, b) and torch.equal(x.grad, grad)
+
+
 @pytest.mark.parametrize("B,n", [(3, 300), (2, 700), (2, 2048)])
 @pytest.mark.parametrize("scheme", ["ndcgLoss2PP_scheme", "ndcgLoss1_scheme", None])
 def test_lambda_long_slates(B, n, scheme):
