@@ -44,6 +44,7 @@ struct LambdaParams {
     float* loss;                // [1] -sum, or -sum / count for reduction "mean"
     float* count_out;           // [1] number of masked pairs, or null
     int mean;
+    int force_track;            // debugging: never take the untracked tiles
 };
 constexpr int LAMBDA_ORDER_MAX_B = 4096;        // batches the schedule is built for (its arrays live in the workspace)
 constexpr int LAMBDA_ARRIVE = 1024;
@@ -82,9 +83,32 @@ __device__ __forceinline__ void pair_from_e(float e, float w, float& lw, float& 
 // carry u = v = 0 and y = NaN: e = 0, so whatever their weight, they add 0 to the loss and to both gradients).
 // Equal labels: the gain-based weights and the label-difference weights are 0 by themselves; only the constant weight of
 // `None` needs the label comparison.  The number of masked pairs is not counted here (closed form, see the kernel).
+// TRACK = false (the kernel has bounded the slate's log2-sigmoids and pair weights from its score range and label range: no
+// clamp can become active, nothing to track) and a gain-difference weight: the SIGNED weight ws = h (g_a - g_b)(mu dt + |dd|)
+// carries which doc is the better-labelled one (gains grow with the label), so the loss term is |ws| log2 sig and the
+// gradient pair is -+ ws (1 - sig), with no label in the tile at all: 16 instructions per pair instead of 21.
 template <int SCHEME>
+constexpr bool lambda_gain_scheme() { return SCHEME == SCHEME_NDCG2 || SCHEME == SCHEME_LAMBDARANK || SCHEME == SCHEME_NDCG2PP; }
+
+template <int SCHEME, bool TRACK>
 __device__ __forceinline__ void lambda_pair(const LDoc& a, const LDoc& b, float h, float dt, float mu, float& loss, float& mn,
                                             float& mn2, float& ga, float& gb) {
+    if (!TRACK && lambda_gain_scheme<SCHEME>()) {
+        const float dgs = a.g * h - b.g * h;                   // (h = 1 or 1/2: exact; the products are shared by the tile's pairs)
+        float t;
+        if (SCHEME == SCHEME_NDCG2) t = dt;
+        else if (SCHEME == SCHEME_LAMBDARANK) t = fabsf(a.d - b.d);
+        else t = fmaf(mu, dt, fabsf(a.d - b.d));
+        const float ws = dgs * t;
+        const float e = dgs > 0.f ? a.v * b.s : b.v * a.s;     // equal gains: ws = 0, either e will do
+        const float q = 1.0f + e;
+        const float sig = rcp_approx(q);
+        loss = fmaf(fabsf(ws), -lg2_approx(q), loss);
+        const float dl = ws * (e * sig);
+        ga -= dl;
+        gb += dl;
+        return;
+    }
     if (SCHEME == SCHEME_NDCG1) {
         if (!(a.y == a.y) || !(b.y == b.y)) return;
         // no label condition: both ordered pairs are in the mask, weight G_i / D_i of the FIRST doc (lambdaL.py:96-97)
@@ -143,7 +167,7 @@ __device__ __forceinline__ void tile_dtab(const float* dtab, int r0, int c0, flo
 // K, Y, G, invD: the slate in rank order (Y = -inf beyond the block); gpart: [4][2][256] floats of shared memory.
 // On exit gpart holds the per-warp row / column partial gradients of positions 0 .. lim-1 (after a barrier).
 // K holds u = 2^(t - c) and V holds 2^-(t - c) of the block's docs.  mn / mn2: see pair_from_e.
-template <int SCHEME, int R>
+template <int SCHEME, int R, bool TRACK>
 __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V, const float* Y, const float* G,
                                                  const float* invD, const float* dtab, int lim, int b, float mu,
                                                  float* gpart, float& loss, float& mn, float& mn2) {
@@ -183,7 +207,7 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
             }
 #pragma unroll
             for (int c = r + 1; c < R; ++c)
-                lambda_pair<SCHEME>(row[r], row[c], 1.0f, dtab[c - r], mu, loss, mn, mn2, g_r[r], g_r[c]);
+                lambda_pair<SCHEME, TRACK>(row[r], row[c], 1.0f, dtab[c - r], mu, loss, mn, mn2, g_r[r], g_r[c]);
         }
     }
 #pragma unroll 1
@@ -198,14 +222,14 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int c = 0; c < R; ++c)
-                lambda_pair<SCHEME>(row[r], col[c], h, dv[r - c + R - 1], mu, loss, mn, mn2, g_r[r], g_c[c]);
+                lambda_pair<SCHEME, TRACK>(row[r], col[c], h, dv[r - c + R - 1], mu, loss, mn, mn2, g_r[r], g_c[c]);
         }
         if (D + 1 < d_hi) {
 #pragma unroll
             for (int c = 0; c < R; ++c) {
                 col[c].s = __shfl_sync(LTR_FULL_MASK, col[c].s, src);
                 if (FACT) col[c].v = __shfl_sync(LTR_FULL_MASK, col[c].v, src);
-                col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
+                if (TRACK || !lambda_gain_scheme<SCHEME>()) col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
                 col[c].g = __shfl_sync(LTR_FULL_MASK, col[c].g, src);
                 col[c].d = __shfl_sync(LTR_FULL_MASK, col[c].d, src);
                 g_c[c] = __shfl_sync(LTR_FULL_MASK, g_c[c], src);
@@ -230,7 +254,7 @@ __device__ __forceinline__ void lambda_sym_slate(const float* K, const float* V,
 // the SAME tile code:  A x A and B x B are symmetric (steps 1..T/2 of a ring of T = ceil(group/4) lanes + the
 // in-block triangle);  A x B is a full ring of 32 lanes, rows from A, columns from B (blocks beyond B are non-docs).
 // The steps of every phase are split over the 4 warps; a lane's row accumulators stay in registers across phases.
-template <int SCHEME>
+template <int SCHEME, bool TRACK>
 __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V, const float* Y, const float* G,
                                                   const float* invD, const float* dtab, int lim, int b, float mu,
                                                   float* gpart, float& loss, float& mn, float& mn2) {
@@ -305,7 +329,7 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
                 }
 #pragma unroll
                 for (int c = r + 1; c < R; ++c)
-                    lambda_pair<SCHEME>(row[r], row[c], 1.0f, dtab[c - r], mu, loss, mn, mn2, g_r[r], g_r[c]);
+                    lambda_pair<SCHEME, TRACK>(row[r], row[c], 1.0f, dtab[c - r], mu, loss, mn, mn2, g_r[r], g_r[c]);
             }
         }
 #pragma unroll 1
@@ -320,14 +344,14 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int c = 0; c < R; ++c)
-                    lambda_pair<SCHEME>(row[r], col[c], h, dv[r - c + R - 1], mu, loss, mn, mn2, g_r[r], g_c[c]);
+                    lambda_pair<SCHEME, TRACK>(row[r], col[c], h, dv[r - c + R - 1], mu, loss, mn, mn2, g_r[r], g_c[c]);
             }
             if (D + 1 < d_hi) {
 #pragma unroll
                 for (int c = 0; c < R; ++c) {
                     col[c].s = __shfl_sync(LTR_FULL_MASK, col[c].s, src);
                     if (FACT) col[c].v = __shfl_sync(LTR_FULL_MASK, col[c].v, src);
-                    col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
+                    if (TRACK || !lambda_gain_scheme<SCHEME>()) col[c].y = __shfl_sync(LTR_FULL_MASK, col[c].y, src);
                     col[c].g = __shfl_sync(LTR_FULL_MASK, col[c].g, src);
                     col[c].d = __shfl_sync(LTR_FULL_MASK, col[c].d, src);
                     g_c[c] = __shfl_sync(LTR_FULL_MASK, g_c[c], src);
@@ -355,6 +379,31 @@ __device__ __forceinline__ void lambda_sym_slate4(const float* K, const float* V
         }
     }
     __syncthreads();
+}
+
+// The tracking tiles as a function of their own where the kernel also holds the untracked ones (the gain schemes): inlined next
+// to them they cost the common path its register allocation (measured: 50 -> 56 us for the tracked path, 52 for the untracked).
+template <int SCHEME>
+__device__ __noinline__ void lambda_slate_tracked_call(const float* K, const float* V, const float* Y, const float* G, const float* invD,
+                                                       const float* dtab, int lim, int b, float mu, float* gpart, float* acc) {
+    float loss = acc[0], mn = acc[1], mn2 = acc[2];
+    if (lim > 64) lambda_sym_slate4<SCHEME, true>(K, V, Y, G, invD, dtab, lim, b, mu, gpart, loss, mn, mn2);
+    else lambda_sym_slate<SCHEME, 2, true>(K, V, Y, G, invD, dtab, lim, b, mu, gpart, loss, mn, mn2);
+    acc[0] = loss, acc[1] = mn, acc[2] = mn2;
+}
+template <int SCHEME>
+__device__ __forceinline__ void lambda_slate_tracked(const float* K, const float* V, const float* Y, const float* G, const float* invD,
+                                                     const float* dtab, int lim, int b, float mu, float* gpart, float& loss,
+                                                     float& mn, float& mn2) {
+    if (lambda_gain_scheme<SCHEME>()) {
+        float acc[3] = {loss, mn, mn2};
+        lambda_slate_tracked_call<SCHEME>(K, V, Y, G, invD, dtab, lim, b, mu, gpart, acc);
+        loss = acc[0], mn = acc[1], mn2 = acc[2];
+    } else if (lim > 64) {
+        lambda_sym_slate4<SCHEME, true>(K, V, Y, G, invD, dtab, lim, b, mu, gpart, loss, mn, mn2);
+    } else {
+        lambda_sym_slate<SCHEME, 2, true>(K, V, Y, G, invD, dtab, lim, b, mu, gpart, loss, mn, mn2);
+    }
 }
 
 #ifndef LAMBDA_MIN_CTAS
@@ -408,23 +457,25 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         // Whatever the hardware's placement, claim flags keep it exact: an entry is taken once; a CTA whose entry does not
         // exist or is gone steals from the short end.
         if (tid == 0) {
-            int item = -1;
+            int slate = p.B;                                                       // (nothing left: leave)
             if (p.one_wave) {
                 unsigned smid;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 const int s = (int)(smid % (unsigned)p.nsm);
                 const unsigned k = atomicAdd(p.arrive + (s & (LAMBDA_ARRIVE - 1)), 1u);
                 const long long pos = (long long)k * p.nsm + ((k & 1u) ? p.nsm - 1 - s : s);
-                if (pos < p.B && atomicCAS(p.claimed + pos, 0u, 1u) == 0u) item = (int)pos;
-                while (item < 0) {
+                const unsigned mine = pos < p.B ? __ldcg(p.order + pos) : 0u;      // (in flight together with the claim)
+                if (pos < p.B && atomicCAS(p.claimed + pos, 0u, 1u) == 0u) slate = (int)mine;
+                while (slate == p.B) {
                     const unsigned q = atomicAdd(p.cursor, 1u);
                     if (q >= (unsigned)p.B) break;
-                    if (atomicCAS(p.claimed + (p.B - 1 - (int)q), 0u, 1u) == 0u) item = p.B - 1 - (int)q;
+                    const int at = p.B - 1 - (int)q;
+                    if (atomicCAS(p.claimed + at, 0u, 1u) == 0u) slate = (int)__ldcg(p.order + at);
                 }
             } else {
-                item = blockIdx.x;
+                slate = (int)__ldcg(p.order + blockIdx.x);
             }
-            sh_next = (item >= 0 && item < p.B) ? (int)__ldcg(p.order + item) : p.B;
+            sh_next = slate;
         }
         __syncthreads();
         b = sh_next;
@@ -519,8 +570,23 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
             }
             __syncthreads();
             float mn = 0.f, mn2 = 0.f;
-            if (lim > 64) lambda_sym_slate4<SCHEME>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
-            else lambda_sym_slate<SCHEME, 2>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
+            // Can a clamp become active at all?  log2 sig >= -log2(1 + 2^range) > -(range + 1); a pair weight is at most
+            // gmax (mu dtab[1] + 1/D_0 - 1/D_{lim-1}), gmax = the gain of the highest label present (histogram labels only).
+            bool track = true;
+            if (lambda_gain_scheme<SCHEME>() && hist && p.mu >= 0.f && !p.force_track) {
+                const int top = e4 ? 4 : (e3 ? 3 : (e2 ? 2 : (e1 ? 1 : 0)));
+                const float gmax = (float)((1 << top) - 1) / maxdcg;
+                const float dd = invD[0] - invD[lim - 1];
+                const float wmax = gmax * (SCHEME == SCHEME_NDCG2 ? dtab[1] : (SCHEME == SCHEME_LAMBDARANK ? dd : fmaf(p.mu, dtab[1], dd)));
+                const float lmax = fabsf(range) + 1.0f;
+                track = !(lmax < -0.98f * log_eps2 && wmax * lmax < -0.98f * log_eps2);
+            }
+            if (!track) {
+                if (lim > 64) lambda_sym_slate4<SCHEME, false>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
+                else lambda_sym_slate<SCHEME, 2, false>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
+            } else {
+                lambda_slate_tracked<SCHEME>(U, V, Y, G, invD, dtab, lim, b, p.mu, gpart, loss_part, mn, mn2);
+            }
             // (a NaN anywhere -- it cannot come from finite inputs here -- also sends the slate to the exact loop)
             exact = __syncthreads_or(!(mn >= log_eps2) || !(mn2 >= log_eps2) || !(loss_part == loss_part)) != 0;
         }
@@ -631,24 +697,22 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         b = sh_next;
     }
     if (p.finished) {
-        __shared__ double fin[2][LAMBDA_THREADS / 32];
+        // the last CTA to leave adds up the slates' sums (its first warp: the others are gone at once, nobody waits for the counter)
         __syncthreads();
+        if (tid >= 32) return;
+        unsigned last = 0u;
         if (tid == 0) {
             __threadfence();
-            sh_m = (atomicAdd(p.finished, 1u) == gridDim.x - 1) ? 1 : 0;
+            last = (atomicAdd(p.finished, 1u) == gridDim.x - 1) ? 1u : 0u;
         }
-        __syncthreads();
-        if (!sh_m) return;
+        last = __shfl_sync(LTR_FULL_MASK, last, 0);
+        if (!last) return;
         __threadfence();
         double ts = 0.0, tc = 0.0;
-        for (int i = tid; i < p.B; i += LAMBDA_THREADS) ts += (double)__ldcg(p.slate_sum + i), tc += (double)__ldcg(p.slate_cnt + i);
+        for (int i = tid; i < p.B; i += 32) ts += (double)__ldcg(p.slate_sum + i), tc += (double)__ldcg(p.slate_cnt + i);
         ts = warp_sum(ts);
         tc = warp_sum(tc);
-        if ((tid & 31) == 0) fin[0][tid >> 5] = ts, fin[1][tid >> 5] = tc;
-        __syncthreads();
         if (tid == 0) {
-            ts = tc = 0.0;
-            for (int w = 0; w < LAMBDA_THREADS / 32; ++w) ts += fin[0][w], tc += fin[1][w];
             p.loss[0] = p.mean ? (float)(-ts / tc) : (float)(-ts);
             if (p.count_out) p.count_out[0] = (float)tc;
             *p.finished = 0u;
@@ -791,8 +855,10 @@ LTR_API int ltr_lambda_fwdbwd(const float* y_pred, const float* y_true, int B, i
     p.eps = eps; p.pad = pad_value; p.sigma = sigma; p.mu = mu; p.natural_log = natural_log;
     p.slate_sum = slate_sum; p.slate_cnt = slate_count; p.grad = grad;
     p.next = workspace ? ws_counter(workspace, LTR_WS_LAMBDA_COUNTER) : nullptr;
-    p.finished = workspace ? ws_counter(workspace, LTR_WS_LAMBDA_FINISHED) : nullptr;
+    p.finished = (workspace && B <= 8192) ? ws_counter(workspace, LTR_WS_LAMBDA_FINISHED) : nullptr;   // (larger batches: lambda_finish_kernel)
     p.loss = loss; p.count_out = pair_count; p.mean = reduction_mean;
+    static const bool force_track = getenv("LTR_LAMBDA_TRACK") != nullptr;
+    p.force_track = force_track ? 1 : 0;
     const size_t smem = ((size_t)p.len * 6 + 10 * 256) * sizeof(float);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nsm = device_sm_count();

@@ -153,6 +153,8 @@ def test_lambda_dynamic_slate_handout(B, scheme):
     (1300, 160, "ndcgLoss2PP_scheme", {}),                        # two waves: longest first through the counter
     (700, 192, "lamdbaRank_scheme", {"reduction": "mean"}),       # the mean's second launch behind the in-kernel reduction
     (500, 300, "ndcgLoss2PP_scheme", {"k": 40}),                  # long rows, short top-k blocks (work classes by k)
+    (300, 256, "ndcgLoss2PP_scheme", {"mu": 400.0}),              # weight bound too large for the untracked tiles, no clamp active: the tracking tiles' result stands
+    (9000, 40, "ndcgLoss2_scheme", {}),                           # more than 8192 slates: sums reduced by the second launch
 ])
 def test_lambda_longest_first_schedule(B, n, scheme, kw):
     """Batches of 296..4096 slates of more than 128 docs run in the order lambda_order_kernel builds (longest top-k block
