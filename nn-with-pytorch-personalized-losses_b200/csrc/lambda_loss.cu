@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel
         }
         __syncthreads();
         const int m = sh_m;
-        block_sort_desc(K, I, Y, n, len, TIES_STDSORT, m);
+        block_sort_desc<false, LAMBDA_THREADS>(K, I, Y, n, len, TIES_STDSORT, m);
         const int kk = (p.k >= 0 && p.k < n) ? p.k : n;
         const bool hist = !sh_lvl[0];
         // labels 0..4: level L fills the ideal ranks [e_{L+1}, e_L), e_L = #docs with label >= L, so the label at ideal

@@ -85,7 +85,7 @@ __device__ __forceinline__ void lr_softmax(const float* src, int stride, int n, 
 // On exit K = scores in rank order, I = permutation, Y = labels in rank order, G = gains in rank order.
 __device__ __forceinline__ void lr_rank_system(LrSmem& sm, int n, int len, float eps, float* red) {
     const float ninf = __int_as_float(0xff800000);
-    block_sort_desc(sm.K, sm.I, sm.K0, n, len, TIES_STDSORT);
+    block_sort_desc<false, LR_THREADS>(sm.K, sm.I, sm.K0, n, len, TIES_STDSORT);
     for (int i = threadIdx.x; i < len; i += LR_THREADS) sm.G[i] = (i < n) ? sm.pt[i] : ninf;
     block_bitonic_desc(sm.G, len);                                   // ideal label order (values only)
     float part = 0.f;
@@ -261,7 +261,7 @@ __device__ __forceinline__ float pm_rank_prologue(LrSmem& sm, const PairMatrixPa
         sm.pt[i] = pad ? ninf : yp[i];
     }
     __syncthreads();
-    block_sort_desc(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
+    block_sort_desc<false, LR_THREADS>(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
     for (int i = threadIdx.x; i < p.len; i += LR_THREADS) sm.G[i] = (i < n) ? sm.pt[i] : ninf;
     block_bitonic_desc(sm.G, p.len);
     const int kk = (p.k >= 0 && p.k < n) ? p.k : n;

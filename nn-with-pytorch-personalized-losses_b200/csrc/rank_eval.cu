@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(RANK_THREADS) sort_desc_kernel(const float* ke
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) sm.K[i] = keys[(size_t)b * n + i];
         __syncthreads();
-        block_sort_desc(sm.K, sm.I, sm.K0, n, len, tie_rule);
+        block_sort_desc<false, RANK_THREADS>(sm.K, sm.I, sm.K0, n, len, tie_rule);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             if (perm) perm[(size_t)b * n + i] = sm.I[i];
             if (sorted) sorted[(size_t)b * n + i] = sm.K[i];
@@ -96,7 +96,7 @@ __device__ __forceinline__ void ndcg_sorted_query(const NdcgParams& p, RankSmem&
     const float* yt = p.y_true + (size_t)b * p.n;
     for (int i = grp_tid<WARP>(); i < p.n; i += grp_size<WARP>()) sm.K[i] = p.y_pred[(size_t)b * p.n + i];
     grp_sync<WARP>();
-    block_sort_desc<WARP>(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1,
+    block_sort_desc<WARP, WARP ? 0 : RANK_THREADS>(sm.K, sm.I, sm.K0, p.n, p.len, p.tie_rule, p.kmax + 1,
                           WARP ? reinterpret_cast<int*>(sm.L + p.len) : nullptr, known_tie);   // ranks >= kmax are never read
     // labels in predicted order (K0) and in ideal order (L; values only, so ties are immaterial)
     if (count_hist) {
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(RANK_THREADS) rank_loss_kernel(const RankLossP
             // order by softmax(y_pred) (exactNDCG.py:12), gains softmax(y_true), discount ln(r) + 1 (:17)
             for (int i = threadIdx.x; i < n; i += blockDim.x) sm.K[i] = expf(yp[i] - mp) / sp;
             __syncthreads();
-            block_sort_desc(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
+            block_sort_desc<false, RANK_THREADS>(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
             for (int i = threadIdx.x; i < p.len; i += blockDim.x) sm.L[i] = (i < n) ? expf(yt[i] - mt) / st : ninf;
             __syncthreads();
             float dcg = 0.f;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(RANK_THREADS) rank_loss_kernel(const RankLossP
             // order by softmax(y_true) (orderScore.py:14), value sum_r (-n + 2r) log softmax(y_pred)[order_r]
             for (int i = threadIdx.x; i < n; i += blockDim.x) sm.K[i] = expf(yt[i] - mt) / st;
             __syncthreads();
-            block_sort_desc(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
+            block_sort_desc<false, RANK_THREADS>(sm.K, sm.I, sm.K0, n, p.len, TIES_STDSORT);
             const float lse = mp + logf(sp);
             const float invB = 1.0f / (float)p.B;
             float acc = 0.f;

@@ -90,6 +90,90 @@ __device__ __forceinline__ void block_bitonic_packed(unsigned long long* P, int 
     grp_sync<WARP>();
 }
 
+// The same network with the entries in REGISTERS: thread t of a CTA of THREADS threads holds the E consecutive entries
+// t E .. t E + E - 1 (len = THREADS * E).  A compare-exchange at distance j is local for j < E, a warp shuffle for
+// j < 32 E, and goes through the shared scratch P (len words) only for the few stages that cross warps (3 of the 36 stages of
+// 256 entries on 128 threads) -- no barrier, no shared-memory round trip and no index arithmetic on the others: ~19 instead of
+// ~42 instructions per thread and stage.  The packed words are distinct (index bits), so every correct network gives the same
+// result as block_bitonic_packed.
+__device__ __forceinline__ unsigned long long bitonic_pick(unsigned long long a, unsigned long long o, bool take_max) {
+    return ((o > a) == take_max) ? o : a;
+}
+// compare-exchanges at distance J inside a thread's E entries; the run's direction may differ per entry (k < E)
+template <int J, int E>
+__device__ __forceinline__ void bitonic_local(unsigned long long (&v)[E], int i0, int k) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if ((e & J) == 0 && (e | J) < E) {
+            const bool up = ((i0 + e) & k) == 0;
+            const unsigned long long a = v[e], c = v[e | J];
+            const bool sw = up ? (c > a) : (c < a);
+            v[e] = sw ? c : a;
+            v[e | J] = sw ? a : c;
+        }
+    }
+}
+template <int THREADS, int E>
+__device__ __forceinline__ void block_bitonic_packed_regs(unsigned long long* P, unsigned long long (&v)[E]) {
+    static_assert(E == 1 || E == 2 || E == 4 || E == 8, "entries per thread");
+    constexpr int LEN = THREADS * E;
+    const int t = threadIdx.x, lane = t & 31, i0 = t * E;
+#pragma unroll 1
+    for (int k = 2; k <= LEN; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+                if (j == 1) bitonic_local<1, E>(v, i0, k);
+                else if (j == 2) bitonic_local<2, E>(v, i0, k);
+                else bitonic_local<4, E>(v, i0, k);
+            } else if (j < 32 * E) {
+                const int m = j / E;                          // partner lane = lane ^ m
+                const bool take_max = (((lane & m) == 0) == ((i0 & k) == 0));     // lower entry of a descending run keeps the larger
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = bitonic_pick(v[e], __shfl_xor_sync(LTR_FULL_MASK, v[e], m), take_max);
+            } else {
+                const bool take_max = (((i0 & j) == 0) == ((i0 & k) == 0));
+#pragma unroll
+                for (int e = 0; e < E; ++e) P[i0 + e] = v[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = bitonic_pick(v[e], P[(i0 + e) ^ j], take_max);
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// block_sort_desc's packed path on block_bitonic_packed_regs (K and I adjacent, len = THREADS * E)
+template <int THREADS, int E>
+__device__ __forceinline__ void block_sort_packed_regs(float* K, int* I, float* K0, int n, bool rev) {
+    const float ninf = __int_as_float(0xff800000);
+    unsigned long long* P = reinterpret_cast<unsigned long long*>(K);
+    const int i0 = threadIdx.x * E;
+    unsigned long long v[E];
+    float mine[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) mine[e] = (i0 + e < n) ? K[i0 + e] : 0.f;
+    __syncthreads();                                           // (K is about to become the network's scratch)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = i0 + e;
+        if (i < n) K0[i] = mine[e];
+        const unsigned kb = (i < n) ? sort_key_bits(mine[e]) : 0u;
+        v[e] = ((unsigned long long)kb << 32) | (unsigned)(rev ? i : ~i);
+    }
+    block_bitonic_packed_regs<THREADS, E>(P, v);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const unsigned low = (unsigned)v[e];
+        const int idx = (int)(rev ? low : ~low);
+        K[i0 + e] = (idx < n) ? K0[idx] : ninf;               // sentinels: -inf, index >= n, i.e. last
+        I[i0 + e] = idx;
+    }
+    __syncthreads();
+}
+
 // ---- libstdc++ std::sort, replayed by ONE thread on (K, I) in their original order ---------------------
 struct StdSortEmu {
     float* K;
@@ -335,7 +419,7 @@ struct StdSortEmu {
 // `tie_limit`: the caller only reads the first tie_limit entries of the result (callers whose trailing entries
 // are -inf padding that no output depends on pass the number of real docs; NDCG@k passes kmax + 1).  Only ties
 // among those entries trigger the replay, and after a replay entries at and beyond tie_limit may be in any order.
-template <bool WARP = false>
+template <bool WARP = false, int FAST_THREADS = 0>
 __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int n, int len, int tie_rule,
                                                 int tie_limit = 1 << 30, int* warp_stack = nullptr, bool known_tie = false) {
     const float ninf = __int_as_float(0xff800000);
@@ -356,7 +440,21 @@ __device__ __forceinline__ void block_sort_desc(float* K, int* I, float* K0, int
         grp_sync<WARP>();
         return;
     }
-    if (reinterpret_cast<void*>(I) == reinterpret_cast<void*>(K + len) && (reinterpret_cast<uintptr_t>(K) & 7) == 0 &&
+    // FAST_THREADS = the CTA's thread count (compile time): slates of 1, 2, 4 or 8 entries per thread are sorted in registers
+    bool fast = false;
+    if constexpr (!WARP && FAST_THREADS > 0) {
+        fast = reinterpret_cast<void*>(I) == reinterpret_cast<void*>(K + len) && (reinterpret_cast<uintptr_t>(K) & 7) == 0 &&
+               (len == FAST_THREADS || len == 2 * FAST_THREADS || len == 4 * FAST_THREADS || len == 8 * FAST_THREADS);
+    }
+    if (fast) {
+        if constexpr (!WARP && FAST_THREADS > 0) {
+            const bool rev = tie_rule == TIES_REVERSED;
+            if (len == FAST_THREADS) block_sort_packed_regs<FAST_THREADS, 1>(K, I, K0, n, rev);
+            else if (len == 2 * FAST_THREADS) block_sort_packed_regs<FAST_THREADS, 2>(K, I, K0, n, rev);
+            else if (len == 4 * FAST_THREADS) block_sort_packed_regs<FAST_THREADS, 4>(K, I, K0, n, rev);
+            else block_sort_packed_regs<FAST_THREADS, 8>(K, I, K0, n, rev);
+        }
+    } else if (reinterpret_cast<void*>(I) == reinterpret_cast<void*>(K + len) && (reinterpret_cast<uintptr_t>(K) & 7) == 0 &&
         len <= 8 * grp_size<WARP>()) {
         // K and I are adjacent: sort ONE packed 64-bit word per entry, in place over both arrays.  Every thread first
         // holds its (at most 8) entries in registers, so the in-place repacking cannot overwrite an unread entry.
