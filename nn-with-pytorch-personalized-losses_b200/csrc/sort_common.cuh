@@ -114,32 +114,43 @@ __device__ __forceinline__ void bitonic_local(unsigned long long (&v)[E], int i0
     }
 }
 template <int THREADS, int E>
+__device__ __forceinline__ void bitonic_stage_regs(unsigned long long* P, unsigned long long (&v)[E], int k, int j, int lane, int i0) {
+    if (j < E) {
+        if (j == 1) bitonic_local<1, E>(v, i0, k);
+        else if (j == 2) bitonic_local<2, E>(v, i0, k);
+        else bitonic_local<4, E>(v, i0, k);
+    } else if (j < 32 * E) {
+        const int m = j / E;                          // partner lane = lane ^ m
+        const bool take_max = (((lane & m) == 0) == ((i0 & k) == 0));     // lower entry of a descending run keeps the larger
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = bitonic_pick(v[e], __shfl_xor_sync(LTR_FULL_MASK, v[e], m), take_max);
+    } else {
+        const bool take_max = (((i0 & j) == 0) == ((i0 & k) == 0));
+#pragma unroll
+        for (int e = 0; e < E; ++e) P[i0 + e] = v[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = bitonic_pick(v[e], P[(i0 + e) ^ j], take_max);
+        __syncthreads();
+    }
+}
+template <int THREADS, int E>
 __device__ __forceinline__ void block_bitonic_packed_regs(unsigned long long* P, unsigned long long (&v)[E]) {
     static_assert(E == 1 || E == 2 || E == 4 || E == 8, "entries per thread");
     constexpr int LEN = THREADS * E;
     const int t = threadIdx.x, lane = t & 31, i0 = t * E;
+    if constexpr (E <= 2) {
+        // straight-line code (28 / 36 stages): no loop counters, no stage-kind branches, shuffle masks as immediates
+#pragma unroll
+        for (int k = 2; k <= LEN; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) bitonic_stage_regs<THREADS, E>(P, v, k, j, lane, i0);
+        }
+    } else {
 #pragma unroll 1
-    for (int k = 2; k <= LEN; k <<= 1) {
+        for (int k = 2; k <= LEN; k <<= 1) {
 #pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j < E) {
-                if (j == 1) bitonic_local<1, E>(v, i0, k);
-                else if (j == 2) bitonic_local<2, E>(v, i0, k);
-                else bitonic_local<4, E>(v, i0, k);
-            } else if (j < 32 * E) {
-                const int m = j / E;                          // partner lane = lane ^ m
-                const bool take_max = (((lane & m) == 0) == ((i0 & k) == 0));     // lower entry of a descending run keeps the larger
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = bitonic_pick(v[e], __shfl_xor_sync(LTR_FULL_MASK, v[e], m), take_max);
-            } else {
-                const bool take_max = (((i0 & j) == 0) == ((i0 & k) == 0));
-#pragma unroll
-                for (int e = 0; e < E; ++e) P[i0 + e] = v[e];
-                __syncthreads();
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = bitonic_pick(v[e], P[(i0 + e) ^ j], take_max);
-                __syncthreads();
-            }
+            for (int j = k >> 1; j > 0; j >>= 1) bitonic_stage_regs<THREADS, E>(P, v, k, j, lane, i0);
         }
     }
 }
