@@ -27,6 +27,8 @@ N(0,1), alpha = 10), per GPU.  Slates are independent, so N GPUs each take their
                CPU port of torchNdcg on all host cores.  The driver's parser keeps `config`, `roofline`, `e2e` and
                `cpu_baseline`: the block is `config.ndcg_eval`, with its roofline / e2e / cpu numbers repeated as
                `roofline.ndcg_eval`, `e2e.ndcg_eval`, `cpu_baseline.ndcg_eval`.
+  ranker_ddp_step (N > 1) `config.ranker_ddp_step`: the fused ranker training step with its gradients averaged over the ranks
+                  through NVLink peer memory (ltr_peer_allreduce_avg) and through NCCL, us per step and whole-job slates/s.
   georisk_sharded (N > 1) `config.georisk_sharded`: BASELINE configs[3], 8192 queries over the N ranks, S in {2, 4}:
                us per fwd+bwd step with the in-kernel NVLink exchange and with one all-gather per round, the latency
                of one such all-gather, and a parity flag against the unsharded call on rank 0.
@@ -413,6 +415,9 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---- GeoRisk, query-sharded (BASELINE configs[3]) -----------------------------------------------------------------
     georisk = bench_georisk_sharded(dev, rank, world, barrier, max_over_ranks) if world > 1 else None
 
+    # ---- the fused ranker step under data parallelism: gradients averaged over the ranks (peer memory / NCCL) ----------
+    ddp_step = bench_ranker_ddp_step(dev, rank, world, barrier, max_over_ranks) if world > 1 else None
+
     if rank != 0:
         return
 
@@ -461,6 +466,8 @@ def run_b200_arm(args, rank, local_rank, world):
     }
     if georisk is not None:
         config["georisk_sharded"] = georisk
+    if ddp_step is not None:
+        config["ranker_ddp_step"] = ddp_step
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -590,6 +597,79 @@ def bench_ndcg_eval(lib, rt, dev, rank, world, barrier, max_over_ranks, NdcgEval
                 "path": "ltr_ndcg_at_k_host: pinned host labels/scores -> cudaMemcpyAsync -> sweep kernel -> cudaMemcpyAsync "
                         "-> pinned [Q, 3] NDCG, 3 streams in flight"},
     }
+
+
+def bench_ranker_ddp_step(dev, rank, world, barrier, max_over_ranks, B=B_PER_GPU, n=N_DOCS, F=136, iters=30):
+    """BASELINE configs[1] as a data-parallel TRAINING step (the reference's DDP loop, main_batch_execution.py:120-171): every
+    rank runs the fused TripleLayerNet + approxNDCG step on its own `B` slates, then the 13,441 gradient floats are averaged over
+    the ranks -- through NVLink peer memory (`ltr_peer_allreduce_avg`, one launch) or by one NCCL all-reduce.  us per step
+    (CUDA events, max over ranks), whole-job slates/s, and the check that both averages agree."""
+    import torch.distributed as dist
+    from ltr_b200 import _lib, _runtime as rt, sharding
+    from ltr_b200.architeture.tripleLayer import TripleLayerNet
+    lib = _lib.load()
+    torch.manual_seed(SEED)                                               # the same weights on every rank
+    net = TripleLayerNet(F).to(dev)
+    ring = 3
+    data = []
+    for i in range(ring):
+        g = torch.Generator().manual_seed(SEED + 1000 * rank + i)
+        _, y, _ = make_batch(SEED + 7 * rank + i, B, n)
+        data.append((torch.rand(B, n, F, generator=g).to(dev), y.to(dev)))
+    prm = [t.detach() for t in (net.l1.weight, net.l1.bias, net.l2.weight, net.l2.bias, net.l3.weight, net.l3.bias)]
+    sizes = [t.numel() for t in prm]
+    flat = torch.zeros(sum(sizes), device=dev)
+    offs = [sum(sizes[:i]) for i in range(len(sizes))]
+    scores, slate, loss = torch.empty(B, n, device=dev), torch.empty(B, device=dev), torch.empty(1, device=dev)
+    nscr = lib.ltr_triple_step_scratch_bytes(B, n, F)
+    scr = torch.empty(nscr, dtype=torch.uint8, device=dev)
+    tab, ws = rt.disc_prefix(dev), rt.workspace(dev)
+    base = flat.data_ptr()
+    ex = sharding.grad_peer_exchange(dist.group.WORLD, dev)
+
+    def step(i, how):
+        X, y = data[i % ring]
+        rc = lib.ltr_triple_approx_ndcg_step(X.data_ptr(), y.data_ptr(), *[t.data_ptr() for t in prm], B, n, F, 10.0, 1e-10, -1.0,
+                                             tab.data_ptr(), tab.numel(), scores.data_ptr(), slate.data_ptr(), loss.data_ptr(),
+                                             *[base + 4 * o for o in offs], scr.data_ptr(), nscr, ws.data_ptr(), rt.stream_ptr())
+        if rc != 0:
+            raise RuntimeError("ltr_triple_approx_ndcg_step failed: " + lib.ltr_last_error().decode())
+        if how == "p2p":
+            ex.average([flat])
+        elif how == "nccl":
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
+
+    def timed(how):
+        for i in range(5):
+            step(i, how)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            step(5 + i, how)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / iters * 1e3            # us
+
+    out = {"workload": f"TripleLayerNet({F}) + approxNDCG alpha=10 fused training step, {B} slates x {n} docs x {F} features per rank, "
+                       f"gradients (13,441 floats) averaged over {world} ranks", "iters": iters,
+           "peer_memory_available": ex is not None}
+    out["step_only_us"] = timed("none")
+    out["nccl_allreduce_us_per_step"] = timed("nccl")
+    out["nccl_slates_per_s"] = world * B / (out["nccl_allreduce_us_per_step"] * 1e-6)
+    if ex is not None:
+        out["peer_memory_us_per_step"] = timed("p2p")
+        out["peer_memory_slates_per_s"] = world * B / (out["peer_memory_us_per_step"] * 1e-6)
+        step(0, "nccl")
+        ref = flat.clone()
+        step(0, "p2p")
+        out["peer_vs_nccl_max_rel_diff"] = float((flat - ref).abs().max() / ref.abs().max())
+        out["peer_status"] = ex.status()
+        flag = torch.tensor([1 if (out["peer_vs_nccl_max_rel_diff"] < 1e-6 and out["peer_status"] == 0) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["peer_parity_ok"] = bool(int(flag))
+    return out
 
 
 def bench_georisk_sharded(dev, rank, world, barrier, max_over_ranks, Q_total=8192, n=N_DOCS, iters=200):
