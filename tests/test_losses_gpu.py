@@ -506,6 +506,43 @@ def test_ndcg_sweep_near_ties_and_crowded_quads():
         np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12, err_msg=gains)
 
 
+@pytest.mark.parametrize("n", [512, 640, 1024])
+def test_ndcg_sweep_long_rows_special_cases(n):
+    """Long rows (four warps per tile of 32 queries, chunks of 128 docs): non-finite scores, odd labels and ties inside the
+    first 11 ranks are marked for the full sort, ties at ranks 10 / 11 and beyond are not and must not matter; sorted and
+    reverse-sorted rows (every doc / no doc enters the top list); fp64 arithmetic of mNdcg on the same rows."""
+    from ltr_b200.utils.metrics import mNdcg, ndcg_sweep
+    from oracle import ltr_oracle as O
+    Q = 300
+    s, y = make_slates(Q, n, seed=5000 + n)
+    s[1, 5] = float("inf")
+    s[2, n - 3] = float("-inf")
+    s[3, 17] = float("nan")
+    top = s.topk(13, dim=1)
+    s[4, top.indices[4, 1]] = top.values[4, 0]          # tie at ranks 0 / 1
+    s[5, top.indices[5, 10]] = top.values[5, 9]         # tie at ranks 9 / 10: decides the top 10
+    s[6, top.indices[6, 11]] = top.values[6, 10]        # tie at ranks 10 / 11: immaterial
+    s[7, top.indices[7, 12]] = top.values[7, 11]        # tie at ranks 11 / 12
+    y[8, 3] = 2.5
+    y[9, n - 1] = 7.0
+    y[10] = 0.0
+    y[11, 0] = -1.0                                     # a padded doc
+    s[12, :] = 0.25                                     # all scores equal
+    s[13] = torch.arange(n, 0, -1).float()              # already sorted: every doc of the first step enters, then none
+    s[14] = torch.arange(n).float()                     # ascending: every doc enters the list
+    s[15, : n // 2] = -0.0
+    s[15, n // 2:] = 0.0                                # -0 == +0: one big tie
+    got = ndcg_sweep(y.cuda(), s.cuda(), ks=(1, 5, 10)).cpu().numpy()
+    for j, k in enumerate((1, 5, 10)):
+        ref = O.torch_ndcg(y, s, k=k, return_type="tensor").numpy()
+        np.testing.assert_allclose(np.nan_to_num(got[:, j]), np.nan_to_num(ref), rtol=2e-6, atol=1e-7, err_msg=f"k={k}")
+    keep = [i for i in range(Q) if i not in (1, 2, 3)]                      # (finite scores for the fp64 oracle loop)
+    for gains in ("linear", "exponential"):
+        ref = np.asarray(O.m_ndcg(y[keep].numpy(), s[keep].numpy(), k=10, gains=gains))
+        out = np.asarray(mNdcg(y[keep].numpy(), s[keep].numpy(), k=10, gains=gains))
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12, err_msg=gains)
+
+
 def test_ndcg_sweep_large_eval_set_matches_small_batches():
     """More tiles than the label-in-key kernel's resident grid (148 x 4 CTAs x 4 warps): tiles wrap around the grid
     (tile t -> CTA t % grid); the result must equal, bit for bit, the same queries evaluated in slices, and an oracle
