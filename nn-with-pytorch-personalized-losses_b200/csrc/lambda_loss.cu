@@ -412,6 +412,7 @@ __device__ __forceinline__ void lambda_slate_tracked(const float* K, const float
                                 //   1024 x 256: 58.0 / 58.9 / 53.0 / 56.1 (7 x 148 = 1036 slots: the batch is ONE wave)
                                 //   4096 x 256: 225 / 170 / 180 / 188;   2048 x 128: 52.0 / 46.5 / 43.4 / 43.8;   1024 x 100: 28.8 / 28.3 / 24.5 / 24.3
                                 // (4 was best for the round-1 code, whose tiles needed 128 registers)
+                                // End of round 2 (untracked tiles, register sort, longest-first schedule), 1024 x 256: 44.6 / 46.5 / 44.1 / 46.5 at 5 / 6 / 7 / 8
 #endif
 template <int SCHEME>
 __global__ void __launch_bounds__(LAMBDA_THREADS, LAMBDA_MIN_CTAS) lambda_kernel(const LambdaParams p) {
