@@ -339,7 +339,7 @@ int ltr_triple_listnet_step(const float* X, const float* y_true, const float* W1
  *   ptrs / counts : nseg <= 8 device segments, at most ltr_peer_xchg_max_floats() floats in total; averaged IN PLACE,
  *                   every rank gets the same bits.   xchg : this rank's block (ltr_peer_xchg_alloc: ltr_peer_xchg_bytes()
  *   of cudaMalloc'd, zero-filled memory); peer_xchg[world] : every rank's block as mapped into this process (ltr_ipc_export /
- *   ltr_ipc_open; peer_xchg[rank] == xchg).  Two launches (push, gather) on `stream`, capturable in a CUDA graph; every rank
+ *   ltr_ipc_open; peer_xchg[rank] == xchg).  ONE launch on `stream` (CTA b pushes values [1024 b, 1024 b + 1024) to every peer, then gathers them), capturable in a CUDA graph; every rank
  *   must make the same sequence of calls.  ltr_peer_xchg_status: 1 after a peer failed to arrive within 4 s (results NaN).
  */
 size_t ltr_peer_xchg_bytes(void);
