@@ -272,6 +272,17 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
                 if (kd > L) key_insert<TPQ_K>(top, kd);
             }
         }
+        if (p.partial) {
+            // a chunk of a long row: its 11 largest keys, label histogram and flag go to the merge (ndcg_chunk_merge_kernel)
+            if (q < p.B) {
+#pragma unroll
+                for (int j = 0; j < TPQ_K; ++j) p.partial[(size_t)j * p.B + q] = top[j];
+                p.partial[(size_t)TPQ_K * p.B + q] = __uint_as_float(myhist);
+                p.partial[(size_t)(TPQ_K + 1) * p.B + q] = __uint_as_float((unsigned)mybad);
+            }
+            __syncwarp();                                        // the tile is free for the next phase 1
+            continue;
+        }
         // keys that agree in their upper 29 bits among the ranks the sweep reads: exact compares on the row itself
         int bad = mybad;
         int tied = 0;                                    // an exact tie seen by the exact path below
@@ -375,6 +386,88 @@ __global__ void __launch_bounds__(TPQ_THREADS, KEY_CTAS) ndcg_key_kernel(const _
             }
         }
         __syncwarp();                                            // the tile is free for the next phase 1
+    }
+}
+
+// Rows of several whole chunks: ndcg_key_kernel has left, per chunk, the 11 largest keys (label in the low 3 bits), the label
+// histogram and the flag in p.partial ([13][B * chunks], chunk c of query q at column q * chunks + c).  A group of G = 2..32 lanes
+// (the chunk count rounded up to a power of two) owns a query: lane c loads chunk c's list (coalesced: neighbouring lanes read
+// neighbouring columns), then log2 G butterfly rounds merge the lists -- a lane inserts its partner's 11 keys, 2 FMNMX per slot and
+// key, so every lane of the group ends with the query's 11 largest keys -- and add the histograms.  The group's first lane
+// finishes like the key kernel; keys that agree in their upper 29 bits among the ranks the sweep reads (an exact tie, or scores
+// 1e-7 apart) are left to ndcg_kernel, which replays the reference's sort on the row (flag 2), as are rows with odd labels or
+// non-finite scores (flag 1).
+__global__ void __launch_bounds__(128) ndcg_chunk_merge_kernel(const NdcgParams p) {
+    __shared__ float term32[(TPQ_K - 1) * 8];
+    const int chunks = p.n / TPQ_N;
+    const size_t rows = (size_t)p.B * chunks;
+    int G = 2;
+    while (G < chunks && G < 32) G <<= 1;
+    unsigned kends = 0;                                    // bit r: some k of the sweep equals r + 1
+    for (int j = 0; j < p.nk; ++j) kends |= 1u << (p.ks[j] - 1);
+    pdl_prologue();
+    if ((int)threadIdx.x < (TPQ_K - 1) * 8) {
+        const int r = (int)threadIdx.x >> 3, l = (int)threadIdx.x & 7;
+        if (r < p.kmax && l <= 4) term32[threadIdx.x] = (float)((1 << l) - 1) / p.disc32[r];
+    }
+    __syncthreads();
+    const int per_cta = 128 / G;                           // queries per CTA
+    const int sub = (int)threadIdx.x % G;                  // lane of the group (groups do not straddle warps: G <= 32)
+    const int q = (int)blockIdx.x * per_cta + (int)threadIdx.x / G;
+    const bool live = q < p.B;                             // (whole groups are live or not: the shuffles below stay convergent)
+    float top[TPQ_K];
+#pragma unroll
+    for (int j = 0; j < TPQ_K; ++j) top[j] = __uint_as_float(0xff7ffff8u);      // below every finite score, label 0
+    int c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    unsigned bad = 0;
+    if (live) {
+#pragma unroll 1
+        for (int c = sub; c < chunks; c += G) {            // (more than 32 chunks: a lane folds several)
+            const size_t col = (size_t)q * chunks + c;
+            float mine[TPQ_K];
+#pragma unroll
+            for (int j = 0; j < TPQ_K; ++j) mine[j] = __ldcg(p.partial + (size_t)j * rows + col);
+            const unsigned h = __float_as_uint(__ldcg(p.partial + (size_t)TPQ_K * rows + col));
+            bad |= __float_as_uint(__ldcg(p.partial + (size_t)(TPQ_K + 1) * rows + col));
+#pragma unroll
+            for (int j = 0; j < TPQ_K; ++j) key_insert<TPQ_K>(top, mine[j]);
+            c4 += (int)(h >> 24), c3 += (int)((h >> 16) & 255u), c2 += (int)((h >> 8) & 255u), c1 += (int)(h & 255u);
+        }
+    }
+    for (int o = 1; o < G; o <<= 1) {
+        float theirs[TPQ_K];
+#pragma unroll
+        for (int j = 0; j < TPQ_K; ++j) theirs[j] = __shfl_xor_sync(LTR_FULL_MASK, top[j], o);
+#pragma unroll
+        for (int j = 0; j < TPQ_K; ++j) key_insert<TPQ_K>(top, theirs[j]);
+        c1 += __shfl_xor_sync(LTR_FULL_MASK, c1, o);
+        c2 += __shfl_xor_sync(LTR_FULL_MASK, c2, o);
+        c3 += __shfl_xor_sync(LTR_FULL_MASK, c3, o);
+        c4 += __shfl_xor_sync(LTR_FULL_MASK, c4, o);
+        bad |= __shfl_xor_sync(LTR_FULL_MASK, bad, o);
+    }
+    if (!live || sub != 0) return;
+    bool near = false;
+#pragma unroll
+    for (int j = 0; j + 1 < TPQ_K; ++j) near = near || (j < p.kmax && key_near(top[j], top[j + 1]));
+    p.flags[1 + q] = bad ? 1 : (near ? 2 : 0);
+    if (bad || near) return;
+    c3 += c4, c2 += c3, c1 += c2;                              // #docs with label >= L
+    unsigned pred_lab = 0;                                     // 3 bits per rank
+#pragma unroll
+    for (int r = 0; r < TPQ_K - 1; ++r) pred_lab |= (__float_as_uint(top[r]) & 7u) << (3 * r);
+    float got = 0.f, ideal = 0.f;
+    float* out = p.out32 + (size_t)q * p.nk;
+#pragma unroll 1
+    for (int r = 0; r < p.kmax; ++r) {
+        const int li = (c4 > r) + (c3 > r) + (c2 > r) + (c1 > r);
+        got += term32[8 * r + ((pred_lab >> (3 * r)) & 7u)];
+        ideal += term32[8 * r + li];
+        if ((kends >> r) & 1u) {
+            const float val = got / ideal;
+            for (int j = 0; j < p.nk; ++j)
+                if (p.ks[j] == r + 1) out[j] = val;
+        }
     }
 }
 

@@ -84,6 +84,9 @@ struct NdcgParams {
     int kmax;                // largest k of the sweep (top-k fast path)
     int* flags;              // [1 + B] scratch: flags[1 + q] != 0 marks a query the top-k path left to the full sort
                              // (a tie among its first kmax + 1 ranks, a NaN score, an unusual label)
+    float* partial;          // long rows in 128-doc chunks (ndcg_keys.cuh): [13][rows] words -- a chunk's 11 largest keys, its label
+                             // histogram and its "not on the fast path" flag -- written by ndcg_key_kernel INSTEAD of its outputs
+                             // (the kernel then sees every chunk as a row of 128 docs), read by ndcg_chunk_merge_kernel; else null
 };
 
 // one query: full sort with the caller's tie rule, labels in predicted and in ideal order, all k of the sweep
@@ -568,6 +571,23 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         // The opt-in shared-memory size is a per-device function attribute: set on every call (cheap), never cached
         // in a process-wide flag (a second device in one process would otherwise launch without it).
         // warps per tile of 32 queries: long rows are split chunk-wise over the warps of a CTA
+        // rows of 2..64 whole chunks with scratch from the caller: the label-in-key kernel chunk by chunk, then a merge
+        const bool chunked = p.partial && !f64 && p.n > TPQ_N && p.n % TPQ_N == 0 && p.n <= 64 * TPQ_N &&
+                             (long long)p.B * (p.n / TPQ_N) < (1ll << 30);
+        if (chunked) {
+            NdcgParams pv = p;
+            pv.B = p.B * (p.n / TPQ_N);
+            pv.n = TPQ_N;
+            const int vt = (pv.B + 31) / 32, vcap = device_sm_count() * KEY_CTAS;
+            LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
+            int rc = launch_pdl(ndcg_key_kernel<false>, vt < vcap ? vt : vcap, TPQ_THREADS, KEY_SMEM, st, pv);
+            if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (chunk keys)");
+            int G = 2;                                              // lanes per query in the merge (ndcg_keys.cuh)
+            while (G < p.n / TPQ_N && G < 32) G <<= 1;
+            const int per_cta = 128 / G;
+            rc = launch_pdl(ndcg_chunk_merge_kernel, (p.B + per_cta - 1) / per_cta, 128, 0, st, p);
+            if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (chunk merge)");
+        }
         const int share = p.n <= TPQ_N ? 1 : (p.n <= 2 * TPQ_N ? 2 : 4);
         const int tiles = (p.B + 31) / 32;
         const bool keys = share == 1;          // rows of one chunk: label-in-key kernel (ndcg_keys.cuh), which also sorts
@@ -576,7 +596,7 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         int g = (tiles * share + TPQ_WARPS - 1) / TPQ_WARPS;
         g = g < gcap ? g : gcap;
         if (keys) g = tiles < gcap ? tiles : gcap;     // tile t -> CTA t % g: every SM gets its share of a small batch
-        int rc;
+        int rc = 0;
 #define LTR_TPQ(C)                                                                                                      \
     do {                                                                                                                \
         if (f64) {                                                                                                      \
@@ -589,7 +609,9 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
             rc = launch_pdl(ndcg_tpq_wide_kernel<false, C>, g, TPQ_THREADS, TPQ_SMEM, st, p);                           \
         }                                                                                                               \
     } while (0)
-        if (keys) {
+        if (chunked) {
+            // (launched above)
+        } else if (keys) {
             if (f64) {
                 LTR_CUDA(cudaFuncSetAttribute(ndcg_key_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KEY_SMEM));
                 rc = launch_pdl(ndcg_key_kernel<true>, g, TPQ_THREADS, KEY_SMEM, st, p);
@@ -601,7 +623,7 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
 #undef LTR_TPQ
         if (rc) return set_cuda_error(rc, "ltr_ndcg_at_k (one thread per query)");
         marked_only = true;
-        keys_done = keys;
+        keys_done = keys && !chunked;
     } else if (kmax <= 31 && p.n <= 1024 && p.flags) {
         // top-k fast path (one warp per query), then the full sort for the queries it marked
         int g = (p.B + 7) / 8;
@@ -649,6 +671,25 @@ LTR_API int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n
     p.y_true = y_true; p.y_pred = y_pred; p.B = Q; p.n = n; p.tie_rule = tie_rule; p.disc32 = disc32; p.out32 = out;
     p.flags = flags;
     if (!disc32 || !out) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k: null table / output");
+    return ndcg_common(p, ks, nk, false, stream);
+}
+
+LTR_API size_t ltr_ndcg_at_k_scratch_bytes(int Q, int n) {
+    using namespace ltr;
+    if (Q <= 0 || n <= TPQ_N || n % TPQ_N != 0 || n > 64 * TPQ_N || (long long)Q * (n / TPQ_N) >= (1ll << 30)) return 0;
+    return (size_t)13 * sizeof(float) * (size_t)Q * (size_t)(n / TPQ_N);
+}
+
+LTR_API int ltr_ndcg_at_k_ws(const float* y_true, const float* y_pred, int Q, int n, const int* ks, int nk, int tie_rule,
+                             const float* disc32, float* out, int* flags, void* scratch, size_t scratch_bytes, void* stream) {
+    ltr::NdcgParams p{};
+    p.y_true = y_true; p.y_pred = y_pred; p.B = Q; p.n = n; p.tie_rule = tie_rule; p.disc32 = disc32; p.out32 = out;
+    p.flags = flags;
+    if (!disc32 || !out) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k_ws: null table / output");
+    const size_t need = ltr_ndcg_at_k_scratch_bytes(Q, n);
+    if (scratch && need && scratch_bytes < need) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k_ws: scratch too small");
+    if (scratch && need && (reinterpret_cast<uintptr_t>(scratch) & 15)) return ltr::set_error(LTR_EINVAL, "ltr_ndcg_at_k_ws: scratch not 16-byte aligned");
+    p.partial = (scratch && need) ? static_cast<float*>(scratch) : nullptr;
     return ndcg_common(p, ks, nk, false, stream);
 }
 

@@ -32,6 +32,8 @@ _SIGNATURES = {
     "ltr_ordinal_fwdbwd": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "ltr_sort_desc": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "ltr_ndcg_at_k": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P]),
+    "ltr_ndcg_at_k_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "ltr_ndcg_at_k_ws": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "ltr_ndcg_at_k_host_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ltr_ndcg_at_k_host": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "ltr_ndcg_at_k_f64": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), c_int, c_int, c_int, c_double, _P, _P, _P, _P]),

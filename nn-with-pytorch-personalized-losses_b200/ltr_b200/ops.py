@@ -273,6 +273,13 @@ def ndcg_at_k(y_true, y_pred, ks, tie_rule=TIES_STDSORT):
     d32, _ = _disc_tables(n, y_pred.device)
     out = torch.empty(Q, len(ks), dtype=torch.float32, device=y_pred.device)
     flags = torch.empty(Q + 1, dtype=torch.int32, device=y_pred.device)
+    need = int(lib.ltr_ndcg_at_k_scratch_bytes(Q, n))          # long rows of whole 128-doc chunks: per-chunk top lists
+    if need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=y_pred.device)
+        _lib.check(lib.ltr_ndcg_at_k_ws(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
+                                        d32.data_ptr(), out.data_ptr(), flags.data_ptr(), scratch.data_ptr(), need,
+                                        rt.stream_ptr()), "ltr_ndcg_at_k_ws")
+        return out
     _lib.check(lib.ltr_ndcg_at_k(y_true.data_ptr(), y_pred.data_ptr(), Q, n, _ks_array(ks), len(ks), int(tie_rule),
                                  d32.data_ptr(), out.data_ptr(), flags.data_ptr(), rt.stream_ptr()), "ltr_ndcg_at_k")
     return out

@@ -543,6 +543,45 @@ def test_ndcg_sweep_long_rows_special_cases(n):
         np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12, err_msg=gains)
 
 
+@pytest.mark.parametrize("Q,n", [(3000, 1024), (777, 256), (100, 2048), (64, 1536), (50, 640)])
+def test_ndcg_chunked_long_rows_equal_the_tile_path(Q, n):
+    """`ltr_ndcg_at_k_ws` (label-in-key kernel per 128-doc chunk + merge) against `ltr_ndcg_at_k` (tile kernel) on the same
+    rows: the same sums in the same order, so the same bits; both against an oracle sample; scratch argument checks."""
+    import ctypes
+    from ltr_b200 import _lib, ops, _runtime as rt
+    from oracle import ltr_oracle as O
+    lib = _lib.load()
+    s, y = make_slates(Q, n, seed=7000 + n)
+    # (the key kernel validates labels and scores per tile of 32 chunks: the special rows sit in different tiles)
+    s[0, 5] = float("nan")
+    y[10, 7] = 2.5
+    top = s.topk(3, dim=1)
+    s[20, top.indices[20, 1]] = top.values[20, 0]                 # exact tie at ranks 0 / 1, possibly across chunks
+    s[30, n - 1] = s[30].max() + 1.0                              # the best doc is the last one of the last chunk
+    sd, yd = s.cuda(), y.cuda()
+    ks = (1, 5, 10)
+    karr = (ctypes.c_int * 3)(*ks)
+    d32, _ = ops._disc_tables(n, sd.device)
+    out_a, out_b = torch.zeros(Q, 3, device="cuda"), torch.zeros(Q, 3, device="cuda")
+    fl_a, fl_b = torch.zeros(Q + 1, dtype=torch.int32, device="cuda"), torch.zeros(Q + 1, dtype=torch.int32, device="cuda")
+    need = int(lib.ltr_ndcg_at_k_scratch_bytes(Q, n))
+    assert need == 13 * 4 * Q * (n // 128)
+    _lib.check(lib.ltr_ndcg_at_k(yd.data_ptr(), sd.data_ptr(), Q, n, karr, 3, ops.TIES_STDSORT, d32.data_ptr(), out_a.data_ptr(),
+                                 fl_a.data_ptr(), rt.stream_ptr()), "ltr_ndcg_at_k")
+    scratch = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.ltr_ndcg_at_k_ws(yd.data_ptr(), sd.data_ptr(), Q, n, karr, 3, ops.TIES_STDSORT, d32.data_ptr(), out_b.data_ptr(),
+                                    fl_b.data_ptr(), scratch.data_ptr(), need, rt.stream_ptr()), "ltr_ndcg_at_k_ws")
+    assert torch.equal(torch.nan_to_num(out_a), torch.nan_to_num(out_b))
+    if need:
+        assert int(fl_b[1 + 0]) == 1 and int(fl_b[1 + 10]) == 1 and int(fl_b[1 + 20]) == 2 and int(fl_b[1 + 30]) == 0
+        assert lib.ltr_ndcg_at_k_ws(yd.data_ptr(), sd.data_ptr(), Q, n, karr, 3, ops.TIES_STDSORT, d32.data_ptr(), out_b.data_ptr(),
+                                    fl_b.data_ptr(), scratch.data_ptr(), need - 1, rt.stream_ptr()) != 0      # scratch too small
+    m = min(Q, 64)
+    for j, k in enumerate(ks):
+        ref = O.torch_ndcg(y[:m], s[:m], k=k, return_type="tensor").numpy()
+        np.testing.assert_allclose(np.nan_to_num(out_b[:m, j].cpu().numpy()), np.nan_to_num(ref), rtol=2e-6, atol=1e-7)
+
+
 def test_ndcg_sweep_large_eval_set_matches_small_batches():
     """More tiles than the label-in-key kernel's resident grid (148 x 4 CTAs x 4 warps): tiles wrap around the grid
     (tile t -> CTA t % grid); the result must equal, bit for bit, the same queries evaluated in slices, and an oracle

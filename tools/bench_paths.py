@@ -128,15 +128,23 @@ def bench_ndcg(iters=100, Q=65536, n=128, ks=(1, 5, 10), ring=3):
     marks = [torch.empty(Q + 1, dtype=torch.int32, device=dev) for _ in range(ring)]
     karr = (ctypes.c_int * len(ks))(*ks)
 
+    need = int(lib.ltr_ndcg_at_k_scratch_bytes(Q, n)) if not os.environ.get("LTR_NDCG_NO_CHUNKS") else 0
+    scratch = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+
     def step(i):
         s, y = data[i % ring]
-        _ok(lib.ltr_ndcg_at_k(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(), out.data_ptr(),
-                          marks[i % ring].data_ptr(), rt.stream_ptr()))
+        if need:
+            _ok(lib.ltr_ndcg_at_k_ws(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(), out.data_ptr(),
+                                     marks[i % ring].data_ptr(), scratch.data_ptr(), need, rt.stream_ptr()))
+        else:
+            _ok(lib.ltr_ndcg_at_k(y.data_ptr(), s.data_ptr(), Q, n, karr, len(ks), ops.TIES_STDSORT, d32.data_ptr(), out.data_ptr(),
+                                  marks[i % ring].data_ptr(), rt.stream_ptr()))
 
     sec = _time(step, iters)
     marked = [int((m[1:] != 0).sum()) for m in marks]
     kern = "ndcg_key_kernel<false> (sorts the queries it marks itself)" if n <= 128 and max(ks) <= 10 else \
-        "ndcg_topk_wide_kernel<false> + ndcg_kernel<false> (marked queries only)"
+        ("ndcg_key_kernel<false> per 128-doc chunk + ndcg_chunk_merge_kernel + ndcg_kernel<false> (marked queries only)" if need else
+         "ndcg_tpq_wide_kernel<false, 4> + ndcg_kernel<false> (marked queries only)")
     return {"metric": f"NDCG@{{{','.join(map(str, ks))}}} eval queries/s (n={n})", "value": Q / sec, "unit": "queries/s",
             "us_per_call": sec * 1e6,
             "config": {"workload": f"{Q} queries x {n} docs, k sweep {list(ks)}, torchNdcg arithmetic, ring of {ring} batches",
