@@ -126,7 +126,7 @@ int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n, const 
  * The same call with scratch memory for long rows.   replaces utils/metrics.py:83-104 (torchNdcg) at the evaluation shape of
  * BASELINE configs[4] (8192 queries x 1024 docs)
  *   scratch : ltr_ndcg_at_k_scratch_bytes(Q, n) bytes of 16-byte aligned device memory (0 bytes: rows of at most 128 docs, or
- *   not a multiple of 128 -- the call is then ltr_ndcg_at_k), no initialisation needed, or NULL.  With it, rows of 2..64
+ *   not a multiple of 128 -- the call is then ltr_ndcg_at_k), no initialisation needed, or NULL.  With it, rows of 2..16
  *   whole 128-doc chunks (largest k <= 10, flags given) run the label-in-key kernel chunk by chunk -- every chunk a row of its
  *   own, at that kernel's occupancy -- and one thread per query merges the chunks' top-11 lists; queries with (near-)tied keys
  *   among their first k + 1 ranks, odd labels or non-finite scores are marked in `flags` and sorted in full as before.

@@ -571,8 +571,8 @@ static int ndcg_common(ltr::NdcgParams& p, const int* ks, int nk, bool f64, void
         // The opt-in shared-memory size is a per-device function attribute: set on every call (cheap), never cached
         // in a process-wide flag (a second device in one process would otherwise launch without it).
         // warps per tile of 32 queries: long rows are split chunk-wise over the warps of a CTA
-        // rows of 2..64 whole chunks with scratch from the caller: the label-in-key kernel chunk by chunk, then a merge
-        const bool chunked = p.partial && !f64 && p.n > TPQ_N && p.n % TPQ_N == 0 && p.n <= 64 * TPQ_N &&
+        // rows of 2..16 whole chunks with scratch from the caller: the label-in-key kernel chunk by chunk, then a merge
+        const bool chunked = p.partial && !f64 && p.n > TPQ_N && p.n % TPQ_N == 0 && p.n <= RANK_MAX_N &&
                              (long long)p.B * (p.n / TPQ_N) < (1ll << 30);
         if (chunked) {
             NdcgParams pv = p;
@@ -676,7 +676,7 @@ LTR_API int ltr_ndcg_at_k(const float* y_true, const float* y_pred, int Q, int n
 
 LTR_API size_t ltr_ndcg_at_k_scratch_bytes(int Q, int n) {
     using namespace ltr;
-    if (Q <= 0 || n <= TPQ_N || n % TPQ_N != 0 || n > 64 * TPQ_N || (long long)Q * (n / TPQ_N) >= (1ll << 30)) return 0;
+    if (Q <= 0 || n <= TPQ_N || n % TPQ_N != 0 || n > RANK_MAX_N || (long long)Q * (n / TPQ_N) >= (1ll << 30)) return 0;
     return (size_t)13 * sizeof(float) * (size_t)Q * (size_t)(n / TPQ_N);
 }
 
