@@ -136,8 +136,9 @@ int ltr_ndcg_at_k_ws(const float* y_true, const float* y_pred, int Q, int n, con
                      const float* disc32, float* out, int* flags, void* scratch, size_t scratch_bytes, void* stream);
 
 /*
- * The same sweep from HOST buffers (pinned for asynchrony): H2D of y_true / y_pred, ltr_ndcg_at_k, D2H of out, all
- * queued on `stream`.  d_scratch: ltr_ndcg_at_k_host_scratch_bytes(Q, n, nk) bytes of device memory; disc32 stays a
+ * The same sweep from HOST buffers (pinned for asynchrony): H2D of y_true / y_pred, ltr_ndcg_at_k_ws, D2H of out, all
+ * queued on `stream`.  d_scratch: ltr_ndcg_at_k_host_scratch_bytes(Q, n, nk) bytes of 16-byte aligned device memory (the
+ * device copies, the flags and the per-chunk lists of long rows); disc32 stays a
  * device table.  This is the call a CPU-resident evaluation loop (main.py:145) makes once per epoch.
  */
 size_t ltr_ndcg_at_k_host_scratch_bytes(int Q, int n, int nk);

@@ -709,7 +709,8 @@ LTR_API size_t ltr_ndcg_at_k_host_scratch_bytes(int Q, int n, int nk) {
     if (Q <= 0 || n <= 0 || nk <= 0) return 0;
     const size_t qn = (((size_t)Q * n + 3) & ~(size_t)3);
     const size_t qk = (((size_t)Q * nk + 3) & ~(size_t)3);
-    return (2 * qn + qk + (((size_t)Q + 1 + 3) & ~(size_t)3)) * sizeof(float);
+    // (+ the per-chunk top lists of long rows: ltr_ndcg_at_k_ws)
+    return (2 * qn + qk + (((size_t)Q + 1 + 3) & ~(size_t)3)) * sizeof(float) + ltr_ndcg_at_k_scratch_bytes(Q, n);
 }
 
 LTR_API int ltr_ndcg_at_k_host(const float* h_y_true, const float* h_y_pred, int Q, int n, const int* ks, int nk,
@@ -730,7 +731,10 @@ LTR_API int ltr_ndcg_at_k_host(const float* h_y_true, const float* h_y_pred, int
     const size_t bytes = (size_t)Q * n * sizeof(float);
     LTR_CUDA(cudaMemcpyAsync(d_true, h_y_true, bytes, cudaMemcpyHostToDevice, st));
     LTR_CUDA(cudaMemcpyAsync(d_pred, h_y_pred, bytes, cudaMemcpyHostToDevice, st));
-    if (int rc = ltr_ndcg_at_k(d_true, d_pred, Q, n, ks, nk, tie_rule, disc32, d_out, d_flags, stream)) return rc;
+    void* d_chunks = reinterpret_cast<float*>(d_flags) + (((size_t)Q + 1 + 3) & ~(size_t)3);
+    if (int rc = ltr_ndcg_at_k_ws(d_true, d_pred, Q, n, ks, nk, tie_rule, disc32, d_out, d_flags, d_chunks,
+                                  ltr_ndcg_at_k_scratch_bytes(Q, n), stream))
+        return rc;
     LTR_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)Q * nk * sizeof(float), cudaMemcpyDeviceToHost, st));
     return 0;
 }

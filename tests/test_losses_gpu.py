@@ -582,6 +582,24 @@ def test_ndcg_chunked_long_rows_equal_the_tile_path(Q, n):
         np.testing.assert_allclose(np.nan_to_num(out_b[:m, j].cpu().numpy()), np.nan_to_num(ref), rtol=2e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("Q,n", [(1000, 128), (600, 512), (300, 1000)])
+def test_ndcg_eval_from_host_arrays(Q, n):
+    """`ltr_ndcg_at_k_host` through the NdcgEvalHost plan (main.py:145 keeps validation data on the CPU): pinned labels / scores
+    in, pinned NDCG out, slots reused; equal to the device sweep bit for bit (rows of whole chunks take the chunked path in both)."""
+    from ltr_b200.host import NdcgEvalHost
+    from ltr_b200.utils.metrics import ndcg_sweep
+    plan = NdcgEvalHost(Q, n, ks=(1, 5, 10), depth=2)
+    batches = []
+    for i in range(5):                                            # more submissions than slots
+        s, y = make_slates(Q, n, seed=8000 + 10 * n + i)
+        batches.append((s.pin_memory(), y.pin_memory()))
+    for i, (s, y) in enumerate(batches):
+        slot, out = plan.submit(y, s)
+        plan.wait(slot)
+        want = ndcg_sweep(y.cuda(), s.cuda(), ks=(1, 5, 10)).cpu()
+        assert torch.equal(torch.nan_to_num(out), torch.nan_to_num(want)), i
+
+
 def test_ndcg_sweep_large_eval_set_matches_small_batches():
     """More tiles than the label-in-key kernel's resident grid (148 x 4 CTAs x 4 warps): tiles wrap around the grid
     (tile t -> CTA t % grid); the result must equal, bit for bit, the same queries evaluated in slices, and an oracle
