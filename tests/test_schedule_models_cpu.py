@@ -163,3 +163,89 @@ def test_register_bitonic_network_sorts_descending(threads, E):
         keys = (hi << np.uint64(32)) | lo
         out = _bitonic_regs_model(keys, threads, E)
         assert np.array_equal(out, np.sort(keys)[::-1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# csrc/peer_allreduce.cu: two slot parities are enough
+# ---------------------------------------------------------------------------------------------------------------------
+def _peer_allreduce_model(world, calls, ctas, rng, nbuf=2):
+    """Every (rank, CTA) is a little state machine: PUSH (stores into slot [q & 1][rank] of every peer, one peer per micro-step, in
+    a random order), FLAG (release-stores q into flag [q & 1][rank][cta] of every peer, after all of its pushes), WAIT (until its
+    own flags [q & 1][*][cta] carry q), GATHER (reads the slots, one per micro-step), DONE.  A rank starts call q + 1 only when all
+    of its CTAs are DONE with call q (stream order).  The scheduler picks a random runnable machine each step; a read that sees a
+    value pushed for another call is the bug the two parities must exclude."""
+    slot = [[[[None] * ctas for _ in range(world)] for _ in range(2)] for _ in range(world)]   # [owner][par][from][cta] -> call id
+    par = (lambda q: q & 1) if nbuf == 2 else (lambda q: 0)
+    flag = [[[[0] * ctas for _ in range(world)] for _ in range(2)] for _ in range(world)]
+    call = [1] * world                                                 # the call a rank is executing
+    state = {}                                                         # (rank, cta) -> [phase, todo list]
+
+    def start(r):
+        for b in range(ctas):
+            peers = list(range(world))
+            rng.shuffle(peers)
+            state[(r, b)] = ["push", peers]
+
+    for r in range(world):
+        start(r)
+    finished = 0
+    steps = 0
+    while finished < world:
+        steps += 1
+        assert steps < 10 ** 6, "deadlock"
+        runnable = []
+        for (r, b), (ph, todo) in state.items():
+            q = call[r]
+            if ph == "wait":
+                if all(flag[r][par(q)][s][b] == q for s in range(world)):
+                    runnable.append((r, b))
+            elif ph != "done":
+                runnable.append((r, b))
+        assert runnable, "deadlock"
+        r, b = rng.choice(runnable)
+        ph, todo = state[(r, b)]
+        q = call[r]
+        if ph == "push":
+            peer = todo.pop()
+            slot[peer][par(q)][r][b] = q
+            if not todo:
+                state[(r, b)] = ["flag", list(range(world))]
+        elif ph == "flag":
+            peer = todo.pop()
+            flag[peer][par(q)][r][b] = q
+            if not todo:
+                state[(r, b)] = ["wait", None]
+        elif ph == "wait":
+            state[(r, b)] = ["gather", list(range(world))]
+        elif ph == "gather":
+            s = todo.pop()
+            assert slot[r][par(q)][s][b] == q, (r, b, s, q, slot[r][par(q)][s][b])
+            if not todo:
+                state[(r, b)] = ["done", None]
+                if all(state[(r, c)][0] == "done" for c in range(ctas)):
+                    if call[r] == calls:
+                        finished += 1
+                    else:
+                        call[r] += 1
+                        start(r)
+    return steps
+
+
+@pytest.mark.parametrize("world,ctas", [(2, 1), (2, 3), (3, 2), (8, 2)])
+def test_peer_allreduce_two_parities_never_mix_calls(world, ctas):
+    rng = random.Random(world * 100 + ctas)
+    for trial in range(20):
+        _peer_allreduce_model(world, calls=7, ctas=ctas, rng=rng)
+
+
+def test_peer_allreduce_model_catches_a_single_parity():
+    """The same model with ONE slot per sender fails for some interleaving (a rank pushes call q + 1 over values its peer has not
+    gathered yet) -- the test above is not vacuous."""
+    rng = random.Random(5)
+    caught = 0
+    for trial in range(50):
+        try:
+            _peer_allreduce_model(2, calls=5, ctas=1, rng=rng, nbuf=1)
+        except AssertionError:
+            caught += 1
+    assert caught > 0
