@@ -835,7 +835,8 @@ template <int SCHEME>
 static int launch_lambda(const LambdaParams& p, size_t smem, int grid, cudaStream_t st) {
     if (smem > 48 * 1024)
         LTR_CUDA(cudaFuncSetAttribute(lambda_kernel<SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return launch_pdl(lambda_kernel<SCHEME>, grid, LAMBDA_THREADS, smem, st, p);
+    const int rc = launch_pdl(lambda_kernel<SCHEME>, grid, LAMBDA_THREADS, smem, st, p);
+    return rc ? set_cuda_error(rc, "ltr_lambda_fwdbwd (launch)") : 0;
 }
 
 }  // namespace ltr
