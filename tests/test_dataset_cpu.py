@@ -113,3 +113,30 @@ def test_file_of_whole_pages_and_no_trailing_newline(tmp_path):
     X, y, qids, lens = D.load_slates(path, pin=False)
     assert X.shape == (1, 301, 3) and int(qids[0]) == 7 and int(lens[0]) == 301
     assert float(X[0, 0, 0]) == 0.5 and float(X[0, 300, 2]) == 0.25 and bool((y[0] == 2).all())
+
+
+def test_number_forms_parse_like_strtod(tmp_path):
+    """The parsers' fast decimal path (at most 15 significant digits, |exponent| <= 22: one exact IEEE operation) and its strtod
+    fallback return what Python's float() -- correctly rounded, like strtod -- returns, for every number form a file may hold."""
+    toks = ["0", "-0", "+3.5", ".5", "5.", "0.1", "0.30000000000000004", "1e-5", "1E5", "1e22", "1e23", "1e-22", "1e-23",
+            "123456789012345", "1234567890123456", "123456789012345678901234567890", "0.000000000000000000001234",
+            "4.9e-324", "1.7976931348623157e308", "2.2250738585072014e-308", "9007199254740993", "0.1e1", "00012.5000",
+            "3.4028235e38", "1.17549435e-38", "7.006492321624085e-46", "1e400", "-1e-400", "16777217", "0.3333333333333333",
+            "8.5e-1", "12345.678901234567", "1e+3", "2e-0", "inf", "-inf", "nan"]
+    F = len(toks)
+    line = "3 qid:1 " + " ".join(f"{i + 1}:{t}" for i, t in enumerate(toks))
+    path = os.path.join(str(tmp_path), "numbers.txt")
+    with open(path, "w") as f:
+        f.write(line + "\n" + "1.5e0 qid:1 1:1\n")
+    X, y, qids, lens = D.load_slates(path, n_features=F, index_base=1, pin=False)
+    with np.errstate(over="ignore"):
+        want = np.asarray([float(t) for t in toks], dtype=np.float64).astype(np.float32)
+    got = X[0, 0].numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), [(t, g, w) for t, g, w in zip(toks, got, want) if not (g == w or (g != g and w != w))]
+    assert float(y[0, 0]) == 3.0 and float(y[0, 1]) == 1.5
+    bpath = os.path.join(str(tmp_path), "baseline.numbers.txt")
+    with open(bpath, "w") as f:
+        f.write("1, 0.25,-1e-3,7\n1,1e22, .5,-0\n")
+    S = D.load_baselines(bpath, pin=False)
+    S = S[0] if isinstance(S, (tuple, list)) else S
+    assert np.array_equal(S[0, :2].numpy(), np.asarray([[0.25, -1e-3, 7.0], [1e22, 0.5, -0.0]], dtype=np.float32))
