@@ -155,10 +155,15 @@ static inline long long fast_strtoll(const char* s, char** endp) {
     return neg ? -(long long)v : (long long)v;
 }
 
-// non-empty lines of the file (comment-only and blank lines are skipped, as sklearn's parser does)
-static void split_lines(const MappedFile& f, std::vector<Line>& lines) {
-    size_t pos = 0;
-    while (pos < f.size) {
+// non-empty lines of the byte range [from, to) of the file: a line belongs to the range its first byte lies in
+// (comment-only and blank lines are skipped, as sklearn's parser does)
+static void split_range(const MappedFile& f, size_t from, size_t to, std::vector<Line>& lines) {
+    size_t pos = from;
+    if (from > 0) {                                        // the line that straddles `from` belongs to the range before
+        const char* nl = static_cast<const char*>(memchr(f.data + from - 1, '\n', f.size - (from - 1)));
+        pos = nl ? (size_t)(nl - f.data) + 1 : f.size;
+    }
+    while (pos < to && pos < f.size) {
         const char* nl = static_cast<const char*>(memchr(f.data + pos, '\n', f.size - pos));
         const size_t eol = nl ? (size_t)(nl - f.data) : f.size;
         size_t b = pos, e = eol;
@@ -169,6 +174,22 @@ static void split_lines(const MappedFile& f, std::vector<Line>& lines) {
         if (e > b) lines.push_back(Line{b, e});
         pos = eol + 1;
     }
+}
+static void split_lines(const MappedFile& f, std::vector<Line>& lines, int threads = 1) {
+    const int T = (threads > 1 && f.size > (1u << 20)) ? (threads > 64 ? 64 : threads) : 1;
+    if (T == 1) {
+        split_range(f, 0, f.size, lines);
+        return;
+    }
+    std::vector<std::vector<Line>> part(T);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t)
+        pool.emplace_back([&, t] { split_range(f, f.size * t / T, f.size * (t + 1) / T, part[t]); });
+    for (auto& th : pool) th.join();
+    size_t total = 0;
+    for (auto& v : part) total += v.size();
+    lines.reserve(total);
+    for (auto& v : part) lines.insert(lines.end(), v.begin(), v.end());
 }
 
 // "label qid:ID idx:val ..." -> the qid (or -1 when the line has none); *after_label receives the offset after the label
@@ -239,7 +260,7 @@ LTR_API int ltr_svmlight_scan(const char* path, int threads, long long* counts) 
     if (!path || !counts) return set_error(LTR_EINVAL, "ltr_svmlight_scan: null argument");
     SvmIndex ix;
     if (!ix.file.open_file(path)) return set_error(LTR_EINVAL, "ltr_svmlight_scan: cannot open / map the file");
-    split_lines(ix.file, ix.lines);
+    split_lines(ix.file, ix.lines, host_threads(threads, (size_t)1 << 30));
     const size_t L = ix.lines.size();
     ix.qid.resize(L);
     const int T = host_threads(threads, L);
@@ -294,7 +315,7 @@ LTR_API int ltr_svmlight_load(const char* path, long long first_query, long long
         return set_error(LTR_EINVAL, "ltr_svmlight_load: bad arguments");
     SvmIndex ix;
     if (!ix.file.open_file(path)) return set_error(LTR_EINVAL, "ltr_svmlight_load: cannot open / map the file");
-    split_lines(ix.file, ix.lines);
+    split_lines(ix.file, ix.lines, host_threads(threads, (size_t)1 << 30));
     const size_t L = ix.lines.size();
     ix.qid.resize(L);
     const char* d = ix.file.data;

@@ -140,3 +140,36 @@ def test_number_forms_parse_like_strtod(tmp_path):
     S = D.load_baselines(bpath, pin=False)
     S = S[0] if isinstance(S, (tuple, list)) else S
     assert np.array_equal(S[0, :2].numpy(), np.asarray([[0.25, -1e-3, 7.0], [1e22, 0.5, -0.0]], dtype=np.float32))
+
+
+@pytest.mark.parametrize("trailing_newline", [True, False])
+def test_parallel_line_split_equals_the_serial_one(tmp_path, trailing_newline):
+    """Files above 1 MB are split into lines by several threads (a line belongs to the byte range its first byte lies in):
+    the same slates as with one thread for 2..13 threads, on lines of very different lengths with comments, blank lines and
+    CR LF endings in between."""
+    rng = np.random.default_rng(11 + trailing_newline)
+    rows = []
+    for q in range(260):
+        for _ in range(int(rng.integers(1, 30))):
+            k = int(rng.integers(1, 136))
+            idx = np.sort(rng.choice(136, size=k, replace=False)) + 1
+            feats = " ".join(f"{i}:{rng.random():.6f}" for i in idx)
+            rows.append(f"{int(rng.integers(0, 5))} qid:{q} {feats}" + (" # doc" if rng.random() < 0.1 else "") + ("\r" if rng.random() < 0.05 else ""))
+        if rng.random() < 0.2:
+            rows.append("# only a comment " + "x" * int(rng.integers(0, 3000)))
+        if rng.random() < 0.2:
+            rows.append("")
+    text = "\n".join(rows) + ("\n" if trailing_newline else "")
+    assert len(text) > (1 << 20)
+    path = os.path.join(str(tmp_path), "big.txt")
+    with open(path, "w", newline="") as f:
+        f.write(text)
+    one = D.load_slates(path, pin=False, threads=1)
+    info1 = D.scan_svmlight(path, threads=1)
+    for th in (2, 3, 8, 13):
+        assert D.scan_svmlight(path, threads=th) == info1
+        many = D.load_slates(path, pin=False, threads=th)
+        for a, b in zip(one, many):
+            assert torch.equal(a, b), th
+    feats, labels = _reference_procedure(path)
+    assert len(feats) == one[0].shape[0] and [len(x) for x in feats] == one[3].tolist()
